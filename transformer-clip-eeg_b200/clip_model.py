@@ -1,0 +1,506 @@
+"""Drop-in mirror of the reference ``clip_model.py`` for the EEG-CLIP hot path, on B200 kernels.
+
+Same class names, constructor / forward signatures, return arity and ``state_dict`` keys as
+/root/reference/clip_model.py, so ``import clip_model`` with this directory on
+``sys.path`` replaces the reference module for the path in scope:
+
+    MultiHeadAttention, ResidualAdd, FeedForwardBlock, TransformerEncoderBlock, TransformerEncoder  (:19-99)
+    BasicBlock (:234-249), EEGConformer (:327-398), EEGConformerInterleaved (:400-474)
+    SpeechSmallConv (:204-232), EEGConvLSTM (:251-325)
+    CLIP (:657-693), memoryBank (:697-745), CLIPSimNoLatentProj (:868-944)
+
+The nested containers (nn.Sequential / nn.Linear / nn.LayerNorm / nn.Conv1d) only *hold* the
+parameters under the reference's key names; every forward below goes through the C ABI of
+libeegclip_b200.so (include/eegclip.h).  There is no eager/CPU fallback: CPU tensors raise.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from .parallel import infonce_loss, ce_rows_loss
+
+__all__ = [
+    "MultiHeadAttention", "ResidualAdd", "FeedForwardBlock", "TransformerEncoderBlock", "TransformerEncoder",
+    "BasicBlock", "EEGConformer", "EEGConformerInterleaved", "SpeechSmallConv", "EEGConvLSTM", "CLIP", "memoryBank",
+    "CLIPSimNoLatentProj",
+]
+
+
+def _bytes(n):
+    return torch.empty(max(int(n), 16), dtype=torch.uint8, device="cuda")
+
+
+def _flat_grads(params):
+    """One contiguous gradient buffer + per-parameter views (so the backward zero-fills with one memset)."""
+    sizes = [p.numel() for p in params]
+    offs, o = [], 0
+    for s in sizes:
+        offs.append(o)
+        o += (s + 3) // 4 * 4  # keep every view 16-byte aligned
+    flat = torch.empty(o, dtype=torch.float32, device=params[0].device)
+    views = [flat[a:a + s].view(p.shape) for a, s, p in zip(offs, sizes, params)]
+    return flat, views
+
+
+# ---------------------------------------------------------------------------------------------------
+# autograd glue (each Function == one pair of C-ABI calls)
+# ---------------------------------------------------------------------------------------------------
+class _TowerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, desc, *params):
+        x = L.f32c(x)
+        ps = [L.f32c(p) for p in params]
+        save_b, scr_b = ctypes.c_size_t(), ctypes.c_size_t()
+        L.call("eegclip_tower_workspace", ctypes.byref(desc), ctypes.byref(save_b), ctypes.byref(scr_b))
+        save, scratch = _bytes(save_b.value), _bytes(scr_b.value)
+        out = torch.empty(desc.B, desc.T, desc.latent, dtype=torch.float32, device=x.device)
+        tab = L.ptr_table(ps)
+        L.call("eegclip_tower_forward", ctypes.byref(desc), tab.data_ptr(), L.ptr(x), L.ptr(out), L.ptr(save), L.ptr(scratch),
+               L.stream())
+        ctx.desc, ctx.save, ctx.scr_bytes, ctx.x, ctx.ps = desc, save, scr_b.value, x, ps
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        desc, ps, x = ctx.desc, ctx.ps, ctx.x
+        dout = L.f32c(dout)
+        flat, views = _flat_grads(ps)
+        scratch = _bytes(ctx.scr_bytes)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        ptab, gtab = L.ptr_table(ps), L.ptr_table(views)
+        L.call("eegclip_tower_backward", ctypes.byref(desc), ptab.data_ptr(), gtab.data_ptr(), L.ptr(flat), flat.numel() * 4,
+               L.ptr(x), L.ptr(dout), L.ptr(dx), L.ptr(ctx.save), L.ptr(scratch), L.stream())
+        ctx.save = None
+        return (dx, None, *views)
+
+
+class _XfBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, desc, *params):
+        z = L.f32c(z)
+        ps = [L.f32c(p) for p in params]
+        save_b, scr_b = ctypes.c_size_t(), ctypes.c_size_t()
+        L.call("eegclip_xfblock_workspace", ctypes.byref(desc), ctypes.byref(save_b), ctypes.byref(scr_b))
+        save, scratch = _bytes(save_b.value), _bytes(scr_b.value)
+        out = torch.empty_like(z)
+        tab = L.ptr_table(ps)
+        L.call("eegclip_xfblock_forward", ctypes.byref(desc), tab.data_ptr(), L.ptr(z), L.ptr(out), L.ptr(save), L.ptr(scratch),
+               L.stream())
+        ctx.desc, ctx.save, ctx.scr_bytes, ctx.z, ctx.ps = desc, save, scr_b.value, z, ps
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        desc, ps, z = ctx.desc, ctx.ps, ctx.z
+        dout = L.f32c(dout)
+        flat, views = _flat_grads(ps)
+        scratch = _bytes(ctx.scr_bytes)
+        dz = torch.empty_like(z)
+        ptab, gtab = L.ptr_table(ps), L.ptr_table(views)
+        L.call("eegclip_xfblock_backward", ctypes.byref(desc), ptab.data_ptr(), gtab.data_ptr(), L.ptr(flat), flat.numel() * 4,
+               L.ptr(z), L.ptr(dout), L.ptr(dz), L.ptr(ctx.save), L.ptr(scratch), L.stream())
+        ctx.save = None
+        return (dz, None, *views)
+
+
+class _ConvBlockFn(torch.autograd.Function):
+    """x, skip: time-major (B,T,Cin); returns time-major (B,T,Cout)."""
+
+    @staticmethod
+    def forward(ctx, x, skip, desc, w, b, gamma, beta):
+        x, w, b, gamma, beta = (L.f32c(t) for t in (x, w, b, gamma, beta))
+        skip = L.f32c(skip) if skip is not None else None
+        save_b, scr_b = ctypes.c_size_t(), ctypes.c_size_t()
+        L.call("eegclip_convblock_workspace", ctypes.byref(desc), ctypes.byref(save_b), ctypes.byref(scr_b))
+        save, scratch = _bytes(save_b.value), _bytes(scr_b.value)
+        out = torch.empty(desc.B, desc.T, desc.Cout, dtype=torch.float32, device=x.device)
+        L.call("eegclip_convblock_forward", ctypes.byref(desc), L.ptr(x), L.ptr(skip), L.ptr(w), L.ptr(b), L.ptr(gamma),
+               L.ptr(beta), L.ptr(out), L.ptr(save), L.ptr(scratch), L.stream())
+        ctx.desc, ctx.save, ctx.scr_bytes, ctx.t = desc, save, scr_b.value, (x, skip, w, gamma, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        desc = ctx.desc
+        x, skip, w, gamma, beta = ctx.t
+        dout = L.f32c(dout)
+        scratch = _bytes(ctx.scr_bytes)
+        dx = torch.empty_like(x)
+        dw, dg, dbe = torch.empty_like(w), torch.empty_like(gamma), torch.empty_like(beta)
+        db = torch.empty(desc.Cout, dtype=torch.float32, device=x.device)
+        L.call("eegclip_convblock_backward", ctypes.byref(desc), L.ptr(x), L.ptr(skip), L.ptr(w), L.ptr(gamma), L.ptr(beta),
+               L.ptr(dout), L.ptr(dx), L.ptr(dw), L.ptr(db), L.ptr(dg), L.ptr(dbe), L.ptr(ctx.save), L.ptr(scratch), L.stream())
+        ctx.save = None
+        return dx, (dx if skip is not None else None), None, dw, db, dg, dbe
+
+
+class _LinearFn(torch.autograd.Function):
+    """Per-token linear (nn.Linear / 1x1 Conv1d) on (..., K) -> (..., N)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w2 = L.f32c(x), L.f32c(w).reshape(w.shape[0], -1)
+        b = L.f32c(b) if b is not None else None
+        M, K, N = x.numel() // x.shape[-1], x.shape[-1], w2.shape[0]
+        out = torch.empty(*x.shape[:-1], N, dtype=torch.float32, device=x.device)
+        L.call("eegclip_linear_forward", L.ptr(x), L.ptr(w2), L.ptr(b), L.ptr(out), M, N, K, L.default_math(), L.stream())
+        ctx.t, ctx.wshape, ctx.has_b = (x, w2), w.shape, b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w2 = ctx.t
+        dout = L.f32c(dout)
+        M, K, N = x.numel() // x.shape[-1], x.shape[-1], w2.shape[0]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w2)
+        db = torch.empty(N, dtype=torch.float32, device=x.device) if ctx.has_b else None
+        L.call("eegclip_linear_backward", L.ptr(x), L.ptr(w2), L.ptr(dout), L.ptr(dx), L.ptr(dw), L.ptr(db), M, N, K,
+               L.default_math(), L.stream())
+        return dx, dw.view(ctx.wshape), db
+
+
+def _require_cuda(x, who):
+    if not x.is_cuda:
+        raise L.EegclipError(f"{who}: input is on {x.device}; this implementation runs on CUDA (sm_100a) only")
+
+
+# ---------------------------------------------------------------------------------------------------
+# Transformer blocks (parameter containers keep the reference key names)
+# ---------------------------------------------------------------------------------------------------
+class MultiHeadAttention(nn.Module):
+    """clip_model.py:19-45.  ``mask`` is dead in the reference (``energy.mask_fill`` does not exist, :37)."""
+
+    def __init__(self, emb_size, num_heads, dropout):
+        super().__init__()
+        self.emb_size, self.num_heads = emb_size, num_heads
+        self.keys = nn.Linear(emb_size, emb_size)
+        self.queries = nn.Linear(emb_size, emb_size)
+        self.values = nn.Linear(emb_size, emb_size)
+        self.att_drop = nn.Dropout(dropout)
+        self.projection = nn.Linear(emb_size, emb_size)
+
+    def forward(self, x, mask=None):
+        if mask is not None:  # same failure as the reference: Tensor has no attribute mask_fill
+            raise AttributeError("'Tensor' object has no attribute 'mask_fill'")
+        raise L.EegclipError("MultiHeadAttention is fused into TransformerEncoderBlock on this path; call the block")
+
+
+class ResidualAdd(nn.Module):
+    """clip_model.py:48-57 (container only; the residual add is fused into the block kernels)."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+    def forward(self, x, **kwargs):
+        raise L.EegclipError("ResidualAdd is fused into TransformerEncoderBlock on this path; call the block")
+
+
+class FeedForwardBlock(nn.Sequential):
+    """clip_model.py:60-67."""
+
+    def __init__(self, emb_size, expansion, drop_p):
+        super().__init__(nn.Linear(emb_size, expansion * emb_size), nn.GELU(), nn.Dropout(drop_p),
+                         nn.Linear(expansion * emb_size, emb_size))
+
+
+_XF_ORDER = ("0.fn.0.weight", "0.fn.0.bias", "0.fn.1.queries.weight", "0.fn.1.queries.bias", "0.fn.1.keys.weight",
+             "0.fn.1.keys.bias", "0.fn.1.values.weight", "0.fn.1.values.bias", "0.fn.1.projection.weight",
+             "0.fn.1.projection.bias", "1.fn.0.weight", "1.fn.0.bias", "1.fn.1.0.weight", "1.fn.1.0.bias",
+             "1.fn.1.3.weight", "1.fn.1.3.bias")
+
+
+class TransformerEncoderBlock(nn.Sequential):
+    """clip_model.py:75-94: x + Drop(MHA(LN(x))); x + Drop(FFN(LN(x))) as one fused call."""
+
+    def __init__(self, emb_size, num_heads=8, drop_p=0.5, forward_expansion=4, forward_drop_p=0.5):
+        super().__init__(
+            ResidualAdd(nn.Sequential(nn.LayerNorm(emb_size), MultiHeadAttention(emb_size, num_heads, drop_p), nn.Dropout(drop_p))),
+            ResidualAdd(nn.Sequential(nn.LayerNorm(emb_size),
+                                      FeedForwardBlock(emb_size, expansion=forward_expansion, drop_p=forward_drop_p),
+                                      nn.Dropout(drop_p))))
+        if emb_size != 64 or num_heads != 8 or forward_expansion != 4:
+            raise L.EegclipError("the B200 kernels are specialised for emb_size=64, 8 heads, expansion 4 (the reference's only use)")
+        self.drop_p, self.forward_drop_p = drop_p, forward_drop_p
+
+    def abi_params(self):
+        named = dict(self.named_parameters())
+        return [named[k] for k in _XF_ORDER]
+
+    def forward(self, x, layer=0):
+        _require_cuda(x, "TransformerEncoderBlock")
+        B, T, _ = x.shape
+        d = L.XfBlockDesc(B=B, T=T, layer=layer, train=int(self.training), math=L.default_math(), p_attn=self.drop_p,
+                          p_proj=self.drop_p, p_ffn_hid=self.forward_drop_p, p_ffn_out=self.drop_p,
+                          seed=L.new_seed() if self.training else 0)
+        return _XfBlockFn.apply(x, d, *self.abi_params())
+
+
+class TransformerEncoder(nn.Sequential):
+    """clip_model.py:97-99."""
+
+    def __init__(self, depth, emb_size):
+        super().__init__(*[TransformerEncoderBlock(emb_size) for _ in range(depth)])
+
+    def forward(self, x):
+        for i, blk in enumerate(self):
+            x = blk(x, layer=i)
+        return x
+
+
+# ---------------------------------------------------------------------------------------------------
+# Conv front block
+# ---------------------------------------------------------------------------------------------------
+class BasicBlock(nn.Module):
+    """clip_model.py:234-249: Conv1d('same') -> Dropout -> LayerNorm([C,T]) -> GELU on (B,C,T) tensors."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=64, time_dimension=320, dropout_rate=0.2, stride=1,
+                 padding='same', dilation=1, activation=nn.LeakyReLU()):
+        super().__init__()
+        if stride != 1 or dilation != 1 or padding != 'same':
+            raise L.EegclipError("BasicBlock kernels cover stride=1, dilation=1, padding='same' (the reference's only use)")
+        self.conv = nn.Conv1d(in_channels, out_channels, kernel_size, stride, padding, dilation=dilation)
+        self.dropout = nn.Dropout(dropout_rate)
+        self.normalization = nn.LayerNorm([out_channels, time_dimension])
+        self.activation = nn.GELU()  # the ``activation`` argument is ignored by the reference too (:240-241)
+        self._act = 0
+
+    def forward_time_major(self, x, skip=None, layer=0):
+        """x, skip: (B,T,Cin) -> (B,T,Cout)."""
+        _require_cuda(x, "BasicBlock")
+        B, T, cin = x.shape
+        w = self.conv.weight
+        d = L.ConvBlockDesc(B=B, T=T, Cin=cin, Cout=w.shape[0], taps=w.shape[2], act=self._act, train=int(self.training),
+                            math=L.default_math(), p_drop=self.dropout.p, layer=layer,
+                            seed=L.new_seed() if self.training else 0)
+        return _ConvBlockFn.apply(x, skip, d, w, self.conv.bias, self.normalization.weight, self.normalization.bias)
+
+    def forward(self, x):
+        # reference layout is channel-major (B,C,T); the kernels are time-major
+        return self.forward_time_major(x.transpose(1, 2)).transpose(1, 2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# EEG towers
+# ---------------------------------------------------------------------------------------------------
+class _TowerBase(nn.Module):
+    _kind = L.TOWER_INTERLEAVED
+
+    def _conv_blocks(self):
+        return [getattr(self, f"conv_{i}") for i in range(self._n_conv)]
+
+    def _xf_blocks(self):
+        raise NotImplementedError
+
+    def abi_params(self):
+        ps = [self.eeg_spatial_mapping.weight, self.eeg_spatial_mapping.bias]
+        for c in self._conv_blocks():
+            ps += [c.conv.weight, c.conv.bias, c.normalization.weight, c.normalization.bias]
+        for blk in self._xf_blocks():
+            ps += blk.abi_params()
+        return ps + [self.final_layer.weight, self.final_layer.bias]
+
+    def get_output_dim(self, input_window_size):
+        return input_window_size * self.output_dim
+
+    def forward(self, x):
+        _require_cuda(x, type(self).__name__)
+        B, T, cin = x.shape
+        convs, xfs = self._conv_blocks(), self._xf_blocks()
+        if cin != 64:
+            raise L.EegclipError("EEG towers take 64-channel windows (B,T,64)")
+        taps = convs[0].conv.weight.shape[2] if convs else 1
+        blk0 = xfs[0] if xfs else None
+        d = L.TowerDesc(kind=self._kind, B=B, T=T, n_conv=len(convs), depth=len(xfs), taps=taps, latent=self.output_dim,
+                        train=int(self.training), math=L.default_math(),
+                        p_conv=convs[0].dropout.p if convs else 0.0,
+                        p_attn=blk0.drop_p if blk0 else 0.0, p_proj=blk0.drop_p if blk0 else 0.0,
+                        p_ffn_hid=blk0.forward_drop_p if blk0 else 0.0, p_ffn_out=blk0.drop_p if blk0 else 0.0,
+                        seed=L.new_seed() if self.training else 0)
+        return _TowerFn.apply(x, d, *self.abi_params())
+
+
+class EEGConformer(_TowerBase):
+    """clip_model.py:327-398: conv stack (input skip except last block) then TransformerEncoder(depth)."""
+    _kind = L.TOWER_SEQUENTIAL
+
+    def __init__(self, output_dim=8, conformer_input_dim=64, dropout_rate=0.2, eeg_dim=64, filters=(64,) * 2,
+                 kernels=(64,) * 2, dilation_rate=1, input_channels=64, time_dimension=64 * 5, depth=2,
+                 normalization_fn='layer_norm', activation_fn='leaky_relu'):
+        super().__init__()
+        self.spatial_filters, self.output_dim = input_channels, output_dim
+        self.eeg_spatial_mapping = nn.Conv1d(eeg_dim, filters[0], kernel_size=1)
+        self.n_blocks = self._n_conv = len(filters)
+        for i, (f, k) in enumerate(zip(filters, kernels)):
+            setattr(self, f"conv_{i}", BasicBlock(f, f, kernel_size=k, dilation=dilation_rate, time_dimension=time_dimension,
+                                                  dropout_rate=dropout_rate))
+        self.transformerEncoder = TransformerEncoder(depth, conformer_input_dim)
+        self.final_layer = nn.Linear(conformer_input_dim, output_dim)
+
+    def _xf_blocks(self):
+        return list(self.transformerEncoder)
+
+
+class EEGConformerInterleaved(_TowerBase):
+    """clip_model.py:400-474: depth x [BasicBlock(x + eeg_x) -> 1-layer TransformerEncoder(+ eeg_x unless last)]."""
+    _kind = L.TOWER_INTERLEAVED
+
+    def __init__(self, output_dim=8, conformer_input_dim=64, dropout_rate=0.2, eeg_dim=64, filters=(64,) * 1,
+                 kernels=(64,) * 1, dilation_rate=1, input_channels=64, time_dimension=64 * 5, depth=4,
+                 normalization_fn='layer_norm', activation_fn='leaky_relu'):
+        super().__init__()
+        self.spatial_filters, self.output_dim = input_channels, output_dim
+        self.eeg_spatial_mapping = nn.Conv1d(eeg_dim, filters[0], kernel_size=1)
+        self.n_blocks = self._n_conv = depth
+        for i in range(depth):
+            setattr(self, f"conv_{i}", BasicBlock(filters[0], filters[0], kernel_size=kernels[0], dilation=dilation_rate,
+                                                  time_dimension=time_dimension, dropout_rate=dropout_rate))
+            setattr(self, f"conformer_{i}", TransformerEncoder(1, conformer_input_dim))
+        self.final_layer = nn.Linear(conformer_input_dim, output_dim)
+
+    def _xf_blocks(self):
+        return [getattr(self, f"conformer_{i}")[0] for i in range(self._n_conv)]
+
+
+# ---------------------------------------------------------------------------------------------------
+# Speech towers (boundary: SURVEY §8(a14)).  The conv/LN blocks run on the kernels above; the two
+# bi-LSTMs of the default tower are cuDNN library calls in this round.
+# ---------------------------------------------------------------------------------------------------
+class SpeechSmallConv(nn.Module):
+    """clip_model.py:204-232: Conv1d(speech_dim->out, k, 'same') -> Dropout -> LayerNorm([out,T]) -> LeakyReLU."""
+
+    def __init__(self, output_dim=64, ks_temporal=20, dropout_rate=0.2, speech_dim=1024, time_dimension=64 * 5):
+        super().__init__()
+        self.speech_spatial_mapping = nn.Conv1d(speech_dim, output_dim, kernel_size=ks_temporal, padding='same')
+        self.dropout = nn.Dropout(dropout_rate)
+        self.layernorm = nn.LayerNorm([output_dim, time_dimension])
+        self.activation = nn.LeakyReLU()
+        self.output_dim = output_dim
+
+    def get_output_dim(self, input_window_size):
+        return int(input_window_size * self.output_dim)
+
+    def forward(self, x):
+        _require_cuda(x, "SpeechSmallConv")
+        B, T, cin = x.shape
+        w = self.speech_spatial_mapping.weight
+        d = L.ConvBlockDesc(B=B, T=T, Cin=cin, Cout=w.shape[0], taps=w.shape[2], act=1, train=int(self.training),
+                            math=L.default_math(), p_drop=self.dropout.p, layer=0, seed=L.new_seed() if self.training else 0)
+        return _ConvBlockFn.apply(x, None, d, w, self.speech_spatial_mapping.bias, self.layernorm.weight, self.layernorm.bias)
+
+
+class EEGConvLSTM(nn.Module):
+    """clip_model.py:251-325: 1x1 conv -> BasicBlocks (input skip except last) -> two bi-LSTMs."""
+
+    def __init__(self, units_lstm=128, output_dim=64, dropout_rate=0.2, eeg_dim=64, filters=(256, 256, 256, 128, 128),
+                 kernels=(64,) * 5, dilation_rate=1, input_channels=64, time_dimension=64 * 5,
+                 normalization_fn='layer_norm', activation_fn='leaky_relu'):
+        super().__init__()
+        self.speech_lstm1 = nn.LSTM(filters[-1], units_lstm, batch_first=True, bidirectional=True)
+        self.speech_lstm2 = nn.LSTM(units_lstm * 2, int(output_dim / 2), batch_first=True, bidirectional=True)
+        self.spatial_filters, self.output_dim = input_channels, output_dim
+        self.eeg_spatial_mapping = nn.Conv1d(eeg_dim, filters[0], kernel_size=1)
+        self.n_blocks = len(filters)
+        for i, (f, k) in enumerate(zip(filters, kernels)):
+            setattr(self, f"conv_{i}", BasicBlock(f, f, kernel_size=k, dilation=dilation_rate, time_dimension=time_dimension,
+                                                  dropout_rate=dropout_rate))
+
+    def get_output_dim(self, input_window_size):
+        return input_window_size * self.output_dim
+
+    def forward(self, x):
+        _require_cuda(x, "EEGConvLSTM")
+        x = _LinearFn.apply(x, self.eeg_spatial_mapping.weight, self.eeg_spatial_mapping.bias)  # (B,T,f0), time-major
+        eeg = x
+        for i in range(self.n_blocks):
+            blk = getattr(self, f"conv_{i}")
+            x = blk.forward_time_major(x, None if i == self.n_blocks - 1 else eeg, layer=i)
+        x, _ = self.speech_lstm1(x)
+        x, _ = self.speech_lstm2(x)
+        return x
+
+
+# ---------------------------------------------------------------------------------------------------
+# Loss wrappers
+# ---------------------------------------------------------------------------------------------------
+class CLIP(nn.Module):
+    """clip_model.py:657-693: symmetric InfoNCE with a learnable log-scale."""
+
+    def __init__(self, eegModel, speechModel, temperature=1.):
+        super().__init__()
+        self.eegModel, self.speechModel = eegModel, speechModel
+        self.temperature = nn.Parameter(torch.tensor(temperature))
+        self.shard_group = None  # set to a torch.distributed group for sharded InfoNCE
+
+    def forward(self, eeg, speech):
+        E = torch.flatten(self.eegModel(eeg), start_dim=1)
+        S = torch.flatten(self.speechModel(speech), start_dim=1)
+        return infonce_loss(E, S, self.temperature, group=self.shard_group)
+
+
+class memoryBank(nn.Module):
+    """clip_model.py:697-745: EMA bank indexed by segment id; updated in train *and* eval mode."""
+
+    def __init__(self, bank_size, device, dim, momentum=0.90):
+        super().__init__()
+        self.bank_size, self.dim, self.momentum = bank_size, dim, momentum
+        self.register_buffer("memory", torch.rand(bank_size + 1, dim).to(device))
+
+    def forward(self, idx, data):
+        _require_cuda(data, "memoryBank")
+        d = L.f32c(data)
+        idx = idx.view(-1).to(torch.int64).contiguous()
+        old = torch.empty_like(d)
+        L.call("eegclip_membank_update", L.ptr(self.memory), L.ptr(idx), L.ptr(d), L.ptr(old), d.shape[0], d.shape[1],
+               float(self.momentum), float(1 - self.momentum), L.stream())
+        return old
+
+
+class _ZeroGradLink(torch.autograd.Function):
+    """value passes through; ``anchors`` receive exact-zero gradients (the reference's lambda_average == 0 case:
+    temperature_eeg.grad is tensor(0.), not None, so AdamW still decays it)."""
+
+    @staticmethod
+    def forward(ctx, value, *anchors):
+        ctx.shapes = [a.shape for a in anchors]
+        ctx.dev = value.device
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, *[torch.zeros(s, device=ctx.dev) for s in ctx.shapes])
+
+
+class CLIPSimNoLatentProj(nn.Module):
+    """clip_model.py:868-944 (CLI default): CLIP loss + memory-bank cross-entropy, returns three 0-dim losses."""
+
+    def __init__(self, eegModel, speechModel, eegMemoryBank, temperature=1., window_length=192, lambda_clip=1,
+                 lambda_average=1):
+        super().__init__()
+        self.eegModel, self.speechModel, self.eegMemoryBank = eegModel, speechModel, eegMemoryBank
+        self.window_length, self.lambda_clip, self.lambda_average = window_length, lambda_clip, lambda_average
+        self.temperature = nn.Parameter(torch.tensor(temperature))
+        self.temperature_eeg = nn.Parameter(torch.tensor(temperature))
+        self.shard_group = None
+
+    def forward(self, eeg, speech, ids):
+        ef, sf = self.eegModel(eeg), self.speechModel(speech)
+        if sf.shape[1] > sf.shape[2]:
+            sf = sf.transpose(1, 2)
+        if ef.shape[1] > ef.shape[2]:
+            ef = ef.transpose(1, 2)
+        E_raw, S_raw = torch.flatten(ef, start_dim=1), torch.flatten(sf, start_dim=1)
+        loss_ce, En = infonce_loss(E_raw, S_raw, self.temperature, group=self.shard_group, return_normalized=True)
+        avg = self.eegMemoryBank(ids, En.detach())
+        if self.lambda_average == 0:
+            with torch.no_grad():
+                avg_val = ce_rows_loss(avg, En.detach(), self.temperature_eeg.detach())
+            avg_loss = _ZeroGradLink.apply(avg_val, self.temperature_eeg)
+        else:
+            avg_loss = ce_rows_loss(avg, En, self.temperature_eeg)
+        loss_total = self.lambda_clip * loss_ce + self.lambda_average * avg_loss
+        return loss_ce.mean(), avg_loss.mean(), loss_total.mean()

@@ -1,0 +1,125 @@
+// Shared device/host helpers for the EEG-CLIP B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define EEGCLIP_OK 0
+#define EEGCLIP_ERR_ARG -1
+#define EEGCLIP_ERR_CUDA -2
+#define EEGCLIP_ERR_UNSUPPORTED -3
+
+#define CUDA_TRY(expr)                                   \
+  do {                                                   \
+    cudaError_t _e = (expr);                             \
+    if (_e != cudaSuccess) return EEGCLIP_ERR_CUDA;      \
+  } while (0)
+
+#define LAUNCH_CHECK()                                   \
+  do {                                                   \
+    if (cudaPeekAtLastError() != cudaSuccess) return EEGCLIP_ERR_CUDA; \
+  } while (0)
+
+namespace eegclip {
+
+// dropout site ids; stream = layer * 16 + site  (oracle/philox_ref.py::stream_id)
+enum : int { SITE_CONV = 0, SITE_ATTN = 1, SITE_PROJ = 2, SITE_FFN_HID = 3, SITE_FFN_OUT = 4 };
+
+struct Drop {
+  uint32_t seed_lo, seed_hi;
+  uint32_t stream;
+  uint32_t thresh;   // keep iff word >= thresh
+  float scale;       // 1/(1-p); p == 0 -> disabled (thresh 0, scale 1)
+  int enabled;
+};
+
+__host__ inline Drop make_drop(uint64_t seed, int layer, int site, float p, int train) {
+  Drop d;
+  d.seed_lo = (uint32_t)(seed & 0xffffffffull);
+  d.seed_hi = (uint32_t)(seed >> 32);
+  d.stream = (uint32_t)(layer * 16 + site);
+  d.enabled = (train && p > 0.f) ? 1 : 0;
+  double t = floor((double)p * 4294967296.0);
+  if (t > 4294967295.0) t = 4294967295.0;
+  d.thresh = d.enabled ? (uint32_t)t : 0u;
+  d.scale = d.enabled ? 1.0f / (1.0f - p) : 1.0f;
+  return d;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// The four random words covering element indices [4*block, 4*block+3].
+__device__ __forceinline__ uint4 drop_words(const Drop& d, uint64_t block) {
+  return philox4x32_10((uint32_t)(block & 0xffffffffull), (uint32_t)(block >> 32), d.stream, 0u, d.seed_lo, d.seed_hi);
+}
+
+// Multiplier (0 or 1/(1-p)) for a single element index.
+__device__ __forceinline__ float drop_mult(const Drop& d, uint64_t idx) {
+  if (!d.enabled) return 1.0f;
+  uint4 w = drop_words(d, idx >> 2);
+  uint32_t lane = (uint32_t)(idx & 3);
+  uint32_t word = lane == 0 ? w.x : lane == 1 ? w.y : lane == 2 ? w.z : w.w;
+  return word >= d.thresh ? d.scale : 0.0f;
+}
+
+// Multipliers for the 4 consecutive elements starting at idx (idx % 4 == 0).
+__device__ __forceinline__ float4 drop_mult4(const Drop& d, uint64_t idx) {
+  if (!d.enabled) return make_float4(1.f, 1.f, 1.f, 1.f);
+  uint4 w = drop_words(d, idx >> 2);
+  return make_float4(w.x >= d.thresh ? d.scale : 0.f, w.y >= d.thresh ? d.scale : 0.f,
+                     w.z >= d.thresh ? d.scale : 0.f, w.w >= d.thresh ? d.scale : 0.f);
+}
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+// activation ids for conv+LN blocks: 0 = GELU (BasicBlock), 1 = LeakyReLU(0.01) (VLAAI / SpeechSmallConv)
+__device__ __forceinline__ float act_f(float x, int act) { return act == 0 ? gelu_f(x) : (x > 0.f ? x : 0.01f * x); }
+__device__ __forceinline__ float act_grad_f(float x, int act) { return act == 0 ? gelu_grad_f(x) : (x > 0.f ? 1.f : 0.01f); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum of two values (blockDim.x multiple of 32, <= 1024). Result valid in all threads.
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* sh /* >= 33 entries */) {
+  a = warp_sum(a); b = warp_sum(b);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = make_float2(a, b);
+  __syncthreads();
+  if (w == 0) {
+    float2 v = l < nw ? sh[l] : make_float2(0.f, 0.f);
+    v.x = warp_sum(v.x); v.y = warp_sum(v.y);
+    if (l == 0) sh[32] = v;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace eegclip

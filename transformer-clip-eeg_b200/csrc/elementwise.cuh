@@ -1,0 +1,348 @@
+// HBM-bound kernels of the encoder: padding, LayerNorm([C,T])+activation, per-token LayerNorm,
+// GELU/dropout, column sums, L2 normalisation.  All activations are time-major (B,T,C) fp32.
+// Judged on achieved GB/s: every kernel reads/writes each element once, 128-bit where the
+// layout allows, warp-shuffle reductions, no smem staging (no reuse to exploit).
+#pragma once
+#include "common.cuh"
+
+namespace eegclip {
+
+// ---------------------------------------------------------------------------------------------
+// upad[b][PL + t][c] = x1[b][t][c] (+ x2[b][t][c]); rows [0,PL) and [PL+T, T+taps-1) are zero.
+// Conv1d 'same' (clip_model.py:237): PL = (k-1)/2 for the forward, k-1-PL for the data gradient.
+// ---------------------------------------------------------------------------------------------
+__global__ void pad_add_kernel(const float* __restrict__ x1, const float* __restrict__ x2, float* __restrict__ out,
+                               int T, int C, int PL, int TP, long total4) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  int c4 = C >> 2;
+  long row = i / c4;           // b*TP + tp
+  int cc = (int)(i - row * c4);
+  long b = row / TP;
+  int tp = (int)(row - b * TP);
+  int t = tp - PL;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t >= 0 && t < T) {
+    long src = ((b * T + t) * (long)C) / 4 + cc;
+    v = reinterpret_cast<const float4*>(x1)[src];
+    if (x2) {
+      float4 w = reinterpret_cast<const float4*>(x2)[src];
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+  }
+  reinterpret_cast<float4*>(out)[i] = v;
+}
+
+inline int pad_add(const float* x1, const float* x2, float* out, int B, int T, int C, int PL, int taps, cudaStream_t st) {
+  int TP = T + taps - 1;
+  long total4 = (long)B * TP * (C / 4);
+  pad_add_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x1, x2, out, T, C, PL, TP, total4);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+// out = a + b (b optional), float4
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long n4) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<const float4*>(a)[i];
+  if (b) { float4 w = reinterpret_cast<const float4*>(b)[i]; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+  reinterpret_cast<float4*>(out)[i] = v;
+}
+inline int add_f32(const float* a, const float* b, float* out, long n, cudaStream_t st) {
+  long n4 = n / 4;
+  add_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(a, b, out, n4);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+// out[i] = in[i] * dropmult(i)      (backward of a residual-branch dropout)
+__global__ void drop_mul_kernel(const float* __restrict__ in, float* __restrict__ out, long n4, Drop d) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<const float4*>(in)[i];
+  float4 m = drop_mult4(d, (uint64_t)i * 4);
+  v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+  reinterpret_cast<float4*>(out)[i] = v;
+}
+inline int drop_mul(const float* in, float* out, long n, const Drop& d, cudaStream_t st) {
+  long n4 = n / 4;
+  drop_mul_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(in, out, n4, d);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+// f = dropout(GELU(pre))   (recomputed in backward instead of being stored)
+__global__ void gelu_drop_kernel(const float* __restrict__ pre, float* __restrict__ out, long n4, Drop d) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<const float4*>(pre)[i];
+  float4 m = drop_mult4(d, (uint64_t)i * 4);
+  v.x = gelu_f(v.x) * m.x; v.y = gelu_f(v.y) * m.y; v.z = gelu_f(v.z) * m.z; v.w = gelu_f(v.w) * m.w;
+  reinterpret_cast<float4*>(out)[i] = v;
+}
+inline int gelu_drop(const float* pre, float* out, long n, const Drop& d, cudaStream_t st) {
+  long n4 = n / 4;
+  gelu_drop_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(pre, out, n4, d);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over the whole (C,T) sample with (C,T)-shaped affine + activation (+ skip).
+// clip_model.py:239,247-248 (BasicBlock), vlaai.py:31,62.  One CTA per sample; the sample (T*C*4 B
+// = 80 KB at T=320,C=64) is read twice (second read hits L1/L2).
+//   y     : (B,T,C) conv output after bias+dropout
+//   gamma : (C,T) reference layout (channel-major)
+//   out   : act(gamma*xhat+beta) + skip
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) ln_ct_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, const float* __restrict__ skip,
+                                                           float* __restrict__ out, float* __restrict__ stats, int T, int C,
+                                                           int act, float eps) {
+  __shared__ float2 sh[33];
+  const int b = blockIdx.x;
+  const long n = (long)T * C;
+  const float* yb = y + b * n;
+  float s = 0.f, ss = 0.f;
+  for (long i = threadIdx.x * 4L; i < n; i += blockDim.x * 4L) {
+    float4 v = *reinterpret_cast<const float4*>(yb + i);
+    s += v.x + v.y + v.z + v.w;
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  float2 r = block_sum2(s, ss, sh);
+  float mean = r.x / (float)n;
+  float var = fmaxf(r.y / (float)n - mean * mean, 0.f);
+  // second, numerically safer pass for the variance (values are L1/L2 resident)
+  float sq = 0.f;
+  for (long i = threadIdx.x * 4L; i < n; i += blockDim.x * 4L) {
+    float4 v = *reinterpret_cast<const float4*>(yb + i);
+    float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+    sq += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+  }
+  r = block_sum2(sq, 0.f, sh);
+  var = r.x / (float)n;
+  float rstd = rsqrtf(var + eps);
+  if (threadIdx.x == 0) { stats[2 * b] = mean; stats[2 * b + 1] = rstd; }
+  const float* sb = skip ? skip + b * n : nullptr;
+  float* ob = out + b * n;
+  for (long i = threadIdx.x * 4L; i < n; i += blockDim.x * 4L) {
+    int t = (int)(i / C), c = (int)(i - (long)t * C);
+    float4 v = *reinterpret_cast<const float4*>(yb + i);
+    float vv[4] = {v.x, v.y, v.z, v.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float g = __ldg(gamma + (long)(c + j) * T + t), be = __ldg(beta + (long)(c + j) * T + t);
+      o[j] = act_f((vv[j] - mean) * rstd * g + be, act);
+    }
+    if (sb) { float4 k = *reinterpret_cast<const float4*>(sb + i); o[0] += k.x; o[1] += k.y; o[2] += k.z; o[3] += k.w; }
+    *reinterpret_cast<float4*>(ob + i) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+inline int ln_ct_act_fwd(const float* y, const float* gamma, const float* beta, const float* skip, float* out, float* stats,
+                         int B, int T, int C, int act, cudaStream_t st) {
+  ln_ct_act_fwd_kernel<<<B, 512, 0, st>>>(y, gamma, beta, skip, out, stats, T, C, act, 1e-5f);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+// Backward of the block above.  dout: gradient w.r.t. out (skip gradient handled by the caller).
+// Writes dy (gradient w.r.t. the conv output *before* dropout, i.e. already multiplied by the conv
+// dropout mask) into a zero-padded buffer dypad[b][PL + t][c] (rows outside are left untouched: the
+// caller zeroes the buffer once), and accumulates dgamma/dbeta (C,T) with atomics over the batch.
+__global__ void __launch_bounds__(512) ln_ct_act_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y,
+                                                           const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ dypad,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int T, int C,
+                                                           int PL, int TP, int act, Drop drop) {
+  __shared__ float2 sh[33];
+  const int b = blockIdx.x;
+  const long n = (long)T * C;
+  const float* yb = y + b * n;
+  const float* db = dout + b * n;
+  const float mean = stats[2 * b], rstd = stats[2 * b + 1];
+  float s1 = 0.f, s2 = 0.f;
+  for (long i = threadIdx.x * 4L; i < n; i += blockDim.x * 4L) {
+    int t = (int)(i / C), c = (int)(i - (long)t * C);
+    float4 v = *reinterpret_cast<const float4*>(yb + i);
+    float4 d = *reinterpret_cast<const float4*>(db + i);
+    float vv[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float g = __ldg(gamma + (long)(c + j) * T + t), be = __ldg(beta + (long)(c + j) * T + t);
+      float xh = (vv[j] - mean) * rstd;
+      float dl = dd[j] * act_grad_f(xh * g + be, act);
+      atomicAdd(dgamma + (long)(c + j) * T + t, dl * xh);
+      atomicAdd(dbeta + (long)(c + j) * T + t, dl);
+      float dxh = dl * g;
+      s1 += dxh; s2 += dxh * xh;
+    }
+  }
+  float2 r = block_sum2(s1, s2, sh);
+  const float m1 = r.x / (float)n, m2 = r.y / (float)n;
+  float* ob = dypad + ((long)b * TP + PL) * C;
+  for (long i = threadIdx.x * 4L; i < n; i += blockDim.x * 4L) {
+    int t = (int)(i / C), c = (int)(i - (long)t * C);
+    float4 v = *reinterpret_cast<const float4*>(yb + i);
+    float4 d = *reinterpret_cast<const float4*>(db + i);
+    float vv[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
+    float4 m = drop_mult4(drop, (uint64_t)b * n + i);
+    float mm[4] = {m.x, m.y, m.z, m.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float g = __ldg(gamma + (long)(c + j) * T + t), be = __ldg(beta + (long)(c + j) * T + t);
+      float xh = (vv[j] - mean) * rstd;
+      float dxh = dd[j] * act_grad_f(xh * g + be, act) * g;
+      o[j] = rstd * (dxh - m1 - xh * m2) * mm[j];
+    }
+    *reinterpret_cast<float4*>(ob + i) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+inline int ln_ct_act_bwd(const float* dout, const float* y, const float* stats, const float* gamma, const float* beta,
+                         float* dypad, float* dgamma, float* dbeta, int B, int T, int C, int PL, int taps, int act,
+                         const Drop& drop, cudaStream_t st) {
+  ln_ct_act_bwd_kernel<<<B, 512, 0, st>>>(dout, y, stats, gamma, beta, dypad, dgamma, dbeta, T, C, PL, T + taps - 1, act, drop);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-token LayerNorm over 64 features (clip_model.py:84,89).  Half-warp per token (float4/lane).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln64_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                      const float* __restrict__ be, float* __restrict__ out, long rows) {
+  long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  int l = threadIdx.x & 15;
+  if (row >= rows) return;
+  float4 v = reinterpret_cast<const float4*>(x + row * 64)[l];
+  float s = v.x + v.y + v.z + v.w;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
+  float mean = s * (1.f / 64.f);
+  float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+  float q = a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o, 16);
+  float rstd = rsqrtf(q * (1.f / 64.f) + 1e-5f);
+  float4 gg = reinterpret_cast<const float4*>(g)[l], bb = reinterpret_cast<const float4*>(be)[l];
+  reinterpret_cast<float4*>(out + row * 64)[l] =
+      make_float4(a0 * rstd * gg.x + bb.x, a1 * rstd * gg.y + bb.y, a2 * rstd * gg.z + bb.z, a3 * rstd * gg.w + bb.w);
+}
+inline int ln64_fwd(const float* x, const float* g, const float* b, float* out, long rows, cudaStream_t st) {
+  long threads = rows * 16;
+  ln64_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, g, b, out, rows);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+// dx_out = resid + LNbwd(dh ; x, gamma) ; dgamma += sum dh*xhat ; dbeta += sum dh.
+// Each CTA handles a contiguous chunk of rows, keeps its dgamma/dbeta partials in registers/smem
+// and issues 128 atomics at the end.
+__global__ void __launch_bounds__(256) ln64_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ x,
+                                                      const float* __restrict__ g, const float* __restrict__ resid,
+                                                      float* __restrict__ dx, float* __restrict__ dgamma,
+                                                      float* __restrict__ dbeta, long rows, int rows_per_cta) {
+  __shared__ float sg[16][64], sb[16][64];
+  const int l = threadIdx.x & 15, grp = threadIdx.x >> 4;  // 16 groups of 16 lanes
+  float4 gg = reinterpret_cast<const float4*>(g)[l];
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
+  long r0 = (long)blockIdx.x * rows_per_cta;
+  long r1 = min(rows, r0 + rows_per_cta);
+  for (long row = r0 + grp; row < r1; row += 16) {
+    float4 v = reinterpret_cast<const float4*>(x + row * 64)[l];
+    float4 d = reinterpret_cast<const float4*>(dh + row * 64)[l];
+    float s = v.x + v.y + v.z + v.w;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
+    float mean = s * (1.f / 64.f);
+    float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+    float q = a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o, 16);
+    float rstd = rsqrtf(q * (1.f / 64.f) + 1e-5f);
+    float x0 = a0 * rstd, x1 = a1 * rstd, x2 = a2 * rstd, x3 = a3 * rstd;
+    ag.x += d.x * x0; ag.y += d.y * x1; ag.z += d.z * x2; ag.w += d.w * x3;
+    ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+    float e0 = d.x * gg.x, e1 = d.y * gg.y, e2 = d.z * gg.z, e3 = d.w * gg.w;
+    float s1 = e0 + e1 + e2 + e3, s2 = e0 * x0 + e1 * x1 + e2 * x2 + e3 * x3;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o, 16); s2 += __shfl_xor_sync(0xffffffffu, s2, o, 16); }
+    s1 *= (1.f / 64.f); s2 *= (1.f / 64.f);
+    float4 o4 = make_float4(rstd * (e0 - s1 - x0 * s2), rstd * (e1 - s1 - x1 * s2), rstd * (e2 - s1 - x2 * s2), rstd * (e3 - s1 - x3 * s2));
+    if (resid) { float4 rr = reinterpret_cast<const float4*>(resid + row * 64)[l]; o4.x += rr.x; o4.y += rr.y; o4.z += rr.z; o4.w += rr.w; }
+    reinterpret_cast<float4*>(dx + row * 64)[l] = o4;
+  }
+  reinterpret_cast<float4*>(&sg[grp][0])[l] = ag;
+  reinterpret_cast<float4*>(&sb[grp][0])[l] = ab;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    int c = threadIdx.x & 63;
+    float acc = 0.f;
+    if (threadIdx.x < 64) { for (int k = 0; k < 16; ++k) acc += sg[k][c]; atomicAdd(dgamma + c, acc); }
+    else                  { for (int k = 0; k < 16; ++k) acc += sb[k][c]; atomicAdd(dbeta + c, acc); }
+  }
+}
+inline int ln64_bwd(const float* dh, const float* x, const float* g, const float* resid, float* dx, float* dgamma, float* dbeta,
+                    long rows, cudaStream_t st) {
+  int rows_per_cta = 256;
+  ln64_bwd_kernel<<<(unsigned)((rows + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(dh, x, g, resid, dx, dgamma, dbeta, rows, rows_per_cta);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+// out[n] += sum_m X[m][n]   (bias gradients). N <= 256, N % 4 == 0.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, float* __restrict__ out, long M, int N,
+                                                    int ld, int rows_per_cta) {
+  __shared__ float sh[256 * 4];
+  const int n4 = N >> 2;                  // float4 columns
+  const int lanes = n4;                   // threads across columns
+  const int rgroups = 256 / lanes;        // row groups per CTA
+  const int cl = threadIdx.x % lanes, rg = threadIdx.x / lanes;
+  long r0 = (long)blockIdx.x * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rg < rgroups)
+    for (long r = r0 + rg; r < r1; r += rgroups) {
+      float4 v = reinterpret_cast<const float4*>(X + r * ld)[cl];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  reinterpret_cast<float4*>(sh)[threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.x < N) {
+    int c4 = threadIdx.x >> 2, j = threadIdx.x & 3;
+    float acc = 0.f;
+    for (int g = 0; g < rgroups; ++g) acc += sh[(g * lanes + c4) * 4 + j];
+    atomicAdd(out + threadIdx.x, acc);
+  }
+}
+inline int colsum(const float* X, float* out, long M, int N, int ld, cudaStream_t st) {
+  if (N > 256 || (N & 3) || (256 % (N >> 2)) || (ld & 3)) return EEGCLIP_ERR_UNSUPPORTED;
+  int rows_per_cta = 512;
+  colsum_kernel<<<(unsigned)((M + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(X, out, M, N, ld, rows_per_cta);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+// Column sum over a zero-padded (B,TP,C) buffer (conv bias gradient): pads are zero so they can be summed too.
+
+// dW[co][ci][k] = tmp[co][k][ci]   (weight-gradient GEMM output -> reference Conv1d layout)
+__global__ void wgrad_unpack_kernel(const float* __restrict__ tmp, float* __restrict__ dW, int Cout, int Cin, int K, long total) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int k = (int)(i % K);
+  long r = i / K;
+  int ci = (int)(r % Cin);
+  int co = (int)(r / Cin);
+  dW[i] = tmp[((long)co * K + k) * Cin + ci];
+}
+inline int wgrad_unpack(const float* tmp, float* dW, int Cout, int Cin, int K, cudaStream_t st) {
+  long total = (long)Cout * Cin * K;
+  wgrad_unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tmp, dW, Cout, Cin, K, total);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+}  // namespace eegclip

@@ -1,0 +1,330 @@
+// Contrastive head: L2 normalise, symmetric InfoNCE (local or sharded), memory bank, AdamW, match-mismatch scoring.
+// Replaces clip_model.py:675-693 / 909-944 (loss), :731-745 (memoryBank), train_clip_final.py:409-413,492 (AdamW),
+// train_clip_helper_functions.py:153-163,176-187 (scoring).
+#include "../../include/eegclip.h"
+#include "common.cuh"
+#include "gemm_f32.cuh"
+
+using namespace eegclip;
+
+#define TRY(x) do { int _r = (x); if (_r != EEGCLIP_OK) return _r; } while (0)
+
+namespace {
+
+// ---- L2 normalise rows: xn = x / max(||x||, 1e-12)  (F.normalize, clip_model.py:675-676) -----------
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ xn,
+                                                        float* __restrict__ inv_norm, int D) {
+  __shared__ float2 sh[33];
+  const long row = blockIdx.x;
+  const float* xr = x + row * D;
+  float s = 0.f;
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(xr + i);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  float2 r = block_sum2(s, 0.f, sh);
+  float inv = 1.f / fmaxf(sqrtf(r.x), 1e-12f);
+  if (threadIdx.x == 0 && inv_norm) inv_norm[row] = inv;
+  float* o = xn + row * D;
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(xr + i);
+    *reinterpret_cast<float4*>(o + i) = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+  }
+}
+
+// dx = inv * (dxn - xn * <xn, dxn>)
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ xn, const float* __restrict__ inv_norm,
+                                                        const float* __restrict__ dxn, float* __restrict__ dx, int D) {
+  __shared__ float2 sh[33];
+  const long row = blockIdx.x;
+  const float* a = xn + row * D;
+  const float* g = dxn + row * D;
+  float s = 0.f;
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(a + i), w = *reinterpret_cast<const float4*>(g + i);
+    s += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+  }
+  float2 r = block_sum2(s, 0.f, sh);
+  const float dot = r.x, inv = inv_norm[row];
+  float* o = dx + row * D;
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(a + i), w = *reinterpret_cast<const float4*>(g + i);
+    *reinterpret_cast<float4*>(o + i) =
+        make_float4(inv * (w.x - v.x * dot), inv * (w.y - v.y * dot), inv * (w.z - v.z * dot), inv * (w.w - v.w * dot));
+  }
+}
+
+// combine per-tile (max,sumexp) partials into a log-sum-exp per row
+__global__ void lse_combine_kernel(const float2* __restrict__ part, int ntiles, float* __restrict__ lse, int rows) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float m = -INFINITY;
+  for (int t = 0; t < ntiles; ++t) m = fmaxf(m, part[(long)r * ntiles + t].x);
+  float s = 0.f;
+  for (int t = 0; t < ntiles; ++t) { float2 p = part[(long)r * ntiles + t]; s += p.y * __expf(p.x - m); }
+  lse[r] = m + __logf(s);
+}
+
+// diag[i] = exp(tau) * <S[row0+i], E[row0+i]>   (one warp per row)
+__global__ void diag_kernel(const float* __restrict__ S, const float* __restrict__ E, const float* __restrict__ tau,
+                            float* __restrict__ diag, int b, int row0, int D) {
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+  if (w >= b) return;
+  const float* s = S + (long)(row0 + w) * D;
+  const float* e = E + (long)(row0 + w) * D;
+  float a = 0.f;
+  for (int i = l * 4; i < D; i += 128) {
+    float4 x = *reinterpret_cast<const float4*>(s + i), y = *reinterpret_cast<const float4*>(e + i);
+    a += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+  }
+  a = warp_sum(a);
+  if (l == 0) diag[w] = a * __expf(*tau);
+}
+
+__global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ lr, const float* __restrict__ lc,
+                                                  const float* __restrict__ dg, int Bg, int one_sided, float* __restrict__ loss) {
+  __shared__ float2 sh[33];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < Bg; i += blockDim.x) s += one_sided ? (lr[i] - dg[i]) : (lr[i] - dg[i]) + (lc[i] - dg[i]);
+  float2 r = block_sum2(s, 0.f, sh);
+  if (threadIdx.x == 0) *loss = r.x / ((one_sided ? 1.f : 2.f) * (float)Bg);
+}
+
+__global__ void __launch_bounds__(256) membank_kernel(float* __restrict__ mem, const int64_t* __restrict__ idx,
+                                                     const float* __restrict__ data, float* __restrict__ old_out, int D,
+                                                     float momentum, float om) {
+  const long r = blockIdx.x;
+  float* m = mem + idx[r] * (long)D;
+  const float* d = data + r * D;
+  float* o = old_out + r * D;
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    float4 a = *reinterpret_cast<const float4*>(m + i), x = *reinterpret_cast<const float4*>(d + i);
+    *reinterpret_cast<float4*>(o + i) = a;
+    // new = old*momentum + data*(1-momentum), same operation order as the reference (mul_ then add_)
+    *reinterpret_cast<float4*>(m + i) = make_float4(a.x * momentum + x.x * om, a.y * momentum + x.y * om,
+                                                    a.z * momentum + x.z * om, a.w * momentum + x.w * om);
+  }
+}
+
+// AdamW, one launch for all tensors: blockIdx.y = tensor, grid-stride over its elements
+__global__ void __launch_bounds__(256) adamw_kernel(const eegclip_adamw_entry* __restrict__ tab, float lr, float b1, float b2,
+                                                   float eps, float wd, float bc1, float bc2_sqrt) {
+  const eegclip_adamw_entry e = tab[blockIdx.y];
+  float* p = (float*)e.p; const float* g = (const float*)e.g; float* m = (float*)e.m; float* v = (float*)e.v;
+  const long n = e.numel;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const float step_size = lr / bc1;
+  const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  const long n4 = vec ? (n >> 2) : 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<const float4*>(g)[i];
+    float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    float pp[4] = {P.x, P.y, P.z, P.w}, gg[4] = {G.x, G.y, G.z, G.w}, mm[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pp[j] *= (1.f - lr * wd);
+      mm[j] = b1 * mm[j] + (1.f - b1) * gg[j];
+      vv[j] = b2 * vv[j] + (1.f - b2) * gg[j] * gg[j];
+      pp[j] -= step_size * mm[j] / (sqrtf(vv[j]) / bc2_sqrt + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  }
+  for (long i = n4 * 4 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float P = p[i] * (1.f - lr * wd), G = g[i];
+    float M = b1 * m[i] + (1.f - b1) * G, V = b2 * v[i] + (1.f - b2) * G * G;
+    p[i] = P - step_size * M / (sqrtf(V) / bc2_sqrt + eps);
+    m[i] = M; v[i] = V;
+  }
+}
+
+// scores[k][n] = <eeg[n], cand[n][k]> and choice[n] = argmax_k (first max wins, as torch.argmax)
+__global__ void __launch_bounds__(128) mm_rowdots_kernel(const float* __restrict__ eeg, const float* __restrict__ cand,
+                                                        float* __restrict__ scores, int64_t* __restrict__ choice, int N, int K,
+                                                        int D) {
+  __shared__ float2 sh[33];
+  const int n = blockIdx.x;
+  const float* e = eeg + (long)n * D;
+  float best = -INFINITY;
+  int bi = 0;
+  for (int k = 0; k < K; ++k) {
+    const float* c = cand + ((long)n * K + k) * D;
+    float a = 0.f;
+    for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+      float4 x = *reinterpret_cast<const float4*>(e + i), y = *reinterpret_cast<const float4*>(c + i);
+      a += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+    }
+    float2 r = block_sum2(a, 0.f, sh);
+    if (threadIdx.x == 0) scores[(long)k * N + n] = r.x;
+    if (r.x > best) { best = r.x; bi = k; }
+  }
+  if (threadIdx.x == 0 && choice) choice[n] = bi;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eegclip_abi_version(void) { return EEGCLIP_ABI_VERSION; }
+const char* eegclip_build_info(void) { return "eegclip_b200 sm_100a " __DATE__ " " __TIME__; }
+
+int eegclip_l2norm_forward(const float* x, float* xn, float* inv_norm, int32_t rows, int32_t D, void* stream) {
+  if (!x || !xn || rows <= 0 || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
+  l2norm_fwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, xn, inv_norm, D);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+int eegclip_l2norm_backward(const float* xn, const float* inv_norm, const float* dxn, float* dx, int32_t rows, int32_t D,
+                            void* stream) {
+  if (!xn || !inv_norm || !dxn || !dx || rows <= 0 || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
+  l2norm_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(xn, inv_norm, dxn, dx, D);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+int eegclip_infonce_workspace(int32_t b, int32_t Bg, int32_t D, size_t* scratch_bytes) {
+  if (b <= 0 || Bg < b || D <= 0 || !scratch_bytes) return EEGCLIP_ERR_ARG;
+  size_t part = align_up((size_t)b * ceil_div(Bg, GBN) * sizeof(float2), 256);
+  size_t g = align_up((size_t)b * Bg * sizeof(float), 256);
+  *scratch_bytes = 2 * part + 2 * g;
+  return EEGCLIP_OK;
+}
+
+int eegclip_infonce_lse(const float* S_all, const float* E_all, const float* tau, int32_t b, int32_t row0, int32_t Bg, int32_t D,
+                        float* lse_row, float* lse_col, float* diag, int32_t math, int32_t one_sided, void* scratch, void* stream) {
+  if (!S_all || !E_all || !tau || !lse_row || (!lse_col && !one_sided) || !diag || !scratch) return EEGCLIP_ERR_ARG;
+  if (b <= 0 || row0 < 0 || row0 + b > Bg || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
+  (void)math;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ntiles = ceil_div(Bg, GBN);
+  float2* part = (float2*)scratch;
+  // rows: this rank's speech rows against every EEG column
+  GemmArgs g;
+  g.A = S_all + (long)row0 * D; g.B = E_all; g.C = nullptr;
+  g.M = b; g.N = Bg; g.K = D; g.KT = D;
+  g.a_ms = D; g.a_ks = 1; g.b_ks = 1; g.b_ns = D;
+  g.epi.tau = tau; g.epi.lse_part = part;
+  TRY(gemm_f32<1>(g, st));
+  lse_combine_kernel<<<ceil_div(b, 128), 128, 0, st>>>(part, ntiles, lse_row, b);
+  LAUNCH_CHECK();
+  diag_kernel<<<ceil_div(b * 32, 256), 256, 0, st>>>(S_all, E_all, tau, diag, b, row0, D);
+  LAUNCH_CHECK();
+  if (one_sided) return EEGCLIP_OK;
+  // columns: this rank's EEG rows against every speech row (the transposed block)
+  float2* part2 = (float2*)((char*)scratch + align_up((size_t)b * ntiles * sizeof(float2), 256));
+  g.A = E_all + (long)row0 * D; g.B = S_all;
+  g.epi.lse_part = part2;
+  TRY(gemm_f32<1>(g, st));
+  lse_combine_kernel<<<ceil_div(b, 128), 128, 0, st>>>(part2, ntiles, lse_col, b);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+int eegclip_infonce_loss(const float* lse_row_all, const float* lse_col_all, const float* diag_all, int32_t Bg, int32_t one_sided,
+                         float* loss, void* stream) {
+  if (!lse_row_all || (!lse_col_all && !one_sided) || !diag_all || !loss || Bg <= 0) return EEGCLIP_ERR_ARG;
+  loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(lse_row_all, lse_col_all, diag_all, Bg, one_sided, loss);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+int eegclip_infonce_backward(const float* S_all, const float* E_all, const float* tau, const float* lse_row_all,
+                             const float* lse_col_all, int32_t b, int32_t row0, int32_t Bg, int32_t D, const float* dloss,
+                             float* dS_loc, float* dE_loc, float* dtau_partial, int32_t math, int32_t one_sided, void* scratch,
+                             void* stream) {
+  if (!S_all || !E_all || !tau || !lse_row_all || !dE_loc || !dtau_partial || !scratch || !dloss) return EEGCLIP_ERR_ARG;
+  if (!one_sided && (!lse_col_all || !dS_loc)) return EEGCLIP_ERR_ARG;
+  if (b <= 0 || row0 < 0 || row0 + b > Bg || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
+  (void)math;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ntiles = ceil_div(Bg, GBN);
+  char* base = (char*)scratch + 2 * align_up((size_t)b * ntiles * sizeof(float2), 256);
+  float* Gr = (float*)base;                                             // (b, Bg): rows local, all columns
+  float* Gc = (float*)(base + align_up((size_t)b * Bg * sizeof(float), 256));  // (Bg, b): all rows, local columns
+  CUDA_TRY(cudaMemsetAsync(dtau_partial, 0, sizeof(float), st));
+  // G rows block, scaled by dloss * exp(tau) on the fly?  exp(tau) is a device scalar -> applied in the second GEMM.
+  GemmArgs g;
+  g.A = S_all + (long)row0 * D; g.B = E_all; g.C = Gr;
+  g.M = b; g.N = Bg; g.K = D; g.KT = D;
+  g.a_ms = D; g.a_ks = 1; g.b_ks = 1; g.b_ns = D;
+  g.c_ms = Bg; g.c_ns = 1;
+  g.epi.tau = tau; g.epi.lse_m = lse_row_all; g.epi.lse_n = lse_col_all; g.epi.m_off = row0; g.epi.n_off = 0;
+  g.epi.inv_2b = 0.5f / (float)Bg; g.epi.alpha_dev = dloss; g.epi.one_sided = one_sided; g.epi.dtau = dtau_partial;
+  TRY(gemm_f32<2>(g, st));
+  const float* Gcols = Gr;
+  long gc_ms = 1, gc_ks = Bg;   // A(m=j, k=i) = Gr[i][j] when the local block is the whole matrix
+  if (b != Bg) {
+    GemmArgs h;
+    h.A = S_all; h.B = E_all + (long)row0 * D; h.C = Gc;
+    h.M = Bg; h.N = b; h.K = D; h.KT = D;
+    h.a_ms = D; h.a_ks = 1; h.b_ks = 1; h.b_ns = D;
+    h.c_ms = b; h.c_ns = 1;
+    h.epi.tau = tau; h.epi.lse_m = lse_row_all; h.epi.lse_n = lse_col_all; h.epi.m_off = 0; h.epi.n_off = row0;
+    h.epi.inv_2b = 0.5f / (float)Bg; h.epi.alpha_dev = dloss; h.epi.one_sided = one_sided; h.epi.dtau = nullptr;
+    TRY(gemm_f32<2>(h, st));
+    Gcols = Gc; gc_ms = 1; gc_ks = b;
+  }
+  // dS_loc = exp(tau) * Gr . E_all      (b x D, K = Bg)
+  // dE_loc = exp(tau) * Gcols^T . S_all (b x D, K = Bg)
+  // exp(tau) is folded in by a tiny scale kernel-free trick: alpha is host-side, so read tau on device via MODE 0 epilogue
+  // multiplier: we pre-multiply through `scale_by_exp_tau` below.
+  GemmArgs s1;
+  s1.A = Gr; s1.B = E_all; s1.C = dS_loc;
+  s1.M = b; s1.N = D; s1.K = Bg; s1.KT = Bg;
+  s1.a_ms = Bg; s1.a_ks = 1; s1.b_ks = D; s1.b_ns = 1; s1.c_ms = D; s1.c_ns = 1;
+  s1.epi.tau = tau;   // MODE 0 multiplies by exp(tau) when tau != nullptr
+  if (dS_loc) TRY(gemm_f32<0>(s1, st));
+  GemmArgs s2;
+  s2.A = Gcols; s2.B = S_all; s2.C = dE_loc;
+  s2.M = b; s2.N = D; s2.K = Bg; s2.KT = Bg;
+  s2.a_ms = gc_ms; s2.a_ks = gc_ks; s2.b_ks = D; s2.b_ns = 1; s2.c_ms = D; s2.c_ns = 1;
+  s2.epi.tau = tau;
+  TRY(gemm_f32<0>(s2, st));
+  return EEGCLIP_OK;
+}
+
+int eegclip_membank_update(float* memory, const int64_t* idx, const float* data, float* old_out, int32_t rows, int32_t D,
+                           float momentum, float one_minus_momentum, void* stream) {
+  if (!memory || !idx || !data || !old_out || rows <= 0 || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
+  membank_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(memory, idx, data, old_out, D, momentum, one_minus_momentum);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+int eegclip_adamw_step(const eegclip_adamw_entry* table_dev, int32_t n_tensors, int64_t max_numel, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int64_t step, void* stream) {
+  if (!table_dev || n_tensors <= 0 || max_numel <= 0 || step <= 0) return EEGCLIP_ERR_ARG;
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  long per_cta = 256L * 4 * 4;
+  int gx = (int)((max_numel + per_cta - 1) / per_cta);
+  if (gx < 1) gx = 1;
+  if (gx > 128) gx = 128;
+  dim3 grid(gx, n_tensors);
+  adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table_dev, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2));
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+int eegclip_mm_rowdots(const float* eeg, const float* cand, float* scores, int64_t* choice, int32_t N, int32_t K, int32_t D,
+                       void* stream) {
+  if (!eeg || !cand || !scores || N <= 0 || K <= 0 || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
+  mm_rowdots_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(eeg, cand, scores, choice, N, K, D);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+int eegclip_mm_bank_logits(const float* eeg, const float* bank, float* logits, int32_t N, int32_t M, int32_t D, int32_t math,
+                           void* stream) {
+  if (!eeg || !bank || !logits || N <= 0 || M <= 0 || D <= 0) return EEGCLIP_ERR_ARG;
+  (void)math;
+  GemmArgs g;
+  g.A = eeg; g.B = bank; g.C = logits;
+  g.M = N; g.N = M; g.K = D; g.KT = D;
+  g.a_ms = D; g.a_ks = 1; g.b_ks = 1; g.b_ns = D; g.c_ms = M; g.c_ns = 1;
+  return gemm_f32<0>(g, (cudaStream_t)stream);
+}
+
+}  // extern "C"

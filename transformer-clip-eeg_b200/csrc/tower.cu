@@ -1,0 +1,545 @@
+// EEG tower forward / backward: host-side orchestration of the per-layer kernels behind one C-ABI call.
+// Replaces EEGConformerInterleaved.forward / EEGConformer.forward and their autograd
+// (/root/reference/clip_model.py:445-474, 373-398, 75-94, 30-45, 60-67, 234-249).
+//
+// One call enqueues the whole tower on the caller's stream: no Python between kernels, graph-capturable.
+// Layout: every activation is time-major (B,T,64) fp32, so the reference's permutes (clip_model.py:446,458,461)
+// vanish; LayerNorm([C,T]) affines are read transposed from their (C,T) checkpoint layout.
+#include "../../include/eegclip.h"
+#include "common.cuh"
+#include "gemm_f32.cuh"
+#include "elementwise.cuh"
+#include "attention.cuh"
+#include "conv_tc.cuh"
+
+using namespace eegclip;
+
+namespace {
+
+constexpr int C = 64;      // channels == embedding
+constexpr int FF = 256;    // FFN hidden
+constexpr int NP_CONV = 4, NP_XF = 16;
+
+struct ConvP { const float *w, *b, *g, *be; };
+struct XfP { const float *ln1g, *ln1b, *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo, *ln2g, *ln2b, *w1, *b1, *w2, *b2; };
+struct ConvG { float *w, *b, *g, *be; };
+struct XfG { float *ln1g, *ln1b, *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo, *ln2g, *ln2b, *w1, *b1, *w2, *b2; };
+
+template <class P, class T>
+P conv_at(T* tab, int i) { T* t = tab + 2 + NP_CONV * i; return P{t[0], t[1], t[2], t[3]}; }
+template <class P, class T>
+P xf_at(T* tab, int n_conv, int j) {
+  T* t = tab + 2 + NP_CONV * n_conv + NP_XF * j;
+  return P{t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[9], t[10], t[11], t[12], t[13], t[14], t[15]};
+}
+
+// ---- saved-activation layout (floats) -------------------------------------------------------
+struct SaveLayout {
+  size_t eegx;                 // n*C
+  size_t conv_stride, xf_stride, conv0, xf0, total;
+  // within a conv block: y (n*C), out (n*C), stats (2B rounded to 4)
+  size_t c_y, c_out, c_stats;
+  // within a transformer block: qkv (n*192), o (n*C), lse (B*8*T), z1 (n*C), fpre (n*FF), zout (n*C)
+  size_t x_qkv, x_o, x_lse, x_z1, x_fpre, x_zout;
+};
+
+SaveLayout save_layout(const eegclip_tower_desc& d) {
+  SaveLayout L;
+  size_t n = (size_t)d.B * d.T;
+  size_t o = 0;
+  L.eegx = o; o += n * C;
+  L.c_y = 0; L.c_out = n * C; L.c_stats = 2 * n * C;
+  L.conv_stride = 2 * n * C + align_up((size_t)2 * d.B, 4);
+  L.x_qkv = 0; L.x_o = n * AQKV; L.x_lse = L.x_o + n * C; L.x_z1 = L.x_lse + align_up((size_t)d.B * AH * d.T, 4);
+  L.x_fpre = L.x_z1 + n * C; L.x_zout = L.x_fpre + n * FF;
+  L.xf_stride = L.x_zout + n * C;
+  L.conv0 = o; o += L.conv_stride * d.n_conv;
+  L.xf0 = o; o += L.xf_stride * d.depth;
+  L.total = o;
+  return L;
+}
+
+struct Scratch {
+  float *upad, *dypad, *h, *f, *dfpre, *dqkv, *d_o, *dg, *dza, *dzb, *dzc, *deeg, *wtmp;
+  size_t total;
+};
+
+Scratch scratch_layout(const eegclip_tower_desc& d, float* base) {
+  Scratch s;
+  size_t n = (size_t)d.B * d.T, TP = d.T + d.taps - 1;
+  size_t o = 0;
+  auto take = [&](size_t cnt) { float* p = base ? base + o : nullptr; o += align_up(cnt, 64); return p; };
+  s.upad = take((size_t)d.B * TP * C);
+  s.dypad = take((size_t)d.B * TP * C);
+  s.h = take(n * C);
+  s.f = take(n * FF);
+  s.dfpre = take(n * FF);
+  s.dqkv = take(n * AQKV);
+  s.d_o = take(n * C);
+  s.dg = take(n * C);
+  s.dza = take(n * C);
+  s.dzb = take(n * C);
+  s.dzc = take(n * C);
+  s.deeg = take(n * C);
+  s.wtmp = take((size_t)C * C * d.taps);
+  s.total = o;
+  return s;
+}
+
+bool desc_ok(const eegclip_tower_desc* d) {
+  if (!d) return false;
+  if (d->B <= 0 || d->T <= 0 || (d->T & 3) || d->depth < 0 || d->n_conv < 0 || d->taps <= 0 || d->latent <= 0) return false;
+  if (d->kind == EEGCLIP_TOWER_INTERLEAVED && d->n_conv != d->depth) return false;
+  if (d->kind != EEGCLIP_TOWER_INTERLEAVED && d->kind != EEGCLIP_TOWER_SEQUENTIAL) return false;
+  if (d->latent & 3) return false;
+  return true;
+}
+
+#define TRY(x) do { int _r = (x); if (_r != EEGCLIP_OK) return _r; } while (0)
+
+// out[m][n] = x[m][:] . w[n][:] + b[n]  with optional epilogue
+int linear_f32(const float* x, long ldx, const float* w, const float* b, float* out, long ldo, long M, int N, int K,
+               GemmEpi epi, cudaStream_t st) {
+  GemmArgs g;
+  g.A = x; g.B = w; g.C = out;
+  g.M = (int)M; g.N = N; g.K = K; g.KT = K;
+  g.a_ms = ldx; g.a_ks = 1;
+  g.b_ks = 1; g.b_ns = K;
+  g.c_ms = ldo; g.c_ns = 1;
+  epi.bias_n = b;
+  g.epi = epi;
+  return gemm_f32(g, st);
+}
+
+// dx[m][k] = sum_n dy[m][n] * w[n][k]   (w is (N,K) row-major)
+int linear_dgrad_f32(const float* dy, long lddy, const float* w, float* dx, long lddx, long M, int N, int K, GemmEpi epi,
+                     cudaStream_t st) {
+  GemmArgs g;
+  g.A = dy; g.B = w; g.C = dx;
+  g.M = (int)M; g.N = K; g.K = N; g.KT = N;
+  g.a_ms = lddy; g.a_ks = 1;
+  g.b_ks = K; g.b_ns = 1;
+  g.c_ms = lddx; g.c_ns = 1;
+  g.epi = epi;
+  return gemm_f32(g, st);
+}
+
+// dw[n][k] += sum_m dy[m][n] * x[m][k]   (atomic split over m; dw must be zeroed by the caller)
+int linear_wgrad_f32(const float* dy, long lddy, const float* x, long ldx, float* dw, long M, int N, int K, cudaStream_t st) {
+  GemmArgs g;
+  g.A = dy; g.B = x; g.C = dw;
+  g.M = N; g.N = K; g.K = (int)M; g.KT = (int)M;
+  g.a_ms = 1; g.a_ks = lddy;
+  g.b_ks = ldx; g.b_ns = 1;
+  g.c_ms = K; g.c_ns = 1;
+  int tiles = ceil_div(N, GBM) * ceil_div(K, GBN);
+  int sk = max(1, min(ceil_div((int)M, 512), (148 * 4) / max(1, tiles)));
+  g.splitk = sk;
+  g.epi.atomic = 1;
+  return gemm_f32(g, st);
+}
+
+// conv forward: y[b][t][co] = bias[co] + sum_{k,ci} upad[b][t+k][ci] * W[co][ci][k], then dropout
+int conv_fwd_f32(const float* upad, const float* W, const float* bias, float* y, int B, int T, int Cin, int Cout, int taps,
+                 const Drop& drop, cudaStream_t st) {
+  GemmArgs g;
+  int TP = T + taps - 1;
+  g.A = upad; g.B = W; g.C = y;
+  g.batch = B; g.M = T; g.N = Cout; g.K = taps * Cin; g.KT = Cin;
+  g.a_bs = (long)TP * Cin; g.a_ms = Cin; g.a_kbs = Cin; g.a_ks = 1;
+  g.b_kbs = 1; g.b_ks = taps; g.b_ns = (long)Cin * taps;
+  g.c_bs = (long)T * Cout; g.c_ms = Cout; g.c_ns = 1;
+  g.epi.bias_n = bias;
+  g.epi.drop_on = drop.enabled; g.epi.drop = drop;
+  return gemm_f32(g, st);
+}
+
+// conv data gradient: du[b][t][ci] = sum_{k',co} dypad[b][t+k'][co] * W[co][ci][taps-1-k']
+int conv_dgrad_f32(const float* dypad, const float* W, float* du, int B, int T, int Cin, int Cout, int taps, cudaStream_t st) {
+  GemmArgs g;
+  int TP = T + taps - 1;
+  g.A = dypad; g.B = W + (taps - 1); g.C = du;
+  g.batch = B; g.M = T; g.N = Cin; g.K = taps * Cout; g.KT = Cout;
+  g.a_bs = (long)TP * Cout; g.a_ms = Cout; g.a_kbs = Cout; g.a_ks = 1;
+  g.b_kbs = -1; g.b_ks = (long)Cin * taps; g.b_ns = taps;
+  g.c_bs = (long)T * Cin; g.c_ms = Cin; g.c_ns = 1;
+  return gemm_f32(g, st);
+}
+
+// conv weight gradient into tmp[co][k][ci] (zeroed by caller), reduction over (b,t)
+int conv_wgrad_f32(const float* dypad, int PLb, const float* upad, float* tmp, int B, int T, int Cin, int Cout, int taps,
+                   cudaStream_t st) {
+  GemmArgs g;
+  int TP = T + taps - 1;
+  g.A = dypad + (long)PLb * Cout; g.B = upad; g.C = tmp;
+  g.M = Cout; g.N = taps * Cin; g.K = B * T; g.KT = T;
+  g.a_ms = 1; g.a_ks = Cout; g.a_kbs = (long)TP * Cout;
+  g.b_ks = Cin; g.b_kbs = (long)TP * Cin; g.b_ns = 1;
+  g.c_ms = (long)taps * Cin; g.c_ns = 1;
+  int tiles = ceil_div(g.M, GBM) * ceil_div(g.N, GBN);
+  g.splitk = max(1, min(ceil_div(g.K, 256), (148 * 4) / max(1, tiles)));
+  g.epi.atomic = 1;
+  return gemm_f32(g, st);
+}
+
+// -------------------------------------------------------------------------------------------------
+// BasicBlock forward on time-major data.  xin (+ skip_in) -> conv -> dropout -> LN([C,T]) -> act (+ skip_out)
+// -------------------------------------------------------------------------------------------------
+int conv_block_fwd(int math, const float* xin, const float* skip_in, const ConvP& p, const float* skip_out, float* y, float* stats,
+                   float* out, float* upad, int B, int T, int Cin, int Cout, int taps, int act, const Drop& drop,
+                   cudaStream_t st) {
+  const int PL = (taps - 1) / 2;
+  if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
+    TRY(conv_tc_forward(math, xin, skip_in, p.w, p.b, y, B, T, PL, drop, upad, st));
+  } else {
+    TRY(pad_add(xin, skip_in, upad, B, T, Cin, PL, taps, st));
+    TRY(conv_fwd_f32(upad, p.w, p.b, y, B, T, Cin, Cout, taps, drop, st));
+  }
+  TRY(ln_ct_act_fwd(y, p.g, p.be, skip_out, out, stats, B, T, Cout, act, st));
+  return EEGCLIP_OK;
+}
+
+// Backward of the block: dout is the gradient w.r.t. `out` (excluding skip_out's own path).
+// Produces du (gradient w.r.t. xin + skip_in) and fills the four parameter gradients (pre-zeroed).
+int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP& p, const ConvG& gr, const float* y,
+                   const float* stats, const float* dout, float* du, float* upad, float* dypad, float* wtmp, int B, int T,
+                   int Cin, int Cout, int taps, int act, const Drop& drop, cudaStream_t st) {
+  const int PL = (taps - 1) / 2, PLb = taps - 1 - PL, TP = T + taps - 1;
+  CUDA_TRY(cudaMemsetAsync(dypad, 0, (size_t)B * TP * Cout * sizeof(float), st));
+  TRY(ln_ct_act_bwd(dout, y, stats, p.g, p.be, dypad, gr.g, gr.be, B, T, Cout, PLb, taps, act, drop, st));
+  TRY(colsum(dypad, gr.b, (long)B * TP, Cout, Cout, st));
+  if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
+    TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, PLb, du, gr.w, B, T, upad, wtmp, st));
+  } else {
+    TRY(pad_add(xin, skip_in, upad, B, T, Cin, PL, taps, st));
+    CUDA_TRY(cudaMemsetAsync(wtmp, 0, (size_t)Cout * Cin * taps * sizeof(float), st));
+    TRY(conv_wgrad_f32(dypad, PLb, upad, wtmp, B, T, Cin, Cout, taps, st));
+    TRY(wgrad_unpack(wtmp, gr.w, Cout, Cin, taps, st));
+    TRY(conv_dgrad_f32(dypad, p.w, du, B, T, Cin, Cout, taps, st));
+  }
+  return EEGCLIP_OK;
+}
+
+struct XfSave { float *qkv, *o, *lse, *z1, *fpre, *zout; };
+
+// TransformerEncoderBlock forward (clip_model.py:75-94).  zin -> zout
+int xf_block_fwd(const eegclip_tower_desc& d, int layer, const XfP& p, const float* zin, const XfSave& s, Scratch& w,
+                 cudaStream_t st) {
+  const long n = (long)d.B * d.T;
+  TRY(ln64_fwd(zin, p.ln1g, p.ln1b, w.h, n, st));
+  GemmEpi none;
+  TRY(linear_f32(w.h, C, p.wq, p.bq, s.qkv + 0, AQKV, n, C, C, none, st));
+  TRY(linear_f32(w.h, C, p.wk, p.bk, s.qkv + 64, AQKV, n, C, C, none, st));
+  TRY(linear_f32(w.h, C, p.wv, p.bv, s.qkv + 128, AQKV, n, C, C, none, st));
+  TRY(attention_fwd(s.qkv, s.o, s.lse, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
+  GemmEpi e1;
+  e1.drop = make_drop(d.seed, layer, SITE_PROJ, d.p_proj, d.train); e1.drop_on = e1.drop.enabled;
+  e1.residual = zin;
+  TRY(linear_f32(s.o, C, p.wo, p.bo, s.z1, C, n, C, C, e1, st));
+  TRY(ln64_fwd(s.z1, p.ln2g, p.ln2b, w.h, n, st));
+  GemmEpi e2;
+  e2.act = 1; e2.aux = s.fpre;
+  e2.drop = make_drop(d.seed, layer, SITE_FFN_HID, d.p_ffn_hid, d.train); e2.drop_on = e2.drop.enabled;
+  TRY(linear_f32(w.h, C, p.w1, p.b1, w.f, FF, n, FF, C, e2, st));
+  GemmEpi e3;
+  e3.drop = make_drop(d.seed, layer, SITE_FFN_OUT, d.p_ffn_out, d.train); e3.drop_on = e3.drop.enabled;
+  e3.residual = s.z1;
+  TRY(linear_f32(w.f, FF, p.w2, p.b2, s.zout, C, n, C, FF, e3, st));
+  return EEGCLIP_OK;
+}
+
+// Backward: dzout -> dzin (both n*C). Parameter gradients accumulate into pre-zeroed buffers.
+int xf_block_bwd(const eegclip_tower_desc& d, int layer, const XfP& p, const XfG& g, const float* zin, const XfSave& s,
+                 const float* dzout, float* dzin, Scratch& w, cudaStream_t st) {
+  const long n = (long)d.B * d.T;
+  // ---- FFN branch -------------------------------------------------------------------------
+  Drop d_out = make_drop(d.seed, layer, SITE_FFN_OUT, d.p_ffn_out, d.train);
+  const float* dg = dzout;
+  if (d_out.enabled) { TRY(drop_mul(dzout, w.dg, n * C, d_out, st)); dg = w.dg; }
+  TRY(colsum(dg, g.b2, n, C, C, st));
+  Drop d_hid = make_drop(d.seed, layer, SITE_FFN_HID, d.p_ffn_hid, d.train);
+  TRY(gelu_drop(s.fpre, w.f, n * FF, d_hid, st));
+  TRY(linear_wgrad_f32(dg, C, w.f, FF, g.w2, n, C, FF, st));
+  GemmEpi e;
+  e.drop = d_hid; e.drop_on = d_hid.enabled; e.act_grad_src = s.fpre;
+  TRY(linear_dgrad_f32(dg, C, p.w2, w.dfpre, FF, n, C, FF, e, st));
+  TRY(colsum(w.dfpre, g.b1, n, FF, FF, st));
+  TRY(ln64_fwd(s.z1, p.ln2g, p.ln2b, w.h, n, st));
+  TRY(linear_wgrad_f32(w.dfpre, FF, w.h, C, g.w1, n, FF, C, st));
+  GemmEpi none;
+  TRY(linear_dgrad_f32(w.dfpre, FF, p.w1, w.d_o, C, n, FF, C, none, st));      // d_o reused as dh2
+  TRY(ln64_bwd(w.d_o, s.z1, p.ln2g, dzout, w.dzc, g.ln2g, g.ln2b, n, st));     // dzc = dz1
+  // ---- attention branch -------------------------------------------------------------------
+  Drop d_proj = make_drop(d.seed, layer, SITE_PROJ, d.p_proj, d.train);
+  const float* dp = w.dzc;
+  if (d_proj.enabled) { TRY(drop_mul(w.dzc, w.dg, n * C, d_proj, st)); dp = w.dg; }
+  TRY(colsum(dp, g.bo, n, C, C, st));
+  TRY(linear_wgrad_f32(dp, C, s.o, C, g.wo, n, C, C, st));
+  TRY(linear_dgrad_f32(dp, C, p.wo, w.d_o, C, n, C, C, none, st));             // d_o = grad wrt attention output
+  TRY(attention_bwd(s.qkv, s.o, w.d_o, s.lse, w.dqkv, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
+  TRY(colsum(w.dqkv + 0, g.bq, n, C, AQKV, st));
+  TRY(colsum(w.dqkv + 64, g.bk, n, C, AQKV, st));
+  TRY(colsum(w.dqkv + 128, g.bv, n, C, AQKV, st));
+  TRY(ln64_fwd(zin, p.ln1g, p.ln1b, w.h, n, st));
+  TRY(linear_wgrad_f32(w.dqkv + 0, AQKV, w.h, C, g.wq, n, C, C, st));
+  TRY(linear_wgrad_f32(w.dqkv + 64, AQKV, w.h, C, g.wk, n, C, C, st));
+  TRY(linear_wgrad_f32(w.dqkv + 128, AQKV, w.h, C, g.wv, n, C, C, st));
+  TRY(linear_dgrad_f32(w.dqkv + 0, AQKV, p.wq, w.d_o, C, n, C, C, none, st));  // d_o reused as dh1
+  GemmEpi acc; acc.residual = w.d_o;
+  TRY(linear_dgrad_f32(w.dqkv + 64, AQKV, p.wk, w.d_o, C, n, C, C, acc, st));
+  TRY(linear_dgrad_f32(w.dqkv + 128, AQKV, p.wv, w.d_o, C, n, C, C, acc, st));
+  TRY(ln64_bwd(w.d_o, zin, p.ln1g, w.dzc, dzin, g.ln1g, g.ln1b, n, st));
+  return EEGCLIP_OK;
+}
+
+XfSave xf_save(float* save, const SaveLayout& L, int j) {
+  float* b = save + L.xf0 + L.xf_stride * j;
+  return XfSave{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, b + L.x_zout};
+}
+
+}  // namespace
+
+extern "C" {
+
+int eegclip_tower_workspace(const eegclip_tower_desc* d, size_t* save_bytes, size_t* scratch_bytes) {
+  if (!desc_ok(d)) return EEGCLIP_ERR_ARG;
+  if (save_bytes) *save_bytes = save_layout(*d).total * sizeof(float);
+  if (scratch_bytes) *scratch_bytes = scratch_layout(*d, nullptr).total * sizeof(float) + conv_tc_scratch_bytes(d->B, d->T, d->taps);
+  return EEGCLIP_OK;
+}
+
+int eegclip_tower_forward(const eegclip_tower_desc* dp, const float* const* params, const float* x, float* out, void* save_v,
+                          void* scratch_v, void* stream) {
+  if (!desc_ok(dp) || !params || !x || !out || !scratch_v || !save_v) return EEGCLIP_ERR_ARG;
+  const eegclip_tower_desc& d = *dp;
+  cudaStream_t st = (cudaStream_t)stream;
+  SaveLayout L = save_layout(d);
+  float* save = (float*)save_v;
+  Scratch w = scratch_layout(d, (float*)scratch_v);
+  const long n = (long)d.B * d.T;
+  float* eegx = save + L.eegx;
+  GemmEpi none;
+  // eeg_spatial_mapping: 1x1 conv == per-token linear (clip_model.py:447)
+  TRY(linear_f32(x, C, params[0], params[1], eegx, C, n, C, C, none, st));
+  const float* xin = eegx;
+  if (d.kind == EEGCLIP_TOWER_INTERLEAVED) {
+    for (int i = 0; i < d.depth; ++i) {
+      ConvP cp = conv_at<ConvP>(params, i);
+      float* cb = save + L.conv0 + L.conv_stride * i;
+      const bool last = (i == d.depth - 1);
+      // conv input is x + eeg_x (clip_model.py:459); transformer input adds eeg_x again unless last (:465-469)
+      TRY(conv_block_fwd(d.math, xin, eegx, cp, last ? nullptr : eegx, cb + L.c_y, cb + L.c_stats, cb + L.c_out, w.upad, d.B, d.T, C,
+                         C, d.taps, 0, make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st));
+      XfSave xs = xf_save(save, L, i);
+      TRY(xf_block_fwd(d, i, xf_at<XfP>(params, d.n_conv, i), cb + L.c_out, xs, w, st));
+      xin = xs.zout;
+    }
+  } else {
+    for (int i = 0; i < d.n_conv; ++i) {
+      ConvP cp = conv_at<ConvP>(params, i);
+      float* cb = save + L.conv0 + L.conv_stride * i;
+      const bool last = (i == d.n_conv - 1);  // no input skip in the last conv block (clip_model.py:385-390)
+      TRY(conv_block_fwd(d.math, xin, last ? nullptr : eegx, cp, nullptr, cb + L.c_y, cb + L.c_stats, cb + L.c_out, w.upad, d.B, d.T,
+                         C, C, d.taps, 0, make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st));
+      xin = cb + L.c_out;
+    }
+    for (int j = 0; j < d.depth; ++j) {
+      XfSave xs = xf_save(save, L, j);
+      TRY(xf_block_fwd(d, d.n_conv + j, xf_at<XfP>(params, d.n_conv, j), xin, xs, w, st));
+      xin = xs.zout;
+    }
+  }
+  const int fi = 2 + NP_CONV * d.n_conv + NP_XF * d.depth;
+  TRY(linear_f32(xin, C, params[fi], params[fi + 1], out, d.latent, n, d.latent, C, none, st));
+  return EEGCLIP_OK;
+}
+
+int eegclip_tower_backward(const eegclip_tower_desc* dp, const float* const* params, float* const* grads, void* grad_base,
+                           size_t grad_bytes, const float* x, const float* dout, float* dx, const void* save_v, void* scratch_v,
+                           void* stream) {
+  if (!desc_ok(dp) || !params || !grads || !x || !dout || !save_v || !scratch_v) return EEGCLIP_ERR_ARG;
+  const eegclip_tower_desc& d = *dp;
+  cudaStream_t st = (cudaStream_t)stream;
+  SaveLayout L = save_layout(d);
+  float* save = (float*)save_v;  // read-only use
+  Scratch w = scratch_layout(d, (float*)scratch_v);
+  const long n = (long)d.B * d.T;
+  const float* eegx = save + L.eegx;
+  if (grad_base && grad_bytes) CUDA_TRY(cudaMemsetAsync(grad_base, 0, grad_bytes, st));
+  GemmEpi none;
+  const int fi = 2 + NP_CONV * d.n_conv + NP_XF * d.depth;
+
+  // last activation feeding the final linear
+  const float* xlast = eegx;
+  if (d.depth > 0) xlast = xf_save(save, L, d.depth - 1).zout;
+  else if (d.n_conv > 0) xlast = save + L.conv0 + L.conv_stride * (d.n_conv - 1) + L.c_out;
+
+  TRY(colsum(dout, grads[fi + 1], n, d.latent, d.latent, st));
+  TRY(linear_wgrad_f32(dout, d.latent, xlast, C, grads[fi], n, d.latent, C, st));
+  float* dz = w.dza;
+  float* dz2 = w.dzb;
+  TRY(linear_dgrad_f32(dout, d.latent, params[fi], dz, C, n, d.latent, C, none, st));
+  CUDA_TRY(cudaMemsetAsync(w.deeg, 0, (size_t)n * C * sizeof(float), st));
+
+  if (d.kind == EEGCLIP_TOWER_INTERLEAVED) {
+    for (int i = d.depth - 1; i >= 0; --i) {
+      float* cb = save + L.conv0 + L.conv_stride * i;
+      const bool last = (i == d.depth - 1);
+      XfSave xs = xf_save(save, L, i);
+      TRY(xf_block_bwd(d, i, xf_at<XfP>(params, d.n_conv, i), xf_at<XfG>(grads, d.n_conv, i), cb + L.c_out, xs, dz, dz2, w, st));
+      if (!last) TRY(add_f32(w.deeg, dz2, w.deeg, n * C, st));  // skip into the transformer input
+      const float* xin = (i == 0) ? eegx : xf_save(save, L, i - 1).zout;
+      TRY(conv_block_bwd(d.math, xin, eegx, conv_at<ConvP>(params, i), conv_at<ConvG>(grads, i), cb + L.c_y, cb + L.c_stats, dz2, dz,
+                         w.upad, w.dypad, w.wtmp, d.B, d.T, C, C, d.taps, 0, make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st));
+      TRY(add_f32(w.deeg, dz, w.deeg, n * C, st));              // skip into the conv input
+    }
+    TRY(add_f32(w.deeg, dz, w.deeg, n * C, st));                // x_0 == eeg_x itself
+  } else {
+    for (int j = d.depth - 1; j >= 0; --j) {
+      XfSave xs = xf_save(save, L, j);
+      const float* zin = (j == 0) ? (d.n_conv > 0 ? save + L.conv0 + L.conv_stride * (d.n_conv - 1) + L.c_out : eegx)
+                                  : xf_save(save, L, j - 1).zout;
+      TRY(xf_block_bwd(d, d.n_conv + j, xf_at<XfP>(params, d.n_conv, j), xf_at<XfG>(grads, d.n_conv, j), zin, xs, dz, dz2, w, st));
+      float* t = dz; dz = dz2; dz2 = t;
+    }
+    for (int i = d.n_conv - 1; i >= 0; --i) {
+      float* cb = save + L.conv0 + L.conv_stride * i;
+      const bool last = (i == d.n_conv - 1);
+      const float* xin = (i == 0) ? eegx : save + L.conv0 + L.conv_stride * (i - 1) + L.c_out;
+      TRY(conv_block_bwd(d.math, xin, last ? nullptr : eegx, conv_at<ConvP>(params, i), conv_at<ConvG>(grads, i), cb + L.c_y,
+                         cb + L.c_stats, dz, dz2, w.upad, w.dypad, w.wtmp, d.B, d.T, C, C, d.taps, 0,
+                         make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st));
+      if (!last) TRY(add_f32(w.deeg, dz2, w.deeg, n * C, st));
+      float* t = dz; dz = dz2; dz2 = t;
+    }
+    TRY(add_f32(w.deeg, dz, w.deeg, n * C, st));                // x_0 == eeg_x
+  }
+  // eeg_spatial_mapping backward
+  TRY(colsum(w.deeg, grads[1], n, C, C, st));
+  TRY(linear_wgrad_f32(w.deeg, C, x, C, grads[0], n, C, C, st));
+  if (dx) TRY(linear_dgrad_f32(w.deeg, C, params[0], dx, C, n, C, C, none, st));
+  return EEGCLIP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Stand-alone conv block (BasicBlock of the speech tower, VLAAI layers) and linear layers
+// -------------------------------------------------------------------------------------------------
+int eegclip_convblock_workspace(const eegclip_convblock_desc* d, size_t* save_bytes, size_t* scratch_bytes) {
+  if (!d || d->B <= 0 || d->T <= 0 || (d->Cin & 3) || (d->Cout & 3) || d->taps <= 0) return EEGCLIP_ERR_ARG;
+  size_t n = (size_t)d->B * d->T, TP = d->T + d->taps - 1;
+  if (save_bytes) *save_bytes = (n * d->Cout + align_up((size_t)2 * d->B, 4)) * sizeof(float);
+  if (scratch_bytes)
+    *scratch_bytes = (align_up((size_t)d->B * TP * d->Cin, 64) + align_up((size_t)d->B * TP * d->Cout, 64) +
+                      align_up((size_t)d->Cout * d->Cin * d->taps, 64)) * sizeof(float) + conv_tc_scratch_bytes(d->B, d->T, d->taps);
+  return EEGCLIP_OK;
+}
+
+int eegclip_convblock_forward(const eegclip_convblock_desc* d, const float* x, const float* skip_in, const float* w,
+                              const float* bias, const float* gamma, const float* beta, float* out, void* save, void* scratch,
+                              void* stream) {
+  if (!d || !x || !w || !gamma || !beta || !out || !save || !scratch) return EEGCLIP_ERR_ARG;
+  if ((d->Cin & 3) || (d->Cout & 3) || (d->T & 3) || d->Cout > 256) return EEGCLIP_ERR_UNSUPPORTED;
+  size_t n = (size_t)d->B * d->T;
+  float* y = (float*)save;
+  float* stats = y + n * d->Cout;
+  float* upad = (float*)scratch;
+  ConvP p{w, bias, gamma, beta};
+  return conv_block_fwd(d->math, x, skip_in, p, nullptr, y, stats, out, upad, d->B, d->T, d->Cin, d->Cout, d->taps, d->act,
+                        make_drop(d->seed, d->layer, SITE_CONV, d->p_drop, d->train), (cudaStream_t)stream);
+}
+
+int eegclip_convblock_backward(const eegclip_convblock_desc* d, const float* x, const float* skip_in, const float* w,
+                               const float* gamma, const float* beta, const float* dout, float* dx, float* dw, float* dbias,
+                               float* dgamma, float* dbeta, const void* save, void* scratch, void* stream) {
+  if (!d || !x || !w || !gamma || !beta || !dout || !dx || !dw || !dbias || !dgamma || !dbeta || !save || !scratch)
+    return EEGCLIP_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n = (size_t)d->B * d->T, TP = d->T + d->taps - 1;
+  const float* y = (const float*)save;
+  const float* stats = y + n * d->Cout;
+  float* upad = (float*)scratch;
+  float* dypad = upad + align_up((size_t)d->B * TP * d->Cin, 64);
+  float* wtmp = dypad + align_up((size_t)d->B * TP * d->Cout, 64);
+  CUDA_TRY(cudaMemsetAsync(dbias, 0, d->Cout * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(dgamma, 0, (size_t)d->Cout * d->T * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(dbeta, 0, (size_t)d->Cout * d->T * sizeof(float), st));
+  ConvP p{w, nullptr, gamma, beta};
+  ConvG g{dw, dbias, dgamma, dbeta};
+  return conv_block_bwd(d->math, x, skip_in, p, g, y, stats, dout, dx, upad, dypad, wtmp, d->B, d->T, d->Cin, d->Cout, d->taps, d->act,
+                        make_drop(d->seed, d->layer, SITE_CONV, d->p_drop, d->train), st);
+}
+
+int eegclip_linear_forward(const float* x, const float* w, const float* b, float* out, int64_t M, int32_t N, int32_t K, int32_t math,
+                           void* stream) {
+  if (!x || !w || !out || M <= 0 || N <= 0 || K <= 0) return EEGCLIP_ERR_ARG;
+  (void)math;
+  GemmEpi none;
+  return linear_f32(x, K, w, b, out, N, M, N, K, none, (cudaStream_t)stream);
+}
+
+int eegclip_linear_backward(const float* x, const float* w, const float* dout, float* dx, float* dw, float* db, int64_t M, int32_t N,
+                            int32_t K, int32_t math, void* stream) {
+  if (!x || !w || !dout || M <= 0 || N <= 0 || K <= 0) return EEGCLIP_ERR_ARG;
+  (void)math;
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmEpi none;
+  if (dx) TRY(linear_dgrad_f32(dout, N, w, dx, K, M, N, K, none, st));
+  if (dw) {
+    CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), st));
+    TRY(linear_wgrad_f32(dout, N, x, K, dw, M, N, K, st));
+  }
+  if (db) {
+    CUDA_TRY(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+    if ((N & 3) == 0 && N <= 256 && 256 % (N >> 2) == 0) TRY(colsum(dout, db, M, N, N, st));
+    else return EEGCLIP_ERR_UNSUPPORTED;
+  }
+  return EEGCLIP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Stand-alone TransformerEncoderBlock
+// -------------------------------------------------------------------------------------------------
+static eegclip_tower_desc xf_as_tower(const eegclip_xfblock_desc* d) {
+  eegclip_tower_desc t{};
+  t.kind = EEGCLIP_TOWER_SEQUENTIAL; t.B = d->B; t.T = d->T; t.n_conv = 0; t.depth = 1; t.taps = 1; t.latent = 8;
+  t.train = d->train; t.math = d->math;
+  t.p_attn = d->p_attn; t.p_proj = d->p_proj; t.p_ffn_hid = d->p_ffn_hid; t.p_ffn_out = d->p_ffn_out; t.seed = d->seed;
+  return t;
+}
+
+int eegclip_xfblock_workspace(const eegclip_xfblock_desc* d, size_t* save_bytes, size_t* scratch_bytes) {
+  if (!d || d->B <= 0 || d->T <= 0 || (d->T & 3)) return EEGCLIP_ERR_ARG;
+  eegclip_tower_desc t = xf_as_tower(d);
+  SaveLayout L = save_layout(t);
+  if (save_bytes) *save_bytes = L.xf_stride * sizeof(float);
+  if (scratch_bytes) *scratch_bytes = scratch_layout(t, nullptr).total * sizeof(float);
+  return EEGCLIP_OK;
+}
+
+int eegclip_xfblock_forward(const eegclip_xfblock_desc* d, const float* const* params, const float* zin, float* zout, void* save,
+                            void* scratch, void* stream) {
+  if (!d || !params || !zin || !zout || !save || !scratch || d->B <= 0 || d->T <= 0 || (d->T & 3)) return EEGCLIP_ERR_ARG;
+  eegclip_tower_desc t = xf_as_tower(d);
+  SaveLayout L = save_layout(t);
+  float* b = (float*)save;
+  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, zout};
+  Scratch w = scratch_layout(t, (float*)scratch);
+  const float* const* tp = params - 2;  // xf_at() skips the two mapping entries
+  return xf_block_fwd(t, d->layer, xf_at<XfP>(tp, 0, 0), zin, xs, w, (cudaStream_t)stream);
+}
+
+int eegclip_xfblock_backward(const eegclip_xfblock_desc* d, const float* const* params, float* const* grads, void* grad_base,
+                             size_t grad_bytes, const float* zin, const float* dzout, float* dzin, const void* save, void* scratch,
+                             void* stream) {
+  if (!d || !params || !grads || !zin || !dzout || !dzin || !save || !scratch) return EEGCLIP_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  eegclip_tower_desc t = xf_as_tower(d);
+  SaveLayout L = save_layout(t);
+  float* b = (float*)save;
+  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, nullptr};
+  Scratch w = scratch_layout(t, (float*)scratch);
+  if (grad_base && grad_bytes) CUDA_TRY(cudaMemsetAsync(grad_base, 0, grad_bytes, st));
+  return xf_block_bwd(t, d->layer, xf_at<XfP>(params - 2, 0, 0), xf_at<XfG>(grads - 2, 0, 0), zin, xs, dzout, dzin, w, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+"""Symmetric InfoNCE head, local or sharded over a data-parallel group.
+
+The reference has no distributed code; the sharded scheme is defined by the north star:
+each rank encodes its batch shard, the L2-normalised embeddings are all-gathered (NCCL over NVLink),
+every rank scores its speech rows and its EEG columns against the global batch, the three per-row
+vectors (row LSE, column LSE, diagonal) are all-gathered, and the loss is identical on every rank.
+The backward recomputes the two logit blocks, so no embedding-gradient reduce-scatter is needed;
+parameter gradients are all-reduced with SUM (each rank already holds exact global-loss gradients
+with respect to its own rows).  With world size 1 this is exactly clip_model.py:675-693.
+
+Device compute goes through the C ABI (``CudaHeadOps``).  The collective plumbing is written against
+a small ops interface so that the world_size-2 gloo tests can drive the very same code on CPU with a
+checker implementation injected by the test-suite; the product path never leaves ``CudaHeadOps``.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+
+class CudaHeadOps:
+    """Head kernels behind include/eegclip.h (eegclip_l2norm_*, eegclip_infonce_*)."""
+
+    @staticmethod
+    def _scratch(b, Bg, D, device):
+        n = ctypes.c_size_t()
+        L.call("eegclip_infonce_workspace", b, Bg, D, ctypes.byref(n))
+        return torch.empty(max(n.value, 16), dtype=torch.uint8, device=device)
+
+    def l2norm_fwd(self, x):
+        x = L.f32c(x)
+        xn = torch.empty_like(x)
+        inv = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        L.call("eegclip_l2norm_forward", L.ptr(x), L.ptr(xn), L.ptr(inv), x.shape[0], x.shape[1], L.stream())
+        return xn, inv
+
+    def l2norm_bwd(self, xn, inv, dxn):
+        dx = torch.empty_like(xn)
+        L.call("eegclip_l2norm_backward", L.ptr(xn), L.ptr(inv), L.ptr(L.f32c(dxn)), L.ptr(dx), xn.shape[0], xn.shape[1], L.stream())
+        return dx
+
+    def lse(self, S_all, E_all, tau, b, row0, one_sided):
+        Bg, D = E_all.shape
+        dev = E_all.device
+        out = torch.empty(3, b, dtype=torch.float32, device=dev)  # lse_row, lse_col, diag
+        if one_sided:
+            out[1].zero_()
+        scratch = self._scratch(b, Bg, D, dev)
+        L.call("eegclip_infonce_lse", L.ptr(S_all), L.ptr(E_all), L.ptr(tau), b, row0, Bg, D, L.ptr(out[0]), L.ptr(out[1]),
+               L.ptr(out[2]), L.default_math(), int(one_sided), L.ptr(scratch), L.stream())
+        return out
+
+    def loss(self, vec_all, one_sided):
+        Bg = vec_all.shape[1]
+        loss = torch.empty((), dtype=torch.float32, device=vec_all.device)
+        L.call("eegclip_infonce_loss", L.ptr(vec_all[0]), L.ptr(vec_all[1]), L.ptr(vec_all[2]), Bg, int(one_sided), L.ptr(loss),
+               L.stream())
+        return loss
+
+    def backward(self, S_all, E_all, tau, vec_all, b, row0, dloss, one_sided):
+        Bg, D = E_all.shape
+        dev = E_all.device
+        dS = None if one_sided else torch.empty(b, D, dtype=torch.float32, device=dev)
+        dE = torch.empty(b, D, dtype=torch.float32, device=dev)
+        dtau = torch.empty((), dtype=torch.float32, device=dev)
+        scratch = self._scratch(b, Bg, D, dev)
+        L.call("eegclip_infonce_backward", L.ptr(S_all), L.ptr(E_all), L.ptr(tau), L.ptr(vec_all[0]), L.ptr(vec_all[1]), b, row0,
+               Bg, D, L.ptr(dloss), L.ptr(dS), L.ptr(dE), L.ptr(dtau), L.default_math(), int(one_sided), L.ptr(scratch), L.stream())
+        return dS, dE, dtau
+
+
+_CUDA_OPS = CudaHeadOps()
+
+
+def _world(group):
+    if group is None or not dist.is_available() or not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def _all_gather_rows(x, group, world):
+    """(b, ...) -> (world*b, ...) in rank order."""
+    if world == 1:
+        return x
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+class _InfoNCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, E_raw, S_raw, tau, group, ops):
+        world, rank = _world(group)
+        b = E_raw.shape[0]
+        En, invE = ops.l2norm_fwd(E_raw)
+        Sn, invS = ops.l2norm_fwd(S_raw)
+        E_all = _all_gather_rows(En, group, world)
+        S_all = _all_gather_rows(Sn, group, world)
+        tau_c = tau.detach().to(En.dtype).reshape(1).contiguous()
+        vec = ops.lse(S_all, E_all, tau_c, b, rank * b, False)              # (3, b)
+        if world > 1:
+            gathered = _all_gather_rows(vec.t().contiguous(), group, world)  # (world*b, 3)
+            vec_all = gathered.t().contiguous()
+        else:
+            vec_all = vec
+        loss = ops.loss(vec_all, False)
+        ctx.saved = (En, invE, Sn, invS, E_all, S_all, tau_c, vec_all)
+        ctx.meta = (b, rank * b, ops, tau.shape)
+        ctx.mark_non_differentiable(En)
+        return loss, En
+
+    @staticmethod
+    def backward(ctx, dloss, _dEn):
+        En, invE, Sn, invS, E_all, S_all, tau_c, vec_all = ctx.saved
+        b, row0, ops, tau_shape = ctx.meta
+        dl = dloss.detach().to(En.dtype).reshape(1).contiguous()
+        dSn, dEn, dtau = ops.backward(S_all, E_all, tau_c, vec_all, b, row0, dl, False)
+        dE = ops.l2norm_bwd(En, invE, dEn)
+        dS = ops.l2norm_bwd(Sn, invS, dSn)
+        return dE, dS, dtau.reshape(tau_shape), None, None
+
+
+class _CERowsFn(torch.autograd.Function):
+    """CE(normalize(X) . En^T * exp(tau), arange) with gradients for En and tau only (clip_model.py:919,934-937)."""
+
+    @staticmethod
+    def forward(ctx, X_raw, En, tau, ops):
+        Xn, _ = ops.l2norm_fwd(X_raw)
+        En = En.detach().contiguous()
+        tau_c = tau.detach().to(En.dtype).reshape(1).contiguous()
+        b = En.shape[0]
+        vec = ops.lse(Xn, En, tau_c, b, 0, True)
+        loss = ops.loss(vec, True)
+        ctx.saved = (Xn, En, tau_c, vec)
+        ctx.meta = (b, ops, tau.shape)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        Xn, En, tau_c, vec = ctx.saved
+        b, ops, tau_shape = ctx.meta
+        dl = dloss.detach().to(En.dtype).reshape(1).contiguous()
+        _, dEn, dtau = ops.backward(Xn, En, tau_c, vec, b, 0, dl, True)
+        return None, dEn, dtau.reshape(tau_shape), None
+
+
+def infonce_loss(E_raw, S_raw, tau, group=None, return_normalized=False, ops=None):
+    """Symmetric InfoNCE of clip_model.py:675-693 on raw (un-normalised) flattened embeddings (b,D).
+
+    With ``group`` set and torch.distributed initialised the batch is the concatenation over ranks.
+    Returns the loss (0-dim) and, if asked, this rank's normalised EEG embeddings (detached).
+    """
+    ops = ops or _CUDA_OPS
+    if ops is _CUDA_OPS and not E_raw.is_cuda:
+        raise L.EegclipError("infonce_loss: embeddings must be CUDA tensors (no CPU fallback on this path)")
+    loss, En = _InfoNCEFn.apply(E_raw, S_raw, tau, group, ops)
+    return (loss, En) if return_normalized else loss
+
+
+def ce_rows_loss(X_raw, En, tau, ops=None):
+    return _CERowsFn.apply(X_raw, En, tau, ops or _CUDA_OPS)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Data-parallel plumbing
+# ---------------------------------------------------------------------------------------------------
+def broadcast_parameters(module, group=None, src=0):
+    """Make every rank start from rank ``src``'s weights and buffers."""
+    world, _ = _world(group if group is not None else dist.group.WORLD if dist.is_initialized() else None)
+    if world == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)
+
+
+def allreduce_gradients(params, group=None, flat=None):
+    """SUM-all-reduce the gradients (one collective when ``flat`` -- the optimizer's flat gradient arena -- is given)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    if dist.get_world_size(group) == 1:
+        return
+    if flat is not None:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    buf = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    o = 0
+    for g in grads:
+        g.copy_(buf[o:o + g.numel()].view_as(g))
+        o += g.numel()

@@ -1,0 +1,248 @@
+"""Entry points of the reference ``train_clip_final.py`` for the EEG-CLIP hot path, on B200 kernels.
+
+Call-compatible pieces:
+  * ``load_eeg_encoder`` / ``load_speech_encoder``  -- same positional signatures and hard-wired hyper-parameters
+    as train_clip_final.py:37-100 / 102-130 for the encoders in scope;
+  * the CLI flags of train_clip_final.py:158-216 (same names and defaults), parsed by ``build_parser``;
+  * ``train_step`` -- the body of the hot loop (train_clip_final.py:476-492): forward, zero_grad, backward, AdamW;
+  * ``main`` -- the training loop with StepLR per epoch (:419,503-504), validation and checkpointing (:506-540),
+    optionally data-parallel under torchrun (sharded InfoNCE + SUM all-reduce; new functionality).
+
+Dataset plumbing (dataset_loader.py, file split, regression evaluations) is out of scope; ``--data_dir synthetic``
+feeds seeded synthetic batches of the reference's shapes, any other value expects the reference's own
+``dataset_loader`` / ``train_clip_helper_functions.get_train_val_test_files_final`` to be importable.
+"""
+import argparse
+import json
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from .clip_model import (CLIPSimNoLatentProj, EEGConformer, EEGConformerInterleaved, EEGConvLSTM, SpeechSmallConv,
+                         memoryBank)
+from .optim import AdamW
+from .parallel import allreduce_gradients, broadcast_parameters
+from .vlaai import VLAAI
+
+# flag table: (name, type, default, choices) -- train_clip_final.py:163-216
+_FLAGS = [
+    ("debug", str, "no", ["yes", "no"]), ("only_evaluate", str, "no", ["yes", "no"]),
+    ("results_folder", str, os.path.join(os.path.dirname(os.path.abspath(__file__)), "results"), None),
+    ("run", int, 4, None), ("lstm_units", int, 128, None), ("lambda_sim_loss", float, 0.0, None),
+    ("warmup_epochs", int, 0, None), ("momentum_membank", float, 0.90, None), ("eeg_norm", str, "mvn", ["mvn"]),
+    ("stimulus_features", str, "wav2vec_19", None),
+    ("model_arch", str, "clip_sim_no_latent_proj",
+     ["no_contrastive_learning", "clip_kld", "clip_kld_latent_proj", "clip_mp", "clip_sim", "clip_sim_no_latent_proj",
+      "clip_extended", "clip_no_eeg_loss", "clip_correct"]),
+    ("speech_encoder", str, "convLSTM", ["conformer", "smallConv", "lstm", "convLSTM", "no", "double_lstm", "Wav2vecSmallModel"]),
+    ("eeg_encoder", str, "EEGConformerInterleaved",
+     ["EEGConformerInterleaved", "conformer", "convLSTMnew", "convLSTM", "lstm_newvals", "vlaai", "clipmeta", "lstm", "lstm_lstm",
+      "double_lstm", "transformerEncoder"]),
+    ("attention_depth", int, 10, None), ("load_pretrain", str, "no", ["yes", "no"]), ("shuffle", str, "yes", ["yes", "no"]),
+    ("shuffle_percentage", float, 1.0, None), ("addEEG", str, "no", ["yes", "no"]),
+    ("data_augmentation", str, "no", ["no", "SignFlip", "FTSurrogate", "FrequencyShift", "BandstopFilter", "GaussianNoise",
+                                      "SmoothTimeMask", "ChannelsDropout", "ChannelsShuffle"]),
+    ("data_augmentation_percentage", float, 0.5, None), ("learning_rate", float, 1e-3, None), ("beta1", float, 0.90, None),
+    ("beta2", float, 0.999, None), ("use_amsgrad", str, "no", ["yes", "no"]), ("optimizer", str, "adamw", ["adam", "adamw"]),
+    ("weight_decay", float, 0.01, None), ("lr_scheduler", str, "step", ["no", "plateau", "step", "cosine", "cosine_warmup"]),
+    ("step_size_scheduler", int, 10, None), ("epochs", int, 500, None), ("patience", int, 15, None),
+    ("batch_size", int, 128, None), ("number_conv_layers", int, 1, None), ("fun_act", str, "relu", None),
+    ("temperature", float, 0.075, None), ("subject_split", str, "icassp_testset", ["within", "heldout", "icassp_testset"]),
+    ("data_dir", str, "/esat/audioslave/lbollens/sparrkulee_data/sparrkulee", None),
+    ("number_of_training_subjects", int, 1000, None), ("lambda_clip_loss", float, 1, None), ("latent_dim", int, 8, None),
+]
+
+WINDOW_LENGTH = 3 * 64  # train_clip_final.py:150-152
+
+
+def build_parser():
+    p = argparse.ArgumentParser(description="Train CLIP model (B200 kernels).")
+    for name, typ, default, choices in _FLAGS:
+        p.add_argument(f"--{name}", type=typ, default=default, choices=choices)
+    # additions (not in the reference): synthetic-data sizing for --data_dir synthetic
+    p.add_argument("--window_length", type=int, default=WINDOW_LENGTH)
+    p.add_argument("--synthetic_batches", type=int, default=8)
+    p.add_argument("--math", type=str, default=None, choices=["fp32", "bf16x3", "bf16"])
+    return p
+
+
+_latent_dim_global = 8  # the reference's smallConv / convLSTM speech factories read the *global* latent_dim (:114,119)
+
+
+def load_eeg_encoder(eeg_encoder, units_lstm, padding, spatial_filters, number_conv_layers, window_length, latent_dim,
+                     attention_depth):
+    """train_clip_final.py:37-100 for the encoders on the hot path."""
+    conv = dict(dropout_rate=0.2, eeg_dim=64, filters=(64,) * number_conv_layers, kernels=(64,) * number_conv_layers,
+                dilation_rate=1, input_channels=64, time_dimension=window_length)
+    if eeg_encoder == 'EEGConformerInterleaved':
+        return EEGConformerInterleaved(output_dim=latent_dim, conformer_input_dim=64, depth=attention_depth, **conv)
+    if eeg_encoder == 'conformer':
+        return EEGConformer(output_dim=latent_dim, conformer_input_dim=64, depth=attention_depth, **conv)
+    if eeg_encoder == 'vlaai':
+        return VLAAI()
+    if eeg_encoder == 'convLSTM':
+        return EEGConvLSTM(units_lstm=128, output_dim=latent_dim, dropout_rate=0.4, eeg_dim=64, filters=(64,) * number_conv_layers,
+                           kernels=(32,) * number_conv_layers, dilation_rate=1, input_channels=64, time_dimension=window_length,
+                           normalization_fn='layer_norm', activation_fn='leaky_relu')
+    # same outcome as the reference for names it never constructs: `eeg` is unbound (:100)
+    raise UnboundLocalError(f"eeg encoder '{eeg_encoder}' is outside the B200 hot path (SURVEY §2.1 #9)")
+
+
+def load_speech_encoder(speech_encoder, units_lstm, padding, spatial_filters, number_conv_layers, window_length,
+                        stride_temporal, speech_dimension):
+    """train_clip_final.py:102-130 for the encoders on the hot path."""
+    if speech_encoder == 'smallConv':
+        return SpeechSmallConv(output_dim=_latent_dim_global, ks_temporal=16, dropout_rate=0.4, speech_dim=speech_dimension,
+                               time_dimension=window_length)
+    if speech_encoder == 'convLSTM':
+        return EEGConvLSTM(units_lstm=128, output_dim=_latent_dim_global, dropout_rate=0.4, eeg_dim=speech_dimension,
+                           filters=(64,) * number_conv_layers, kernels=(32,) * number_conv_layers, dilation_rate=1,
+                           input_channels=speech_dimension, time_dimension=window_length, normalization_fn='layer_norm',
+                           activation_fn='leaky_relu')
+    raise UnboundLocalError(f"speech encoder '{speech_encoder}' is outside the B200 hot path (SURVEY §2.1 #8)")
+
+
+def speech_dimension_of(stimulus_features):
+    """train_clip_final.py:292-300."""
+    if stimulus_features == 'mel':
+        return 28, 64
+    if stimulus_features == 'env':
+        return 1, 8
+    if 'wav2vec' in stimulus_features:
+        return 1024, 128
+    raise ValueError(stimulus_features)
+
+
+def build_model(args, window_length, bank_size, device):
+    """Model construction of train_clip_final.py:338-399 (clip_sim_no_latent_proj branch)."""
+    global _latent_dim_global
+    _latent_dim_global = args.latent_dim
+    speech_dim, spatial_filters = speech_dimension_of(args.stimulus_features)
+    eeg = load_eeg_encoder(args.eeg_encoder, args.lstm_units, 'valid', spatial_filters, args.number_conv_layers, window_length,
+                           args.latent_dim, args.attention_depth)
+    speech = load_speech_encoder(args.speech_encoder, args.lstm_units, 'valid', spatial_filters, args.number_conv_layers,
+                                 window_length, 3, speech_dim)
+    if args.model_arch != 'clip_sim_no_latent_proj':
+        raise NameError(f"model_arch '{args.model_arch}' is outside the B200 hot path (SURVEY §2.1 #7)")
+    bank = memoryBank(bank_size=bank_size, dim=speech.get_output_dim(window_length), momentum=args.momentum_membank,
+                      device=device) if bank_size else None
+    model = CLIPSimNoLatentProj(eeg, speech, bank, temperature=args.temperature, window_length=window_length,
+                                lambda_clip=args.lambda_clip_loss, lambda_average=args.lambda_sim_loss)
+    return model.to(device)
+
+
+def train_step(model, optimizer, eeg, speech, ids, use_total=True, group=None):
+    """One iteration of the reference hot loop (train_clip_final.py:484-492).
+
+    Order is the reference's: forward, zero_grad, backward, step.  Under a data-parallel ``group`` gradients are
+    SUM-all-reduced (one collective on the optimizer's flat arena) before the step.
+    """
+    loss_ce, loss_avg, loss_total = model(eeg, speech, ids)
+    optimizer.zero_grad()
+    (loss_total if use_total else loss_ce).backward()
+    if group is not None:
+        flats = optimizer.flat_grads() if hasattr(optimizer, "flat_grads") else [None]
+        for f in flats:
+            allreduce_gradients(model.parameters(), group, flat=f)
+    optimizer.step()
+    return loss_ce, loss_avg, loss_total
+
+
+class SyntheticBatches:
+    """Seeded stand-in for EEGDatasetSimdata (dataset_loader.py:392-422): yields (eeg, [speech], ids, subs)."""
+
+    def __init__(self, n_batches, batch_size, window_length, speech_dim, seed=0, n_segments=10000):
+        self.n, self.b, self.T, self.F, self.seed, self.n_segments = n_batches, batch_size, window_length, speech_dim, seed, n_segments
+
+    def get_number_of_stimuli_segments(self):
+        return self.n_segments
+
+    def __iter__(self):
+        g = torch.Generator().manual_seed(self.seed)
+        for _ in range(self.n):
+            eeg = torch.randn(self.b, self.T, 64, generator=g)
+            speech = torch.randn(self.b, self.T, self.F, generator=g)
+            ids = torch.randperm(self.n_segments, generator=g)[:self.b] + 1
+            yield eeg, [speech], ids, torch.zeros(self.b, dtype=torch.int64)
+
+
+def printf(s, file):
+    print(s)
+    with open(file, 'a') as f:
+        f.write(s + '\n')
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    if args.math:
+        L.set_default_math(args.math)
+    if not torch.cuda.is_available():
+        raise L.EegclipError("train_clip_final (B200): no CUDA device; this implementation has no CPU path")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        group = dist.group.WORLD
+    window_length = args.window_length
+    speech_dim, _ = speech_dimension_of(args.stimulus_features)
+    if args.data_dir != "synthetic":
+        raise L.EegclipError("only --data_dir synthetic is wired here; dataset plumbing is the reference's own (out of scope)")
+    train_data = SyntheticBatches(args.synthetic_batches, args.batch_size, window_length, speech_dim, seed=rank)
+    val_data = SyntheticBatches(max(1, args.synthetic_batches // 4), args.batch_size, window_length, speech_dim, seed=1000 + rank)
+    model = build_model(args, window_length, train_data.get_number_of_stimuli_segments(), device)
+    model.shard_group = group
+    broadcast_parameters(model, group)
+    if args.optimizer != 'adamw':
+        raise L.EegclipError("only --optimizer adamw is on the B200 path (reference default)")
+    opt = AdamW(model.parameters(), betas=(args.beta1, args.beta2), amsgrad=args.use_amsgrad == 'yes',
+                weight_decay=args.weight_decay, lr=args.learning_rate)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=args.step_size_scheduler, gamma=0.1) if args.lr_scheduler == 'step' else None
+    results = os.path.join(args.results_folder, f"results_{args.model_arch}_eeg_{args.eeg_encoder}_speech_{args.speech_encoder}_date_"
+                           f"{time.strftime('%m-%d-%H-%M-%S')}")
+    ckpt_dir = os.path.join(results, 'checkpoints')
+    file_loss = os.path.join(results, 'loss.txt')
+    if rank == 0:
+        os.makedirs(ckpt_dir, exist_ok=True)
+        with open(os.path.join(results, 'args.txt'), 'w') as f:
+            json.dump(args.__dict__, f, indent=2)
+    best_loss, best_epoch = float('inf'), 0
+    for epoch in range(args.epochs):
+        if epoch > best_epoch + args.patience and epoch > args.warmup_epochs:
+            break
+        model.train()
+        for batch, data in enumerate(train_data):
+            eeg = data[0].to(device, dtype=torch.float, non_blocking=True)
+            speech = data[1][0].to(device, dtype=torch.float, non_blocking=True)
+            ids = data[2].to(device, dtype=torch.int64)
+            loss_ce, loss_avg, _ = train_step(model, opt, eeg, speech, ids, use_total=epoch >= args.warmup_epochs, group=group)
+            if batch % 100 == 0 and rank == 0:
+                printf(f'train epoch {epoch} batch {batch} loss_ce  {loss_ce.item()} loss average eeg {loss_avg.item()}', file_loss)
+        if sched is not None:
+            sched.step()
+        model.eval()
+        ce = []
+        with torch.no_grad():
+            for data in val_data:
+                l_ce, _, _ = model(data[0].to(device), data[1][0].to(device), data[2].to(device, dtype=torch.int64))
+                ce.append(l_ce)
+        mean_ce = torch.stack(ce).mean().item()
+        if rank == 0:
+            printf(f'validation epoch {epoch}: mean loss ce : {mean_ce}', file_loss)
+            if mean_ce < best_loss:
+                torch.save(model.state_dict(), os.path.join(ckpt_dir, 'model.ckpt'))
+        if mean_ce < best_loss:
+            best_loss, best_epoch = mean_ce, epoch
+    if world > 1:
+        dist.destroy_process_group()
+    return best_loss
+
+
+if __name__ == '__main__':
+    main()
