@@ -34,6 +34,13 @@ def cm(pkg):
 DEV = "cuda"
 
 
+def _lstm_train(model):
+    """cuDNN refuses RNN backward in eval mode; the LSTMs have no dropout, so train() changes nothing numerically."""
+    for m in model.modules():
+        if isinstance(m, torch.nn.LSTM):
+            m.train()
+
+
 def _grads_ok(model, gdig, tol, prefix=""):
     floor = 1e-4 * global_grad_norm(gdig)
     for k, p in model.named_parameters():
@@ -156,6 +163,7 @@ def test_speech_golden(cm, golden, name):
                                input_channels=1024, time_dimension=T)
         model.load_state_dict(synth.make_state_dict(synth.conv_lstm_shapes(T), g["seed"]))
     model.to(DEV).eval()
+    _lstm_train(model)
     x = synth.randn(g["seed"] + 1, g["B"], T, 1024).to(DEV).requires_grad_(True)
     w = synth.randn(g["seed"] + 2, g["B"], T, 8).to(DEV)
     y = model(x)
@@ -177,6 +185,7 @@ def test_full_model_golden(cm, golden):
     model = cm.CLIPSimNoLatentProj(eeg_m, sp_m, mb, temperature=0.075, window_length=T, lambda_clip=1, lambda_average=0.0).to(DEV)
     mb.memory.copy_(synth.randn(g["seed"] + 5, g["bank"] + 1, T * 8).abs().to(DEV))
     model.eval()
+    _lstm_train(model)
     l_ce, l_avg, l_tot = model(synth.randn(g["seed"] + 10, B, T, 64).to(DEV), synth.randn(g["seed"] + 11, B, T, 1024).to(DEV),
                                torch.arange(1, B + 1, device=DEV))
     assert abs(float(l_ce) - g["loss_ce"]) <= 1e-5 * max(1.0, abs(g["loss_ce"]))
@@ -243,6 +252,33 @@ def test_mm_decisions_golden(cm, golden):
     for sub in g["top_x"]:
         assert np.allclose(ev_top[sub], g["top_x"][sub], atol=1e-9), sub                  # top-x curves identical
         check_digest(torch.tensor(ev_top_logits[sub]["logits"]), g["bank_logits_digest"][sub], 1e-3, "bank logits")
+
+
+@pytest.mark.parametrize("T,B", [(192, 3), (320, 5), (64, 2)])
+@pytest.mark.parametrize("math", ["bf16x3", "bf16"])
+def test_conv_tensor_core_vs_fp32(cm, pkg, T, B, math):
+    """tcgen05 implicit-GEMM conv (forward, dgrad, wgrad) against the exact-fp32 CUDA-core path, same inputs."""
+    from transformer_clip_eeg_b200 import _lib
+    blk = cm.BasicBlock(64, 64, kernel_size=64, time_dimension=T).to(DEV).eval()
+    with torch.no_grad():
+        blk.normalization.weight.add_(0.1 * torch.randn_like(blk.normalization.weight))
+    x = torch.randn(B, T, 64, device=DEV)
+    skip = torch.randn(B, T, 64, device=DEV)
+    w = torch.randn(B, T, 64, device=DEV)
+    res = {}
+    for m in ("fp32", math):
+        _lib.set_default_math(m)
+        try:
+            xx = x.clone().requires_grad_(True)
+            blk.zero_grad()
+            y = blk.forward_time_major(xx, skip)
+            (y * w).sum().backward()
+            res[m] = (y.detach(), xx.grad.detach(), blk.conv.weight.grad.detach().clone(), blk.conv.bias.grad.detach().clone())
+        finally:
+            _lib.set_default_math("bf16x3")
+    tol = 2e-4 if math == "bf16x3" else 3e-2
+    for a, b, name in zip(res[math], res["fp32"], ("y", "dx", "dw", "db")):
+        assert rel_err(a, b) < tol, (name, rel_err(a, b))
 
 
 def test_full_size_properties(cm):

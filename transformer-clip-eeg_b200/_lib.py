@@ -80,7 +80,7 @@ SIGNATURES = {
     "eegclip_infonce_workspace": (C.c_int, [_i32, _i32, _i32, _psz]),
     "eegclip_infonce_lse": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "eegclip_infonce_loss": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
-    "eegclip_infonce_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "eegclip_infonce_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "eegclip_membank_update": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _vp]),
     "eegclip_adamw_step": (C.c_int, [_vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _vp]),
     "eegclip_mm_rowdots": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),

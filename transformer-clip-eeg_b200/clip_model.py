@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib as L
-from .parallel import infonce_loss, ce_rows_loss
+from .parallel import infonce_loss, ce_rows_loss, l2_normalize
 
 __all__ = [
     "MultiHeadAttention", "ResidualAdd", "FeedForwardBlock", "TransformerEncoderBlock", "TransformerEncoder",
@@ -501,6 +501,7 @@ class CLIPSimNoLatentProj(nn.Module):
                 avg_val = ce_rows_loss(avg, En.detach(), self.temperature_eeg.detach())
             avg_loss = _ZeroGradLink.apply(avg_val, self.temperature_eeg)
         else:
-            avg_loss = ce_rows_loss(avg, En, self.temperature_eeg)
+            # gradient reaches the EEG tower through the normalised embeddings here (clip_model.py:934)
+            avg_loss = ce_rows_loss(avg, l2_normalize(E_raw), self.temperature_eeg)
         loss_total = self.lambda_clip * loss_ce + self.lambda_average * avg_loss
         return loss_ce.mean(), avg_loss.mean(), loss_total.mean()

@@ -1,18 +1,423 @@
-// tcgen05 implicit-GEMM Conv1d(64,64,k=64,'same') -- interface used by tower.cu.
+// tcgen05 implicit-GEMM for Conv1d(64 -> 64, k = 64, 'same') on time-major activations: forward, data gradient and
+// weight gradient (clip_model.py:237,245 -- 74 % of the EEG tower's FLOPs).
+//
+// Forward / data gradient (conv64_tc_kernel): one CTA per sample keeps the whole zero-padded activation tile
+// (T+63 rows x 64 channels, bf16 hi+lo planes, chunk-major -- see tc_common.cuh) resident in shared memory.  Tap k of
+// the convolution is the SAME tile read through a descriptor whose start address is shifted by k rows (+16 B), so the
+// K = 4096 contraction is 64 taps x 4 K16-steps of tcgen05.mma with no im2col and no re-staging.  Weights (16 KB per
+// tap, pre-split and pre-arranged in the UMMA layout by pack_conv_weights) stream through a 4-stage ring filled by
+// 1-D bulk async copies (TMA engine) signalled on mbarriers.  Accumulators for all time tiles (128,128,64 rows at
+// T=320) live in TMEM for the whole kernel; the epilogue reads them with tcgen05.ld, adds bias, applies the Philox
+// dropout mask and stores fp32.
+// The data gradient is the same kernel over the zero-padded output gradient with flipped / transposed weights.
+//
+// Weight gradient (wgrad64_tc_kernel): dW[co][ci][k] = sum_{b,t} dy[b,t,co] * u[b,t+k-31,ci].  Both operands are
+// MN-major views of the same chunk-major tiles (K = time); each CTA owns 16 taps (16 M=64 x N=64 accumulators =
+// all 512 TMEM columns, two per column block in the two 16-lane halves) and a slice of the batch, accumulating over its
+// samples in TMEM; per-CTA partials are reduced by wgrad_reduce_kernel.
+//
+// Arithmetic: NTERMS = 3 -> split-bf16 (hi*hi + hi*lo + lo*hi, fp32 accumulate, ~2^-16 relative, meets the 1e-3
+// gradient tolerance); NTERMS = 1 -> plain bf16 (fast mode, does not meet it).
 #pragma once
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace eegclip {
+namespace convtc {
 
-inline bool conv_tc_supported(int Cin, int Cout, int taps, int T) { (void)Cin; (void)Cout; (void)taps; (void)T; return false; }
-inline size_t conv_tc_scratch_bytes(int B, int T, int taps) { (void)B; (void)T; (void)taps; return 0; }
-inline int conv_tc_forward(int math, const float* xin, const float* skip_in, const float* w, const float* bias, float* y, int B, int T,
-                           int PL, const Drop& drop, float* scratch, cudaStream_t st) {
-  return EEGCLIP_ERR_UNSUPPORTED;
+constexpr int CH = 64;               // channels in == out
+constexpr int TAPS = 64;
+constexpr int NSTAGE = 4;            // weight ring depth
+constexpr int W_PLANE_BYTES = CH * CH * 2;      // 8 KB: one tap, one plane, [ci chunk][co][8]
+constexpr int W_TAP_BYTES = 2 * W_PLANE_BYTES;  // hi + lo
+constexpr int WG_TAPS = 16;          // taps per weight-gradient CTA
+constexpr int WG_MAX_GROUPS = 37;    // 4 tap groups x 37 sample groups = 148 CTAs
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing: fp32 W[co][ci][k]  ->  bf16 hi/lo, per tap [plane][k-chunk][n][8]
+//   mode 0 (forward) : n = co, contraction index = ci, tap = k
+//   mode 1 (dgrad)   : n = ci, contraction index = co, tap k' holds W[..][..][63-k']
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int mode) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over taps * 8 chunks * 64 n
+  if (i >= TAPS * 8 * CH) return;
+  int n = i & 63, ch = (i >> 6) & 7, tap = i >> 9;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    int kk = ch * 8 + e;  // contraction index
+    v[e] = mode == 0 ? W[((long)n * CH + kk) * TAPS + tap] : W[((long)kk * CH + n) * TAPS + (TAPS - 1 - tap)];
+  }
+  uint4 hi, lo;
+  tc::split8(v, hi, lo);
+  uint8_t* base = out + (long)tap * W_TAP_BYTES + ch * (CH * 16) + n * 16;
+  *reinterpret_cast<uint4*>(base) = hi;
+  *reinterpret_cast<uint4*>(base + W_PLANE_BYTES) = lo;
 }
+
+struct ConvTcArgs {
+  const float* src;       // (B, src_rows, 64) fp32
+  const float* skip;      // optional addend, same shape as src
+  const uint8_t* wpacked; // TAPS * W_TAP_BYTES
+  const float* bias;      // optional
+  float* out;             // (B, T, 64)
+  int T;                  // output rows
+  int src_rows;           // valid source rows
+  int row_off;            // smem row r holds src row r - row_off (zero outside)
+  Drop drop;
+};
+
+__host__ __device__ inline uint32_t conv_smem_bytes(int T) {
+  uint32_t TP = T + TAPS - 1;
+  return 2u * 8u * TP * 16u + NSTAGE * W_TAP_BYTES + 128;
+}
+
+template <int NTERMS>
+__global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x;
+  const int T = a.T, TP = T + TAPS - 1;
+  const uint32_t CS = (uint32_t)TP * 16u;   // chunk stride (bytes)
+  const uint32_t PS = 8u * CS;              // plane stride
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 2u * PS;             // 2*PS = 256*TP: 128-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NSTAGE * W_TAP_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + NSTAGE;
+  uint64_t* accfull = bars + 2 * NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
+
+  const int ntiles = (T + 127) >> 7;
+  const bool last64 = (T & 127) != 0;       // T % 128 == 64 -> last tile has M = 64
+  uint32_t ncols = 64;
+  while (ncols < (uint32_t)ntiles * 64u) ncols <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(accfull, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, ncols);
+
+  // ---- stage the activation tile: fp32 (+skip) -> bf16 hi/lo, chunk-major, zero padded ----
+  {
+    const float* sb = a.src + (long)b * a.src_rows * CH;
+    const float* kb = a.skip ? a.skip + (long)b * a.src_rows * CH : nullptr;
+    for (int idx = tid; idx < TP * 8; idx += 256) {
+      const int r = idx >> 3, ch = idx & 7;
+      const int t = r - a.row_off;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (t >= 0 && t < a.src_rows) {
+        const float4* p = reinterpret_cast<const float4*>(sb + (long)t * CH + ch * 8);
+        float4 x0 = p[0], x1 = p[1];
+        if (kb) {
+          const float4* q = reinterpret_cast<const float4*>(kb + (long)t * CH + ch * 8);
+          float4 y0 = q[0], y1 = q[1];
+          x0.x += y0.x; x0.y += y0.y; x0.z += y0.z; x0.w += y0.w;
+          x1.x += y1.x; x1.y += y1.y; x1.z += y1.z; x1.w += y1.w;
+        }
+        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+      }
+      uint4 hi, lo;
+      tc::split8(v, hi, lo);
+      uint8_t* d = sA + ch * CS + r * 16;
+      *reinterpret_cast<uint4*>(d) = hi;
+      if (NTERMS > 1) *reinterpret_cast<uint4*>(d + PS) = lo;
+    }
+  }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===== weight producer: one 1-D bulk copy per tap into the ring =====
+    const uint32_t bytes = NTERMS > 1 ? W_TAP_BYTES : W_PLANE_BYTES;
+    for (int tap = 0; tap < TAPS; ++tap) {
+      const int s = tap % NSTAGE;
+      const uint32_t ph = (tap / NSTAGE) & 1;
+      tc::mbar_wait(&empty[s], ph ^ 1);
+      tc::mbar_expect_tx(&full[s], bytes);
+      tc::bulk_g2s(sB + s * W_TAP_BYTES, a.wpacked + (long)tap * W_TAP_BYTES, bytes, &full[s]);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
+    const uint32_t id128 = tc::idesc_bf16(128, CH, 0, 0), id64 = tc::idesc_bf16(64, CH, 0, 0);
+    for (int tap = 0; tap < TAPS; ++tap) {
+      const int s = tap % NSTAGE;
+      const uint32_t ph = (tap / NSTAGE) & 1;
+      tc::mbar_wait(&full[s], ph);
+      tc::tc_fence_after();
+      const uint32_t wb = sB_u + s * W_TAP_BYTES;
+      for (int tile = 0; tile < ntiles; ++tile) {
+        const uint32_t idesc = (last64 && tile == ntiles - 1) ? id64 : id128;
+        const uint32_t d = tmem + tile * 64;
+        const uint32_t arow = sA_u + (uint32_t)(tile * 128 + tap) * 16u;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+          for (int term = 0; term < NTERMS; ++term) {
+            const uint32_t pa = (term == 2) ? PS : 0u;              // hi*hi, hi*lo, lo*hi
+            const uint32_t pb = (term == 1) ? W_PLANE_BYTES : 0u;
+            const uint64_t ad = tc::smem_desc(arow + pa + (2 * ks) * CS, CS, 128);
+            const uint64_t bd = tc::smem_desc(wb + pb + (2 * ks) * (CH * 16), CH * 16, 128);
+            tc::mma_bf16(d, ad, bd, idesc, (tap | ks | term) != 0);
+          }
+        }
+      }
+      tc::tc_commit(&empty[s]);
+    }
+    tc::tc_commit(accfull);
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> bias / dropout -> global =====
+    const int q = warp - 4;  // TMEM lane quarter of this warp
+    tc::mbar_wait(accfull, 0);
+    tc::tc_fence_after();
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const bool m64 = last64 && tile == ntiles - 1;
+      const int row = m64 ? tile * 128 + q * 16 + lane : tile * 128 + q * 32 + lane;
+      const bool valid = m64 ? (lane < 16) : true;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + tile * 64;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tc::tmem_ld32(taddr + half * 32, v);
+        if (valid && row < T) {
+          float* o = a.out + ((long)b * T + row) * CH + half * 32;
+          const uint64_t didx = ((uint64_t)b * T + row) * CH + half * 32;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float4 r = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            if (a.bias) {
+              float4 bb = *reinterpret_cast<const float4*>(a.bias + half * 32 + c);
+              r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+            }
+            float4 m = drop_mult4(a.drop, didx + c);
+            r.x *= m.x; r.y *= m.y; r.z *= m.z; r.w *= m.w;
+            *reinterpret_cast<float4*>(o + c) = r;
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient
+// ------------------------------------------------------------------------------------------------
+struct WgradTcArgs {
+  const float* xin;     // (B,T,64) conv input
+  const float* skip;    // optional addend
+  const float* dypad;   // (B,TP,64) zero-padded output gradient, valid rows [PLb, PLb+T)
+  float* partial;       // [groups][TAPS][64 co][64 ci]
+  int B, T, PL, PLb, groups;
+};
+
+__host__ __device__ inline uint32_t wgrad_smem_bytes(int T) {
+  return 2u * 8u * (uint32_t)(T + WG_TAPS - 1) * 16u + 2u * 8u * (uint32_t)T * 16u + 128;
+}
+
+template <int NTERMS>
+__global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tg = blockIdx.x, grp = blockIdx.y;
+  const int T = a.T, TU = T + WG_TAPS - 1;
+  const int k0 = tg * WG_TAPS;
+  const uint32_t CSU = (uint32_t)TU * 16u, PSU = 8u * CSU;
+  const uint32_t CSD = (uint32_t)T * 16u, PSD = 8u * CSD;
+  uint8_t* sU = smem;
+  uint8_t* sD = smem + 2u * PSU;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sD + 2u * PSD);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t idesc = tc::idesc_bf16(64, CH, 1, 1);   // both operands MN-major (K = time)
+  uint32_t phase = 0;
+  bool first = true;
+  for (int b = grp; b < a.B; b += a.groups) {
+    // ---- stage u rows [k0 - PL, k0 - PL + TU) of the padded input and the T rows of dy ----
+    const float* xb = a.xin + (long)b * T * CH;
+    const float* kb = a.skip ? a.skip + (long)b * T * CH : nullptr;
+    for (int idx = tid; idx < TU * 8; idx += 256) {
+      const int r = idx >> 3, ch = idx & 7;
+      const int t = r + k0 - a.PL;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (t >= 0 && t < T) {
+        const float4* p = reinterpret_cast<const float4*>(xb + (long)t * CH + ch * 8);
+        float4 x0 = p[0], x1 = p[1];
+        if (kb) {
+          const float4* q = reinterpret_cast<const float4*>(kb + (long)t * CH + ch * 8);
+          float4 y0 = q[0], y1 = q[1];
+          x0.x += y0.x; x0.y += y0.y; x0.z += y0.z; x0.w += y0.w;
+          x1.x += y1.x; x1.y += y1.y; x1.z += y1.z; x1.w += y1.w;
+        }
+        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+      }
+      uint4 hi, lo;
+      tc::split8(v, hi, lo);
+      uint8_t* d = sU + ch * CSU + r * 16;
+      *reinterpret_cast<uint4*>(d) = hi;
+      if (NTERMS > 1) *reinterpret_cast<uint4*>(d + PSU) = lo;
+    }
+    const float* db = a.dypad + ((long)b * (T + TAPS - 1) + a.PLb) * CH;
+    for (int idx = tid; idx < T * 8; idx += 256) {
+      const int r = idx >> 3, ch = idx & 7;
+      const float4* p = reinterpret_cast<const float4*>(db + (long)r * CH + ch * 8);
+      float4 x0 = p[0], x1 = p[1];
+      float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      uint4 hi, lo;
+      tc::split8(v, hi, lo);
+      uint8_t* d = sD + ch * CSD + r * 16;
+      *reinterpret_cast<uint4*>(d) = hi;
+      if (NTERMS > 1) *reinterpret_cast<uint4*>(d + PSD) = lo;
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (tid == 0) {
+      const uint32_t sU_u = tc::smem_u32(sU), sD_u = tc::smem_u32(sD);
+      const int ksteps = T >> 4;
+      for (int j = 0; j < WG_TAPS; ++j) {
+        const uint32_t d = tmem + (uint32_t)(j >> 1) * 64u + ((uint32_t)((j & 1) * 16) << 16);
+        for (int ks = 0; ks < ksteps; ++ks) {
+#pragma unroll
+          for (int term = 0; term < NTERMS; ++term) {
+            const uint32_t pa = (term == 2) ? PSD : 0u;   // A = dy, B = u : hi*hi, hi*lo, lo*hi
+            const uint32_t pb = (term == 1) ? PSU : 0u;
+            const uint64_t ad = tc::smem_desc(sD_u + pa + (uint32_t)(ks * 16) * 16u, 128, CSD);
+            const uint64_t bd = tc::smem_desc(sU_u + pb + (uint32_t)(j + ks * 16) * 16u, 128, CSU);
+            tc::mma_bf16(d, ad, bd, idesc, !(first && ks == 0 && term == 0));
+          }
+        }
+      }
+      tc::tc_commit(bar);
+    }
+    tc::mbar_wait(bar, phase);   // all MMAs that read this sample's tiles are done
+    tc::tc_fence_after();
+    phase ^= 1;
+    first = false;
+    __syncthreads();
+  }
+  // ---- epilogue: 16 accumulators -> partial[grp][tap][co][ci] ----
+  if (warp >= 4 && !first) {
+    const int q = warp - 4;
+    const int co = q * 16 + (lane & 15);
+    for (int cb = 0; cb < 8; ++cb) {
+      const int tap = k0 + cb * 2 + (lane >> 4);
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + cb * 64;
+      float* o = a.partial + (((long)grp * TAPS + tap) * CH + co) * CH;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tc::tmem_ld32(taddr + half * 32, v);
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(o + half * 32 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem, 512);
+}
+
+// dW[co][ci][k] = sum_g partial[g][k][co][ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int groups) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over k*4096 + co*64 + ci
+  if (i >= TAPS * CH * CH) return;
+  float s = 0.f;
+  for (int g = 0; g < groups; ++g) s += partial[(long)g * TAPS * CH * CH + i];
+  int ci = i & 63, co = (i >> 6) & 63, k = i >> 12;
+  dW[((long)co * CH + ci) * TAPS + k] = s;
+}
+
+}  // namespace convtc
+
+// ------------------------------------------------------------------------------------------------
+// Interface used by tower.cu
+// ------------------------------------------------------------------------------------------------
+inline bool conv_tc_supported(int Cin, int Cout, int taps, int T) {
+  return Cin == 64 && Cout == 64 && taps == 64 && T >= 64 && (T % 64) == 0 && T <= 512;
+}
+
+// scratch: packed weights (1 MB) + weight-gradient partials (groups MB)
+inline size_t conv_tc_scratch_bytes(int B, int T, int taps) {
+  (void)T;
+  if (taps != 64) return 0;
+  int groups = B < convtc::WG_MAX_GROUPS ? B : convtc::WG_MAX_GROUPS;
+  return (size_t)convtc::TAPS * convtc::W_TAP_BYTES + (size_t)groups * 64 * 64 * 64 * sizeof(float) + 256;
+}
+
+template <int NTERMS>
+inline int conv_tc_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
+  static bool configured = false;
+  uint32_t smem = convtc::conv_smem_bytes(a.T);
+  if (!configured) {
+    if (cudaFuncSetAttribute(convtc::conv64_tc_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return EEGCLIP_ERR_CUDA;
+    configured = true;
+  }
+  convtc::conv64_tc_kernel<NTERMS><<<B, 256, smem, st>>>(a);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+inline int conv_tc_forward(int math, const float* xin, const float* skip_in, const float* w, const float* bias, float* y, int B, int T,
+                           int PL, const Drop& drop, void* scratch, cudaStream_t st) {
+  uint8_t* wp = (uint8_t*)scratch;
+  convtc::pack_conv_weights_kernel<<<(convtc::TAPS * 8 * 64 + 255) / 256, 256, 0, st>>>(w, wp, 0);
+  LAUNCH_CHECK();
+  convtc::ConvTcArgs a;
+  a.src = xin; a.skip = skip_in; a.wpacked = wp; a.bias = bias; a.out = y; a.T = T; a.src_rows = T; a.row_off = PL; a.drop = drop;
+  return math == EEGCLIP_MATH_BF16 ? conv_tc_launch<1>(a, B, st) : conv_tc_launch<3>(a, B, st);
+}
+
+template <int NTERMS>
+inline int wgrad_tc_launch(const convtc::WgradTcArgs& a, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(convtc::wgrad64_tc_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return EEGCLIP_ERR_CUDA;
+    configured = true;
+  }
+  dim3 grid(convtc::TAPS / convtc::WG_TAPS, a.groups);
+  convtc::wgrad64_tc_kernel<NTERMS><<<grid, 256, convtc::wgrad_smem_bytes(a.T), st>>>(a);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+// du = dgrad(dypad, w) ; dw = wgrad(dypad, xin + skip_in)
 inline int conv_tc_backward(int math, const float* xin, const float* skip_in, const float* w, const float* dypad, int PLb, float* du,
-                            float* dw, int B, int T, float* scratch, float* wtmp, cudaStream_t st) {
-  return EEGCLIP_ERR_UNSUPPORTED;
+                            float* dw, int B, int T, void* scratch, cudaStream_t st) {
+  uint8_t* wp = (uint8_t*)scratch;
+  float* partial = (float*)(wp + (size_t)convtc::TAPS * convtc::W_TAP_BYTES);
+  const int TP = T + convtc::TAPS - 1;
+  convtc::pack_conv_weights_kernel<<<(convtc::TAPS * 8 * 64 + 255) / 256, 256, 0, st>>>(w, wp, 1);
+  LAUNCH_CHECK();
+  convtc::ConvTcArgs a;
+  a.src = dypad; a.skip = nullptr; a.wpacked = wp; a.bias = nullptr; a.out = du; a.T = T; a.src_rows = TP; a.row_off = 0;
+  a.drop = make_drop(0, 0, 0, 0.f, 0);
+  int rc = math == EEGCLIP_MATH_BF16 ? conv_tc_launch<1>(a, B, st) : conv_tc_launch<3>(a, B, st);
+  if (rc != EEGCLIP_OK) return rc;
+  convtc::WgradTcArgs g;
+  g.xin = xin; g.skip = skip_in; g.dypad = dypad; g.partial = partial; g.B = B; g.T = T; g.PL = convtc::TAPS - 1 - PLb; g.PLb = PLb;
+  g.groups = B < convtc::WG_MAX_GROUPS ? B : convtc::WG_MAX_GROUPS;
+  rc = math == EEGCLIP_MATH_BF16 ? wgrad_tc_launch<1>(g, st) : wgrad_tc_launch<3>(g, st);
+  if (rc != EEGCLIP_OK) return rc;
+  convtc::wgrad_reduce_kernel<<<(convtc::TAPS * 64 * 64 + 255) / 256, 256, 0, st>>>(partial, dw, g.groups);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
 }
 
 }  // namespace eegclip

@@ -61,6 +61,7 @@ SaveLayout save_layout(const eegclip_tower_desc& d) {
 
 struct Scratch {
   float *upad, *dypad, *h, *f, *dfpre, *dqkv, *d_o, *dg, *dza, *dzb, *dzc, *deeg, *wtmp;
+  void* tc;
   size_t total;
 };
 
@@ -82,6 +83,7 @@ Scratch scratch_layout(const eegclip_tower_desc& d, float* base) {
   s.dzc = take(n * C);
   s.deeg = take(n * C);
   s.wtmp = take((size_t)C * C * d.taps);
+  s.tc = take(conv_tc_scratch_bytes(d.B, d.T, d.taps) / sizeof(float) + 64);
   s.total = o;
   return s;
 }
@@ -186,11 +188,11 @@ int conv_wgrad_f32(const float* dypad, int PLb, const float* upad, float* tmp, i
 // BasicBlock forward on time-major data.  xin (+ skip_in) -> conv -> dropout -> LN([C,T]) -> act (+ skip_out)
 // -------------------------------------------------------------------------------------------------
 int conv_block_fwd(int math, const float* xin, const float* skip_in, const ConvP& p, const float* skip_out, float* y, float* stats,
-                   float* out, float* upad, int B, int T, int Cin, int Cout, int taps, int act, const Drop& drop,
+                   float* out, float* upad, void* tcs, int B, int T, int Cin, int Cout, int taps, int act, const Drop& drop,
                    cudaStream_t st) {
   const int PL = (taps - 1) / 2;
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
-    TRY(conv_tc_forward(math, xin, skip_in, p.w, p.b, y, B, T, PL, drop, upad, st));
+    TRY(conv_tc_forward(math, xin, skip_in, p.w, p.b, y, B, T, PL, drop, tcs, st));
   } else {
     TRY(pad_add(xin, skip_in, upad, B, T, Cin, PL, taps, st));
     TRY(conv_fwd_f32(upad, p.w, p.b, y, B, T, Cin, Cout, taps, drop, st));
@@ -202,14 +204,14 @@ int conv_block_fwd(int math, const float* xin, const float* skip_in, const ConvP
 // Backward of the block: dout is the gradient w.r.t. `out` (excluding skip_out's own path).
 // Produces du (gradient w.r.t. xin + skip_in) and fills the four parameter gradients (pre-zeroed).
 int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP& p, const ConvG& gr, const float* y,
-                   const float* stats, const float* dout, float* du, float* upad, float* dypad, float* wtmp, int B, int T,
+                   const float* stats, const float* dout, float* du, float* upad, float* dypad, float* wtmp, void* tcs, int B, int T,
                    int Cin, int Cout, int taps, int act, const Drop& drop, cudaStream_t st) {
   const int PL = (taps - 1) / 2, PLb = taps - 1 - PL, TP = T + taps - 1;
   CUDA_TRY(cudaMemsetAsync(dypad, 0, (size_t)B * TP * Cout * sizeof(float), st));
   TRY(ln_ct_act_bwd(dout, y, stats, p.g, p.be, dypad, gr.g, gr.be, B, T, Cout, PLb, taps, act, drop, st));
   TRY(colsum(dypad, gr.b, (long)B * TP, Cout, Cout, st));
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
-    TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, PLb, du, gr.w, B, T, upad, wtmp, st));
+    TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, PLb, du, gr.w, B, T, tcs, st));
   } else {
     TRY(pad_add(xin, skip_in, upad, B, T, Cin, PL, taps, st));
     CUDA_TRY(cudaMemsetAsync(wtmp, 0, (size_t)Cout * Cin * taps * sizeof(float), st));
@@ -304,7 +306,7 @@ extern "C" {
 int eegclip_tower_workspace(const eegclip_tower_desc* d, size_t* save_bytes, size_t* scratch_bytes) {
   if (!desc_ok(d)) return EEGCLIP_ERR_ARG;
   if (save_bytes) *save_bytes = save_layout(*d).total * sizeof(float);
-  if (scratch_bytes) *scratch_bytes = scratch_layout(*d, nullptr).total * sizeof(float) + conv_tc_scratch_bytes(d->B, d->T, d->taps);
+  if (scratch_bytes) *scratch_bytes = scratch_layout(*d, nullptr).total * sizeof(float);
   return EEGCLIP_OK;
 }
 
@@ -328,7 +330,7 @@ int eegclip_tower_forward(const eegclip_tower_desc* dp, const float* const* para
       float* cb = save + L.conv0 + L.conv_stride * i;
       const bool last = (i == d.depth - 1);
       // conv input is x + eeg_x (clip_model.py:459); transformer input adds eeg_x again unless last (:465-469)
-      TRY(conv_block_fwd(d.math, xin, eegx, cp, last ? nullptr : eegx, cb + L.c_y, cb + L.c_stats, cb + L.c_out, w.upad, d.B, d.T, C,
+      TRY(conv_block_fwd(d.math, xin, eegx, cp, last ? nullptr : eegx, cb + L.c_y, cb + L.c_stats, cb + L.c_out, w.upad, w.tc, d.B, d.T, C,
                          C, d.taps, 0, make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st));
       XfSave xs = xf_save(save, L, i);
       TRY(xf_block_fwd(d, i, xf_at<XfP>(params, d.n_conv, i), cb + L.c_out, xs, w, st));
@@ -339,7 +341,7 @@ int eegclip_tower_forward(const eegclip_tower_desc* dp, const float* const* para
       ConvP cp = conv_at<ConvP>(params, i);
       float* cb = save + L.conv0 + L.conv_stride * i;
       const bool last = (i == d.n_conv - 1);  // no input skip in the last conv block (clip_model.py:385-390)
-      TRY(conv_block_fwd(d.math, xin, last ? nullptr : eegx, cp, nullptr, cb + L.c_y, cb + L.c_stats, cb + L.c_out, w.upad, d.B, d.T,
+      TRY(conv_block_fwd(d.math, xin, last ? nullptr : eegx, cp, nullptr, cb + L.c_y, cb + L.c_stats, cb + L.c_out, w.upad, w.tc, d.B, d.T,
                          C, C, d.taps, 0, make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st));
       xin = cb + L.c_out;
     }
@@ -390,7 +392,7 @@ int eegclip_tower_backward(const eegclip_tower_desc* dp, const float* const* par
       if (!last) TRY(add_f32(w.deeg, dz2, w.deeg, n * C, st));  // skip into the transformer input
       const float* xin = (i == 0) ? eegx : xf_save(save, L, i - 1).zout;
       TRY(conv_block_bwd(d.math, xin, eegx, conv_at<ConvP>(params, i), conv_at<ConvG>(grads, i), cb + L.c_y, cb + L.c_stats, dz2, dz,
-                         w.upad, w.dypad, w.wtmp, d.B, d.T, C, C, d.taps, 0, make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st));
+                         w.upad, w.dypad, w.wtmp, w.tc, d.B, d.T, C, C, d.taps, 0, make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st));
       TRY(add_f32(w.deeg, dz, w.deeg, n * C, st));              // skip into the conv input
     }
     TRY(add_f32(w.deeg, dz, w.deeg, n * C, st));                // x_0 == eeg_x itself
@@ -407,7 +409,7 @@ int eegclip_tower_backward(const eegclip_tower_desc* dp, const float* const* par
       const bool last = (i == d.n_conv - 1);
       const float* xin = (i == 0) ? eegx : save + L.conv0 + L.conv_stride * (i - 1) + L.c_out;
       TRY(conv_block_bwd(d.math, xin, last ? nullptr : eegx, conv_at<ConvP>(params, i), conv_at<ConvG>(grads, i), cb + L.c_y,
-                         cb + L.c_stats, dz, dz2, w.upad, w.dypad, w.wtmp, d.B, d.T, C, C, d.taps, 0,
+                         cb + L.c_stats, dz, dz2, w.upad, w.dypad, w.wtmp, w.tc, d.B, d.T, C, C, d.taps, 0,
                          make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st));
       if (!last) TRY(add_f32(w.deeg, dz2, w.deeg, n * C, st));
       float* t = dz; dz = dz2; dz2 = t;
@@ -430,7 +432,7 @@ int eegclip_convblock_workspace(const eegclip_convblock_desc* d, size_t* save_by
   if (save_bytes) *save_bytes = (n * d->Cout + align_up((size_t)2 * d->B, 4)) * sizeof(float);
   if (scratch_bytes)
     *scratch_bytes = (align_up((size_t)d->B * TP * d->Cin, 64) + align_up((size_t)d->B * TP * d->Cout, 64) +
-                      align_up((size_t)d->Cout * d->Cin * d->taps, 64)) * sizeof(float) + conv_tc_scratch_bytes(d->B, d->T, d->taps);
+                      align_up((size_t)d->Cout * d->Cin * d->taps, 64)) * sizeof(float) + conv_tc_scratch_bytes(d->B, d->T, d->taps) + 256;
   return EEGCLIP_OK;
 }
 
@@ -443,8 +445,11 @@ int eegclip_convblock_forward(const eegclip_convblock_desc* d, const float* x, c
   float* y = (float*)save;
   float* stats = y + n * d->Cout;
   float* upad = (float*)scratch;
+  size_t TPf = d->T + d->taps - 1;
+  void* tcs = upad + align_up((size_t)d->B * TPf * d->Cin, 64) + align_up((size_t)d->B * TPf * d->Cout, 64) +
+              align_up((size_t)d->Cout * d->Cin * d->taps, 64);
   ConvP p{w, bias, gamma, beta};
-  return conv_block_fwd(d->math, x, skip_in, p, nullptr, y, stats, out, upad, d->B, d->T, d->Cin, d->Cout, d->taps, d->act,
+  return conv_block_fwd(d->math, x, skip_in, p, nullptr, y, stats, out, upad, tcs, d->B, d->T, d->Cin, d->Cout, d->taps, d->act,
                         make_drop(d->seed, d->layer, SITE_CONV, d->p_drop, d->train), (cudaStream_t)stream);
 }
 
@@ -460,12 +465,13 @@ int eegclip_convblock_backward(const eegclip_convblock_desc* d, const float* x, 
   float* upad = (float*)scratch;
   float* dypad = upad + align_up((size_t)d->B * TP * d->Cin, 64);
   float* wtmp = dypad + align_up((size_t)d->B * TP * d->Cout, 64);
+  void* tcs = wtmp + align_up((size_t)d->Cout * d->Cin * d->taps, 64);
   CUDA_TRY(cudaMemsetAsync(dbias, 0, d->Cout * sizeof(float), st));
   CUDA_TRY(cudaMemsetAsync(dgamma, 0, (size_t)d->Cout * d->T * sizeof(float), st));
   CUDA_TRY(cudaMemsetAsync(dbeta, 0, (size_t)d->Cout * d->T * sizeof(float), st));
   ConvP p{w, nullptr, gamma, beta};
   ConvG g{dw, dbias, dgamma, dbeta};
-  return conv_block_bwd(d->math, x, skip_in, p, g, y, stats, dout, dx, upad, dypad, wtmp, d->B, d->T, d->Cin, d->Cout, d->taps, d->act,
+  return conv_block_bwd(d->math, x, skip_in, p, g, y, stats, dout, dx, upad, dypad, wtmp, tcs, d->B, d->T, d->Cin, d->Cout, d->taps, d->act,
                         make_drop(d->seed, d->layer, SITE_CONV, d->p_drop, d->train), st);
 }
 

@@ -146,6 +146,25 @@ class _CERowsFn(torch.autograd.Function):
         return None, dEn, dtau.reshape(tau_shape), None
 
 
+class _L2NormFn(torch.autograd.Function):
+    """F.normalize(p=2, dim=1) with its backward (clip_model.py:913)."""
+
+    @staticmethod
+    def forward(ctx, x, ops):
+        xn, inv = ops.l2norm_fwd(x)
+        ctx.saved, ctx.ops = (xn, inv), ops
+        return xn
+
+    @staticmethod
+    def backward(ctx, dxn):
+        xn, inv = ctx.saved
+        return ctx.ops.l2norm_bwd(xn, inv, dxn.contiguous()), None
+
+
+def l2_normalize(x, ops=None):
+    return _L2NormFn.apply(x, ops or _CUDA_OPS)
+
+
 def infonce_loss(E_raw, S_raw, tau, group=None, return_normalized=False, ops=None):
     """Symmetric InfoNCE of clip_model.py:675-693 on raw (un-normalised) flattened embeddings (b,D).
 
