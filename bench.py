@@ -1,0 +1,287 @@
+"""Benchmark of the EEG-CLIP train step (BASELINE.json metric), one process per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference algorithm's CPU port (oracle/) on the host cores
+
+A step is the reference hot loop body (train_clip_final.py:484-492): forward of both towers, symmetric InfoNCE,
+zero_grad, backward, AdamW -- train mode (dropout on), default towers (EEGConformerInterleaved depth 10, convLSTM
+speech tower), 64-channel 64 Hz 5 s windows (T=320), wav2vec2-shaped speech features (1024), batch 256 per GPU.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "EEG-speech CLIP train samples/sec"
+UNIT = "samples/s"
+T_WIN, F_SPEECH, DEPTH = 320, 1024, 10
+CONV_FLOP_PER_SAMPLE = 2 * T_WIN * 64 * 64 * 64          # one Conv1d(64,64,k=64) pass over one window (fwd == dgrad == wgrad)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    p.add_argument("--batch", type=int, default=256, help="windows per GPU")
+    p.add_argument("--cpu_batch", type=int, default=8, help="windows per CPU-baseline step (bounded sample)")
+    p.add_argument("--math", type=str, default=None, choices=["fp32", "bf16x3", "bf16"])
+    p.add_argument("--no_cpu_baseline", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = max([int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline: the reference algorithm restated in oracle/ (the reference itself is Python and is not on the GPU box)
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_step_fn(batch):
+    from oracle import eegclip_oracle as O, synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {}
+    sd.update(synth.make_state_dict(synth.interleaved_shapes(DEPTH, T_WIN), 1, "eegModel."))
+    sd.update(synth.make_state_dict(synth.conv_lstm_shapes(T_WIN), 2, "speechModel."))
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    tau = torch.tensor(0.075, requires_grad=True)
+    tau_e = torch.tensor(0.075, requires_grad=True)
+    params = list(sd.values()) + [tau, tau_e]
+    opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.999), weight_decay=0.01)
+    mem = torch.rand(10001, T_WIN * 8)
+    drop = O.Drop(train=True, seed=0, native=True)   # torch's own dropout: the reference's actual cost (72 % bernoulli_)
+    eeg, sp = synth.randn(3, batch, T_WIN, 64), synth.randn(4, batch, T_WIN, F_SPEECH)
+    ids = torch.arange(1, batch + 1)
+
+    def step():
+        ef = O.eeg_conformer_interleaved(sd, eeg, DEPTH, drop, pre="eegModel.")
+        sf = O.eeg_conv_lstm(sd, sp, drop=drop, pre="speechModel.", fast_lstm=True)
+        l_ce, l_avg, l_tot = O.clip_sim_no_latent_proj(ef, sf, ids, mem, tau, tau_e, 1.0, 0.0)
+        opt.zero_grad()
+        l_tot.backward()
+        opt.step()
+        return float(l_ce)
+    return step
+
+
+def time_cpu_port(batch, steps, warmup):
+    step = cpu_port_step_fn(batch)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return batch / dt, dt * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, ms = time_cpu_port(args.cpu_batch, args.steps, max(args.warmup, 1))
+    cores = os.cpu_count() or 1
+    sample = f"{args.cpu_batch} windows per step (bounded sample of the batch-256 workload), train mode, fwd+bwd+AdamW"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.batch), "reference_arm": "CPU port of the reference algorithm (oracle/), "
+                   "torch CPU ops, all host threads; the Python reference itself is not present on the GPU box"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_name(batch):
+    return (f"full CLIP train step (fwd+bwd+AdamW, train mode): EEGConformerInterleaved depth {DEPTH} + convLSTM speech tower + "
+            f"CLIPSimNoLatentProj, 64-ch 64 Hz 5 s windows (T={T_WIN}), wav2vec2-shaped speech ({F_SPEECH}), batch {batch} per GPU")
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    import transformer_clip_eeg_b200 as pkg
+    from transformer_clip_eeg_b200 import _lib, train_clip_final as tcf
+    from transformer_clip_eeg_b200.optim import AdamW
+    from transformer_clip_eeg_b200.parallel import broadcast_parameters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback; use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    if args.math:
+        _lib.set_default_math(args.math)
+    lib = _lib.load()
+    B = args.batch
+    torch.manual_seed(0)
+    cli = tcf.build_parser().parse_args([])          # reference defaults: depth 10, convLSTM, latent 8, tau 0.075 ...
+    model = tcf.build_model(cli, T_WIN, 10000, dev)
+    model.shard_group = group
+    broadcast_parameters(model, group)
+    opt = AdamW(model.parameters(), betas=(cli.beta1, cli.beta2), weight_decay=cli.weight_decay, lr=cli.learning_rate)
+    model.train()
+
+    # synthetic inputs: NBUF distinct batches in pinned host memory (+ resident device copies for the kernel-side number)
+    NBUF = 2
+    g = torch.Generator().manual_seed(rank)
+    host = [(torch.randn(B, T_WIN, 64, generator=g).pin_memory(), torch.randn(B, T_WIN, F_SPEECH, generator=g).pin_memory(),
+             (torch.randperm(10000, generator=g)[:B] + 1).pin_memory()) for _ in range(NBUF)]
+    resident = [tuple(t.to(dev) for t in h) for h in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident(i):
+        eeg, sp, ids = resident[i % NBUF]
+        return tcf.train_step(model, opt, eeg, sp, ids, group=group)
+
+    def step_e2e(i):
+        eeg_h, sp_h, ids_h = host[i % NBUF]
+        eeg, sp, ids = eeg_h.to(dev, non_blocking=True), sp_h.to(dev, non_blocking=True), ids_h.to(dev, non_blocking=True)
+        loss_ce, _, _ = tcf.train_step(model, opt, eeg, sp, ids, group=group)
+        return loss_ce.item()                        # device -> host read of the step's result
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.eegclip_launch_count()
+    _lib.call("eegclip_profile_begin")
+    ms_step = timed(step_resident, args.steps)
+    prof_ms = (ctypes.c_double * 8)()
+    prof_n = (ctypes.c_longlong * 8)()
+    _lib.call("eegclip_profile_end", ctypes.cast(prof_ms, ctypes.c_void_p), ctypes.cast(prof_n, ctypes.c_void_p), 8)
+    launches = lib.eegclip_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    names = ["conv_fwd_dgrad_tc", "conv_wgrad_tc", "attn_fwd", "attn_bwd", "ln_ct", "gemm_f32"]
+    kern = {n: {"ms_per_step": prof_ms[i] / args.steps, "launches_per_step": prof_n[i] / args.steps} for i, n in enumerate(names)}
+    conv_launches = max(1, prof_n[0])
+    conv_ms = prof_ms[0] / conv_launches
+    achieved = B * CONV_FLOP_PER_SAMPLE / (conv_ms * 1e-3) / 1e12 if prof_n[0] else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    math_name = {0: "f32", 1: "bf16x3-fp32acc", 2: "bf16-fp32acc"}[_lib.default_math()]
+    line = {
+        "metric": METRIC, "value": world * B / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": math_name, "data": "synthetic",
+        "config": {"workload": workload_name(B), "global_batch": world * B,
+                   "parallelism": f"dp{world}: per-rank towers, NCCL all-gather of embeddings, sharded InfoNCE, SUM all-reduce of grads",
+                   "l2": f"per-step inputs ({h2d_bytes / 1e6:.0f} MB) and activations (>2 GB) exceed the 126 MB L2; {NBUF} batches rotate",
+                   "speech_tower": "conv/LN blocks on eegclip kernels, the two bi-LSTMs are cuDNN library calls (SURVEY 8(f).1)"},
+        "clocks": clocks,
+        "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "conv64_tc_kernel (Conv1d k=64 forward + data-gradient launches)",
+                     "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                     "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                     "algorithmic_flop_per_launch": B * CONV_FLOP_PER_SAMPLE, "avg_launch_ms": conv_ms,
+                     "launches_timed": int(prof_n[0]), "note": "bf16x3 executes 3 MMAs per algorithmic MAC: ceiling of frac is 1/3",
+                     "traffic": traffic},
+        "kernels": kern,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        val, ms = time_cpu_port(args.cpu_batch, 2, 1)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": f"{args.cpu_batch} windows per step, 2 timed steps after 1 warm-up ({ms:.0f} ms/step), same "
+                                          "model/step as the GPU arm, torch CPU ops on all host threads"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

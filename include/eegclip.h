@@ -90,6 +90,14 @@ typedef struct {
 EEGCLIP_API int eegclip_abi_version(void);
 EEGCLIP_API const char* eegclip_build_info(void);
 
+/* Measurement hooks (bench.py): number of kernels this library has launched so far, and optional CUDA-event timing of
+ * the dominant kernel classes on the stream they are launched on.  Classes: 0 conv fwd/dgrad (tcgen05), 1 conv wgrad
+ * (tcgen05), 2 attention fwd, 3 attention bwd, 4 LayerNorm([C,T]) fwd+bwd, 5 fp32 GEMMs.  eegclip_profile_end
+ * synchronises the device and returns summed milliseconds and launch counts per class (arrays of >= 8 entries). */
+EEGCLIP_API long long eegclip_launch_count(void);
+EEGCLIP_API int eegclip_profile_begin(void);
+EEGCLIP_API int eegclip_profile_end(double* ms_by_class, long long* launches_by_class, int32_t n_classes);
+
 /* Bytes of saved activations (forward -> backward) and of scratch for one tower call. */
 EEGCLIP_API int eegclip_tower_workspace(const eegclip_tower_desc* d, size_t* save_bytes, size_t* scratch_bytes);
 

@@ -28,14 +28,17 @@ SITE_CONV, SITE_ATTN, SITE_PROJ, SITE_FFN_HID, SITE_FFN_OUT = 0, 1, 2, 3, 4
 class Drop:
     """Dropout policy: eval (identity) or train with Philox masks."""
 
-    def __init__(self, train=False, seed=0):
+    def __init__(self, train=False, seed=0, native=False):
         self.train = bool(train)
         self.seed = int(seed)
+        self.native = bool(native)   # torch's own dropout (what the reference executes): used for CPU timing only
 
     def __call__(self, x, p, layer, site, order=None):
         """x: tensor; mask index = flat index of x (after ``order`` permutation, if given)."""
         if not self.train or p <= 0.0:
             return x
+        if self.native:
+            return F.dropout(x, p, True)
         if order is not None:
             xs = x.permute(*order)
         else:
@@ -160,15 +163,31 @@ def bilstm(sd, pre, x):
     return torch.cat([f, r], dim=2)
 
 
-def eeg_conv_lstm(sd, x, n_blocks=1, drop=EVAL, pre="", p=0.4):
+_LSTM_CACHE = {}
+
+
+def bilstm_fast(sd, pre, x):
+    """Same bi-LSTM through torch's fused nn.LSTM kernel (what the reference runs, clip_model.py:267-268,322-323)."""
+    w_ih = sd[pre + "weight_ih_l0"]
+    hid, inp = w_ih.shape[0] // 4, w_ih.shape[1]
+    mod = _LSTM_CACHE.get((inp, hid))
+    if mod is None:
+        mod = _LSTM_CACHE[(inp, hid)] = torch.nn.LSTM(inp, hid, batch_first=True, bidirectional=True)
+    names = [n for n, _ in mod.named_parameters()]
+    out, _ = torch.func.functional_call(mod, {n: sd[pre + n] for n in names}, (x,))
+    return out
+
+
+def eeg_conv_lstm(sd, x, n_blocks=1, drop=EVAL, pre="", p=0.4, fast_lstm=False):
     """EEGConvLSTM.forward -- clip_model.py:302-325 (default speech tower)."""
     x = F.conv1d(x.permute(0, 2, 1), sd[pre + "eeg_spatial_mapping.weight"], sd[pre + "eeg_spatial_mapping.bias"])
     eeg = x
     for i in range(n_blocks):
         x = basic_block(sd, pre + f"conv_{i}.", x if i == n_blocks - 1 else x + eeg, drop, i, p)
     x = x.permute(0, 2, 1)
-    x = bilstm(sd, pre + "speech_lstm1.", x)
-    return bilstm(sd, pre + "speech_lstm2.", x)
+    lstm = bilstm_fast if fast_lstm else bilstm
+    x = lstm(sd, pre + "speech_lstm1.", x)
+    return lstm(sd, pre + "speech_lstm2.", x)
 
 
 def l2_normalize(x):

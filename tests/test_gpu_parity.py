@@ -41,8 +41,14 @@ def _lstm_train(model):
             m.train()
 
 
+# Absolute floor of SURVEY H3: a tensor whose reference gradient norm is below FLOOR_EPS x the global gradient norm
+# (mathematically-zero gradients such as keys.bias, or the log-scale's gradient of an untrained model) is compared
+# against that floor instead of its own norm -- it then contributes < FLOOR_EPS * tol to the global relative error.
+FLOOR_EPS = 1e-3
+
+
 def _grads_ok(model, gdig, tol, prefix=""):
-    floor = 1e-4 * global_grad_norm(gdig)
+    floor = FLOOR_EPS * global_grad_norm(gdig)
     for k, p in model.named_parameters():
         assert p.grad is not None, k
         check_digest(p.grad.cpu(), gdig[prefix + k], tol, k, floor=floor)
@@ -106,7 +112,10 @@ def test_tower_vs_live_oracle_fp64(cm):
     named = dict(model.named_parameters())
     for k, gr in zip(sdo, go[1:]):
         gr = gr if gr is not None else torch.zeros_like(sdo[k])
-        assert rel_err(named[k].grad, gr, floor=1e-4 * total) < GRAD_TOL, k
+        assert rel_err(named[k].grad, gr, floor=FLOOR_EPS * total) < GRAD_TOL, k
+    # the whole gradient vector
+    num = sum(float((named[k].grad.cpu().double() - (g if g is not None else 0 * sdo[k])).norm()) ** 2 for k, g in zip(sdo, go[1:])) ** 0.5
+    assert num / total < GRAD_TOL
 
 
 @pytest.mark.parametrize("name", ["head_B64_D2560", "head_B16_D1536", "head_B96_D200"])

@@ -143,6 +143,14 @@ def test_speech(golden, name):
         check_digest(gr, g["grads"][k], TOL, k, floor=floor)
 
 
+def test_fast_lstm_equals_restated_lstm():
+    sd = synth.make_state_dict(synth.conv_lstm_shapes(64), 5)
+    x = synth.randn(6, 2, 64, 1024)
+    a = O.eeg_conv_lstm(sd, x)
+    b = O.eeg_conv_lstm(sd, x, fast_lstm=True)
+    assert float((a - b).abs().max()) < 1e-5
+
+
 def test_full_model(golden):
     g = golden["full_d2_T192"]
     T, B, depth = g["T"], g["B"], g["depth"]

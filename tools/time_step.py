@@ -17,6 +17,9 @@ eeg = torch.randn(B, T, 64, device=dev); sp = torch.randn(B, T, 1024, device=dev
 model.train()
 for mode in ("train", "eval"):
     model.train(mode == "train")
+    for m in model.modules():
+        if isinstance(m, torch.nn.LSTM):
+            m.train()   # cuDNN refuses RNN backward in eval mode
     for i in range(2):
         t.train_step(model, opt, eeg, sp, ids)
     torch.cuda.synchronize()

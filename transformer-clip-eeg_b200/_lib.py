@@ -64,6 +64,9 @@ _psz = C.POINTER(C.c_size_t)
 SIGNATURES = {
     "eegclip_abi_version": (C.c_int, []),
     "eegclip_build_info": (C.c_char_p, []),
+    "eegclip_launch_count": (C.c_longlong, []),
+    "eegclip_profile_begin": (C.c_int, []),
+    "eegclip_profile_end": (C.c_int, [_vp, _vp, _i32]),
     "eegclip_tower_workspace": (C.c_int, [C.POINTER(TowerDesc), _psz, _psz]),
     "eegclip_tower_forward": (C.c_int, [C.POINTER(TowerDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "eegclip_tower_backward": (C.c_int, [C.POINTER(TowerDesc), _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -187,6 +187,7 @@ __global__ void attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* 
 inline int attention_fwd(const float* qkv, float* out, float* lse, int B, int T, const Drop& drop, cudaStream_t st) {
   if (T % 4) return EEGCLIP_ERR_UNSUPPORTED;
   size_t smem = (size_t)T * AD * 2 * sizeof(float);
+  ProfScope prof(PROF_ATTN_FWD, st);
   attn_fwd_kernel<<<B * AH, 128, smem, st>>>(qkv, out, lse, T, 0.125f, drop);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
@@ -196,6 +197,7 @@ inline int attention_bwd(const float* qkv, const float* out, const float* dout, 
                          const Drop& drop, cudaStream_t st) {
   if (T % 4) return EEGCLIP_ERR_UNSUPPORTED;
   size_t smem = (size_t)T * AD * 2 * sizeof(float);
+  ProfScope prof(PROF_ATTN_BWD, st);
   attn_bwd_dq_kernel<<<B * AH, 128, smem, st>>>(qkv, out, dout, lse, dqkv, T, 0.125f, drop);
   LAUNCH_CHECK();
   int threads = ((T / 4 + 31) / 32) * 32;

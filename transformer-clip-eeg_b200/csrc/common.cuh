@@ -17,10 +17,22 @@
 
 #define LAUNCH_CHECK()                                   \
   do {                                                   \
+    ++::eegclip::g_launch_count;                         \
     if (cudaPeekAtLastError() != cudaSuccess) return EEGCLIP_ERR_CUDA; \
   } while (0)
 
 namespace eegclip {
+
+// ---- launch accounting + optional per-kernel-class device timing (bench.py roofline; see eegclip_profile_*) ----
+extern long long g_launch_count;
+enum : int { PROF_CONV_TC = 0, PROF_WGRAD_TC = 1, PROF_ATTN_FWD = 2, PROF_ATTN_BWD = 3, PROF_LNCT = 4, PROF_GEMM_F32 = 5, PROF_NCLASS = 8 };
+void prof_begin(int cls, cudaStream_t st);
+void prof_end(int cls, cudaStream_t st);
+struct ProfScope {
+  int cls; cudaStream_t st;
+  ProfScope(int c, cudaStream_t s) : cls(c), st(s) { prof_begin(c, s); }
+  ~ProfScope() { prof_end(cls, st); }
+};
 
 // dropout site ids; stream = layer * 16 + site  (oracle/philox_ref.py::stream_id)
 enum : int { SITE_CONV = 0, SITE_ATTN = 1, SITE_PROJ = 2, SITE_FFN_HID = 3, SITE_FFN_OUT = 4 };

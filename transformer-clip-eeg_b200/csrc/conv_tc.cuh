@@ -368,6 +368,7 @@ inline int conv_tc_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
+  ProfScope prof(PROF_CONV_TC, st);
   convtc::conv64_tc_kernel<NTERMS><<<B, 256, smem, st>>>(a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
@@ -392,6 +393,7 @@ inline int wgrad_tc_launch(const convtc::WgradTcArgs& a, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(convtc::TAPS / convtc::WG_TAPS, a.groups);
+  ProfScope prof(PROF_WGRAD_TC, st);
   convtc::wgrad64_tc_kernel<NTERMS><<<grid, 256, convtc::wgrad_smem_bytes(a.T), st>>>(a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;

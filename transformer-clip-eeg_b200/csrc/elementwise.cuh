@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(512) ln_ct_act_fwd_kernel(const float* __restr
 
 inline int ln_ct_act_fwd(const float* y, const float* gamma, const float* beta, const float* skip, float* out, float* stats,
                          int B, int T, int C, int act, cudaStream_t st) {
+  ProfScope prof(PROF_LNCT, st);
   ln_ct_act_fwd_kernel<<<B, 512, 0, st>>>(y, gamma, beta, skip, out, stats, T, C, act, 1e-5f);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(512) ln_ct_act_bwd_kernel(const float* __restr
 inline int ln_ct_act_bwd(const float* dout, const float* y, const float* stats, const float* gamma, const float* beta,
                          float* dypad, float* dgamma, float* dbeta, int B, int T, int C, int PL, int taps, int act,
                          const Drop& drop, cudaStream_t st) {
+  ProfScope prof(PROF_LNCT, st);
   ln_ct_act_bwd_kernel<<<B, 512, 0, st>>>(dout, y, stats, gamma, beta, dypad, dgamma, dbeta, T, C, PL, T + taps - 1, act, drop);
   LAUNCH_CHECK();
   return EEGCLIP_OK;

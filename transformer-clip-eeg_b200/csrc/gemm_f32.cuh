@@ -227,6 +227,7 @@ inline int gemm_f32(const GemmArgs& g, cudaStream_t st) {
   if (a.KT <= 0) a.KT = a.K;
   if (a.splitk < 1) a.splitk = 1;
   dim3 grid(ceil_div(a.N, GBN), ceil_div(a.M, GBM), a.batch * a.splitk);
+  ProfScope prof(PROF_GEMM_F32, st);
   gemm_f32_kernel<MODE><<<grid, 256, 0, st>>>(a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;

@@ -9,6 +9,28 @@ using namespace eegclip;
 
 #define TRY(x) do { int _r = (x); if (_r != EEGCLIP_OK) return _r; } while (0)
 
+// ---- launch accounting / per-kernel-class timing state (declared in common.cuh) ---------------------------
+namespace eegclip {
+long long g_launch_count = 0;
+constexpr int PROF_MAX = 8192;
+static bool g_prof_on = false;
+static int g_prof_n = 0;
+static cudaEvent_t g_prof_ev[PROF_MAX][2];
+static int g_prof_cls[PROF_MAX];
+static bool g_prof_init = false;
+void prof_begin(int cls, cudaStream_t st) {
+  if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+  g_prof_cls[g_prof_n] = cls;
+  cudaEventRecord(g_prof_ev[g_prof_n][0], st);
+}
+void prof_end(int cls, cudaStream_t st) {
+  (void)cls;
+  if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+  cudaEventRecord(g_prof_ev[g_prof_n][1], st);
+  ++g_prof_n;
+}
+}  // namespace eegclip
+
 namespace {
 
 // ---- L2 normalise rows: xn = x / max(||x||, 1e-12)  (F.normalize, clip_model.py:675-676) -----------
@@ -167,6 +189,37 @@ __global__ void __launch_bounds__(128) mm_rowdots_kernel(const float* __restrict
 extern "C" {
 
 int eegclip_abi_version(void) { return EEGCLIP_ABI_VERSION; }
+
+long long eegclip_launch_count(void) { return eegclip::g_launch_count; }
+
+int eegclip_profile_begin(void) {
+  using namespace eegclip;
+  if (!g_prof_init) {
+    for (int i = 0; i < PROF_MAX; ++i)
+      for (int j = 0; j < 2; ++j)
+        if (cudaEventCreate(&g_prof_ev[i][j]) != cudaSuccess) return EEGCLIP_ERR_CUDA;
+    g_prof_init = true;
+  }
+  g_prof_n = 0;
+  g_prof_on = true;
+  return EEGCLIP_OK;
+}
+
+int eegclip_profile_end(double* ms_by_class, long long* launches_by_class, int32_t n_classes) {
+  using namespace eegclip;
+  g_prof_on = false;
+  if (!ms_by_class || !launches_by_class || n_classes < PROF_NCLASS) return EEGCLIP_ERR_ARG;
+  for (int c = 0; c < n_classes; ++c) { ms_by_class[c] = 0.0; launches_by_class[c] = 0; }
+  if (cudaDeviceSynchronize() != cudaSuccess) return EEGCLIP_ERR_CUDA;
+  for (int i = 0; i < g_prof_n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof_ev[i][0], g_prof_ev[i][1]) != cudaSuccess) return EEGCLIP_ERR_CUDA;
+    ms_by_class[g_prof_cls[i]] += ms;
+    launches_by_class[g_prof_cls[i]] += 1;
+  }
+  g_prof_n = 0;
+  return EEGCLIP_OK;
+}
 const char* eegclip_build_info(void) { return "eegclip_b200 sm_100a " __DATE__ " " __TIME__; }
 
 int eegclip_l2norm_forward(const float* x, float* xn, float* inv_norm, int32_t rows, int32_t D, void* stream) {
