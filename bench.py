@@ -239,7 +239,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     pk = peaks()
-    names = ["conv_fwd_dgrad_tc", "conv_wgrad_tc", "attn_fwd", "attn_bwd", "ln_ct", "gemm_f32"]
+    names = ["conv_fwd_dgrad_tc", "conv_wgrad_tc", "attn_fwd", "attn_bwd", "ln_ct", "gemm_f32", "lin_tc", "lin_wgrad_tc"]
     kern = {n: {"ms_per_step": prof_ms[i] / args.steps, "launches_per_step": prof_n[i] / args.steps} for i, n in enumerate(names)}
     conv_launches = max(1, prof_n[0])
     conv_ms = prof_ms[0] / conv_launches

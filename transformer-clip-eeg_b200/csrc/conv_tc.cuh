@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
       tc::mbar_expect_tx(&full[s], bytes);
       tc::bulk_g2s(sB + s * W_TAP_BYTES, a.wpacked + (long)tap * W_TAP_BYTES, bytes, &full[s]);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
+  } else if (warp == 1) {
+    // ===== MMA issuer: the whole warp runs the loop (descriptors stay in uniform registers), one elected lane issues =====
     const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
     const uint32_t id128 = tc::idesc_bf16(128, CH, 0, 0), id64 = tc::idesc_bf16(64, CH, 0, 0);
     for (int tap = 0; tap < TAPS; ++tap) {
@@ -152,25 +152,30 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
       tc::mbar_wait(&full[s], ph);
       tc::tc_fence_after();
       const uint32_t wb = sB_u + s * W_TAP_BYTES;
-      for (int tile = 0; tile < ntiles; ++tile) {
-        const uint32_t idesc = (last64 && tile == ntiles - 1) ? id64 : id128;
-        const uint32_t d = tmem + tile * 64;
-        const uint32_t arow = sA_u + (uint32_t)(tile * 128 + tap) * 16u;
+      const uint64_t b_hi = tc::smem_desc(wb, CH * 16, 128), b_lo = tc::smem_desc(wb + W_PLANE_BYTES, CH * 16, 128);
+      if (tc::elect_one()) {
+        for (int tile = 0; tile < ntiles; ++tile) {
+          const uint32_t idesc = (last64 && tile == ntiles - 1) ? id64 : id128;
+          const uint32_t d = tmem + tile * 64;
+          const uint32_t arow = sA_u + (uint32_t)(tile * 128 + tap) * 16u;
+          const uint64_t a_hi = tc::smem_desc(arow, CS, 128), a_lo = tc::smem_desc(arow + PS, CS, 128);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-          for (int term = 0; term < NTERMS; ++term) {
-            const uint32_t pa = (term == 2) ? PS : 0u;              // hi*hi, hi*lo, lo*hi
-            const uint32_t pb = (term == 1) ? W_PLANE_BYTES : 0u;
-            const uint64_t ad = tc::smem_desc(arow + pa + (2 * ks) * CS, CS, 128);
-            const uint64_t bd = tc::smem_desc(wb + pb + (2 * ks) * (CH * 16), CH * 16, 128);
-            tc::mma_bf16(d, ad, bd, idesc, (tap | ks | term) != 0);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t da = (uint64_t)((2 * ks * CS) >> 4);           // start-address field is in 16-byte units
+            const uint64_t db = (uint64_t)((2 * ks * (CH * 16)) >> 4);
+            tc::mma_bf16(d, a_hi + da, b_hi + db, idesc, (tap | ks) != 0);  // hi*hi
+            if (NTERMS > 1) {
+              tc::mma_bf16(d, a_hi + da, b_lo + db, idesc, 1);              // hi*lo
+              tc::mma_bf16(d, a_lo + da, b_hi + db, idesc, 1);              // lo*hi
+            }
           }
         }
+        tc::tc_commit(&empty[s]);
       }
-      tc::tc_commit(&empty[s]);
+      __syncwarp();
     }
-    tc::tc_commit(accfull);
+    if (tc::elect_one()) tc::tc_commit(accfull);
+    __syncwarp();
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> bias / dropout -> global =====
     const int q = warp - 4;  // TMEM lane quarter of this warp
@@ -286,23 +291,28 @@ __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a)
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    if (tid == 0) {
+    if (warp == 0) {
       const uint32_t sU_u = tc::smem_u32(sU), sD_u = tc::smem_u32(sD);
       const int ksteps = T >> 4;
-      for (int j = 0; j < WG_TAPS; ++j) {
-        const uint32_t d = tmem + (uint32_t)(j >> 1) * 64u + ((uint32_t)((j & 1) * 16) << 16);
-        for (int ks = 0; ks < ksteps; ++ks) {
-#pragma unroll
-          for (int term = 0; term < NTERMS; ++term) {
-            const uint32_t pa = (term == 2) ? PSD : 0u;   // A = dy, B = u : hi*hi, hi*lo, lo*hi
-            const uint32_t pb = (term == 1) ? PSU : 0u;
-            const uint64_t ad = tc::smem_desc(sD_u + pa + (uint32_t)(ks * 16) * 16u, 128, CSD);
-            const uint64_t bd = tc::smem_desc(sU_u + pb + (uint32_t)(j + ks * 16) * 16u, 128, CSU);
-            tc::mma_bf16(d, ad, bd, idesc, !(first && ks == 0 && term == 0));
+      const uint32_t acc0 = first ? 0u : 1u;
+      if (tc::elect_one()) {
+        for (int j = 0; j < WG_TAPS; ++j) {
+          const uint32_t d = tmem + (uint32_t)(j >> 1) * 64u + ((uint32_t)((j & 1) * 16) << 16);
+          // A = dy, B = u (both MN-major, K = time): hi*hi, hi*lo, lo*hi
+          const uint64_t a_hi = tc::smem_desc(sD_u, 128, CSD), a_lo = tc::smem_desc(sD_u + PSD, 128, CSD);
+          const uint64_t b_hi = tc::smem_desc(sU_u + (uint32_t)j * 16u, 128, CSU), b_lo = tc::smem_desc(sU_u + PSU + (uint32_t)j * 16u, 128, CSU);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t dk = (uint64_t)(ks * 16);                     // 16 time rows = 256 bytes = 16 address units
+            tc::mma_bf16(d, a_hi + dk, b_hi + dk, idesc, acc0 | (uint32_t)(ks != 0));
+            if (NTERMS > 1) {
+              tc::mma_bf16(d, a_hi + dk, b_lo + dk, idesc, 1);
+              tc::mma_bf16(d, a_lo + dk, b_hi + dk, idesc, 1);
+            }
           }
         }
+        tc::tc_commit(bar);
       }
-      tc::tc_commit(bar);
+      __syncwarp();
     }
     tc::mbar_wait(bar, phase);   // all MMAs that read this sample's tiles are done
     tc::tc_fence_after();

@@ -1,0 +1,585 @@
+// tcgen05 token GEMMs of the Transformer block (clip_model.py:24-26,31-33,43,63-66): QKV / out-projection / FFN
+// linears, their data gradients and their weight gradients, on time-major (tokens, features) fp32 activations.
+//
+// All of these have a tiny contraction (K = 64..256) and a huge token count (M = B*T = 81 920 at B=256): they are
+// HBM-bound (AI ~ 24..48 FLOP/B in fp32 storage), so the kernels are organised around streaming the activations once:
+//
+//   lin_tc_kernel   C[m][n] = epi( sum_k pro(A[m][k]) * W[n][k] )        (forward and data gradient: W or W^T packed)
+//     persistent CTAs, warp-specialised:
+//       warps 0-3  epilogue : TMEM -> registers -> per-warp smem transpose -> coalesced 128-bit global stores with
+//                             bias / GELU(+pre-activation save) / Philox dropout / GELU' / residual fused
+//       warps 4-7  producers: coalesced 128-bit loads of a 128-token x 64-feature fp32 chunk (+ optional dropout /
+//                             GELU.dropout prologue), split into bf16 hi/lo planes in the chunk-major UMMA layout
+//                             (tc_common.cuh), 4-stage ring signalled on mbarriers
+//       warp  8    MMA      : one thread issues tcgen05.mma (M=128, N = full output width <= 256) into one of two TMEM
+//                             accumulator buffers, so the epilogue of tile i overlaps the MMAs of tile i+1
+//     the packed weights (<= 64 KB) are fetched once per CTA by a 1-D bulk async copy (TMA engine) and stay resident.
+//
+//   lin_wgrad_tc_kernel   dW[n][k] = sum_m pro(dy[m][n]) * pro(x[m][k]),  db[n] = sum_m pro(dy[m][n])
+//     contraction over tokens: both operands are MN-major views of the same chunk-major tiles (as the conv weight
+//     gradient); each CTA accumulates its token slice in TMEM and writes one partial; lin_wgrad_reduce_kernel sums the
+//     partials in a fixed order (deterministic gradients, no atomics).
+//
+// Arithmetic: NTERMS = 3 -> split-bf16 (hi*hi + hi*lo + lo*hi, fp32 accumulate); NTERMS = 1 -> plain bf16.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace eegclip {
+namespace lintc {
+
+constexpr int BM = 128;                  // tokens per tile
+constexpr int KC = 64;                   // features per pipeline chunk
+constexpr int NSTAGE = 4;
+constexpr int A_CS = BM * 16;            // stride between 8-feature chunks inside a plane (bytes)
+constexpr int A_PLANE = (KC / 8) * A_CS; // 16 KB
+constexpr int A_STAGE = 2 * A_PLANE;     // hi + lo
+constexpr int EPI_LD = 36;               // floats per staged row (32 + pad: 16 B aligned, conflict-free 128-bit access)
+constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
+constexpr int NTHREADS = 288;
+
+enum : int { PRO_NONE = 0, PRO_DROP = 1, PRO_GELU_DROP = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing.  Packed operand B (Ntot x Ktot, "n" = output feature, "k" = contraction index):
+//   plane p (0 hi, 1 lo), element (n,k) at  p*Ntot*Ktot*2 + (k/8)*(Ntot*16) + n*16 + (k%8)*2   bytes.
+// A job copies an (n_cnt x k_cnt) block at (n_off,k_off) from a strided fp32 source: src[n*sn + k*sk].
+// kind 1 jobs copy n_cnt floats (bias concatenation).
+// ------------------------------------------------------------------------------------------------
+struct PackJob {
+  const float* src;
+  uint8_t* dst;
+  int kind, Ntot, Ktot, n_off, k_off, n_cnt, k_cnt, sn, sk;
+};
+constexpr int MAX_PACK_JOBS = 16;
+struct PackJobs { PackJob j[MAX_PACK_JOBS]; int n; };
+
+__global__ void __launch_bounds__(256) pack_lin_weights_kernel(const PackJobs jobs) {
+  const PackJob& J = jobs.j[blockIdx.y];
+  if (J.kind == 1) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < J.n_cnt; i += gridDim.x * blockDim.x)
+      reinterpret_cast<float*>(J.dst)[J.n_off + i] = J.src[i];
+    return;
+  }
+  const int kch = J.k_cnt >> 3;
+  const long plane = (long)J.Ntot * J.Ktot * 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < J.n_cnt * kch; i += gridDim.x * blockDim.x) {
+    const int n = i % J.n_cnt, c = i / J.n_cnt;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = J.src[(long)n * J.sn + (long)(c * 8 + e) * J.sk];
+    uint4 hi, lo;
+    tc::split8(v, hi, lo);
+    uint8_t* d = J.dst + (long)((J.k_off >> 3) + c) * (J.Ntot * 16) + (long)(J.n_off + n) * 16;
+    *reinterpret_cast<uint4*>(d) = hi;
+    *reinterpret_cast<uint4*>(d + plane) = lo;
+  }
+}
+
+inline int pack_launch(const PackJobs& jobs, cudaStream_t st) {
+  if (jobs.n <= 0) return EEGCLIP_OK;
+  pack_lin_weights_kernel<<<dim3(8, jobs.n), 256, 0, st>>>(jobs);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+inline void add_pack(PackJobs& J, const float* src, uint8_t* dst, int Ntot, int Ktot, int n_off, int k_off, int n_cnt, int k_cnt,
+                     int sn, int sk) {
+  PackJob& j = J.j[J.n++];
+  j.src = src; j.dst = dst; j.kind = 0; j.Ntot = Ntot; j.Ktot = Ktot; j.n_off = n_off; j.k_off = k_off; j.n_cnt = n_cnt; j.k_cnt = k_cnt;
+  j.sn = sn; j.sk = sk;
+}
+inline void add_copy(PackJobs& J, const float* src, float* dst, int off, int cnt) {
+  PackJob& j = J.j[J.n++];
+  j.src = src; j.dst = reinterpret_cast<uint8_t*>(dst); j.kind = 1; j.Ntot = j.Ktot = 0; j.n_off = off; j.k_off = 0; j.n_cnt = cnt;
+  j.k_cnt = 0; j.sn = j.sk = 0;
+}
+inline size_t packed_bytes(int N, int K) { return (size_t)N * K * 4; }
+
+// ------------------------------------------------------------------------------------------------
+// Shared producer: stage ROWS x 64 fp32 features (row-major, leading dimension ld) as bf16 hi/lo chunk-major planes.
+//   lane -> (row = lane & 7, chunk = lane >> 3) inside an 8-row x 4-chunk block: each row contributes 128 contiguous
+//   bytes to a request (full lines) and the eight 16-byte smem stores of a quarter-warp fill one 128-byte wavefront.
+// Every thread keeps a FIXED chunk ((pw & 1) * 4 + (lane >> 3)), so column sums can live in registers.
+// ------------------------------------------------------------------------------------------------
+template <int ROWS, int NTERMS, int NPW /* producer warps */>
+__device__ __forceinline__ void stage_chunk(const float* __restrict__ src, long ld, long row0, long rows_total, int col0, int ncols_total,
+                                            uint8_t* dst, uint32_t CS, uint32_t PS, int pw, int lane, int pro, const Drop& drop,
+                                            float* colsum /* nullptr or 8 running sums */) {
+  constexpr int NBLK = (ROWS / 8) * 2;      // (row block, chunk half) combos
+  constexpr int ITERS = NBLK / NPW;
+  static_assert(NBLK % NPW == 0, "producer warps must divide the chunk");
+  const int ch = (pw & 1) * 4 + (lane >> 3);
+  float4 x0[ITERS], x1[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int rb = it * (NPW / 2) + (pw >> 1);
+    const long r = row0 + rb * 8 + (lane & 7);
+    if (r < rows_total) {
+      const float4* p = reinterpret_cast<const float4*>(src + r * ld + col0 + ch * 8);
+      x0[it] = __ldg(p); x1[it] = __ldg(p + 1);
+    } else {
+      x0[it] = make_float4(0.f, 0.f, 0.f, 0.f); x1[it] = x0[it];
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int rb = it * (NPW / 2) + (pw >> 1);
+    const int rl = rb * 8 + (lane & 7);
+    float v[8] = {x0[it].x, x0[it].y, x0[it].z, x0[it].w, x1[it].x, x1[it].y, x1[it].z, x1[it].w};
+    if (pro != PRO_NONE) {
+      const long r = row0 + rl;
+      if (r < rows_total) {
+        const uint64_t idx = (uint64_t)r * (uint64_t)ncols_total + (uint64_t)(col0 + ch * 8);
+        const float4 m0 = drop_mult4(drop, idx), m1 = drop_mult4(drop, idx + 4);
+        const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (pro == PRO_GELU_DROP ? gelu_f(v[e]) : v[e]) * mm[e];
+      }
+    }
+    if (colsum) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) colsum[e] += v[e];
+    }
+    uint4 hi, lo;
+    tc::split8(v, hi, lo);
+    uint8_t* d = dst + ch * CS + rl * 16;
+    *reinterpret_cast<uint4*>(d) = hi;
+    if (NTERMS > 1) *reinterpret_cast<uint4*>(d + PS) = lo;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward / data-gradient GEMM
+// ------------------------------------------------------------------------------------------------
+struct LinTcArgs {
+  const float* A; long lda;       // (M, K) fp32
+  const uint8_t* wpacked;         // packed (N x K) operand, see pack_lin_weights_kernel
+  float* C; long ldc;             // (M, N) fp32; aux / act_grad_src / residual share C's indexing
+  int M, N, K;
+  int pro; Drop pro_drop;         // prologue on A (element index m*K + k)
+  const float* bias;              // + bias[n]
+  int act; float* aux;            // act == 1: aux = v (pre-activation, optional); v = GELU(v)
+  int drop_on; Drop drop;         // v *= dropmult(m*N + n)
+  const float* act_grad_src;      // v *= GELU'(src[m][n])
+  const float* residual;          // v += residual[m][n]
+};
+
+inline uint32_t lin_smem_bytes(int N, int K) {
+  return (uint32_t)packed_bytes(N, K) + NSTAGE * A_STAGE + 4 * EPI_WARP_FLOATS * 4 + 256;
+}
+
+template <int NTERMS>
+__global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = a.N, K = a.K;
+  const uint32_t WP = (uint32_t)N * K * 2;                 // weight plane bytes
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + 2 * WP;
+  float* sE = reinterpret_cast<float*>(sA + NSTAGE * A_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + 4 * EPI_WARP_FLOATS);
+  uint64_t* full = bars;                  // [NSTAGE] producers -> MMA   (128 arrivals)
+  uint64_t* empty = bars + NSTAGE;        // [NSTAGE] MMA -> producers   (tcgen05.commit)
+  uint64_t* accfull = bars + 2 * NSTAGE;  // [2] MMA -> epilogue
+  uint64_t* accempty = accfull + 2;       // [2] epilogue -> MMA         (128 arrivals)
+  uint64_t* wfull = accempty + 2;         // weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  uint32_t ncols = 32;
+  while (ncols < 2u * (uint32_t)N) ncols <<= 1;
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 128); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&accfull[i], 1); tc::mbar_init(&accempty[i], 128); }
+    tc::mbar_init(wfull, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 8) tc::tmem_alloc(tmem_slot, ncols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ntiles = (a.M + BM - 1) / BM;
+  const int nchunk = K / KC;
+
+  if (warp >= 4 && warp < 8) {
+    // ===== producers =====
+    const int pw = warp - 4;
+    uint32_t c = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int kc = 0; kc < nchunk; ++kc, ++c) {
+        const int s = c % NSTAGE;
+        tc::mbar_wait(&empty[s], ((c / NSTAGE) & 1) ^ 1);
+        stage_chunk<BM, NTERMS, 4>(a.A, a.lda, (long)tile * BM, a.M, kc * KC, K, sA + s * A_STAGE, A_CS, A_PLANE, pw, lane, a.pro,
+                                   a.pro_drop, nullptr);
+        tc::fence_async_smem();
+        tc::mbar_arrive(&full[s]);
+      }
+    }
+  } else if (warp == 8) {
+    // ===== weights (once) + MMA issue: the whole warp runs the loop, one elected lane issues =====
+    const uint32_t wbytes = NTERMS > 1 ? 2 * WP : WP;
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx(wfull, wbytes);
+      tc::bulk_g2s(sW, a.wpacked, wbytes, wfull);
+    }
+    __syncwarp();
+    tc::mbar_wait(wfull, 0);
+    const uint32_t sA_u = tc::smem_u32(sA), sW_u = tc::smem_u32(sW);
+    const uint32_t idesc = tc::idesc_bf16(128, N, 0, 0);
+    const uint32_t nb16 = (uint32_t)N * 16u;
+    uint32_t c = 0, t = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+      const uint32_t buf = t & 1;
+      tc::mbar_wait(&accempty[buf], ((t >> 1) & 1) ^ 1);
+      tc::tc_fence_after();
+      const uint32_t d = tmem + buf * (uint32_t)N;
+      for (int kc = 0; kc < nchunk; ++kc, ++c) {
+        const int s = c % NSTAGE;
+        tc::mbar_wait(&full[s], (c / NSTAGE) & 1);
+        tc::tc_fence_after();
+        const uint64_t a_hi = tc::smem_desc(sA_u + s * A_STAGE, A_CS, 128);
+        const uint64_t a_lo = tc::smem_desc(sA_u + s * A_STAGE + A_PLANE, A_CS, 128);
+        const uint64_t b_hi = tc::smem_desc(sW_u + (uint32_t)(kc * 8) * nb16, nb16, 128);
+        const uint64_t b_lo = tc::smem_desc(sW_u + WP + (uint32_t)(kc * 8) * nb16, nb16, 128);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            const uint64_t da = (uint64_t)((2 * ks * A_CS) >> 4);          // descriptor start-address field is in 16-byte units
+            const uint64_t db = (uint64_t)((2 * ks * nb16) >> 4);
+            tc::mma_bf16(d, a_hi + da, b_hi + db, idesc, (kc | ks) != 0);   // hi*hi
+            if (NTERMS > 1) {
+              tc::mma_bf16(d, a_hi + da, b_lo + db, idesc, 1);              // hi*lo
+              tc::mma_bf16(d, a_lo + da, b_hi + db, idesc, 1);              // lo*hi
+            }
+          }
+          tc::tc_commit(&empty[s]);
+        }
+        __syncwarp();
+      }
+      if (tc::elect_one()) tc::tc_commit(&accfull[buf]);
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue (warps 0-3 == TMEM lane quarters 0-3) =====
+    const int q = warp;
+    float* stg = sE + q * EPI_WARP_FLOATS;
+    const int cq = (lane & 7) * 4, rq = lane >> 3;      // coalesced phase: 4 columns x (4 rows per iteration)
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+      const uint32_t buf = t & 1;
+      tc::mbar_wait(&accfull[buf], (t >> 1) & 1);
+      tc::tc_fence_after();
+      const long mrow0 = (long)tile * BM + q * 32;
+      for (int cb = 0; cb < N; cb += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)N + cb, v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        const int n = cb + cq;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias) bb = *reinterpret_cast<const float4*>(a.bias + n);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + rq;
+          const long m = mrow0 + rl;
+          if (m < a.M) {
+            float4 r = *reinterpret_cast<const float4*>(stg + rl * EPI_LD + cq);
+            const long ci = m * a.ldc + n;
+            r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+            if (a.act == 1) {
+              if (a.aux) *reinterpret_cast<float4*>(a.aux + ci) = r;
+              r.x = gelu_f(r.x); r.y = gelu_f(r.y); r.z = gelu_f(r.z); r.w = gelu_f(r.w);
+            }
+            if (a.drop_on) {
+              const float4 mk = drop_mult4(a.drop, (uint64_t)m * (uint64_t)N + (uint64_t)n);
+              r.x *= mk.x; r.y *= mk.y; r.z *= mk.z; r.w *= mk.w;
+            }
+            if (a.act_grad_src) {
+              const float4 s4 = *reinterpret_cast<const float4*>(a.act_grad_src + ci);
+              r.x *= gelu_grad_f(s4.x); r.y *= gelu_grad_f(s4.y); r.z *= gelu_grad_f(s4.z); r.w *= gelu_grad_f(s4.w);
+            }
+            if (a.residual) {
+              const float4 s4 = *reinterpret_cast<const float4*>(a.residual + ci);
+              r.x += s4.x; r.y += s4.y; r.z += s4.z; r.w += s4.w;
+            }
+            *reinterpret_cast<float4*>(a.C + ci) = r;
+          }
+        }
+        __syncwarp();
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&accempty[buf]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, ncols);
+}
+
+inline bool lin_tc_supported(long M, int N, int K) {
+  return M >= 1 && (N == 64 || N == 128 || N == 192 || N == 256) && (K % KC) == 0 && K >= KC &&
+         lin_smem_bytes(N, K) <= 227u * 1024u;
+}
+
+template <int NTERMS>
+inline int lin_tc_launch_t(const LinTcArgs& a, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(lin_tc_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return EEGCLIP_ERR_CUDA;
+    configured = true;
+  }
+  const int ntiles = (a.M + BM - 1) / BM;
+  const int grid = ntiles < 148 ? ntiles : 148;
+  ProfScope prof(PROF_LIN_TC, st);
+  lin_tc_kernel<NTERMS><<<grid, NTHREADS, lin_smem_bytes(a.N, a.K), st>>>(a);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+inline int lin_tc_launch(int math, const LinTcArgs& a, cudaStream_t st) {
+  return math == EEGCLIP_MATH_BF16 ? lin_tc_launch_t<1>(a, st) : lin_tc_launch_t<3>(a, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient (contraction over tokens)
+// ------------------------------------------------------------------------------------------------
+constexpr int WT = 64;                   // tokens per stage
+constexpr int W_CS = WT * 16;            // chunk stride (bytes)
+constexpr int WG_THREADS = 288;
+constexpr int WG_MAX_CTAS = 148;
+
+struct LinWgradArgs {
+  const float* dy; long lddy; int Nout;   // (M, Nout): rows of dW
+  const float* x; long ldx; int Kin;      // (M, Kin) : columns of dW
+  int M;
+  int pro_dy; Drop drop_dy;               // prologue on dy (element index m*Nout + n)
+  int pro_x; Drop drop_x;                 // prologue on x  (element index m*Kin + k)
+  float* partial;                         // [ctas][Nout*Kin + Nout]
+  int want_db;
+};
+
+inline uint32_t wgrad_stage_bytes(int Nout, int Kin) { return (uint32_t)(Nout + Kin) * WT * 4; }
+inline uint32_t wgrad_lin_smem_bytes(int Nout, int Kin) { return 2 * wgrad_stage_bytes(Nout, Kin) + 9 * 256 * 4 + 256; }
+
+template <int NTERMS>
+__global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWgradArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Nout = a.Nout, Kin = a.Kin;
+  const uint32_t PSD = (uint32_t)(Nout / 8) * W_CS, PSX = (uint32_t)(Kin / 8) * W_CS;   // plane strides
+  const uint32_t STAGE = 2 * PSD + 2 * PSX;
+  float* sCol = reinterpret_cast<float*>(smem + 2 * STAGE);     // [8 warps? -> 4 producer warps][256] column-sum staging (+1 spare)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + 9 * 256);
+  uint64_t* full = bars;          // [2]
+  uint64_t* empty = bars + 2;     // [2]
+  uint64_t* accfull = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int nmt = (Nout + 127) / 128;                 // M tiles (rows of dW)
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)(nmt * Kin)) ncols <<= 1;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&full[i], 128); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(accfull, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 8) tc::tmem_alloc(tmem_slot, ncols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // token range of this CTA, in units of WT-token stages
+  const int nst_total = (a.M + WT - 1) / WT;
+  const int per = (nst_total + gridDim.x - 1) / gridDim.x;
+  const int st_beg = blockIdx.x * per;
+  const int st_end = min(nst_total, st_beg + per);
+  const int nst = max(0, st_end - st_beg);
+  const int ndc = Nout / KC, nxc = Kin / KC;          // 64-feature chunks per operand
+
+  if (warp >= 4 && warp < 8) {
+    // ===== producers =====
+    const int pw = warp - 4;
+    float cs[4][8];                                   // column sums of dy: chunk dc*8 + (pw&1)*4 + (lane>>3), dc < 4
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) cs[i][e] = 0.f;
+    for (int it = 0; it < nst; ++it) {
+      const int s = it & 1;
+      tc::mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+      uint8_t* sb = smem + s * STAGE;
+      const long row0 = (long)(st_beg + it) * WT;
+#pragma unroll
+      for (int dc = 0; dc < 4; ++dc)
+        if (dc < ndc)
+          stage_chunk<WT, NTERMS, 4>(a.dy, a.lddy, row0, a.M, dc * KC, Nout, sb + dc * 8 * W_CS, W_CS, PSD, pw, lane, a.pro_dy, a.drop_dy,
+                                     a.want_db ? cs[dc] : nullptr);
+      for (int xc = 0; xc < nxc; ++xc)
+        stage_chunk<WT, NTERMS, 4>(a.x, a.ldx, row0, a.M, xc * KC, Kin, sb + 2 * PSD + xc * 8 * W_CS, W_CS, PSX, pw, lane, a.pro_x, a.drop_x,
+                                   nullptr);
+      tc::fence_async_smem();
+      tc::mbar_arrive(&full[s]);
+    }
+    if (a.want_db) {
+      // reduce over the 8 row-lanes of a warp (lane & 7), then over the two warps sharing a chunk half (pw>>1)
+#pragma unroll
+      for (int dc = 0; dc < 4; ++dc)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float v = cs[dc][e];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          cs[dc][e] = v;
+        }
+      if ((lane & 7) == 0) {
+        const int ch = (pw & 1) * 4 + (lane >> 3);
+#pragma unroll
+        for (int dc = 0; dc < 4; ++dc)
+          if (dc < ndc)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sCol[(pw >> 1) * 256 + dc * 64 + ch * 8 + e] = cs[dc][e];
+      }
+    }
+  } else if (warp == 8) {
+    // whole warp runs the loop (uniform descriptors), one elected lane issues
+    const uint32_t base = tc::smem_u32(smem);
+    for (int it = 0; it < nst; ++it) {
+      const int s = it & 1;
+      tc::mbar_wait(&full[s], (it >> 1) & 1);
+      tc::tc_fence_after();
+      const uint32_t sD = base + s * STAGE, sX = sD + 2 * PSD;
+      const uint64_t b_hi = tc::smem_desc(sX, 128, W_CS), b_lo = tc::smem_desc(sX + PSX, 128, W_CS);
+      if (tc::elect_one()) {
+        for (int mt = 0; mt < nmt; ++mt) {
+          const int mrows = min(128, Nout - mt * 128);          // 128 or 64
+          const uint32_t idesc = tc::idesc_bf16(mrows, Kin, 1, 1);
+          const uint32_t d = tmem + (uint32_t)(mt * Kin);
+          // A = dy, B = x (both MN-major, K = tokens): hi*hi, hi*lo, lo*hi
+          const uint64_t a_hi = tc::smem_desc(sD + (uint32_t)(mt * 16) * W_CS, 128, W_CS);
+          const uint64_t a_lo = tc::smem_desc(sD + PSD + (uint32_t)(mt * 16) * W_CS, 128, W_CS);
+#pragma unroll
+          for (int ks = 0; ks < WT / 16; ++ks) {
+            const uint64_t dk = (uint64_t)(ks * 16);            // 16 token rows = 256 bytes = 16 address units
+            tc::mma_bf16(d, a_hi + dk, b_hi + dk, idesc, (it | ks) != 0);
+            if (NTERMS > 1) {
+              tc::mma_bf16(d, a_hi + dk, b_lo + dk, idesc, 1);
+              tc::mma_bf16(d, a_lo + dk, b_hi + dk, idesc, 1);
+            }
+          }
+        }
+        tc::tc_commit(&empty[s]);
+      }
+      __syncwarp();
+    }
+    if (tc::elect_one()) tc::tc_commit(accfull);
+    __syncwarp();
+  }
+  __syncthreads();   // column sums staged; all roles done issuing
+  float* part = a.partial + (long)blockIdx.x * ((long)Nout * Kin + Nout);
+  if (warp < 4) {
+    // ===== epilogue: accumulators -> partial[cta][n][k] =====
+    const int q = warp;
+    if (nst > 0) {
+      tc::mbar_wait(accfull, 0);
+      tc::tc_fence_after();
+    }
+    for (int mt = 0; mt < nmt; ++mt) {
+      const int mrows = min(128, Nout - mt * 128);
+      // M = 128: row = q*32 + lane ; M = 64: row = q*16 + lane (lanes 0-15 of each sub-partition)
+      const int row = mrows == 128 ? q * 32 + lane : q * 16 + lane;
+      const bool valid = mrows == 128 || lane < 16;
+      for (int cb = 0; cb < Kin; cb += 32) {
+        float v[32];
+        if (nst > 0) tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * Kin + cb), v);
+        else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (valid) {
+          float* o = part + (long)(mt * 128 + row) * Kin + cb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+    }
+    if (a.want_db) {
+      float* pb = part + (long)Nout * Kin;
+      for (int n = tid; n < Nout; n += 128) pb[n] = nst > 0 ? sCol[n] + sCol[256 + n] : 0.f;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, ncols);
+}
+
+// dW (split over up to 3 destinations of rows_per_dst rows each) = sum over CTAs of the partials, fixed order.
+struct WgradReduceArgs {
+  const float* partial; int ctas, Nout, Kin, rows_per_dst;
+  float* dW[3]; float* db[3];
+};
+__global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const WgradReduceArgs a) {
+  __shared__ float sh[4][64];
+  const int total = a.Nout * a.Kin + a.Nout;
+  const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int g = threadIdx.x >> 6;
+  float s = 0.f;
+  if (i < total) {
+    const float* p = a.partial + i;
+#pragma unroll 4
+    for (int c = g; c < a.ctas; c += 4) s += p[(long)c * total];
+  }
+  sh[g][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (g == 0 && i < total) {
+    s = sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x];
+    if (i < a.Nout * a.Kin) {
+      const int n = i / a.Kin, k = i - n * a.Kin;
+      const int d = n / a.rows_per_dst;
+      a.dW[d][(long)(n - d * a.rows_per_dst) * a.Kin + k] = s;
+    } else {
+      const int n = i - a.Nout * a.Kin;
+      const int d = n / a.rows_per_dst;
+      if (a.db[d]) a.db[d][n - d * a.rows_per_dst] = s;
+    }
+  }
+}
+
+inline bool lin_wgrad_tc_supported(long M, int Nout, int Kin) {
+  return M >= 1 && (Nout == 64 || Nout == 128 || Nout == 192 || Nout == 256) && (Kin == 64 || Kin == 128 || Kin == 192 || Kin == 256) &&
+         ((Nout + 127) / 128) * Kin <= 512 && wgrad_lin_smem_bytes(Nout, Kin) <= 227u * 1024u;
+}
+inline size_t lin_wgrad_partial_bytes(int Nout, int Kin) { return (size_t)WG_MAX_CTAS * ((size_t)Nout * Kin + Nout) * sizeof(float); }
+
+template <int NTERMS>
+inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const db[3], int rows_per_dst, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(lin_wgrad_tc_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return EEGCLIP_ERR_CUDA;
+    configured = true;
+  }
+  const int nst = (a.M + WT - 1) / WT;
+  const int ctas = nst < WG_MAX_CTAS ? nst : WG_MAX_CTAS;
+  a.want_db = (db[0] != nullptr) ? 1 : 0;
+  {
+    ProfScope prof(PROF_LIN_WGRAD, st);
+    lin_wgrad_tc_kernel<NTERMS><<<ctas, WG_THREADS, wgrad_lin_smem_bytes(a.Nout, a.Kin), st>>>(a);
+    LAUNCH_CHECK();
+  }
+  WgradReduceArgs r;
+  r.partial = a.partial; r.ctas = ctas; r.Nout = a.Nout; r.Kin = a.Kin; r.rows_per_dst = rows_per_dst;
+  for (int i = 0; i < 3; ++i) { r.dW[i] = dW[i]; r.db[i] = db[i]; }
+  const int total = a.Nout * a.Kin + a.Nout;
+  lin_wgrad_reduce_kernel<<<(total + 63) / 64, 256, 0, st>>>(r);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+inline int lin_wgrad_launch(int math, const LinWgradArgs& a, float* const dW[3], float* const db[3], int rows_per_dst, cudaStream_t st) {
+  return math == EEGCLIP_MATH_BF16 ? lin_wgrad_launch_t<1>(a, dW, db, rows_per_dst, st) : lin_wgrad_launch_t<3>(a, dW, db, rows_per_dst, st);
+}
+
+}  // namespace lintc
+}  // namespace eegclip

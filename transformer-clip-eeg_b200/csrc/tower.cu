@@ -11,6 +11,7 @@
 #include "elementwise.cuh"
 #include "attention.cuh"
 #include "conv_tc.cuh"
+#include "lin_tc.cuh"
 
 using namespace eegclip;
 
@@ -40,8 +41,24 @@ struct SaveLayout {
   // within a conv block: y (n*C), out (n*C), stats (2B rounded to 4)
   size_t c_y, c_out, c_stats;
   // within a transformer block: qkv (n*192), o (n*C), lse (B*8*T), z1 (n*C), fpre (n*FF), zout (n*C)
-  size_t x_qkv, x_o, x_lse, x_z1, x_fpre, x_zout;
+  size_t x_qkv, x_o, x_lse, x_z1, x_fpre, x_zout, x_wp;
+  size_t map_wp;               // packed eeg_spatial_mapping weights (forward + data-gradient forms)
 };
+
+// packed tensor-core operands of one transformer block (byte offsets inside its x_wp region)
+struct XfPacked {
+  static constexpr size_t QKV_F = 0;                       // (192 x 64)  forward
+  static constexpr size_t QKV_D = QKV_F + 192 * 64 * 4;    // (64 x 192)  data gradient
+  static constexpr size_t WO_F = QKV_D + 64 * 192 * 4;     // (64 x 64)
+  static constexpr size_t WO_D = WO_F + 64 * 64 * 4;
+  static constexpr size_t W1_F = WO_D + 64 * 64 * 4;       // (256 x 64)
+  static constexpr size_t W1_D = W1_F + 256 * 64 * 4;      // (64 x 256)
+  static constexpr size_t W2_F = W1_D + 64 * 256 * 4;      // (64 x 256)
+  static constexpr size_t W2_D = W2_F + 64 * 256 * 4;      // (256 x 64)
+  static constexpr size_t BQKV = W2_D + 256 * 64 * 4;      // 192 floats
+  static constexpr size_t BYTES = BQKV + 1024;
+};
+constexpr size_t MAP_WP_BYTES = 2 * 64 * 64 * 4;
 
 SaveLayout save_layout(const eegclip_tower_desc& d) {
   SaveLayout L;
@@ -52,7 +69,9 @@ SaveLayout save_layout(const eegclip_tower_desc& d) {
   L.conv_stride = 2 * n * C + align_up((size_t)2 * d.B, 4);
   L.x_qkv = 0; L.x_o = n * AQKV; L.x_lse = L.x_o + n * C; L.x_z1 = L.x_lse + align_up((size_t)d.B * AH * d.T, 4);
   L.x_fpre = L.x_z1 + n * C; L.x_zout = L.x_fpre + n * FF;
-  L.xf_stride = L.x_zout + n * C;
+  L.x_wp = L.x_zout + n * C;
+  L.xf_stride = L.x_wp + XfPacked::BYTES / sizeof(float);
+  L.map_wp = o; o += MAP_WP_BYTES / sizeof(float);
   L.conv0 = o; o += L.conv_stride * d.n_conv;
   L.xf0 = o; o += L.xf_stride * d.depth;
   L.total = o;
@@ -60,7 +79,7 @@ SaveLayout save_layout(const eegclip_tower_desc& d) {
 }
 
 struct Scratch {
-  float *upad, *dypad, *h, *f, *dfpre, *dqkv, *d_o, *dg, *dza, *dzb, *dzc, *deeg, *wtmp;
+  float *upad, *dypad, *h, *f, *dfpre, *dqkv, *d_o, *dg, *dza, *dzb, *dzc, *deeg, *wtmp, *wgp;
   void* tc;
   size_t total;
 };
@@ -83,6 +102,7 @@ Scratch scratch_layout(const eegclip_tower_desc& d, float* base) {
   s.dzc = take(n * C);
   s.deeg = take(n * C);
   s.wtmp = take((size_t)C * C * d.taps);
+  s.wgp = take(lintc::lin_wgrad_partial_bytes(256, 64) / sizeof(float));
   s.tc = take(conv_tc_scratch_bytes(d.B, d.T, d.taps) / sizeof(float) + 64);
   s.total = o;
   return s;
@@ -222,11 +242,16 @@ int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP
   return EEGCLIP_OK;
 }
 
-struct XfSave { float *qkv, *o, *lse, *z1, *fpre, *zout; };
+struct XfSave { float *qkv, *o, *lse, *z1, *fpre, *zout; uint8_t* wp; };
+bool xf_tc_ok(const eegclip_tower_desc& d);
+int xf_block_fwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const float* zin, const XfSave& s, Scratch& w, cudaStream_t st);
+int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const XfG& g, const float* zin, const XfSave& s,
+                    const float* dzout, float* dzin, Scratch& w, cudaStream_t st);
 
 // TransformerEncoderBlock forward (clip_model.py:75-94).  zin -> zout
 int xf_block_fwd(const eegclip_tower_desc& d, int layer, const XfP& p, const float* zin, const XfSave& s, Scratch& w,
                  cudaStream_t st) {
+  if (xf_tc_ok(d)) return xf_block_fwd_tc(d, layer, p, zin, s, w, st);
   const long n = (long)d.B * d.T;
   TRY(ln64_fwd(zin, p.ln1g, p.ln1b, w.h, n, st));
   GemmEpi none;
@@ -253,6 +278,7 @@ int xf_block_fwd(const eegclip_tower_desc& d, int layer, const XfP& p, const flo
 // Backward: dzout -> dzin (both n*C). Parameter gradients accumulate into pre-zeroed buffers.
 int xf_block_bwd(const eegclip_tower_desc& d, int layer, const XfP& p, const XfG& g, const float* zin, const XfSave& s,
                  const float* dzout, float* dzin, Scratch& w, cudaStream_t st) {
+  if (xf_tc_ok(d)) return xf_block_bwd_tc(d, layer, p, g, zin, s, dzout, dzin, w, st);
   const long n = (long)d.B * d.T;
   // ---- FFN branch -------------------------------------------------------------------------
   Drop d_out = make_drop(d.seed, layer, SITE_FFN_OUT, d.p_ffn_out, d.train);
@@ -294,9 +320,139 @@ int xf_block_bwd(const eegclip_tower_desc& d, int layer, const XfP& p, const XfG
   return EEGCLIP_OK;
 }
 
+
+// ---- tensor-core (tcgen05) token-GEMM path of the transformer block -----------------------------------------
+bool xf_tc_ok(const eegclip_tower_desc& d) { return d.math != EEGCLIP_MATH_FP32; }
+
+// fp32 weights of one block -> packed bf16 hi/lo operands (forward and data-gradient forms) + concatenated QKV bias
+int xf_pack(const XfP& p, uint8_t* wp, cudaStream_t st) {
+  using namespace lintc;
+  PackJobs J; J.n = 0;
+  const float* wqkv[3] = {p.wq, p.wk, p.wv};
+  const float* bqkv[3] = {p.bq, p.bk, p.bv};
+  for (int i = 0; i < 3; ++i) {
+    add_pack(J, wqkv[i], wp + XfPacked::QKV_F, 192, 64, 64 * i, 0, 64, 64, 64, 1);   // out n = 64*i + row, contraction k = column
+    add_pack(J, wqkv[i], wp + XfPacked::QKV_D, 64, 192, 0, 64 * i, 64, 64, 1, 64);   // out n' = column, contraction k' = 64*i + row
+    add_copy(J, bqkv[i], (float*)(wp + XfPacked::BQKV), 64 * i, 64);
+  }
+  add_pack(J, p.wo, wp + XfPacked::WO_F, 64, 64, 0, 0, 64, 64, 64, 1);
+  add_pack(J, p.wo, wp + XfPacked::WO_D, 64, 64, 0, 0, 64, 64, 1, 64);
+  add_pack(J, p.w1, wp + XfPacked::W1_F, 256, 64, 0, 0, 256, 64, 64, 1);
+  add_pack(J, p.w1, wp + XfPacked::W1_D, 64, 256, 0, 0, 64, 256, 1, 64);
+  add_pack(J, p.w2, wp + XfPacked::W2_F, 64, 256, 0, 0, 64, 256, 256, 1);
+  add_pack(J, p.w2, wp + XfPacked::W2_D, 256, 64, 0, 0, 256, 64, 1, 256);
+  return pack_launch(J, st);
+}
+
+lintc::LinTcArgs lin_args(const float* A, long lda, const uint8_t* w, float* Cp, long ldc, long M, int N, int K) {
+  lintc::LinTcArgs a{};
+  a.A = A; a.lda = lda; a.wpacked = w; a.C = Cp; a.ldc = ldc; a.M = (int)M; a.N = N; a.K = K;
+  a.pro = lintc::PRO_NONE; a.pro_drop = make_drop(0, 0, 0, 0.f, 0); a.drop = a.pro_drop;
+  return a;
+}
+
+int xf_block_fwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const float* zin, const XfSave& s, Scratch& w,
+                    cudaStream_t st) {
+  using namespace lintc;
+  const long n = (long)d.B * d.T;
+  TRY(xf_pack(p, s.wp, st));
+  TRY(ln64_fwd(zin, p.ln1g, p.ln1b, w.h, n, st));
+  {
+    LinTcArgs a = lin_args(w.h, C, s.wp + XfPacked::QKV_F, s.qkv, AQKV, n, AQKV, C);
+    a.bias = (const float*)(s.wp + XfPacked::BQKV);
+    TRY(lin_tc_launch(d.math, a, st));
+  }
+  TRY(attention_fwd(s.qkv, s.o, s.lse, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
+  {
+    LinTcArgs a = lin_args(s.o, C, s.wp + XfPacked::WO_F, s.z1, C, n, C, C);
+    a.bias = p.bo; a.drop = make_drop(d.seed, layer, SITE_PROJ, d.p_proj, d.train); a.drop_on = a.drop.enabled; a.residual = zin;
+    TRY(lin_tc_launch(d.math, a, st));
+  }
+  TRY(ln64_fwd(s.z1, p.ln2g, p.ln2b, w.h, n, st));
+  {
+    LinTcArgs a = lin_args(w.h, C, s.wp + XfPacked::W1_F, w.f, FF, n, FF, C);
+    a.bias = p.b1; a.act = 1; a.aux = s.fpre;
+    a.drop = make_drop(d.seed, layer, SITE_FFN_HID, d.p_ffn_hid, d.train); a.drop_on = a.drop.enabled;
+    TRY(lin_tc_launch(d.math, a, st));
+  }
+  {
+    LinTcArgs a = lin_args(w.f, FF, s.wp + XfPacked::W2_F, s.zout, C, n, C, FF);
+    a.bias = p.b2; a.drop = make_drop(d.seed, layer, SITE_FFN_OUT, d.p_ffn_out, d.train); a.drop_on = a.drop.enabled; a.residual = s.z1;
+    TRY(lin_tc_launch(d.math, a, st));
+  }
+  return EEGCLIP_OK;
+}
+
+int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const XfG& g, const float* zin, const XfSave& s,
+                    const float* dzout, float* dzin, Scratch& w, cudaStream_t st) {
+  using namespace lintc;
+  const long n = (long)d.B * d.T;
+  const Drop d_out = make_drop(d.seed, layer, SITE_FFN_OUT, d.p_ffn_out, d.train);
+  const Drop d_hid = make_drop(d.seed, layer, SITE_FFN_HID, d.p_ffn_hid, d.train);
+  const Drop d_proj = make_drop(d.seed, layer, SITE_PROJ, d.p_proj, d.train);
+  // ---- FFN branch: dg = dzout * mask_out (never materialised: prologue of both consumers) ----
+  {
+    LinWgradArgs a{};
+    a.dy = dzout; a.lddy = C; a.Nout = C; a.x = s.fpre; a.ldx = FF; a.Kin = FF; a.M = (int)n;
+    a.pro_dy = d_out.enabled ? PRO_DROP : PRO_NONE; a.drop_dy = d_out;
+    a.pro_x = PRO_GELU_DROP; a.drop_x = d_hid;                       // f = dropout(GELU(fpre)) recomputed on the fly
+    a.partial = w.wgp;
+    float* dW[3] = {g.w2, nullptr, nullptr}; float* db[3] = {g.b2, nullptr, nullptr};
+    TRY(lin_wgrad_launch(d.math, a, dW, db, C, st));
+  }
+  {
+    LinTcArgs a = lin_args(dzout, C, s.wp + XfPacked::W2_D, w.dfpre, FF, n, FF, C);
+    a.pro = d_out.enabled ? PRO_DROP : PRO_NONE; a.pro_drop = d_out;
+    a.drop = d_hid; a.drop_on = d_hid.enabled; a.act_grad_src = s.fpre;
+    TRY(lin_tc_launch(d.math, a, st));
+  }
+  TRY(ln64_fwd(s.z1, p.ln2g, p.ln2b, w.h, n, st));
+  {
+    LinWgradArgs a{};
+    a.dy = w.dfpre; a.lddy = FF; a.Nout = FF; a.x = w.h; a.ldx = C; a.Kin = C; a.M = (int)n;
+    a.drop_dy = d_out; a.drop_x = d_out; a.partial = w.wgp;
+    float* dW[3] = {g.w1, nullptr, nullptr}; float* db[3] = {g.b1, nullptr, nullptr};
+    TRY(lin_wgrad_launch(d.math, a, dW, db, FF, st));
+  }
+  {
+    LinTcArgs a = lin_args(w.dfpre, FF, s.wp + XfPacked::W1_D, w.d_o, C, n, C, FF);     // d_o reused as dh2
+    TRY(lin_tc_launch(d.math, a, st));
+  }
+  TRY(ln64_bwd(w.d_o, s.z1, p.ln2g, dzout, w.dzc, g.ln2g, g.ln2b, n, st));              // dzc = dz1
+  // ---- attention branch: dp = dz1 * mask_proj (prologue) ----
+  {
+    LinWgradArgs a{};
+    a.dy = w.dzc; a.lddy = C; a.Nout = C; a.x = s.o; a.ldx = C; a.Kin = C; a.M = (int)n;
+    a.pro_dy = d_proj.enabled ? PRO_DROP : PRO_NONE; a.drop_dy = d_proj; a.drop_x = d_proj; a.partial = w.wgp;
+    float* dW[3] = {g.wo, nullptr, nullptr}; float* db[3] = {g.bo, nullptr, nullptr};
+    TRY(lin_wgrad_launch(d.math, a, dW, db, C, st));
+  }
+  {
+    LinTcArgs a = lin_args(w.dzc, C, s.wp + XfPacked::WO_D, w.d_o, C, n, C, C);         // grad wrt attention output
+    a.pro = d_proj.enabled ? PRO_DROP : PRO_NONE; a.pro_drop = d_proj;
+    TRY(lin_tc_launch(d.math, a, st));
+  }
+  TRY(attention_bwd(s.qkv, s.o, w.d_o, s.lse, w.dqkv, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
+  TRY(ln64_fwd(zin, p.ln1g, p.ln1b, w.h, n, st));
+  {
+    LinWgradArgs a{};
+    a.dy = w.dqkv; a.lddy = AQKV; a.Nout = AQKV; a.x = w.h; a.ldx = C; a.Kin = C; a.M = (int)n;
+    a.drop_dy = d_out; a.drop_x = d_out; a.partial = w.wgp;
+    float* dW[3] = {g.wq, g.wk, g.wv}; float* db[3] = {g.bq, g.bk, g.bv};
+    TRY(lin_wgrad_launch(d.math, a, dW, db, C, st));
+  }
+  {
+    LinTcArgs a = lin_args(w.dqkv, AQKV, s.wp + XfPacked::QKV_D, w.d_o, C, n, C, AQKV);  // dh1 = dq.Wq + dk.Wk + dv.Wv
+    TRY(lin_tc_launch(d.math, a, st));
+  }
+
+  TRY(ln64_bwd(w.d_o, zin, p.ln1g, w.dzc, dzin, g.ln1g, g.ln1b, n, st));
+  return EEGCLIP_OK;
+}
+
 XfSave xf_save(float* save, const SaveLayout& L, int j) {
   float* b = save + L.xf0 + L.xf_stride * j;
-  return XfSave{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, b + L.x_zout};
+  return XfSave{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, b + L.x_zout, (uint8_t*)(b + L.x_wp)};
 }
 
 }  // namespace
@@ -528,7 +684,7 @@ int eegclip_xfblock_forward(const eegclip_xfblock_desc* d, const float* const* p
   eegclip_tower_desc t = xf_as_tower(d);
   SaveLayout L = save_layout(t);
   float* b = (float*)save;
-  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, zout};
+  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, zout, (uint8_t*)(b + L.x_wp)};
   Scratch w = scratch_layout(t, (float*)scratch);
   const float* const* tp = params - 2;  // xf_at() skips the two mapping entries
   return xf_block_fwd(t, d->layer, xf_at<XfP>(tp, 0, 0), zin, xs, w, (cudaStream_t)stream);
@@ -542,7 +698,7 @@ int eegclip_xfblock_backward(const eegclip_xfblock_desc* d, const float* const* 
   eegclip_tower_desc t = xf_as_tower(d);
   SaveLayout L = save_layout(t);
   float* b = (float*)save;
-  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, nullptr};
+  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, nullptr, (uint8_t*)(b + L.x_wp)};
   Scratch w = scratch_layout(t, (float*)scratch);
   if (grad_base && grad_bytes) CUDA_TRY(cudaMemsetAsync(grad_base, 0, grad_bytes, st));
   return xf_block_bwd(t, d->layer, xf_at<XfP>(params - 2, 0, 0), xf_at<XfG>(grads - 2, 0, 0), zin, xs, dzout, dzin, w, st);
