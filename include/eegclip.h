@@ -95,6 +95,8 @@ EEGCLIP_API const char* eegclip_build_info(void);
  * (tcgen05), 2 attention fwd, 3 attention bwd, 4 LayerNorm([C,T]) fwd+bwd, 5 fp32 GEMMs.  eegclip_profile_end
  * synchronises the device and returns summed milliseconds and launch counts per class (arrays of >= 8 entries). */
 EEGCLIP_API long long eegclip_launch_count(void);
+/* Development knob for kernel tuning sweeps (tools/bench_xfblock.py); 0 everywhere = shipped configuration. */
+EEGCLIP_API int eegclip_tune_set(int32_t key, int32_t value);
 EEGCLIP_API int eegclip_profile_begin(void);
 EEGCLIP_API int eegclip_profile_end(double* ms_by_class, long long* launches_by_class, int32_t n_classes);
 

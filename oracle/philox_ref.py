@@ -6,11 +6,11 @@ element index).  The reference uses torch's nn.Dropout (clip_model.py:27,65,86,9
 its masks cannot be reproduced bit-for-bit by any other RNG, so train-mode
 parity is checked by feeding *these* masks to the reference/oracle.
 
-Element index convention (shared with the kernels):
-    block = idx >> 2, lane = idx & 3
-    ctr   = (block & 0xffffffff, block >> 32, stream, 0)
-    key   = (seed & 0xffffffff, seed >> 32)
-    keep  = philox(ctr, key)[lane] >= floor(p * 2**32)
+Element index convention (shared with the kernels).  Philox block b = philox(ctr = (b lo, b hi, stream, 0), key = seed).
+  p != 0.5 : 16 bits per decision, 8 per Philox call
+      block = idx >> 3, e = idx & 7 ; draw = (words[e >> 1] >> (16 * (e & 1))) & 0xffff ; keep = draw >= floor(p * 2**16)
+  p == 0.5 : ONE bit per decision, 128 per Philox call (the attention / projection / FFN sites of the encoder)
+      block = idx >> 7, e = idx & 127 ; keep = (words[e >> 5] >> (e & 31)) & 1
 """
 import numpy as np
 
@@ -47,20 +47,28 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def dropout_threshold(p):
-    return np.uint32(min(int(np.floor(float(p) * 4294967296.0)), 0xFFFFFFFF))
+    return np.uint32(min(int(np.floor(float(p) * 65536.0)), 0xFFFF))
 
 
 def keep_mask(n, seed, stream, p):
     """Boolean keep mask for element indices 0..n-1 (flat, C order)."""
     n = int(n)
-    nb = (n + 3) // 4
+    onebit = float(np.float32(p)) == 0.5
+    per = 128 if onebit else 8
+    nb = (n + per - 1) // per
     blk = np.arange(nb, dtype=np.uint64)
     c0 = (blk & MASK32).astype(np.uint32)
     c1 = (blk >> np.uint64(32)).astype(np.uint32)
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     w = philox4x32_10(c0, c1, np.uint32(stream), np.uint32(0), seed & 0xFFFFFFFF, seed >> 32)
-    words = np.stack(w, axis=1).reshape(-1)[:n]
-    return words >= dropout_threshold(p)
+    words = np.stack(w, axis=1)                                   # (nb, 4)
+    if onebit:
+        bits = (words[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & np.uint32(1)
+        return bits.reshape(-1)[:n].astype(bool)                  # element e -> word e>>5, bit e&31
+    lo = words & np.uint32(0xFFFF)
+    hi = words >> np.uint32(16)
+    draws = np.stack([lo, hi], axis=2).reshape(-1)[:n]            # element e -> word e>>1, half e&1
+    return draws >= dropout_threshold(p)
 
 
 def stream_id(layer, site):

@@ -25,6 +25,7 @@ namespace eegclip {
 
 // ---- launch accounting + optional per-kernel-class device timing (bench.py roofline; see eegclip_profile_*) ----
 extern long long g_launch_count;
+extern int g_tune[16];   // development knobs (eegclip_tune_set): 0 lin ring depth, 1 streaming-load policy
 enum : int { PROF_CONV_TC = 0, PROF_WGRAD_TC = 1, PROF_ATTN_FWD = 2, PROF_ATTN_BWD = 3, PROF_LNCT = 4, PROF_GEMM_F32 = 5, PROF_LIN_TC = 6, PROF_LIN_WGRAD = 7, PROF_NCLASS = 8 };
 void prof_begin(int cls, cudaStream_t st);
 void prof_end(int cls, cudaStream_t st);
@@ -40,9 +41,10 @@ enum : int { SITE_CONV = 0, SITE_ATTN = 1, SITE_PROJ = 2, SITE_FFN_HID = 3, SITE
 struct Drop {
   uint32_t seed_lo, seed_hi;
   uint32_t stream;
-  uint32_t thresh;   // keep iff word >= thresh
+  uint32_t thresh;   // 16-bit mode: keep iff 16-bit draw >= thresh  (thresh = floor(p * 65536))
   float scale;       // 1/(1-p); p == 0 -> disabled (thresh 0, scale 1)
   int enabled;
+  int onebit;        // p == 0.5 exactly: ONE bit per decision (128 decisions per Philox call), keep iff bit set
 };
 
 __host__ inline Drop make_drop(uint64_t seed, int layer, int site, float p, int train) {
@@ -51,8 +53,9 @@ __host__ inline Drop make_drop(uint64_t seed, int layer, int site, float p, int 
   d.seed_hi = (uint32_t)(seed >> 32);
   d.stream = (uint32_t)(layer * 16 + site);
   d.enabled = (train && p > 0.f) ? 1 : 0;
-  double t = floor((double)p * 4294967296.0);
-  if (t > 4294967295.0) t = 4294967295.0;
+  d.onebit = (d.enabled && p == 0.5f) ? 1 : 0;
+  double t = floor((double)p * 65536.0);
+  if (t > 65535.0) t = 65535.0;
   d.thresh = d.enabled ? (uint32_t)t : 0u;
   d.scale = d.enabled ? 1.0f / (1.0f - p) : 1.0f;
   return d;
@@ -72,26 +75,51 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return make_uint4(c0, c1, c2, c3);
 }
 
-// The four random words covering element indices [4*block, 4*block+3].
+// Dropout decisions (oracle/philox_ref.py::keep_mask).  Philox block `blk` = philox(ctr = (blk lo, blk hi, stream, 0), key = seed).
+//   16-bit mode (p != 0.5): block = idx >> 3; element e = idx & 7 draws (word[e >> 1] >> (16 * (e & 1))) & 0xffff, keep iff >= thresh
+//   1-bit  mode (p == 0.5): block = idx >> 7; element e = idx & 127 keeps iff bit (e & 31) of word[e >> 5] is set
 __device__ __forceinline__ uint4 drop_words(const Drop& d, uint64_t block) {
   return philox4x32_10((uint32_t)(block & 0xffffffffull), (uint32_t)(block >> 32), d.stream, 0u, d.seed_lo, d.seed_hi);
+}
+__device__ __forceinline__ uint32_t word_of(const uint4& w, uint32_t i) { return i == 0 ? w.x : i == 1 ? w.y : i == 2 ? w.z : w.w; }
+
+// keep bits (bit e <-> element idx + e) of the 8 consecutive elements starting at idx (idx % 8 == 0)
+__device__ __forceinline__ uint32_t drop_bits8(const Drop& d, uint64_t idx) {
+  if (!d.enabled) return 0xffu;
+  if (d.onebit) {
+    const uint4 w = drop_words(d, idx >> 7);
+    const uint32_t e = (uint32_t)(idx & 127);
+    return (word_of(w, e >> 5) >> (e & 31)) & 0xffu;
+  }
+  const uint4 w = drop_words(d, idx >> 3);
+  const uint32_t t = d.thresh;
+  uint32_t m = 0;
+  m |= ((w.x & 0xffffu) >= t) ? 1u : 0u;   m |= ((w.x >> 16) >= t) ? 2u : 0u;
+  m |= ((w.y & 0xffffu) >= t) ? 4u : 0u;   m |= ((w.y >> 16) >= t) ? 8u : 0u;
+  m |= ((w.z & 0xffffu) >= t) ? 16u : 0u;  m |= ((w.z >> 16) >= t) ? 32u : 0u;
+  m |= ((w.w & 0xffffu) >= t) ? 64u : 0u;  m |= ((w.w >> 16) >= t) ? 128u : 0u;
+  return m;
 }
 
 // Multiplier (0 or 1/(1-p)) for a single element index.
 __device__ __forceinline__ float drop_mult(const Drop& d, uint64_t idx) {
   if (!d.enabled) return 1.0f;
-  uint4 w = drop_words(d, idx >> 2);
-  uint32_t lane = (uint32_t)(idx & 3);
-  uint32_t word = lane == 0 ? w.x : lane == 1 ? w.y : lane == 2 ? w.z : w.w;
-  return word >= d.thresh ? d.scale : 0.0f;
+  const uint32_t bits = drop_bits8(d, idx & ~7ull);
+  return (bits >> (uint32_t)(idx & 7)) & 1u ? d.scale : 0.0f;
+}
+
+// Multipliers for the 8 consecutive elements starting at idx (idx % 8 == 0).
+__device__ __forceinline__ void drop_mult8(const Drop& d, uint64_t idx, float* m) {
+  const uint32_t bits = drop_bits8(d, idx);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m[e] = (bits >> e) & 1u ? d.scale : 0.f;
 }
 
 // Multipliers for the 4 consecutive elements starting at idx (idx % 4 == 0).
 __device__ __forceinline__ float4 drop_mult4(const Drop& d, uint64_t idx) {
   if (!d.enabled) return make_float4(1.f, 1.f, 1.f, 1.f);
-  uint4 w = drop_words(d, idx >> 2);
-  return make_float4(w.x >= d.thresh ? d.scale : 0.f, w.y >= d.thresh ? d.scale : 0.f,
-                     w.z >= d.thresh ? d.scale : 0.f, w.w >= d.thresh ? d.scale : 0.f);
+  const uint32_t bits = drop_bits8(d, idx & ~7ull) >> (uint32_t)(idx & 4);
+  return make_float4(bits & 1u ? d.scale : 0.f, bits & 2u ? d.scale : 0.f, bits & 4u ? d.scale : 0.f, bits & 8u ? d.scale : 0.f);
 }
 
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }

@@ -26,7 +26,7 @@ namespace eegclip {
 namespace convtc {
 
 constexpr int CH = 64;               // channels in == out
-constexpr int TAPS = 64;
+constexpr int MAX_TAPS = 64;         // kernel sizes 16..64 (multiples of 16): 64 for the EEG tower, 32 for the speech BasicBlock
 constexpr int NSTAGE = 4;            // weight ring depth
 constexpr int W_PLANE_BYTES = CH * CH * 2;      // 8 KB: one tap, one plane, [ci chunk][co][8]
 constexpr int W_TAP_BYTES = 2 * W_PLANE_BYTES;  // hi + lo
@@ -38,7 +38,7 @@ constexpr int WG_MAX_GROUPS = 37;    // 4 tap groups x 37 sample groups = 148 CT
 //   mode 0 (forward) : n = co, contraction index = ci, tap = k
 //   mode 1 (dgrad)   : n = ci, contraction index = co, tap k' holds W[..][..][63-k']
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int mode) {
+__global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int mode, int TAPS) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over taps * 8 chunks * 64 n
   if (i >= TAPS * 8 * CH) return;
   int n = i & 63, ch = (i >> 6) & 7, tap = i >> 9;
@@ -64,11 +64,12 @@ struct ConvTcArgs {
   int T;                  // output rows
   int src_rows;           // valid source rows
   int row_off;            // smem row r holds src row r - row_off (zero outside)
+  int taps;               // kernel size
   Drop drop;
 };
 
-__host__ __device__ inline uint32_t conv_smem_bytes(int T) {
-  uint32_t TP = T + TAPS - 1;
+__host__ __device__ inline uint32_t conv_smem_bytes(int T, int taps) {
+  uint32_t TP = T + taps - 1;
   return 2u * 8u * TP * 16u + NSTAGE * W_TAP_BYTES + 128;
 }
 
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x;
-  const int T = a.T, TP = T + TAPS - 1;
+  const int T = a.T, TAPS = a.taps, TP = T + TAPS - 1;
   const uint32_t CS = (uint32_t)TP * 16u;   // chunk stride (bytes)
   const uint32_t PS = 8u * CS;              // plane stride
   uint8_t* sA = smem;
@@ -220,8 +221,8 @@ struct WgradTcArgs {
   const float* xin;     // (B,T,64) conv input
   const float* skip;    // optional addend
   const float* dypad;   // (B,TP,64) zero-padded output gradient, valid rows [PLb, PLb+T)
-  float* partial;       // [groups][TAPS][64 co][64 ci]
-  int B, T, PL, PLb, groups;
+  float* partial;       // [groups][taps][64 co][64 ci]
+  int B, T, PL, PLb, groups, taps;
 };
 
 __host__ __device__ inline uint32_t wgrad_smem_bytes(int T) {
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a)
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tg = blockIdx.x, grp = blockIdx.y;
-  const int T = a.T, TU = T + WG_TAPS - 1;
+  const int T = a.T, TAPS = a.taps, TU = T + WG_TAPS - 1;
   const int k0 = tg * WG_TAPS;
   const uint32_t CSU = (uint32_t)TU * 16u, PSU = 8u * CSU;
   const uint32_t CSD = (uint32_t)T * 16u, PSD = 8u * CSD;
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a)
 }
 
 // dW[co][ci][k] = sum_g partial[g][k][co][ci]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int groups) {
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int groups, int TAPS) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over k*4096 + co*64 + ci
   if (i >= TAPS * CH * CH) return;
   float s = 0.f;
@@ -358,21 +359,21 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 // Interface used by tower.cu
 // ------------------------------------------------------------------------------------------------
 inline bool conv_tc_supported(int Cin, int Cout, int taps, int T) {
-  return Cin == 64 && Cout == 64 && taps == 64 && T >= 64 && (T % 64) == 0 && T <= 512;
+  return Cin == 64 && Cout == 64 && taps >= 16 && taps <= convtc::MAX_TAPS && (taps % 16) == 0 && T >= 64 && (T % 64) == 0 && T <= 512;
 }
 
 // scratch: packed weights (1 MB) + weight-gradient partials (groups MB)
 inline size_t conv_tc_scratch_bytes(int B, int T, int taps) {
   (void)T;
-  if (taps != 64) return 0;
+  if (taps > convtc::MAX_TAPS || (taps % 16)) return 0;
   int groups = B < convtc::WG_MAX_GROUPS ? B : convtc::WG_MAX_GROUPS;
-  return (size_t)convtc::TAPS * convtc::W_TAP_BYTES + (size_t)groups * 64 * 64 * 64 * sizeof(float) + 256;
+  return (size_t)taps * convtc::W_TAP_BYTES + (size_t)groups * taps * 64 * 64 * sizeof(float) + 256;
 }
 
 template <int NTERMS>
 inline int conv_tc_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
   static bool configured = false;
-  uint32_t smem = convtc::conv_smem_bytes(a.T);
+  uint32_t smem = convtc::conv_smem_bytes(a.T, a.taps);
   if (!configured) {
     if (cudaFuncSetAttribute(convtc::conv64_tc_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return EEGCLIP_ERR_CUDA;
@@ -385,12 +386,12 @@ inline int conv_tc_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
 }
 
 inline int conv_tc_forward(int math, const float* xin, const float* skip_in, const float* w, const float* bias, float* y, int B, int T,
-                           int PL, const Drop& drop, void* scratch, cudaStream_t st) {
+                           int taps, int PL, const Drop& drop, void* scratch, cudaStream_t st) {
   uint8_t* wp = (uint8_t*)scratch;
-  convtc::pack_conv_weights_kernel<<<(convtc::TAPS * 8 * 64 + 255) / 256, 256, 0, st>>>(w, wp, 0);
+  convtc::pack_conv_weights_kernel<<<(taps * 8 * 64 + 255) / 256, 256, 0, st>>>(w, wp, 0, taps);
   LAUNCH_CHECK();
   convtc::ConvTcArgs a;
-  a.src = xin; a.skip = skip_in; a.wpacked = wp; a.bias = bias; a.out = y; a.T = T; a.src_rows = T; a.row_off = PL; a.drop = drop;
+  a.src = xin; a.skip = skip_in; a.wpacked = wp; a.bias = bias; a.out = y; a.T = T; a.src_rows = T; a.row_off = PL; a.taps = taps; a.drop = drop;
   return math == EEGCLIP_MATH_BF16 ? conv_tc_launch<1>(a, B, st) : conv_tc_launch<3>(a, B, st);
 }
 
@@ -402,7 +403,7 @@ inline int wgrad_tc_launch(const convtc::WgradTcArgs& a, cudaStream_t st) {
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
-  dim3 grid(convtc::TAPS / convtc::WG_TAPS, a.groups);
+  dim3 grid(a.taps / convtc::WG_TAPS, a.groups);
   ProfScope prof(PROF_WGRAD_TC, st);
   convtc::wgrad64_tc_kernel<NTERMS><<<grid, 256, convtc::wgrad_smem_bytes(a.T), st>>>(a);
   LAUNCH_CHECK();
@@ -410,24 +411,24 @@ inline int wgrad_tc_launch(const convtc::WgradTcArgs& a, cudaStream_t st) {
 }
 
 // du = dgrad(dypad, w) ; dw = wgrad(dypad, xin + skip_in)
-inline int conv_tc_backward(int math, const float* xin, const float* skip_in, const float* w, const float* dypad, int PLb, float* du,
-                            float* dw, int B, int T, void* scratch, cudaStream_t st) {
+inline int conv_tc_backward(int math, const float* xin, const float* skip_in, const float* w, const float* dypad, int taps, int PLb,
+                            float* du, float* dw, int B, int T, void* scratch, cudaStream_t st) {
   uint8_t* wp = (uint8_t*)scratch;
-  float* partial = (float*)(wp + (size_t)convtc::TAPS * convtc::W_TAP_BYTES);
-  const int TP = T + convtc::TAPS - 1;
-  convtc::pack_conv_weights_kernel<<<(convtc::TAPS * 8 * 64 + 255) / 256, 256, 0, st>>>(w, wp, 1);
+  float* partial = (float*)(wp + (size_t)taps * convtc::W_TAP_BYTES);
+  const int TP = T + taps - 1;
+  convtc::pack_conv_weights_kernel<<<(taps * 8 * 64 + 255) / 256, 256, 0, st>>>(w, wp, 1, taps);
   LAUNCH_CHECK();
   convtc::ConvTcArgs a;
-  a.src = dypad; a.skip = nullptr; a.wpacked = wp; a.bias = nullptr; a.out = du; a.T = T; a.src_rows = TP; a.row_off = 0;
+  a.src = dypad; a.skip = nullptr; a.wpacked = wp; a.bias = nullptr; a.out = du; a.T = T; a.src_rows = TP; a.row_off = 0; a.taps = taps;
   a.drop = make_drop(0, 0, 0, 0.f, 0);
   int rc = math == EEGCLIP_MATH_BF16 ? conv_tc_launch<1>(a, B, st) : conv_tc_launch<3>(a, B, st);
   if (rc != EEGCLIP_OK) return rc;
   convtc::WgradTcArgs g;
-  g.xin = xin; g.skip = skip_in; g.dypad = dypad; g.partial = partial; g.B = B; g.T = T; g.PL = convtc::TAPS - 1 - PLb; g.PLb = PLb;
+  g.xin = xin; g.skip = skip_in; g.dypad = dypad; g.partial = partial; g.B = B; g.T = T; g.PL = taps - 1 - PLb; g.PLb = PLb; g.taps = taps;
   g.groups = B < convtc::WG_MAX_GROUPS ? B : convtc::WG_MAX_GROUPS;
   rc = math == EEGCLIP_MATH_BF16 ? wgrad_tc_launch<1>(g, st) : wgrad_tc_launch<3>(g, st);
   if (rc != EEGCLIP_OK) return rc;
-  convtc::wgrad_reduce_kernel<<<(convtc::TAPS * 64 * 64 + 255) / 256, 256, 0, st>>>(partial, dw, g.groups);
+  convtc::wgrad_reduce_kernel<<<(taps * 64 * 64 + 255) / 256, 256, 0, st>>>(partial, dw, g.groups, taps);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

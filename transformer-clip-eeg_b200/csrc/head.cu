@@ -12,6 +12,7 @@ using namespace eegclip;
 // ---- launch accounting / per-kernel-class timing state (declared in common.cuh) ---------------------------
 namespace eegclip {
 long long g_launch_count = 0;
+int g_tune[16] = {0};
 constexpr int PROF_MAX = 8192;
 static bool g_prof_on = false;
 static int g_prof_n = 0;
@@ -191,6 +192,12 @@ extern "C" {
 int eegclip_abi_version(void) { return EEGCLIP_ABI_VERSION; }
 
 long long eegclip_launch_count(void) { return eegclip::g_launch_count; }
+
+int eegclip_tune_set(int32_t key, int32_t value) {
+  if (key < 0 || key >= 16) return EEGCLIP_ERR_ARG;
+  eegclip::g_tune[key] = value;
+  return EEGCLIP_OK;
+}
 
 int eegclip_profile_begin(void) {
   using namespace eegclip;

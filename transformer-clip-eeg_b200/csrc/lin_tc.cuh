@@ -6,13 +6,15 @@
 //
 //   lin_tc_kernel   C[m][n] = epi( sum_k pro(A[m][k]) * W[n][k] )        (forward and data gradient: W or W^T packed)
 //     persistent CTAs, warp-specialised:
-//       warps 0-3  epilogue : TMEM -> registers -> per-warp smem transpose -> coalesced 128-bit global stores with
+//       warps 0-7  epilogue : TMEM -> registers -> per-warp smem transpose -> coalesced 128-bit global stores with
 //                             bias / GELU(+pre-activation save) / Philox dropout / GELU' / residual fused
-//       warps 4-7  producers: coalesced 128-bit loads of a 128-token x 64-feature fp32 chunk (+ optional dropout /
+//                             (warp w: TMEM lane quarter w%4, column half w/4)
+//       warps 8-11 producers: coalesced 128-bit loads of a 128-token x 64-feature fp32 chunk (+ optional dropout /
 //                             GELU.dropout prologue), split into bf16 hi/lo planes in the chunk-major UMMA layout
-//                             (tc_common.cuh), 4-stage ring signalled on mbarriers
-//       warp  8    MMA      : one thread issues tcgen05.mma (M=128, N = full output width <= 256) into one of two TMEM
-//                             accumulator buffers, so the epilogue of tile i overlaps the MMAs of tile i+1
+//                             (tc_common.cuh), 3-stage ring signalled on mbarriers
+//       warp  12   MMA      : one elected lane issues tcgen05.mma (M=128, N = full output width <= 256) into one of two
+//                             TMEM accumulator buffers, so the epilogue of tile i overlaps the MMAs of tile i+1
+//     (the erf / Philox work of the epilogues needs 8 warps: with 4 it was issue-bound at ~100 us per launch)
 //     the packed weights (<= 64 KB) are fetched once per CTA by a 1-D bulk async copy (TMA engine) and stay resident.
 //
 //   lin_wgrad_tc_kernel   dW[n][k] = sum_m pro(dy[m][n]) * pro(x[m][k]),  db[n] = sum_m pro(dy[m][n])
@@ -30,15 +32,25 @@ namespace lintc {
 
 constexpr int BM = 128;                  // tokens per tile
 constexpr int KC = 64;                   // features per pipeline chunk
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 3;                // maximum ring depth (runtime depth in LinTcArgs::nstage)
 constexpr int A_CS = BM * 16;            // stride between 8-feature chunks inside a plane (bytes)
 constexpr int A_PLANE = (KC / 8) * A_CS; // 16 KB
 constexpr int A_STAGE = 2 * A_PLANE;     // hi + lo
 constexpr int EPI_LD = 36;               // floats per staged row (32 + pad: 16 B aligned, conflict-free 128-bit access)
 constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
-constexpr int NTHREADS = 288;
+constexpr int NEPI = 8, NPROD = 4;           // epilogue / producer warps (13 warps: <= 4 per scheduler -> 128 registers each)
+constexpr int NTHREADS = (NEPI + NPROD + 1) * 32;
 
 enum : int { PRO_NONE = 0, PRO_DROP = 1, PRO_GELU_DROP = 2 };
+
+// streaming 128-bit load.  The CTAs here keep > 160 KB of shared memory, which leaves only a few KB of L1: plain
+// (allocating) loads then throttle on free L1 lines long before HBM saturates, so activations bypass L1 allocation.
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_act(const float4* p, int policy) { return policy == 1 ? __ldg(p) : ld_stream(p); }
 
 // ------------------------------------------------------------------------------------------------
 // Weight packing.  Packed operand B (Ntot x Ktot, "n" = output feature, "k" = contraction index):
@@ -104,7 +116,7 @@ inline size_t packed_bytes(int N, int K) { return (size_t)N * K * 4; }
 template <int ROWS, int NTERMS, int NPW /* producer warps */>
 __device__ __forceinline__ void stage_chunk(const float* __restrict__ src, long ld, long row0, long rows_total, int col0, int ncols_total,
                                             uint8_t* dst, uint32_t CS, uint32_t PS, int pw, int lane, int pro, const Drop& drop,
-                                            float* colsum /* nullptr or 8 running sums */) {
+                                            float* colsum /* nullptr or 8 running sums */, int policy) {
   constexpr int NBLK = (ROWS / 8) * 2;      // (row block, chunk half) combos
   constexpr int ITERS = NBLK / NPW;
   static_assert(NBLK % NPW == 0, "producer warps must divide the chunk");
@@ -116,7 +128,7 @@ __device__ __forceinline__ void stage_chunk(const float* __restrict__ src, long 
     const long r = row0 + rb * 8 + (lane & 7);
     if (r < rows_total) {
       const float4* p = reinterpret_cast<const float4*>(src + r * ld + col0 + ch * 8);
-      x0[it] = __ldg(p); x1[it] = __ldg(p + 1);
+      x0[it] = ld_act(p, policy); x1[it] = ld_act(p + 1, policy);
     } else {
       x0[it] = make_float4(0.f, 0.f, 0.f, 0.f); x1[it] = x0[it];
     }
@@ -130,8 +142,8 @@ __device__ __forceinline__ void stage_chunk(const float* __restrict__ src, long 
       const long r = row0 + rl;
       if (r < rows_total) {
         const uint64_t idx = (uint64_t)r * (uint64_t)ncols_total + (uint64_t)(col0 + ch * 8);
-        const float4 m0 = drop_mult4(drop, idx), m1 = drop_mult4(drop, idx + 4);
-        const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        float mm[8];
+        drop_mult8(drop, idx, mm);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = (pro == PRO_GELU_DROP ? gelu_f(v[e]) : v[e]) * mm[e];
       }
@@ -162,10 +174,12 @@ struct LinTcArgs {
   int drop_on; Drop drop;         // v *= dropmult(m*N + n)
   const float* act_grad_src;      // v *= GELU'(src[m][n])
   const float* residual;          // v += residual[m][n]
+  int nstage;                     // ring depth (2..NSTAGE)
+  int policy;                     // load policy of the streamed activations (0: L1 no-allocate, 1: __ldg)
 };
 
-inline uint32_t lin_smem_bytes(int N, int K) {
-  return (uint32_t)packed_bytes(N, K) + NSTAGE * A_STAGE + 4 * EPI_WARP_FLOATS * 4 + 256;
+inline uint32_t lin_smem_bytes(int N, int K, int nstage = NSTAGE) {
+  return (uint32_t)packed_bytes(N, K) + nstage * A_STAGE + NEPI * EPI_WARP_FLOATS * 4 + 256;
 }
 
 template <int NTERMS>
@@ -176,24 +190,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
   const uint32_t WP = (uint32_t)N * K * 2;                 // weight plane bytes
   uint8_t* sW = smem;
   uint8_t* sA = smem + 2 * WP;
-  float* sE = reinterpret_cast<float*>(sA + NSTAGE * A_STAGE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + 4 * EPI_WARP_FLOATS);
-  uint64_t* full = bars;                  // [NSTAGE] producers -> MMA   (128 arrivals)
+  const int nstage = a.nstage;
+  float* sE = reinterpret_cast<float*>(sA + nstage * A_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + NEPI * EPI_WARP_FLOATS);
+  uint64_t* full = bars;                  // [NSTAGE] producers -> MMA   (NPROD*32 arrivals)
   uint64_t* empty = bars + NSTAGE;        // [NSTAGE] MMA -> producers   (tcgen05.commit)
   uint64_t* accfull = bars + 2 * NSTAGE;  // [2] MMA -> epilogue
-  uint64_t* accempty = accfull + 2;       // [2] epilogue -> MMA         (128 arrivals)
+  uint64_t* accempty = accfull + 2;       // [2] epilogue -> MMA         (NEPI*32 arrivals)
   uint64_t* wfull = accempty + 2;         // weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  constexpr int MMA_WARP = NEPI + NPROD;
 
   uint32_t ncols = 32;
   while (ncols < 2u * (uint32_t)N) ncols <<= 1;
   if (tid == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 128); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&accfull[i], 1); tc::mbar_init(&accempty[i], 128); }
+    for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], NPROD * 32); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&accfull[i], 1); tc::mbar_init(&accempty[i], NEPI * 32); }
     tc::mbar_init(wfull, 1);
     tc::mbar_fence_init();
   }
-  if (warp == 8) tc::tmem_alloc(tmem_slot, ncols);
+  if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, ncols);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -201,21 +217,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
   const int ntiles = (a.M + BM - 1) / BM;
   const int nchunk = K / KC;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= NEPI && warp < MMA_WARP) {
     // ===== producers =====
-    const int pw = warp - 4;
-    uint32_t c = 0;
+    const int pw = warp - NEPI;
+    int s = 0; uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      for (int kc = 0; kc < nchunk; ++kc, ++c) {
-        const int s = c % NSTAGE;
-        tc::mbar_wait(&empty[s], ((c / NSTAGE) & 1) ^ 1);
-        stage_chunk<BM, NTERMS, 4>(a.A, a.lda, (long)tile * BM, a.M, kc * KC, K, sA + s * A_STAGE, A_CS, A_PLANE, pw, lane, a.pro,
-                                   a.pro_drop, nullptr);
+      for (int kc = 0; kc < nchunk; ++kc) {
+        tc::mbar_wait(&empty[s], ph ^ 1);
+        stage_chunk<BM, NTERMS, NPROD>(a.A, a.lda, (long)tile * BM, a.M, kc * KC, K, sA + s * A_STAGE, A_CS, A_PLANE, pw, lane, a.pro,
+                                       a.pro_drop, nullptr, a.policy);
         tc::fence_async_smem();
         tc::mbar_arrive(&full[s]);
+        if (++s == nstage) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     // ===== weights (once) + MMA issue: the whole warp runs the loop, one elected lane issues =====
     const uint32_t wbytes = NTERMS > 1 ? 2 * WP : WP;
     if (tc::elect_one()) {
@@ -227,15 +243,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
     const uint32_t sA_u = tc::smem_u32(sA), sW_u = tc::smem_u32(sW);
     const uint32_t idesc = tc::idesc_bf16(128, N, 0, 0);
     const uint32_t nb16 = (uint32_t)N * 16u;
-    uint32_t c = 0, t = 0;
+    uint32_t t = 0, ph = 0;
+    int s = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
       const uint32_t buf = t & 1;
       tc::mbar_wait(&accempty[buf], ((t >> 1) & 1) ^ 1);
       tc::tc_fence_after();
       const uint32_t d = tmem + buf * (uint32_t)N;
-      for (int kc = 0; kc < nchunk; ++kc, ++c) {
-        const int s = c % NSTAGE;
-        tc::mbar_wait(&full[s], (c / NSTAGE) & 1);
+      for (int kc = 0; kc < nchunk; ++kc) {
+        tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
         const uint64_t a_hi = tc::smem_desc(sA_u + s * A_STAGE, A_CS, 128);
         const uint64_t a_lo = tc::smem_desc(sA_u + s * A_STAGE + A_PLANE, A_CS, 128);
@@ -255,22 +271,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
           tc::tc_commit(&empty[s]);
         }
         __syncwarp();
+        if (++s == nstage) { s = 0; ph ^= 1; }
       }
       if (tc::elect_one()) tc::tc_commit(&accfull[buf]);
       __syncwarp();
     }
   } else {
-    // ===== epilogue (warps 0-3 == TMEM lane quarters 0-3) =====
-    const int q = warp;
-    float* stg = sE + q * EPI_WARP_FLOATS;
+    // ===== epilogue: warp w reads TMEM lane quarter w%4, columns [ (w/4)*N/2, (w/4+1)*N/2 ) =====
+    const int q = warp & 3, chalf = warp >> 2;
+    float* stg = sE + warp * EPI_WARP_FLOATS;
     const int cq = (lane & 7) * 4, rq = lane >> 3;      // coalesced phase: 4 columns x (4 rows per iteration)
+    const int cb0 = chalf * (N >> 1), cb1 = cb0 + (N >> 1);
     uint32_t t = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
       const uint32_t buf = t & 1;
       tc::mbar_wait(&accfull[buf], (t >> 1) & 1);
       tc::tc_fence_after();
       const long mrow0 = (long)tile * BM + q * 32;
-      for (int cb = 0; cb < N; cb += 32) {
+      for (int cb = cb0; cb < cb1; cb += 32) {
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)N + cb, v);
 #pragma unroll
@@ -279,7 +297,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
         const int n = cb + cq;
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.bias) bb = *reinterpret_cast<const float4*>(a.bias + n);
-#pragma unroll
+#pragma unroll 4
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + rq;
           const long m = mrow0 + rl;
@@ -296,11 +314,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
               r.x *= mk.x; r.y *= mk.y; r.z *= mk.z; r.w *= mk.w;
             }
             if (a.act_grad_src) {
-              const float4 s4 = *reinterpret_cast<const float4*>(a.act_grad_src + ci);
+              const float4 s4 = ld_act(reinterpret_cast<const float4*>(a.act_grad_src + ci), a.policy);
               r.x *= gelu_grad_f(s4.x); r.y *= gelu_grad_f(s4.y); r.z *= gelu_grad_f(s4.z); r.w *= gelu_grad_f(s4.w);
             }
             if (a.residual) {
-              const float4 s4 = *reinterpret_cast<const float4*>(a.residual + ci);
+              const float4 s4 = ld_act(reinterpret_cast<const float4*>(a.residual + ci), a.policy);
               r.x += s4.x; r.y += s4.y; r.z += s4.z; r.w += s4.w;
             }
             *reinterpret_cast<float4*>(a.C + ci) = r;
@@ -314,16 +332,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem, ncols);
+  if (warp == MMA_WARP) tc::tmem_dealloc(tmem, ncols);
 }
 
 inline bool lin_tc_supported(long M, int N, int K) {
   return M >= 1 && (N == 64 || N == 128 || N == 192 || N == 256) && (K % KC) == 0 && K >= KC &&
-         lin_smem_bytes(N, K) <= 227u * 1024u;
+         lin_smem_bytes(N, K, 2) <= 227u * 1024u;
 }
 
 template <int NTERMS>
-inline int lin_tc_launch_t(const LinTcArgs& a, cudaStream_t st) {
+inline int lin_tc_launch_t(LinTcArgs a, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(lin_tc_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
@@ -332,8 +350,11 @@ inline int lin_tc_launch_t(const LinTcArgs& a, cudaStream_t st) {
   }
   const int ntiles = (a.M + BM - 1) / BM;
   const int grid = ntiles < 148 ? ntiles : 148;
+  a.nstage = g_tune[0] >= 2 && g_tune[0] <= NSTAGE ? g_tune[0] : 2;
+  while (a.nstage > 2 && lin_smem_bytes(a.N, a.K, a.nstage) > 227u * 1024u) --a.nstage;
+  a.policy = g_tune[1];
   ProfScope prof(PROF_LIN_TC, st);
-  lin_tc_kernel<NTERMS><<<grid, NTHREADS, lin_smem_bytes(a.N, a.K), st>>>(a);
+  lin_tc_kernel<NTERMS><<<grid, NTHREADS, lin_smem_bytes(a.N, a.K, a.nstage), st>>>(a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -346,8 +367,10 @@ inline int lin_tc_launch(int math, const LinTcArgs& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 constexpr int WT = 64;                   // tokens per stage
 constexpr int W_CS = WT * 16;            // chunk stride (bytes)
-constexpr int WG_THREADS = 288;
+constexpr int WG_NPROD = 16;             // producer warps (they are the ALU-heavy role: convert + GELU/Philox prologues)
+constexpr int WG_THREADS = WG_NPROD * 32;   // warp 0 also issues the MMAs (16 warps: 128 registers each)
 constexpr int WG_MAX_CTAS = 148;
+constexpr int WG_MAXC = 5;               // 64-feature chunks of dy plus x per stage (Nout + Kin <= 320)
 
 struct LinWgradArgs {
   const float* dy; long lddy; int Nout;   // (M, Nout): rows of dW
@@ -357,10 +380,11 @@ struct LinWgradArgs {
   int pro_x; Drop drop_x;                 // prologue on x  (element index m*Kin + k)
   float* partial;                         // [ctas][Nout*Kin + Nout]
   int want_db;
+  int policy;                             // load policy of the streamed activations (0: L1 no-allocate, 1: __ldg)
 };
 
 inline uint32_t wgrad_stage_bytes(int Nout, int Kin) { return (uint32_t)(Nout + Kin) * WT * 4; }
-inline uint32_t wgrad_lin_smem_bytes(int Nout, int Kin) { return 2 * wgrad_stage_bytes(Nout, Kin) + 9 * 256 * 4 + 256; }
+inline uint32_t wgrad_lin_smem_bytes(int Nout, int Kin) { return 2 * wgrad_stage_bytes(Nout, Kin) + 8 * 256 * 4 + 256; }
 
 template <int NTERMS>
 __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWgradArgs a) {
@@ -369,8 +393,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
   const int Nout = a.Nout, Kin = a.Kin;
   const uint32_t PSD = (uint32_t)(Nout / 8) * W_CS, PSX = (uint32_t)(Kin / 8) * W_CS;   // plane strides
   const uint32_t STAGE = 2 * PSD + 2 * PSX;
-  float* sCol = reinterpret_cast<float*>(smem + 2 * STAGE);     // [8 warps? -> 4 producer warps][256] column-sum staging (+1 spare)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + 9 * 256);
+  float* sCol = reinterpret_cast<float*>(smem + 2 * STAGE);     // [8 row blocks][256] column-sum staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + 8 * 256);
   uint64_t* full = bars;          // [2]
   uint64_t* empty = bars + 2;     // [2]
   uint64_t* accfull = bars + 4;
@@ -380,11 +404,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
   uint32_t ncols = 32;
   while (ncols < (uint32_t)(nmt * Kin)) ncols <<= 1;
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&full[i], 128); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&full[i], WG_NPROD * 32); tc::mbar_init(&empty[i], 1); }
     tc::mbar_init(accfull, 1);
     tc::mbar_fence_init();
   }
-  if (warp == 8) tc::tmem_alloc(tmem_slot, ncols);
+  if (warp == 1) tc::tmem_alloc(tmem_slot, ncols);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -397,33 +421,94 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
   const int st_end = min(nst_total, st_beg + per);
   const int nst = max(0, st_end - st_beg);
   const int ndc = Nout / KC, nxc = Kin / KC;          // 64-feature chunks per operand
+  const int ntot = ndc + nxc;
 
-  if (warp >= 4 && warp < 8) {
-    // ===== producers =====
-    const int pw = warp - 4;
-    float cs[4][8];                                   // column sums of dy: chunk dc*8 + (pw&1)*4 + (lane>>3), dc < 4
+  {
+    // ===== producers: warp pw owns row block pw>>1 (8 tokens) and chunk half pw&1 of every 64-feature chunk =====
+    const int pw = warp;
+    const int ch = (pw & 1) * 4 + (lane >> 3);
+    const int rl = (pw >> 1) * 8 + (lane & 7);
+    const uint32_t base = tc::smem_u32(smem);
+    float cs[4][8];                                   // column sums of dy chunks
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int e = 0; e < 8; ++e) cs[i][e] = 0.f;
     for (int it = 0; it < nst; ++it) {
       const int s = it & 1;
-      tc::mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
       uint8_t* sb = smem + s * STAGE;
-      const long row0 = (long)(st_beg + it) * WT;
+      const long r = (long)(st_beg + it) * WT + rl;
+      const bool ok = r < a.M;
+      float4 x0[WG_MAXC], x1[WG_MAXC];
 #pragma unroll
-      for (int dc = 0; dc < 4; ++dc)
-        if (dc < ndc)
-          stage_chunk<WT, NTERMS, 4>(a.dy, a.lddy, row0, a.M, dc * KC, Nout, sb + dc * 8 * W_CS, W_CS, PSD, pw, lane, a.pro_dy, a.drop_dy,
-                                     a.want_db ? cs[dc] : nullptr);
-      for (int xc = 0; xc < nxc; ++xc)
-        stage_chunk<WT, NTERMS, 4>(a.x, a.ldx, row0, a.M, xc * KC, Kin, sb + 2 * PSD + xc * 8 * W_CS, W_CS, PSX, pw, lane, a.pro_x, a.drop_x,
-                                   nullptr);
+      for (int c = 0; c < WG_MAXC; ++c) {
+        x0[c] = make_float4(0.f, 0.f, 0.f, 0.f); x1[c] = x0[c];
+        if (c < ntot && ok) {
+          const float* src = (c < ndc) ? a.dy + r * a.lddy + c * KC + ch * 8 : a.x + r * a.ldx + (c - ndc) * KC + ch * 8;
+          x0[c] = ld_act(reinterpret_cast<const float4*>(src), a.policy); x1[c] = ld_act(reinterpret_cast<const float4*>(src) + 1, a.policy);
+        }
+      }
+      tc::mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+#pragma unroll
+      for (int c = 0; c < WG_MAXC; ++c) {
+        if (c < ntot) {
+          const bool is_dy = c < ndc;
+          float v[8] = {x0[c].x, x0[c].y, x0[c].z, x0[c].w, x1[c].x, x1[c].y, x1[c].z, x1[c].w};
+          const int pro = is_dy ? a.pro_dy : a.pro_x;
+          if (pro != PRO_NONE && ok) {
+            const int col = (is_dy ? c : c - ndc) * KC + ch * 8;
+            const uint64_t idx = (uint64_t)r * (uint64_t)(is_dy ? Nout : Kin) + (uint64_t)col;
+            const Drop& dr = is_dy ? a.drop_dy : a.drop_x;
+            float mm[8];
+            drop_mult8(dr, idx, mm);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (pro == PRO_GELU_DROP ? gelu_f(v[e]) : v[e]) * mm[e];
+          }
+          if (c < 4 && is_dy && a.want_db) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cs[c < 4 ? c : 0][e] += v[e];
+          }
+          uint4 hi, lo;
+          tc::split8(v, hi, lo);
+          uint8_t* d = sb + (is_dy ? (uint32_t)(c * 8) * W_CS : 2 * PSD + (uint32_t)((c - ndc) * 8) * W_CS) + ch * W_CS + rl * 16;
+          *reinterpret_cast<uint4*>(d) = hi;
+          if (NTERMS > 1) *reinterpret_cast<uint4*>(d + (is_dy ? PSD : PSX)) = lo;
+        }
+      }
       tc::fence_async_smem();
       tc::mbar_arrive(&full[s]);
+      if (warp == 0) {
+        // ===== MMA (warp 0, after its own share of the stage): uniform descriptors, one elected lane issues =====
+        tc::mbar_wait(&full[s], (it >> 1) & 1);
+        tc::tc_fence_after();
+        const uint32_t sD = base + s * STAGE, sX = sD + 2 * PSD;
+        const uint64_t b_hi = tc::smem_desc(sX, 128, W_CS), b_lo = tc::smem_desc(sX + PSX, 128, W_CS);
+        if (tc::elect_one()) {
+          for (int mt = 0; mt < nmt; ++mt) {
+            const int mrows = min(128, Nout - mt * 128);          // 128 or 64
+            const uint32_t idesc = tc::idesc_bf16(mrows, Kin, 1, 1);
+            const uint32_t d = tmem + (uint32_t)(mt * Kin);
+            // A = dy, B = x (both MN-major, K = tokens): hi*hi, hi*lo, lo*hi
+            const uint64_t a_hi = tc::smem_desc(sD + (uint32_t)(mt * 16) * W_CS, 128, W_CS);
+            const uint64_t a_lo = tc::smem_desc(sD + PSD + (uint32_t)(mt * 16) * W_CS, 128, W_CS);
+#pragma unroll
+            for (int ks = 0; ks < WT / 16; ++ks) {
+              const uint64_t dk = (uint64_t)(ks * 16);            // 16 token rows = 256 bytes = 16 address units
+              tc::mma_bf16(d, a_hi + dk, b_hi + dk, idesc, (it | ks) != 0);
+              if (NTERMS > 1) {
+                tc::mma_bf16(d, a_hi + dk, b_lo + dk, idesc, 1);
+                tc::mma_bf16(d, a_lo + dk, b_hi + dk, idesc, 1);
+              }
+            }
+          }
+          tc::tc_commit(&empty[s]);
+          if (it == nst - 1) tc::tc_commit(accfull);
+        }
+        __syncwarp();
+      }
     }
     if (a.want_db) {
-      // reduce over the 8 row-lanes of a warp (lane & 7), then over the two warps sharing a chunk half (pw>>1)
+      // reduce over the 8 token lanes of a warp (lane & 7); the 8 row-block warps of a chunk half are summed below
 #pragma unroll
       for (int dc = 0; dc < 4; ++dc)
 #pragma unroll
@@ -435,7 +520,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
           cs[dc][e] = v;
         }
       if ((lane & 7) == 0) {
-        const int ch = (pw & 1) * 4 + (lane >> 3);
 #pragma unroll
         for (int dc = 0; dc < 4; ++dc)
           if (dc < ndc)
@@ -443,39 +527,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
             for (int e = 0; e < 8; ++e) sCol[(pw >> 1) * 256 + dc * 64 + ch * 8 + e] = cs[dc][e];
       }
     }
-  } else if (warp == 8) {
-    // whole warp runs the loop (uniform descriptors), one elected lane issues
-    const uint32_t base = tc::smem_u32(smem);
-    for (int it = 0; it < nst; ++it) {
-      const int s = it & 1;
-      tc::mbar_wait(&full[s], (it >> 1) & 1);
-      tc::tc_fence_after();
-      const uint32_t sD = base + s * STAGE, sX = sD + 2 * PSD;
-      const uint64_t b_hi = tc::smem_desc(sX, 128, W_CS), b_lo = tc::smem_desc(sX + PSX, 128, W_CS);
-      if (tc::elect_one()) {
-        for (int mt = 0; mt < nmt; ++mt) {
-          const int mrows = min(128, Nout - mt * 128);          // 128 or 64
-          const uint32_t idesc = tc::idesc_bf16(mrows, Kin, 1, 1);
-          const uint32_t d = tmem + (uint32_t)(mt * Kin);
-          // A = dy, B = x (both MN-major, K = tokens): hi*hi, hi*lo, lo*hi
-          const uint64_t a_hi = tc::smem_desc(sD + (uint32_t)(mt * 16) * W_CS, 128, W_CS);
-          const uint64_t a_lo = tc::smem_desc(sD + PSD + (uint32_t)(mt * 16) * W_CS, 128, W_CS);
-#pragma unroll
-          for (int ks = 0; ks < WT / 16; ++ks) {
-            const uint64_t dk = (uint64_t)(ks * 16);            // 16 token rows = 256 bytes = 16 address units
-            tc::mma_bf16(d, a_hi + dk, b_hi + dk, idesc, (it | ks) != 0);
-            if (NTERMS > 1) {
-              tc::mma_bf16(d, a_hi + dk, b_lo + dk, idesc, 1);
-              tc::mma_bf16(d, a_lo + dk, b_hi + dk, idesc, 1);
-            }
-          }
-        }
-        tc::tc_commit(&empty[s]);
-      }
-      __syncwarp();
-    }
-    if (tc::elect_one()) tc::tc_commit(accfull);
-    __syncwarp();
   }
   __syncthreads();   // column sums staged; all roles done issuing
   float* part = a.partial + (long)blockIdx.x * ((long)Nout * Kin + Nout);
@@ -507,12 +558,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
     }
     if (a.want_db) {
       float* pb = part + (long)Nout * Kin;
-      for (int n = tid; n < Nout; n += 128) pb[n] = nst > 0 ? sCol[n] + sCol[256 + n] : 0.f;
+      for (int n = tid; n < Nout; n += 128) {
+        float sum = 0.f;
+        if (nst > 0)
+#pragma unroll
+          for (int g = 0; g < 8; ++g) sum += sCol[g * 256 + n];
+        pb[n] = sum;
+      }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem, ncols);
+  if (warp == 1) tc::tmem_dealloc(tmem, ncols);
 }
 
 // dW (split over up to 3 destinations of rows_per_dst rows each) = sum over CTAs of the partials, fixed order.
@@ -564,6 +621,7 @@ inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const d
   const int nst = (a.M + WT - 1) / WT;
   const int ctas = nst < WG_MAX_CTAS ? nst : WG_MAX_CTAS;
   a.want_db = (db[0] != nullptr) ? 1 : 0;
+  a.policy = g_tune[1];
   {
     ProfScope prof(PROF_LIN_WGRAD, st);
     lin_wgrad_tc_kernel<NTERMS><<<ctas, WG_THREADS, wgrad_lin_smem_bytes(a.Nout, a.Kin), st>>>(a);

@@ -10,6 +10,7 @@
 #include "gemm_f32.cuh"
 #include "elementwise.cuh"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "conv_tc.cuh"
 #include "lin_tc.cuh"
 
@@ -212,7 +213,7 @@ int conv_block_fwd(int math, const float* xin, const float* skip_in, const ConvP
                    cudaStream_t st) {
   const int PL = (taps - 1) / 2;
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
-    TRY(conv_tc_forward(math, xin, skip_in, p.w, p.b, y, B, T, PL, drop, tcs, st));
+    TRY(conv_tc_forward(math, xin, skip_in, p.w, p.b, y, B, T, taps, PL, drop, tcs, st));
   } else {
     TRY(pad_add(xin, skip_in, upad, B, T, Cin, PL, taps, st));
     TRY(conv_fwd_f32(upad, p.w, p.b, y, B, T, Cin, Cout, taps, drop, st));
@@ -231,7 +232,7 @@ int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP
   TRY(ln_ct_act_bwd(dout, y, stats, p.g, p.be, dypad, gr.g, gr.be, B, T, Cout, PLb, taps, act, drop, st));
   TRY(colsum(dypad, gr.b, (long)B * TP, Cout, Cout, st));
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
-    TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, PLb, du, gr.w, B, T, tcs, st));
+    TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, taps, PLb, du, gr.w, B, T, tcs, st));
   } else {
     TRY(pad_add(xin, skip_in, upad, B, T, Cin, PL, taps, st));
     CUDA_TRY(cudaMemsetAsync(wtmp, 0, (size_t)Cout * Cin * taps * sizeof(float), st));
@@ -362,7 +363,8 @@ int xf_block_fwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
     a.bias = (const float*)(s.wp + XfPacked::BQKV);
     TRY(lin_tc_launch(d.math, a, st));
   }
-  TRY(attention_fwd(s.qkv, s.o, s.lse, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
+  if (attention_tc_supported(d.T)) TRY(attention_fwd_tc(s.qkv, s.o, s.lse, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
+  else TRY(attention_fwd(s.qkv, s.o, s.lse, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
   {
     LinTcArgs a = lin_args(s.o, C, s.wp + XfPacked::WO_F, s.z1, C, n, C, C);
     a.bias = p.bo; a.drop = make_drop(d.seed, layer, SITE_PROJ, d.p_proj, d.train); a.drop_on = a.drop.enabled; a.residual = zin;
@@ -432,7 +434,8 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
     a.pro = d_proj.enabled ? PRO_DROP : PRO_NONE; a.pro_drop = d_proj;
     TRY(lin_tc_launch(d.math, a, st));
   }
-  TRY(attention_bwd(s.qkv, s.o, w.d_o, s.lse, w.dqkv, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
+  if (attention_tc_supported(d.T)) TRY(attention_bwd_tc(s.qkv, s.o, w.d_o, s.lse, w.dqkv, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
+  else TRY(attention_bwd(s.qkv, s.o, w.d_o, s.lse, w.dqkv, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
   TRY(ln64_fwd(zin, p.ln1g, p.ln1b, w.h, n, st));
   {
     LinWgradArgs a{};
