@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EEGCLIP_ABI_VERSION 1
+#define EEGCLIP_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define EEGCLIP_API __attribute__((visibility("default")))
@@ -151,12 +151,14 @@ EEGCLIP_API int eegclip_convblock_backward(const eegclip_convblock_desc* d, cons
                                const float* gamma, const float* beta, const float* dout, float* dx, float* dw,
                                float* dbias, float* dgamma, float* dbeta, const void* save, void* scratch, void* stream);
 
-/* Linear over tokens: out[m][n] = sum_k x[m][k] w[n][k] + b[n]  (1x1 Conv1d / nn.Linear; clip_model.py:421,439;
- * vlaai.py:18,91,94,104). */
+/* Linear over tokens: out[m][n] = sum_k x[m][k] w[n][k] + b[n]  (1x1 Conv1d / nn.Linear; clip_model.py:421,439,267;
+ * vlaai.py:18,91,94,104).  `scratch` (eegclip_linear_workspace bytes) holds the packed tensor-core operands and the
+ * weight-gradient partials; with scratch == NULL or math == FP32 the exact-fp32 CUDA-core kernels run. */
+EEGCLIP_API int eegclip_linear_workspace(int64_t M, int32_t N, int32_t K, size_t* scratch_bytes);
 EEGCLIP_API int eegclip_linear_forward(const float* x, const float* w, const float* b, float* out, int64_t M, int32_t N, int32_t K,
-                           int32_t math, void* stream);
+                           int32_t math, void* scratch, void* stream);
 EEGCLIP_API int eegclip_linear_backward(const float* x, const float* w, const float* dout, float* dx, float* dw, float* db, int64_t M,
-                            int32_t N, int32_t K, int32_t math, void* stream);
+                            int32_t N, int32_t K, int32_t math, void* scratch, void* stream);
 
 /* Symmetric InfoNCE head (clip_model.py:675-693, 913-930), local or sharded.
  *   rows : this rank's raw (un-normalised) flattened embeddings, S_loc / E_loc (b,D)

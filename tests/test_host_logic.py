@@ -27,7 +27,7 @@ def test_abi_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/eegclip.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == declared
-    assert lib.eegclip_abi_version() == 1
+    assert lib.eegclip_abi_version() == 2
 
 
 def test_cpu_tensors_fail_loudly():

@@ -77,8 +77,9 @@ SIGNATURES = {
     "eegclip_convblock_workspace": (C.c_int, [C.POINTER(ConvBlockDesc), _psz, _psz]),
     "eegclip_convblock_forward": (C.c_int, [C.POINTER(ConvBlockDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "eegclip_convblock_backward": (C.c_int, [C.POINTER(ConvBlockDesc)] + [_vp] * 14),
-    "eegclip_linear_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
-    "eegclip_linear_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "eegclip_linear_workspace": (C.c_int, [_i64, _i32, _i32, _psz]),
+    "eegclip_linear_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "eegclip_linear_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "eegclip_l2norm_forward": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "eegclip_l2norm_backward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "eegclip_infonce_workspace": (C.c_int, [_i32, _i32, _i32, _psz]),
@@ -109,7 +110,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.eegclip_abi_version() != 1:
+    if lib.eegclip_abi_version() != 2:
         raise EegclipError("libeegclip_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -141,13 +141,21 @@ class _LinearFn(torch.autograd.Function):
     """Per-token linear (nn.Linear / 1x1 Conv1d) on (..., K) -> (..., N)."""
 
     @staticmethod
+    def _scratch(M, N, K):
+        nb = ctypes.c_size_t()
+        L.call("eegclip_linear_workspace", M, N, K, ctypes.byref(nb))
+        return _bytes(nb.value)
+
+    @staticmethod
     def forward(ctx, x, w, b):
         x, w2 = L.f32c(x), L.f32c(w).reshape(w.shape[0], -1)
         b = L.f32c(b) if b is not None else None
         M, K, N = x.numel() // x.shape[-1], x.shape[-1], w2.shape[0]
         out = torch.empty(*x.shape[:-1], N, dtype=torch.float32, device=x.device)
-        L.call("eegclip_linear_forward", L.ptr(x), L.ptr(w2), L.ptr(b), L.ptr(out), M, N, K, L.default_math(), L.stream())
-        ctx.t, ctx.wshape, ctx.has_b = (x, w2), w.shape, b is not None
+        scratch = _LinearFn._scratch(M, N, K)
+        L.call("eegclip_linear_forward", L.ptr(x), L.ptr(w2), L.ptr(b), L.ptr(out), M, N, K, L.default_math(), L.ptr(scratch),
+               L.stream())
+        ctx.t, ctx.wshape, ctx.has_b, ctx.math = (x, w2), w.shape, b is not None, L.default_math()
         return out
 
     @staticmethod
@@ -158,8 +166,9 @@ class _LinearFn(torch.autograd.Function):
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dw = torch.empty_like(w2)
         db = torch.empty(N, dtype=torch.float32, device=x.device) if ctx.has_b else None
+        scratch = _LinearFn._scratch(M, N, K)
         L.call("eegclip_linear_backward", L.ptr(x), L.ptr(w2), L.ptr(dout), L.ptr(dx), L.ptr(dw), L.ptr(db), M, N, K,
-               L.default_math(), L.stream())
+               ctx.math, L.ptr(scratch), L.stream())
         return dx, dw.view(ctx.wshape), db
 
 

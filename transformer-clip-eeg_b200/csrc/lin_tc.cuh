@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
               r.x *= gelu_grad_f(s4.x); r.y *= gelu_grad_f(s4.y); r.z *= gelu_grad_f(s4.z); r.w *= gelu_grad_f(s4.w);
             }
             if (a.residual) {
-              const float4 s4 = ld_act(reinterpret_cast<const float4*>(a.residual + ci), a.policy);
+              // plain (coherent) load: the residual may alias C (K-split accumulation passes)
+              const float4 s4 = *reinterpret_cast<const float4*>(a.residual + ci);
               r.x += s4.x; r.y += s4.y; r.z += s4.z; r.w += s4.w;
             }
             *reinterpret_cast<float4*>(a.C + ci) = r;
@@ -575,6 +576,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
 // dW (split over up to 3 destinations of rows_per_dst rows each) = sum over CTAs of the partials, fixed order.
 struct WgradReduceArgs {
   const float* partial; int ctas, Nout, Kin, rows_per_dst;
+  long ldw;                       // row stride of the destination(s) (>= Kin: column blocks of a wider dW)
   float* dW[3]; float* db[3];
 };
 __global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const WgradReduceArgs a) {
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const WgradReduce
     if (i < a.Nout * a.Kin) {
       const int n = i / a.Kin, k = i - n * a.Kin;
       const int d = n / a.rows_per_dst;
-      a.dW[d][(long)(n - d * a.rows_per_dst) * a.Kin + k] = s;
+      a.dW[d][(long)(n - d * a.rows_per_dst) * a.ldw + k] = s;
     } else {
       const int n = i - a.Nout * a.Kin;
       const int d = n / a.rows_per_dst;
@@ -611,7 +613,7 @@ inline bool lin_wgrad_tc_supported(long M, int Nout, int Kin) {
 inline size_t lin_wgrad_partial_bytes(int Nout, int Kin) { return (size_t)WG_MAX_CTAS * ((size_t)Nout * Kin + Nout) * sizeof(float); }
 
 template <int NTERMS>
-inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const db[3], int rows_per_dst, cudaStream_t st) {
+inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const db[3], int rows_per_dst, long ldw, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(lin_wgrad_tc_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
@@ -628,15 +630,97 @@ inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const d
     LAUNCH_CHECK();
   }
   WgradReduceArgs r;
-  r.partial = a.partial; r.ctas = ctas; r.Nout = a.Nout; r.Kin = a.Kin; r.rows_per_dst = rows_per_dst;
+  r.partial = a.partial; r.ctas = ctas; r.Nout = a.Nout; r.Kin = a.Kin; r.rows_per_dst = rows_per_dst; r.ldw = ldw > 0 ? ldw : a.Kin;
   for (int i = 0; i < 3; ++i) { r.dW[i] = dW[i]; r.db[i] = db[i]; }
   const int total = a.Nout * a.Kin + a.Nout;
   lin_wgrad_reduce_kernel<<<(total + 63) / 64, 256, 0, st>>>(r);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
-inline int lin_wgrad_launch(int math, const LinWgradArgs& a, float* const dW[3], float* const db[3], int rows_per_dst, cudaStream_t st) {
-  return math == EEGCLIP_MATH_BF16 ? lin_wgrad_launch_t<1>(a, dW, db, rows_per_dst, st) : lin_wgrad_launch_t<3>(a, dW, db, rows_per_dst, st);
+inline int lin_wgrad_launch(int math, const LinWgradArgs& a, float* const dW[3], float* const db[3], int rows_per_dst, cudaStream_t st,
+                            long ldw = 0) {
+  return math == EEGCLIP_MATH_BF16 ? lin_wgrad_launch_t<1>(a, dW, db, rows_per_dst, ldw, st)
+                                   : lin_wgrad_launch_t<3>(a, dW, db, rows_per_dst, ldw, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic linear layers on the kernels above (nn.Linear / 1x1 Conv1d with N in {64,128,192,256}, K % 64 == 0):
+// K wider than the resident-weight budget is split into passes that accumulate through the residual input
+// (speech tower: 1024 -> 64 in four K = 256 passes).
+// ------------------------------------------------------------------------------------------------
+inline int lin_pass_width(int N, int K) {
+  int kp = K < 256 ? K : 256;
+  while (kp > KC && ((long)N * kp > 16384 || K % kp)) kp -= KC;
+  return kp;
+}
+inline bool linear_tc_ok(long M, int N, int K) {
+  if (!(N == 64 || N == 128 || N == 192 || N == 256) || K < KC || (K % KC)) return false;
+  const int kp = lin_pass_width(N, K);
+  return (long)N * kp <= 16384 && K % kp == 0 && lin_tc_supported(M, N, kp);
+}
+inline size_t linear_tc_scratch_bytes(int N, int K) {
+  size_t a = packed_bytes(N, K) + 256;                                     // packed weights (all passes)
+  size_t b = lin_wgrad_partial_bytes(N, K < 256 ? K : 256) + 256;          // weight-gradient partials
+  size_t c = packed_bytes(K, N) + 256;                                     // transposed pack for the data gradient
+  return a + b + c;
+}
+
+// out[m][n] = sum_k x[m][k] W[n][k] + b[n]
+inline int linear_tc_fwd(int math, const float* x, long ldx, const float* W, const float* b, float* out, long ldo, long M, int N, int K,
+                         uint8_t* wp, cudaStream_t st) {
+  const int kp = lin_pass_width(N, K), npass = K / kp;
+  for (int p0 = 0; p0 < npass; p0 += MAX_PACK_JOBS) {
+    PackJobs J; J.n = 0;
+    for (int p = p0; p < npass && p < p0 + MAX_PACK_JOBS; ++p)
+      add_pack(J, W + (long)p * kp, wp + (size_t)p * packed_bytes(N, kp), N, kp, 0, 0, N, kp, K, 1);
+    int rc = pack_launch(J, st);
+    if (rc != EEGCLIP_OK) return rc;
+  }
+  for (int p = 0; p < npass; ++p) {
+    LinTcArgs a{};
+    a.A = x + (long)p * kp; a.lda = ldx; a.wpacked = wp + (size_t)p * packed_bytes(N, kp); a.C = out; a.ldc = ldo;
+    a.M = (int)M; a.N = N; a.K = kp;
+    a.pro = PRO_NONE; a.pro_drop = make_drop(0, 0, 0, 0.f, 0); a.drop = a.pro_drop;
+    a.bias = p == 0 ? b : nullptr;
+    a.residual = p == 0 ? nullptr : out;
+    int rc = lin_tc_launch(math, a, st);
+    if (rc != EEGCLIP_OK) return rc;
+  }
+  return EEGCLIP_OK;
+}
+
+// dW[n][k] = sum_m dy[m][n] x[m][k] ; db[n] = sum_m dy[m][n]   (overwrites)
+inline int linear_tc_wgrad(int math, const float* dy, long lddy, const float* x, long ldx, float* dW, float* db, long M, int N, int K,
+                           float* partial, cudaStream_t st) {
+  const int kb = K < 256 ? K : 256;
+  for (int k0 = 0; k0 < K; k0 += kb) {
+    LinWgradArgs a{};
+    a.dy = dy; a.lddy = lddy; a.Nout = N; a.x = x + k0; a.ldx = ldx; a.Kin = kb; a.M = (int)M;
+    a.drop_dy = make_drop(0, 0, 0, 0.f, 0); a.drop_x = a.drop_dy; a.partial = partial;
+    float* dWs[3] = {dW + k0, nullptr, nullptr};
+    float* dbs[3] = {k0 == 0 ? db : nullptr, nullptr, nullptr};
+    int rc = lin_wgrad_launch(math, a, dWs, dbs, N, st, K);
+    if (rc != EEGCLIP_OK) return rc;
+  }
+  return EEGCLIP_OK;
+}
+inline bool linear_tc_wgrad_ok(long M, int N, int K) {
+  const int kb = K < 256 ? K : 256;
+  return (K % kb) == 0 && lin_wgrad_tc_supported(M, N, kb);
+}
+
+// dx[m][k] = sum_n dy[m][n] W[n][k]      (output width K in {64..256}, contraction N)
+inline bool linear_tc_dgrad_ok(long M, int N, int K) { return linear_tc_ok(M, K, N) && lin_pass_width(K, N) == N; }
+inline int linear_tc_dgrad(int math, const float* dy, long lddy, const float* W, float* dx, long lddx, long M, int N, int K, uint8_t* wp,
+                           cudaStream_t st) {
+  PackJobs J; J.n = 0;
+  add_pack(J, W, wp, K, N, 0, 0, K, N, 1, K);        // operand (n' = k, k' = n) = W[n][k]
+  int rc = pack_launch(J, st);
+  if (rc != EEGCLIP_OK) return rc;
+  LinTcArgs a{};
+  a.A = dy; a.lda = lddy; a.wpacked = wp; a.C = dx; a.ldc = lddx; a.M = (int)M; a.N = K; a.K = N;
+  a.pro = PRO_NONE; a.pro_drop = make_drop(0, 0, 0, 0.f, 0); a.drop = a.pro_drop;
+  return lin_tc_launch(math, a, st);
 }
 
 }  // namespace lintc

@@ -481,7 +481,8 @@ int eegclip_tower_forward(const eegclip_tower_desc* dp, const float* const* para
   float* eegx = save + L.eegx;
   GemmEpi none;
   // eeg_spatial_mapping: 1x1 conv == per-token linear (clip_model.py:447)
-  TRY(linear_f32(x, C, params[0], params[1], eegx, C, n, C, C, none, st));
+  if (xf_tc_ok(d) && lintc::linear_tc_ok(n, C, C)) TRY(lintc::linear_tc_fwd(d.math, x, C, params[0], params[1], eegx, C, n, C, C, (uint8_t*)(save + L.map_wp), st));
+  else TRY(linear_f32(x, C, params[0], params[1], eegx, C, n, C, C, none, st));
   const float* xin = eegx;
   if (d.kind == EEGCLIP_TOWER_INTERLEAVED) {
     for (int i = 0; i < d.depth; ++i) {
@@ -576,9 +577,14 @@ int eegclip_tower_backward(const eegclip_tower_desc* dp, const float* const* par
     TRY(add_f32(w.deeg, dz, w.deeg, n * C, st));                // x_0 == eeg_x
   }
   // eeg_spatial_mapping backward
-  TRY(colsum(w.deeg, grads[1], n, C, C, st));
-  TRY(linear_wgrad_f32(w.deeg, C, x, C, grads[0], n, C, C, st));
-  if (dx) TRY(linear_dgrad_f32(w.deeg, C, params[0], dx, C, n, C, C, none, st));
+  if (xf_tc_ok(d) && lintc::linear_tc_wgrad_ok(n, C, C) && lintc::linear_tc_dgrad_ok(n, C, C)) {
+    TRY(lintc::linear_tc_wgrad(d.math, w.deeg, C, x, C, grads[0], grads[1], n, C, C, w.wgp, st));
+    if (dx) TRY(lintc::linear_tc_dgrad(d.math, w.deeg, C, params[0], dx, C, n, C, C, (uint8_t*)w.wtmp, st));
+  } else {
+    TRY(colsum(w.deeg, grads[1], n, C, C, st));
+    TRY(linear_wgrad_f32(w.deeg, C, x, C, grads[0], n, C, C, st));
+    if (dx) TRY(linear_dgrad_f32(w.deeg, C, params[0], dx, C, n, C, C, none, st));
+  }
   return EEGCLIP_OK;
 }
 
@@ -634,26 +640,49 @@ int eegclip_convblock_backward(const eegclip_convblock_desc* d, const float* x, 
                         make_drop(d->seed, d->layer, SITE_CONV, d->p_drop, d->train), st);
 }
 
+int eegclip_linear_workspace(int64_t M, int32_t N, int32_t K, size_t* scratch_bytes) {
+  if (M <= 0 || N <= 0 || K <= 0 || !scratch_bytes) return EEGCLIP_ERR_ARG;
+  *scratch_bytes = lintc::linear_tc_ok(M, N, K) || lintc::linear_tc_wgrad_ok(M, N, K) ? lintc::linear_tc_scratch_bytes(N, K) : 256;
+  return EEGCLIP_OK;
+}
+
 int eegclip_linear_forward(const float* x, const float* w, const float* b, float* out, int64_t M, int32_t N, int32_t K, int32_t math,
-                           void* stream) {
+                           void* scratch, void* stream) {
   if (!x || !w || !out || M <= 0 || N <= 0 || K <= 0) return EEGCLIP_ERR_ARG;
-  (void)math;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (math != EEGCLIP_MATH_FP32 && scratch && lintc::linear_tc_ok(M, N, K))
+    return lintc::linear_tc_fwd(math, x, K, w, b, out, N, M, N, K, (uint8_t*)scratch, st);
   GemmEpi none;
-  return linear_f32(x, K, w, b, out, N, M, N, K, none, (cudaStream_t)stream);
+  return linear_f32(x, K, w, b, out, N, M, N, K, none, st);
 }
 
 int eegclip_linear_backward(const float* x, const float* w, const float* dout, float* dx, float* dw, float* db, int64_t M, int32_t N,
-                            int32_t K, int32_t math, void* stream) {
+                            int32_t K, int32_t math, void* scratch, void* stream) {
   if (!x || !w || !dout || M <= 0 || N <= 0 || K <= 0) return EEGCLIP_ERR_ARG;
-  (void)math;
   cudaStream_t st = (cudaStream_t)stream;
   GemmEpi none;
-  if (dx) TRY(linear_dgrad_f32(dout, N, w, dx, K, M, N, K, none, st));
-  if (dw) {
-    CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), st));
-    TRY(linear_wgrad_f32(dout, N, x, K, dw, M, N, K, st));
+  const bool tc = math != EEGCLIP_MATH_FP32 && scratch;
+  uint8_t* sc = (uint8_t*)scratch;
+  if (dx) {
+    if (tc && lintc::linear_tc_dgrad_ok(M, N, K)) {
+      uint8_t* wpT = sc + lintc::packed_bytes(N, K) + 256 + lintc::lin_wgrad_partial_bytes(N, K < 256 ? K : 256) + 256;
+      TRY(lintc::linear_tc_dgrad(math, dout, N, w, dx, K, M, N, K, wpT, st));
+    } else {
+      TRY(linear_dgrad_f32(dout, N, w, dx, K, M, N, K, none, st));
+    }
   }
-  if (db) {
+  bool db_done = false;
+  if (dw) {
+    if (tc && lintc::linear_tc_wgrad_ok(M, N, K)) {
+      float* partial = (float*)(sc + lintc::packed_bytes(N, K) + 256);
+      TRY(lintc::linear_tc_wgrad(math, dout, N, x, K, dw, db, M, N, K, partial, st));
+      db_done = db != nullptr;
+    } else {
+      CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), st));
+      TRY(linear_wgrad_f32(dout, N, x, K, dw, M, N, K, st));
+    }
+  }
+  if (db && !db_done) {
     CUDA_TRY(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
     if ((N & 3) == 0 && N <= 256 && 256 % (N >> 2) == 0) TRY(colsum(dout, db, M, N, N, st));
     else return EEGCLIP_ERR_UNSUPPORTED;
