@@ -4,6 +4,8 @@
 #include "../../include/eegclip.h"
 #include "common.cuh"
 #include "gemm_f32.cuh"
+#include "lin_tc.cuh"
+#include "head_tc.cuh"
 
 using namespace eegclip;
 
@@ -244,11 +246,34 @@ int eegclip_l2norm_backward(const float* xn, const float* inv_norm, const float*
   return EEGCLIP_OK;
 }
 
+struct HeadScratch {
+  size_t part1, part2, g1, g2, packS, packE, wgp, total;
+};
+static HeadScratch head_scratch(int b, int Bg, int D) {
+  HeadScratch h;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
+  const size_t part = (size_t)b * ceil_div(Bg, GBN) * sizeof(float2);
+  h.part1 = take(part); h.part2 = take(part);
+  h.g1 = take((size_t)b * Bg * sizeof(float));
+  h.g2 = take((size_t)b * Bg * sizeof(float));
+  const bool tcok = headtc::head_tc_supported(b, Bg, D);
+  h.packS = take(tcok ? headtc::epack_bytes(Bg, D) : 0);
+  h.packE = take(tcok ? headtc::epack_bytes(Bg, D) : 0);
+  // weight-gradient-style partials of a backward contraction: [D/kin blocks][token CTAs][256 x kin (+256)]
+  const int kin = 64;
+  h.wgp = take(tcok ? lintc::lin_wgrad_partial_bytes(256, kin, D / kin) : 0);
+  h.total = o;
+  return h;
+}
+// tensor-core head: D % 64 == 0, local rows start on a 128-row operand block, b splits into 64-row multiples
+static bool head_use_tc(int math, int b, int row0, int Bg, int D) {
+  return math != EEGCLIP_MATH_FP32 && headtc::head_tc_supported(b, Bg, D) && (row0 % headtc::RB) == 0 && (b % 64) == 0;
+}
+
 int eegclip_infonce_workspace(int32_t b, int32_t Bg, int32_t D, size_t* scratch_bytes) {
   if (b <= 0 || Bg < b || D <= 0 || !scratch_bytes) return EEGCLIP_ERR_ARG;
-  size_t part = align_up((size_t)b * ceil_div(Bg, GBN) * sizeof(float2), 256);
-  size_t g = align_up((size_t)b * Bg * sizeof(float), 256);
-  *scratch_bytes = 2 * part + 2 * g;
+  *scratch_bytes = head_scratch(b, Bg, D).total;
   return EEGCLIP_OK;
 }
 
@@ -256,10 +281,32 @@ int eegclip_infonce_lse(const float* S_all, const float* E_all, const float* tau
                         float* lse_row, float* lse_col, float* diag, int32_t math, int32_t one_sided, void* scratch, void* stream) {
   if (!S_all || !E_all || !tau || !lse_row || (!lse_col && !one_sided) || !diag || !scratch) return EEGCLIP_ERR_ARG;
   if (b <= 0 || row0 < 0 || row0 + b > Bg || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
-  (void)math;
   cudaStream_t st = (cudaStream_t)stream;
+  const HeadScratch hs = head_scratch(b, Bg, D);
+  char* sc = (char*)scratch;
+  float2* part = (float2*)(sc + hs.part1);
+  float2* part2 = (float2*)(sc + hs.part2);
+  if (head_use_tc(math, b, row0, Bg, D)) {
+    // ---- tcgen05: pack both gathered matrices once, then one logits pass per direction ----
+    uint8_t* pS = (uint8_t*)(sc + hs.packS);
+    uint8_t* pE = (uint8_t*)(sc + hs.packE);
+    TRY(headtc::epack(S_all, pS, Bg, D, st));
+    TRY(headtc::epack(E_all, pE, Bg, D, st));
+    const int nt = ceil_div(Bg, headtc::NT);
+    headtc::LogitsArgs a{};
+    a.Ap = pS; a.Bp = pE; a.a_blk0 = row0 / headtc::RB; a.M = b; a.N = Bg; a.D = D; a.tau = tau;
+    a.m_off = row0; a.n_off = 0; a.part = part; a.diag = diag;
+    TRY(headtc::logits_launch<1>(math, a, st));
+    lse_combine_kernel<<<ceil_div(b, 128), 128, 0, st>>>(part, nt, lse_row, b);
+    LAUNCH_CHECK();
+    if (one_sided) return EEGCLIP_OK;
+    a.Ap = pE; a.Bp = pS; a.part = part2; a.diag = nullptr;
+    TRY(headtc::logits_launch<1>(math, a, st));
+    lse_combine_kernel<<<ceil_div(b, 128), 128, 0, st>>>(part2, nt, lse_col, b);
+    LAUNCH_CHECK();
+    return EEGCLIP_OK;
+  }
   const int ntiles = ceil_div(Bg, GBN);
-  float2* part = (float2*)scratch;
   // rows: this rank's speech rows against every EEG column
   GemmArgs g;
   g.A = S_all + (long)row0 * D; g.B = E_all; g.C = nullptr;
@@ -273,7 +320,6 @@ int eegclip_infonce_lse(const float* S_all, const float* E_all, const float* tau
   LAUNCH_CHECK();
   if (one_sided) return EEGCLIP_OK;
   // columns: this rank's EEG rows against every speech row (the transposed block)
-  float2* part2 = (float2*)((char*)scratch + align_up((size_t)b * ntiles * sizeof(float2), 256));
   g.A = E_all + (long)row0 * D; g.B = S_all;
   g.epi.lse_part = part2;
   TRY(gemm_f32<1>(g, st));
@@ -297,13 +343,52 @@ int eegclip_infonce_backward(const float* S_all, const float* E_all, const float
   if (!S_all || !E_all || !tau || !lse_row_all || !dE_loc || !dtau_partial || !scratch || !dloss) return EEGCLIP_ERR_ARG;
   if (!one_sided && (!lse_col_all || !dS_loc)) return EEGCLIP_ERR_ARG;
   if (b <= 0 || row0 < 0 || row0 + b > Bg || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
-  (void)math;
   cudaStream_t st = (cudaStream_t)stream;
-  const int ntiles = ceil_div(Bg, GBN);
-  char* base = (char*)scratch + 2 * align_up((size_t)b * ntiles * sizeof(float2), 256);
-  float* Gr = (float*)base;                                             // (b, Bg): rows local, all columns
-  float* Gc = (float*)(base + align_up((size_t)b * Bg * sizeof(float), 256));  // (Bg, b): all rows, local columns
+  const HeadScratch hs = head_scratch(b, Bg, D);
+  char* sc = (char*)scratch;
+  float* Gr = (float*)(sc + hs.g1);   // fp32 path: (b, Bg) rows local, all columns ; tensor-core path: its transpose (Bg, b)
+  float* Gc = (float*)(sc + hs.g2);   // (Bg, b): all rows, local columns
   CUDA_TRY(cudaMemsetAsync(dtau_partial, 0, sizeof(float), st));
+  if (head_use_tc(math, b, row0, Bg, D)) {
+    uint8_t* pS = (uint8_t*)(sc + hs.packS);
+    uint8_t* pE = (uint8_t*)(sc + hs.packE);
+    TRY(headtc::epack(S_all, pS, Bg, D, st));
+    TRY(headtc::epack(E_all, pE, Bg, D, st));
+    // GrT[j][i] = G(i = local speech row, j = any EEG column)        -> dS_loc = exp(tau) GrT^T . E_all
+    headtc::LogitsArgs a{};
+    a.Ap = pS; a.Bp = pE; a.a_blk0 = row0 / headtc::RB; a.M = b; a.N = Bg; a.D = D; a.tau = tau;
+    a.m_off = row0; a.n_off = 0; a.lse_m = lse_row_all; a.lse_n = lse_col_all; a.up = dloss; a.inv_2b = 0.5f / (float)Bg;
+    a.one_sided = one_sided; a.GT = Gr; a.ldg = b; a.dtau = dtau_partial;
+    TRY(headtc::logits_launch<2>(math, a, st));
+    // Gc[i][j] = G(i = any speech row, j = local EEG column): the (E_loc x S_all) product stored transposed.
+    // One-sided (memory-bank term, clip_model.py:934-937): G(i,j) = (softmax_j L(i,.) - delta) / B, the statistics belong to
+    // the rows i of X = S_all, which are the n side of this product (one_sided = 2); only E has a gradient.
+    headtc::LogitsArgs c = a;
+    c.Ap = pE; c.Bp = pS; c.GT = Gc; c.dtau = nullptr;
+    c.lse_m = one_sided ? nullptr : lse_col_all;
+    c.lse_n = lse_row_all;
+    c.one_sided = one_sided ? 2 : 0;
+    float* const none3[3] = {nullptr, nullptr, nullptr};
+    auto contract = [&](const float* GT, const float* X, float* out) -> int {
+      // out[i][d] = exp(tau) * sum_j GT[j][i] * X[j][d]   (contraction over the global batch index j; D in 64-wide blocks
+      // handled by one launch, the local rows i in blocks of <= 256)
+      const int kin = 64;
+      for (int i0 = 0; i0 < b; i0 += 256) {
+        const int nb = min(256, b - i0);
+        lintc::LinWgradArgs w{};
+        w.dy = GT + i0; w.lddy = b; w.Nout = nb; w.x = X; w.ldx = D; w.Kin = kin; w.M = Bg;
+        w.drop_dy = make_drop(0, 0, 0, 0.f, 0); w.drop_x = w.drop_dy; w.partial = (float*)(sc + hs.wgp);
+        float* dW[3] = {out + (long)i0 * D, nullptr, nullptr};
+        int rc = lintc::lin_wgrad_launch(math, w, dW, none3, nb, st, D, tau, D / kin);
+        if (rc != EEGCLIP_OK) return rc;
+      }
+      return EEGCLIP_OK;
+    };
+    TRY(headtc::logits_launch<2>(math, c, st));
+    if (dS_loc && !one_sided) TRY(contract(Gr, E_all, dS_loc));
+    TRY(contract(Gc, S_all, dE_loc));
+    return EEGCLIP_OK;
+  }
   // G rows block, scaled by dloss * exp(tau) on the fly?  exp(tau) is a device scalar -> applied in the second GEMM.
   GemmArgs g;
   g.A = S_all + (long)row0 * D; g.B = E_all; g.C = Gr;

@@ -1,0 +1,254 @@
+// tcgen05 similarity kernels of the contrastive head (clip_model.py:675-693, 913-930): logits = S.E^T * exp(tau) are
+// produced tile by tile in TMEM and consumed in the epilogue -- the B x B logit matrix never exists in HBM.
+//
+//   epack_kernel        normalised embeddings (R x D fp32) -> bf16 hi/lo operand blocks, one 32 KB block per
+//                       (128-row block, 64-column chunk):  [plane][c8][row][8]   (tc_common.cuh chunk-major layout)
+//                       so that a GEMM stage is ONE contiguous bulk async copy (TMA engine) per operand block.
+//   logits_tc_kernel    CTA (m block of 128 rows) x (n tile of 256 columns): TMA producer thread + MMA thread (K loop over
+//                       D in 64-column chunks, 2-stage ring) + 4 epilogue warps (one thread per row):
+//       MODE 1  per-row (max, sum exp) partial of the tile + the diagonal logit        (forward: row / column LSE)
+//       MODE 2  G = (exp(L - lse_m) + exp(L - lse_n) - 2 delta) / (2B) * upstream, stored TRANSPOSED (n-major, coalesced)
+//               + sum G.L for d tau                                                     (backward: cross-entropy gradient)
+//   The two products of the backward, dS = exp(tau) G.E and dE = exp(tau) G^T.S, are contractions over the batch index
+//   and run on lin_wgrad_tc_kernel (lin_tc.cuh) with G^T / G as the token-major operand.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace eegclip {
+namespace headtc {
+
+constexpr int RB = 128;                        // rows per operand block
+constexpr int KC = 64;                         // columns per operand block
+constexpr int PLANE = 8 * RB * 16;             // 16 KB
+constexpr int BLK = 2 * PLANE;                 // hi + lo
+constexpr int NT = 256;                        // logit columns per CTA (two operand blocks)
+constexpr int NSTAGE = 2;
+constexpr int STAGE = 3 * BLK;                 // A block + 2 B blocks = 96 KB
+constexpr float LOG2E = 1.4426950408889634f;
+
+inline size_t epack_bytes(int R, int D) { return (size_t)((R + RB - 1) / RB) * (D / KC) * BLK; }
+
+// grid: (D/64 chunks, row blocks); block 256: lane -> (row = lane & 7, c8 = lane >> 3 (+4 per half)) as in lin_tc stage_chunk
+__global__ void __launch_bounds__(256) epack_kernel(const float* __restrict__ X, uint8_t* __restrict__ P, int R, int D) {
+  const int kc = blockIdx.x, rb = blockIdx.y, nkc = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* blk = P + ((size_t)rb * nkc + kc) * BLK;
+  // 16 row groups of 8 x 2 chunk halves = 32 combos over 8 warps
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int combo = it * 8 + warp;
+    const int rgrp = combo >> 1, half = combo & 1;
+    const int r = rgrp * 8 + (lane & 7), c8 = half * 4 + (lane >> 3);
+    const long row = (long)rb * RB + r;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (row < R) {
+      const float4* p = reinterpret_cast<const float4*>(X + row * D + kc * KC + c8 * 8);
+      const float4 a = __ldg(p), b = __ldg(p + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    uint4 hi, lo;
+    tc::split8(v, hi, lo);
+    uint8_t* d = blk + (c8 * RB + r) * 16;
+    *reinterpret_cast<uint4*>(d) = hi;
+    *reinterpret_cast<uint4*>(d + PLANE) = lo;
+  }
+}
+
+struct LogitsArgs {
+  const uint8_t* Ap;      // packed row operand (m), block index = (m0/128 + blockIdx.y) * nkc + kc
+  const uint8_t* Bp;      // packed column operand (n)
+  int a_blk0;             // first row block of A for blockIdx.y == 0 (local rows inside the gathered matrix)
+  int M, N, D;            // valid rows of this call (m), valid columns (n), features
+  const float* tau;       // device scalar: logits = dot * exp(tau)
+  int m_off, n_off;       // global indices of m = 0 / n = 0 (diagonal where m + m_off == n + n_off)
+  // MODE 1
+  float2* part;           // [M][ntiles]
+  float* diag;            // [M] (written by the tile that holds the diagonal)
+  // MODE 2
+  const float* lse_m;     // indexed by m + m_off
+  const float* lse_n;     // indexed by n + n_off   (unused when one_sided)
+  const float* up;        // device scalar: upstream gradient of the loss
+  float inv_2b;
+  int one_sided;          // 1: G = (exp(L - lse_m) - delta) / B ; 2: G = (exp(L - lse_n) - delta) / B ; 0: symmetric
+  float* GT;              // [N][ldg]: GT[n][m] = G(m, n)
+  int ldg;
+  float* dtau;            // += sum G * L (nullptr: skip)
+};
+
+template <int MODE, int NTERMS>
+__global__ void __launch_bounds__(192, 1) logits_tc_kernel(const LogitsArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE);
+  uint64_t* full = bars;              // [NSTAGE]
+  uint64_t* empty = bars + NSTAGE;    // [NSTAGE]
+  uint64_t* accfull = bars + 2 * NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
+  const int nkc = a.D / KC;
+  const int n0 = blockIdx.x * NT, m0 = blockIdx.y * RB;
+  const int nb_blocks = (a.N - n0 > RB) ? 2 : 1;            // valid column blocks of this tile
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(accfull, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 5) tc::tmem_alloc(tmem_slot, 256);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // ===== TMA producer: one bulk copy per operand block =====
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(1 + nb_blocks) * (NTERMS > 1 ? BLK : PLANE);
+      const uint8_t* ab = a.Ap + (size_t)(a.a_blk0 + blockIdx.y) * nkc * BLK;
+      const uint8_t* bb0 = a.Bp + (size_t)(blockIdx.x * 2) * nkc * BLK;
+      for (int kc = 0; kc < nkc; ++kc) {
+        const int s = kc % NSTAGE;
+        tc::mbar_wait(&empty[s], ((kc / NSTAGE) & 1) ^ 1);
+        tc::mbar_expect_tx(&full[s], bytes);
+        uint8_t* st = smem + s * STAGE;
+        const uint32_t one = NTERMS > 1 ? BLK : PLANE;
+        tc::bulk_g2s(st, ab + (size_t)kc * BLK, one, &full[s]);
+        for (int j = 0; j < nb_blocks; ++j) tc::bulk_g2s(st + (1 + j) * BLK, bb0 + ((size_t)j * nkc + kc) * BLK, one, &full[s]);
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issue (whole warp runs the loop, one elected lane issues) =====
+    const uint32_t base = tc::smem_u32(smem);
+    const uint32_t idesc = tc::idesc_bf16(128, 128, 0, 0);
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int s = kc % NSTAGE;
+      tc::mbar_wait(&full[s], (kc / NSTAGE) & 1);
+      tc::tc_fence_after();
+      const uint32_t st = base + s * STAGE;
+      const uint64_t a_hi = tc::smem_desc(st, RB * 16, 128), a_lo = tc::smem_desc(st + PLANE, RB * 16, 128);
+      if (tc::elect_one()) {
+        for (int j = 0; j < nb_blocks; ++j) {
+          const uint32_t bs = st + (1 + j) * BLK;
+          const uint64_t b_hi = tc::smem_desc(bs, RB * 16, 128), b_lo = tc::smem_desc(bs + PLANE, RB * 16, 128);
+          const uint32_t d = tmem + j * 128;
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            const uint64_t dk = (uint64_t)((2 * ks * RB * 16) >> 4);
+            tc::mma_bf16(d, a_hi + dk, b_hi + dk, idesc, (kc | ks) != 0);
+            if (NTERMS > 1) {
+              tc::mma_bf16(d, a_hi + dk, b_lo + dk, idesc, 1);
+              tc::mma_bf16(d, a_lo + dk, b_hi + dk, idesc, 1);
+            }
+          }
+        }
+        tc::tc_commit(&empty[s]);
+        if (kc == nkc - 1) tc::tc_commit(accfull);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: thread = logit row m =====
+    const int q = warp;
+    const int m = m0 + q * 32 + lane;
+    const bool mv = m < a.M;
+    tc::mbar_wait(accfull, 0);
+    tc::tc_fence_after();
+    const float scale = __expf(*a.tau);
+    const int ncols = min(NT, a.N - n0);
+    const int gm = m + a.m_off;
+    if (MODE == 1) {
+      const float sc2 = scale * LOG2E;                     // work in base 2
+      float mx = -INFINITY, sum = 0.f;
+      for (int cb = 0; cb < ncols; cb += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb, v);
+        float cm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = (cb + j < ncols) ? v[j] * sc2 : -INFINITY;
+          cm = fmaxf(cm, v[j]);
+        }
+        const float nm = fmaxf(mx, cm);
+        float cs = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cs += exp2f(v[j] - nm);
+        sum = sum * exp2f(mx - nm) + cs;
+        mx = nm;
+        const int dj = gm - (n0 + a.n_off) - cb;            // column of the diagonal inside this chunk
+        if (mv && dj >= 0 && dj < 32 && a.diag) {
+          float dv = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dv = (j == dj) ? v[j] : dv;
+          a.diag[m] = dv * (1.0f / LOG2E);
+        }
+      }
+      // natural-log convention of the partials: (max, sum exp(L - max))
+      if (mv) a.part[(long)m * gridDim.x + blockIdx.x] = make_float2(mx * (1.0f / LOG2E), sum);
+    } else {
+      const float up = a.up ? *a.up : 1.f;
+      const bool use_m = a.one_sided != 2, use_n = a.one_sided != 1;
+      const float lm = (mv && use_m) ? a.lse_m[gm] : 0.f;
+      const float kk = (a.one_sided ? 2.f * a.inv_2b : a.inv_2b) * up;
+      const float dsub = a.one_sided ? 1.f : 2.f;
+      float tsum = 0.f;
+      for (int cb = 0; cb < ncols; cb += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + cb + j;
+          if (cb + j < ncols) {
+            const float Lg = v[j] * scale;
+            float g = use_m ? __expf(Lg - lm) : 0.f;
+            if (use_n) g += __expf(Lg - __ldg(a.lse_n + n + a.n_off));
+            g = (g - (gm == n + a.n_off ? dsub : 0.f)) * kk;
+            if (mv) {
+              a.GT[(long)n * a.ldg + m] = g;
+              tsum += g * Lg;
+            }
+          }
+        }
+      }
+      if (a.dtau) {
+        tsum = warp_sum(tsum);
+        if (lane == 0) atomicAdd(a.dtau, tsum);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc(tmem, 256);
+}
+
+inline bool head_tc_supported(int b, int Bg, int D) {
+  return (D % KC) == 0 && D >= KC && b >= 1 && Bg >= b;
+}
+
+inline int epack(const float* X, uint8_t* P, int R, int D, cudaStream_t st) {
+  dim3 grid(D / KC, (R + RB - 1) / RB);
+  epack_kernel<<<grid, 256, 0, st>>>(X, P, R, D);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+template <int MODE, int NTERMS>
+inline int logits_launch_t(const LogitsArgs& a, cudaStream_t st) {
+  static bool configured = false;
+  const uint32_t smem = NSTAGE * STAGE + 256;
+  if (!configured) {
+    if (cudaFuncSetAttribute(logits_tc_kernel<MODE, NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return EEGCLIP_ERR_CUDA;
+    configured = true;
+  }
+  dim3 grid((a.N + NT - 1) / NT, (a.M + RB - 1) / RB);
+  ProfScope prof(PROF_GEMM_F32, st);
+  logits_tc_kernel<MODE, NTERMS><<<grid, 192, smem, st>>>(a);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+template <int MODE>
+inline int logits_launch(int math, const LogitsArgs& a, cudaStream_t st) {
+  return math == EEGCLIP_MATH_BF16 ? logits_launch_t<MODE, 1>(a, st) : logits_launch_t<MODE, 3>(a, st);
+}
+
+}  // namespace headtc
+}  // namespace eegclip

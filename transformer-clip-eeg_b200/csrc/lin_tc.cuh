@@ -66,7 +66,7 @@ struct PackJob {
 constexpr int MAX_PACK_JOBS = 16;
 struct PackJobs { PackJob j[MAX_PACK_JOBS]; int n; };
 
-__global__ void __launch_bounds__(256) pack_lin_weights_kernel(const PackJobs jobs) {
+static __global__ void __launch_bounds__(256) pack_lin_weights_kernel(const PackJobs jobs) {
   const PackJob& J = jobs.j[blockIdx.y];
   if (J.kind == 1) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < J.n_cnt; i += gridDim.x * blockDim.x)
@@ -379,7 +379,7 @@ struct LinWgradArgs {
   int M;
   int pro_dy; Drop drop_dy;               // prologue on dy (element index m*Nout + n)
   int pro_x; Drop drop_x;                 // prologue on x  (element index m*Kin + k)
-  float* partial;                         // [ctas][Nout*Kin + Nout]
+  float* partial;                         // [kin blocks][ctas][Nout*Kin + Nout]
   int want_db;
   int policy;                             // load policy of the streamed activations (0: L1 no-allocate, 1: __ldg)
 };
@@ -445,7 +445,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
       for (int c = 0; c < WG_MAXC; ++c) {
         x0[c] = make_float4(0.f, 0.f, 0.f, 0.f); x1[c] = x0[c];
         if (c < ntot && ok) {
-          const float* src = (c < ndc) ? a.dy + r * a.lddy + c * KC + ch * 8 : a.x + r * a.ldx + (c - ndc) * KC + ch * 8;
+          const float* src = (c < ndc) ? a.dy + r * a.lddy + c * KC + ch * 8
+                                       : a.x + r * a.ldx + (long)blockIdx.y * Kin + (c - ndc) * KC + ch * 8;
           x0[c] = ld_act(reinterpret_cast<const float4*>(src), a.policy); x1[c] = ld_act(reinterpret_cast<const float4*>(src) + 1, a.policy);
         }
       }
@@ -530,7 +531,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
     }
   }
   __syncthreads();   // column sums staged; all roles done issuing
-  float* part = a.partial + (long)blockIdx.x * ((long)Nout * Kin + Nout);
+  // blockIdx.y selects a Kin-wide column block of x (wide layers: one launch covers all blocks)
+  float* part = a.partial + ((long)blockIdx.y * gridDim.x + blockIdx.x) * ((long)Nout * Kin + Nout);
   if (warp < 4) {
     // ===== epilogue: accumulators -> partial[cta][n][k] =====
     const int q = warp;
@@ -575,18 +577,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
 
 // dW (split over up to 3 destinations of rows_per_dst rows each) = sum over CTAs of the partials, fixed order.
 struct WgradReduceArgs {
-  const float* partial; int ctas, Nout, Kin, rows_per_dst;
+  const float* partial; int ctas, Nout, Kin, rows_per_dst;   // blockIdx.y = Kin block: partial and dW advance per block
   long ldw;                       // row stride of the destination(s) (>= Kin: column blocks of a wider dW)
+  const float* log_scale;         // optional device scalar: results are multiplied by exp(*log_scale)
   float* dW[3]; float* db[3];
 };
-__global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const WgradReduceArgs a) {
+static __global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const WgradReduceArgs a) {
   __shared__ float sh[4][64];
   const int total = a.Nout * a.Kin + a.Nout;
   const int i = blockIdx.x * 64 + (threadIdx.x & 63);
   const int g = threadIdx.x >> 6;
   float s = 0.f;
   if (i < total) {
-    const float* p = a.partial + i;
+    const float* p = a.partial + (long)blockIdx.y * a.ctas * total + i;
 #pragma unroll 4
     for (int c = g; c < a.ctas; c += 4) s += p[(long)c * total];
   }
@@ -594,53 +597,64 @@ __global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const WgradReduce
   __syncthreads();
   if (g == 0 && i < total) {
     s = sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x];
+    if (a.log_scale) s *= __expf(*a.log_scale);
     if (i < a.Nout * a.Kin) {
       const int n = i / a.Kin, k = i - n * a.Kin;
       const int d = n / a.rows_per_dst;
-      a.dW[d][(long)(n - d * a.rows_per_dst) * a.ldw + k] = s;
+      a.dW[d][(long)(n - d * a.rows_per_dst) * a.ldw + (long)blockIdx.y * a.Kin + k] = s;
     } else {
       const int n = i - a.Nout * a.Kin;
       const int d = n / a.rows_per_dst;
-      if (a.db[d]) a.db[d][n - d * a.rows_per_dst] = s;
+      if (a.db[d] && blockIdx.y == 0) a.db[d][n - d * a.rows_per_dst] = s;
     }
   }
 }
 
 inline bool lin_wgrad_tc_supported(long M, int Nout, int Kin) {
   return M >= 1 && (Nout == 64 || Nout == 128 || Nout == 192 || Nout == 256) && (Kin == 64 || Kin == 128 || Kin == 192 || Kin == 256) &&
-         ((Nout + 127) / 128) * Kin <= 512 && wgrad_lin_smem_bytes(Nout, Kin) <= 227u * 1024u;
+         ((Nout + 127) / 128) * Kin <= 512 && (Nout + Kin) / KC <= WG_MAXC && wgrad_lin_smem_bytes(Nout, Kin) <= 227u * 1024u;
 }
-inline size_t lin_wgrad_partial_bytes(int Nout, int Kin) { return (size_t)WG_MAX_CTAS * ((size_t)Nout * Kin + Nout) * sizeof(float); }
+// CTAs along the token dimension: all SMs for a single column block, ~2 waves in total when blockIdx.y multiplies the grid
+inline int wgrad_token_ctas(int nst, int kin_blocks) {
+  int ctas = nst < WG_MAX_CTAS ? nst : WG_MAX_CTAS;
+  if (kin_blocks > 1) ctas = max(1, min(ctas, (2 * WG_MAX_CTAS) / kin_blocks));
+  return ctas;
+}
+inline size_t lin_wgrad_partial_bytes(int Nout, int Kin, int kin_blocks = 1) {
+  return (size_t)kin_blocks * wgrad_token_ctas(WG_MAX_CTAS, kin_blocks) * ((size_t)Nout * Kin + Nout) * sizeof(float);
+}
 
 template <int NTERMS>
-inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const db[3], int rows_per_dst, long ldw, cudaStream_t st) {
+inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const db[3], int rows_per_dst, long ldw, cudaStream_t st,
+                              const float* log_scale = nullptr, int kin_blocks = 1) {
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(lin_wgrad_tc_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
+  if (!lin_wgrad_tc_supported(a.M, a.Nout, a.Kin)) return EEGCLIP_ERR_UNSUPPORTED;
   const int nst = (a.M + WT - 1) / WT;
-  const int ctas = nst < WG_MAX_CTAS ? nst : WG_MAX_CTAS;
+  const int ctas = wgrad_token_ctas(nst, kin_blocks);
   a.want_db = (db[0] != nullptr) ? 1 : 0;
   a.policy = g_tune[1];
   {
     ProfScope prof(PROF_LIN_WGRAD, st);
-    lin_wgrad_tc_kernel<NTERMS><<<ctas, WG_THREADS, wgrad_lin_smem_bytes(a.Nout, a.Kin), st>>>(a);
+    lin_wgrad_tc_kernel<NTERMS><<<dim3(ctas, kin_blocks), WG_THREADS, wgrad_lin_smem_bytes(a.Nout, a.Kin), st>>>(a);
     LAUNCH_CHECK();
   }
   WgradReduceArgs r;
-  r.partial = a.partial; r.ctas = ctas; r.Nout = a.Nout; r.Kin = a.Kin; r.rows_per_dst = rows_per_dst; r.ldw = ldw > 0 ? ldw : a.Kin;
+  r.partial = a.partial; r.ctas = ctas; r.Nout = a.Nout; r.Kin = a.Kin; r.rows_per_dst = rows_per_dst; r.ldw = ldw > 0 ? ldw : a.Kin; r.log_scale = log_scale;
   for (int i = 0; i < 3; ++i) { r.dW[i] = dW[i]; r.db[i] = db[i]; }
   const int total = a.Nout * a.Kin + a.Nout;
-  lin_wgrad_reduce_kernel<<<(total + 63) / 64, 256, 0, st>>>(r);
+  lin_wgrad_reduce_kernel<<<dim3((total + 63) / 64, kin_blocks), 256, 0, st>>>(r);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
 inline int lin_wgrad_launch(int math, const LinWgradArgs& a, float* const dW[3], float* const db[3], int rows_per_dst, cudaStream_t st,
-                            long ldw = 0) {
-  return math == EEGCLIP_MATH_BF16 ? lin_wgrad_launch_t<1>(a, dW, db, rows_per_dst, ldw, st)
-                                   : lin_wgrad_launch_t<3>(a, dW, db, rows_per_dst, ldw, st);
+                            long ldw = 0, const float* log_scale = nullptr, int kin_blocks = 1) {
+  return math == EEGCLIP_MATH_BF16 ? lin_wgrad_launch_t<1>(a, dW, db, rows_per_dst, ldw, st, log_scale, kin_blocks)
+                                   : lin_wgrad_launch_t<3>(a, dW, db, rows_per_dst, ldw, st, log_scale, kin_blocks);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -660,7 +674,7 @@ inline bool linear_tc_ok(long M, int N, int K) {
 }
 inline size_t linear_tc_scratch_bytes(int N, int K) {
   size_t a = packed_bytes(N, K) + 256;                                     // packed weights (all passes)
-  size_t b = lin_wgrad_partial_bytes(N, K < 256 ? K : 256) + 256;          // weight-gradient partials
+  size_t b = lin_wgrad_partial_bytes(N, K < 256 ? K : 256, K < 256 ? 1 : K / 256) + 256;   // weight-gradient partials
   size_t c = packed_bytes(K, N) + 256;                                     // transposed pack for the data gradient
   return a + b + c;
 }
@@ -693,16 +707,12 @@ inline int linear_tc_fwd(int math, const float* x, long ldx, const float* W, con
 inline int linear_tc_wgrad(int math, const float* dy, long lddy, const float* x, long ldx, float* dW, float* db, long M, int N, int K,
                            float* partial, cudaStream_t st) {
   const int kb = K < 256 ? K : 256;
-  for (int k0 = 0; k0 < K; k0 += kb) {
-    LinWgradArgs a{};
-    a.dy = dy; a.lddy = lddy; a.Nout = N; a.x = x + k0; a.ldx = ldx; a.Kin = kb; a.M = (int)M;
-    a.drop_dy = make_drop(0, 0, 0, 0.f, 0); a.drop_x = a.drop_dy; a.partial = partial;
-    float* dWs[3] = {dW + k0, nullptr, nullptr};
-    float* dbs[3] = {k0 == 0 ? db : nullptr, nullptr, nullptr};
-    int rc = lin_wgrad_launch(math, a, dWs, dbs, N, st, K);
-    if (rc != EEGCLIP_OK) return rc;
-  }
-  return EEGCLIP_OK;
+  LinWgradArgs a{};
+  a.dy = dy; a.lddy = lddy; a.Nout = N; a.x = x; a.ldx = ldx; a.Kin = kb; a.M = (int)M;
+  a.drop_dy = make_drop(0, 0, 0, 0.f, 0); a.drop_x = a.drop_dy; a.partial = partial;
+  float* dWs[3] = {dW, nullptr, nullptr};
+  float* dbs[3] = {db, nullptr, nullptr};
+  return lin_wgrad_launch(math, a, dWs, dbs, N, st, K, nullptr, K / kb);
 }
 inline bool linear_tc_wgrad_ok(long M, int N, int K) {
   const int kb = K < 256 ? K : 256;

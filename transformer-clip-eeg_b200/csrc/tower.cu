@@ -665,7 +665,7 @@ int eegclip_linear_backward(const float* x, const float* w, const float* dout, f
   uint8_t* sc = (uint8_t*)scratch;
   if (dx) {
     if (tc && lintc::linear_tc_dgrad_ok(M, N, K)) {
-      uint8_t* wpT = sc + lintc::packed_bytes(N, K) + 256 + lintc::lin_wgrad_partial_bytes(N, K < 256 ? K : 256) + 256;
+      uint8_t* wpT = sc + lintc::packed_bytes(N, K) + 256 + lintc::lin_wgrad_partial_bytes(N, K < 256 ? K : 256, K < 256 ? 1 : K / 256) + 256;
       TRY(lintc::linear_tc_dgrad(math, dout, N, w, dx, K, M, N, K, wpT, st));
     } else {
       TRY(linear_dgrad_f32(dout, N, w, dx, K, M, N, K, none, st));
