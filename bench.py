@@ -141,7 +141,8 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
 
 
 def workload_name(batch):
@@ -274,13 +275,23 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": f"{args.cpu_batch} windows per step, 2 timed steps after 1 warm-up ({ms:.0f} ms/step), same "
                                           "model/step as the GPU arm, torch CPU ops on all host threads"}
-    print(json.dumps(line))
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, cuDNN warnings) write to fd 1 too."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 if __name__ == "__main__":
     a = parse()
+    _OUT = _claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
