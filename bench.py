@@ -226,9 +226,9 @@ def run_b200(args):
     l0 = lib.eegclip_launch_count()
     _lib.call("eegclip_profile_begin")
     ms_step = timed(step_resident, args.steps)
-    prof_ms = (ctypes.c_double * 8)()
-    prof_n = (ctypes.c_longlong * 8)()
-    _lib.call("eegclip_profile_end", ctypes.cast(prof_ms, ctypes.c_void_p), ctypes.cast(prof_n, ctypes.c_void_p), 8)
+    prof_ms = (ctypes.c_double * 12)()
+    prof_n = (ctypes.c_longlong * 12)()
+    _lib.call("eegclip_profile_end", ctypes.cast(prof_ms, ctypes.c_void_p), ctypes.cast(prof_n, ctypes.c_void_p), 12)
     launches = lib.eegclip_launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     for i in range(2):
@@ -240,7 +240,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     pk = peaks()
-    names = ["conv_fwd_dgrad_tc", "conv_wgrad_tc", "attn_fwd", "attn_bwd", "ln_ct", "gemm_f32", "lin_tc", "lin_wgrad_tc"]
+    names = ["conv_fwd_dgrad_tc", "conv_wgrad_tc", "attn_fwd", "attn_bwd", "ln_ct", "gemm_f32", "lin_tc", "lin_wgrad_tc", "lstm_recurrence"]
     kern = {n: {"ms_per_step": prof_ms[i] / args.steps, "launches_per_step": prof_n[i] / args.steps} for i, n in enumerate(names)}
     conv_launches = max(1, prof_n[0])
     conv_ms = prof_ms[0] / conv_launches
@@ -257,7 +257,7 @@ def run_b200(args):
         "config": {"workload": workload_name(B), "global_batch": world * B,
                    "parallelism": f"dp{world}: per-rank towers, NCCL all-gather of embeddings, sharded InfoNCE, SUM all-reduce of grads",
                    "l2": f"per-step inputs ({h2d_bytes / 1e6:.0f} MB) and activations (>2 GB) exceed the 126 MB L2; {NBUF} batches rotate",
-                   "speech_tower": "conv/LN blocks on eegclip kernels, the two bi-LSTMs are cuDNN library calls (SURVEY 8(f).1)"},
+                   "speech_tower": "1x1 conv, BasicBlock(k=32) and both bi-LSTMs (input GEMMs + recurrence kernels) on eegclip kernels"},
         "clocks": clocks,
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4},

@@ -92,8 +92,9 @@ EEGCLIP_API const char* eegclip_build_info(void);
 
 /* Measurement hooks (bench.py): number of kernels this library has launched so far, and optional CUDA-event timing of
  * the dominant kernel classes on the stream they are launched on.  Classes: 0 conv fwd/dgrad (tcgen05), 1 conv wgrad
- * (tcgen05), 2 attention fwd, 3 attention bwd, 4 LayerNorm([C,T]) fwd+bwd, 5 fp32 GEMMs.  eegclip_profile_end
- * synchronises the device and returns summed milliseconds and launch counts per class (arrays of >= 8 entries). */
+ * (tcgen05), 2 attention fwd, 3 attention bwd, 4 LayerNorm([C,T]) fwd+bwd, 5 fp32 GEMMs + head logits, 6 token GEMMs
+ * (tcgen05), 7 token weight-gradient GEMMs (tcgen05), 8 LSTM recurrences.  eegclip_profile_end synchronises the device and
+ * returns summed milliseconds and launch counts per class (arrays of >= 12 entries). */
 EEGCLIP_API long long eegclip_launch_count(void);
 /* Development knob for kernel tuning sweeps (tools/bench_xfblock.py); 0 everywhere = shipped configuration. */
 EEGCLIP_API int eegclip_tune_set(int32_t key, int32_t value);
@@ -159,6 +160,24 @@ EEGCLIP_API int eegclip_linear_forward(const float* x, const float* w, const flo
                            int32_t math, void* scratch, void* stream);
 EEGCLIP_API int eegclip_linear_backward(const float* x, const float* w, const float* dout, float* dx, float* dw, float* db, int64_t M,
                             int32_t N, int32_t K, int32_t math, void* scratch, void* stream);
+
+/* Bidirectional single-layer LSTM with zero initial state (nn.LSTM(batch_first=True, bidirectional=True); speech tower,
+ * clip_model.py:267-268, 322-323).  x (B,T,In) -> out (B,T,2H), forward direction in columns [0,H), reverse in [H,2H).
+ * params / grads (host arrays of 8 device pointers): weight_ih_l0 (4H,In), weight_hh_l0 (4H,H), bias_ih_l0, bias_hh_l0,
+ * then the four *_reverse tensors; gate order i,f,g,o.  Covered shapes: H = 128 with In in {64,128} (speech_lstm1) and
+ * H = 4 with In in {64,...,256} (speech_lstm2); eegclip_bilstm_supported tells, other shapes are the caller's business
+ * (the Python mirror keeps them on the cuDNN library call).  `save` links forward and backward and is consumed by the
+ * backward; all eight gradients are overwritten; dx may be NULL. */
+typedef struct {
+  int32_t B, T, In, H, math, reserved;
+} eegclip_bilstm_desc;
+
+EEGCLIP_API int eegclip_bilstm_supported(const eegclip_bilstm_desc* d);
+EEGCLIP_API int eegclip_bilstm_workspace(const eegclip_bilstm_desc* d, size_t* save_bytes, size_t* scratch_bytes);
+EEGCLIP_API int eegclip_bilstm_forward(const eegclip_bilstm_desc* d, const float* const* params, const float* x, float* out, void* save,
+                           void* scratch, void* stream);
+EEGCLIP_API int eegclip_bilstm_backward(const eegclip_bilstm_desc* d, const float* const* params, float* const* grads, const float* x,
+                            const float* dout, float* dx, void* save, void* scratch, void* stream);
 
 /* Symmetric InfoNCE head (clip_model.py:675-693, 913-930), local or sharded.
  *   rows : this rank's raw (un-normalised) flattened embeddings, S_loc / E_loc (b,D)

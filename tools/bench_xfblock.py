@@ -15,7 +15,7 @@ from transformer_clip_eeg_b200 import clip_model as cm, _lib
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 320
 sweeps = sys.argv[3] if len(sys.argv) > 3 else "0=2,1=0;0=3,1=0;0=2,1=1;0=3,1=1"
-names = ["conv", "conv_wgrad", "attn_fwd", "attn_bwd", "ln_ct", "gemm_f32", "lin_tc", "lin_wgrad"]
+names = ["conv", "conv_wgrad", "attn_fwd", "attn_bwd", "ln_ct", "gemm_f32", "lin_tc", "lin_wgrad", "lstm"]
 torch.manual_seed(0)
 dev = "cuda"
 blk = cm.TransformerEncoderBlock(64).to(dev).train()
@@ -42,8 +42,8 @@ for sw in sweeps.split(";"):
         step()
     e1.record()
     torch.cuda.synchronize()
-    ms = (ctypes.c_double * 8)()
-    cnt = (ctypes.c_longlong * 8)()
-    _lib.call("eegclip_profile_end", ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(cnt, ctypes.c_void_p), 8)
-    parts = ", ".join(f"{names[i]} {ms[i] / n:.3f} ms/{cnt[i] // n}" for i in range(8) if cnt[i])
+    ms = (ctypes.c_double * 12)()
+    cnt = (ctypes.c_longlong * 12)()
+    _lib.call("eegclip_profile_end", ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(cnt, ctypes.c_void_p), 12)
+    parts = ", ".join(f"{names[i]} {ms[i] / n:.3f} ms/{cnt[i] // n}" for i in range(len(names)) if cnt[i])
     print(f"[{sw}] block fwd+bwd {e0.elapsed_time(e1) / n:.3f} ms :: {parts}", flush=True)

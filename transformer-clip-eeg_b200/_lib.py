@@ -49,6 +49,10 @@ class ConvBlockDesc(C.Structure):
     ]
 
 
+class BiLstmDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("In", C.c_int32), ("H", C.c_int32), ("math", C.c_int32), ("reserved", C.c_int32)]
+
+
 class XfBlockDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("T", C.c_int32), ("layer", C.c_int32), ("train", C.c_int32), ("math", C.c_int32),
@@ -80,6 +84,10 @@ SIGNATURES = {
     "eegclip_linear_workspace": (C.c_int, [_i64, _i32, _i32, _psz]),
     "eegclip_linear_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "eegclip_linear_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "eegclip_bilstm_supported": (C.c_int, [C.POINTER(BiLstmDesc)]),
+    "eegclip_bilstm_workspace": (C.c_int, [C.POINTER(BiLstmDesc), _psz, _psz]),
+    "eegclip_bilstm_forward": (C.c_int, [C.POINTER(BiLstmDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "eegclip_bilstm_backward": (C.c_int, [C.POINTER(BiLstmDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "eegclip_l2norm_forward": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "eegclip_l2norm_backward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "eegclip_infonce_workspace": (C.c_int, [_i32, _i32, _i32, _psz]),

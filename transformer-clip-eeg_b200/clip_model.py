@@ -172,6 +172,49 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw.view(ctx.wshape), db
 
 
+_LSTM_ORDER = ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0",
+               "weight_ih_l0_reverse", "weight_hh_l0_reverse", "bias_ih_l0_reverse", "bias_hh_l0_reverse")
+
+
+class _BiLSTMFn(torch.autograd.Function):
+    """nn.LSTM(batch_first=True, bidirectional=True), zero initial state: x (B,T,In) -> (B,T,2H) on the eegclip kernels."""
+
+    @staticmethod
+    def forward(ctx, x, desc, *params):
+        x = L.f32c(x)
+        ps = [L.f32c(p) for p in params]
+        save_b, scr_b = ctypes.c_size_t(), ctypes.c_size_t()
+        L.call("eegclip_bilstm_workspace", ctypes.byref(desc), ctypes.byref(save_b), ctypes.byref(scr_b))
+        save, scratch = _bytes(save_b.value), _bytes(scr_b.value)
+        out = torch.empty(desc.B, desc.T, 2 * desc.H, dtype=torch.float32, device=x.device)
+        tab = L.ptr_table(ps)
+        L.call("eegclip_bilstm_forward", ctypes.byref(desc), tab.data_ptr(), L.ptr(x), L.ptr(out), L.ptr(save), L.ptr(scratch), L.stream())
+        ctx.desc, ctx.save, ctx.scr_bytes, ctx.x, ctx.ps = desc, save, scr_b.value, x, ps
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        desc, ps, x = ctx.desc, ctx.ps, ctx.x
+        dout = L.f32c(dout)
+        grads = [torch.empty_like(p) for p in ps]
+        scratch = _bytes(ctx.scr_bytes)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        ptab, gtab = L.ptr_table(ps), L.ptr_table(grads)
+        L.call("eegclip_bilstm_backward", ctypes.byref(desc), ptab.data_ptr(), gtab.data_ptr(), L.ptr(x), L.ptr(dout), L.ptr(dx),
+               L.ptr(ctx.save), L.ptr(scratch), L.stream())
+        ctx.save = None
+        return (dx, None, *grads)
+
+
+def _bilstm(mod, x):
+    """Run an nn.LSTM parameter container on the eegclip kernels when the shape is covered, else on the cuDNN library call."""
+    B, T, In = x.shape
+    d = L.BiLstmDesc(B=B, T=T, In=In, H=mod.hidden_size, math=L.default_math())
+    if mod.bidirectional and mod.num_layers == 1 and mod.batch_first and L.load().eegclip_bilstm_supported(ctypes.byref(d)):
+        return _BiLSTMFn.apply(x, d, *[getattr(mod, n) for n in _LSTM_ORDER])
+    return mod(x)[0]
+
+
 def _require_cuda(x, who):
     if not x.is_cuda:
         raise L.EegclipError(f"{who}: input is on {x.device}; this implementation runs on CUDA (sm_100a) only")
@@ -377,7 +420,7 @@ class EEGConformerInterleaved(_TowerBase):
 
 # ---------------------------------------------------------------------------------------------------
 # Speech towers (boundary: SURVEY §8(a14)).  The conv/LN blocks run on the kernels above; the two
-# bi-LSTMs of the default tower are cuDNN library calls in this round.
+# bi-LSTMs of the default tower run on the recurrence kernels of csrc/lstm.cuh (other LSTM shapes: cuDNN library call).
 # ---------------------------------------------------------------------------------------------------
 class SpeechSmallConv(nn.Module):
     """clip_model.py:204-232: Conv1d(speech_dim->out, k, 'same') -> Dropout -> LayerNorm([out,T]) -> LeakyReLU."""
@@ -428,8 +471,8 @@ class EEGConvLSTM(nn.Module):
         for i in range(self.n_blocks):
             blk = getattr(self, f"conv_{i}")
             x = blk.forward_time_major(x, None if i == self.n_blocks - 1 else eeg, layer=i)
-        x, _ = self.speech_lstm1(x)
-        x, _ = self.speech_lstm2(x)
+        x = _bilstm(self.speech_lstm1, x)
+        x = _bilstm(self.speech_lstm2, x)
         return x
 
 

@@ -26,7 +26,7 @@ namespace eegclip {
 // ---- launch accounting + optional per-kernel-class device timing (bench.py roofline; see eegclip_profile_*) ----
 extern long long g_launch_count;
 extern int g_tune[16];   // development knobs (eegclip_tune_set): 0 lin ring depth, 1 streaming-load policy
-enum : int { PROF_CONV_TC = 0, PROF_WGRAD_TC = 1, PROF_ATTN_FWD = 2, PROF_ATTN_BWD = 3, PROF_LNCT = 4, PROF_GEMM_F32 = 5, PROF_LIN_TC = 6, PROF_LIN_WGRAD = 7, PROF_NCLASS = 8 };
+enum : int { PROF_CONV_TC = 0, PROF_WGRAD_TC = 1, PROF_ATTN_FWD = 2, PROF_ATTN_BWD = 3, PROF_LNCT = 4, PROF_GEMM_F32 = 5, PROF_LIN_TC = 6, PROF_LIN_WGRAD = 7, PROF_LSTM = 8, PROF_NCLASS = 12 };
 void prof_begin(int cls, cudaStream_t st);
 void prof_end(int cls, cudaStream_t st);
 struct ProfScope {

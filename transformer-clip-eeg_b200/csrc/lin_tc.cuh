@@ -580,7 +580,7 @@ struct WgradReduceArgs {
   const float* partial; int ctas, Nout, Kin, rows_per_dst;   // blockIdx.y = Kin block: partial and dW advance per block
   long ldw;                       // row stride of the destination(s) (>= Kin: column blocks of a wider dW)
   const float* log_scale;         // optional device scalar: results are multiplied by exp(*log_scale)
-  float* dW[3]; float* db[3];
+  float* dW[4]; float* db[4];     // destination d covers rows [d*rows_per_dst, (d+1)*rows_per_dst); null = discard (padding rows)
 };
 static __global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const WgradReduceArgs a) {
   __shared__ float sh[4][64];
@@ -601,11 +601,11 @@ static __global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const Wgra
     if (i < a.Nout * a.Kin) {
       const int n = i / a.Kin, k = i - n * a.Kin;
       const int d = n / a.rows_per_dst;
-      a.dW[d][(long)(n - d * a.rows_per_dst) * a.ldw + (long)blockIdx.y * a.Kin + k] = s;
+      if (d < 4 && a.dW[d]) a.dW[d][(long)(n - d * a.rows_per_dst) * a.ldw + (long)blockIdx.y * a.Kin + k] = s;
     } else {
       const int n = i - a.Nout * a.Kin;
       const int d = n / a.rows_per_dst;
-      if (a.db[d] && blockIdx.y == 0) a.db[d][n - d * a.rows_per_dst] = s;
+      if (d < 4 && a.db[d] && blockIdx.y == 0) a.db[d][n - d * a.rows_per_dst] = s;
     }
   }
 }
@@ -646,6 +646,7 @@ inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const d
   WgradReduceArgs r;
   r.partial = a.partial; r.ctas = ctas; r.Nout = a.Nout; r.Kin = a.Kin; r.rows_per_dst = rows_per_dst; r.ldw = ldw > 0 ? ldw : a.Kin; r.log_scale = log_scale;
   for (int i = 0; i < 3; ++i) { r.dW[i] = dW[i]; r.db[i] = db[i]; }
+  r.dW[3] = nullptr; r.db[3] = nullptr;
   const int total = a.Nout * a.Kin + a.Nout;
   lin_wgrad_reduce_kernel<<<dim3((total + 63) / 64, kin_blocks), 256, 0, st>>>(r);
   LAUNCH_CHECK();

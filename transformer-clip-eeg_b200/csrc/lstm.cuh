@@ -1,0 +1,308 @@
+// Bidirectional single-layer LSTM of the default speech tower (clip_model.py:267-268, 322-323; nn.LSTM semantics: gate order
+// i,f,g,o, zero initial state, batch_first, outputs of the two directions concatenated).
+//
+// The input projections x.W_ih^T (+ both biases) of ALL time steps are one token GEMM (lin_tc.cuh), and so are the weight
+// gradients and the input gradient; only the recurrence itself is sequential.  The recurrence keeps W_hh on chip:
+//   H = 128 (speech_lstm1): one CTA = 4 sequences of one direction, 512 threads = the 512 gate rows; each thread holds its
+//       row of W_hh (64 weights in registers, 64 in shared memory), h_{t-1} of the 4 sequences is broadcast from shared
+//       memory; exact fp32 FMA.  The backward runs the transposed product the same way (thread = (hidden unit, row quarter)).
+//   H = 4 (speech_lstm2): one half-warp per (sequence, direction), lane = gate row, coalesced 64-byte gate rows, shuffles.
+// Saved for the backward: post-activation gates (in place over the input projections), cell states, h_{t-1}.
+#pragma once
+#include "common.cuh"
+
+namespace eegclip {
+namespace lstm {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------
+// H = 128 forward.  grid (ceil(B/4), 2 directions), block 512.
+//   G   : (B*T, GS) rows; direction d owns columns [d*512, d*512+512) = [gate][unit]; in: x-projection + biases, out: gates
+//   out : (B*T, 256)  h_t          Cs : (B*T, 256) c_t          Hp : (B*T, 256) h_{t-1} (the state the step started from)
+// ------------------------------------------------------------------------------------------------
+constexpr int LH = 128, LG = 512, LNB = 4;
+constexpr int L128_SMEM = (16 * LG * 4 + LNB * LH + LNB * LG) * 4;   // W half + h + pre-activations
+
+__global__ void __launch_bounds__(512, 1) lstm128_fwd_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
+                                                            float* __restrict__ G, int GS, float* __restrict__ out,
+                                                            float* __restrict__ Cs, float* __restrict__ Hp, int B, int T) {
+  extern __shared__ __align__(16) float sml[];
+  float4* Wsm = reinterpret_cast<float4*>(sml);          // [k4 = 16][row 512] : W[row][64 + 4*k4 .. +3]
+  float* hs = sml + 16 * LG * 4;                         // [seq 4][128]
+  float* pre = hs + LNB * LH;                            // [seq 4][512]
+  const int dir = blockIdx.y, b0 = blockIdx.x * LNB;
+  const int r = threadIdx.x;
+  const float* W = (dir ? w_hh_r : w_hh_f) + (long)r * LH;
+  float w[64];
+#pragma unroll
+  for (int k4 = 0; k4 < 16; ++k4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(W) + k4);
+    w[4 * k4] = v.x; w[4 * k4 + 1] = v.y; w[4 * k4 + 2] = v.z; w[4 * k4 + 3] = v.w;
+    Wsm[k4 * LG + r] = __ldg(reinterpret_cast<const float4*>(W) + 16 + k4);
+  }
+  hs[r] = 0.f;                                            // 512 = 4 x 128 zeros
+  // gate-combine role: thread = (unit u, sequence s)
+  const int u = r & 127, s = r >> 7;
+  const int b = b0 + s;
+  const bool live = b < B;
+  float c = 0.f;
+  __syncthreads();
+  for (int step = 0; step < T; ++step) {
+    const int t = dir ? T - 1 - step : step;
+    const long row = (long)b * T + t;
+    float gx[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) gx[g] = G[row * GS + dir * LG + g * LH + u];
+    }
+    // ---- recurrent product: acc[q] = sum_k W[r][k] h[q][k] ----
+    float acc[LNB] = {0.f, 0.f, 0.f, 0.f};
+    const float4* h4 = reinterpret_cast<const float4*>(hs);
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) {
+#pragma unroll
+      for (int q = 0; q < LNB; ++q) {
+        const float4 h = h4[q * 32 + k4];
+        acc[q] = fmaf(w[4 * k4], h.x, acc[q]); acc[q] = fmaf(w[4 * k4 + 1], h.y, acc[q]);
+        acc[q] = fmaf(w[4 * k4 + 2], h.z, acc[q]); acc[q] = fmaf(w[4 * k4 + 3], h.w, acc[q]);
+      }
+    }
+#pragma unroll 4
+    for (int k4 = 0; k4 < 16; ++k4) {
+      const float4 wv = Wsm[k4 * LG + r];
+#pragma unroll
+      for (int q = 0; q < LNB; ++q) {
+        const float4 h = h4[q * 32 + 16 + k4];
+        acc[q] = fmaf(wv.x, h.x, acc[q]); acc[q] = fmaf(wv.y, h.y, acc[q]);
+        acc[q] = fmaf(wv.z, h.z, acc[q]); acc[q] = fmaf(wv.w, h.w, acc[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < LNB; ++q) pre[q * LG + r] = acc[q];
+    __syncthreads();
+    // ---- gates, state update (thread = (u, s)) ----
+    const float hprev = hs[s * LH + u];
+    const float ai = pre[s * LG + u] + gx[0], af = pre[s * LG + LH + u] + gx[1];
+    const float ag = pre[s * LG + 2 * LH + u] + gx[2], ao = pre[s * LG + 3 * LH + u] + gx[3];
+    const float gi = sigmoidf_(ai), gf = sigmoidf_(af), gg = tanhf(ag), go = sigmoidf_(ao);
+    c = gf * c + gi * gg;
+    const float h = go * tanhf(c);
+    hs[s * LH + u] = h;                                   // only this thread read hs[s][u] since the product phase ended
+    if (live) {
+      float* gp = G + row * GS + dir * LG + u;
+      gp[0] = gi; gp[LH] = gf; gp[2 * LH] = gg; gp[3 * LH] = go;
+      out[row * 256 + dir * LH + u] = h;
+      Cs[row * 256 + dir * LH + u] = c;
+      Hp[row * 256 + dir * LH + u] = hprev;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// H = 128 backward recurrence.  Same grid.  Walks the time steps in the opposite order of the forward, turns the saved
+// gates into pre-activation gradients da (in place in G) and carries dh, dc.
+//   dh_{prev}[k] = sum_r W_hh[r][k] da[r] : thread (k = tid & 127, q = tid >> 7) sums rows [128q, 128q+128), 4 partials reduced in smem
+// ------------------------------------------------------------------------------------------------
+constexpr int L128B_SMEM = (16 * LG * 4 + LNB * LG + 4 * LNB * LH + LNB * LH) * 4;
+
+__global__ void __launch_bounds__(512, 1) lstm128_bwd_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
+                                                            float* __restrict__ G, int GS, const float* __restrict__ dout,
+                                                            const float* __restrict__ Cs, int B, int T) {
+  extern __shared__ __align__(16) float sml[];
+  float4* Wsm = reinterpret_cast<float4*>(sml);          // [j4 = 16][tid 512] : W[128q + 64 + 4*j4 .. +3][k]
+  float* das = sml + 16 * LG * 4;                        // [seq 4][512]
+  float* part = das + LNB * LG;                          // [q 4][seq 4][128]
+  float* dhs = part + 4 * LNB * LH;                      // [seq 4][128]
+  const int dir = blockIdx.y, b0 = blockIdx.x * LNB;
+  const int tid = threadIdx.x;
+  const int k = tid & 127, q = tid >> 7;
+  const float* W = (dir ? w_hh_r : w_hh_f) + (long)(q * LH) * LH + k;   // W[128q + j][k] = W[j * 128]
+  float w[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) w[j] = __ldg(W + (long)j * LH);
+#pragma unroll
+  for (int j4 = 0; j4 < 16; ++j4)
+    Wsm[j4 * LG + tid] = make_float4(__ldg(W + (long)(64 + 4 * j4) * LH), __ldg(W + (long)(65 + 4 * j4) * LH),
+                                     __ldg(W + (long)(66 + 4 * j4) * LH), __ldg(W + (long)(67 + 4 * j4) * LH));
+  dhs[tid] = 0.f;
+  const int u = k, s = q;                                // gate role: (unit, sequence)
+  const int b = b0 + s;
+  const bool live = b < B;
+  float dc = 0.f;
+  __syncthreads();
+  for (int step = 0; step < T; ++step) {
+    const int t = dir ? step : T - 1 - step;             // reverse of the forward order
+    const int tp = dir ? t + 1 : t - 1;                  // time index of the forward's previous step
+    const long row = (long)b * T + t;
+    float da[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      float* gp = G + row * GS + dir * LG + u;
+      const float gi = gp[0], gf = gp[LH], gg = gp[2 * LH], go = gp[3 * LH];
+      const float ct = Cs[row * 256 + dir * LH + u];
+      const float cp = (tp >= 0 && tp < T) ? Cs[((long)b * T + tp) * 256 + dir * LH + u] : 0.f;
+      const float dh = dout[row * 256 + dir * LH + u] + dhs[s * LH + u];
+      const float tc = tanhf(ct);
+      const float dct = dc + dh * go * (1.f - tc * tc);
+      da[0] = dct * gg * gi * (1.f - gi);
+      da[1] = dct * cp * gf * (1.f - gf);
+      da[2] = dct * gi * (1.f - gg * gg);
+      da[3] = dh * tc * go * (1.f - go);
+      dc = dct * gf;
+      gp[0] = da[0]; gp[LH] = da[1]; gp[2 * LH] = da[2]; gp[3 * LH] = da[3];
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) das[s * LG + g * LH + u] = da[g];
+    __syncthreads();
+    // ---- transposed recurrent product ----
+    float acc[LNB] = {0.f, 0.f, 0.f, 0.f};
+    const float4* d4 = reinterpret_cast<const float4*>(das);
+#pragma unroll
+    for (int j4 = 0; j4 < 16; ++j4) {
+#pragma unroll
+      for (int ss = 0; ss < LNB; ++ss) {
+        const float4 d = d4[ss * 128 + q * 32 + j4];
+        acc[ss] = fmaf(w[4 * j4], d.x, acc[ss]); acc[ss] = fmaf(w[4 * j4 + 1], d.y, acc[ss]);
+        acc[ss] = fmaf(w[4 * j4 + 2], d.z, acc[ss]); acc[ss] = fmaf(w[4 * j4 + 3], d.w, acc[ss]);
+      }
+    }
+#pragma unroll 4
+    for (int j4 = 0; j4 < 16; ++j4) {
+      const float4 wv = Wsm[j4 * LG + tid];
+#pragma unroll
+      for (int ss = 0; ss < LNB; ++ss) {
+        const float4 d = d4[ss * 128 + q * 32 + 16 + j4];
+        acc[ss] = fmaf(wv.x, d.x, acc[ss]); acc[ss] = fmaf(wv.y, d.y, acc[ss]);
+        acc[ss] = fmaf(wv.z, d.z, acc[ss]); acc[ss] = fmaf(wv.w, d.w, acc[ss]);
+      }
+    }
+#pragma unroll
+    for (int ss = 0; ss < LNB; ++ss) part[(q * LNB + ss) * LH + k] = acc[ss];
+    __syncthreads();
+    // thread (u, s) sums the 4 row-quarter partials of its (sequence, unit)
+    // (dhs[s][u] is private to this thread; the next write of `part` comes after the next barrier)
+    dhs[s * LH + u] = part[(0 * LNB + s) * LH + u] + part[(1 * LNB + s) * LH + u] + part[(2 * LNB + s) * LH + u] +
+                      part[(3 * LNB + s) * LH + u];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// H = 4 (speech_lstm2): 16 gate rows = one half-warp per (sequence, direction); lane j of the group owns gate row j
+// (gate j >> 2, unit j & 3), so the gate row of a time step is one coalesced 64-byte access.  State exchange by shuffles;
+// the next step's input projection is prefetched while the current one is computed.
+//   grid = ceil(2*B / 8) CTAs of 128 threads (8 groups); group id = dir * B + b.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) lstm4_fwd_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
+                                                       float* __restrict__ G, int GS, float* __restrict__ out, float* __restrict__ Cs,
+                                                       float* __restrict__ Hp, int B, int T) {
+  const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int j = threadIdx.x & 15;                       // gate row
+  const bool live = gid < 2 * B;
+  const int dir = live ? gid / B : 0, b = live ? gid - dir * B : 0;
+  const unsigned gmask = 0xffffu << (threadIdx.x & 16); // the 16 lanes of this group
+  const int lbase = threadIdx.x & 16;                   // first lane of the group inside the warp
+  const float* W = (dir ? w_hh_r : w_hh_f) + j * 4;
+  const float w0 = __ldg(W), w1 = __ldg(W + 1), w2 = __ldg(W + 2), w3 = __ldg(W + 3);
+  float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, c = 0.f;  // h replicated in every lane, c in the unit lanes (j < 4)
+  const long rbase = (long)b * T;
+  float gnext = live ? G[(rbase + (dir ? T - 1 : 0)) * GS + dir * 16 + j] : 0.f;
+  for (int step = 0; step < T; ++step) {
+    const int t = dir ? T - 1 - step : step;
+    const long row = rbase + t;
+    const float gx = gnext;
+    if (step + 1 < T && live) gnext = G[(rbase + (dir ? t - 1 : t + 1)) * GS + dir * 16 + j];
+    float a = gx;
+    a = fmaf(w0, h0, a); a = fmaf(w1, h1, a); a = fmaf(w2, h2, a); a = fmaf(w3, h3, a);
+    const float act = (j >> 2) == 2 ? tanhf(a) : sigmoidf_(a);
+    // unit lane u (= j & 3) gathers i, f, g, o of its unit
+    const int u = j & 3;
+    const float gi = __shfl_sync(gmask, act, lbase + u), gf = __shfl_sync(gmask, act, lbase + 4 + u);
+    const float gg = __shfl_sync(gmask, act, lbase + 8 + u), go = __shfl_sync(gmask, act, lbase + 12 + u);
+    c = gf * c + gi * gg;                               // identical in the 4 lanes sharing a unit; lanes j < 4 are authoritative
+    const float hn = go * tanhf(c);
+    if (live) {
+      G[row * GS + dir * 16 + j] = act;
+      if (j < 4) {
+        const float hp = j == 0 ? h0 : j == 1 ? h1 : j == 2 ? h2 : h3;
+        Hp[row * 8 + dir * 4 + j] = hp;
+        out[row * 8 + dir * 4 + j] = hn;
+        Cs[row * 8 + dir * 4 + j] = c;
+      }
+    }
+    h0 = __shfl_sync(gmask, hn, lbase + 0); h1 = __shfl_sync(gmask, hn, lbase + 1);
+    h2 = __shfl_sync(gmask, hn, lbase + 2); h3 = __shfl_sync(gmask, hn, lbase + 3);
+  }
+}
+
+// backward: lane j owns gate row j; also accumulates dW_hh[j][0..3] (reduced over the CTA, then atomics; pre-zeroed)
+__global__ void __launch_bounds__(128) lstm4_bwd_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
+                                                       float* __restrict__ G, int GS, const float* __restrict__ dout,
+                                                       const float* __restrict__ Cs, const float* __restrict__ Hp,
+                                                       float* __restrict__ dwhh_f, float* __restrict__ dwhh_r, int B, int T) {
+  __shared__ float red[2][64];
+  const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int j = threadIdx.x & 15;
+  const bool live = gid < 2 * B;
+  const int dir = live ? gid / B : 0, b = live ? gid - dir * B : 0;
+  const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+  const int lbase = threadIdx.x & 16;
+  const float* W = (dir ? w_hh_r : w_hh_f) + j * 4;
+  const float w0 = __ldg(W), w1 = __ldg(W + 1), w2 = __ldg(W + 2), w3 = __ldg(W + 3);
+  const int u = j & 3, gate = j >> 2;
+  float dw0 = 0.f, dw1 = 0.f, dw2 = 0.f, dw3 = 0.f;
+  float dh = 0.f, dc = 0.f;                              // of unit u, replicated in the 4 lanes sharing it
+  const long rbase = (long)b * T;
+  if (threadIdx.x < 128) { red[0][threadIdx.x & 63] = 0.f; red[1][threadIdx.x & 63] = 0.f; }
+  __syncthreads();
+  for (int step = 0; step < T; ++step) {
+    const int t = dir ? step : T - 1 - step;
+    const int tp = dir ? t + 1 : t - 1;
+    const long row = rbase + t;
+    float act = 0.f, ct = 0.f, cp = 0.f, dy = 0.f, hp = 0.f;
+    if (live) {
+      act = G[row * GS + dir * 16 + j];
+      ct = Cs[row * 8 + dir * 4 + u];
+      cp = (tp >= 0 && tp < T) ? Cs[(rbase + tp) * 8 + dir * 4 + u] : 0.f;
+      dy = dout[row * 8 + dir * 4 + u];
+      hp = Hp[row * 8 + dir * 4 + u];
+    }
+    const float gi = __shfl_sync(gmask, act, lbase + u), gf = __shfl_sync(gmask, act, lbase + 4 + u);
+    const float gg = __shfl_sync(gmask, act, lbase + 8 + u), go = __shfl_sync(gmask, act, lbase + 12 + u);
+    const float dht = dy + dh;
+    const float tc = tanhf(ct);
+    const float dct = dc + dht * go * (1.f - tc * tc);
+    // pre-activation gradient of THIS lane's gate row
+    float da;
+    if (gate == 0) da = dct * gg * gi * (1.f - gi);
+    else if (gate == 1) da = dct * cp * gf * (1.f - gf);
+    else if (gate == 2) da = dct * gi * (1.f - gg * gg);
+    else da = dht * tc * go * (1.f - go);
+    dc = dct * gf;
+    if (live) G[row * GS + dir * 16 + j] = da;
+    // dW_hh[j][k] += da * h_prev[k]  (h_prev[k] lives in the lanes with u == k)
+    dw0 = fmaf(da, __shfl_sync(gmask, hp, lbase + 0), dw0); dw1 = fmaf(da, __shfl_sync(gmask, hp, lbase + 1), dw1);
+    dw2 = fmaf(da, __shfl_sync(gmask, hp, lbase + 2), dw2); dw3 = fmaf(da, __shfl_sync(gmask, hp, lbase + 3), dw3);
+    // dh_prev[k] = sum_j W[j][k] da[j] : reduce over the 16 lanes, lane ends up with the value of its unit u
+    float p0 = w0 * da, p1 = w1 * da, p2 = w2 * da, p3 = w3 * da;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      p0 += __shfl_xor_sync(gmask, p0, o); p1 += __shfl_xor_sync(gmask, p1, o);
+      p2 += __shfl_xor_sync(gmask, p2, o); p3 += __shfl_xor_sync(gmask, p3, o);
+    }
+    dh = u == 0 ? p0 : u == 1 ? p1 : u == 2 ? p2 : p3;
+  }
+  // CTA-level reduction of dW_hh per direction (a CTA may straddle the two directions)
+  if (live) {
+    float* r = red[dir];
+    atomicAdd(r + j * 4 + 0, dw0); atomicAdd(r + j * 4 + 1, dw1); atomicAdd(r + j * 4 + 2, dw2); atomicAdd(r + j * 4 + 3, dw3);
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    if (red[0][threadIdx.x] != 0.f) atomicAdd(dwhh_f + threadIdx.x, red[0][threadIdx.x]);
+    if (red[1][threadIdx.x] != 0.f) atomicAdd(dwhh_r + threadIdx.x, red[1][threadIdx.x]);
+  }
+}
+
+}  // namespace lstm
+}  // namespace eegclip
