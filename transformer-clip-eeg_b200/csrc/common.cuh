@@ -128,6 +128,13 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+// GELU(x) and GELU'(x) together (one erf)
+__device__ __forceinline__ void gelu_both(float x, float& g, float& gd) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  g = x * cdf;
+  gd = cdf + x * pdf;
+}
 // activation ids for conv+LN blocks: 0 = GELU (BasicBlock), 1 = LeakyReLU(0.01) (VLAAI / SpeechSmallConv)
 __device__ __forceinline__ float act_f(float x, int act) { return act == 0 ? gelu_f(x) : (x > 0.f ? x : 0.01f * x); }
 __device__ __forceinline__ float act_grad_f(float x, int act) { return act == 0 ? gelu_grad_f(x) : (x > 0.f ? 1.f : 0.01f); }

@@ -152,12 +152,14 @@ inline int ln_ct_act_fwd(const float* y, const float* gamma, const float* beta, 
 // Backward of the block above.  dout: gradient w.r.t. out (skip gradient handled by the caller).
 // Writes dy (gradient w.r.t. the conv output *before* dropout, i.e. already multiplied by the conv
 // dropout mask) into a zero-padded buffer dypad[b][PL + t][c] (rows outside are left untouched: the
-// caller zeroes the buffer once), and accumulates dgamma/dbeta (C,T) with atomics over the batch.
-__global__ void __launch_bounds__(512) ln_ct_act_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y,
-                                                           const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, float* __restrict__ dypad,
-                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int T, int C,
-                                                           int PL, int TP, int act, Drop drop) {
+// caller zeroes the buffer once), and accumulates dgamma/dbeta (C,T).
+//   pass 1 (one CTA per sample): the two per-sample means  m1 = mean(dxh), m2 = mean(dxh * xhat)
+//   pass 2 (thread = fixed (t, 8 channels), loop over a group of samples): dy, and dgamma/dbeta summed over the group in
+//          registers -> one atomic per (element, group) instead of one per (element, sample)
+__global__ void __launch_bounds__(512) ln_ct_bwd_stats_kernel(const float* __restrict__ dout, const float* __restrict__ y,
+                                                             const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float* __restrict__ m12, int T, int C,
+                                                             int act) {
   __shared__ float2 sh[33];
   const int b = blockIdx.x;
   const long n = (long)T * C;
@@ -166,48 +168,78 @@ __global__ void __launch_bounds__(512) ln_ct_act_bwd_kernel(const float* __restr
   const float mean = stats[2 * b], rstd = stats[2 * b + 1];
   float s1 = 0.f, s2 = 0.f;
   for (long i = threadIdx.x * 4L; i < n; i += blockDim.x * 4L) {
-    int t = (int)(i / C), c = (int)(i - (long)t * C);
-    float4 v = *reinterpret_cast<const float4*>(yb + i);
-    float4 d = *reinterpret_cast<const float4*>(db + i);
-    float vv[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
+    const int t = (int)(i / C), c = (int)(i - (long)t * C);
+    const float4 v = *reinterpret_cast<const float4*>(yb + i);
+    const float4 d = *reinterpret_cast<const float4*>(db + i);
+    const float vv[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float g = __ldg(gamma + (long)(c + j) * T + t), be = __ldg(beta + (long)(c + j) * T + t);
-      float xh = (vv[j] - mean) * rstd;
-      float dl = dd[j] * act_grad_f(xh * g + be, act);
-      atomicAdd(dgamma + (long)(c + j) * T + t, dl * xh);
-      atomicAdd(dbeta + (long)(c + j) * T + t, dl);
-      float dxh = dl * g;
+      const float g = __ldg(gamma + (long)(c + j) * T + t), be = __ldg(beta + (long)(c + j) * T + t);
+      const float xh = (vv[j] - mean) * rstd;
+      const float dxh = dd[j] * act_grad_f(xh * g + be, act) * g;
       s1 += dxh; s2 += dxh * xh;
     }
   }
-  float2 r = block_sum2(s1, s2, sh);
-  const float m1 = r.x / (float)n, m2 = r.y / (float)n;
-  float* ob = dypad + ((long)b * TP + PL) * C;
-  for (long i = threadIdx.x * 4L; i < n; i += blockDim.x * 4L) {
-    int t = (int)(i / C), c = (int)(i - (long)t * C);
-    float4 v = *reinterpret_cast<const float4*>(yb + i);
-    float4 d = *reinterpret_cast<const float4*>(db + i);
-    float vv[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
-    float4 m = drop_mult4(drop, (uint64_t)b * n + i);
-    float mm[4] = {m.x, m.y, m.z, m.w};
-    float o[4];
+  const float2 r = block_sum2(s1, s2, sh);
+  if (threadIdx.x == 0) { m12[2 * b] = r.x / (float)n; m12[2 * b + 1] = r.y / (float)n; }
+}
+
+// grid (T*C/8/256, groups), block 256; thread = (t, c8) position, samples b = group, group + groups, ...
+__global__ void __launch_bounds__(256) ln_ct_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y,
+                                                             const float* __restrict__ stats, const float* __restrict__ m12,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float* __restrict__ dypad, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, int B, int T, int C, int PL, int TP, int act,
+                                                             Drop drop) {
+  const long n = (long)T * C;
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  const int t = (int)(i / C), c = (int)(i - (long)t * C);
+  float g[8], be[8], ag[8], ab[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float g = __ldg(gamma + (long)(c + j) * T + t), be = __ldg(beta + (long)(c + j) * T + t);
-      float xh = (vv[j] - mean) * rstd;
-      float dxh = dd[j] * act_grad_f(xh * g + be, act) * g;
-      o[j] = rstd * (dxh - m1 - xh * m2) * mm[j];
+  for (int j = 0; j < 8; ++j) {
+    g[j] = __ldg(gamma + (long)(c + j) * T + t); be[j] = __ldg(beta + (long)(c + j) * T + t);
+    ag[j] = 0.f; ab[j] = 0.f;
+  }
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const float mean = stats[2 * b], rstd = stats[2 * b + 1], m1 = m12[2 * b], m2 = m12[2 * b + 1];
+    const float4* yp = reinterpret_cast<const float4*>(y + b * n + i);
+    const float4* dp = reinterpret_cast<const float4*>(dout + b * n + i);
+    const float4 v0 = yp[0], v1 = yp[1], d0 = dp[0], d1 = dp[1];
+    const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float mm[8], o[8];
+    drop_mult8(drop, (uint64_t)b * n + i, mm);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (vv[j] - mean) * rstd;
+      const float dl = dd[j] * act_grad_f(xh * g[j] + be[j], act);
+      ag[j] += dl * xh; ab[j] += dl;
+      o[j] = rstd * (dl * g[j] - m1 - xh * m2) * mm[j];
     }
-    *reinterpret_cast<float4*>(ob + i) = make_float4(o[0], o[1], o[2], o[3]);
+    float4* op = reinterpret_cast<float4*>(dypad + ((long)b * TP + PL) * C + i);
+    op[0] = make_float4(o[0], o[1], o[2], o[3]);
+    op[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(dgamma + (long)(c + j) * T + t, ag[j]);
+    atomicAdd(dbeta + (long)(c + j) * T + t, ab[j]);
   }
 }
 
+// m12: 2*B floats of scratch
 inline int ln_ct_act_bwd(const float* dout, const float* y, const float* stats, const float* gamma, const float* beta,
-                         float* dypad, float* dgamma, float* dbeta, int B, int T, int C, int PL, int taps, int act,
+                         float* dypad, float* dgamma, float* dbeta, float* m12, int B, int T, int C, int PL, int taps, int act,
                          const Drop& drop, cudaStream_t st) {
+  if (C & 7) return EEGCLIP_ERR_UNSUPPORTED;
   ProfScope prof(PROF_LNCT, st);
-  ln_ct_act_bwd_kernel<<<B, 512, 0, st>>>(dout, y, stats, gamma, beta, dypad, dgamma, dbeta, T, C, PL, T + taps - 1, act, drop);
+  ln_ct_bwd_stats_kernel<<<B, 512, 0, st>>>(dout, y, stats, gamma, beta, m12, T, C, act);
+  LAUNCH_CHECK();
+  const long n8 = (long)T * C / 8;
+  const int groups = B < 32 ? B : 32;
+  dim3 grid((unsigned)((n8 + 255) / 256), groups);
+  ln_ct_bwd_apply_kernel<<<grid, 256, 0, st>>>(dout, y, stats, m12, gamma, beta, dypad, dgamma, dbeta, B, T, C, PL, T + taps - 1, act, drop);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

@@ -171,6 +171,8 @@ struct LinTcArgs {
   int pro; Drop pro_drop;         // prologue on A (element index m*K + k)
   const float* bias;              // + bias[n]
   int act; float* aux;            // act == 1: aux = v (pre-activation, optional); v = GELU(v)
+                                  // act == 2: v = GELU(pre), aux = GELU'(pre), BOTH multiplied by the dropout mask below
+  const float* mul_src;           // v *= mul_src[m][n]
   int drop_on; Drop drop;         // v *= dropmult(m*N + n)
   const float* act_grad_src;      // v *= GELU'(src[m][n])
   const float* residual;          // v += residual[m][n]
@@ -305,13 +307,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
             float4 r = *reinterpret_cast<const float4*>(stg + rl * EPI_LD + cq);
             const long ci = m * a.ldc + n;
             r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+            float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
             if (a.act == 1) {
               if (a.aux) *reinterpret_cast<float4*>(a.aux + ci) = r;
               r.x = gelu_f(r.x); r.y = gelu_f(r.y); r.z = gelu_f(r.z); r.w = gelu_f(r.w);
+            } else if (a.act == 2) {
+              gelu_both(r.x, r.x, gd.x); gelu_both(r.y, r.y, gd.y); gelu_both(r.z, r.z, gd.z); gelu_both(r.w, r.w, gd.w);
             }
             if (a.drop_on) {
               const float4 mk = drop_mult4(a.drop, (uint64_t)m * (uint64_t)N + (uint64_t)n);
               r.x *= mk.x; r.y *= mk.y; r.z *= mk.z; r.w *= mk.w;
+              gd.x *= mk.x; gd.y *= mk.y; gd.z *= mk.z; gd.w *= mk.w;
+            }
+            if (a.act == 2) *reinterpret_cast<float4*>(a.aux + ci) = gd;
+            if (a.mul_src) {
+              const float4 s4 = ld_act(reinterpret_cast<const float4*>(a.mul_src + ci), a.policy);
+              r.x *= s4.x; r.y *= s4.y; r.z *= s4.z; r.w *= s4.w;
             }
             if (a.act_grad_src) {
               const float4 s4 = ld_act(reinterpret_cast<const float4*>(a.act_grad_src + ci), a.policy);
@@ -583,20 +594,28 @@ struct WgradReduceArgs {
   float* dW[4]; float* db[4];     // destination d covers rows [d*rows_per_dst, (d+1)*rows_per_dst); null = discard (padding rows)
 };
 static __global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const WgradReduceArgs a) {
-  __shared__ float sh[4][64];
+  // 32 consecutive outputs x 8 partial groups per CTA; 8 independent loads in flight per thread (latency-bound otherwise)
+  __shared__ float sh[8][33];
   const int total = a.Nout * a.Kin + a.Nout;
-  const int i = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int g = threadIdx.x >> 6;
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   float s = 0.f;
   if (i < total) {
     const float* p = a.partial + (long)blockIdx.y * a.ctas * total + i;
-#pragma unroll 4
-    for (int c = g; c < a.ctas; c += 4) s += p[(long)c * total];
+    int c = g;
+    for (; c + 56 < a.ctas; c += 64) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = p[(long)(c + 8 * u) * total];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; c < a.ctas; c += 8) s += p[(long)c * total];
   }
-  sh[g][threadIdx.x & 63] = s;
+  sh[g][lane] = s;
   __syncthreads();
   if (g == 0 && i < total) {
-    s = sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x];
+    s = ((sh[0][lane] + sh[1][lane]) + (sh[2][lane] + sh[3][lane])) + ((sh[4][lane] + sh[5][lane]) + (sh[6][lane] + sh[7][lane]));
     if (a.log_scale) s *= __expf(*a.log_scale);
     if (i < a.Nout * a.Kin) {
       const int n = i / a.Kin, k = i - n * a.Kin;
@@ -648,7 +667,7 @@ inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const d
   for (int i = 0; i < 3; ++i) { r.dW[i] = dW[i]; r.db[i] = db[i]; }
   r.dW[3] = nullptr; r.db[3] = nullptr;
   const int total = a.Nout * a.Kin + a.Nout;
-  lin_wgrad_reduce_kernel<<<dim3((total + 63) / 64, kin_blocks), 256, 0, st>>>(r);
+  lin_wgrad_reduce_kernel<<<dim3((total + 31) / 32, kin_blocks), 256, 0, st>>>(r);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

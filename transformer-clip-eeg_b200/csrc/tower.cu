@@ -41,8 +41,10 @@ struct SaveLayout {
   size_t conv_stride, xf_stride, conv0, xf0, total;
   // within a conv block: y (n*C), out (n*C), stats (2B rounded to 4)
   size_t c_y, c_out, c_stats;
-  // within a transformer block: qkv (n*192), o (n*C), lse (B*8*T), z1 (n*C), fpre (n*FF), zout (n*C)
-  size_t x_qkv, x_o, x_lse, x_z1, x_fpre, x_zout, x_wp;
+  // within a transformer block: qkv (n*192), o (n*C), lse (B*8*T), z1 (n*C), fpre (n*FF), gp (n*FF), zout (n*C)
+  //   fp32 path   : fpre = FFN pre-activation (GELU and mask recomputed in the backward), gp unused
+  //   tcgen05 path: fpre slot holds f = dropout(GELU(pre)), gp = mask * GELU'(pre): the backward multiplies, no erf / Philox
+  size_t x_qkv, x_o, x_lse, x_z1, x_fpre, x_gp, x_zout, x_wp;
   size_t map_wp;               // packed eeg_spatial_mapping weights (forward + data-gradient forms)
 };
 
@@ -69,7 +71,7 @@ SaveLayout save_layout(const eegclip_tower_desc& d) {
   L.c_y = 0; L.c_out = n * C; L.c_stats = 2 * n * C;
   L.conv_stride = 2 * n * C + align_up((size_t)2 * d.B, 4);
   L.x_qkv = 0; L.x_o = n * AQKV; L.x_lse = L.x_o + n * C; L.x_z1 = L.x_lse + align_up((size_t)d.B * AH * d.T, 4);
-  L.x_fpre = L.x_z1 + n * C; L.x_zout = L.x_fpre + n * FF;
+  L.x_fpre = L.x_z1 + n * C; L.x_gp = L.x_fpre + n * FF; L.x_zout = L.x_gp + n * FF;
   L.x_wp = L.x_zout + n * C;
   L.xf_stride = L.x_wp + XfPacked::BYTES / sizeof(float);
   L.map_wp = o; o += MAP_WP_BYTES / sizeof(float);
@@ -229,7 +231,8 @@ int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP
                    int Cin, int Cout, int taps, int act, const Drop& drop, cudaStream_t st) {
   const int PL = (taps - 1) / 2, PLb = taps - 1 - PL, TP = T + taps - 1;
   CUDA_TRY(cudaMemsetAsync(dypad, 0, (size_t)B * TP * Cout * sizeof(float), st));
-  TRY(ln_ct_act_bwd(dout, y, stats, p.g, p.be, dypad, gr.g, gr.be, B, T, Cout, PLb, taps, act, drop, st));
+  TRY(ln_ct_act_bwd(dout, y, stats, p.g, p.be, dypad, gr.g, gr.be, wtmp /* 2B floats of per-sample means */, B, T, Cout, PLb, taps, act,
+                    drop, st));
   TRY(colsum(dypad, gr.b, (long)B * TP, Cout, Cout, st));
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
     TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, taps, PLb, du, gr.w, B, T, tcs, st));
@@ -243,7 +246,7 @@ int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP
   return EEGCLIP_OK;
 }
 
-struct XfSave { float *qkv, *o, *lse, *z1, *fpre, *zout; uint8_t* wp; };
+struct XfSave { float *qkv, *o, *lse, *z1, *fpre, *gp, *zout; uint8_t* wp; };
 bool xf_tc_ok(const eegclip_tower_desc& d);
 int xf_block_fwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const float* zin, const XfSave& s, Scratch& w, cudaStream_t st);
 int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const XfG& g, const float* zin, const XfSave& s,
@@ -372,13 +375,14 @@ int xf_block_fwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
   }
   TRY(ln64_fwd(s.z1, p.ln2g, p.ln2b, w.h, n, st));
   {
-    LinTcArgs a = lin_args(w.h, C, s.wp + XfPacked::W1_F, w.f, FF, n, FF, C);
-    a.bias = p.b1; a.act = 1; a.aux = s.fpre;
+    // f = mask * GELU(pre) -> saved (W2 operand now, dW2 operand later); gp = mask * GELU'(pre) -> saved for the data gradient
+    LinTcArgs a = lin_args(w.h, C, s.wp + XfPacked::W1_F, s.fpre, FF, n, FF, C);
+    a.bias = p.b1; a.act = 2; a.aux = s.gp;
     a.drop = make_drop(d.seed, layer, SITE_FFN_HID, d.p_ffn_hid, d.train); a.drop_on = a.drop.enabled;
     TRY(lin_tc_launch(d.math, a, st));
   }
   {
-    LinTcArgs a = lin_args(w.f, FF, s.wp + XfPacked::W2_F, s.zout, C, n, C, FF);
+    LinTcArgs a = lin_args(s.fpre, FF, s.wp + XfPacked::W2_F, s.zout, C, n, C, FF);
     a.bias = p.b2; a.drop = make_drop(d.seed, layer, SITE_FFN_OUT, d.p_ffn_out, d.train); a.drop_on = a.drop.enabled; a.residual = s.z1;
     TRY(lin_tc_launch(d.math, a, st));
   }
@@ -397,7 +401,7 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
     LinWgradArgs a{};
     a.dy = dzout; a.lddy = C; a.Nout = C; a.x = s.fpre; a.ldx = FF; a.Kin = FF; a.M = (int)n;
     a.pro_dy = d_out.enabled ? PRO_DROP : PRO_NONE; a.drop_dy = d_out;
-    a.pro_x = PRO_GELU_DROP; a.drop_x = d_hid;                       // f = dropout(GELU(fpre)) recomputed on the fly
+    a.pro_x = PRO_NONE; a.drop_x = d_hid;                            // x = f = dropout(GELU(pre)), saved by the forward
     a.partial = w.wgp;
     float* dW[3] = {g.w2, nullptr, nullptr}; float* db[3] = {g.b2, nullptr, nullptr};
     TRY(lin_wgrad_launch(d.math, a, dW, db, C, st));
@@ -405,7 +409,7 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
   {
     LinTcArgs a = lin_args(dzout, C, s.wp + XfPacked::W2_D, w.dfpre, FF, n, FF, C);
     a.pro = d_out.enabled ? PRO_DROP : PRO_NONE; a.pro_drop = d_out;
-    a.drop = d_hid; a.drop_on = d_hid.enabled; a.act_grad_src = s.fpre;
+    a.mul_src = s.gp;                                                // * mask * GELU'(pre), saved by the forward
     TRY(lin_tc_launch(d.math, a, st));
   }
   TRY(ln64_fwd(s.z1, p.ln2g, p.ln2b, w.h, n, st));
@@ -455,7 +459,7 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
 
 XfSave xf_save(float* save, const SaveLayout& L, int j) {
   float* b = save + L.xf0 + L.xf_stride * j;
-  return XfSave{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, b + L.x_zout, (uint8_t*)(b + L.x_wp)};
+  return XfSave{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, b + L.x_gp, b + L.x_zout, (uint8_t*)(b + L.x_wp)};
 }
 
 }  // namespace
@@ -716,7 +720,7 @@ int eegclip_xfblock_forward(const eegclip_xfblock_desc* d, const float* const* p
   eegclip_tower_desc t = xf_as_tower(d);
   SaveLayout L = save_layout(t);
   float* b = (float*)save;
-  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, zout, (uint8_t*)(b + L.x_wp)};
+  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, b + L.x_gp, zout, (uint8_t*)(b + L.x_wp)};
   Scratch w = scratch_layout(t, (float*)scratch);
   const float* const* tp = params - 2;  // xf_at() skips the two mapping entries
   return xf_block_fwd(t, d->layer, xf_at<XfP>(tp, 0, 0), zin, xs, w, (cudaStream_t)stream);
@@ -730,7 +734,7 @@ int eegclip_xfblock_backward(const eegclip_xfblock_desc* d, const float* const* 
   eegclip_tower_desc t = xf_as_tower(d);
   SaveLayout L = save_layout(t);
   float* b = (float*)save;
-  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, nullptr, (uint8_t*)(b + L.x_wp)};
+  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, b + L.x_gp, nullptr, (uint8_t*)(b + L.x_wp)};
   Scratch w = scratch_layout(t, (float*)scratch);
   if (grad_base && grad_bytes) CUDA_TRY(cudaMemsetAsync(grad_base, 0, grad_bytes, st));
   return xf_block_bwd(t, d->layer, xf_at<XfP>(params - 2, 0, 0), xf_at<XfG>(grads - 2, 0, 0), zin, xs, dzout, dzin, w, st);
