@@ -98,6 +98,9 @@ EEGCLIP_API const char* eegclip_build_info(void);
 EEGCLIP_API long long eegclip_launch_count(void);
 /* Development knob for kernel tuning sweeps (tools/bench_xfblock.py); 0 everywhere = shipped configuration. */
 EEGCLIP_API int eegclip_tune_set(int32_t key, int32_t value);
+/* Development: device buffer (>= 3*256 uint64) that CTA 0 of the token-GEMM kernel fills with a (event, globaltimer) timeline
+ * of its producer / MMA / epilogue roles; NULL (default) disables it. */
+EEGCLIP_API int eegclip_debug_buffer(void* dev_ptr);
 EEGCLIP_API int eegclip_profile_begin(void);
 EEGCLIP_API int eegclip_profile_end(double* ms_by_class, long long* launches_by_class, int32_t n_classes);
 

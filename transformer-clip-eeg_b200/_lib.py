@@ -70,6 +70,7 @@ SIGNATURES = {
     "eegclip_build_info": (C.c_char_p, []),
     "eegclip_launch_count": (C.c_longlong, []),
     "eegclip_tune_set": (C.c_int, [_i32, _i32]),
+    "eegclip_debug_buffer": (C.c_int, [_vp]),
     "eegclip_profile_begin": (C.c_int, []),
     "eegclip_profile_end": (C.c_int, [_vp, _vp, _i32]),
     "eegclip_tower_workspace": (C.c_int, [C.POINTER(TowerDesc), _psz, _psz]),

@@ -25,7 +25,8 @@ namespace eegclip {
 
 // ---- launch accounting + optional per-kernel-class device timing (bench.py roofline; see eegclip_profile_*) ----
 extern long long g_launch_count;
-extern int g_tune[16];   // development knobs (eegclip_tune_set): 0 lin ring depth, 1 streaming-load policy
+extern int g_tune[16];
+extern unsigned long long* g_dbg_buf;   // development timeline buffer (eegclip_debug_buffer), nullptr in production   // development knobs (eegclip_tune_set): 0 lin ring depth, 1 streaming-load policy
 enum : int { PROF_CONV_TC = 0, PROF_WGRAD_TC = 1, PROF_ATTN_FWD = 2, PROF_ATTN_BWD = 3, PROF_LNCT = 4, PROF_GEMM_F32 = 5, PROF_LIN_TC = 6, PROF_LIN_WGRAD = 7, PROF_LSTM = 8, PROF_NCLASS = 12 };
 void prof_begin(int cls, cudaStream_t st);
 void prof_end(int cls, cudaStream_t st);
@@ -61,7 +62,8 @@ __host__ inline Drop make_drop(uint64_t seed, int layer, int site, float p, int 
   return d;
 }
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+// not inlined on purpose: ~100 instructions per copy, and the fused kernels call it from many unrolled sites
+static __device__ __noinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {

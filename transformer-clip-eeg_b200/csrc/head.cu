@@ -15,6 +15,7 @@ using namespace eegclip;
 namespace eegclip {
 long long g_launch_count = 0;
 int g_tune[16] = {0};
+unsigned long long* g_dbg_buf = nullptr;
 constexpr int PROF_MAX = 8192;
 static bool g_prof_on = false;
 static int g_prof_n = 0;
@@ -194,6 +195,11 @@ extern "C" {
 int eegclip_abi_version(void) { return EEGCLIP_ABI_VERSION; }
 
 long long eegclip_launch_count(void) { return eegclip::g_launch_count; }
+
+int eegclip_debug_buffer(void* dev_ptr) {
+  eegclip::g_dbg_buf = (unsigned long long*)dev_ptr;
+  return EEGCLIP_OK;
+}
 
 int eegclip_tune_set(int32_t key, int32_t value) {
   if (key < 0 || key >= 16) return EEGCLIP_ERR_ARG;

@@ -42,6 +42,10 @@ constexpr int NEPI = 8, NPROD = 4;           // epilogue / producer warps (13 wa
 constexpr int NTHREADS = (NEPI + NPROD + 1) * 32;
 
 enum : int { PRO_NONE = 0, PRO_DROP = 1, PRO_GELU_DROP = 2 };
+// Compile-time feature masks of the token-GEMM epilogue.  The kernels are instantiated per (prologue, epilogue mask) actually
+// used by the encoder, so each variant carries only its own code: the all-features kernel was > 64 KB of SASS, twice the
+// instruction cache, and every role ran ~4x slower than its instruction count predicts.  Mask -1 = generic (runtime flags).
+enum : int { EF_BIAS = 1, EF_ACT1 = 2, EF_ACT2 = 4, EF_DROP = 8, EF_ACTGRAD = 16, EF_MULSRC = 32, EF_RES = 64 };
 
 // streaming 128-bit load.  The CTAs here keep > 160 KB of shared memory, which leaves only a few KB of L1: plain
 // (allocating) loads then throttle on free L1 lines long before HBM saturates, so activations bypass L1 allocation.
@@ -49,6 +53,17 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
+}
+// development timeline (tools/lin_timeline.py): role `who` of CTA 0 records (event id, globaltimer ns) pairs
+__device__ __forceinline__ void dbg_mark(unsigned long long* dbg, int who, int& n, int ev) {
+  if (dbg && n < 120) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    dbg[who * 256 + 2 * n] = (unsigned long long)ev;
+    dbg[who * 256 + 2 * n + 1] = t;
+    ++n;
+    dbg[who * 256 + 255] = (unsigned long long)n;
+  }
 }
 __device__ __forceinline__ float4 ld_act(const float4* p, int policy) { return policy == 1 ? __ldg(p) : ld_stream(p); }
 
@@ -113,7 +128,7 @@ inline size_t packed_bytes(int N, int K) { return (size_t)N * K * 4; }
 //   bytes to a request (full lines) and the eight 16-byte smem stores of a quarter-warp fill one 128-byte wavefront.
 // Every thread keeps a FIXED chunk ((pw & 1) * 4 + (lane >> 3)), so column sums can live in registers.
 // ------------------------------------------------------------------------------------------------
-template <int ROWS, int NTERMS, int NPW /* producer warps */>
+template <int ROWS, int NTERMS, int NPW /* producer warps */, int PRO /* -1: runtime `pro` */>
 __device__ __forceinline__ void stage_chunk(const float* __restrict__ src, long ld, long row0, long rows_total, int col0, int ncols_total,
                                             uint8_t* dst, uint32_t CS, uint32_t PS, int pw, int lane, int pro, const Drop& drop,
                                             float* colsum /* nullptr or 8 running sums */, int policy) {
@@ -138,14 +153,15 @@ __device__ __forceinline__ void stage_chunk(const float* __restrict__ src, long 
     const int rb = it * (NPW / 2) + (pw >> 1);
     const int rl = rb * 8 + (lane & 7);
     float v[8] = {x0[it].x, x0[it].y, x0[it].z, x0[it].w, x1[it].x, x1[it].y, x1[it].z, x1[it].w};
-    if (pro != PRO_NONE) {
+    const int prog = PRO < 0 ? pro : PRO;
+    if (prog != PRO_NONE) {
       const long r = row0 + rl;
       if (r < rows_total) {
         const uint64_t idx = (uint64_t)r * (uint64_t)ncols_total + (uint64_t)(col0 + ch * 8);
         float mm[8];
         drop_mult8(drop, idx, mm);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (pro == PRO_GELU_DROP ? gelu_f(v[e]) : v[e]) * mm[e];
+        for (int e = 0; e < 8; ++e) v[e] = (prog == PRO_GELU_DROP ? gelu_f(v[e]) : v[e]) * mm[e];
       }
     }
     if (colsum) {
@@ -178,13 +194,14 @@ struct LinTcArgs {
   const float* residual;          // v += residual[m][n]
   int nstage;                     // ring depth (2..NSTAGE)
   int policy;                     // load policy of the streamed activations (0: L1 no-allocate, 1: __ldg)
+  unsigned long long* dbg;        // development timeline buffer (nullptr in production)
 };
 
 inline uint32_t lin_smem_bytes(int N, int K, int nstage = NSTAGE) {
   return (uint32_t)packed_bytes(N, K) + nstage * A_STAGE + NEPI * EPI_WARP_FLOATS * 4 + 256;
 }
 
-template <int NTERMS>
+template <int NTERMS, int PRO, int EF>
 __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -223,13 +240,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
     // ===== producers =====
     const int pw = warp - NEPI;
     int s = 0; uint32_t ph = 0;
+    unsigned long long* dbg = (blockIdx.x == 0 && pw == 0 && lane == 0) ? a.dbg : nullptr;
+    int dn = 0;
+    dbg_mark(dbg, 0, dn, 0);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int kc = 0; kc < nchunk; ++kc) {
         tc::mbar_wait(&empty[s], ph ^ 1);
-        stage_chunk<BM, NTERMS, NPROD>(a.A, a.lda, (long)tile * BM, a.M, kc * KC, K, sA + s * A_STAGE, A_CS, A_PLANE, pw, lane, a.pro,
+        dbg_mark(dbg, 0, dn, 1);
+        stage_chunk<BM, NTERMS, NPROD, PRO>(a.A, a.lda, (long)tile * BM, a.M, kc * KC, K, sA + s * A_STAGE, A_CS, A_PLANE, pw, lane, a.pro,
                                        a.pro_drop, nullptr, a.policy);
         tc::fence_async_smem();
         tc::mbar_arrive(&full[s]);
+        dbg_mark(dbg, 0, dn, 2);
         if (++s == nstage) { s = 0; ph ^= 1; }
       }
     }
@@ -242,6 +264,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
     }
     __syncwarp();
     tc::mbar_wait(wfull, 0);
+    unsigned long long* dbg = (blockIdx.x == 0 && lane == 0) ? a.dbg : nullptr;
+    int dn = 0;
+    dbg_mark(dbg, 1, dn, 10);
     const uint32_t sA_u = tc::smem_u32(sA), sW_u = tc::smem_u32(sW);
     const uint32_t idesc = tc::idesc_bf16(128, N, 0, 0);
     const uint32_t nb16 = (uint32_t)N * 16u;
@@ -251,10 +276,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
       const uint32_t buf = t & 1;
       tc::mbar_wait(&accempty[buf], ((t >> 1) & 1) ^ 1);
       tc::tc_fence_after();
+      dbg_mark(dbg, 1, dn, 11);
       const uint32_t d = tmem + buf * (uint32_t)N;
       for (int kc = 0; kc < nchunk; ++kc) {
         tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
+        dbg_mark(dbg, 1, dn, 12);
         const uint64_t a_hi = tc::smem_desc(sA_u + s * A_STAGE, A_CS, 128);
         const uint64_t a_lo = tc::smem_desc(sA_u + s * A_STAGE + A_PLANE, A_CS, 128);
         const uint64_t b_hi = tc::smem_desc(sW_u + (uint32_t)(kc * 8) * nb16, nb16, 128);
@@ -285,10 +312,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
     const int cq = (lane & 7) * 4, rq = lane >> 3;      // coalesced phase: 4 columns x (4 rows per iteration)
     const int cb0 = chalf * (N >> 1), cb1 = cb0 + (N >> 1);
     uint32_t t = 0;
+    unsigned long long* dbg = (blockIdx.x == 0 && warp == 0 && lane == 0) ? a.dbg : nullptr;
+    int dn = 0;
+    dbg_mark(dbg, 2, dn, 20);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
       const uint32_t buf = t & 1;
       tc::mbar_wait(&accfull[buf], (t >> 1) & 1);
       tc::tc_fence_after();
+      dbg_mark(dbg, 2, dn, 21);
       const long mrow0 = (long)tile * BM + q * 32;
       for (int cb = cb0; cb < cb1; cb += 32) {
         float v[32];
@@ -297,9 +328,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
         const int n = cb + cq;
+        const bool f_bias = EF < 0 ? a.bias != nullptr : (EF & EF_BIAS) != 0;
+        const bool f_act1 = EF < 0 ? a.act == 1 : (EF & EF_ACT1) != 0;
+        const bool f_act2 = EF < 0 ? a.act == 2 : (EF & EF_ACT2) != 0;
+        const bool f_drop = EF < 0 ? a.drop_on != 0 : (EF & EF_DROP) != 0;
+        const bool f_ag = EF < 0 ? a.act_grad_src != nullptr : (EF & EF_ACTGRAD) != 0;
+        const bool f_mul = EF < 0 ? a.mul_src != nullptr : (EF & EF_MULSRC) != 0;
+        const bool f_res = EF < 0 ? a.residual != nullptr : (EF & EF_RES) != 0;
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.bias) bb = *reinterpret_cast<const float4*>(a.bias + n);
-#pragma unroll 4
+        if (f_bias) bb = *reinterpret_cast<const float4*>(a.bias + n);
+#pragma unroll 2
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + rq;
           const long m = mrow0 + rl;
@@ -308,27 +346,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
             const long ci = m * a.ldc + n;
             r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
             float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.act == 1) {
+            if (f_act1) {
               if (a.aux) *reinterpret_cast<float4*>(a.aux + ci) = r;
               r.x = gelu_f(r.x); r.y = gelu_f(r.y); r.z = gelu_f(r.z); r.w = gelu_f(r.w);
-            } else if (a.act == 2) {
+            } else if (f_act2) {
               gelu_both(r.x, r.x, gd.x); gelu_both(r.y, r.y, gd.y); gelu_both(r.z, r.z, gd.z); gelu_both(r.w, r.w, gd.w);
             }
-            if (a.drop_on) {
+            if (f_drop) {
               const float4 mk = drop_mult4(a.drop, (uint64_t)m * (uint64_t)N + (uint64_t)n);
               r.x *= mk.x; r.y *= mk.y; r.z *= mk.z; r.w *= mk.w;
               gd.x *= mk.x; gd.y *= mk.y; gd.z *= mk.z; gd.w *= mk.w;
             }
-            if (a.act == 2) *reinterpret_cast<float4*>(a.aux + ci) = gd;
-            if (a.mul_src) {
+            if (f_act2) *reinterpret_cast<float4*>(a.aux + ci) = gd;
+            if (f_mul) {
               const float4 s4 = ld_act(reinterpret_cast<const float4*>(a.mul_src + ci), a.policy);
               r.x *= s4.x; r.y *= s4.y; r.z *= s4.z; r.w *= s4.w;
             }
-            if (a.act_grad_src) {
+            if (f_ag) {
               const float4 s4 = ld_act(reinterpret_cast<const float4*>(a.act_grad_src + ci), a.policy);
               r.x *= gelu_grad_f(s4.x); r.y *= gelu_grad_f(s4.y); r.z *= gelu_grad_f(s4.z); r.w *= gelu_grad_f(s4.w);
             }
-            if (a.residual) {
+            if (f_res) {
               // plain (coherent) load: the residual may alias C (K-split accumulation passes)
               const float4 s4 = *reinterpret_cast<const float4*>(a.residual + ci);
               r.x += s4.x; r.y += s4.y; r.z += s4.z; r.w += s4.w;
@@ -340,6 +378,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
       }
       tc::tc_fence_before();
       tc::mbar_arrive(&accempty[buf]);
+      dbg_mark(dbg, 2, dn, 22);
     }
   }
   tc::tc_fence_before();
@@ -352,23 +391,48 @@ inline bool lin_tc_supported(long M, int N, int K) {
          lin_smem_bytes(N, K, 2) <= 227u * 1024u;
 }
 
-template <int NTERMS>
-inline int lin_tc_launch_t(LinTcArgs a, cudaStream_t st) {
+template <int NTERMS, int PRO, int EF>
+inline int lin_tc_launch_v(const LinTcArgs& a, int grid, uint32_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(lin_tc_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(lin_tc_kernel<NTERMS, PRO, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
+  lin_tc_kernel<NTERMS, PRO, EF><<<grid, NTHREADS, smem, st>>>(a);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+template <int NTERMS>
+inline int lin_tc_launch_t(LinTcArgs a, cudaStream_t st) {
   const int ntiles = (a.M + BM - 1) / BM;
   const int grid = ntiles < 148 ? ntiles : 148;
   a.nstage = g_tune[0] >= 2 && g_tune[0] <= NSTAGE ? g_tune[0] : 2;
   while (a.nstage > 2 && lin_smem_bytes(a.N, a.K, a.nstage) > 227u * 1024u) --a.nstage;
   a.policy = g_tune[1];
+  a.dbg = g_dbg_buf;
+  const uint32_t smem = lin_smem_bytes(a.N, a.K, a.nstage);
+  const int mask = (a.bias ? EF_BIAS : 0) | (a.act == 1 ? EF_ACT1 : 0) | (a.act == 2 ? EF_ACT2 : 0) | (a.drop_on ? EF_DROP : 0) |
+                   (a.act_grad_src ? EF_ACTGRAD : 0) | (a.mul_src ? EF_MULSRC : 0) | (a.residual ? EF_RES : 0);
   ProfScope prof(PROF_LIN_TC, st);
-  lin_tc_kernel<NTERMS><<<grid, NTHREADS, lin_smem_bytes(a.N, a.K, a.nstage), st>>>(a);
-  LAUNCH_CHECK();
-  return EEGCLIP_OK;
+  if (g_tune[3] == 0) {   // g_tune[3] != 0 forces the generic kernel (development)
+    // the variants the encoder launches: QKV / plain, out-proj + FFN2, FFN1, and the four data gradients
+    if (a.pro == PRO_NONE) {
+      if (mask == 0) return lin_tc_launch_v<NTERMS, PRO_NONE, 0>(a, grid, smem, st);
+      if (mask == EF_BIAS) return lin_tc_launch_v<NTERMS, PRO_NONE, EF_BIAS>(a, grid, smem, st);
+      if (mask == EF_RES) return lin_tc_launch_v<NTERMS, PRO_NONE, EF_RES>(a, grid, smem, st);
+      if (mask == (EF_BIAS | EF_RES)) return lin_tc_launch_v<NTERMS, PRO_NONE, EF_BIAS | EF_RES>(a, grid, smem, st);
+      if (mask == (EF_BIAS | EF_DROP | EF_RES)) return lin_tc_launch_v<NTERMS, PRO_NONE, EF_BIAS | EF_DROP | EF_RES>(a, grid, smem, st);
+      if (mask == (EF_BIAS | EF_ACT2 | EF_DROP)) return lin_tc_launch_v<NTERMS, PRO_NONE, EF_BIAS | EF_ACT2 | EF_DROP>(a, grid, smem, st);
+      if (mask == (EF_BIAS | EF_ACT2)) return lin_tc_launch_v<NTERMS, PRO_NONE, EF_BIAS | EF_ACT2>(a, grid, smem, st);
+      if (mask == EF_MULSRC) return lin_tc_launch_v<NTERMS, PRO_NONE, EF_MULSRC>(a, grid, smem, st);
+    } else if (a.pro == PRO_DROP) {
+      if (mask == 0) return lin_tc_launch_v<NTERMS, PRO_DROP, 0>(a, grid, smem, st);
+      if (mask == EF_MULSRC) return lin_tc_launch_v<NTERMS, PRO_DROP, EF_MULSRC>(a, grid, smem, st);
+    }
+  }
+  return lin_tc_launch_v<NTERMS, -1, -1>(a, grid, smem, st);
 }
 inline int lin_tc_launch(int math, const LinTcArgs& a, cudaStream_t st) {
   return math == EEGCLIP_MATH_BF16 ? lin_tc_launch_t<1>(a, st) : lin_tc_launch_t<3>(a, st);
@@ -398,11 +462,13 @@ struct LinWgradArgs {
 inline uint32_t wgrad_stage_bytes(int Nout, int Kin) { return (uint32_t)(Nout + Kin) * WT * 4; }
 inline uint32_t wgrad_lin_smem_bytes(int Nout, int Kin) { return 2 * wgrad_stage_bytes(Nout, Kin) + 8 * 256 * 4 + 256; }
 
-template <int NTERMS>
+// PDY / PX: compile-time prologues of dy / x (-1 = runtime), WDB: bias-gradient column sums (-1 = runtime)
+template <int NTERMS, int PDY, int PX, int WDB>
 __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Nout = a.Nout, Kin = a.Kin;
+  const bool want_db = WDB < 0 ? a.want_db != 0 : WDB != 0;
   const uint32_t PSD = (uint32_t)(Nout / 8) * W_CS, PSX = (uint32_t)(Kin / 8) * W_CS;   // plane strides
   const uint32_t STAGE = 2 * PSD + 2 * PSX;
   float* sCol = reinterpret_cast<float*>(smem + 2 * STAGE);     // [8 row blocks][256] column-sum staging
@@ -467,7 +533,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
         if (c < ntot) {
           const bool is_dy = c < ndc;
           float v[8] = {x0[c].x, x0[c].y, x0[c].z, x0[c].w, x1[c].x, x1[c].y, x1[c].z, x1[c].w};
-          const int pro = is_dy ? a.pro_dy : a.pro_x;
+          const int pro = is_dy ? (PDY < 0 ? a.pro_dy : PDY) : (PX < 0 ? a.pro_x : PX);
           if (pro != PRO_NONE && ok) {
             const int col = (is_dy ? c : c - ndc) * KC + ch * 8;
             const uint64_t idx = (uint64_t)r * (uint64_t)(is_dy ? Nout : Kin) + (uint64_t)col;
@@ -477,7 +543,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = (pro == PRO_GELU_DROP ? gelu_f(v[e]) : v[e]) * mm[e];
           }
-          if (c < 4 && is_dy && a.want_db) {
+          if (c < 4 && is_dy && want_db) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) cs[c < 4 ? c : 0][e] += v[e];
           }
@@ -520,7 +586,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
         __syncwarp();
       }
     }
-    if (a.want_db) {
+    if (want_db) {
       // reduce over the 8 token lanes of a warp (lane & 7); the 8 row-block warps of a chunk half are summed below
 #pragma unroll
       for (int dc = 0; dc < 4; ++dc)
@@ -570,7 +636,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
         }
       }
     }
-    if (a.want_db) {
+    if (want_db) {
       float* pb = part + (long)Nout * Kin;
       for (int n = tid; n < Nout; n += 128) {
         float sum = 0.f;
@@ -643,15 +709,22 @@ inline size_t lin_wgrad_partial_bytes(int Nout, int Kin, int kin_blocks = 1) {
   return (size_t)kin_blocks * wgrad_token_ctas(WG_MAX_CTAS, kin_blocks) * ((size_t)Nout * Kin + Nout) * sizeof(float);
 }
 
-template <int NTERMS>
-inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const db[3], int rows_per_dst, long ldw, cudaStream_t st,
-                              const float* log_scale = nullptr, int kin_blocks = 1) {
+template <int NTERMS, int PDY, int PX, int WDB>
+inline int lin_wgrad_launch_v(const LinWgradArgs& a, dim3 grid, uint32_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(lin_wgrad_tc_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(lin_wgrad_tc_kernel<NTERMS, PDY, PX, WDB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
+  lin_wgrad_tc_kernel<NTERMS, PDY, PX, WDB><<<grid, WG_THREADS, smem, st>>>(a);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+template <int NTERMS>
+inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const db[3], int rows_per_dst, long ldw, cudaStream_t st,
+                              const float* log_scale = nullptr, int kin_blocks = 1) {
   if (!lin_wgrad_tc_supported(a.M, a.Nout, a.Kin)) return EEGCLIP_ERR_UNSUPPORTED;
   const int nst = (a.M + WT - 1) / WT;
   const int ctas = wgrad_token_ctas(nst, kin_blocks);
@@ -659,8 +732,14 @@ inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const d
   a.policy = g_tune[1];
   {
     ProfScope prof(PROF_LIN_WGRAD, st);
-    lin_wgrad_tc_kernel<NTERMS><<<dim3(ctas, kin_blocks), WG_THREADS, wgrad_lin_smem_bytes(a.Nout, a.Kin), st>>>(a);
-    LAUNCH_CHECK();
+    const dim3 grid(ctas, kin_blocks);
+    const uint32_t smem = wgrad_lin_smem_bytes(a.Nout, a.Kin);
+    int rc;
+    if (g_tune[3] == 0 && a.pro_x == PRO_NONE && a.pro_dy == PRO_NONE && !a.want_db) rc = lin_wgrad_launch_v<NTERMS, PRO_NONE, PRO_NONE, 0>(a, grid, smem, st);
+    else if (g_tune[3] == 0 && a.pro_x == PRO_NONE && a.pro_dy == PRO_NONE && a.want_db) rc = lin_wgrad_launch_v<NTERMS, PRO_NONE, PRO_NONE, 1>(a, grid, smem, st);
+    else if (g_tune[3] == 0 && a.pro_x == PRO_NONE && a.pro_dy == PRO_DROP && a.want_db) rc = lin_wgrad_launch_v<NTERMS, PRO_DROP, PRO_NONE, 1>(a, grid, smem, st);
+    else rc = lin_wgrad_launch_v<NTERMS, -1, -1, -1>(a, grid, smem, st);
+    if (rc != EEGCLIP_OK) return rc;
   }
   WgradReduceArgs r;
   r.partial = a.partial; r.ctas = ctas; r.Nout = a.Nout; r.Kin = a.Kin; r.rows_per_dst = rows_per_dst; r.ldw = ldw > 0 ? ldw : a.Kin; r.log_scale = log_scale;
