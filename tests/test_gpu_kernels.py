@@ -1,0 +1,156 @@
+"""GPU: kernel-level parity of the tensor-core / recurrence kernels against the live oracle (fp64 on CPU) and against the
+exact-fp32 companion path of the same library, at the shapes and edge cases the model-level golden tests do not reach."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from _util import rel_err
+from oracle import eegclip_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-3   # north star: outputs and gradients <= 1e-3 relative
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import transformer_clip_eeg_b200 as p  # noqa: F401
+    from transformer_clip_eeg_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+@pytest.fixture(scope="module")
+def cm(lib):
+    from transformer_clip_eeg_b200 import clip_model
+    return clip_model
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bidirectional LSTM (clip_model.py:267-268,322-323) vs the oracle's restated recurrence, incl. ragged batches
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("In,H,B,T", [(64, 128, 5, 24), (64, 128, 8, 64), (256, 4, 7, 40), (256, 4, 32, 64)])
+def test_bilstm_vs_oracle(cm, In, H, B, T):
+    torch.manual_seed(In + H + B)
+    mod = torch.nn.LSTM(In, H, batch_first=True, bidirectional=True)
+    x = torch.randn(B, T, In)
+    w = torch.randn(B, T, 2 * H)
+    sd = {k: v.detach().double().requires_grad_(True) for k, v in mod.state_dict().items()}
+    xr = x.double().requires_grad_(True)
+    yr = O.bilstm(sd, "", xr)
+    (yr * w.double()).sum().backward()
+    mg = mod.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    yg = cm._bilstm(mg, xg)
+    assert yg.shape == (B, T, 2 * H)
+    (yg * w.to(DEV)).sum().backward()
+    assert rel_err(yg, yr) < TOL
+    assert rel_err(xg.grad, xr.grad) < TOL
+    gall = sum(float(v.grad.norm()) ** 2 for v in sd.values()) ** 0.5
+    for k, p in mg.named_parameters():
+        assert rel_err(p.grad, sd[k].grad, floor=1e-3 * gall) < TOL, k
+
+
+def test_bilstm_uncovered_shape_uses_library(cm):
+    """Shapes outside the two of the default speech tower stay on the cuDNN library call."""
+    mod = torch.nn.LSTM(32, 16, batch_first=True, bidirectional=True).to(DEV)
+    y = cm._bilstm(mod, torch.randn(2, 8, 32, device=DEV))
+    assert y.shape == (2, 8, 32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tensor-core attention vs the exact-fp32 attention kernels of the same library (identical Philox masks)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,B,train,p", [(64, 3, False, 0.5), (192, 2, True, 0.5), (320, 2, True, 0.5), (128, 2, True, 0.3)])
+def test_attention_tc_vs_fp32(cm, lib, T, B, train, p):
+    torch.manual_seed(T + B)
+    blk = cm.TransformerEncoderBlock(64, drop_p=p, forward_drop_p=p).to(DEV)
+    blk.train(train)
+    x = torch.randn(B, T, 64, device=DEV)
+    w = torch.randn(B, T, 64, device=DEV)
+    res = {}
+    seed = 1234567
+    for math in ("fp32", "bf16x3"):
+        lib.set_default_math(math)
+        try:
+            torch.manual_seed(seed)       # same Philox key for both runs
+            xx = x.clone().requires_grad_(True)
+            blk.zero_grad()
+            y = blk(xx)
+            (y * w).sum().backward()
+            res[math] = [y.detach().clone(), xx.grad.detach().clone()] + [q.grad.detach().clone() for q in blk.parameters()]
+        finally:
+            lib.set_default_math("bf16x3")
+    gall = sum(float(t.norm()) ** 2 for t in res["fp32"][2:]) ** 0.5
+    for a, b in zip(res["bf16x3"], res["fp32"]):
+        assert rel_err(a, b, floor=1e-3 * gall) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# token GEMMs through the C ABI: every (N, K) family, ragged M, against fp64
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 64), (4100, 192, 64), (777, 256, 64), (2048, 64, 256), (1300, 64, 1024), (520, 64, 192),
+                                   (640, 128, 128)])
+def test_linear_tc_vs_fp64(cm, M, N, K):
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device=DEV, requires_grad=True)
+    w = (torch.randn(N, K, device=DEV) * 0.2).requires_grad_(True)
+    b = torch.randn(N, device=DEV, requires_grad=True)
+    g = torch.randn(M, N, device=DEV)
+    y = cm._LinearFn.apply(x, w, b)
+    (y * g).sum().backward()
+    xd, wd, bd, gd = (t.detach().double().cpu() for t in (x, w, b, g))
+    yr = xd @ wd.t() + bd
+    assert rel_err(y, yr) < 2e-5
+    assert rel_err(x.grad, gd @ wd) < 2e-5
+    assert rel_err(w.grad, gd.t() @ xd) < 2e-5
+    assert rel_err(b.grad, gd.sum(0)) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tcgen05 head at the benchmark size and sharded (two row blocks emulated on one GPU through the C ABI)
+# ---------------------------------------------------------------------------------------------------------------
+def _head_ref(E, S, tau):
+    Ed, Sd = E.detach().double().cpu().requires_grad_(True), S.detach().double().cpu().requires_grad_(True)
+    td = tau.detach().double().cpu().requires_grad_(True)
+    loss = O.symmetric_infonce(Ed, Sd, td)
+    loss.backward()
+    return loss, Ed.grad, Sd.grad, td.grad
+
+
+@pytest.mark.parametrize("B,D", [(256, 2560), (128, 1536), (320, 512)])
+def test_head_tc_vs_fp64(lib, B, D):
+    from transformer_clip_eeg_b200.parallel import infonce_loss
+    torch.manual_seed(B + D)
+    E = torch.randn(B, D, device=DEV, requires_grad=True)
+    S = (0.7 * E.detach() + torch.randn(B, D, device=DEV)).requires_grad_(True)   # correlated pairs: a peaked softmax
+    tau = torch.tensor(1.3, device=DEV, requires_grad=True)
+    loss = infonce_loss(E, S, tau)
+    loss.backward()
+    lr, dE, dS, dt = _head_ref(E, S, tau)
+    assert abs(float(loss) - float(lr)) <= 1e-5 * max(1.0, abs(float(lr)))
+    assert rel_err(E.grad, dE) < TOL and rel_err(S.grad, dS) < TOL
+    assert abs(float(tau.grad) - float(dt)) <= TOL * max(abs(float(dt)), 1e-3)
+
+
+def test_head_sharded_rows_match_unsharded(lib):
+    """Rank r of 2 scores rows [128r, 128r+128) against the gathered 256: LSE / diag / gradients equal the world-1 result."""
+    from transformer_clip_eeg_b200.parallel import CudaHeadOps
+    ops = CudaHeadOps()
+    torch.manual_seed(5)
+    Bg, b, D = 256, 128, 1536
+    En, _ = ops.l2norm_fwd(torch.randn(Bg, D, device=DEV))
+    Sn, _ = ops.l2norm_fwd(torch.randn(Bg, D, device=DEV))
+    tau = torch.tensor([0.4], device=DEV)
+    full = ops.lse(Sn, En, tau, Bg, 0, False)
+    parts = [ops.lse(Sn, En, tau, b, r * b, False) for r in range(2)]
+    vec = torch.cat(parts, dim=1)
+    assert rel_err(vec, full) < 1e-5
+    dl = torch.ones(1, device=DEV)
+    dS0, dE0, dt0 = ops.backward(Sn, En, tau, full, Bg, 0, dl, False)
+    outs = [ops.backward(Sn, En, tau, vec.contiguous(), b, r * b, dl, False) for r in range(2)]
+    assert rel_err(torch.cat([o[0] for o in outs]), dS0) < 1e-4
+    assert rel_err(torch.cat([o[1] for o in outs]), dE0) < 1e-4
+    assert abs(float(outs[0][2] + outs[1][2]) - float(dt0)) <= 1e-4 * max(abs(float(dt0)), 1e-3)

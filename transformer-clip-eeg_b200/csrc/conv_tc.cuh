@@ -66,6 +66,7 @@ struct ConvTcArgs {
   int row_off;            // smem row r holds src row r - row_off (zero outside)
   int taps;               // kernel size
   Drop drop;
+  unsigned long long* dbg; // development timeline (CTA 0): start, staged, mma-done, end (globaltimer ns)
 };
 
 __host__ __device__ inline uint32_t conv_smem_bytes(int T, int taps) {
@@ -94,6 +95,14 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
   uint32_t ncols = 64;
   while (ncols < (uint32_t)ntiles * 64u) ncols <<= 1;
 
+  auto stamp = [&](int slot) {
+    if (a.dbg && blockIdx.x == 0 && tid == 128) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.dbg[slot] = t;
+    }
+  };
+  stamp(0);
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
     tc::mbar_init(accfull, 1);
@@ -132,6 +141,7 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  stamp(1);
 
   if (warp == 0 && lane == 0) {
     // ===== weight producer: one 1-D bulk copy per tap into the ring =====
@@ -182,6 +192,7 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
     const int q = warp - 4;  // TMEM lane quarter of this warp
     tc::mbar_wait(accfull, 0);
     tc::tc_fence_after();
+    stamp(2);
     for (int tile = 0; tile < ntiles; ++tile) {
       const bool m64 = last64 && tile == ntiles - 1;
       const int row = m64 ? tile * 128 + q * 16 + lane : tile * 128 + q * 32 + lane;
@@ -211,6 +222,7 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
   }
   tc::tc_fence_before();
   __syncthreads();
+  stamp(3);
   if (warp == 2) tc::tmem_dealloc(tmem, ncols);
 }
 
@@ -391,7 +403,7 @@ inline int conv_tc_forward(int math, const float* xin, const float* skip_in, con
   convtc::pack_conv_weights_kernel<<<(taps * 8 * 64 + 255) / 256, 256, 0, st>>>(w, wp, 0, taps);
   LAUNCH_CHECK();
   convtc::ConvTcArgs a;
-  a.src = xin; a.skip = skip_in; a.wpacked = wp; a.bias = bias; a.out = y; a.T = T; a.src_rows = T; a.row_off = PL; a.taps = taps; a.drop = drop;
+  a.src = xin; a.skip = skip_in; a.wpacked = wp; a.bias = bias; a.out = y; a.T = T; a.src_rows = T; a.row_off = PL; a.taps = taps; a.drop = drop; a.dbg = g_dbg_buf;
   return math == EEGCLIP_MATH_BF16 ? conv_tc_launch<1>(a, B, st) : conv_tc_launch<3>(a, B, st);
 }
 
@@ -419,7 +431,7 @@ inline int conv_tc_backward(int math, const float* xin, const float* skip_in, co
   convtc::pack_conv_weights_kernel<<<(taps * 8 * 64 + 255) / 256, 256, 0, st>>>(w, wp, 1, taps);
   LAUNCH_CHECK();
   convtc::ConvTcArgs a;
-  a.src = dypad; a.skip = nullptr; a.wpacked = wp; a.bias = nullptr; a.out = du; a.T = T; a.src_rows = TP; a.row_off = 0; a.taps = taps;
+  a.src = dypad; a.skip = nullptr; a.wpacked = wp; a.bias = nullptr; a.out = du; a.T = T; a.src_rows = TP; a.row_off = 0; a.taps = taps; a.dbg = g_dbg_buf;
   a.drop = make_drop(0, 0, 0, 0.f, 0);
   int rc = math == EEGCLIP_MATH_BF16 ? conv_tc_launch<1>(a, B, st) : conv_tc_launch<3>(a, B, st);
   if (rc != EEGCLIP_OK) return rc;
