@@ -34,7 +34,10 @@ constexpr int WG_TAPS = 16;          // taps per weight-gradient CTA
 constexpr int WG_MAX_GROUPS = 37;    // 4 tap groups x 37 sample groups = 148 CTAs
 
 // ------------------------------------------------------------------------------------------------
-// Weight packing: fp32 W[co][ci][k]  ->  bf16 hi/lo, per tap [plane][k-chunk][n][8]
+// Weight packing: fp32 W[co][ci][k]  ->  bf16, per tap [k-chunk][n' = 128][8] with n' < 64 the hi part of output n' and
+// n' >= 64 the lo part of output n' - 64: ONE N=128 MMA computes A_hi.W_hi and A_hi.W_lo (the activation tile, the larger
+// operand, is read once for both terms -- the kernel is shared-memory-bandwidth bound at N = 64), a second N=64 MMA over the
+// first 64 rows of the same operand adds A_lo.W_hi.
 //   mode 0 (forward) : n = co, contraction index = ci, tap = k
 //   mode 1 (dgrad)   : n = ci, contraction index = co, tap k' holds W[..][..][63-k']
 // ------------------------------------------------------------------------------------------------
@@ -50,9 +53,9 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* _
   }
   uint4 hi, lo;
   tc::split8(v, hi, lo);
-  uint8_t* base = out + (long)tap * W_TAP_BYTES + ch * (CH * 16) + n * 16;
+  uint8_t* base = out + (long)tap * W_TAP_BYTES + ch * (2 * CH * 16) + n * 16;
   *reinterpret_cast<uint4*>(base) = hi;
-  *reinterpret_cast<uint4*>(base + W_PLANE_BYTES) = lo;
+  *reinterpret_cast<uint4*>(base + CH * 16) = lo;
 }
 
 struct ConvTcArgs {
@@ -92,8 +95,9 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
 
   const int ntiles = (T + 127) >> 7;
   const bool last64 = (T & 127) != 0;       // T % 128 == 64 -> last tile has M = 64
+  constexpr uint32_t TCOLS = NTERMS > 1 ? 128u : 64u;   // TMEM columns per time tile: [hi.hi + lo.hi | hi.lo]
   uint32_t ncols = 64;
-  while (ncols < (uint32_t)ntiles * 64u) ncols <<= 1;
+  while (ncols < (uint32_t)ntiles * TCOLS) ncols <<= 1;
 
   auto stamp = [&](int slot) {
     if (a.dbg && blockIdx.x == 0 && tid == 128) {
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
 
   if (warp == 0 && lane == 0) {
     // ===== weight producer: one 1-D bulk copy per tap into the ring =====
-    const uint32_t bytes = NTERMS > 1 ? W_TAP_BYTES : W_PLANE_BYTES;
+    const uint32_t bytes = W_TAP_BYTES;
     for (int tap = 0; tap < TAPS; ++tap) {
       const int s = tap % NSTAGE;
       const uint32_t ph = (tap / NSTAGE) & 1;
@@ -156,28 +160,32 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the loop (descriptors stay in uniform registers), one elected lane issues =====
     const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
-    const uint32_t id128 = tc::idesc_bf16(128, CH, 0, 0), id64 = tc::idesc_bf16(64, CH, 0, 0);
+    // idesc[m64][wide]: wide = N 128 (hi.hi | hi.lo in one MMA), narrow = N 64
+    const uint32_t idw128 = tc::idesc_bf16(128, 2 * CH, 0, 0), idw64 = tc::idesc_bf16(64, 2 * CH, 0, 0);
+    const uint32_t idn128 = tc::idesc_bf16(128, CH, 0, 0), idn64 = tc::idesc_bf16(64, CH, 0, 0);
     for (int tap = 0; tap < TAPS; ++tap) {
       const int s = tap % NSTAGE;
       const uint32_t ph = (tap / NSTAGE) & 1;
       tc::mbar_wait(&full[s], ph);
       tc::tc_fence_after();
       const uint32_t wb = sB_u + s * W_TAP_BYTES;
-      const uint64_t b_hi = tc::smem_desc(wb, CH * 16, 128), b_lo = tc::smem_desc(wb + W_PLANE_BYTES, CH * 16, 128);
+      const uint64_t b_w = tc::smem_desc(wb, 2 * CH * 16, 128);   // chunk stride 2048 B: rows 0-63 hi, 64-127 lo
       if (tc::elect_one()) {
         for (int tile = 0; tile < ntiles; ++tile) {
-          const uint32_t idesc = (last64 && tile == ntiles - 1) ? id64 : id128;
-          const uint32_t d = tmem + tile * 64;
+          const bool m64 = last64 && tile == ntiles - 1;
+          const uint32_t idw = m64 ? idw64 : idw128, idn = m64 ? idn64 : idn128;
+          const uint32_t d = tmem + tile * TCOLS;
           const uint32_t arow = sA_u + (uint32_t)(tile * 128 + tap) * 16u;
           const uint64_t a_hi = tc::smem_desc(arow, CS, 128), a_lo = tc::smem_desc(arow + PS, CS, 128);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t da = (uint64_t)((2 * ks * CS) >> 4);           // start-address field is in 16-byte units
-            const uint64_t db = (uint64_t)((2 * ks * (CH * 16)) >> 4);
-            tc::mma_bf16(d, a_hi + da, b_hi + db, idesc, (tap | ks) != 0);  // hi*hi
+            const uint64_t db = (uint64_t)((2 * ks * (2 * CH * 16)) >> 4);
             if (NTERMS > 1) {
-              tc::mma_bf16(d, a_hi + da, b_lo + db, idesc, 1);              // hi*lo
-              tc::mma_bf16(d, a_lo + da, b_hi + db, idesc, 1);              // lo*hi
+              tc::mma_bf16(d, a_hi + da, b_w + db, idw, (tap | ks) != 0);   // [hi.hi | hi.lo]
+              tc::mma_bf16(d, a_lo + da, b_w + db, idn, 1);                 // += lo.hi (first 64 columns)
+            } else {
+              tc::mma_bf16(d, a_hi + da, b_w + db, idn, (tap | ks) != 0);
             }
           }
         }
@@ -197,11 +205,17 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
       const bool m64 = last64 && tile == ntiles - 1;
       const int row = m64 ? tile * 128 + q * 16 + lane : tile * 128 + q * 32 + lane;
       const bool valid = m64 ? (lane < 16) : true;
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + tile * 64;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + tile * TCOLS;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float v[32];
         tc::tmem_ld32(taddr + half * 32, v);
+        if (NTERMS > 1) {
+          float v2[32];
+          tc::tmem_ld32(taddr + CH + half * 32, v2);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] += v2[c];
+        }
         if (valid && row < T) {
           float* o = a.out + ((long)b * T + row) * CH + half * 32;
           const uint64_t didx = ((uint64_t)b * T + row) * CH + half * 32;
