@@ -169,6 +169,54 @@ class SyntheticBatches:
             yield eeg, [speech], ids, torch.zeros(self.b, dtype=torch.int64)
 
 
+class DevicePrefetcher:
+    """Input pipeline of the hot loop (train_clip_final.py:475-479): yields device-resident (eeg, speech, ids) while the
+    NEXT batch's host->device copies run on a side stream (pinned staging buffers, double-buffered), so the 201-357 MB of
+    wav2vec2 features per batch cross PCIe under the previous step instead of in front of it.  `loader` yields the
+    reference's batch tuples (eeg (b,T,64), [speech (b,T,F)], ids (b,), subs)."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, device
+        self.stream = torch.cuda.Stream(device=device)
+        self._pinned = [None, None]
+
+    def _stage(self, slot, data):
+        eeg, speech, ids = data[0], data[1][0] if isinstance(data[1], (list, tuple)) else data[1], data[2]
+        src = (eeg.float(), speech.float(), ids.to(torch.int64))
+        if all(t.is_pinned() for t in src):
+            pin = src                                  # the loader already hands out page-locked batches (DataLoader(pin_memory=True))
+        else:
+            pin = self._pinned[slot]
+            if pin is None or any(p.shape != t.shape for p, t in zip(pin, src)):
+                pin = self._pinned[slot] = tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in src)
+            for p_, t in zip(pin, src):
+                p_.copy_(t)
+        with torch.cuda.stream(self.stream):
+            dev = tuple(p_.to(self.device, non_blocking=True) for p_ in pin)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return dev, ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        slot = 0
+        try:
+            nxt = self._stage(slot, next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev = nxt
+            slot ^= 1
+            try:
+                nxt = self._stage(slot, next(it))      # overlaps the step that consumes `cur`
+            except StopIteration:
+                nxt = None
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            for t in cur:
+                t.record_stream(torch.cuda.current_stream(self.device))
+            yield cur
+
+
 def printf(s, file):
     print(s)
     with open(file, 'a') as f:
@@ -217,10 +265,7 @@ def main(argv=None):
         if epoch > best_epoch + args.patience and epoch > args.warmup_epochs:
             break
         model.train()
-        for batch, data in enumerate(train_data):
-            eeg = data[0].to(device, dtype=torch.float, non_blocking=True)
-            speech = data[1][0].to(device, dtype=torch.float, non_blocking=True)
-            ids = data[2].to(device, dtype=torch.int64)
+        for batch, (eeg, speech, ids) in enumerate(DevicePrefetcher(train_data, device)):
             loss_ce, loss_avg, _ = train_step(model, opt, eeg, speech, ids, use_total=epoch >= args.warmup_epochs, group=group)
             if batch % 100 == 0 and rank == 0:
                 printf(f'train epoch {epoch} batch {batch} loss_ce  {loss_ce.item()} loss average eeg {loss_avg.item()}', file_loss)
