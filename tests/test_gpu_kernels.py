@@ -154,3 +154,42 @@ def test_head_sharded_rows_match_unsharded(lib):
     assert rel_err(torch.cat([o[0] for o in outs]), dS0) < 1e-4
     assert rel_err(torch.cat([o[1] for o in outs]), dE0) < 1e-4
     assert abs(float(outs[0][2] + outs[1][2]) - float(dt0)) <= 1e-4 * max(abs(float(dt0)), 1e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# gradient sinks: backward kernels writing straight into the optimizer's arena == ordinary autograd accumulation
+# ---------------------------------------------------------------------------------------------------------------
+def test_grad_sinks_match_autograd(cm, lib):
+    from transformer_clip_eeg_b200.optim import AdamW
+    from transformer_clip_eeg_b200 import train_clip_final as tcf
+    torch.manual_seed(11)
+    T, B = 64, 8
+    args = tcf.build_parser().parse_args(["--attention_depth", "2"])
+    model = tcf.build_model(args, T, 100, torch.device(DEV)).eval()
+    for m in model.modules():
+        if isinstance(m, torch.nn.LSTM):
+            m.train()
+    eeg, sp = torch.randn(B, T, 64, device=DEV), torch.randn(B, T, 1024, device=DEV)
+    ids = torch.arange(1, B + 1, device=DEV)
+    mem0 = model.eegMemoryBank.memory.clone()
+    # ordinary path: no arena registered yet
+    _, _, tot = model(eeg, sp, ids)
+    tot.backward()
+    ref = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    # sink path: arena views claimed after zero_grad
+    model.eegMemoryBank.memory.copy_(mem0)
+    opt = AdamW(model.parameters(), lr=1e-3, weight_decay=0.01)
+    _, _, tot = model(eeg, sp, ids)
+    opt.zero_grad()
+    tot.backward()
+    flat = opt.flat_grads()[0]
+    gall = sum(float(v.norm()) ** 2 for v in ref.values()) ** 0.5
+    for k, p in model.named_parameters():
+        assert p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr(), k   # still a view of the arena
+        assert rel_err(p.grad, ref[k], floor=1e-3 * gall) < 1e-5, k
+    # a second backward without zero_grad must accumulate (falls back to autograd's add)
+    _, _, tot = model(eeg, sp, ids)
+    model.eegMemoryBank.memory.copy_(mem0)
+    tot.backward()
+    w = dict(model.named_parameters())["eegModel.conv_0.conv.weight"]
+    assert rel_err(w.grad, 2 * ref["eegModel.conv_0.conv.weight"]) < 1e-3

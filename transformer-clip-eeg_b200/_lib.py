@@ -168,3 +168,37 @@ def ptr_table(tensors):
 def new_seed():
     """Philox key for one forward/backward pair, drawn from torch's CPU generator (honours manual_seed)."""
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+# ---------------------------------------------------------------------------------------------------
+# Gradient sinks: the optimizer (optim.AdamW) owns one flat gradient arena and registers, per parameter, the arena view that
+# is its ``.grad``.  A backward of this package then writes the parameter gradients straight into those views and returns
+# None for them, so autograd launches no ``grad += new`` kernel per parameter (229 launches per step in the default model).
+# A view is handed out at most once per zero_grad() epoch; any second backward falls back to the ordinary accumulate path.
+# ---------------------------------------------------------------------------------------------------
+import weakref
+
+_SINKS = {}
+
+
+def register_grad_sinks(params, views, arena):
+    for p_, v in zip(params, views):
+        _SINKS[p_.data_ptr()] = (weakref.ref(p_), v, arena)
+
+
+def claim_grad_sinks(ps):
+    """Arena views to write the gradients of ``ps`` into (in order), or None when any of them cannot be claimed."""
+    found = []
+    for p_ in ps:
+        e = _SINKS.get(p_.data_ptr())
+        if e is None:
+            return None
+        ref, v, arena = e
+        owner = ref()
+        if (owner is None or owner.data_ptr() != p_.data_ptr() or owner.grad is None or owner.grad.data_ptr() != v.data_ptr()
+                or v.shape != p_.shape or p_.data_ptr() in arena["written"]):
+            return None
+        found.append((v, arena))
+    for p_, (v, arena) in zip(ps, found):
+        arena["written"].add(p_.data_ptr())
+    return [v for v, _ in found]

@@ -67,13 +67,19 @@ class _TowerFn(torch.autograd.Function):
     def backward(ctx, dout):
         desc, ps, x = ctx.desc, ctx.ps, ctx.x
         dout = L.f32c(dout)
-        flat, views = _flat_grads(ps)
+        sinks = L.claim_grad_sinks(ps)                 # zero-filled arena views of the optimizer, or None
+        if sinks is not None:
+            flat, views = None, sinks
+        else:
+            flat, views = _flat_grads(ps)
         scratch = _bytes(ctx.scr_bytes)
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         ptab, gtab = L.ptr_table(ps), L.ptr_table(views)
-        L.call("eegclip_tower_backward", ctypes.byref(desc), ptab.data_ptr(), gtab.data_ptr(), L.ptr(flat), flat.numel() * 4,
-               L.ptr(x), L.ptr(dout), L.ptr(dx), L.ptr(ctx.save), L.ptr(scratch), L.stream())
+        L.call("eegclip_tower_backward", ctypes.byref(desc), ptab.data_ptr(), gtab.data_ptr(), L.ptr(flat),
+               flat.numel() * 4 if flat is not None else 0, L.ptr(x), L.ptr(dout), L.ptr(dx), L.ptr(ctx.save), L.ptr(scratch), L.stream())
         ctx.save = None
+        if sinks is not None:
+            return (dx, None, *([None] * len(ps)))
         return (dx, None, *views)
 
 
@@ -96,13 +102,19 @@ class _XfBlockFn(torch.autograd.Function):
     def backward(ctx, dout):
         desc, ps, z = ctx.desc, ctx.ps, ctx.z
         dout = L.f32c(dout)
-        flat, views = _flat_grads(ps)
+        sinks = L.claim_grad_sinks(ps)
+        if sinks is not None:
+            flat, views = None, sinks
+        else:
+            flat, views = _flat_grads(ps)
         scratch = _bytes(ctx.scr_bytes)
         dz = torch.empty_like(z)
         ptab, gtab = L.ptr_table(ps), L.ptr_table(views)
-        L.call("eegclip_xfblock_backward", ctypes.byref(desc), ptab.data_ptr(), gtab.data_ptr(), L.ptr(flat), flat.numel() * 4,
-               L.ptr(z), L.ptr(dout), L.ptr(dz), L.ptr(ctx.save), L.ptr(scratch), L.stream())
+        L.call("eegclip_xfblock_backward", ctypes.byref(desc), ptab.data_ptr(), gtab.data_ptr(), L.ptr(flat),
+               flat.numel() * 4 if flat is not None else 0, L.ptr(z), L.ptr(dout), L.ptr(dz), L.ptr(ctx.save), L.ptr(scratch), L.stream())
         ctx.save = None
+        if sinks is not None:
+            return (dz, None, *([None] * len(ps)))
         return (dz, None, *views)
 
 
@@ -119,7 +131,7 @@ class _ConvBlockFn(torch.autograd.Function):
         out = torch.empty(desc.B, desc.T, desc.Cout, dtype=torch.float32, device=x.device)
         L.call("eegclip_convblock_forward", ctypes.byref(desc), L.ptr(x), L.ptr(skip), L.ptr(w), L.ptr(b), L.ptr(gamma),
                L.ptr(beta), L.ptr(out), L.ptr(save), L.ptr(scratch), L.stream())
-        ctx.desc, ctx.save, ctx.scr_bytes, ctx.t = desc, save, scr_b.value, (x, skip, w, gamma, beta)
+        ctx.desc, ctx.save, ctx.scr_bytes, ctx.t, ctx.bias = desc, save, scr_b.value, (x, skip, w, gamma, beta), b
         return out
 
     @staticmethod
@@ -129,11 +141,17 @@ class _ConvBlockFn(torch.autograd.Function):
         dout = L.f32c(dout)
         scratch = _bytes(ctx.scr_bytes)
         dx = torch.empty_like(x)
-        dw, dg, dbe = torch.empty_like(w), torch.empty_like(gamma), torch.empty_like(beta)
-        db = torch.empty(desc.Cout, dtype=torch.float32, device=x.device)
+        sinks = L.claim_grad_sinks([w, ctx.bias, gamma, beta]) if ctx.bias is not None else None
+        if sinks is not None:
+            dw, db, dg, dbe = sinks
+        else:
+            dw, dg, dbe = torch.empty_like(w), torch.empty_like(gamma), torch.empty_like(beta)
+            db = torch.empty(desc.Cout, dtype=torch.float32, device=x.device)
         L.call("eegclip_convblock_backward", ctypes.byref(desc), L.ptr(x), L.ptr(skip), L.ptr(w), L.ptr(gamma), L.ptr(beta),
                L.ptr(dout), L.ptr(dx), L.ptr(dw), L.ptr(db), L.ptr(dg), L.ptr(dbe), L.ptr(ctx.save), L.ptr(scratch), L.stream())
         ctx.save = None
+        if sinks is not None:
+            return dx, (dx if skip is not None else None), None, None, None, None, None
         return dx, (dx if skip is not None else None), None, dw, db, dg, dbe
 
 
@@ -156,6 +174,7 @@ class _LinearFn(torch.autograd.Function):
         L.call("eegclip_linear_forward", L.ptr(x), L.ptr(w2), L.ptr(b), L.ptr(out), M, N, K, L.default_math(), L.ptr(scratch),
                L.stream())
         ctx.t, ctx.wshape, ctx.has_b, ctx.math = (x, w2), w.shape, b is not None, L.default_math()
+        ctx.w_orig, ctx.b_orig = L.f32c(w), b
         return out
 
     @staticmethod
@@ -164,11 +183,17 @@ class _LinearFn(torch.autograd.Function):
         dout = L.f32c(dout)
         M, K, N = x.numel() // x.shape[-1], x.shape[-1], w2.shape[0]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dw = torch.empty_like(w2)
-        db = torch.empty(N, dtype=torch.float32, device=x.device) if ctx.has_b else None
+        sinks = L.claim_grad_sinks([ctx.w_orig, ctx.b_orig]) if ctx.has_b else None
+        if sinks is not None:
+            dw, db = sinks[0].view(N, K), sinks[1]
+        else:
+            dw = torch.empty_like(w2)
+            db = torch.empty(N, dtype=torch.float32, device=x.device) if ctx.has_b else None
         scratch = _LinearFn._scratch(M, N, K)
         L.call("eegclip_linear_backward", L.ptr(x), L.ptr(w2), L.ptr(dout), L.ptr(dx), L.ptr(dw), L.ptr(db), M, N, K,
                ctx.math, L.ptr(scratch), L.stream())
+        if sinks is not None:
+            return dx, None, None
         return dx, dw.view(ctx.wshape), db
 
 
@@ -196,13 +221,16 @@ class _BiLSTMFn(torch.autograd.Function):
     def backward(ctx, dout):
         desc, ps, x = ctx.desc, ctx.ps, ctx.x
         dout = L.f32c(dout)
-        grads = [torch.empty_like(p) for p in ps]
+        sinks = L.claim_grad_sinks(ps)
+        grads = sinks if sinks is not None else [torch.empty_like(p) for p in ps]
         scratch = _bytes(ctx.scr_bytes)
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         ptab, gtab = L.ptr_table(ps), L.ptr_table(grads)
         L.call("eegclip_bilstm_backward", ctypes.byref(desc), ptab.data_ptr(), gtab.data_ptr(), L.ptr(x), L.ptr(dout), L.ptr(dx),
                L.ptr(ctx.save), L.ptr(scratch), L.stream())
         ctx.save = None
+        if sinks is not None:
+            return (dx, None, *([None] * len(ps)))
         return (dx, None, *grads)
 
 

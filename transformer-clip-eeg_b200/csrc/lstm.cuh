@@ -16,6 +16,16 @@ namespace lstm {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
+// packed fp32 FMA (sm_100 FFMA2): two independent fp32 FMAs per issue slot -- the recurrences are issue-bound on FFMA
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+
 // ------------------------------------------------------------------------------------------------
 // H = 128 forward.  grid (ceil(B/4), 2 directions), block 512.
 //   G   : (B*T, GS) rows; direction d owns columns [d*512, d*512+512) = [gate][unit]; in: x-projection + biases, out: gates
@@ -57,15 +67,17 @@ __global__ void __launch_bounds__(512, 1) lstm128_fwd_kernel(const float* __rest
       for (int g = 0; g < 4; ++g) gx[g] = G[row * GS + dir * LG + g * LH + u];
     }
     // ---- recurrent product: acc[q] = sum_k W[r][k] h[q][k] ----
-    float acc[LNB] = {0.f, 0.f, 0.f, 0.f};
+    float2 acc2[LNB];                                    // (even-k, odd-k) partial sums: one FFMA2 per two products
+#pragma unroll
+    for (int q = 0; q < LNB; ++q) acc2[q] = make_float2(0.f, 0.f);
     const float4* h4 = reinterpret_cast<const float4*>(hs);
 #pragma unroll
     for (int k4 = 0; k4 < 16; ++k4) {
 #pragma unroll
       for (int q = 0; q < LNB; ++q) {
         const float4 h = h4[q * 32 + k4];
-        acc[q] = fmaf(w[4 * k4], h.x, acc[q]); acc[q] = fmaf(w[4 * k4 + 1], h.y, acc[q]);
-        acc[q] = fmaf(w[4 * k4 + 2], h.z, acc[q]); acc[q] = fmaf(w[4 * k4 + 3], h.w, acc[q]);
+        acc2[q] = ffma2(make_float2(w[4 * k4], w[4 * k4 + 1]), make_float2(h.x, h.y), acc2[q]);
+        acc2[q] = ffma2(make_float2(w[4 * k4 + 2], w[4 * k4 + 3]), make_float2(h.z, h.w), acc2[q]);
       }
     }
 #pragma unroll 4
@@ -74,10 +86,13 @@ __global__ void __launch_bounds__(512, 1) lstm128_fwd_kernel(const float* __rest
 #pragma unroll
       for (int q = 0; q < LNB; ++q) {
         const float4 h = h4[q * 32 + 16 + k4];
-        acc[q] = fmaf(wv.x, h.x, acc[q]); acc[q] = fmaf(wv.y, h.y, acc[q]);
-        acc[q] = fmaf(wv.z, h.z, acc[q]); acc[q] = fmaf(wv.w, h.w, acc[q]);
+        acc2[q] = ffma2(make_float2(wv.x, wv.y), make_float2(h.x, h.y), acc2[q]);
+        acc2[q] = ffma2(make_float2(wv.z, wv.w), make_float2(h.z, h.w), acc2[q]);
       }
     }
+    float acc[LNB];
+#pragma unroll
+    for (int q = 0; q < LNB; ++q) acc[q] = acc2[q].x + acc2[q].y;
 #pragma unroll
     for (int q = 0; q < LNB; ++q) pre[q * LG + r] = acc[q];
     __syncthreads();
@@ -156,15 +171,17 @@ __global__ void __launch_bounds__(512, 1) lstm128_bwd_kernel(const float* __rest
     for (int g = 0; g < 4; ++g) das[s * LG + g * LH + u] = da[g];
     __syncthreads();
     // ---- transposed recurrent product ----
-    float acc[LNB] = {0.f, 0.f, 0.f, 0.f};
+    float2 acc2[LNB];
+#pragma unroll
+    for (int ss = 0; ss < LNB; ++ss) acc2[ss] = make_float2(0.f, 0.f);
     const float4* d4 = reinterpret_cast<const float4*>(das);
 #pragma unroll
     for (int j4 = 0; j4 < 16; ++j4) {
 #pragma unroll
       for (int ss = 0; ss < LNB; ++ss) {
         const float4 d = d4[ss * 128 + q * 32 + j4];
-        acc[ss] = fmaf(w[4 * j4], d.x, acc[ss]); acc[ss] = fmaf(w[4 * j4 + 1], d.y, acc[ss]);
-        acc[ss] = fmaf(w[4 * j4 + 2], d.z, acc[ss]); acc[ss] = fmaf(w[4 * j4 + 3], d.w, acc[ss]);
+        acc2[ss] = ffma2(make_float2(w[4 * j4], w[4 * j4 + 1]), make_float2(d.x, d.y), acc2[ss]);
+        acc2[ss] = ffma2(make_float2(w[4 * j4 + 2], w[4 * j4 + 3]), make_float2(d.z, d.w), acc2[ss]);
       }
     }
 #pragma unroll 4
@@ -173,10 +190,13 @@ __global__ void __launch_bounds__(512, 1) lstm128_bwd_kernel(const float* __rest
 #pragma unroll
       for (int ss = 0; ss < LNB; ++ss) {
         const float4 d = d4[ss * 128 + q * 32 + 16 + j4];
-        acc[ss] = fmaf(wv.x, d.x, acc[ss]); acc[ss] = fmaf(wv.y, d.y, acc[ss]);
-        acc[ss] = fmaf(wv.z, d.z, acc[ss]); acc[ss] = fmaf(wv.w, d.w, acc[ss]);
+        acc2[ss] = ffma2(make_float2(wv.x, wv.y), make_float2(d.x, d.y), acc2[ss]);
+        acc2[ss] = ffma2(make_float2(wv.z, wv.w), make_float2(d.z, d.w), acc2[ss]);
       }
     }
+    float acc[LNB];
+#pragma unroll
+    for (int ss = 0; ss < LNB; ++ss) acc[ss] = acc2[ss].x + acc2[ss].y;
 #pragma unroll
     for (int ss = 0; ss < LNB; ++ss) part[(q * LNB + ss) * LH + k] = acc[ss];
     __syncthreads();

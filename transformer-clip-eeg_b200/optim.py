@@ -45,7 +45,8 @@ class AdamW(torch.optim.Optimizer):
             rows.append([p.data_ptr(), view.data_ptr(), flat_m.data_ptr() + 4 * off, flat_v.data_ptr() + 4 * off, p.numel()])
         table = torch.tensor(rows, dtype=torch.int64).to(dev)
         a = dict(key=key, ps=ps, flat_g=flat_g, flat_m=flat_m, flat_v=flat_v, table=table, max_numel=max(p.numel() for p in ps),
-                 step=0)
+                 step=0, written=set(p.data_ptr() for p in ps))   # nothing may be written directly before the first zero_grad
+        L.register_grad_sinks(ps, [p.grad for p in ps], a)
         self._arena[gi] = a
         return a
 
@@ -55,7 +56,9 @@ class AdamW(torch.optim.Optimizer):
     def zero_grad(self, set_to_none=True):
         # gradients stay views of the arena (stable pointers); one memset per group
         for gi, g in enumerate(self.param_groups):
-            self._group_arena(gi, g)["flat_g"].zero_()
+            a = self._group_arena(gi, g)
+            a["flat_g"].zero_()
+            a["written"].clear()                       # the package's backward kernels may now write each view once, directly
 
     @torch.no_grad()
     def step(self, closure=None):
