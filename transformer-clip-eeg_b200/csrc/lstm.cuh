@@ -30,34 +30,46 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 // H = 128 forward.  grid (ceil(B/4), 2 directions), block 512.
 //   G   : (B*T, GS) rows; direction d owns columns [d*512, d*512+512) = [gate][unit]; in: x-projection + biases, out: gates
 //   out : (B*T, 256)  h_t          Cs : (B*T, 256) c_t          Hp : (B*T, 256) h_{t-1} (the state the step started from)
+// Recurrent product pre[q][r] = sum_k W[r][k] h[q][k] (512 rows x 4 sequences x K = 128), register-tiled: thread
+// (rg = tid >> 2, kq = tid & 3) owns the 4 rows 4rg..4rg+3 over the k-quarter [32kq, 32kq+32): every h value it loads
+// feeds 4 rows and every weight 4 sequences (48 shared-memory loads per 256 packed FMAs instead of 144), the four
+// k-quarters are summed with two shuffles.  Weights: rows 0,1 of the tile in registers, rows 2,3 in shared memory.
 // ------------------------------------------------------------------------------------------------
 constexpr int LH = 128, LG = 512, LNB = 4;
-constexpr int L128_SMEM = (16 * LG * 4 + LNB * LH + LNB * LG) * 4;   // W half + h + pre-activations
+constexpr int LHS = LNB * 4 * 9 * 4;                                  // h / da staging: [seq][k-quarter][8 float4 + 1 pad]
+constexpr int L128_SMEM = (16 * LG * 4 + LHS + LNB * LG) * 4;         // W half + h + pre-activations
 
 __global__ void __launch_bounds__(512, 1) lstm128_fwd_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
                                                             float* __restrict__ G, int GS, float* __restrict__ out,
                                                             float* __restrict__ Cs, float* __restrict__ Hp, int B, int T) {
   extern __shared__ __align__(16) float sml[];
-  float4* Wsm = reinterpret_cast<float4*>(sml);          // [k4 = 16][row 512] : W[row][64 + 4*k4 .. +3]
-  float* hs = sml + 16 * LG * 4;                         // [seq 4][128]
-  float* pre = hs + LNB * LH;                            // [seq 4][512]
+  float4* Wsm = reinterpret_cast<float4*>(sml);          // [j = 16][tid 512] : rows 2,3 of the thread's tile
+  float* hs = sml + 16 * LG * 4;                         // h of the 4 sequences, padded (see hidx)
+  float* pre = hs + LHS;                                 // [seq 4][512]
   const int dir = blockIdx.y, b0 = blockIdx.x * LNB;
-  const int r = threadIdx.x;
-  const float* W = (dir ? w_hh_r : w_hh_f) + (long)r * LH;
-  float w[64];
+  const int tid = threadIdx.x;
+  const int rg = tid >> 2, kq = tid & 3;
+  const float* W = (dir ? w_hh_r : w_hh_f) + (long)(rg * 4) * LH + kq * 32;   // tile origin: row 4rg, column 32kq
+  float w[64];                                           // rows 0,1: w[row*32 + k]
 #pragma unroll
-  for (int k4 = 0; k4 < 16; ++k4) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(W) + k4);
-    w[4 * k4] = v.x; w[4 * k4 + 1] = v.y; w[4 * k4 + 2] = v.z; w[4 * k4 + 3] = v.w;
-    Wsm[k4 * LG + r] = __ldg(reinterpret_cast<const float4*>(W) + 16 + k4);
-  }
-  hs[r] = 0.f;                                            // 512 = 4 x 128 zeros
+  for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(W + (long)rr * LH) + i);
+      w[rr * 32 + 4 * i] = v.x; w[rr * 32 + 4 * i + 1] = v.y; w[rr * 32 + 4 * i + 2] = v.z; w[rr * 32 + 4 * i + 3] = v.w;
+    }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) Wsm[j * LG + tid] = __ldg(reinterpret_cast<const float4*>(W + (long)(2 + (j >> 3)) * LH) + (j & 7));
+  // h[q][k] lives at hs[((q*4 + k/32)*9 + (k%32)/4)*4 + k%4]: the four k-quarters start 16 B apart modulo 128 B
+  auto hidx = [](int q, int k) { return ((q * 4 + (k >> 5)) * 9 + ((k & 31) >> 2)) * 4 + (k & 3); };
   // gate-combine role: thread = (unit u, sequence s)
-  const int u = r & 127, s = r >> 7;
+  const int u = tid & 127, s = tid >> 7;
+  hs[hidx(s, u)] = 0.f;
   const int b = b0 + s;
   const bool live = b < B;
   float c = 0.f;
   __syncthreads();
+  const float4* h4 = reinterpret_cast<const float4*>(hs);
   for (int step = 0; step < T; ++step) {
     const int t = dir ? T - 1 - step : step;
     const long row = (long)b * T + t;
@@ -66,44 +78,55 @@ __global__ void __launch_bounds__(512, 1) lstm128_fwd_kernel(const float* __rest
 #pragma unroll
       for (int g = 0; g < 4; ++g) gx[g] = G[row * GS + dir * LG + g * LH + u];
     }
-    // ---- recurrent product: acc[q] = sum_k W[r][k] h[q][k] ----
-    float2 acc2[LNB];                                    // (even-k, odd-k) partial sums: one FFMA2 per two products
+    // ---- recurrent product over this thread's k-quarter ----
+    float2 acc[4][LNB];                                  // [row][seq], (even-k, odd-k) partial sums
 #pragma unroll
-    for (int q = 0; q < LNB; ++q) acc2[q] = make_float2(0.f, 0.f);
-    const float4* h4 = reinterpret_cast<const float4*>(hs);
+    for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-    for (int k4 = 0; k4 < 16; ++k4) {
+      for (int q = 0; q < LNB; ++q) acc[rr][q] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int q = 0; q < LNB; ++q) {
-        const float4 h = h4[q * 32 + k4];
-        acc2[q] = ffma2(make_float2(w[4 * k4], w[4 * k4 + 1]), make_float2(h.x, h.y), acc2[q]);
-        acc2[q] = ffma2(make_float2(w[4 * k4 + 2], w[4 * k4 + 3]), make_float2(h.z, h.w), acc2[q]);
-      }
-    }
-#pragma unroll 4
-    for (int k4 = 0; k4 < 16; ++k4) {
-      const float4 wv = Wsm[k4 * LG + r];
+    for (int i = 0; i < 8; ++i) {
+      float4 h[LNB];
+#pragma unroll
+      for (int q = 0; q < LNB; ++q) h[q] = h4[(q * 4 + kq) * 9 + i];
+      const float4 w2 = Wsm[i * LG + tid], w3 = Wsm[(8 + i) * LG + tid];
 #pragma unroll
       for (int q = 0; q < LNB; ++q) {
-        const float4 h = h4[q * 32 + 16 + k4];
-        acc2[q] = ffma2(make_float2(wv.x, wv.y), make_float2(h.x, h.y), acc2[q]);
-        acc2[q] = ffma2(make_float2(wv.z, wv.w), make_float2(h.z, h.w), acc2[q]);
+        const float2 hlo = make_float2(h[q].x, h[q].y), hhi = make_float2(h[q].z, h[q].w);
+        acc[0][q] = ffma2(make_float2(w[4 * i], w[4 * i + 1]), hlo, acc[0][q]);
+        acc[0][q] = ffma2(make_float2(w[4 * i + 2], w[4 * i + 3]), hhi, acc[0][q]);
+        acc[1][q] = ffma2(make_float2(w[32 + 4 * i], w[32 + 4 * i + 1]), hlo, acc[1][q]);
+        acc[1][q] = ffma2(make_float2(w[32 + 4 * i + 2], w[32 + 4 * i + 3]), hhi, acc[1][q]);
+        acc[2][q] = ffma2(make_float2(w2.x, w2.y), hlo, acc[2][q]);
+        acc[2][q] = ffma2(make_float2(w2.z, w2.w), hhi, acc[2][q]);
+        acc[3][q] = ffma2(make_float2(w3.x, w3.y), hlo, acc[3][q]);
+        acc[3][q] = ffma2(make_float2(w3.z, w3.w), hhi, acc[3][q]);
       }
     }
-    float acc[LNB];
+    // sum the four k-quarters (lanes kq = 0..3 of a quad); lane kq then stores sequence q = kq
+    float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int q = 0; q < LNB; ++q) acc[q] = acc2[q].x + acc2[q].y;
+    for (int q = 0; q < LNB; ++q) {
+      float v[4];
 #pragma unroll
-    for (int q = 0; q < LNB; ++q) pre[q * LG + r] = acc[q];
+      for (int rr = 0; rr < 4; ++rr) {
+        float x = acc[rr][q].x + acc[rr][q].y;
+        x += __shfl_xor_sync(0xffffffffu, x, 1);
+        x += __shfl_xor_sync(0xffffffffu, x, 2);
+        v[rr] = x;
+      }
+      if (q == kq) mine = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    *reinterpret_cast<float4*>(pre + kq * LG + rg * 4) = mine;
     __syncthreads();
     // ---- gates, state update (thread = (u, s)) ----
-    const float hprev = hs[s * LH + u];
+    const float hprev = hs[hidx(s, u)];
     const float ai = pre[s * LG + u] + gx[0], af = pre[s * LG + LH + u] + gx[1];
     const float ag = pre[s * LG + 2 * LH + u] + gx[2], ao = pre[s * LG + 3 * LH + u] + gx[3];
     const float gi = sigmoidf_(ai), gf = sigmoidf_(af), gg = tanhf(ag), go = sigmoidf_(ao);
     c = gf * c + gi * gg;
     const float h = go * tanhf(c);
-    hs[s * LH + u] = h;                                   // only this thread read hs[s][u] since the product phase ended
+    hs[hidx(s, u)] = h;                                   // only this thread read hs[s][u] since the product phase ended
     if (live) {
       float* gp = G + row * GS + dir * LG + u;
       gp[0] = gi; gp[LH] = gf; gp[2 * LH] = gg; gp[3 * LH] = go;
@@ -118,35 +141,38 @@ __global__ void __launch_bounds__(512, 1) lstm128_fwd_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------
 // H = 128 backward recurrence.  Same grid.  Walks the time steps in the opposite order of the forward, turns the saved
 // gates into pre-activation gradients da (in place in G) and carries dh, dc.
-//   dh_{prev}[k] = sum_r W_hh[r][k] da[r] : thread (k = tid & 127, q = tid >> 7) sums rows [128q, 128q+128), 4 partials reduced in smem
+//   dh_prev[q][k] = sum_r W[r][k] da[q][r]  (128 x 4 outputs, contraction 512): thread (kg = tid >> 4, rp = tid & 15) owns
+//   the 4 outputs k = 4kg..4kg+3 over the row part [32rp, 32rp+32); the 16 parts are summed with four shuffles.
 // ------------------------------------------------------------------------------------------------
-constexpr int L128B_SMEM = (16 * LG * 4 + LNB * LG + 4 * LNB * LH + LNB * LH) * 4;
+constexpr int LDS_ = LNB * 16 * 9 * 4;                                 // da staging: [seq][row part 16][8 float4 + 1 pad]
+constexpr int L128B_SMEM = (16 * LG * 4 + LDS_ + LNB * LH) * 4;
 
 __global__ void __launch_bounds__(512, 1) lstm128_bwd_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
                                                             float* __restrict__ G, int GS, const float* __restrict__ dout,
                                                             const float* __restrict__ Cs, int B, int T) {
   extern __shared__ __align__(16) float sml[];
-  float4* Wsm = reinterpret_cast<float4*>(sml);          // [j4 = 16][tid 512] : W[128q + 64 + 4*j4 .. +3][k]
-  float* das = sml + 16 * LG * 4;                        // [seq 4][512]
-  float* part = das + LNB * LG;                          // [q 4][seq 4][128]
-  float* dhs = part + 4 * LNB * LH;                      // [seq 4][128]
+  float4* Wsm = reinterpret_cast<float4*>(sml);          // [j = 16][tid 512] : W[32rp + 16 + j][4kg .. 4kg+3]
+  float* das = sml + 16 * LG * 4;                        // da of the 4 sequences, padded (see didx)
+  float* dhs = das + LDS_;                               // [seq 4][128]
   const int dir = blockIdx.y, b0 = blockIdx.x * LNB;
   const int tid = threadIdx.x;
-  const int k = tid & 127, q = tid >> 7;
-  const float* W = (dir ? w_hh_r : w_hh_f) + (long)(q * LH) * LH + k;   // W[128q + j][k] = W[j * 128]
-  float w[64];
+  const int kg = tid >> 4, rp = tid & 15;
+  const float* W = (dir ? w_hh_r : w_hh_f) + (long)(rp * 32) * LH + kg * 4;   // W[32rp + j][4kg ..]
+  float4 w[16];                                          // rows j = 0..15 of the part
 #pragma unroll
-  for (int j = 0; j < 64; ++j) w[j] = __ldg(W + (long)j * LH);
-#pragma unroll
-  for (int j4 = 0; j4 < 16; ++j4)
-    Wsm[j4 * LG + tid] = make_float4(__ldg(W + (long)(64 + 4 * j4) * LH), __ldg(W + (long)(65 + 4 * j4) * LH),
-                                     __ldg(W + (long)(66 + 4 * j4) * LH), __ldg(W + (long)(67 + 4 * j4) * LH));
+  for (int j = 0; j < 16; ++j) {
+    w[j] = __ldg(reinterpret_cast<const float4*>(W + (long)j * LH));
+    Wsm[j * LG + tid] = __ldg(reinterpret_cast<const float4*>(W + (long)(16 + j) * LH));
+  }
+  // da[q][r] lives at das[((q*16 + r/32)*9 + (r%32)/4)*4 + r%4]
+  auto didx = [](int q, int r) { return ((q * 16 + (r >> 5)) * 9 + ((r & 31) >> 2)) * 4 + (r & 3); };
+  const int u = tid & 127, s = tid >> 7;                 // gate role: (unit, sequence)
   dhs[tid] = 0.f;
-  const int u = k, s = q;                                // gate role: (unit, sequence)
   const int b = b0 + s;
   const bool live = b < B;
   float dc = 0.f;
   __syncthreads();
+  const float4* d4 = reinterpret_cast<const float4*>(das);
   for (int step = 0; step < T; ++step) {
     const int t = dir ? step : T - 1 - step;             // reverse of the forward order
     const int tp = dir ? t + 1 : t - 1;                  // time index of the forward's previous step
@@ -168,42 +194,47 @@ __global__ void __launch_bounds__(512, 1) lstm128_bwd_kernel(const float* __rest
       gp[0] = da[0]; gp[LH] = da[1]; gp[2 * LH] = da[2]; gp[3 * LH] = da[3];
     }
 #pragma unroll
-    for (int g = 0; g < 4; ++g) das[s * LG + g * LH + u] = da[g];
+    for (int g = 0; g < 4; ++g) das[didx(s, g * LH + u)] = da[g];
     __syncthreads();
-    // ---- transposed recurrent product ----
-    float2 acc2[LNB];
+    // ---- transposed recurrent product over this thread's row part ----
+    float2 acc[2][LNB];                                  // [k pair][seq]: (k0,k1) and (k2,k3)
 #pragma unroll
-    for (int ss = 0; ss < LNB; ++ss) acc2[ss] = make_float2(0.f, 0.f);
-    const float4* d4 = reinterpret_cast<const float4*>(das);
+    for (int q = 0; q < LNB; ++q) { acc[0][q] = make_float2(0.f, 0.f); acc[1][q] = make_float2(0.f, 0.f); }
 #pragma unroll
-    for (int j4 = 0; j4 < 16; ++j4) {
+    for (int i = 0; i < 8; ++i) {
+      float4 d[LNB];
 #pragma unroll
-      for (int ss = 0; ss < LNB; ++ss) {
-        const float4 d = d4[ss * 128 + q * 32 + j4];
-        acc2[ss] = ffma2(make_float2(w[4 * j4], w[4 * j4 + 1]), make_float2(d.x, d.y), acc2[ss]);
-        acc2[ss] = ffma2(make_float2(w[4 * j4 + 2], w[4 * j4 + 3]), make_float2(d.z, d.w), acc2[ss]);
+      for (int q = 0; q < LNB; ++q) d[q] = d4[(q * 16 + rp) * 9 + i];
+      // rows 4i..4i+3 of the part: registers for i < 4, shared memory for i >= 4
+      float4 wr[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) wr[e] = i < 4 ? w[4 * i + e] : Wsm[(4 * (i - 4) + e) * LG + tid];
+#pragma unroll
+      for (int q = 0; q < LNB; ++q) {
+        const float dd[4] = {d[q].x, d[q].y, d[q].z, d[q].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 dv = make_float2(dd[e], dd[e]);
+          acc[0][q] = ffma2(make_float2(wr[e].x, wr[e].y), dv, acc[0][q]);
+          acc[1][q] = ffma2(make_float2(wr[e].z, wr[e].w), dv, acc[1][q]);
+        }
       }
     }
-#pragma unroll 4
-    for (int j4 = 0; j4 < 16; ++j4) {
-      const float4 wv = Wsm[j4 * LG + tid];
+    // sum the 16 row parts (lanes rp = 0..15 of a half-warp); lane rp < 4 then stores sequence q = rp
+    float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int ss = 0; ss < LNB; ++ss) {
-        const float4 d = d4[ss * 128 + q * 32 + 16 + j4];
-        acc2[ss] = ffma2(make_float2(wv.x, wv.y), make_float2(d.x, d.y), acc2[ss]);
-        acc2[ss] = ffma2(make_float2(wv.z, wv.w), make_float2(d.z, d.w), acc2[ss]);
+    for (int q = 0; q < LNB; ++q) {
+      float v[4] = {acc[0][q].x, acc[0][q].y, acc[1][q].x, acc[1][q].y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
       }
+      if (q == rp) mine = make_float4(v[0], v[1], v[2], v[3]);
     }
-    float acc[LNB];
-#pragma unroll
-    for (int ss = 0; ss < LNB; ++ss) acc[ss] = acc2[ss].x + acc2[ss].y;
-#pragma unroll
-    for (int ss = 0; ss < LNB; ++ss) part[(q * LNB + ss) * LH + k] = acc[ss];
-    __syncthreads();
-    // thread (u, s) sums the 4 row-quarter partials of its (sequence, unit)
-    // (dhs[s][u] is private to this thread; the next write of `part` comes after the next barrier)
-    dhs[s * LH + u] = part[(0 * LNB + s) * LH + u] + part[(1 * LNB + s) * LH + u] + part[(2 * LNB + s) * LH + u] +
-                      part[(3 * LNB + s) * LH + u];
+    // all reads of dhs of this step happened before the barrier above
+    if (rp < LNB) *reinterpret_cast<float4*>(dhs + rp * LH + kg * 4) = mine;
+    __syncthreads();                                      // dhs visible to its (unit, sequence) readers; das free for the next step
   }
 }
 
