@@ -32,7 +32,7 @@ _lib.call("eegclip_debug_buffer", None)
 d = dbg.cpu().view(3, 256)
 t0 = min(int(d[w_, 1]) for w_ in range(3) if int(d[w_, 255]) > 0)
 names = {0: "prod:start", 1: "prod:slot-free", 2: "prod:filled", 10: "mma:weights", 11: "mma:acc-free", 12: "mma:stage-full", 20: "epi:start",
-         21: "epi:acc-full", 22: "epi:done"}
+         21: "epi:acc-full", 22: "epi:done", 23: "epi:  tmem loaded", 24: "epi:  staged", 25: "epi:  stored"}
 ev = []
 for w_ in range(3):
     for i in range(int(d[w_, 255])):

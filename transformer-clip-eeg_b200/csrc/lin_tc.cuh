@@ -38,8 +38,11 @@ constexpr int A_PLANE = (KC / 8) * A_CS; // 16 KB
 constexpr int A_STAGE = 2 * A_PLANE;     // hi + lo
 constexpr int EPI_LD = 36;               // floats per staged row (32 + pad: 16 B aligned, conflict-free 128-bit access)
 constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
-constexpr int NEPI = 8, NPROD = 4;           // epilogue / producer warps (13 warps: <= 4 per scheduler -> 128 registers each)
-constexpr int NTHREADS = (NEPI + NPROD + 1) * 32;
+// 13 warps (<= 4 per scheduler -> 128 registers each): NE epilogue warps + (12 - NE) producer warps + 1 MMA warp.
+//   NE = 8: heavy epilogues (GELU, wide outputs).   NE = 4: deep contractions / narrow outputs -- 8 producer warps, each with
+//   the loads of the NEXT chunk in flight while it converts the current one (the K >= 192 shapes are load-latency bound).
+constexpr int NWARPS = 13;
+constexpr int NTHREADS = NWARPS * 32;
 
 enum : int { PRO_NONE = 0, PRO_DROP = 1, PRO_GELU_DROP = 2 };
 // Compile-time feature masks of the token-GEMM epilogue.  The kernels are instantiated per (prologue, epilogue mask) actually
@@ -128,31 +131,41 @@ inline size_t packed_bytes(int N, int K) { return (size_t)N * K * 4; }
 //   bytes to a request (full lines) and the eight 16-byte smem stores of a quarter-warp fill one 128-byte wavefront.
 // Every thread keeps a FIXED chunk ((pw & 1) * 4 + (lane >> 3)), so column sums can live in registers.
 // ------------------------------------------------------------------------------------------------
-template <int ROWS, int NTERMS, int NPW /* producer warps */, int PRO /* -1: runtime `pro` */>
-__device__ __forceinline__ void stage_chunk(const float* __restrict__ src, long ld, long row0, long rows_total, int col0, int ncols_total,
-                                            uint8_t* dst, uint32_t CS, uint32_t PS, int pw, int lane, int pro, const Drop& drop,
-                                            float* colsum /* nullptr or 8 running sums */, int policy) {
-  constexpr int NBLK = (ROWS / 8) * 2;      // (row block, chunk half) combos
-  constexpr int ITERS = NBLK / NPW;
-  static_assert(NBLK % NPW == 0, "producer warps must divide the chunk");
+template <int ROWS, int NPW>
+struct ChunkRegs { float4 x0[(ROWS / 8) * 2 / NPW], x1[(ROWS / 8) * 2 / NPW]; };
+
+// issue the global loads of this thread's share of a ROWS x 64 chunk
+template <int ROWS, int NPW>
+__device__ __forceinline__ void load_chunk(ChunkRegs<ROWS, NPW>& R, const float* __restrict__ src, long ld, long row0, long rows_total,
+                                           int col0, int pw, int lane, int policy) {
+  constexpr int ITERS = (ROWS / 8) * 2 / NPW;
+  static_assert(((ROWS / 8) * 2) % NPW == 0, "producer warps must divide the chunk");
   const int ch = (pw & 1) * 4 + (lane >> 3);
-  float4 x0[ITERS], x1[ITERS];
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     const int rb = it * (NPW / 2) + (pw >> 1);
     const long r = row0 + rb * 8 + (lane & 7);
     if (r < rows_total) {
       const float4* p = reinterpret_cast<const float4*>(src + r * ld + col0 + ch * 8);
-      x0[it] = ld_act(p, policy); x1[it] = ld_act(p + 1, policy);
+      R.x0[it] = ld_act(p, policy); R.x1[it] = ld_act(p + 1, policy);
     } else {
-      x0[it] = make_float4(0.f, 0.f, 0.f, 0.f); x1[it] = x0[it];
+      R.x0[it] = make_float4(0.f, 0.f, 0.f, 0.f); R.x1[it] = R.x0[it];
     }
   }
+}
+
+// prologue + bf16 hi/lo split + shared-memory store of the loaded share
+template <int ROWS, int NTERMS, int NPW, int PRO /* -1: runtime `pro` */>
+__device__ __forceinline__ void convert_chunk(const ChunkRegs<ROWS, NPW>& R, long row0, long rows_total, int col0, int ncols_total,
+                                              uint8_t* dst, uint32_t CS, uint32_t PS, int pw, int lane, int pro, const Drop& drop,
+                                              float* colsum /* nullptr or 8 running sums */) {
+  constexpr int ITERS = (ROWS / 8) * 2 / NPW;
+  const int ch = (pw & 1) * 4 + (lane >> 3);
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     const int rb = it * (NPW / 2) + (pw >> 1);
     const int rl = rb * 8 + (lane & 7);
-    float v[8] = {x0[it].x, x0[it].y, x0[it].z, x0[it].w, x1[it].x, x1[it].y, x1[it].z, x1[it].w};
+    float v[8] = {R.x0[it].x, R.x0[it].y, R.x0[it].z, R.x0[it].w, R.x1[it].x, R.x1[it].y, R.x1[it].z, R.x1[it].w};
     const int prog = PRO < 0 ? pro : PRO;
     if (prog != PRO_NONE) {
       const long r = row0 + rl;
@@ -176,6 +189,15 @@ __device__ __forceinline__ void stage_chunk(const float* __restrict__ src, long 
   }
 }
 
+template <int ROWS, int NTERMS, int NPW /* producer warps */, int PRO /* -1: runtime `pro` */>
+__device__ __forceinline__ void stage_chunk(const float* __restrict__ src, long ld, long row0, long rows_total, int col0, int ncols_total,
+                                            uint8_t* dst, uint32_t CS, uint32_t PS, int pw, int lane, int pro, const Drop& drop,
+                                            float* colsum /* nullptr or 8 running sums */, int policy) {
+  ChunkRegs<ROWS, NPW> R;
+  load_chunk<ROWS, NPW>(R, src, ld, row0, rows_total, col0, pw, lane, policy);
+  convert_chunk<ROWS, NTERMS, NPW, PRO>(R, row0, rows_total, col0, ncols_total, dst, CS, PS, pw, lane, pro, drop, colsum);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Forward / data-gradient GEMM
 // ------------------------------------------------------------------------------------------------
@@ -197,12 +219,13 @@ struct LinTcArgs {
   unsigned long long* dbg;        // development timeline buffer (nullptr in production)
 };
 
-inline uint32_t lin_smem_bytes(int N, int K, int nstage = NSTAGE) {
-  return (uint32_t)packed_bytes(N, K) + nstage * A_STAGE + NEPI * EPI_WARP_FLOATS * 4 + 256;
+inline uint32_t lin_smem_bytes(int N, int K, int nstage = NSTAGE, int nepi = 8) {
+  return (uint32_t)packed_bytes(N, K) + nstage * A_STAGE + nepi * EPI_WARP_FLOATS * 4 + 256 + 1024;   // + barriers + bias[256]
 }
 
-template <int NTERMS, int PRO, int EF>
+template <int NTERMS, int PRO, int EF, int NEPI>
 __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) {
+  constexpr int NPROD = NWARPS - 1 - NEPI;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = a.N, K = a.K;
@@ -218,6 +241,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
   uint64_t* accempty = accfull + 2;       // [2] epilogue -> MMA         (NEPI*32 arrivals)
   uint64_t* wfull = accempty + 2;         // weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  float* sBias = reinterpret_cast<float*>(bars) + 64;      // 256 B past the barrier block: bias[N] (zeros when absent)
   constexpr int MMA_WARP = NEPI + NPROD;
 
   uint32_t ncols = 32;
@@ -229,6 +253,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
     tc::mbar_fence_init();
   }
   if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, ncols);
+  for (int n = tid; n < N; n += NTHREADS) sBias[n] = a.bias ? __ldg(a.bias + n) : 0.f;
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -243,16 +268,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
     unsigned long long* dbg = (blockIdx.x == 0 && pw == 0 && lane == 0) ? a.dbg : nullptr;
     int dn = 0;
     dbg_mark(dbg, 0, dn, 0);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      for (int kc = 0; kc < nchunk; ++kc) {
-        tc::mbar_wait(&empty[s], ph ^ 1);
-        dbg_mark(dbg, 0, dn, 1);
-        stage_chunk<BM, NTERMS, NPROD, PRO>(a.A, a.lda, (long)tile * BM, a.M, kc * KC, K, sA + s * A_STAGE, A_CS, A_PLANE, pw, lane, a.pro,
-                                       a.pro_drop, nullptr, a.policy);
-        tc::fence_async_smem();
-        tc::mbar_arrive(&full[s]);
-        dbg_mark(dbg, 0, dn, 2);
-        if (++s == nstage) { s = 0; ph ^= 1; }
+    if (NPROD >= 8) {
+      // software-pipelined: chunk c+1's loads are issued before chunk c is converted (2 x 8 float4 per thread in flight)
+      const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const int total = my_tiles * nchunk;
+      ChunkRegs<BM, NPROD> R[2];
+      if (total > 0) load_chunk<BM, NPROD>(R[0], a.A, a.lda, (long)blockIdx.x * BM, a.M, 0, pw, lane, a.policy);
+      int tile = blockIdx.x, kc = 0;
+      for (int c = 0; c < total; c += 2) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (c + u < total) {
+            int ntile = tile, nkc = kc + 1;
+            if (nkc == nchunk) { nkc = 0; ntile += gridDim.x; }
+            if (c + u + 1 < total) load_chunk<BM, NPROD>(R[u ^ 1], a.A, a.lda, (long)ntile * BM, a.M, nkc * KC, pw, lane, a.policy);
+            tc::mbar_wait(&empty[s], ph ^ 1);
+            dbg_mark(dbg, 0, dn, 1);
+            convert_chunk<BM, NTERMS, NPROD, PRO>(R[u], (long)tile * BM, a.M, kc * KC, K, sA + s * A_STAGE, A_CS, A_PLANE, pw, lane, a.pro,
+                                                  a.pro_drop, nullptr);
+            tc::fence_async_smem();
+            tc::mbar_arrive(&full[s]);
+            dbg_mark(dbg, 0, dn, 2);
+            if (++s == nstage) { s = 0; ph ^= 1; }
+            tile = ntile; kc = nkc;
+          }
+        }
+      }
+    } else {
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int kc = 0; kc < nchunk; ++kc) {
+          tc::mbar_wait(&empty[s], ph ^ 1);
+          dbg_mark(dbg, 0, dn, 1);
+          stage_chunk<BM, NTERMS, NPROD, PRO>(a.A, a.lda, (long)tile * BM, a.M, kc * KC, K, sA + s * A_STAGE, A_CS, A_PLANE, pw, lane, a.pro,
+                                              a.pro_drop, nullptr, a.policy);
+          tc::fence_async_smem();
+          tc::mbar_arrive(&full[s]);
+          dbg_mark(dbg, 0, dn, 2);
+          if (++s == nstage) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == MMA_WARP) {
@@ -310,7 +363,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
     const int q = warp & 3, chalf = warp >> 2;
     float* stg = sE + warp * EPI_WARP_FLOATS;
     const int cq = (lane & 7) * 4, rq = lane >> 3;      // coalesced phase: 4 columns x (4 rows per iteration)
-    const int cb0 = chalf * (N >> 1), cb1 = cb0 + (N >> 1);
+    const int ncol_w = NEPI == 8 ? (N >> 1) : N;          // columns of this warp: half of N (8 warps) or all of it (4 warps)
+    const int cb0 = chalf * ncol_w, cb1 = cb0 + ncol_w;
     uint32_t t = 0;
     unsigned long long* dbg = (blockIdx.x == 0 && warp == 0 && lane == 0) ? a.dbg : nullptr;
     int dn = 0;
@@ -324,9 +378,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
       for (int cb = cb0; cb < cb1; cb += 32) {
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)N + cb, v);
+        dbg_mark(dbg, 2, dn, 23);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
+        dbg_mark(dbg, 2, dn, 24);
         const int n = cb + cq;
         const bool f_bias = EF < 0 ? a.bias != nullptr : (EF & EF_BIAS) != 0;
         const bool f_act1 = EF < 0 ? a.act == 1 : (EF & EF_ACT1) != 0;
@@ -336,7 +392,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
         const bool f_mul = EF < 0 ? a.mul_src != nullptr : (EF & EF_MULSRC) != 0;
         const bool f_res = EF < 0 ? a.residual != nullptr : (EF & EF_RES) != 0;
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (f_bias) bb = *reinterpret_cast<const float4*>(a.bias + n);
+        if (f_bias) bb = *reinterpret_cast<const float4*>(sBias + n);
+        // the side stream of the epilogue (residual, or the saved multiplier) is fetched for all 8 row groups before any
+        // of it is used: one exposed memory latency per 32-column block instead of one per row group
+        const float* side_p = f_res ? a.residual : (f_mul ? a.mul_src : nullptr);
+        float4 side[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long m = mrow0 + i * 4 + rq;
+          side[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (side_p && m < a.M) side[i] = *reinterpret_cast<const float4*>(side_p + m * a.ldc + n);
+        }
 #pragma unroll 2
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + rq;
@@ -359,7 +425,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
             }
             if (f_act2) *reinterpret_cast<float4*>(a.aux + ci) = gd;
             if (f_mul) {
-              const float4 s4 = ld_act(reinterpret_cast<const float4*>(a.mul_src + ci), a.policy);
+              const float4 s4 = f_res ? ld_act(reinterpret_cast<const float4*>(a.mul_src + ci), a.policy) : side[i];
               r.x *= s4.x; r.y *= s4.y; r.z *= s4.z; r.w *= s4.w;
             }
             if (f_ag) {
@@ -367,14 +433,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
               r.x *= gelu_grad_f(s4.x); r.y *= gelu_grad_f(s4.y); r.z *= gelu_grad_f(s4.z); r.w *= gelu_grad_f(s4.w);
             }
             if (f_res) {
-              // plain (coherent) load: the residual may alias C (K-split accumulation passes)
-              const float4 s4 = *reinterpret_cast<const float4*>(a.residual + ci);
+              // (plain coherent loads above: the residual may alias C in the K-split accumulation passes)
+              const float4 s4 = side[i];
               r.x += s4.x; r.y += s4.y; r.z += s4.z; r.w += s4.w;
             }
             *reinterpret_cast<float4*>(a.C + ci) = r;
           }
         }
         __syncwarp();
+        dbg_mark(dbg, 2, dn, 25);
       }
       tc::tc_fence_before();
       tc::mbar_arrive(&accempty[buf]);
@@ -391,17 +458,24 @@ inline bool lin_tc_supported(long M, int N, int K) {
          lin_smem_bytes(N, K, 2) <= 227u * 1024u;
 }
 
-template <int NTERMS, int PRO, int EF>
-inline int lin_tc_launch_v(const LinTcArgs& a, int grid, uint32_t smem, cudaStream_t st) {
+template <int NTERMS, int PRO, int EF, int NEPI>
+inline int lin_tc_launch_w(const LinTcArgs& a, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(lin_tc_kernel<NTERMS, PRO, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(lin_tc_kernel<NTERMS, PRO, EF, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
-  lin_tc_kernel<NTERMS, PRO, EF><<<grid, NTHREADS, smem, st>>>(a);
+  lin_tc_kernel<NTERMS, PRO, EF, NEPI><<<grid, NTHREADS, lin_smem_bytes(a.N, a.K, a.nstage, NEPI), st>>>(a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
+}
+// deep contractions with narrow outputs run the producer-heavy split, everything else the epilogue-heavy one
+template <int NTERMS, int PRO, int EF>
+inline int lin_tc_launch_v(const LinTcArgs& a, int grid, uint32_t, cudaStream_t st) {
+  constexpr bool light = (EF >= 0) && (EF & (EF_ACT1 | EF_ACT2 | EF_ACTGRAD)) == 0;
+  if (light && a.N <= 64 && a.K >= 128 && g_tune[4] == 0) return lin_tc_launch_w<NTERMS, PRO, EF, 4>(a, grid, st);
+  return lin_tc_launch_w<NTERMS, PRO, EF, 8>(a, grid, st);
 }
 
 template <int NTERMS>
@@ -412,7 +486,7 @@ inline int lin_tc_launch_t(LinTcArgs a, cudaStream_t st) {
   while (a.nstage > 2 && lin_smem_bytes(a.N, a.K, a.nstage) > 227u * 1024u) --a.nstage;
   a.policy = g_tune[1];
   a.dbg = g_dbg_buf;
-  const uint32_t smem = lin_smem_bytes(a.N, a.K, a.nstage);
+  const uint32_t smem = 0;
   const int mask = (a.bias ? EF_BIAS : 0) | (a.act == 1 ? EF_ACT1 : 0) | (a.act == 2 ? EF_ACT2 : 0) | (a.drop_on ? EF_DROP : 0) |
                    (a.act_grad_src ? EF_ACTGRAD : 0) | (a.mul_src ? EF_MULSRC : 0) | (a.residual ? EF_RES : 0);
   ProfScope prof(PROF_LIN_TC, st);

@@ -171,14 +171,18 @@ class SyntheticBatches:
 
 class DevicePrefetcher:
     """Input pipeline of the hot loop (train_clip_final.py:475-479): yields device-resident (eeg, speech, ids) while the
-    NEXT batch's host->device copies run on a side stream (pinned staging buffers, double-buffered), so the 201-357 MB of
-    wav2vec2 features per batch cross PCIe under the previous step instead of in front of it.  `loader` yields the
-    reference's batch tuples (eeg (b,T,64), [speech (b,T,F)], ids (b,), subs)."""
+    NEXT batch's host->device copies run on a side stream, so the 201-357 MB of wav2vec2 features per batch cross PCIe
+    under the previous step instead of in front of it.  Two persistent device buffers (and two pinned staging buffers when
+    the loader's tensors are pageable) are reused in turn: no allocation in steady state, ordering by CUDA events only.
+    `loader` yields the reference's batch tuples (eeg (b,T,64), [speech (b,T,F)], ids (b,), subs).  A yielded batch is
+    valid until the next-but-one batch is requested."""
 
     def __init__(self, loader, device):
         self.loader, self.device = loader, device
         self.stream = torch.cuda.Stream(device=device)
         self._pinned = [None, None]
+        self._dev = [None, None]
+        self._free = [None, None]      # main-stream event after which device buffer `slot` may be overwritten
 
     def _stage(self, slot, data):
         eeg, speech, ids = data[0], data[1][0] if isinstance(data[1], (list, tuple)) else data[1], data[2]
@@ -191,14 +195,21 @@ class DevicePrefetcher:
                 pin = self._pinned[slot] = tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in src)
             for p_, t in zip(pin, src):
                 p_.copy_(t)
+        dev = self._dev[slot]
+        if dev is None or any(d.shape != t.shape for d, t in zip(dev, src)):
+            dev = self._dev[slot] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in src)
         with torch.cuda.stream(self.stream):
-            dev = tuple(p_.to(self.device, non_blocking=True) for p_ in pin)
+            if self._free[slot] is not None:
+                self.stream.wait_event(self._free[slot])   # the step that read this buffer has finished
+            for d, p_ in zip(dev, pin):
+                d.copy_(p_, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         return dev, ev
 
     def __iter__(self):
         it = iter(self.loader)
+        main = torch.cuda.current_stream(self.device)
         slot = 0
         try:
             nxt = self._stage(slot, next(it))
@@ -206,15 +217,17 @@ class DevicePrefetcher:
             return
         while nxt is not None:
             cur, ev = nxt
+            cur_slot = slot
             slot ^= 1
             try:
                 nxt = self._stage(slot, next(it))      # overlaps the step that consumes `cur`
             except StopIteration:
                 nxt = None
-            torch.cuda.current_stream(self.device).wait_event(ev)
-            for t in cur:
-                t.record_stream(torch.cuda.current_stream(self.device))
+            main.wait_event(ev)
             yield cur
+            done = torch.cuda.Event()                  # the consumer's work on `cur` is enqueued by now
+            done.record(main)
+            self._free[cur_slot] = done
 
 
 def printf(s, file):
