@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EEGCLIP_ABI_VERSION 2
+#define EEGCLIP_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define EEGCLIP_API __attribute__((visibility("default")))
@@ -233,11 +233,13 @@ EEGCLIP_API int eegclip_adamw_step(const eegclip_adamw_entry* table_dev, int32_t
 
 /* Match-mismatch scoring (train_clip_helper_functions.py:153-163,176-187).
  *   eegclip_mm_rowdots : scores[k][n] = <eeg[n], cand[n][k]>  (replaces the N x N matmul + diag) and argmax over k
- *   eegclip_mm_bank_logits : logits (N,M) = eeg (N,D) . bank (M,D)^T  (top-k is taken by the caller) */
+ *   eegclip_mm_bank_logits : logits (N,M) = eeg (N,D) . bank (M,D)^T  (top-k is taken by the caller); with `scratch`
+ *                            (eegclip_mm_bank_workspace bytes) and math != FP32 the tcgen05 similarity kernel runs */
 EEGCLIP_API int eegclip_mm_rowdots(const float* eeg, const float* cand, float* scores, int64_t* choice, int32_t N, int32_t K, int32_t D,
                        void* stream);
+EEGCLIP_API int eegclip_mm_bank_workspace(int32_t N, int32_t M, int32_t D, size_t* scratch_bytes);
 EEGCLIP_API int eegclip_mm_bank_logits(const float* eeg, const float* bank, float* logits, int32_t N, int32_t M, int32_t D, int32_t math,
-                           void* stream);
+                           void* scratch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -193,3 +193,49 @@ def test_grad_sinks_match_autograd(cm, lib):
     tot.backward()
     w = dict(model.named_parameters())["eegModel.conv_0.conv.weight"]
     assert rel_err(w.grad, 2 * ref["eegModel.conv_0.conv.weight"]) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# match-mismatch scoring (train_clip_helper_functions.py:153-163,176-187): candidate row-dots and the N x M bank
+# similarity on the tcgen05 kernel; decisions (argmax / top-k sets) must equal fp64 decisions on continuous inputs
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,M,D", [(64, 100, 1536), (300, 1000, 2560), (129, 257, 2560), (16, 2053, 512)])
+def test_bank_logits_tc_vs_fp64(lib, N, M, D):
+    from transformer_clip_eeg_b200 import train_clip_helper_functions as H
+    torch.manual_seed(N + M)
+    E = torch.randn(N, D, device=DEV)
+    Bk = torch.randn(M, D, device=DEV)
+    got = H.bank_logits(E, Bk)
+    ref = E.double() @ Bk.double().T
+    assert got.shape == (N, M)
+    assert rel_err(got, ref) < 1e-5
+    k = min(100, M)
+    ti = torch.topk(got, k, dim=1).indices
+    tr = torch.topk(ref, k, dim=1).indices
+    assert torch.equal(ti[:, 0], tr[:, 0])
+    # same top-k SET per row (order inside the set may flip only where fp64 gaps are below fp32 resolution)
+    same = (torch.sort(ti, dim=1).values == torch.sort(tr, dim=1).values).all(dim=1).float().mean()
+    assert float(same) > 0.99
+
+
+@pytest.mark.parametrize("K", [2, 5, 100])
+def test_mm_rowdots_decisions(lib, K):
+    from transformer_clip_eeg_b200 import train_clip_helper_functions as H
+    torch.manual_seed(K)
+    N, D = 257, 2560
+    E = torch.randn(N, D, device=DEV)
+    C = torch.randn(N, K, D, device=DEV)
+    scores, choice = H.mm_scores(E, C)
+    ref = torch.einsum("nd,nkd->kn", E.double(), C.double())
+    assert rel_err(scores, ref) < 1e-5
+    assert torch.equal(choice, ref.argmax(dim=0))
+
+
+def test_bank_topk_world1_matches_reference_topk(lib):
+    from transformer_clip_eeg_b200 import train_clip_helper_functions as H
+    torch.manual_seed(3)
+    E, Bk = torch.randn(96, 2560, device=DEV), torch.randn(1500, 2560, device=DEV)
+    v, i = H.bank_topk(E, Bk, 100)
+    rv, ri = torch.topk(E.double() @ Bk.double().T, 100, dim=1)
+    assert torch.equal(i[:, :10], ri[:, :10])
+    assert rel_err(v, rv) < 1e-5

@@ -27,7 +27,7 @@ def test_abi_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/eegclip.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == declared
-    assert lib.eegclip_abi_version() == 2
+    assert lib.eegclip_abi_version() == 3
 
 
 def test_cpu_tensors_fail_loudly():
@@ -167,6 +167,39 @@ def test_sharded_infonce_two_ranks_gloo(tmp_path):
     env = dict(os.environ, EEGCLIP_ROOT=ROOT)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29631", str(script)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("ok") == 2
+
+
+_TOPK_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["EEGCLIP_ROOT"]); sys.path.insert(0, os.path.join(os.environ["EEGCLIP_ROOT"], "tests"))
+from _util import synth
+from transformer_clip_eeg_b200.train_clip_helper_functions import bank_topk
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+N, D = 9, 16
+for M, k in [(37, 5), (11, 8), (3, 100)]:               # ragged slices; k above a slice; k above the whole bank
+    E, Bk = synth.randn(1, N, D).double(), synth.randn(2, M, D).double()
+    bounds = [0, M // 3, M] if world == 2 else [0, M]
+    loc = Bk[bounds[rank]:bounds[rank + 1]]
+    v, i = bank_topk(E, loc, k, group=dist.group.WORLD, logits_fn=lambda e, b: e @ b.T)
+    rv, ri = torch.topk(E @ Bk.T, min(k, M), dim=1)
+    assert torch.equal(i, ri), (M, k, i, ri)
+    assert torch.allclose(v, rv, rtol=1e-12, atol=1e-12)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_sharded_bank_topk_two_ranks_gloo(tmp_path):
+    """BASELINE config 4 host logic: candidate bank sharded over 2 ranks, local top-k + all-gather + merge == global top-k."""
+    script = tmp_path / "worker_topk.py"
+    script.write_text(_TOPK_WORKER)
+    env = dict(os.environ, EEGCLIP_ROOT=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29633", str(script)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("ok") == 2

@@ -12,12 +12,17 @@ blk = cm.BasicBlock(64, 64, kernel_size=64, time_dimension=T).to(dev).train()
 x = torch.randn(B, T, 64, device=dev); skip = torch.randn(B, T, 64, device=dev)
 for _ in range(3):
     blk.forward_time_major(x, skip)
-dbg = torch.zeros(768, dtype=torch.int64, device=dev)
-_lib.call("eegclip_debug_buffer", dbg.data_ptr())
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); blk.forward_time_major(x, skip); e1.record(); torch.cuda.synchronize()
-_lib.call("eegclip_debug_buffer", None)
-d = dbg.cpu()
-t = [int(d[i]) - int(d[0]) for i in range(4)]
-print(f"conv block fwd (pack + conv + LN) {e0.elapsed_time(e1) * 1e3:.1f} us; CTA0: staged {t[1] / 1e3:.2f} us, mma done {t[2] / 1e3:.2f} us, end {t[3] / 1e3:.2f} us")
+modes = [int(m) for m in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
+for mode in modes:     # bit 0: last tile as M=128; bit 1: no weight re-fetch (timing only); bit 2: no lo.hi MMA (timing only)
+    _lib.call("eegclip_tune_set", 5, mode)
+    dbg = torch.zeros(768, dtype=torch.int64, device=dev)
+    blk.forward_time_major(x, skip)
+    _lib.call("eegclip_debug_buffer", dbg.data_ptr())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); blk.forward_time_major(x, skip); e1.record(); torch.cuda.synchronize()
+    _lib.call("eegclip_debug_buffer", None)
+    d = dbg.cpu()
+    t = [int(d[i]) - int(d[0]) for i in range(4)]
+    print(f"exp_mode {mode}: conv block fwd (pack + conv + LN) {e0.elapsed_time(e1) * 1e3:.1f} us; CTA0: staged {t[1] / 1e3:.2f} us, mma done {t[2] / 1e3:.2f} us, end {t[3] / 1e3:.2f} us")
+_lib.call("eegclip_tune_set", 5, 0)

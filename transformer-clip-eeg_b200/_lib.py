@@ -98,7 +98,8 @@ SIGNATURES = {
     "eegclip_membank_update": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _vp]),
     "eegclip_adamw_step": (C.c_int, [_vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _vp]),
     "eegclip_mm_rowdots": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
-    "eegclip_mm_bank_logits": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "eegclip_mm_bank_workspace": (C.c_int, [_i32, _i32, _i32, _psz]),
+    "eegclip_mm_bank_logits": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
 }
 
 _ERR = {-1: "invalid argument", -2: "CUDA error", -3: "unsupported shape/configuration"}
@@ -119,7 +120,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.eegclip_abi_version() != 2:
+    if lib.eegclip_abi_version() != 3:
         raise EegclipError("libeegclip_b200.so ABI version mismatch")
     _lib = lib
     return lib

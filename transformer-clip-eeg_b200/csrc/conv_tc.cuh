@@ -70,6 +70,7 @@ struct ConvTcArgs {
   int taps;               // kernel size
   Drop drop;
   unsigned long long* dbg; // development timeline (CTA 0): start, staged, mma-done, end (globaltimer ns)
+  int exp_mode;            // development experiments (g_tune[5]); 0 = shipped path
 };
 
 __host__ __device__ inline uint32_t conv_smem_bytes(int T, int taps) {
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
 
   const int ntiles = (T + 127) >> 7;
-  const bool last64 = (T & 127) != 0;       // T % 128 == 64 -> last tile has M = 64
+  const bool last64 = (T & 127) != 0 && !(a.exp_mode & 1);   // T % 128 == 64 -> last tile has M = 64 (exp bit 0: run it as M = 128 over-read)
   constexpr uint32_t TCOLS = NTERMS > 1 ? 128u : 64u;   // TMEM columns per time tile: [hi.hi + lo.hi | hi.lo]
   uint32_t ncols = 64;
   while (ncols < (uint32_t)ntiles * TCOLS) ncols <<= 1;
@@ -115,29 +116,44 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
   if (warp == 2) tc::tmem_alloc(tmem_slot, ncols);
 
   // ---- stage the activation tile: fp32 (+skip) -> bf16 hi/lo, chunk-major, zero padded ----
+  // Loads are issued STAGE_U items deep before the first conversion: the tile is 82-164 KB per CTA and a load-convert-store
+  // loop exposes one DRAM round trip per iteration (ncu: long_scoreboard was the top stall of this kernel).
   {
     const float* sb = a.src + (long)b * a.src_rows * CH;
     const float* kb = a.skip ? a.skip + (long)b * a.src_rows * CH : nullptr;
-    for (int idx = tid; idx < TP * 8; idx += 256) {
-      const int r = idx >> 3, ch = idx & 7;
-      const int t = r - a.row_off;
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (t >= 0 && t < a.src_rows) {
-        const float4* p = reinterpret_cast<const float4*>(sb + (long)t * CH + ch * 8);
-        float4 x0 = p[0], x1 = p[1];
-        if (kb) {
-          const float4* q = reinterpret_cast<const float4*>(kb + (long)t * CH + ch * 8);
-          float4 y0 = q[0], y1 = q[1];
-          x0.x += y0.x; x0.y += y0.y; x0.z += y0.z; x0.w += y0.w;
-          x1.x += y1.x; x1.y += y1.y; x1.z += y1.z; x1.w += y1.w;
+    constexpr int STAGE_U = 6;
+    const int total = TP * 8;
+    for (int base = 0; base < total; base += 256 * STAGE_U) {
+      float4 x[STAGE_U][2], y[STAGE_U][2];
+#pragma unroll
+      for (int u = 0; u < STAGE_U; ++u) {
+        const int idx = base + u * 256 + tid;
+        const int r = idx >> 3, ch = idx & 7;
+        const int t = r - a.row_off;
+        x[u][0] = x[u][1] = y[u][0] = y[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < total && t >= 0 && t < a.src_rows) {
+          const float4* p = reinterpret_cast<const float4*>(sb + (long)t * CH + ch * 8);
+          x[u][0] = __ldg(p); x[u][1] = __ldg(p + 1);
+          if (kb) {
+            const float4* q = reinterpret_cast<const float4*>(kb + (long)t * CH + ch * 8);
+            y[u][0] = __ldg(q); y[u][1] = __ldg(q + 1);
+          }
         }
-        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
       }
-      uint4 hi, lo;
-      tc::split8(v, hi, lo);
-      uint8_t* d = sA + ch * CS + r * 16;
-      *reinterpret_cast<uint4*>(d) = hi;
-      if (NTERMS > 1) *reinterpret_cast<uint4*>(d + PS) = lo;
+#pragma unroll
+      for (int u = 0; u < STAGE_U; ++u) {
+        const int idx = base + u * 256 + tid;
+        if (idx < total) {
+          const int r = idx >> 3, ch = idx & 7;
+          const float v[8] = {x[u][0].x + y[u][0].x, x[u][0].y + y[u][0].y, x[u][0].z + y[u][0].z, x[u][0].w + y[u][0].w,
+                              x[u][1].x + y[u][1].x, x[u][1].y + y[u][1].y, x[u][1].z + y[u][1].z, x[u][1].w + y[u][1].w};
+          uint4 hi, lo;
+          tc::split8(v, hi, lo);
+          uint8_t* d = sA + ch * CS + r * 16;
+          *reinterpret_cast<uint4*>(d) = hi;
+          if (NTERMS > 1) *reinterpret_cast<uint4*>(d + PS) = lo;
+        }
+      }
     }
   }
   tc::fence_async_smem();
@@ -154,6 +170,7 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
       const int s = tap % NSTAGE;
       const uint32_t ph = (tap / NSTAGE) & 1;
       tc::mbar_wait(&empty[s], ph ^ 1);
+      if ((a.exp_mode & 2) && tap >= NSTAGE) { tc::mbar_arrive(&full[s]); continue; }   // timing experiment: no weight re-fetch
       tc::mbar_expect_tx(&full[s], bytes);
       tc::bulk_g2s(sB + s * W_TAP_BYTES, a.wpacked + (long)tap * W_TAP_BYTES, bytes, &full[s]);
     }
@@ -183,7 +200,7 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
             const uint64_t db = (uint64_t)((2 * ks * (2 * CH * 16)) >> 4);
             if (NTERMS > 1) {
               tc::mma_bf16(d, a_hi + da, b_w + db, idw, (tap | ks) != 0);   // [hi.hi | hi.lo]
-              tc::mma_bf16(d, a_lo + da, b_w + db, idn, 1);                 // += lo.hi (first 64 columns)
+              if (!(a.exp_mode & 4)) tc::mma_bf16(d, a_lo + da, b_w + db, idn, 1);   // += lo.hi (first 64 columns)
             } else {
               tc::mma_bf16(d, a_hi + da, b_w + db, idn, (tap | ks) != 0);
             }
@@ -195,41 +212,41 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
     }
     if (tc::elect_one()) tc::tc_commit(accfull);
     __syncwarp();
-  } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> bias / dropout -> global =====
-    const int q = warp - 4;  // TMEM lane quarter of this warp
+  }
+  __syncwarp();
+  {
+    // ===== epilogue (all 8 warps): TMEM -> registers -> bias / dropout -> global.  Warp w reads TMEM lane quarter w % 4;
+    // warps 4-7 take output channels 0-31, warps 0-3 (done with their producer / MMA roles by now) channels 32-63 =====
+    const int q = warp & 3;
+    const int half = warp < 4 ? 1 : 0;
     tc::mbar_wait(accfull, 0);
     tc::tc_fence_after();
     stamp(2);
+    float4 bb[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) bb[c] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + half * 32) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int tile = 0; tile < ntiles; ++tile) {
       const bool m64 = last64 && tile == ntiles - 1;
       const int row = m64 ? tile * 128 + q * 16 + lane : tile * 128 + q * 32 + lane;
       const bool valid = m64 ? (lane < 16) : true;
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + tile * TCOLS;
+      float v[32];
+      tc::tmem_ld32(taddr + half * 32, v);
+      if (NTERMS > 1) {
+        float v2[32];
+        tc::tmem_ld32(taddr + CH + half * 32, v2);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float v[32];
-        tc::tmem_ld32(taddr + half * 32, v);
-        if (NTERMS > 1) {
-          float v2[32];
-          tc::tmem_ld32(taddr + CH + half * 32, v2);
+        for (int c = 0; c < 32; ++c) v[c] += v2[c];
+      }
+      if (valid && row < T) {
+        float* o = a.out + ((long)b * T + row) * CH + half * 32;
+        const uint64_t didx = ((uint64_t)b * T + row) * CH + half * 32;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] += v2[c];
-        }
-        if (valid && row < T) {
-          float* o = a.out + ((long)b * T + row) * CH + half * 32;
-          const uint64_t didx = ((uint64_t)b * T + row) * CH + half * 32;
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            float4 r = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-            if (a.bias) {
-              float4 bb = *reinterpret_cast<const float4*>(a.bias + half * 32 + c);
-              r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
-            }
-            float4 m = drop_mult4(a.drop, didx + c);
-            r.x *= m.x; r.y *= m.y; r.z *= m.z; r.w *= m.w;
-            *reinterpret_cast<float4*>(o + c) = r;
-          }
+        for (int c = 0; c < 32; c += 4) {
+          float4 r = make_float4(v[c] + bb[c >> 2].x, v[c + 1] + bb[c >> 2].y, v[c + 2] + bb[c >> 2].z, v[c + 3] + bb[c >> 2].w);
+          float4 m = drop_mult4(a.drop, didx + c);
+          r.x *= m.x; r.y *= m.y; r.z *= m.z; r.w *= m.w;
+          *reinterpret_cast<float4*>(o + c) = r;
         }
       }
     }
@@ -278,41 +295,50 @@ __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a)
   uint32_t phase = 0;
   bool first = true;
   for (int b = grp; b < a.B; b += a.groups) {
-    // ---- stage u rows [k0 - PL, k0 - PL + TU) of the padded input and the T rows of dy ----
+    // ---- stage u rows [k0 - PL, k0 - PL + TU) of the padded input and the T rows of dy (loads issued WG_U deep) ----
     const float* xb = a.xin + (long)b * T * CH;
     const float* kb = a.skip ? a.skip + (long)b * T * CH : nullptr;
-    for (int idx = tid; idx < TU * 8; idx += 256) {
-      const int r = idx >> 3, ch = idx & 7;
-      const int t = r + k0 - a.PL;
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (t >= 0 && t < T) {
-        const float4* p = reinterpret_cast<const float4*>(xb + (long)t * CH + ch * 8);
-        float4 x0 = p[0], x1 = p[1];
-        if (kb) {
-          const float4* q = reinterpret_cast<const float4*>(kb + (long)t * CH + ch * 8);
-          float4 y0 = q[0], y1 = q[1];
-          x0.x += y0.x; x0.y += y0.y; x0.z += y0.z; x0.w += y0.w;
-          x1.x += y1.x; x1.y += y1.y; x1.z += y1.z; x1.w += y1.w;
-        }
-        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-      }
-      uint4 hi, lo;
-      tc::split8(v, hi, lo);
-      uint8_t* d = sU + ch * CSU + r * 16;
-      *reinterpret_cast<uint4*>(d) = hi;
-      if (NTERMS > 1) *reinterpret_cast<uint4*>(d + PSU) = lo;
-    }
     const float* db = a.dypad + ((long)b * (T + TAPS - 1) + a.PLb) * CH;
-    for (int idx = tid; idx < T * 8; idx += 256) {
-      const int r = idx >> 3, ch = idx & 7;
-      const float4* p = reinterpret_cast<const float4*>(db + (long)r * CH + ch * 8);
-      float4 x0 = p[0], x1 = p[1];
-      float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-      uint4 hi, lo;
-      tc::split8(v, hi, lo);
-      uint8_t* d = sD + ch * CSD + r * 16;
-      *reinterpret_cast<uint4*>(d) = hi;
-      if (NTERMS > 1) *reinterpret_cast<uint4*>(d + PSD) = lo;
+    constexpr int WG_U = 6;
+    const int nu = TU * 8, total = nu + T * 8;       // items [0, nu): u tile; [nu, total): dy tile
+    for (int base = 0; base < total; base += 256 * WG_U) {
+      float4 x[WG_U][2], y[WG_U][2];
+#pragma unroll
+      for (int u = 0; u < WG_U; ++u) {
+        const int idx = base + u * 256 + tid;
+        x[u][0] = x[u][1] = y[u][0] = y[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < nu) {
+          const int r = idx >> 3, ch = idx & 7;
+          const int t = r + k0 - a.PL;
+          if (t >= 0 && t < T) {
+            const float4* p = reinterpret_cast<const float4*>(xb + (long)t * CH + ch * 8);
+            x[u][0] = __ldg(p); x[u][1] = __ldg(p + 1);
+            if (kb) {
+              const float4* q = reinterpret_cast<const float4*>(kb + (long)t * CH + ch * 8);
+              y[u][0] = __ldg(q); y[u][1] = __ldg(q + 1);
+            }
+          }
+        } else if (idx < total) {
+          const int i2 = idx - nu;
+          const float4* p = reinterpret_cast<const float4*>(db + (long)(i2 >> 3) * CH + (i2 & 7) * 8);
+          x[u][0] = __ldg(p); x[u][1] = __ldg(p + 1);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < WG_U; ++u) {
+        const int idx = base + u * 256 + tid;
+        if (idx < total) {
+          const float v[8] = {x[u][0].x + y[u][0].x, x[u][0].y + y[u][0].y, x[u][0].z + y[u][0].z, x[u][0].w + y[u][0].w,
+                              x[u][1].x + y[u][1].x, x[u][1].y + y[u][1].y, x[u][1].z + y[u][1].z, x[u][1].w + y[u][1].w};
+          uint4 hi, lo;
+          tc::split8(v, hi, lo);
+          const bool isu = idx < nu;
+          const int i2 = isu ? idx : idx - nu;
+          uint8_t* d = isu ? sU + (i2 & 7) * CSU + (i2 >> 3) * 16 : sD + (i2 & 7) * CSD + (i2 >> 3) * 16;
+          *reinterpret_cast<uint4*>(d) = hi;
+          if (NTERMS > 1) *reinterpret_cast<uint4*>(d + (isu ? PSU : PSD)) = lo;
+        }
+      }
     }
     tc::fence_async_smem();
     tc::tc_fence_before();
@@ -417,7 +443,7 @@ inline int conv_tc_forward(int math, const float* xin, const float* skip_in, con
   convtc::pack_conv_weights_kernel<<<(taps * 8 * 64 + 255) / 256, 256, 0, st>>>(w, wp, 0, taps);
   LAUNCH_CHECK();
   convtc::ConvTcArgs a;
-  a.src = xin; a.skip = skip_in; a.wpacked = wp; a.bias = bias; a.out = y; a.T = T; a.src_rows = T; a.row_off = PL; a.taps = taps; a.drop = drop; a.dbg = g_dbg_buf;
+  a.src = xin; a.skip = skip_in; a.wpacked = wp; a.bias = bias; a.out = y; a.T = T; a.src_rows = T; a.row_off = PL; a.taps = taps; a.drop = drop; a.dbg = g_dbg_buf; a.exp_mode = g_tune[5];
   return math == EEGCLIP_MATH_BF16 ? conv_tc_launch<1>(a, B, st) : conv_tc_launch<3>(a, B, st);
 }
 
@@ -445,7 +471,7 @@ inline int conv_tc_backward(int math, const float* xin, const float* skip_in, co
   convtc::pack_conv_weights_kernel<<<(taps * 8 * 64 + 255) / 256, 256, 0, st>>>(w, wp, 1, taps);
   LAUNCH_CHECK();
   convtc::ConvTcArgs a;
-  a.src = dypad; a.skip = nullptr; a.wpacked = wp; a.bias = nullptr; a.out = du; a.T = T; a.src_rows = TP; a.row_off = 0; a.taps = taps; a.dbg = g_dbg_buf;
+  a.src = dypad; a.skip = nullptr; a.wpacked = wp; a.bias = nullptr; a.out = du; a.T = T; a.src_rows = TP; a.row_off = 0; a.taps = taps; a.dbg = g_dbg_buf; a.exp_mode = g_tune[5];
   a.drop = make_drop(0, 0, 0, 0.f, 0);
   int rc = math == EEGCLIP_MATH_BF16 ? conv_tc_launch<1>(a, B, st) : conv_tc_launch<3>(a, B, st);
   if (rc != EEGCLIP_OK) return rc;

@@ -467,15 +467,31 @@ int eegclip_mm_rowdots(const float* eeg, const float* cand, float* scores, int64
   return EEGCLIP_OK;
 }
 
+int eegclip_mm_bank_workspace(int32_t N, int32_t M, int32_t D, size_t* scratch_bytes) {
+  if (N <= 0 || M <= 0 || D <= 0 || !scratch_bytes) return EEGCLIP_ERR_ARG;
+  *scratch_bytes = (D % headtc::KC) == 0 ? headtc::epack_bytes(N, D) + headtc::epack_bytes(M, D) + 512 : 256;
+  return EEGCLIP_OK;
+}
+
 int eegclip_mm_bank_logits(const float* eeg, const float* bank, float* logits, int32_t N, int32_t M, int32_t D, int32_t math,
-                           void* stream) {
+                           void* scratch, void* stream) {
   if (!eeg || !bank || !logits || N <= 0 || M <= 0 || D <= 0) return EEGCLIP_ERR_ARG;
-  (void)math;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (math != EEGCLIP_MATH_FP32 && scratch && (D % headtc::KC) == 0) {
+    // tcgen05: both operands packed once, one 128 x 256 similarity tile per CTA, raw dots stored row-major
+    uint8_t* pE = (uint8_t*)scratch;
+    uint8_t* pB = pE + align_up(headtc::epack_bytes(N, D), 256);
+    TRY(headtc::epack(eeg, pE, N, D, st));
+    TRY(headtc::epack(bank, pB, M, D, st));
+    headtc::LogitsArgs a{};
+    a.Ap = pE; a.Bp = pB; a.a_blk0 = 0; a.M = N; a.N = M; a.D = D; a.tau = nullptr; a.out = logits; a.ldo = M;
+    return headtc::logits_launch<3>(math, a, st);
+  }
   GemmArgs g;
   g.A = eeg; g.B = bank; g.C = logits;
   g.M = N; g.N = M; g.K = D; g.KT = D;
   g.a_ms = D; g.a_ks = 1; g.b_ks = 1; g.b_ns = D; g.c_ms = M; g.c_ns = 1;
-  return gemm_f32<0>(g, (cudaStream_t)stream);
+  return gemm_f32<0>(g, st);
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@
 //       MODE 1  per-row (max, sum exp) partial of the tile + the diagonal logit        (forward: row / column LSE)
 //       MODE 2  G = (exp(L - lse_m) + exp(L - lse_n) - 2 delta) / (2B) * upstream, stored TRANSPOSED (n-major, coalesced)
 //               + sum G.L for d tau                                                     (backward: cross-entropy gradient)
+//       MODE 3  raw similarities stored row-major (match-mismatch bank scoring, train_clip_helper_functions.py:182)
 //   The two products of the backward, dS = exp(tau) G.E and dE = exp(tau) G^T.S, are contractions over the batch index
 //   and run on lin_wgrad_tc_kernel (lin_tc.cuh) with G^T / G as the token-major operand.
 #pragma once
@@ -74,6 +75,9 @@ struct LogitsArgs {
   float* GT;              // [N][ldg]: GT[n][m] = G(m, n)
   int ldg;
   float* dtau;            // += sum G * L (nullptr: skip)
+  // MODE 3
+  float* out;             // [M][ldo] raw dot products (no temperature)
+  long ldo;
 };
 
 template <int MODE, int NTERMS>
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(192, 1) logits_tc_kernel(const LogitsArgs a) {
     const bool mv = m < a.M;
     tc::mbar_wait(accfull, 0);
     tc::tc_fence_after();
-    const float scale = __expf(*a.tau);
+    const float scale = a.tau ? __expf(*a.tau) : 1.f;
     const int ncols = min(NT, a.N - n0);
     const int gm = m + a.m_off;
     if (MODE == 1) {
@@ -183,6 +187,22 @@ __global__ void __launch_bounds__(192, 1) logits_tc_kernel(const LogitsArgs a) {
       }
       // natural-log convention of the partials: (max, sum exp(L - max))
       if (mv) a.part[(long)m * gridDim.x + blockIdx.x] = make_float2(mx * (1.0f / LOG2E), sum);
+    } else if (MODE == 3) {
+      for (int cb = 0; cb < ncols; cb += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb, v);
+        if (mv) {
+          float* o = a.out + (long)m * a.ldo + n0 + cb;
+          if (cb + 32 <= ncols && (a.ldo & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cb + j < ncols) o[j] = v[j];
+          }
+        }
+      }
     } else {
       const float up = a.up ? *a.up : 1.f;
       const bool use_m = a.one_sided != 2, use_n = a.one_sided != 1;

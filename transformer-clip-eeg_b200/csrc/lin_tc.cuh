@@ -474,7 +474,10 @@ inline int lin_tc_launch_w(const LinTcArgs& a, int grid, cudaStream_t st) {
 template <int NTERMS, int PRO, int EF>
 inline int lin_tc_launch_v(const LinTcArgs& a, int grid, uint32_t, cudaStream_t st) {
   constexpr bool light = (EF >= 0) && (EF & (EF_ACT1 | EF_ACT2 | EF_ACTGRAD)) == 0;
-  if (light && a.N <= 64 && a.K >= 128 && g_tune[4] == 0) return lin_tc_launch_w<NTERMS, PRO, EF, 4>(a, grid, st);
+  // g_tune[4]: 0 shipped rule, 1 never, 2 every narrow output, 3 every light epilogue (development sweeps)
+  const bool narrow = g_tune[4] == 3 ? true : a.N <= 64;
+  const bool deep = g_tune[4] >= 2 ? true : a.K >= 128;
+  if (light && narrow && deep && g_tune[4] != 1) return lin_tc_launch_w<NTERMS, PRO, EF, 4>(a, grid, st);
   return lin_tc_launch_w<NTERMS, PRO, EF, 8>(a, grid, st);
 }
 

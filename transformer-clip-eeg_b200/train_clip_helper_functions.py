@@ -46,12 +46,51 @@ def mm_scores(eeg_emb, cand_emb):
 
 def bank_logits(eeg_emb, bank_emb):
     """eeg (N,D) . bank (M,D)^T -> (N,M)."""
+    import ctypes
     eeg_emb, bank_emb = L.f32c(eeg_emb), L.f32c(bank_emb)
     N, D = eeg_emb.shape
     M = bank_emb.shape[0]
     out = torch.empty(N, M, dtype=torch.float32, device=eeg_emb.device)
-    L.call("eegclip_mm_bank_logits", L.ptr(eeg_emb), L.ptr(bank_emb), L.ptr(out), N, M, D, L.default_math(), L.stream())
+    nb = ctypes.c_size_t()
+    L.call("eegclip_mm_bank_workspace", N, M, D, ctypes.byref(nb))
+    scratch = torch.empty(max(nb.value, 16), dtype=torch.uint8, device=eeg_emb.device)
+    L.call("eegclip_mm_bank_logits", L.ptr(eeg_emb), L.ptr(bank_emb), L.ptr(out), N, M, D, L.default_math(), L.ptr(scratch), L.stream())
     return out
+
+
+def bank_topk(eeg_emb, bank_emb, k, group=None, logits_fn=None):
+    """Top-k stimuli of the bank for every EEG window (train_clip_helper_functions.py:182-187), optionally with the bank
+    SHARDED over a process group (BASELINE config 4): every rank holds all N windows and its own slice of the M
+    candidates (``bank_emb`` is the local slice, slices concatenated in rank order form the bank), scores locally, keeps
+    its local top-k, and the k*world candidates are all-gathered and merged.  Returns (values (N,k), global indices (N,k)),
+    identical on all ranks and identical to a single-process top-k over the whole bank (ties aside)."""
+    import torch.distributed as dist
+    logits_fn = logits_fn or bank_logits
+    world = dist.get_world_size(group) if (group is not None and dist.is_initialized()) else 1
+    logits = logits_fn(eeg_emb, bank_emb)
+    m_loc = logits.shape[1]
+    kk = min(k, m_loc)
+    vals, idx = torch.topk(logits, k=kk, dim=1)
+    if world == 1:
+        return vals, idx
+    rank = dist.get_rank(group)
+    sizes = torch.zeros(world, dtype=torch.int64, device=logits.device)
+    sizes[rank] = m_loc
+    dist.all_reduce(sizes, group=group)
+    offset = int(sizes[:rank].sum())
+    if kk < k:   # pad so that every rank contributes k columns
+        pad = k - kk
+        vals = torch.cat([vals, vals.new_full((vals.shape[0], pad), float("-inf"))], dim=1)
+        idx = torch.cat([idx, idx.new_zeros((idx.shape[0], pad))], dim=1)
+    idx = idx + offset
+    all_v = [torch.empty_like(vals) for _ in range(world)]
+    all_i = [torch.empty_like(idx) for _ in range(world)]
+    dist.all_gather(all_v, vals.contiguous(), group=group)
+    dist.all_gather(all_i, idx.contiguous(), group=group)
+    cat_v, cat_i = torch.cat(all_v, dim=1), torch.cat(all_i, dim=1)
+    kout = min(k, int(sizes.sum()))
+    top_v, pos = torch.topk(cat_v, k=kout, dim=1)
+    return top_v, torch.gather(cat_i, 1, pos)
 
 
 def evaluate_model_challenge_2023_mm(model, device, subject=None, speech_feature='omsimel', eeg_folder=''):
