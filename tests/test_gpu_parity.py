@@ -290,6 +290,32 @@ def test_conv_tensor_core_vs_fp32(cm, pkg, T, B, math):
         assert rel_err(a, b) < tol, (name, rel_err(a, b))
 
 
+@pytest.mark.parametrize("Cin,Cout,taps,T,B", [(64, 256, 64, 320, 3), (256, 128, 64, 320, 2), (128, 128, 32, 192, 3), (256, 256, 64, 64, 5)])
+def test_conv_tensor_core_channel_blocks_vs_fp32(cm, pkg, Cin, Cout, taps, T, B):
+    """The VLAAI-shaped convs (vlaai.py:27-33: 64..256 channels): channel-blocked tcgen05 conv == exact-fp32 path."""
+    from transformer_clip_eeg_b200 import _lib
+    blk = cm.BasicBlock(Cin, Cout, kernel_size=taps, time_dimension=T, dropout_rate=0.0).to(DEV).eval()
+    with torch.no_grad():
+        blk.normalization.weight.add_(0.1 * torch.randn_like(blk.normalization.weight))
+    x = torch.randn(B, T, Cin, device=DEV)
+    skip = torch.randn(B, T, Cin, device=DEV)
+    w = torch.randn(B, T, Cout, device=DEV)
+    res = {}
+    for m in ("fp32", "bf16x3"):
+        _lib.set_default_math(m)
+        try:
+            xx = x.clone().requires_grad_(True)
+            blk.zero_grad()
+            y = blk.forward_time_major(xx, skip)
+            (y * w).sum().backward()
+            res[m] = (y.detach(), xx.grad.detach(), blk.conv.weight.grad.detach().clone(), blk.conv.bias.grad.detach().clone(),
+                      blk.normalization.weight.grad.detach().clone())
+        finally:
+            _lib.set_default_math("bf16x3")
+    for a, b, name in zip(res["bf16x3"], res["fp32"], ("y", "dx", "dw", "db", "dgamma")):
+        assert rel_err(a, b) < 2e-4, (name, rel_err(a, b))
+
+
 def test_full_size_properties(cm):
     """BASELINE config 2 sizes (B=256, T=320, depth 10): properties that need no CPU oracle run."""
     torch.manual_seed(0)

@@ -1,5 +1,7 @@
-// tcgen05 implicit-GEMM for Conv1d(64 -> 64, k = 64, 'same') on time-major activations: forward, data gradient and
-// weight gradient (clip_model.py:237,245 -- 74 % of the EEG tower's FLOPs).
+// tcgen05 implicit-GEMM for Conv1d(Cin -> Cout, k = 16..64, 'same') on time-major activations: forward, data gradient
+// and weight gradient (clip_model.py:237,245 -- 74 % of the EEG tower's FLOPs; vlaai.py:27-33,55 -- the
+// 64..256-channel stacks of VLAAI).  Channels are processed in blocks of 64: an output block is a CTA (grid.y), input
+// blocks are an outer loop that re-stages the activation tile and keeps accumulating into the same TMEM columns.
 //
 // Forward / data gradient (conv64_tc_kernel): one CTA per sample keeps the whole zero-padded activation tile
 // (T+63 rows x 64 channels, bf16 hi+lo planes, chunk-major -- see tc_common.cuh) resident in shared memory.  Tap k of
@@ -31,7 +33,6 @@ constexpr int NSTAGE = 4;            // weight ring depth
 constexpr int W_PLANE_BYTES = CH * CH * 2;      // 8 KB: one tap, one plane, [ci chunk][co][8]
 constexpr int W_TAP_BYTES = 2 * W_PLANE_BYTES;  // hi + lo
 constexpr int WG_TAPS = 16;          // taps per weight-gradient CTA
-constexpr int WG_MAX_GROUPS = 37;    // 4 tap groups x 37 sample groups = 148 CTAs
 
 // ------------------------------------------------------------------------------------------------
 // Weight packing: fp32 W[co][ci][k]  ->  bf16, per tap [k-chunk][n' = 128][8] with n' < 64 the hi part of output n' and
@@ -41,29 +42,35 @@ constexpr int WG_MAX_GROUPS = 37;    // 4 tap groups x 37 sample groups = 148 CT
 //   mode 0 (forward) : n = co, contraction index = ci, tap = k
 //   mode 1 (dgrad)   : n = ci, contraction index = co, tap k' holds W[..][..][63-k']
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int mode, int TAPS) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over taps * 8 chunks * 64 n
-  if (i >= TAPS * 8 * CH) return;
-  int n = i & 63, ch = (i >> 6) & 7, tap = i >> 9;
+__global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int mode, int TAPS, int Cin, int Cout) {
+  // packed block (nb, kb) = 64 outputs x 64 contraction channels, all taps: out + ((nb * nkb + kb) * TAPS + tap) * W_TAP_BYTES
+  const int nN = (mode == 0 ? Cout : Cin) / CH, nK = (mode == 0 ? Cin : Cout) / CH;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over blocks * taps * 8 chunks * 64 n
+  if (i >= (long)nN * nK * TAPS * 8 * CH) return;
+  const int n = i & 63, ch = (i >> 6) & 7;
+  const long rest = i >> 9;
+  const int tap = rest % TAPS;
+  const int blk = rest / TAPS, kb = blk % nK, nb = blk / nK;
   float v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    int kk = ch * 8 + e;  // contraction index
-    v[e] = mode == 0 ? W[((long)n * CH + kk) * TAPS + tap] : W[((long)kk * CH + n) * TAPS + (TAPS - 1 - tap)];
+    const int kk = kb * CH + ch * 8 + e, nn = nb * CH + n;  // contraction / output channel
+    v[e] = mode == 0 ? W[((long)nn * Cin + kk) * TAPS + tap] : W[((long)kk * Cin + nn) * TAPS + (TAPS - 1 - tap)];
   }
   uint4 hi, lo;
   tc::split8(v, hi, lo);
-  uint8_t* base = out + (long)tap * W_TAP_BYTES + ch * (2 * CH * 16) + n * 16;
+  uint8_t* base = out + ((long)blk * TAPS + tap) * W_TAP_BYTES + ch * (2 * CH * 16) + n * 16;
   *reinterpret_cast<uint4*>(base) = hi;
   *reinterpret_cast<uint4*>(base + CH * 16) = lo;
 }
 
 struct ConvTcArgs {
-  const float* src;       // (B, src_rows, 64) fp32
+  const float* src;       // (B, src_rows, src_ld) fp32
   const float* skip;      // optional addend, same shape as src
-  const uint8_t* wpacked; // TAPS * W_TAP_BYTES
-  const float* bias;      // optional
-  float* out;             // (B, T, 64)
+  const uint8_t* wpacked; // [n block][k block][tap] W_TAP_BYTES
+  const float* bias;      // optional (out_ld)
+  float* out;             // (B, T, out_ld)
+  int src_ld, out_ld;     // channels of src / out (multiples of 64); grid.y = out_ld / 64, the kernel loops over src_ld / 64
   int T;                  // output rows
   int src_rows;           // valid source rows
   int row_off;            // smem row r holds src row r - row_off (zero outside)
@@ -82,7 +89,8 @@ template <int NTERMS>
 __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, nb = blockIdx.y;
+  const int nkb = a.src_ld / CH;
   const int T = a.T, TAPS = a.taps, TP = T + TAPS - 1;
   const uint32_t CS = (uint32_t)TP * 16u;   // chunk stride (bytes)
   const uint32_t PS = 8u * CS;              // plane stride
@@ -114,13 +122,16 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
     tc::mbar_fence_init();
   }
   if (warp == 2) tc::tmem_alloc(tmem_slot, ncols);
+  uint32_t tmem = 0;
 
+  for (int kb = 0; kb < nkb; ++kb) {
   // ---- stage the activation tile: fp32 (+skip) -> bf16 hi/lo, chunk-major, zero padded ----
   // Loads are issued STAGE_U items deep before the first conversion: the tile is 82-164 KB per CTA and a load-convert-store
   // loop exposes one DRAM round trip per iteration (ncu: long_scoreboard was the top stall of this kernel).
   {
-    const float* sb = a.src + (long)b * a.src_rows * CH;
-    const float* kb = a.skip ? a.skip + (long)b * a.src_rows * CH : nullptr;
+    const int ld = a.src_ld;
+    const float* sb = a.src + (long)b * a.src_rows * ld + kb * CH;
+    const float* kp = a.skip ? a.skip + (long)b * a.src_rows * ld + kb * CH : nullptr;
     constexpr int STAGE_U = 6;
     const int total = TP * 8;
     for (int base = 0; base < total; base += 256 * STAGE_U) {
@@ -132,10 +143,10 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
         const int t = r - a.row_off;
         x[u][0] = x[u][1] = y[u][0] = y[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (idx < total && t >= 0 && t < a.src_rows) {
-          const float4* p = reinterpret_cast<const float4*>(sb + (long)t * CH + ch * 8);
+          const float4* p = reinterpret_cast<const float4*>(sb + (long)t * ld + ch * 8);
           x[u][0] = __ldg(p); x[u][1] = __ldg(p + 1);
-          if (kb) {
-            const float4* q = reinterpret_cast<const float4*>(kb + (long)t * CH + ch * 8);
+          if (kp) {
+            const float4* q = reinterpret_cast<const float4*>(kp + (long)t * ld + ch * 8);
             y[u][0] = __ldg(q); y[u][1] = __ldg(q + 1);
           }
         }
@@ -160,19 +171,21 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  stamp(1);
+  tmem = *tmem_slot;
+  if (kb == 0) stamp(1);
+  const uint8_t* wblk = a.wpacked + ((long)nb * nkb + kb) * TAPS * W_TAP_BYTES;
+  const int g0 = kb * TAPS;                 // global tap counter of this block's first tap (ring slot / phase bookkeeping)
 
   if (warp == 0 && lane == 0) {
     // ===== weight producer: one 1-D bulk copy per tap into the ring =====
     const uint32_t bytes = W_TAP_BYTES;
     for (int tap = 0; tap < TAPS; ++tap) {
-      const int s = tap % NSTAGE;
-      const uint32_t ph = (tap / NSTAGE) & 1;
+      const int s = (g0 + tap) % NSTAGE;
+      const uint32_t ph = ((g0 + tap) / NSTAGE) & 1;
       tc::mbar_wait(&empty[s], ph ^ 1);
       if ((a.exp_mode & 2) && tap >= NSTAGE) { tc::mbar_arrive(&full[s]); continue; }   // timing experiment: no weight re-fetch
       tc::mbar_expect_tx(&full[s], bytes);
-      tc::bulk_g2s(sB + s * W_TAP_BYTES, a.wpacked + (long)tap * W_TAP_BYTES, bytes, &full[s]);
+      tc::bulk_g2s(sB + s * W_TAP_BYTES, wblk + (long)tap * W_TAP_BYTES, bytes, &full[s]);
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the loop (descriptors stay in uniform registers), one elected lane issues =====
@@ -181,28 +194,53 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
     const uint32_t idw128 = tc::idesc_bf16(128, 2 * CH, 0, 0), idw64 = tc::idesc_bf16(64, 2 * CH, 0, 0);
     const uint32_t idn128 = tc::idesc_bf16(128, CH, 0, 0), idn64 = tc::idesc_bf16(64, CH, 0, 0);
     for (int tap = 0; tap < TAPS; ++tap) {
-      const int s = tap % NSTAGE;
-      const uint32_t ph = (tap / NSTAGE) & 1;
+      const int s = (g0 + tap) % NSTAGE;
+      const uint32_t ph = ((g0 + tap) / NSTAGE) & 1;
+      const uint32_t acc = (uint32_t)((kb | tap) != 0);
       tc::mbar_wait(&full[s], ph);
       tc::tc_fence_after();
       const uint32_t wb = sB_u + s * W_TAP_BYTES;
       const uint64_t b_w = tc::smem_desc(wb, 2 * CH * 16, 128);   // chunk stride 2048 B: rows 0-63 hi, 64-127 lo
       if (tc::elect_one()) {
-        for (int tile = 0; tile < ntiles; ++tile) {
-          const bool m64 = last64 && tile == ntiles - 1;
-          const uint32_t idw = m64 ? idw64 : idw128, idn = m64 ? idn64 : idn128;
-          const uint32_t d = tmem + tile * TCOLS;
-          const uint32_t arow = sA_u + (uint32_t)(tile * 128 + tap) * 16u;
-          const uint64_t a_hi = tc::smem_desc(arow, CS, 128), a_lo = tc::smem_desc(arow + PS, CS, 128);
+        if (!(a.exp_mode & 8)) {  // shipped: tile-major issue order (measured 62.7 us vs 67.7 us per window for the K-step-major order below)
+          for (int tile = 0; tile < ntiles; ++tile) {
+            const bool m64 = last64 && tile == ntiles - 1;
+            const uint32_t idw = m64 ? idw64 : idw128, idn = m64 ? idn64 : idn128;
+            const uint32_t d = tmem + tile * TCOLS;
+            const uint32_t arow = sA_u + (uint32_t)(tile * 128 + tap) * 16u;
+            const uint64_t a_hi = tc::smem_desc(arow, CS, 128), a_lo = tc::smem_desc(arow + PS, CS, 128);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t da = (uint64_t)((2 * ks * CS) >> 4);           // start-address field is in 16-byte units
+              const uint64_t db = (uint64_t)((2 * ks * (2 * CH * 16)) >> 4);
+              if (NTERMS > 1) {
+                tc::mma_bf16(d, a_hi + da, b_w + db, idw, acc | (uint32_t)(ks != 0));   // [hi.hi | hi.lo]
+                if (!(a.exp_mode & 4)) tc::mma_bf16(d, a_lo + da, b_w + db, idn, 1);   // += lo.hi (first 64 columns)
+              } else {
+                tc::mma_bf16(d, a_hi + da, b_w + db, idn, acc | (uint32_t)(ks != 0));
+              }
+            }
+          }
+        } else {
+          // development (exp bit 3): K-step-major issue order, consecutive MMAs target different accumulators.  Not faster: the
+          // pipe is paced by the exposed shared-memory fetch of the A operand (M/4 cycles per instruction), not by accumulate
+          // dependencies -- measured cost per MMA = M/4 + max(M,128)*N/256 cycles
+          const int tap_a = (a.exp_mode & 16) ? 0 : (a.exp_mode & 32) ? (tap & ~7) : tap;   // timing experiments: aligned operand starts
+          const uint64_t a0 = tc::smem_desc(sA_u + (uint32_t)tap_a * 16u, CS, 128);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t da = (uint64_t)((2 * ks * CS) >> 4);           // start-address field is in 16-byte units
+            const uint64_t da = (uint64_t)((2 * ks * CS) >> 4);             // start-address field is in 16-byte units
             const uint64_t db = (uint64_t)((2 * ks * (2 * CH * 16)) >> 4);
-            if (NTERMS > 1) {
-              tc::mma_bf16(d, a_hi + da, b_w + db, idw, (tap | ks) != 0);   // [hi.hi | hi.lo]
-              if (!(a.exp_mode & 4)) tc::mma_bf16(d, a_lo + da, b_w + db, idn, 1);   // += lo.hi (first 64 columns)
-            } else {
-              tc::mma_bf16(d, a_hi + da, b_w + db, idn, (tap | ks) != 0);
+            for (int tile = 0; tile < ntiles; ++tile) {
+              const bool m64 = last64 && tile == ntiles - 1;
+              tc::mma_bf16(tmem + tile * TCOLS, a0 + da + (uint64_t)(tile * 128), b_w + db, NTERMS > 1 ? (m64 ? idw64 : idw128) : (m64 ? idn64 : idn128),
+                           acc | (uint32_t)(ks != 0));                       // [hi.hi | hi.lo]
+            }
+            if (NTERMS > 1 && !(a.exp_mode & 4)) {
+              for (int tile = 0; tile < ntiles; ++tile) {
+                const bool m64 = last64 && tile == ntiles - 1;
+                tc::mma_bf16(tmem + tile * TCOLS, a0 + da + (uint64_t)(tile * 128 + (PS >> 4)), b_w + db, m64 ? idn64 : idn128, 1);   // += lo.hi
+              }
             }
           }
         }
@@ -214,17 +252,19 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
     __syncwarp();
   }
   __syncwarp();
+  // every MMA that reads this input block's tile has completed (also: the accumulators are final after the last block)
+  tc::mbar_wait(accfull, (uint32_t)(kb & 1));
+  tc::tc_fence_after();
+  }  // kb
   {
     // ===== epilogue (all 8 warps): TMEM -> registers -> bias / dropout -> global.  Warp w reads TMEM lane quarter w % 4;
     // warps 4-7 take output channels 0-31, warps 0-3 (done with their producer / MMA roles by now) channels 32-63 =====
     const int q = warp & 3;
     const int half = warp < 4 ? 1 : 0;
-    tc::mbar_wait(accfull, 0);
-    tc::tc_fence_after();
     stamp(2);
     float4 bb[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) bb[c] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + half * 32) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < 8; ++c) bb[c] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + nb * CH + half * 32) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int tile = 0; tile < ntiles; ++tile) {
       const bool m64 = last64 && tile == ntiles - 1;
       const int row = m64 ? tile * 128 + q * 16 + lane : tile * 128 + q * 32 + lane;
@@ -239,8 +279,8 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
         for (int c = 0; c < 32; ++c) v[c] += v2[c];
       }
       if (valid && row < T) {
-        float* o = a.out + ((long)b * T + row) * CH + half * 32;
-        const uint64_t didx = ((uint64_t)b * T + row) * CH + half * 32;
+        float* o = a.out + ((long)b * T + row) * a.out_ld + nb * CH + half * 32;
+        const uint64_t didx = ((uint64_t)b * T + row) * a.out_ld + nb * CH + half * 32;
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
           float4 r = make_float4(v[c] + bb[c >> 2].x, v[c + 1] + bb[c >> 2].y, v[c + 2] + bb[c >> 2].z, v[c + 3] + bb[c >> 2].w);
@@ -261,11 +301,12 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
 // Weight gradient
 // ------------------------------------------------------------------------------------------------
 struct WgradTcArgs {
-  const float* xin;     // (B,T,64) conv input
+  const float* xin;     // (B,T,Cin) conv input
   const float* skip;    // optional addend
-  const float* dypad;   // (B,TP,64) zero-padded output gradient, valid rows [PLb, PLb+T)
-  float* partial;       // [groups][taps][64 co][64 ci]
+  const float* dypad;   // (B,TP,Cout) zero-padded output gradient, valid rows [PLb, PLb+T)
+  float* partial;       // [groups][taps][Cout][Cin]
   int B, T, PL, PLb, groups, taps;
+  int Cin, Cout;        // multiples of 64; grid.x = (taps / 16) * (Cout / 64) * (Cin / 64)
 };
 
 __host__ __device__ inline uint32_t wgrad_smem_bytes(int T) {
@@ -276,7 +317,8 @@ template <int NTERMS>
 __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tg = blockIdx.x, grp = blockIdx.y;
+  const int ntg = a.taps / WG_TAPS, nci = a.Cin / CH;
+  const int tg = blockIdx.x % ntg, cib = (blockIdx.x / ntg) % nci, cob = blockIdx.x / (ntg * nci), grp = blockIdx.y;
   const int T = a.T, TAPS = a.taps, TU = T + WG_TAPS - 1;
   const int k0 = tg * WG_TAPS;
   const uint32_t CSU = (uint32_t)TU * 16u, PSU = 8u * CSU;
@@ -296,9 +338,10 @@ __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a)
   bool first = true;
   for (int b = grp; b < a.B; b += a.groups) {
     // ---- stage u rows [k0 - PL, k0 - PL + TU) of the padded input and the T rows of dy (loads issued WG_U deep) ----
-    const float* xb = a.xin + (long)b * T * CH;
-    const float* kb = a.skip ? a.skip + (long)b * T * CH : nullptr;
-    const float* db = a.dypad + ((long)b * (T + TAPS - 1) + a.PLb) * CH;
+    const int ldx = a.Cin, ldy = a.Cout;
+    const float* xb = a.xin + (long)b * T * ldx + cib * CH;
+    const float* kb = a.skip ? a.skip + (long)b * T * ldx + cib * CH : nullptr;
+    const float* db = a.dypad + ((long)b * (T + TAPS - 1) + a.PLb) * ldy + cob * CH;
     constexpr int WG_U = 6;
     const int nu = TU * 8, total = nu + T * 8;       // items [0, nu): u tile; [nu, total): dy tile
     for (int base = 0; base < total; base += 256 * WG_U) {
@@ -311,16 +354,16 @@ __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a)
           const int r = idx >> 3, ch = idx & 7;
           const int t = r + k0 - a.PL;
           if (t >= 0 && t < T) {
-            const float4* p = reinterpret_cast<const float4*>(xb + (long)t * CH + ch * 8);
+            const float4* p = reinterpret_cast<const float4*>(xb + (long)t * ldx + ch * 8);
             x[u][0] = __ldg(p); x[u][1] = __ldg(p + 1);
             if (kb) {
-              const float4* q = reinterpret_cast<const float4*>(kb + (long)t * CH + ch * 8);
+              const float4* q = reinterpret_cast<const float4*>(kb + (long)t * ldx + ch * 8);
               y[u][0] = __ldg(q); y[u][1] = __ldg(q + 1);
             }
           }
         } else if (idx < total) {
           const int i2 = idx - nu;
-          const float4* p = reinterpret_cast<const float4*>(db + (long)(i2 >> 3) * CH + (i2 & 7) * 8);
+          const float4* p = reinterpret_cast<const float4*>(db + (long)(i2 >> 3) * ldy + (i2 & 7) * 8);
           x[u][0] = __ldg(p); x[u][1] = __ldg(p + 1);
         }
       }
@@ -380,7 +423,7 @@ __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a)
     for (int cb = 0; cb < 8; ++cb) {
       const int tap = k0 + cb * 2 + (lane >> 4);
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + cb * 64;
-      float* o = a.partial + (((long)grp * TAPS + tap) * CH + co) * CH;
+      float* o = a.partial + (((long)grp * TAPS + tap) * a.Cout + cob * CH + co) * a.Cin + cib * CH;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float v[32];
@@ -396,13 +439,16 @@ __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a)
 }
 
 // dW[co][ci][k] = sum_g partial[g][k][co][ci]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int groups, int TAPS) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over k*4096 + co*64 + ci
-  if (i >= TAPS * CH * CH) return;
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int groups, int TAPS, int Cin, int Cout) {
+  const long per = (long)TAPS * Cout * Cin;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over (k * Cout + co) * Cin + ci
+  if (i >= per) return;
   float s = 0.f;
-  for (int g = 0; g < groups; ++g) s += partial[(long)g * TAPS * CH * CH + i];
-  int ci = i & 63, co = (i >> 6) & 63, k = i >> 12;
-  dW[((long)co * CH + ci) * TAPS + k] = s;
+  for (int g = 0; g < groups; ++g) s += partial[(long)g * per + i];
+  const int ci = i % Cin;
+  const long r = i / Cin;
+  const int co = r % Cout, k = r / Cout;
+  dW[((long)co * Cin + ci) * TAPS + k] = s;
 }
 
 }  // namespace convtc
@@ -411,15 +457,25 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 // Interface used by tower.cu
 // ------------------------------------------------------------------------------------------------
 inline bool conv_tc_supported(int Cin, int Cout, int taps, int T) {
-  return Cin == 64 && Cout == 64 && taps >= 16 && taps <= convtc::MAX_TAPS && (taps % 16) == 0 && T >= 64 && (T % 64) == 0 && T <= 512;
+  return Cin >= 64 && Cout >= 64 && (Cin % 64) == 0 && (Cout % 64) == 0 && Cin <= 512 && Cout <= 512 && taps >= 16 &&
+         taps <= convtc::MAX_TAPS && (taps % 16) == 0 && T >= 64 && (T % 64) == 0 && T <= 512;
 }
 
-// scratch: packed weights (1 MB) + weight-gradient partials (groups MB)
-inline size_t conv_tc_scratch_bytes(int B, int T, int taps) {
+// weight-gradient sample groups: (tap groups x channel blocks) x groups CTAs ~ one wave of 148 SMs
+inline int conv_tc_wgrad_groups(int B, int taps, int Cin, int Cout) {
+  const int gx = (taps / convtc::WG_TAPS) * (Cin / 64) * (Cout / 64);
+  int g = 148 / (gx > 0 ? gx : 1);
+  if (g < 1) g = 1;
+  return B < g ? B : g;
+}
+
+// scratch: packed weights (16 KB per tap and 64x64 channel block) + weight-gradient partials (groups x |W|)
+inline size_t conv_tc_scratch_bytes(int B, int T, int taps, int Cin, int Cout) {
   (void)T;
-  if (taps > convtc::MAX_TAPS || (taps % 16)) return 0;
-  int groups = B < convtc::WG_MAX_GROUPS ? B : convtc::WG_MAX_GROUPS;
-  return (size_t)taps * convtc::W_TAP_BYTES + (size_t)groups * taps * 64 * 64 * sizeof(float) + 256;
+  if (taps > convtc::MAX_TAPS || (taps % 16) || (Cin % 64) || (Cout % 64)) return 0;
+  const size_t blocks = (size_t)(Cin / 64) * (Cout / 64);
+  return align_up(blocks * taps * convtc::W_TAP_BYTES, 256) +
+         (size_t)conv_tc_wgrad_groups(B, taps, Cin, Cout) * taps * Cin * Cout * sizeof(float) + 256;
 }
 
 template <int NTERMS>
@@ -432,18 +488,25 @@ inline int conv_tc_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
     configured = true;
   }
   ProfScope prof(PROF_CONV_TC, st);
-  convtc::conv64_tc_kernel<NTERMS><<<B, 256, smem, st>>>(a);
+  convtc::conv64_tc_kernel<NTERMS><<<dim3(B, a.out_ld / convtc::CH), 256, smem, st>>>(a);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+inline int conv_tc_pack(const float* w, uint8_t* wp, int mode, int taps, int Cin, int Cout, cudaStream_t st) {
+  const long n = (long)(Cin / 64) * (Cout / 64) * taps * 8 * 64;
+  convtc::pack_conv_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, wp, mode, taps, Cin, Cout);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
 
 inline int conv_tc_forward(int math, const float* xin, const float* skip_in, const float* w, const float* bias, float* y, int B, int T,
-                           int taps, int PL, const Drop& drop, void* scratch, cudaStream_t st) {
+                           int Cin, int Cout, int taps, int PL, const Drop& drop, void* scratch, cudaStream_t st) {
   uint8_t* wp = (uint8_t*)scratch;
-  convtc::pack_conv_weights_kernel<<<(taps * 8 * 64 + 255) / 256, 256, 0, st>>>(w, wp, 0, taps);
-  LAUNCH_CHECK();
+  { int prc = conv_tc_pack(w, wp, 0, taps, Cin, Cout, st); if (prc != EEGCLIP_OK) return prc; }
   convtc::ConvTcArgs a;
-  a.src = xin; a.skip = skip_in; a.wpacked = wp; a.bias = bias; a.out = y; a.T = T; a.src_rows = T; a.row_off = PL; a.taps = taps; a.drop = drop; a.dbg = g_dbg_buf; a.exp_mode = g_tune[5];
+  a.src = xin; a.skip = skip_in; a.wpacked = wp; a.bias = bias; a.out = y; a.src_ld = Cin; a.out_ld = Cout;
+  a.T = T; a.src_rows = T; a.row_off = PL; a.taps = taps; a.drop = drop; a.dbg = g_dbg_buf; a.exp_mode = g_tune[5];
   return math == EEGCLIP_MATH_BF16 ? conv_tc_launch<1>(a, B, st) : conv_tc_launch<3>(a, B, st);
 }
 
@@ -455,7 +518,7 @@ inline int wgrad_tc_launch(const convtc::WgradTcArgs& a, cudaStream_t st) {
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
-  dim3 grid(a.taps / convtc::WG_TAPS, a.groups);
+  dim3 grid((a.taps / convtc::WG_TAPS) * (a.Cin / convtc::CH) * (a.Cout / convtc::CH), a.groups);
   ProfScope prof(PROF_WGRAD_TC, st);
   convtc::wgrad64_tc_kernel<NTERMS><<<grid, 256, convtc::wgrad_smem_bytes(a.T), st>>>(a);
   LAUNCH_CHECK();
@@ -463,24 +526,27 @@ inline int wgrad_tc_launch(const convtc::WgradTcArgs& a, cudaStream_t st) {
 }
 
 // du = dgrad(dypad, w) ; dw = wgrad(dypad, xin + skip_in)
-inline int conv_tc_backward(int math, const float* xin, const float* skip_in, const float* w, const float* dypad, int taps, int PLb,
-                            float* du, float* dw, int B, int T, void* scratch, cudaStream_t st) {
+inline int conv_tc_backward(int math, const float* xin, const float* skip_in, const float* w, const float* dypad, int Cin, int Cout,
+                            int taps, int PLb, float* du, float* dw, int B, int T, void* scratch, cudaStream_t st) {
   uint8_t* wp = (uint8_t*)scratch;
-  float* partial = (float*)(wp + (size_t)taps * convtc::W_TAP_BYTES);
+  const size_t blocks = (size_t)(Cin / 64) * (Cout / 64);
+  float* partial = (float*)(wp + align_up(blocks * taps * convtc::W_TAP_BYTES, 256));
   const int TP = T + taps - 1;
-  convtc::pack_conv_weights_kernel<<<(taps * 8 * 64 + 255) / 256, 256, 0, st>>>(w, wp, 1, taps);
-  LAUNCH_CHECK();
+  { int prc = conv_tc_pack(w, wp, 1, taps, Cin, Cout, st); if (prc != EEGCLIP_OK) return prc; }
   convtc::ConvTcArgs a;
-  a.src = dypad; a.skip = nullptr; a.wpacked = wp; a.bias = nullptr; a.out = du; a.T = T; a.src_rows = TP; a.row_off = 0; a.taps = taps; a.dbg = g_dbg_buf; a.exp_mode = g_tune[5];
+  a.src = dypad; a.skip = nullptr; a.wpacked = wp; a.bias = nullptr; a.out = du; a.src_ld = Cout; a.out_ld = Cin;
+  a.T = T; a.src_rows = TP; a.row_off = 0; a.taps = taps; a.dbg = g_dbg_buf; a.exp_mode = g_tune[5];
   a.drop = make_drop(0, 0, 0, 0.f, 0);
   int rc = math == EEGCLIP_MATH_BF16 ? conv_tc_launch<1>(a, B, st) : conv_tc_launch<3>(a, B, st);
   if (rc != EEGCLIP_OK) return rc;
   convtc::WgradTcArgs g;
   g.xin = xin; g.skip = skip_in; g.dypad = dypad; g.partial = partial; g.B = B; g.T = T; g.PL = taps - 1 - PLb; g.PLb = PLb; g.taps = taps;
-  g.groups = B < convtc::WG_MAX_GROUPS ? B : convtc::WG_MAX_GROUPS;
+  g.Cin = Cin; g.Cout = Cout;
+  g.groups = conv_tc_wgrad_groups(B, taps, Cin, Cout);
   rc = math == EEGCLIP_MATH_BF16 ? wgrad_tc_launch<1>(g, st) : wgrad_tc_launch<3>(g, st);
   if (rc != EEGCLIP_OK) return rc;
-  convtc::wgrad_reduce_kernel<<<(taps * 64 * 64 + 255) / 256, 256, 0, st>>>(partial, dw, g.groups, taps);
+  const long n = (long)taps * Cin * Cout;
+  convtc::wgrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, dw, g.groups, taps, Cin, Cout);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

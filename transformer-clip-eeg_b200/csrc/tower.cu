@@ -106,7 +106,7 @@ Scratch scratch_layout(const eegclip_tower_desc& d, float* base) {
   s.deeg = take(n * C);
   s.wtmp = take((size_t)C * C * d.taps);
   s.wgp = take(lintc::lin_wgrad_partial_bytes(256, 64) / sizeof(float));
-  s.tc = take(conv_tc_scratch_bytes(d.B, d.T, d.taps) / sizeof(float) + 64);
+  s.tc = take(conv_tc_scratch_bytes(d.B, d.T, d.taps, C, C) / sizeof(float) + 64);
   s.total = o;
   return s;
 }
@@ -215,7 +215,7 @@ int conv_block_fwd(int math, const float* xin, const float* skip_in, const ConvP
                    cudaStream_t st) {
   const int PL = (taps - 1) / 2;
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
-    TRY(conv_tc_forward(math, xin, skip_in, p.w, p.b, y, B, T, taps, PL, drop, tcs, st));
+    TRY(conv_tc_forward(math, xin, skip_in, p.w, p.b, y, B, T, Cin, Cout, taps, PL, drop, tcs, st));
   } else {
     TRY(pad_add(xin, skip_in, upad, B, T, Cin, PL, taps, st));
     TRY(conv_fwd_f32(upad, p.w, p.b, y, B, T, Cin, Cout, taps, drop, st));
@@ -235,7 +235,7 @@ int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP
                     drop, st));
   TRY(colsum(dypad, gr.b, (long)B * TP, Cout, Cout, st));
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
-    TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, taps, PLb, du, gr.w, B, T, tcs, st));
+    TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, Cin, Cout, taps, PLb, du, gr.w, B, T, tcs, st));
   } else {
     TRY(pad_add(xin, skip_in, upad, B, T, Cin, PL, taps, st));
     CUDA_TRY(cudaMemsetAsync(wtmp, 0, (size_t)Cout * Cin * taps * sizeof(float), st));
@@ -601,7 +601,7 @@ int eegclip_convblock_workspace(const eegclip_convblock_desc* d, size_t* save_by
   if (save_bytes) *save_bytes = (n * d->Cout + align_up((size_t)2 * d->B, 4)) * sizeof(float);
   if (scratch_bytes)
     *scratch_bytes = (align_up((size_t)d->B * TP * d->Cin, 64) + align_up((size_t)d->B * TP * d->Cout, 64) +
-                      align_up((size_t)d->Cout * d->Cin * d->taps, 64)) * sizeof(float) + conv_tc_scratch_bytes(d->B, d->T, d->taps) + 256;
+                      align_up((size_t)d->Cout * d->Cin * d->taps, 64)) * sizeof(float) + conv_tc_scratch_bytes(d->B, d->T, d->taps, d->Cin, d->Cout) + 256;
   return EEGCLIP_OK;
 }
 
