@@ -13,8 +13,10 @@ x = torch.randn(B, T, 64, device=dev); skip = torch.randn(B, T, 64, device=dev)
 for _ in range(3):
     blk.forward_time_major(x, skip)
 modes = [int(m) for m in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
-for mode in modes:     # bit 0: last tile as M=128; bit 1: no weight re-fetch (timing only); bit 2: no lo.hi MMA (timing only)
+ss_list = [int(m) for m in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0]   # 1 = TS-form kernel (g_tune[6])
+for ss, mode in [(q, m) for q in ss_list for m in modes]:     # mode: unused (the exp_mode experiments are recorded in conv_tc.cuh)
     _lib.call("eegclip_tune_set", 5, mode)
+    _lib.call("eegclip_tune_set", 6, ss)
     dbg = torch.zeros(768, dtype=torch.int64, device=dev)
     blk.forward_time_major(x, skip)
     _lib.call("eegclip_debug_buffer", dbg.data_ptr())
@@ -24,5 +26,6 @@ for mode in modes:     # bit 0: last tile as M=128; bit 1: no weight re-fetch (t
     _lib.call("eegclip_debug_buffer", None)
     d = dbg.cpu()
     t = [int(d[i]) - int(d[0]) for i in range(4)]
-    print(f"exp_mode {mode}: conv block fwd (pack + conv + LN) {e0.elapsed_time(e1) * 1e3:.1f} us; CTA0: staged {t[1] / 1e3:.2f} us, mma done {t[2] / 1e3:.2f} us, end {t[3] / 1e3:.2f} us")
+    print(f"{'TS' if ss else 'SS'} exp_mode {mode}: conv block fwd (pack + conv + LN) {e0.elapsed_time(e1) * 1e3:.1f} us; CTA0: staged {t[1] / 1e3:.2f} us, mma done {t[2] / 1e3:.2f} us, end {t[3] / 1e3:.2f} us")
 _lib.call("eegclip_tune_set", 5, 0)
+_lib.call("eegclip_tune_set", 6, 0)

@@ -77,7 +77,6 @@ struct ConvTcArgs {
   int taps;               // kernel size
   Drop drop;
   unsigned long long* dbg; // development timeline (CTA 0): start, staged, mma-done, end (globaltimer ns)
-  int exp_mode;            // development experiments (g_tune[5]); 0 = shipped path
 };
 
 __host__ __device__ inline uint32_t conv_smem_bytes(int T, int taps) {
@@ -103,7 +102,7 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
 
   const int ntiles = (T + 127) >> 7;
-  const bool last64 = (T & 127) != 0 && !(a.exp_mode & 1);   // T % 128 == 64 -> last tile has M = 64 (exp bit 0: run it as M = 128 over-read)
+  const bool last64 = (T & 127) != 0;       // T % 128 == 64 -> last tile has M = 64
   constexpr uint32_t TCOLS = NTERMS > 1 ? 128u : 64u;   // TMEM columns per time tile: [hi.hi + lo.hi | hi.lo]
   uint32_t ncols = 64;
   while (ncols < (uint32_t)ntiles * TCOLS) ncols <<= 1;
@@ -183,7 +182,6 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
       const int s = (g0 + tap) % NSTAGE;
       const uint32_t ph = ((g0 + tap) / NSTAGE) & 1;
       tc::mbar_wait(&empty[s], ph ^ 1);
-      if ((a.exp_mode & 2) && tap >= NSTAGE) { tc::mbar_arrive(&full[s]); continue; }   // timing experiment: no weight re-fetch
       tc::mbar_expect_tx(&full[s], bytes);
       tc::bulk_g2s(sB + s * W_TAP_BYTES, wblk + (long)tap * W_TAP_BYTES, bytes, &full[s]);
     }
@@ -202,45 +200,25 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
       const uint32_t wb = sB_u + s * W_TAP_BYTES;
       const uint64_t b_w = tc::smem_desc(wb, 2 * CH * 16, 128);   // chunk stride 2048 B: rows 0-63 hi, 64-127 lo
       if (tc::elect_one()) {
-        if (!(a.exp_mode & 8)) {  // shipped: tile-major issue order (measured 62.7 us vs 67.7 us per window for the K-step-major order below)
-          for (int tile = 0; tile < ntiles; ++tile) {
-            const bool m64 = last64 && tile == ntiles - 1;
-            const uint32_t idw = m64 ? idw64 : idw128, idn = m64 ? idn64 : idn128;
-            const uint32_t d = tmem + tile * TCOLS;
-            const uint32_t arow = sA_u + (uint32_t)(tile * 128 + tap) * 16u;
-            const uint64_t a_hi = tc::smem_desc(arow, CS, 128), a_lo = tc::smem_desc(arow + PS, CS, 128);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t da = (uint64_t)((2 * ks * CS) >> 4);           // start-address field is in 16-byte units
-              const uint64_t db = (uint64_t)((2 * ks * (2 * CH * 16)) >> 4);
-              if (NTERMS > 1) {
-                tc::mma_bf16(d, a_hi + da, b_w + db, idw, acc | (uint32_t)(ks != 0));   // [hi.hi | hi.lo]
-                if (!(a.exp_mode & 4)) tc::mma_bf16(d, a_lo + da, b_w + db, idn, 1);   // += lo.hi (first 64 columns)
-              } else {
-                tc::mma_bf16(d, a_hi + da, b_w + db, idn, acc | (uint32_t)(ks != 0));
-              }
-            }
-          }
-        } else {
-          // development (exp bit 3): K-step-major issue order, consecutive MMAs target different accumulators.  Not faster: the
-          // pipe is paced by the exposed shared-memory fetch of the A operand (M/4 cycles per instruction), not by accumulate
-          // dependencies -- measured cost per MMA = M/4 + max(M,128)*N/256 cycles
-          const int tap_a = (a.exp_mode & 16) ? 0 : (a.exp_mode & 32) ? (tap & ~7) : tap;   // timing experiments: aligned operand starts
-          const uint64_t a0 = tc::smem_desc(sA_u + (uint32_t)tap_a * 16u, CS, 128);
+        // Tile-major issue order.  Measured alternatives (tools/conv_timeline.py, 64 taps, T = 320, per window): K-step-major
+        // order (consecutive MMAs on different accumulators) 67.7 us vs 62.7 us here; operand starts aligned to 128 B instead
+        // of tap * 16 B: no change; no weight re-fetch: -2 us; without the lo.hi MMAs: -6 us.  The pipe is paced per
+        // instruction at ~21 + 0.63 * N cycles (M = 128, K = 16) in both the SS form used here and the TS form below.
+        for (int tile = 0; tile < ntiles; ++tile) {
+          const bool m64 = last64 && tile == ntiles - 1;
+          const uint32_t idw = m64 ? idw64 : idw128, idn = m64 ? idn64 : idn128;
+          const uint32_t d = tmem + tile * TCOLS;
+          const uint32_t arow = sA_u + (uint32_t)(tile * 128 + tap) * 16u;
+          const uint64_t a_hi = tc::smem_desc(arow, CS, 128), a_lo = tc::smem_desc(arow + PS, CS, 128);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t da = (uint64_t)((2 * ks * CS) >> 4);             // start-address field is in 16-byte units
+            const uint64_t da = (uint64_t)((2 * ks * CS) >> 4);           // start-address field is in 16-byte units
             const uint64_t db = (uint64_t)((2 * ks * (2 * CH * 16)) >> 4);
-            for (int tile = 0; tile < ntiles; ++tile) {
-              const bool m64 = last64 && tile == ntiles - 1;
-              tc::mma_bf16(tmem + tile * TCOLS, a0 + da + (uint64_t)(tile * 128), b_w + db, NTERMS > 1 ? (m64 ? idw64 : idw128) : (m64 ? idn64 : idn128),
-                           acc | (uint32_t)(ks != 0));                       // [hi.hi | hi.lo]
-            }
-            if (NTERMS > 1 && !(a.exp_mode & 4)) {
-              for (int tile = 0; tile < ntiles; ++tile) {
-                const bool m64 = last64 && tile == ntiles - 1;
-                tc::mma_bf16(tmem + tile * TCOLS, a0 + da + (uint64_t)(tile * 128 + (PS >> 4)), b_w + db, m64 ? idn64 : idn128, 1);   // += lo.hi
-              }
+            if (NTERMS > 1) {
+              tc::mma_bf16(d, a_hi + da, b_w + db, idw, acc | (uint32_t)(ks != 0));   // [hi.hi | hi.lo]
+              tc::mma_bf16(d, a_lo + da, b_w + db, idn, 1);                            // += lo.hi (first 64 columns)
+            } else {
+              tc::mma_bf16(d, a_hi + da, b_w + db, idn, acc | (uint32_t)(ks != 0));
             }
           }
         }
@@ -295,6 +273,237 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
   __syncthreads();
   stamp(3);
   if (warp == 2) tc::tmem_dealloc(tmem, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// "TS" forward / data gradient: operand roles swapped so that the WEIGHTS are the A operand and live in TMEM.
+//
+// Experiment (kept selectable, see conv_ts_selected): does a larger N per instruction / an A operand that is not fetched
+// from shared memory raise the pipe rate?  It does not -- see the measurement next to conv_ts_selected.
+// Here  D[(term, co)][t] = sum_k  Wstack[(term, co)][k] * X[t + tap][k] :
+//   A = Wstack = [W_hi ; W_lo] (M = 128 rows, K = 64 input channels per tap), written into a 4-slot TMEM ring (32 columns
+//       per tap: lane = row, column j = channels 2j, 2j+1) by four loader warps with tcgen05.st straight from the packed
+//       global copy -- no shared-memory weight ring at all;
+//   B = the resident activation tile, N = up to 256 TIME rows per instruction, the tap shift is still a +16 B descriptor
+//       offset; planes X_hi and X_lo are two instructions on the same accumulator, which makes this a 4-term product
+//       (hi.hi + lo.hi + hi.lo + lo.lo) at the price of 2 instructions per K-step: 128 cycles per 256 rows each.
+// Accumulators: lanes 0-63 = sum over W_hi rows, lanes 64-127 = sum over W_lo rows, T columns.  Epilogue: the two lane
+// halves are added through shared memory (the activation tile is dead by then), which also transposes to time-major so
+// that bias / Philox dropout / stores are the same 128-bit code as before.
+// ------------------------------------------------------------------------------------------------
+constexpr int TS_WCOL = 384;         // first TMEM column of the weight ring (accumulators use [0, T), T <= 384)
+constexpr int TS_SLOTS = 4;
+
+// Wstack packing: per (n block, k block, tap) 128 rows x 64 contraction channels bf16 (128 B per row): rows 0-63 hi, 64-127 lo
+__global__ void pack_conv_weights_ts_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int mode, int TAPS, int Cin, int Cout) {
+  const int nN = (mode == 0 ? Cout : Cin) / CH, nK = (mode == 0 ? Cin : Cout) / CH;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over blocks * taps * 64 n * 8 chunks
+  if (i >= (long)nN * nK * TAPS * CH * 8) return;
+  const int ch = i & 7, n = (i >> 3) & 63;
+  const long rest = i >> 9;
+  const int tap = rest % TAPS;
+  const int blk = rest / TAPS, kb = blk % nK, nb = blk / nK;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int kk = kb * CH + ch * 8 + e, nn = nb * CH + n;
+    v[e] = mode == 0 ? W[((long)nn * Cin + kk) * TAPS + tap] : W[((long)kk * Cin + nn) * TAPS + (TAPS - 1 - tap)];
+  }
+  uint4 hi, lo;
+  tc::split8(v, hi, lo);
+  uint8_t* base = out + ((long)blk * TAPS + tap) * W_TAP_BYTES + n * 128 + ch * 16;
+  *reinterpret_cast<uint4*>(base) = hi;
+  *reinterpret_cast<uint4*>(base + CH * 128) = lo;
+}
+
+__host__ __device__ inline uint32_t conv_ts_smem_bytes(int T, int taps) {
+  uint32_t TP = T + taps - 1;
+  return 2u * 8u * TP * 16u + 128;
+}
+
+template <int NTERMS>
+__global__ void __launch_bounds__(256, 1) conv64_ts_kernel(const ConvTcArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x, nb = blockIdx.y;
+  const int nkb = a.src_ld / CH;
+  const int T = a.T, TAPS = a.taps, TP = T + TAPS - 1;
+  const uint32_t CS = (uint32_t)TP * 16u;   // chunk stride (bytes)
+  const uint32_t PS = 8u * CS;              // plane stride
+  uint8_t* sA = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2u * PS);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + TS_SLOTS;
+  uint64_t* accfull = bars + 2 * TS_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TS_SLOTS + 1);
+
+  auto stamp = [&](int slot) {
+    if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 128) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.dbg[slot] = t;
+    }
+  };
+  stamp(0);
+  if (tid == 0) {
+    for (int i = 0; i < TS_SLOTS; ++i) { tc::mbar_init(&full[i], 4); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(accfull, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
+  uint32_t tmem = 0;
+
+  for (int kb = 0; kb < nkb; ++kb) {
+    // ---- stage the activation tile: fp32 (+skip) -> bf16 hi/lo, chunk-major, zero padded (loads issued STAGE_U deep) ----
+    {
+      const int ld = a.src_ld;
+      const float* sb = a.src + (long)b * a.src_rows * ld + kb * CH;
+      const float* kp = a.skip ? a.skip + (long)b * a.src_rows * ld + kb * CH : nullptr;
+      constexpr int STAGE_U = 6;
+      const int total = TP * 8;
+      for (int base = 0; base < total; base += 256 * STAGE_U) {
+        float4 x[STAGE_U][2], y[STAGE_U][2];
+#pragma unroll
+        for (int u = 0; u < STAGE_U; ++u) {
+          const int idx = base + u * 256 + tid;
+          const int r = idx >> 3, ch = idx & 7;
+          const int t = r - a.row_off;
+          x[u][0] = x[u][1] = y[u][0] = y[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < total && t >= 0 && t < a.src_rows) {
+            const float4* p = reinterpret_cast<const float4*>(sb + (long)t * ld + ch * 8);
+            x[u][0] = __ldg(p); x[u][1] = __ldg(p + 1);
+            if (kp) {
+              const float4* q = reinterpret_cast<const float4*>(kp + (long)t * ld + ch * 8);
+              y[u][0] = __ldg(q); y[u][1] = __ldg(q + 1);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < STAGE_U; ++u) {
+          const int idx = base + u * 256 + tid;
+          if (idx < total) {
+            const int r = idx >> 3, ch = idx & 7;
+            const float v[8] = {x[u][0].x + y[u][0].x, x[u][0].y + y[u][0].y, x[u][0].z + y[u][0].z, x[u][0].w + y[u][0].w,
+                                x[u][1].x + y[u][1].x, x[u][1].y + y[u][1].y, x[u][1].z + y[u][1].z, x[u][1].w + y[u][1].w};
+            uint4 hi, lo;
+            tc::split8(v, hi, lo);
+            uint8_t* d = sA + ch * CS + r * 16;
+            *reinterpret_cast<uint4*>(d) = hi;
+            if (NTERMS > 1) *reinterpret_cast<uint4*>(d + PS) = lo;
+          }
+        }
+      }
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    tmem = *tmem_slot;
+    if (kb == 0) stamp(1);
+    const uint8_t* wblk = a.wpacked + ((long)nb * nkb + kb) * TAPS * W_TAP_BYTES;
+    const int g0 = kb * TAPS;               // global tap counter of this block's first tap (ring slot / phase bookkeeping)
+
+    if (warp >= 4) {
+      // ===== weight loaders: this thread owns Wstack row 32*(warp-4)+lane; 128 B per tap: global -> registers -> TMEM ring =====
+      const int row = (warp - 4) * 32 + lane;
+      const uint4* src = reinterpret_cast<const uint4*>(wblk + row * 128);
+      uint4 cur[8], nxt[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[j] = __ldg(src + j);
+      for (int tap = 0; tap < TAPS; ++tap) {
+        if (tap + 1 < TAPS) {
+          const uint4* sn = src + (long)(tap + 1) * (W_TAP_BYTES / 16);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) nxt[j] = __ldg(sn + j);
+        }
+        const int s = (g0 + tap) % TS_SLOTS;
+        const uint32_t ph = ((g0 + tap) / TS_SLOTS) & 1;
+        tc::mbar_wait(&empty[s], ph ^ 1);
+        tc::tc_fence_after();
+        tc::tmem_st32(tmem + ((uint32_t)((warp - 4) * 32) << 16) + TS_WCOL + s * 32, reinterpret_cast<const uint32_t*>(cur));
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&full[s]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+      }
+    } else if (warp == 1) {
+      // ===== MMA issuer (whole warp converged, one elected lane issues) =====
+      const uint32_t sA_u = tc::smem_u32(sA);
+      const int nt = (T + 255) >> 8;
+      const int nlast = T - (nt - 1) * 256;                      // 64 .. 256, multiple of 64
+      const uint32_t id256 = tc::idesc_bf16(128, 256, 0, 0), idlast = tc::idesc_bf16(128, nlast, 0, 0);
+      for (int tap = 0; tap < TAPS; ++tap) {
+        const int s = (g0 + tap) % TS_SLOTS;
+        const uint32_t ph = ((g0 + tap) / TS_SLOTS) & 1;
+        const uint32_t acc = (uint32_t)((kb | tap) != 0);
+        tc::mbar_wait(&full[s], ph);
+        tc::tc_fence_after();
+        const uint32_t wa = tmem + TS_WCOL + s * 32;
+        if (tc::elect_one()) {
+          for (int tile = 0; tile < nt; ++tile) {
+            const uint32_t idn = tile == nt - 1 ? idlast : id256;
+            const uint32_t d = tmem + tile * 256;
+            const uint64_t b_hi = tc::smem_desc(sA_u + (uint32_t)(tile * 256 + tap) * 16u, CS, 128);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t db = (uint64_t)((2 * ks * CS) >> 4);   // start-address field is in 16-byte units
+              tc::mma_bf16_ts(d, wa + ks * 8, b_hi + db, idn, acc | (uint32_t)(ks != 0));
+              if (NTERMS > 1) tc::mma_bf16_ts(d, wa + ks * 8, b_hi + db + (uint64_t)(PS >> 4), idn, 1);
+            }
+          }
+          tc::tc_commit(&empty[s]);
+        }
+        __syncwarp();
+      }
+      if (tc::elect_one()) tc::tc_commit(accfull);
+      __syncwarp();
+    }
+    __syncwarp();
+    // every MMA that reads this input block's tile / the weight ring has completed
+    tc::mbar_wait(accfull, (uint32_t)(kb & 1));
+    tc::tc_fence_after();
+  }  // kb
+  stamp(2);
+  // ===== epilogue: add the W_hi and W_lo lane halves through shared memory, transposed to S[t][co] =====
+  float* S = reinterpret_cast<float*>(sA);
+  {
+    const int q = warp & 3, hsel = warp >> 2;          // TMEM lane quarter; column half of this warp
+    const int c_begin = hsel * (T >> 1), c_end = c_begin + (T >> 1);   // T/2 is a multiple of 32
+    const int co = (q & 1) * 32 + lane;
+    if (q >= 2) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) S[(c0 + j) * CH + co] = v[j];
+      }
+    }
+    __syncthreads();
+    if (q < 2) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) S[(c0 + j) * CH + co] += v[j];
+      }
+    }
+    __syncthreads();
+    const int c4 = tid & 15;
+    const float4 bb = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + nb * CH) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = tid >> 4; t < T; t += 16) {
+      float4 r = *reinterpret_cast<const float4*>(S + t * CH + c4 * 4);
+      r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+      const uint64_t didx = ((uint64_t)b * T + t) * a.out_ld + nb * CH + c4 * 4;
+      const float4 m = drop_mult4(a.drop, didx);
+      r.x *= m.x; r.y *= m.y; r.z *= m.z; r.w *= m.w;
+      *reinterpret_cast<float4*>(a.out + ((long)b * T + t) * a.out_ld + nb * CH + c4 * 4) = r;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  stamp(3);
+  if (warp == 2) tc::tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -478,8 +687,30 @@ inline size_t conv_tc_scratch_bytes(int B, int T, int taps, int Cin, int Cout) {
          (size_t)conv_tc_wgrad_groups(B, taps, Cin, Cout) * taps * Cin * Cout * sizeof(float) + 256;
 }
 
+// The TS kernel (T <= 384: accumulator columns + the 128-column weight ring) is selected with g_tune[6] = 1.  It is parity-
+// tested but NOT the shipped path: measured per window 63.4 us of MMA time against 60.9 us for the SS kernel -- both forms run
+// at ~21 + 0.63 N cycles per instruction (M = 128, K = 16), i.e. the pipe's real column rate, and the 4-term TS product
+// issues 640 accumulator columns per (tap, K-step) against 576 for the 3-term SS product.
+inline bool conv_ts_selected(int T) { return T <= convtc::TS_WCOL && g_tune[6] == 1; }
+
+template <int NTERMS>
+inline int conv_ts_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
+  static bool configured = false;
+  uint32_t smem = convtc::conv_ts_smem_bytes(a.T, a.taps);
+  if (!configured) {
+    if (cudaFuncSetAttribute(convtc::conv64_ts_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return EEGCLIP_ERR_CUDA;
+    configured = true;
+  }
+  ProfScope prof(PROF_CONV_TC, st);
+  convtc::conv64_ts_kernel<NTERMS><<<dim3(B, a.out_ld / convtc::CH), 256, smem, st>>>(a);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
 template <int NTERMS>
 inline int conv_tc_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
+  if (conv_ts_selected(a.T)) return conv_ts_launch<NTERMS>(a, B, st);
   static bool configured = false;
   uint32_t smem = convtc::conv_smem_bytes(a.T, a.taps);
   if (!configured) {
@@ -493,9 +724,10 @@ inline int conv_tc_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
   return EEGCLIP_OK;
 }
 
-inline int conv_tc_pack(const float* w, uint8_t* wp, int mode, int taps, int Cin, int Cout, cudaStream_t st) {
+inline int conv_tc_pack(const float* w, uint8_t* wp, int mode, int taps, int Cin, int Cout, int T, cudaStream_t st) {
   const long n = (long)(Cin / 64) * (Cout / 64) * taps * 8 * 64;
-  convtc::pack_conv_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, wp, mode, taps, Cin, Cout);
+  if (conv_ts_selected(T)) convtc::pack_conv_weights_ts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, wp, mode, taps, Cin, Cout);
+  else convtc::pack_conv_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, wp, mode, taps, Cin, Cout);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -503,10 +735,10 @@ inline int conv_tc_pack(const float* w, uint8_t* wp, int mode, int taps, int Cin
 inline int conv_tc_forward(int math, const float* xin, const float* skip_in, const float* w, const float* bias, float* y, int B, int T,
                            int Cin, int Cout, int taps, int PL, const Drop& drop, void* scratch, cudaStream_t st) {
   uint8_t* wp = (uint8_t*)scratch;
-  { int prc = conv_tc_pack(w, wp, 0, taps, Cin, Cout, st); if (prc != EEGCLIP_OK) return prc; }
+  { int prc = conv_tc_pack(w, wp, 0, taps, Cin, Cout, T, st); if (prc != EEGCLIP_OK) return prc; }
   convtc::ConvTcArgs a;
   a.src = xin; a.skip = skip_in; a.wpacked = wp; a.bias = bias; a.out = y; a.src_ld = Cin; a.out_ld = Cout;
-  a.T = T; a.src_rows = T; a.row_off = PL; a.taps = taps; a.drop = drop; a.dbg = g_dbg_buf; a.exp_mode = g_tune[5];
+  a.T = T; a.src_rows = T; a.row_off = PL; a.taps = taps; a.drop = drop; a.dbg = g_dbg_buf;
   return math == EEGCLIP_MATH_BF16 ? conv_tc_launch<1>(a, B, st) : conv_tc_launch<3>(a, B, st);
 }
 
@@ -532,10 +764,10 @@ inline int conv_tc_backward(int math, const float* xin, const float* skip_in, co
   const size_t blocks = (size_t)(Cin / 64) * (Cout / 64);
   float* partial = (float*)(wp + align_up(blocks * taps * convtc::W_TAP_BYTES, 256));
   const int TP = T + taps - 1;
-  { int prc = conv_tc_pack(w, wp, 1, taps, Cin, Cout, st); if (prc != EEGCLIP_OK) return prc; }
+  { int prc = conv_tc_pack(w, wp, 1, taps, Cin, Cout, T, st); if (prc != EEGCLIP_OK) return prc; }
   convtc::ConvTcArgs a;
   a.src = dypad; a.skip = nullptr; a.wpacked = wp; a.bias = nullptr; a.out = du; a.src_ld = Cout; a.out_ld = Cin;
-  a.T = T; a.src_rows = TP; a.row_off = 0; a.taps = taps; a.dbg = g_dbg_buf; a.exp_mode = g_tune[5];
+  a.T = T; a.src_rows = TP; a.row_off = 0; a.taps = taps; a.dbg = g_dbg_buf;
   a.drop = make_drop(0, 0, 0, 0.f, 0);
   int rc = math == EEGCLIP_MATH_BF16 ? conv_tc_launch<1>(a, B, st) : conv_tc_launch<3>(a, B, st);
   if (rc != EEGCLIP_OK) return rc;

@@ -96,8 +96,68 @@ inline int gelu_drop(const float* pre, float* out, long n, const Drop& d, cudaSt
 //   gamma : (C,T) reference layout (channel-major)
 //   out   : act(gamma*xhat+beta) + skip
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) ln_ct_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, const float* __restrict__ skip,
+// (C,T) -> (T,C) copies of the affine parameters: the activations are time-major, the checkpoint layout of the LayerNorm([C,T])
+// affine is channel-major; reading it in place costs 32 sectors per warp load (measured: the LN kernels ran at 1.2-1.9 TB/s).
+// One 164 KB transpose per block and direction makes every parameter access a coalesced float4.
+constexpr int LNCT_GROUPS = 32;      // sample groups of the backward apply pass (affine-gradient partials per group)
+inline size_t ln_ct_scratch_floats(int T, int C) { return (size_t)(2 + 2 * LNCT_GROUPS) * T * C; }
+
+__global__ void __launch_bounds__(256) ct_transpose2_kernel(const float* __restrict__ g, const float* __restrict__ b,
+                                                           float* __restrict__ gT, float* __restrict__ bT, int C, int T) {
+  __shared__ float tile[2][32][33];
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, t = t0 + tx;
+    if (c < C && t < T) { tile[0][r][tx] = g[(long)c * T + t]; tile[1][r][tx] = b[(long)c * T + t]; }
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, c = c0 + tx;
+    if (c < C && t < T) { gT[(long)t * C + c] = tile[0][tx][r]; bT[(long)t * C + c] = tile[1][tx][r]; }
+  }
+}
+
+// dgamma[c][t] += sum_g part[g][0][t][c],  dbeta[c][t] += sum_g part[g][1][t][c]   (fixed order: deterministic)
+// grid (T/8, C/32), block 256: thread (c = tid & 31, t = tid >> 5) sums its element over the groups with the loads unrolled
+// (independent, coalesced), the 8 x 32 tile is transposed through shared memory for the (C,T) write.
+__global__ void __launch_bounds__(256) ct_reduce_transpose_kernel(const float* __restrict__ part, float* __restrict__ dgamma,
+                                                                 float* __restrict__ dbeta, int groups, int C, int T) {
+  __shared__ float tile[2][8][33];
+  const int t0 = blockIdx.x * 8, c0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long n = (long)T * C;
+  {
+    const int t = t0 + ty, c = c0 + tx;
+    float sg = 0.f, sb = 0.f;
+    if (c < C && t < T) {
+      const float* p0 = part + (long)t * C + c;
+#pragma unroll 8
+      for (int g = 0; g < groups; ++g) {
+        sg += __ldg(p0 + (long)(2 * g) * n);
+        sb += __ldg(p0 + (long)(2 * g + 1) * n);
+      }
+    }
+    tile[0][ty][tx] = sg; tile[1][ty][tx] = sb;
+  }
+  __syncthreads();
+  {
+    const int c = c0 + (threadIdx.x >> 3), t = t0 + (threadIdx.x & 7);
+    if (c < C && t < T) {
+      dgamma[(long)c * T + t] += tile[0][threadIdx.x & 7][threadIdx.x >> 3];
+      dbeta[(long)c * T + t] += tile[1][threadIdx.x & 7][threadIdx.x >> 3];
+    }
+  }
+}
+
+inline int ct_transpose2(const float* g, const float* b, float* gT, float* bT, int C, int T, cudaStream_t st) {
+  dim3 grid((T + 31) / 32, (C + 31) / 32);
+  ct_transpose2_kernel<<<grid, 256, 0, st>>>(g, b, gT, bT, C, T);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
+// gT / bT: (T,C) transposed affine (see above)
+__global__ void __launch_bounds__(512) ln_ct_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gT,
+                                                           const float* __restrict__ bT, const float* __restrict__ skip,
                                                            float* __restrict__ out, float* __restrict__ stats, int T, int C,
                                                            int act, float eps) {
   __shared__ float2 sh[33];
@@ -112,7 +172,6 @@ __global__ void __launch_bounds__(512) ln_ct_act_fwd_kernel(const float* __restr
   }
   float2 r = block_sum2(s, ss, sh);
   float mean = r.x / (float)n;
-  float var = fmaxf(r.y / (float)n - mean * mean, 0.f);
   // second, numerically safer pass for the variance (values are L1/L2 resident)
   float sq = 0.f;
   for (long i = threadIdx.x * 4L; i < n; i += blockDim.x * 4L) {
@@ -121,30 +180,87 @@ __global__ void __launch_bounds__(512) ln_ct_act_fwd_kernel(const float* __restr
     sq += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
   }
   r = block_sum2(sq, 0.f, sh);
-  var = r.x / (float)n;
-  float rstd = rsqrtf(var + eps);
+  const float var = r.x / (float)n;
+  const float rstd = rsqrtf(var + eps);
   if (threadIdx.x == 0) { stats[2 * b] = mean; stats[2 * b + 1] = rstd; }
   const float* sb = skip ? skip + b * n : nullptr;
   float* ob = out + b * n;
   for (long i = threadIdx.x * 4L; i < n; i += blockDim.x * 4L) {
-    int t = (int)(i / C), c = (int)(i - (long)t * C);
-    float4 v = *reinterpret_cast<const float4*>(yb + i);
-    float vv[4] = {v.x, v.y, v.z, v.w};
-    float o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float g = __ldg(gamma + (long)(c + j) * T + t), be = __ldg(beta + (long)(c + j) * T + t);
-      o[j] = act_f((vv[j] - mean) * rstd * g + be, act);
-    }
-    if (sb) { float4 k = *reinterpret_cast<const float4*>(sb + i); o[0] += k.x; o[1] += k.y; o[2] += k.z; o[3] += k.w; }
-    *reinterpret_cast<float4*>(ob + i) = make_float4(o[0], o[1], o[2], o[3]);
+    const float4 v = *reinterpret_cast<const float4*>(yb + i);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gT + i)), be = __ldg(reinterpret_cast<const float4*>(bT + i));
+    float4 o;
+    o.x = act_f((v.x - mean) * rstd * g.x + be.x, act);
+    o.y = act_f((v.y - mean) * rstd * g.y + be.y, act);
+    o.z = act_f((v.z - mean) * rstd * g.z + be.z, act);
+    o.w = act_f((v.w - mean) * rstd * g.w + be.w, act);
+    if (sb) { const float4 k = *reinterpret_cast<const float4*>(sb + i); o.x += k.x; o.y += k.y; o.z += k.z; o.w += k.w; }
+    *reinterpret_cast<float4*>(ob + i) = o;
   }
 }
 
+// Register-resident variant for samples of up to 512 * 4 * NV floats (T = 320, C = 64: NV = 10): every thread issues all of its
+// loads up front (NV independent 128-bit loads in flight per thread), keeps its slice in registers for the mean, the centred
+// variance and the normalise pass -- one HBM read of y instead of one HBM + two L2 passes with a load-use chain per iteration.
+template <int NV>
+__global__ void __launch_bounds__(512) ln_ct_act_fwd_reg_kernel(const float* __restrict__ y, const float* __restrict__ gT,
+                                                               const float* __restrict__ bT, const float* __restrict__ skip,
+                                                               float* __restrict__ out, float* __restrict__ stats, int T, int C,
+                                                               int act, float eps) {
+  __shared__ float2 sh[33];
+  const int b = blockIdx.x;
+  const int n = T * C;
+  const float* yb = y + (long)b * n;
+  float4 v[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = (k * 512 + threadIdx.x) * 4;
+    v[k] = i < n ? *reinterpret_cast<const float4*>(yb + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  float2 r = block_sum2(s, 0.f, sh);
+  const float mean = r.x / (float)n;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = (k * 512 + threadIdx.x) * 4;
+    if (i < n) {
+      const float a0 = v[k].x - mean, a1 = v[k].y - mean, a2 = v[k].z - mean, a3 = v[k].w - mean;
+      sq += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+    }
+  }
+  r = block_sum2(sq, 0.f, sh);
+  const float rstd = rsqrtf(r.x / (float)n + eps);
+  if (threadIdx.x == 0) { stats[2 * b] = mean; stats[2 * b + 1] = rstd; }
+  const float* sb = skip ? skip + (long)b * n : nullptr;
+  float* ob = out + (long)b * n;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = (k * 512 + threadIdx.x) * 4;
+    if (i < n) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gT + i)), be = __ldg(reinterpret_cast<const float4*>(bT + i));
+      float4 o;
+      o.x = act_f((v[k].x - mean) * rstd * g.x + be.x, act);
+      o.y = act_f((v[k].y - mean) * rstd * g.y + be.y, act);
+      o.z = act_f((v[k].z - mean) * rstd * g.z + be.z, act);
+      o.w = act_f((v[k].w - mean) * rstd * g.w + be.w, act);
+      if (sb) { const float4 kk = *reinterpret_cast<const float4*>(sb + i); o.x += kk.x; o.y += kk.y; o.z += kk.z; o.w += kk.w; }
+      *reinterpret_cast<float4*>(ob + i) = o;
+    }
+  }
+}
+
+// lnscr: ln_ct_scratch_floats(T, C) floats
 inline int ln_ct_act_fwd(const float* y, const float* gamma, const float* beta, const float* skip, float* out, float* stats,
-                         int B, int T, int C, int act, cudaStream_t st) {
+                         float* lnscr, int B, int T, int C, int act, cudaStream_t st) {
+  if (C & 3) return EEGCLIP_ERR_UNSUPPORTED;
   ProfScope prof(PROF_LNCT, st);
-  ln_ct_act_fwd_kernel<<<B, 512, 0, st>>>(y, gamma, beta, skip, out, stats, T, C, act, 1e-5f);
+  float* gT = lnscr;
+  float* bT = lnscr + (size_t)T * C;
+  { int rc = ct_transpose2(gamma, beta, gT, bT, C, T, st); if (rc != EEGCLIP_OK) return rc; }
+  if ((long)T * C <= 512L * 4 * 10) ln_ct_act_fwd_reg_kernel<10><<<B, 512, 0, st>>>(y, gT, bT, skip, out, stats, T, C, act, 1e-5f);
+  else ln_ct_act_fwd_kernel<<<B, 512, 0, st>>>(y, gT, bT, skip, out, stats, T, C, act, 1e-5f);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -155,10 +271,11 @@ inline int ln_ct_act_fwd(const float* y, const float* gamma, const float* beta, 
 // caller zeroes the buffer once), and accumulates dgamma/dbeta (C,T).
 //   pass 1 (one CTA per sample): the two per-sample means  m1 = mean(dxh), m2 = mean(dxh * xhat)
 //   pass 2 (thread = fixed (t, 8 channels), loop over a group of samples): dy, and dgamma/dbeta summed over the group in
-//          registers -> one atomic per (element, group) instead of one per (element, sample)
+//          registers -> one (T,C) partial per group, summed over the groups in fixed order and transposed by
+//          ct_reduce_transpose_kernel (deterministic, no atomics)
 __global__ void __launch_bounds__(512) ln_ct_bwd_stats_kernel(const float* __restrict__ dout, const float* __restrict__ y,
-                                                             const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, float* __restrict__ m12, int T, int C,
+                                                             const float* __restrict__ stats, const float* __restrict__ gT,
+                                                             const float* __restrict__ bT, float* __restrict__ m12, int T, int C,
                                                              int act) {
   __shared__ float2 sh[33];
   const int b = blockIdx.x;
@@ -167,17 +284,28 @@ __global__ void __launch_bounds__(512) ln_ct_bwd_stats_kernel(const float* __res
   const float* db = dout + b * n;
   const float mean = stats[2 * b], rstd = stats[2 * b + 1];
   float s1 = 0.f, s2 = 0.f;
-  for (long i = threadIdx.x * 4L; i < n; i += blockDim.x * 4L) {
-    const int t = (int)(i / C), c = (int)(i - (long)t * C);
-    const float4 v = *reinterpret_cast<const float4*>(yb + i);
-    const float4 d = *reinterpret_cast<const float4*>(db + i);
-    const float vv[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
+  constexpr int U = 1;                                   // (batching the loads of several iterations measured slower: 23.7 vs 15.4 us)
+  for (long base = 0; base < n; base += (long)U * blockDim.x * 4L) {
+    float4 v[U], d[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float g = __ldg(gamma + (long)(c + j) * T + t), be = __ldg(beta + (long)(c + j) * T + t);
-      const float xh = (vv[j] - mean) * rstd;
-      const float dxh = dd[j] * act_grad_f(xh * g + be, act) * g;
-      s1 += dxh; s2 += dxh * xh;
+    for (int k = 0; k < U; ++k) {
+      const long i = base + ((long)k * blockDim.x + threadIdx.x) * 4L;
+      if (i < n) { v[k] = *reinterpret_cast<const float4*>(yb + i); d[k] = *reinterpret_cast<const float4*>(db + i); }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const long i = base + ((long)k * blockDim.x + threadIdx.x) * 4L;
+      if (i < n) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gT + i)), b4 = __ldg(reinterpret_cast<const float4*>(bT + i));
+        const float vv[4] = {v[k].x, v[k].y, v[k].z, v[k].w}, dd[4] = {d[k].x, d[k].y, d[k].z, d[k].w};
+        const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xh = (vv[j] - mean) * rstd;
+          const float dxh = dd[j] * act_grad_f(xh * gg[j] + bb[j], act) * gg[j];
+          s1 += dxh; s2 += dxh * xh;
+        }
+      }
     }
   }
   const float2 r = block_sum2(s1, s2, sh);
@@ -187,20 +315,21 @@ __global__ void __launch_bounds__(512) ln_ct_bwd_stats_kernel(const float* __res
 // grid (T*C/8/256, groups), block 256; thread = (t, c8) position, samples b = group, group + groups, ...
 __global__ void __launch_bounds__(256) ln_ct_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y,
                                                              const float* __restrict__ stats, const float* __restrict__ m12,
-                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                             float* __restrict__ dypad, float* __restrict__ dgamma,
-                                                             float* __restrict__ dbeta, int B, int T, int C, int PL, int TP, int act,
-                                                             Drop drop) {
+                                                             const float* __restrict__ gT, const float* __restrict__ bT,
+                                                             float* __restrict__ dypad, float* __restrict__ part, int B, int T, int C,
+                                                             int PL, int TP, int act, Drop drop) {
   const long n = (long)T * C;
   const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
-  const int t = (int)(i / C), c = (int)(i - (long)t * C);
   float g[8], be[8], ag[8], ab[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    g[j] = __ldg(gamma + (long)(c + j) * T + t); be[j] = __ldg(beta + (long)(c + j) * T + t);
-    ag[j] = 0.f; ab[j] = 0.f;
+  {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gT + i)), g1 = __ldg(reinterpret_cast<const float4*>(gT + i) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bT + i)), b1 = __ldg(reinterpret_cast<const float4*>(bT + i) + 1);
+    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+    be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; }
   for (int b = blockIdx.y; b < B; b += gridDim.y) {
     const float mean = stats[2 * b], rstd = stats[2 * b + 1], m1 = m12[2 * b], m2 = m12[2 * b + 1];
     const float4* yp = reinterpret_cast<const float4*>(y + b * n + i);
@@ -221,25 +350,31 @@ __global__ void __launch_bounds__(256) ln_ct_bwd_apply_kernel(const float* __res
     op[0] = make_float4(o[0], o[1], o[2], o[3]);
     op[1] = make_float4(o[4], o[5], o[6], o[7]);
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(dgamma + (long)(c + j) * T + t, ag[j]);
-    atomicAdd(dbeta + (long)(c + j) * T + t, ab[j]);
-  }
+  float4* pg = reinterpret_cast<float4*>(part + (long)(2 * blockIdx.y) * n + i);
+  float4* pb = reinterpret_cast<float4*>(part + (long)(2 * blockIdx.y + 1) * n + i);
+  pg[0] = make_float4(ag[0], ag[1], ag[2], ag[3]); pg[1] = make_float4(ag[4], ag[5], ag[6], ag[7]);
+  pb[0] = make_float4(ab[0], ab[1], ab[2], ab[3]); pb[1] = make_float4(ab[4], ab[5], ab[6], ab[7]);
 }
 
-// m12: 2*B floats of scratch
+// m12: 2*B floats of scratch; lnscr: ln_ct_scratch_floats(T, C) floats
 inline int ln_ct_act_bwd(const float* dout, const float* y, const float* stats, const float* gamma, const float* beta,
-                         float* dypad, float* dgamma, float* dbeta, float* m12, int B, int T, int C, int PL, int taps, int act,
-                         const Drop& drop, cudaStream_t st) {
+                         float* dypad, float* dgamma, float* dbeta, float* m12, float* lnscr, int B, int T, int C, int PL, int taps,
+                         int act, const Drop& drop, cudaStream_t st) {
   if (C & 7) return EEGCLIP_ERR_UNSUPPORTED;
   ProfScope prof(PROF_LNCT, st);
-  ln_ct_bwd_stats_kernel<<<B, 512, 0, st>>>(dout, y, stats, gamma, beta, m12, T, C, act);
+  float* gT = lnscr;
+  float* bT = lnscr + (size_t)T * C;
+  float* part = lnscr + (size_t)2 * T * C;
+  { int rc = ct_transpose2(gamma, beta, gT, bT, C, T, st); if (rc != EEGCLIP_OK) return rc; }
+  ln_ct_bwd_stats_kernel<<<B, 512, 0, st>>>(dout, y, stats, gT, bT, m12, T, C, act);
   LAUNCH_CHECK();
   const long n8 = (long)T * C / 8;
-  const int groups = B < 32 ? B : 32;
+  const int groups = B < LNCT_GROUPS ? B : LNCT_GROUPS;
   dim3 grid((unsigned)((n8 + 255) / 256), groups);
-  ln_ct_bwd_apply_kernel<<<grid, 256, 0, st>>>(dout, y, stats, m12, gamma, beta, dypad, dgamma, dbeta, B, T, C, PL, T + taps - 1, act, drop);
+  ln_ct_bwd_apply_kernel<<<grid, 256, 0, st>>>(dout, y, stats, m12, gT, bT, dypad, part, B, T, C, PL, T + taps - 1, act, drop);
+  LAUNCH_CHECK();
+  dim3 g2((T + 7) / 8, (C + 31) / 32);
+  ct_reduce_transpose_kernel<<<g2, 256, 0, st>>>(part, dgamma, dbeta, groups, C, T);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

@@ -106,7 +106,7 @@ Scratch scratch_layout(const eegclip_tower_desc& d, float* base) {
   s.deeg = take(n * C);
   s.wtmp = take((size_t)C * C * d.taps);
   s.wgp = take(lintc::lin_wgrad_partial_bytes(256, 64) / sizeof(float));
-  s.tc = take(conv_tc_scratch_bytes(d.B, d.T, d.taps, C, C) / sizeof(float) + 64);
+  s.tc = take(align_up(ln_ct_scratch_floats(d.T, C), 64) + conv_tc_scratch_bytes(d.B, d.T, d.taps, C, C) / sizeof(float) + 64);
   s.total = o;
   return s;
 }
@@ -214,13 +214,15 @@ int conv_block_fwd(int math, const float* xin, const float* skip_in, const ConvP
                    float* out, float* upad, void* tcs, int B, int T, int Cin, int Cout, int taps, int act, const Drop& drop,
                    cudaStream_t st) {
   const int PL = (taps - 1) / 2;
+  float* lnscr = (float*)tcs;                      // scratch layout: [LN transposed affine + partials][conv tensor-core scratch]
+  tcs = lnscr + align_up(ln_ct_scratch_floats(T, Cout), 64);
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
     TRY(conv_tc_forward(math, xin, skip_in, p.w, p.b, y, B, T, Cin, Cout, taps, PL, drop, tcs, st));
   } else {
     TRY(pad_add(xin, skip_in, upad, B, T, Cin, PL, taps, st));
     TRY(conv_fwd_f32(upad, p.w, p.b, y, B, T, Cin, Cout, taps, drop, st));
   }
-  TRY(ln_ct_act_fwd(y, p.g, p.be, skip_out, out, stats, B, T, Cout, act, st));
+  TRY(ln_ct_act_fwd(y, p.g, p.be, skip_out, out, stats, lnscr, B, T, Cout, act, st));
   return EEGCLIP_OK;
 }
 
@@ -230,8 +232,10 @@ int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP
                    const float* stats, const float* dout, float* du, float* upad, float* dypad, float* wtmp, void* tcs, int B, int T,
                    int Cin, int Cout, int taps, int act, const Drop& drop, cudaStream_t st) {
   const int PL = (taps - 1) / 2, PLb = taps - 1 - PL, TP = T + taps - 1;
+  float* lnscr = (float*)tcs;
+  tcs = lnscr + align_up(ln_ct_scratch_floats(T, Cout), 64);
   CUDA_TRY(cudaMemsetAsync(dypad, 0, (size_t)B * TP * Cout * sizeof(float), st));
-  TRY(ln_ct_act_bwd(dout, y, stats, p.g, p.be, dypad, gr.g, gr.be, wtmp /* 2B floats of per-sample means */, B, T, Cout, PLb, taps, act,
+  TRY(ln_ct_act_bwd(dout, y, stats, p.g, p.be, dypad, gr.g, gr.be, wtmp /* 2B floats of per-sample means */, lnscr, B, T, Cout, PLb, taps, act,
                     drop, st));
   TRY(colsum(dypad, gr.b, (long)B * TP, Cout, Cout, st));
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
@@ -601,7 +605,8 @@ int eegclip_convblock_workspace(const eegclip_convblock_desc* d, size_t* save_by
   if (save_bytes) *save_bytes = (n * d->Cout + align_up((size_t)2 * d->B, 4)) * sizeof(float);
   if (scratch_bytes)
     *scratch_bytes = (align_up((size_t)d->B * TP * d->Cin, 64) + align_up((size_t)d->B * TP * d->Cout, 64) +
-                      align_up((size_t)d->Cout * d->Cin * d->taps, 64)) * sizeof(float) + conv_tc_scratch_bytes(d->B, d->T, d->taps, d->Cin, d->Cout) + 256;
+                      align_up((size_t)d->Cout * d->Cin * d->taps, 64)) * sizeof(float) + conv_tc_scratch_bytes(d->B, d->T, d->taps, d->Cin, d->Cout) +
+                      align_up(ln_ct_scratch_floats(d->T, d->Cout), 64) * sizeof(float) + 256;
   return EEGCLIP_OK;
 }
 
