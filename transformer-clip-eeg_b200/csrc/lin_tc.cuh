@@ -405,10 +405,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
           side[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (side_p && m < a.M) side[i] = *reinterpret_cast<const float4*>(side_p + m * a.ldc + n);
         }
+        // 1-bit dropout (p = 0.5, every dropout of the transformer block): one Philox call yields 128 decisions of ONE row, so
+        // lane l draws the word of row mrow0 + l for this 32-column block once and the coalesced phase fetches it by shuffle --
+        // one call per block and warp instead of one per float4 (32x redundant: the FFN1 epilogue was issue-bound on it)
+        const bool drop_fast = f_drop && a.drop.enabled && a.drop.onebit;
+        uint32_t wown = 0u;
+        if (drop_fast) {
+          const uint64_t idx0 = (uint64_t)(mrow0 + lane) * (uint64_t)N + (uint64_t)cb;
+          const uint4 w4 = drop_words(a.drop, idx0 >> 7);
+          wown = word_of(w4, (uint32_t)(idx0 >> 5) & 3u);
+        }
 #pragma unroll 2
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + rq;
           const long m = mrow0 + rl;
+          const uint32_t wrow = __shfl_sync(0xffffffffu, wown, rl);
           if (m < a.M) {
             float4 r = *reinterpret_cast<const float4*>(stg + rl * EPI_LD + cq);
             const long ci = m * a.ldc + n;
@@ -421,7 +432,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
               gelu_both(r.x, r.x, gd.x); gelu_both(r.y, r.y, gd.y); gelu_both(r.z, r.z, gd.z); gelu_both(r.w, r.w, gd.w);
             }
             if (f_drop) {
-              const float4 mk = drop_mult4(a.drop, (uint64_t)m * (uint64_t)N + (uint64_t)n);
+              float4 mk;
+              if (drop_fast) {
+                const uint32_t bits = wrow >> cq;
+                mk = make_float4(bits & 1u ? a.drop.scale : 0.f, bits & 2u ? a.drop.scale : 0.f, bits & 4u ? a.drop.scale : 0.f,
+                                 bits & 8u ? a.drop.scale : 0.f);
+              } else {
+                mk = drop_mult4(a.drop, (uint64_t)m * (uint64_t)N + (uint64_t)n);
+              }
               r.x *= mk.x; r.y *= mk.y; r.z *= mk.z; r.w *= mk.w;
               gd.x *= mk.x; gd.y *= mk.y; gd.z *= mk.z; gd.w *= mk.w;
             }
