@@ -13,6 +13,7 @@
 #include "attention_tc.cuh"
 #include "conv_tc.cuh"
 #include "lin_tc.cuh"
+#include "skinny.cuh"
 
 using namespace eegclip;
 
@@ -520,7 +521,8 @@ int eegclip_tower_forward(const eegclip_tower_desc* dp, const float* const* para
     }
   }
   const int fi = 2 + NP_CONV * d.n_conv + NP_XF * d.depth;
-  TRY(linear_f32(xin, C, params[fi], params[fi + 1], out, d.latent, n, d.latent, C, none, st));
+  if (d.math != EEGCLIP_MATH_FP32 && skinny::supported(d.latent, C)) TRY(skinny::fwd(xin, params[fi], params[fi + 1], out, n, d.latent, st));
+  else TRY(linear_f32(xin, C, params[fi], params[fi + 1], out, d.latent, n, d.latent, C, none, st));
   return EEGCLIP_OK;
 }
 
@@ -544,11 +546,16 @@ int eegclip_tower_backward(const eegclip_tower_desc* dp, const float* const* par
   if (d.depth > 0) xlast = xf_save(save, L, d.depth - 1).zout;
   else if (d.n_conv > 0) xlast = save + L.conv0 + L.conv_stride * (d.n_conv - 1) + L.c_out;
 
-  TRY(colsum(dout, grads[fi + 1], n, d.latent, d.latent, st));
-  TRY(linear_wgrad_f32(dout, d.latent, xlast, C, grads[fi], n, d.latent, C, st));
   float* dz = w.dza;
   float* dz2 = w.dzb;
-  TRY(linear_dgrad_f32(dout, d.latent, params[fi], dz, C, n, d.latent, C, none, st));
+  if (d.math != EEGCLIP_MATH_FP32 && skinny::supported(d.latent, C)) {
+    TRY(skinny::wgrad(dout, xlast, grads[fi], grads[fi + 1], w.wgp, n, d.latent, st));
+    TRY(skinny::dgrad(dout, params[fi], dz, n, d.latent, st));
+  } else {
+    TRY(colsum(dout, grads[fi + 1], n, d.latent, d.latent, st));
+    TRY(linear_wgrad_f32(dout, d.latent, xlast, C, grads[fi], n, d.latent, C, st));
+    TRY(linear_dgrad_f32(dout, d.latent, params[fi], dz, C, n, d.latent, C, none, st));
+  }
   CUDA_TRY(cudaMemsetAsync(w.deeg, 0, (size_t)n * C * sizeof(float), st));
 
   if (d.kind == EEGCLIP_TOWER_INTERLEAVED) {
