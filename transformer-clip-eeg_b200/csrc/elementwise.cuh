@@ -421,29 +421,67 @@ __global__ void __launch_bounds__(256) ln64_bwd_kernel(const float* __restrict__
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
   long r0 = (long)blockIdx.x * rows_per_cta;
   long r1 = min(rows, r0 + rows_per_cta);
-  for (long row = r0 + grp; row < r1; row += 16) {
-    float4 v = reinterpret_cast<const float4*>(x + row * 64)[l];
-    float4 d = reinterpret_cast<const float4*>(dh + row * 64)[l];
-    float s = v.x + v.y + v.z + v.w;
+  // R rows per iteration: their loads are issued together and the four 16-lane shuffle reductions of each row interleave
+  // (one row at a time left the loop latency-bound on its 16 dependent shuffles)
+  constexpr int R = 4;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long it0 = r0; it0 < r1; it0 += 16 * R) {       // CTA-uniform trip count: the shuffles below use the full mask
+    const long rowb = it0 + grp;
+    float4 v[R], d[R], rr[R];
+    bool ok[R];
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
-    float mean = s * (1.f / 64.f);
-    float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
-    float q = a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+    for (int u = 0; u < R; ++u) {
+      const long row = rowb + 16 * u;
+      ok[u] = row < r1;
+      v[u] = ok[u] ? reinterpret_cast<const float4*>(x + row * 64)[l] : z4;
+      d[u] = ok[u] ? reinterpret_cast<const float4*>(dh + row * 64)[l] : z4;
+      rr[u] = (ok[u] && resid) ? reinterpret_cast<const float4*>(resid + row * 64)[l] : z4;
+    }
+    float s[R], q[R], s1[R], s2[R];
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o, 16);
-    float rstd = rsqrtf(q * (1.f / 64.f) + 1e-5f);
-    float x0 = a0 * rstd, x1 = a1 * rstd, x2 = a2 * rstd, x3 = a3 * rstd;
-    ag.x += d.x * x0; ag.y += d.y * x1; ag.z += d.z * x2; ag.w += d.w * x3;
-    ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
-    float e0 = d.x * gg.x, e1 = d.y * gg.y, e2 = d.z * gg.z, e3 = d.w * gg.w;
-    float s1 = e0 + e1 + e2 + e3, s2 = e0 * x0 + e1 * x1 + e2 * x2 + e3 * x3;
+    for (int u = 0; u < R; ++u) s[u] = v[u].x + v[u].y + v[u].z + v[u].w;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o, 16); s2 += __shfl_xor_sync(0xffffffffu, s2, o, 16); }
-    s1 *= (1.f / 64.f); s2 *= (1.f / 64.f);
-    float4 o4 = make_float4(rstd * (e0 - s1 - x0 * s2), rstd * (e1 - s1 - x1 * s2), rstd * (e2 - s1 - x2 * s2), rstd * (e3 - s1 - x3 * s2));
-    if (resid) { float4 rr = reinterpret_cast<const float4*>(resid + row * 64)[l]; o4.x += rr.x; o4.y += rr.y; o4.z += rr.z; o4.w += rr.w; }
-    reinterpret_cast<float4*>(dx + row * 64)[l] = o4;
+    for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < R; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o, 16);
+    float a[R][4];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const float mean = s[u] * (1.f / 64.f);
+      a[u][0] = v[u].x - mean; a[u][1] = v[u].y - mean; a[u][2] = v[u].z - mean; a[u][3] = v[u].w - mean;
+      q[u] = a[u][0] * a[u][0] + a[u][1] * a[u][1] + a[u][2] * a[u][2] + a[u][3] * a[u][3];
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < R; ++u) q[u] += __shfl_xor_sync(0xffffffffu, q[u], o, 16);
+    float rstd[R], e[R][4];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      rstd[u] = rsqrtf(q[u] * (1.f / 64.f) + 1e-5f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[u][j] *= rstd[u];                   // xhat
+      ag.x += d[u].x * a[u][0]; ag.y += d[u].y * a[u][1]; ag.z += d[u].z * a[u][2]; ag.w += d[u].w * a[u][3];
+      ab.x += d[u].x; ab.y += d[u].y; ab.z += d[u].z; ab.w += d[u].w;
+      e[u][0] = d[u].x * gg.x; e[u][1] = d[u].y * gg.y; e[u][2] = d[u].z * gg.z; e[u][3] = d[u].w * gg.w;
+      s1[u] = e[u][0] + e[u][1] + e[u][2] + e[u][3];
+      s2[u] = e[u][0] * a[u][0] + e[u][1] * a[u][1] + e[u][2] * a[u][2] + e[u][3] * a[u][3];
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o, 16);
+        s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o, 16);
+      }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const float m1 = s1[u] * (1.f / 64.f), m2 = s2[u] * (1.f / 64.f);
+      float4 o4 = make_float4(rstd[u] * (e[u][0] - m1 - a[u][0] * m2), rstd[u] * (e[u][1] - m1 - a[u][1] * m2),
+                              rstd[u] * (e[u][2] - m1 - a[u][2] * m2), rstd[u] * (e[u][3] - m1 - a[u][3] * m2));
+      o4.x += rr[u].x; o4.y += rr[u].y; o4.z += rr[u].z; o4.w += rr[u].w;
+      if (ok[u]) reinterpret_cast<float4*>(dx + (rowb + 16 * u) * 64)[l] = o4;
+    }
   }
   reinterpret_cast<float4*>(&sg[grp][0])[l] = ag;
   reinterpret_cast<float4*>(&sb[grp][0])[l] = ab;
