@@ -122,6 +122,10 @@ def load():
         fn.argtypes = args
     if lib.eegclip_abi_version() != 3:
         raise EegclipError("libeegclip_b200.so ABI version mismatch")
+    # development knobs from the environment: EEGCLIP_TUNE="7=1,6=1" -> eegclip_tune_set(7, 1), eegclip_tune_set(6, 1)
+    for kv in filter(None, os.environ.get("EEGCLIP_TUNE", "").split(",")):
+        k, v = kv.split("=")
+        lib.eegclip_tune_set(int(k), int(v))
     _lib = lib
     return lib
 

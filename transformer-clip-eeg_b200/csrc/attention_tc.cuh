@@ -64,6 +64,7 @@ __device__ __forceinline__ void build_keep_bits(uint32_t* smask, const Drop& dro
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512, 2) attn_fwd_tc_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                                             float* __restrict__ lse, int T, Drop drop) {
+  pdl_sync();
   extern __shared__ float4 smf[];
   float4* Kf = smf;
   float4* Vf = smf + (T / 32) * 64;
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(512, 2) attn_fwd_tc_kernel(const float* __rest
 __global__ void __launch_bounds__(256, 2) attn_bwd_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ out,
                                                             const float* __restrict__ dout, const float* __restrict__ lse,
                                                             float* __restrict__ dqkv, int T, Drop drop) {
+  pdl_sync();
   extern __shared__ float smb[];
   float* Qs = smb;
   float* dOs = Qs + T * QS;
@@ -342,7 +344,7 @@ inline int attention_fwd_tc(const float* qkv, float* out, float* lse, int B, int
     configured = true;
   }
   ProfScope prof(PROF_ATTN_FWD, st);
-  attntc::attn_fwd_tc_kernel<<<B * AH, (T / 32) * 32, smem, st>>>(qkv, out, lse, T, drop);
+  LAUNCH_PDL((attntc::attn_fwd_tc_kernel), B * AH, (T / 32) * 32, smem, st, qkv, out, lse, T, drop);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -358,7 +360,7 @@ inline int attention_bwd_tc(const float* qkv, const float* out, const float* dou
     configured = true;
   }
   ProfScope prof(PROF_ATTN_BWD, st);
-  attntc::attn_bwd_tc_kernel<<<B * AH, warps * 32, smem, st>>>(qkv, out, dout, lse, dqkv, T, drop);
+  LAUNCH_PDL((attntc::attn_bwd_tc_kernel), B * AH, warps * 32, smem, st, qkv, out, dout, lse, dqkv, T, drop);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

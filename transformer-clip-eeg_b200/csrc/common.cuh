@@ -36,6 +36,31 @@ struct ProfScope {
   ~ProfScope() { prof_end(cls, st); }
 };
 
+// Programmatic dependent launch.  A step is ~510 dependent kernel launches on one stream and the back-to-back launch gap
+// (~2 us: drain, block scheduling, barrier / TMEM set-up of the next kernel) was ~5 % of the step.  Every hot kernel starts
+// with pdl_sync(): `launch_dependents` lets the NEXT kernel's CTAs be scheduled as soon as all of this kernel's CTAs have
+// started, `wait` then blocks until the PREVIOUS grid has completed and its memory is visible -- nothing of the kernel body
+// runs before that, so the semantics are exactly stream order; only launch latency and CTA ramp-up overlap the predecessor's
+// tail.  Launches go through LAUNCH_PDL (cudaLaunchKernelEx + programmatic stream serialization); g_tune[7] = 1 turns the
+// attribute off (A/B timing).  A kernel launched without the attribute executes both instructions as no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
+// (the tensor-core kernels split the pair: barrier initialisation and the TMEM allocation, which touch no global memory, run
+//  between pdl_trigger() and pdl_wait() and so overlap the predecessor's tail as well)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_tune[7] ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define LAUNCH_PDL(kernel, grid, block, smem, st, ...) (void)::eegclip::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
+
 // dropout site ids; stream = layer * 16 + site  (oracle/philox_ref.py::stream_id)
 enum : int { SITE_CONV = 0, SITE_ATTN = 1, SITE_PROJ = 2, SITE_FFN_HID = 3, SITE_FFN_OUT = 4 };
 

@@ -43,6 +43,7 @@ constexpr int WG_TAPS = 16;          // taps per weight-gradient CTA
 //   mode 1 (dgrad)   : n = ci, contraction index = co, tap k' holds W[..][..][63-k']
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int mode, int TAPS, int Cin, int Cout) {
+  pdl_sync();
   // packed block (nb, kb) = 64 outputs x 64 contraction channels, all taps: out + ((nb * nkb + kb) * TAPS + tap) * W_TAP_BYTES
   const int nN = (mode == 0 ? Cout : Cin) / CH, nK = (mode == 0 ? Cin : Cout) / CH;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over blocks * taps * 8 chunks * 64 n
@@ -86,6 +87,7 @@ __host__ __device__ inline uint32_t conv_smem_bytes(int T, int taps) {
 
 template <int NTERMS>
 __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
+  pdl_sync();
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x, nb = blockIdx.y;
@@ -524,6 +526,7 @@ __host__ __device__ inline uint32_t wgrad_smem_bytes(int T) {
 
 template <int NTERMS>
 __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a) {
+  pdl_sync();
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntg = a.taps / WG_TAPS, nci = a.Cin / CH;
@@ -649,6 +652,7 @@ __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a)
 
 // dW[co][ci][k] = sum_g partial[g][k][co][ci]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int groups, int TAPS, int Cin, int Cout) {
+  pdl_sync();
   const long per = (long)TAPS * Cout * Cin;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over (k * Cout + co) * Cin + ci
   if (i >= per) return;
@@ -719,7 +723,7 @@ inline int conv_tc_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
     configured = true;
   }
   ProfScope prof(PROF_CONV_TC, st);
-  convtc::conv64_tc_kernel<NTERMS><<<dim3(B, a.out_ld / convtc::CH), 256, smem, st>>>(a);
+  LAUNCH_PDL((convtc::conv64_tc_kernel<NTERMS>), dim3(B, a.out_ld / convtc::CH), 256, smem, st, a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -727,7 +731,7 @@ inline int conv_tc_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
 inline int conv_tc_pack(const float* w, uint8_t* wp, int mode, int taps, int Cin, int Cout, int T, cudaStream_t st) {
   const long n = (long)(Cin / 64) * (Cout / 64) * taps * 8 * 64;
   if (conv_ts_selected(T)) convtc::pack_conv_weights_ts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, wp, mode, taps, Cin, Cout);
-  else convtc::pack_conv_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, wp, mode, taps, Cin, Cout);
+  else LAUNCH_PDL((convtc::pack_conv_weights_kernel), (unsigned)((n + 255) / 256), 256, 0, st, w, wp, mode, taps, Cin, Cout);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -752,7 +756,7 @@ inline int wgrad_tc_launch(const convtc::WgradTcArgs& a, cudaStream_t st) {
   }
   dim3 grid((a.taps / convtc::WG_TAPS) * (a.Cin / convtc::CH) * (a.Cout / convtc::CH), a.groups);
   ProfScope prof(PROF_WGRAD_TC, st);
-  convtc::wgrad64_tc_kernel<NTERMS><<<grid, 256, convtc::wgrad_smem_bytes(a.T), st>>>(a);
+  LAUNCH_PDL((convtc::wgrad64_tc_kernel<NTERMS>), grid, 256, convtc::wgrad_smem_bytes(a.T), st, a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -778,7 +782,7 @@ inline int conv_tc_backward(int math, const float* xin, const float* skip_in, co
   rc = math == EEGCLIP_MATH_BF16 ? wgrad_tc_launch<1>(g, st) : wgrad_tc_launch<3>(g, st);
   if (rc != EEGCLIP_OK) return rc;
   const long n = (long)taps * Cin * Cout;
-  convtc::wgrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, dw, g.groups, taps, Cin, Cout);
+  LAUNCH_PDL((convtc::wgrad_reduce_kernel), (unsigned)((n + 255) / 256), 256, 0, st, partial, dw, g.groups, taps, Cin, Cout);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

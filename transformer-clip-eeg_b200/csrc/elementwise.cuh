@@ -43,6 +43,7 @@ inline int pad_add(const float* x1, const float* x2, float* out, int B, int T, i
 
 // out = a + b (b optional), float4
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long n4) {
+  pdl_sync();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 v = reinterpret_cast<const float4*>(a)[i];
@@ -51,7 +52,7 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
 }
 inline int add_f32(const float* a, const float* b, float* out, long n, cudaStream_t st) {
   long n4 = n / 4;
-  add_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(a, b, out, n4);
+  LAUNCH_PDL((add_kernel), (unsigned)((n4 + 255) / 256), 256, 0, st, a, b, out, n4);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -104,6 +105,7 @@ inline size_t ln_ct_scratch_floats(int T, int C) { return (size_t)(2 + 2 * LNCT_
 
 __global__ void __launch_bounds__(256) ct_transpose2_kernel(const float* __restrict__ g, const float* __restrict__ b,
                                                            float* __restrict__ gT, float* __restrict__ bT, int C, int T) {
+  pdl_sync();
   __shared__ float tile[2][32][33];
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int r = ty; r < 32; r += 8) {
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(256) ct_transpose2_kernel(const float* __restr
 // (independent, coalesced), the 8 x 32 tile is transposed through shared memory for the (C,T) write.
 __global__ void __launch_bounds__(256) ct_reduce_transpose_kernel(const float* __restrict__ part, float* __restrict__ dgamma,
                                                                  float* __restrict__ dbeta, int groups, int C, int T) {
+  pdl_sync();
   __shared__ float tile[2][8][33];
   const int t0 = blockIdx.x * 8, c0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long n = (long)T * C;
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(256) ct_reduce_transpose_kernel(const float* _
 
 inline int ct_transpose2(const float* g, const float* b, float* gT, float* bT, int C, int T, cudaStream_t st) {
   dim3 grid((T + 31) / 32, (C + 31) / 32);
-  ct_transpose2_kernel<<<grid, 256, 0, st>>>(g, b, gT, bT, C, T);
+  LAUNCH_PDL((ct_transpose2_kernel), grid, 256, 0, st, g, b, gT, bT, C, T);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(512) ln_ct_act_fwd_kernel(const float* __restr
                                                            const float* __restrict__ bT, const float* __restrict__ skip,
                                                            float* __restrict__ out, float* __restrict__ stats, int T, int C,
                                                            int act, float eps) {
+  pdl_sync();
   __shared__ float2 sh[33];
   const int b = blockIdx.x;
   const long n = (long)T * C;
@@ -206,6 +210,7 @@ __global__ void __launch_bounds__(512) ln_ct_act_fwd_reg_kernel(const float* __r
                                                                const float* __restrict__ bT, const float* __restrict__ skip,
                                                                float* __restrict__ out, float* __restrict__ stats, int T, int C,
                                                                int act, float eps) {
+  pdl_sync();
   __shared__ float2 sh[33];
   const int b = blockIdx.x;
   const int n = T * C;
@@ -259,8 +264,8 @@ inline int ln_ct_act_fwd(const float* y, const float* gamma, const float* beta, 
   float* gT = lnscr;
   float* bT = lnscr + (size_t)T * C;
   { int rc = ct_transpose2(gamma, beta, gT, bT, C, T, st); if (rc != EEGCLIP_OK) return rc; }
-  if ((long)T * C <= 512L * 4 * 10) ln_ct_act_fwd_reg_kernel<10><<<B, 512, 0, st>>>(y, gT, bT, skip, out, stats, T, C, act, 1e-5f);
-  else ln_ct_act_fwd_kernel<<<B, 512, 0, st>>>(y, gT, bT, skip, out, stats, T, C, act, 1e-5f);
+  if ((long)T * C <= 512L * 4 * 10) LAUNCH_PDL((ln_ct_act_fwd_reg_kernel<10>), B, 512, 0, st, y, gT, bT, skip, out, stats, T, C, act, 1e-5f);
+  else LAUNCH_PDL((ln_ct_act_fwd_kernel), B, 512, 0, st, y, gT, bT, skip, out, stats, T, C, act, 1e-5f);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -277,6 +282,7 @@ __global__ void __launch_bounds__(512) ln_ct_bwd_stats_kernel(const float* __res
                                                              const float* __restrict__ stats, const float* __restrict__ gT,
                                                              const float* __restrict__ bT, float* __restrict__ m12, int T, int C,
                                                              int act) {
+  pdl_sync();
   __shared__ float2 sh[33];
   const int b = blockIdx.x;
   const long n = (long)T * C;
@@ -318,6 +324,7 @@ __global__ void __launch_bounds__(256) ln_ct_bwd_apply_kernel(const float* __res
                                                              const float* __restrict__ gT, const float* __restrict__ bT,
                                                              float* __restrict__ dypad, float* __restrict__ part, int B, int T, int C,
                                                              int PL, int TP, int act, Drop drop) {
+  pdl_sync();
   const long n = (long)T * C;
   const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
@@ -366,15 +373,15 @@ inline int ln_ct_act_bwd(const float* dout, const float* y, const float* stats, 
   float* bT = lnscr + (size_t)T * C;
   float* part = lnscr + (size_t)2 * T * C;
   { int rc = ct_transpose2(gamma, beta, gT, bT, C, T, st); if (rc != EEGCLIP_OK) return rc; }
-  ln_ct_bwd_stats_kernel<<<B, 512, 0, st>>>(dout, y, stats, gT, bT, m12, T, C, act);
+  LAUNCH_PDL((ln_ct_bwd_stats_kernel), B, 512, 0, st, dout, y, stats, gT, bT, m12, T, C, act);
   LAUNCH_CHECK();
   const long n8 = (long)T * C / 8;
   const int groups = B < LNCT_GROUPS ? B : LNCT_GROUPS;
   dim3 grid((unsigned)((n8 + 255) / 256), groups);
-  ln_ct_bwd_apply_kernel<<<grid, 256, 0, st>>>(dout, y, stats, m12, gT, bT, dypad, part, B, T, C, PL, T + taps - 1, act, drop);
+  LAUNCH_PDL((ln_ct_bwd_apply_kernel), grid, 256, 0, st, dout, y, stats, m12, gT, bT, dypad, part, B, T, C, PL, T + taps - 1, act, drop);
   LAUNCH_CHECK();
   dim3 g2((T + 7) / 8, (C + 31) / 32);
-  ct_reduce_transpose_kernel<<<g2, 256, 0, st>>>(part, dgamma, dbeta, groups, C, T);
+  LAUNCH_PDL((ct_reduce_transpose_kernel), g2, 256, 0, st, part, dgamma, dbeta, groups, C, T);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -384,6 +391,7 @@ inline int ln_ct_act_bwd(const float* dout, const float* y, const float* stats, 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ln64_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                       const float* __restrict__ be, float* __restrict__ out, long rows) {
+  pdl_sync();
   long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   int l = threadIdx.x & 15;
   if (row >= rows) return;
@@ -403,7 +411,7 @@ __global__ void __launch_bounds__(256) ln64_fwd_kernel(const float* __restrict__
 }
 inline int ln64_fwd(const float* x, const float* g, const float* b, float* out, long rows, cudaStream_t st) {
   long threads = rows * 16;
-  ln64_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, g, b, out, rows);
+  LAUNCH_PDL((ln64_fwd_kernel), (unsigned)((threads + 255) / 256), 256, 0, st, x, g, b, out, rows);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -415,6 +423,7 @@ __global__ void __launch_bounds__(256) ln64_bwd_kernel(const float* __restrict__
                                                       const float* __restrict__ g, const float* __restrict__ resid,
                                                       float* __restrict__ dx, float* __restrict__ dgamma,
                                                       float* __restrict__ dbeta, long rows, int rows_per_cta) {
+  pdl_sync();
   __shared__ float sg[16][64], sb[16][64];
   const int l = threadIdx.x & 15, grp = threadIdx.x >> 4;  // 16 groups of 16 lanes
   float4 gg = reinterpret_cast<const float4*>(g)[l];
@@ -496,7 +505,7 @@ __global__ void __launch_bounds__(256) ln64_bwd_kernel(const float* __restrict__
 inline int ln64_bwd(const float* dh, const float* x, const float* g, const float* resid, float* dx, float* dgamma, float* dbeta,
                     long rows, cudaStream_t st) {
   int rows_per_cta = 256;
-  ln64_bwd_kernel<<<(unsigned)((rows + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(dh, x, g, resid, dx, dgamma, dbeta, rows, rows_per_cta);
+  LAUNCH_PDL((ln64_bwd_kernel), (unsigned)((rows + rows_per_cta - 1) / rows_per_cta), 256, 0, st, dh, x, g, resid, dx, dgamma, dbeta, rows, rows_per_cta);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -504,6 +513,7 @@ inline int ln64_bwd(const float* dh, const float* x, const float* g, const float
 // out[n] += sum_m X[m][n]   (bias gradients). N <= 256, N % 4 == 0.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, float* __restrict__ out, long M, int N,
                                                     int ld, int rows_per_cta) {
+  pdl_sync();
   __shared__ float sh[256 * 4];
   const int n4 = N >> 2;                  // float4 columns
   const int lanes = n4;                   // threads across columns
@@ -528,7 +538,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
 inline int colsum(const float* X, float* out, long M, int N, int ld, cudaStream_t st) {
   if (N > 256 || (N & 3) || (256 % (N >> 2)) || (ld & 3)) return EEGCLIP_ERR_UNSUPPORTED;
   int rows_per_cta = 512;
-  colsum_kernel<<<(unsigned)((M + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(X, out, M, N, ld, rows_per_cta);
+  LAUNCH_PDL((colsum_kernel), (unsigned)((M + rows_per_cta - 1) / rows_per_cta), 256, 0, st, X, out, M, N, ld, rows_per_cta);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

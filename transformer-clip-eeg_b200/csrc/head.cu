@@ -22,14 +22,16 @@ static int g_prof_n = 0;
 static cudaEvent_t g_prof_ev[PROF_MAX][2];
 static int g_prof_cls[PROF_MAX];
 static bool g_prof_init = false;
+// g_tune[8]: bit mask of the kernel classes that record events (0 = all).  bench.py times its steps with the roofline
+// kernel's class only, so that the event records do not break up programmatic dependent launch between the other kernels.
+static inline bool prof_cls_on(int cls) { return g_tune[8] == 0 || ((g_tune[8] >> cls) & 1); }
 void prof_begin(int cls, cudaStream_t st) {
-  if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+  if (!g_prof_on || g_prof_n >= PROF_MAX || !prof_cls_on(cls)) return;
   g_prof_cls[g_prof_n] = cls;
   cudaEventRecord(g_prof_ev[g_prof_n][0], st);
 }
 void prof_end(int cls, cudaStream_t st) {
-  (void)cls;
-  if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+  if (!g_prof_on || g_prof_n >= PROF_MAX || !prof_cls_on(cls)) return;
   cudaEventRecord(g_prof_ev[g_prof_n][1], st);
   ++g_prof_n;
 }

@@ -85,6 +85,7 @@ constexpr int MAX_PACK_JOBS = 16;
 struct PackJobs { PackJob j[MAX_PACK_JOBS]; int n; };
 
 static __global__ void __launch_bounds__(256) pack_lin_weights_kernel(const PackJobs jobs) {
+  pdl_sync();
   const PackJob& J = jobs.j[blockIdx.y];
   if (J.kind == 1) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < J.n_cnt; i += gridDim.x * blockDim.x)
@@ -108,7 +109,7 @@ static __global__ void __launch_bounds__(256) pack_lin_weights_kernel(const Pack
 
 inline int pack_launch(const PackJobs& jobs, cudaStream_t st) {
   if (jobs.n <= 0) return EEGCLIP_OK;
-  pack_lin_weights_kernel<<<dim3(8, jobs.n), 256, 0, st>>>(jobs);
+  LAUNCH_PDL((pack_lin_weights_kernel), dim3(8, jobs.n), 256, 0, st, jobs);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -225,6 +226,7 @@ inline uint32_t lin_smem_bytes(int N, int K, int nstage = NSTAGE, int nepi = 8) 
 
 template <int NTERMS, int PRO, int EF, int NEPI>
 __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) {
+  pdl_trigger();
   constexpr int NPROD = NWARPS - 1 - NEPI;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
     tc::mbar_fence_init();
   }
   if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, ncols);
+  pdl_wait();   // everything above touches only this CTA's shared memory / TMEM; global memory is read from here on
   for (int n = tid; n < N; n += NTHREADS) sBias[n] = a.bias ? __ldg(a.bias + n) : 0.f;
   tc::tc_fence_before();
   __syncthreads();
@@ -486,7 +489,7 @@ inline int lin_tc_launch_w(const LinTcArgs& a, int grid, cudaStream_t st) {
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
-  lin_tc_kernel<NTERMS, PRO, EF, NEPI><<<grid, NTHREADS, lin_smem_bytes(a.N, a.K, a.nstage, NEPI), st>>>(a);
+  LAUNCH_PDL((lin_tc_kernel<NTERMS, PRO, EF, NEPI>), grid, NTHREADS, lin_smem_bytes(a.N, a.K, a.nstage, NEPI), st, a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -562,6 +565,7 @@ inline uint32_t wgrad_lin_smem_bytes(int Nout, int Kin) { return 2 * wgrad_stage
 // PDY / PX: compile-time prologues of dy / x (-1 = runtime), WDB: bias-gradient column sums (-1 = runtime)
 template <int NTERMS, int PDY, int PX, int WDB>
 __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWgradArgs a) {
+  pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Nout = a.Nout, Kin = a.Kin;
@@ -588,6 +592,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();   // global memory is read from here on
 
   // token range of this CTA, in units of WT-token stages
   const int nst_total = (a.M + WT - 1) / WT;
@@ -760,6 +765,7 @@ struct WgradReduceArgs {
   float* dW[4]; float* db[4];     // destination d covers rows [d*rows_per_dst, (d+1)*rows_per_dst); null = discard (padding rows)
 };
 static __global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const WgradReduceArgs a) {
+  pdl_sync();
   // 32 consecutive outputs x 8 partial groups per CTA; 8 independent loads in flight per thread (latency-bound otherwise)
   __shared__ float sh[8][33];
   const int total = a.Nout * a.Kin + a.Nout;
@@ -817,7 +823,7 @@ inline int lin_wgrad_launch_v(const LinWgradArgs& a, dim3 grid, uint32_t smem, c
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
-  lin_wgrad_tc_kernel<NTERMS, PDY, PX, WDB><<<grid, WG_THREADS, smem, st>>>(a);
+  LAUNCH_PDL((lin_wgrad_tc_kernel<NTERMS, PDY, PX, WDB>), grid, WG_THREADS, smem, st, a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -846,7 +852,7 @@ inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const d
   for (int i = 0; i < 3; ++i) { r.dW[i] = dW[i]; r.db[i] = db[i]; }
   r.dW[3] = nullptr; r.db[3] = nullptr;
   const int total = a.Nout * a.Kin + a.Nout;
-  lin_wgrad_reduce_kernel<<<dim3((total + 31) / 32, kin_blocks), 256, 0, st>>>(r);
+  LAUNCH_PDL((lin_wgrad_reduce_kernel), dim3((total + 31) / 32, kin_blocks), 256, 0, st, r);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

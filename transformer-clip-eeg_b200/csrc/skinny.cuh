@@ -19,6 +19,7 @@ constexpr int WG_CTAS = 296;
 template <int NL>
 __global__ void __launch_bounds__(128) skinny_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                         const float* __restrict__ b, float* __restrict__ out, long M) {
+  pdl_sync();
   __shared__ __align__(16) float sWt[SK][NL];          // W transposed: one 128-bit broadcast load gives 4 outputs of a feature
   __shared__ float sx[4][32][SK + 1];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(128) skinny_fwd_kernel(const float* __restrict
 template <int NL>
 __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ W,
                                                           float* __restrict__ dx, long M) {
+  pdl_sync();
   __shared__ __align__(16) float sW[NL][SK];
   for (int i = threadIdx.x; i < NL * SK; i += 256) sW[i / SK][i % SK] = W[i];
   __syncthreads();
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restri
 template <int NL>
 __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                           float* __restrict__ partial, long M) {
+  pdl_sync();
   __shared__ float red[16][NL * SK + NL];
   const int tid = threadIdx.x, k4 = (tid & 15) * 4, slot = tid >> 4;
   const long per = (M + gridDim.x - 1) / gridDim.x;
@@ -134,30 +137,30 @@ inline size_t partial_floats(int N) { return (size_t)WG_CTAS * (N * SK + N); }
 
 inline int fwd(const float* x, const float* W, const float* b, float* out, long M, int N, cudaStream_t st) {
   const unsigned grid = (unsigned)((M + 127) / 128);
-  if (N == 8) skinny_fwd_kernel<8><<<grid, 128, 0, st>>>(x, W, b, out, M);
-  else skinny_fwd_kernel<4><<<grid, 128, 0, st>>>(x, W, b, out, M);
+  if (N == 8) LAUNCH_PDL((skinny_fwd_kernel<8>), grid, 128, 0, st, x, W, b, out, M);
+  else LAUNCH_PDL((skinny_fwd_kernel<4>), grid, 128, 0, st, x, W, b, out, M);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
 inline int dgrad(const float* dy, const float* W, float* dx, long M, int N, cudaStream_t st) {
   const unsigned grid = (unsigned)((M * 16 + 255) / 256);
-  if (N == 8) skinny_dgrad_kernel<8><<<grid, 256, 0, st>>>(dy, W, dx, M);
-  else skinny_dgrad_kernel<4><<<grid, 256, 0, st>>>(dy, W, dx, M);
+  if (N == 8) LAUNCH_PDL((skinny_dgrad_kernel<8>), grid, 256, 0, st, dy, W, dx, M);
+  else LAUNCH_PDL((skinny_dgrad_kernel<4>), grid, 256, 0, st, dy, W, dx, M);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
 // dW (N,64) and db (N) are OVERWRITTEN; partial: partial_floats(N) floats of scratch
 inline int wgrad(const float* dy, const float* x, float* dW, float* db, float* partial, long M, int N, cudaStream_t st) {
   int ctas = (int)(M < WG_CTAS ? M : WG_CTAS);
-  if (N == 8) skinny_wgrad_kernel<8><<<ctas, 256, 0, st>>>(dy, x, partial, M);
-  else skinny_wgrad_kernel<4><<<ctas, 256, 0, st>>>(dy, x, partial, M);
+  if (N == 8) LAUNCH_PDL((skinny_wgrad_kernel<8>), ctas, 256, 0, st, dy, x, partial, M);
+  else LAUNCH_PDL((skinny_wgrad_kernel<4>), ctas, 256, 0, st, dy, x, partial, M);
   LAUNCH_CHECK();
   lintc::WgradReduceArgs r;
   r.partial = partial; r.ctas = ctas; r.Nout = N; r.Kin = SK; r.rows_per_dst = N; r.ldw = SK; r.log_scale = nullptr;
   for (int i = 0; i < 4; ++i) { r.dW[i] = nullptr; r.db[i] = nullptr; }
   r.dW[0] = dW; r.db[0] = db;
   const int total = N * SK + N;
-  lintc::lin_wgrad_reduce_kernel<<<dim3((total + 31) / 32, 1), 256, 0, st>>>(r);
+  LAUNCH_PDL((lintc::lin_wgrad_reduce_kernel), dim3((total + 31) / 32, 1), 256, 0, st, r);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

@@ -230,6 +230,38 @@ class DevicePrefetcher:
             self._free[cur_slot] = done
 
 
+class LossReader:
+    """Device -> host read of every step's loss without draining the launch queue: the 0-dim loss is copied into a pinned
+    ring slot on the compute stream (non-blocking) and read on the host ONE step later, when its event has long fired.
+    ``loss.item()`` right after a step (the reference does it every 100 batches, train_clip_final.py:494-500) makes the host
+    wait for the whole step and the GPU then idles while the next step's ~500 launches are enqueued."""
+
+    def __init__(self, device, depth=4):
+        self.buf = torch.empty(depth, dtype=torch.float32).pin_memory()
+        self.ev = [torch.cuda.Event() for _ in range(depth)]
+        self.depth, self.n_push, self.n_pop, self.device = depth, 0, 0, device
+
+    def push(self, loss):
+        """Enqueue the copy of this step's loss; returns the losses of earlier steps that are due (lag one step)."""
+        out = []
+        while self.n_push > self.n_pop:              # the previous step's event: this step's launches are already queued
+            out.append(self._pop())
+        slot = self.n_push % self.depth
+        self.buf[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        self.ev[slot].record(torch.cuda.current_stream(self.device))
+        self.n_push += 1
+        return out
+
+    def _pop(self):
+        slot = self.n_pop % self.depth
+        self.ev[slot].synchronize()
+        self.n_pop += 1
+        return float(self.buf[slot])
+
+    def drain(self):
+        return [self._pop() for _ in range(self.n_push - self.n_pop)]
+
+
 def printf(s, file):
     print(s)
     with open(file, 'a') as f:
