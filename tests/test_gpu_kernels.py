@@ -239,3 +239,39 @@ def test_bank_topk_world1_matches_reference_topk(lib):
     rv, ri = torch.topk(E.double() @ Bk.double().T, 100, dim=1)
     assert torch.equal(i[:, :10], ri[:, :10])
     assert rel_err(v, rv) < 1e-5
+
+
+def test_loss_reader_returns_every_step_in_order(lib):
+    """The e2e loop's deferred device->host loss read (train_clip_final.LossReader) hands back every pushed value, in order."""
+    from transformer_clip_eeg_b200.train_clip_final import LossReader
+    rd = LossReader(torch.device(DEV), depth=4)
+    got = []
+    vals = [float(i) * 0.5 - 3.0 for i in range(11)]
+    for v in vals:
+        got += rd.push(torch.tensor(v, device=DEV))
+    assert len(got) == len(vals) - 1          # lag of exactly one step
+    got += rd.drain()
+    assert got == vals
+
+
+def test_pdl_off_matches_pdl_on(cm, lib):
+    """Programmatic dependent launch only overlaps launch latency: the forward is bit-identical with the attribute off
+    (g_tune[7]); gradients agree to fp32 rounding (the attention backward sums dQ over warps with shared-memory float atomics,
+    so it is not bitwise reproducible run to run with or without PDL)."""
+    torch.manual_seed(11)
+    model = cm.EEGConformerInterleaved(output_dim=8, time_dimension=192, depth=2).to(DEV).eval()
+    x = torch.randn(4, 192, 64, device=DEV)
+    outs = []
+    for off in (0, 1):
+        lib.call("eegclip_tune_set", 7, off)
+        try:
+            xx = x.clone().requires_grad_(True)
+            model.zero_grad()
+            y = model(xx)
+            y.square().sum().backward()
+            outs.append((y.detach().clone(), xx.grad.detach().clone(), model.conv_0.conv.weight.grad.detach().clone()))
+        finally:
+            lib.call("eegclip_tune_set", 7, 0)
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert rel_err(a, b) < 1e-5

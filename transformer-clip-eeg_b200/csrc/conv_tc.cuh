@@ -298,6 +298,7 @@ constexpr int TS_SLOTS = 4;
 
 // Wstack packing: per (n block, k block, tap) 128 rows x 64 contraction channels bf16 (128 B per row): rows 0-63 hi, 64-127 lo
 __global__ void pack_conv_weights_ts_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int mode, int TAPS, int Cin, int Cout) {
+  pdl_sync();
   const int nN = (mode == 0 ? Cout : Cin) / CH, nK = (mode == 0 ? Cin : Cout) / CH;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over blocks * taps * 64 n * 8 chunks
   if (i >= (long)nN * nK * TAPS * CH * 8) return;
@@ -325,6 +326,7 @@ __host__ __device__ inline uint32_t conv_ts_smem_bytes(int T, int taps) {
 
 template <int NTERMS>
 __global__ void __launch_bounds__(256, 1) conv64_ts_kernel(const ConvTcArgs a) {
+  pdl_sync();
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x, nb = blockIdx.y;
@@ -707,7 +709,7 @@ inline int conv_ts_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
     configured = true;
   }
   ProfScope prof(PROF_CONV_TC, st);
-  convtc::conv64_ts_kernel<NTERMS><<<dim3(B, a.out_ld / convtc::CH), 256, smem, st>>>(a);
+  LAUNCH_PDL((convtc::conv64_ts_kernel<NTERMS>), dim3(B, a.out_ld / convtc::CH), 256, smem, st, a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -730,7 +732,7 @@ inline int conv_tc_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
 
 inline int conv_tc_pack(const float* w, uint8_t* wp, int mode, int taps, int Cin, int Cout, int T, cudaStream_t st) {
   const long n = (long)(Cin / 64) * (Cout / 64) * taps * 8 * 64;
-  if (conv_ts_selected(T)) convtc::pack_conv_weights_ts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, wp, mode, taps, Cin, Cout);
+  if (conv_ts_selected(T)) LAUNCH_PDL((convtc::pack_conv_weights_ts_kernel), (unsigned)((n + 255) / 256), 256, 0, st, w, wp, mode, taps, Cin, Cout);
   else LAUNCH_PDL((convtc::pack_conv_weights_kernel), (unsigned)((n + 255) / 256), 256, 0, st, w, wp, mode, taps, Cin, Cout);
   LAUNCH_CHECK();
   return EEGCLIP_OK;

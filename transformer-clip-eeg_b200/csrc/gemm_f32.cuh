@@ -55,6 +55,7 @@ constexpr int GBM = 64, GBN = 64, GBK = 16;
 
 template <int MODE>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs g) {
+  pdl_sync();
   __shared__ float As[GBK][GBM + 4];
   __shared__ float Bs[GBK][GBN + 4];
   const int tid = threadIdx.x;
@@ -228,7 +229,7 @@ inline int gemm_f32(const GemmArgs& g, cudaStream_t st) {
   if (a.splitk < 1) a.splitk = 1;
   dim3 grid(ceil_div(a.N, GBN), ceil_div(a.M, GBM), a.batch * a.splitk);
   ProfScope prof(PROF_GEMM_F32, st);
-  gemm_f32_kernel<MODE><<<grid, 256, 0, st>>>(a);
+  LAUNCH_PDL((gemm_f32_kernel<MODE>), grid, 256, 0, st, a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

@@ -42,6 +42,7 @@ namespace {
 // ---- L2 normalise rows: xn = x / max(||x||, 1e-12)  (F.normalize, clip_model.py:675-676) -----------
 __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ xn,
                                                         float* __restrict__ inv_norm, int D) {
+  pdl_sync();
   __shared__ float2 sh[33];
   const long row = blockIdx.x;
   const float* xr = x + row * D;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict
 // dx = inv * (dxn - xn * <xn, dxn>)
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ xn, const float* __restrict__ inv_norm,
                                                         const float* __restrict__ dxn, float* __restrict__ dx, int D) {
+  pdl_sync();
   __shared__ float2 sh[33];
   const long row = blockIdx.x;
   const float* a = xn + row * D;
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict
 
 // combine per-tile (max,sumexp) partials into a log-sum-exp per row
 __global__ void lse_combine_kernel(const float2* __restrict__ part, int ntiles, float* __restrict__ lse, int rows) {
+  pdl_sync();
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float m = -INFINITY;
@@ -96,6 +99,7 @@ __global__ void lse_combine_kernel(const float2* __restrict__ part, int ntiles, 
 // diag[i] = exp(tau) * <S[row0+i], E[row0+i]>   (one warp per row)
 __global__ void diag_kernel(const float* __restrict__ S, const float* __restrict__ E, const float* __restrict__ tau,
                             float* __restrict__ diag, int b, int row0, int D) {
+  pdl_sync();
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
   if (w >= b) return;
   const float* s = S + (long)(row0 + w) * D;
@@ -111,6 +115,7 @@ __global__ void diag_kernel(const float* __restrict__ S, const float* __restrict
 
 __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ lr, const float* __restrict__ lc,
                                                   const float* __restrict__ dg, int Bg, int one_sided, float* __restrict__ loss) {
+  pdl_sync();
   __shared__ float2 sh[33];
   float s = 0.f;
   for (int i = threadIdx.x; i < Bg; i += blockDim.x) s += one_sided ? (lr[i] - dg[i]) : (lr[i] - dg[i]) + (lc[i] - dg[i]);
@@ -121,6 +126,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ lr,
 __global__ void __launch_bounds__(256) membank_kernel(float* __restrict__ mem, const int64_t* __restrict__ idx,
                                                      const float* __restrict__ data, float* __restrict__ old_out, int D,
                                                      float momentum, float om) {
+  pdl_sync();
   const long r = blockIdx.x;
   float* m = mem + idx[r] * (long)D;
   const float* d = data + r * D;
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(256) membank_kernel(float* __restrict__ mem, c
 // AdamW, one launch for all tensors: blockIdx.y = tensor, grid-stride over its elements
 __global__ void __launch_bounds__(256) adamw_kernel(const eegclip_adamw_entry* __restrict__ tab, float lr, float b1, float b2,
                                                    float eps, float wd, float bc1, float bc2_sqrt) {
+  pdl_sync();
   const eegclip_adamw_entry e = tab[blockIdx.y];
   float* p = (float*)e.p; const float* g = (const float*)e.g; float* m = (float*)e.m; float* v = (float*)e.v;
   const long n = e.numel;
@@ -241,7 +248,7 @@ const char* eegclip_build_info(void) { return "eegclip_b200 sm_100a " __DATE__ "
 
 int eegclip_l2norm_forward(const float* x, float* xn, float* inv_norm, int32_t rows, int32_t D, void* stream) {
   if (!x || !xn || rows <= 0 || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
-  l2norm_fwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, xn, inv_norm, D);
+  LAUNCH_PDL((l2norm_fwd_kernel), rows, 256, 0, (cudaStream_t)stream, x, xn, inv_norm, D);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -249,7 +256,7 @@ int eegclip_l2norm_forward(const float* x, float* xn, float* inv_norm, int32_t r
 int eegclip_l2norm_backward(const float* xn, const float* inv_norm, const float* dxn, float* dx, int32_t rows, int32_t D,
                             void* stream) {
   if (!xn || !inv_norm || !dxn || !dx || rows <= 0 || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
-  l2norm_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(xn, inv_norm, dxn, dx, D);
+  LAUNCH_PDL((l2norm_bwd_kernel), rows, 256, 0, (cudaStream_t)stream, xn, inv_norm, dxn, dx, D);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -305,12 +312,12 @@ int eegclip_infonce_lse(const float* S_all, const float* E_all, const float* tau
     a.Ap = pS; a.Bp = pE; a.a_blk0 = row0 / headtc::RB; a.M = b; a.N = Bg; a.D = D; a.tau = tau;
     a.m_off = row0; a.n_off = 0; a.part = part; a.diag = diag;
     TRY(headtc::logits_launch<1>(math, a, st));
-    lse_combine_kernel<<<ceil_div(b, 128), 128, 0, st>>>(part, nt, lse_row, b);
+    LAUNCH_PDL((lse_combine_kernel), ceil_div(b, 128), 128, 0, st, part, nt, lse_row, b);
     LAUNCH_CHECK();
     if (one_sided) return EEGCLIP_OK;
     a.Ap = pE; a.Bp = pS; a.part = part2; a.diag = nullptr;
     TRY(headtc::logits_launch<1>(math, a, st));
-    lse_combine_kernel<<<ceil_div(b, 128), 128, 0, st>>>(part2, nt, lse_col, b);
+    LAUNCH_PDL((lse_combine_kernel), ceil_div(b, 128), 128, 0, st, part2, nt, lse_col, b);
     LAUNCH_CHECK();
     return EEGCLIP_OK;
   }
@@ -322,16 +329,16 @@ int eegclip_infonce_lse(const float* S_all, const float* E_all, const float* tau
   g.a_ms = D; g.a_ks = 1; g.b_ks = 1; g.b_ns = D;
   g.epi.tau = tau; g.epi.lse_part = part;
   TRY(gemm_f32<1>(g, st));
-  lse_combine_kernel<<<ceil_div(b, 128), 128, 0, st>>>(part, ntiles, lse_row, b);
+  LAUNCH_PDL((lse_combine_kernel), ceil_div(b, 128), 128, 0, st, part, ntiles, lse_row, b);
   LAUNCH_CHECK();
-  diag_kernel<<<ceil_div(b * 32, 256), 256, 0, st>>>(S_all, E_all, tau, diag, b, row0, D);
+  LAUNCH_PDL((diag_kernel), ceil_div(b * 32, 256), 256, 0, st, S_all, E_all, tau, diag, b, row0, D);
   LAUNCH_CHECK();
   if (one_sided) return EEGCLIP_OK;
   // columns: this rank's EEG rows against every speech row (the transposed block)
   g.A = E_all + (long)row0 * D; g.B = S_all;
   g.epi.lse_part = part2;
   TRY(gemm_f32<1>(g, st));
-  lse_combine_kernel<<<ceil_div(b, 128), 128, 0, st>>>(part2, ntiles, lse_col, b);
+  LAUNCH_PDL((lse_combine_kernel), ceil_div(b, 128), 128, 0, st, part2, ntiles, lse_col, b);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -339,7 +346,7 @@ int eegclip_infonce_lse(const float* S_all, const float* E_all, const float* tau
 int eegclip_infonce_loss(const float* lse_row_all, const float* lse_col_all, const float* diag_all, int32_t Bg, int32_t one_sided,
                          float* loss, void* stream) {
   if (!lse_row_all || (!lse_col_all && !one_sided) || !diag_all || !loss || Bg <= 0) return EEGCLIP_ERR_ARG;
-  loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(lse_row_all, lse_col_all, diag_all, Bg, one_sided, loss);
+  LAUNCH_PDL((loss_kernel), 1, 256, 0, (cudaStream_t)stream, lse_row_all, lse_col_all, diag_all, Bg, one_sided, loss);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -441,7 +448,7 @@ int eegclip_infonce_backward(const float* S_all, const float* E_all, const float
 int eegclip_membank_update(float* memory, const int64_t* idx, const float* data, float* old_out, int32_t rows, int32_t D,
                            float momentum, float one_minus_momentum, void* stream) {
   if (!memory || !idx || !data || !old_out || rows <= 0 || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
-  membank_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(memory, idx, data, old_out, D, momentum, one_minus_momentum);
+  LAUNCH_PDL((membank_kernel), rows, 256, 0, (cudaStream_t)stream, memory, idx, data, old_out, D, momentum, one_minus_momentum);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -456,7 +463,7 @@ int eegclip_adamw_step(const eegclip_adamw_entry* table_dev, int32_t n_tensors, 
   if (gx < 1) gx = 1;
   if (gx > 128) gx = 128;
   dim3 grid(gx, n_tensors);
-  adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table_dev, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2));
+  LAUNCH_PDL((adamw_kernel), grid, 256, 0, (cudaStream_t)stream, table_dev, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2));
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

@@ -32,6 +32,7 @@ inline size_t epack_bytes(int R, int D) { return (size_t)((R + RB - 1) / RB) * (
 
 // grid: (D/64 chunks, row blocks); block 256: lane -> (row = lane & 7, c8 = lane >> 3 (+4 per half)) as in lin_tc stage_chunk
 __global__ void __launch_bounds__(256) epack_kernel(const float* __restrict__ X, uint8_t* __restrict__ P, int R, int D) {
+  pdl_sync();
   const int kc = blockIdx.x, rb = blockIdx.y, nkc = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* blk = P + ((size_t)rb * nkc + kc) * BLK;
@@ -82,6 +83,7 @@ struct LogitsArgs {
 
 template <int MODE, int NTERMS>
 __global__ void __launch_bounds__(192, 1) logits_tc_kernel(const LogitsArgs a) {
+  pdl_sync();
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE);
@@ -245,7 +247,7 @@ inline bool head_tc_supported(int b, int Bg, int D) {
 
 inline int epack(const float* X, uint8_t* P, int R, int D, cudaStream_t st) {
   dim3 grid(D / KC, (R + RB - 1) / RB);
-  epack_kernel<<<grid, 256, 0, st>>>(X, P, R, D);
+  LAUNCH_PDL((epack_kernel), grid, 256, 0, st, X, P, R, D);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -261,7 +263,7 @@ inline int logits_launch_t(const LogitsArgs& a, cudaStream_t st) {
   }
   dim3 grid((a.N + NT - 1) / NT, (a.M + RB - 1) / RB);
   ProfScope prof(PROF_GEMM_F32, st);
-  logits_tc_kernel<MODE, NTERMS><<<grid, 192, smem, st>>>(a);
+  LAUNCH_PDL((logits_tc_kernel<MODE, NTERMS>), grid, 192, smem, st, a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

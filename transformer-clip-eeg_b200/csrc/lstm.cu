@@ -48,6 +48,7 @@ LstmLayout lstm_layout(const eegclip_bilstm_desc& d) {
 
 __global__ void lstm_bias_kernel(const float* __restrict__ bif, const float* __restrict__ bhf, const float* __restrict__ bir,
                                  const float* __restrict__ bhr, float* __restrict__ out, int G4, int GS) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= GS) return;
   float v = 0.f;
@@ -91,7 +92,7 @@ int eegclip_bilstm_forward(const eegclip_bilstm_desc* dp, const float* const* pa
   const long M = (long)d.B * d.T;
   const int G4 = 4 * d.H, In = d.In;
   float* bsum = (float*)(sc + L.bsum);
-  lstm_bias_kernel<<<ceil_div(L.GS, 256), 256, 0, st>>>(params[2], params[3], params[6], params[7], bsum, G4, L.GS);
+  LAUNCH_PDL((lstm_bias_kernel), ceil_div(L.GS, 256), 256, 0, st, params[2], params[3], params[6], params[7], bsum, G4, L.GS);
   LAUNCH_CHECK();
   // ---- input projections of every time step: G = x . [W_ih ; W_ih_reverse]^T + biases ----
   uint8_t* wp = sc + L.wp;
@@ -122,12 +123,12 @@ int eegclip_bilstm_forward(const eegclip_bilstm_desc* dp, const float* const* pa
       configured = true;
     }
     ProfScope prof(PROF_LSTM, st);
-    lstm::lstm128_fwd_kernel<<<dim3(ceil_div(d.B, lstm::LNB), 2), 512, lstm::L128_SMEM, st>>>(params[1], params[5], G, L.GS, out,
+    LAUNCH_PDL((lstm::lstm128_fwd_kernel), dim3(ceil_div(d.B, lstm::LNB), 2), 512, lstm::L128_SMEM, st, params[1], params[5], G, L.GS, out,
                                                                                              save + L.cs, save + L.hp, d.B, d.T);
     LAUNCH_CHECK();
   } else {
     ProfScope prof(PROF_LSTM, st);
-    lstm::lstm4_fwd_kernel<<<ceil_div(2 * d.B * 16, 128), 128, 0, st>>>(params[1], params[5], G, L.GS, out, save + L.cs, save + L.hp, d.B,
+    LAUNCH_PDL((lstm::lstm4_fwd_kernel), ceil_div(2 * d.B * 16, 128), 128, 0, st, params[1], params[5], G, L.GS, out, save + L.cs, save + L.hp, d.B,
                                                                         d.T);
     LAUNCH_CHECK();
   }
@@ -160,14 +161,14 @@ int eegclip_bilstm_backward(const eegclip_bilstm_desc* dp, const float* const* p
       configured = true;
     }
     ProfScope prof(PROF_LSTM, st);
-    lstm::lstm128_bwd_kernel<<<dim3(ceil_div(d.B, lstm::LNB), 2), 512, lstm::L128B_SMEM, st>>>(params[1], params[5], G, L.GS, dout, Cs, d.B,
+    LAUNCH_PDL((lstm::lstm128_bwd_kernel), dim3(ceil_div(d.B, lstm::LNB), 2), 512, lstm::L128B_SMEM, st, params[1], params[5], G, L.GS, dout, Cs, d.B,
                                                                                               d.T);
     LAUNCH_CHECK();
   } else {
     CUDA_TRY(cudaMemsetAsync(grads[1], 0, (size_t)G4 * H * sizeof(float), st));
     CUDA_TRY(cudaMemsetAsync(grads[5], 0, (size_t)G4 * H * sizeof(float), st));
     ProfScope prof(PROF_LSTM, st);
-    lstm::lstm4_bwd_kernel<<<ceil_div(2 * d.B * 16, 128), 128, 0, st>>>(params[1], params[5], G, L.GS, dout, Cs, Hp, grads[1], grads[5],
+    LAUNCH_PDL((lstm::lstm4_bwd_kernel), ceil_div(2 * d.B * 16, 128), 128, 0, st, params[1], params[5], G, L.GS, dout, Cs, Hp, grads[1], grads[5],
                                                                         d.B, d.T);
     LAUNCH_CHECK();
   }

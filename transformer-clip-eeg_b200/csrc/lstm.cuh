@@ -42,6 +42,7 @@ constexpr int L128_SMEM = (16 * LG * 4 + LHS + LNB * LG) * 4;         // W half 
 __global__ void __launch_bounds__(512, 1) lstm128_fwd_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
                                                             float* __restrict__ G, int GS, float* __restrict__ out,
                                                             float* __restrict__ Cs, float* __restrict__ Hp, int B, int T) {
+  pdl_sync();
   extern __shared__ __align__(16) float sml[];
   float4* Wsm = reinterpret_cast<float4*>(sml);          // [j = 16][tid 512] : rows 2,3 of the thread's tile
   float* hs = sml + 16 * LG * 4;                         // h of the 4 sequences, padded (see hidx)
@@ -150,6 +151,7 @@ constexpr int L128B_SMEM = (16 * LG * 4 + LDS_ + LNB * LH) * 4;
 __global__ void __launch_bounds__(512, 1) lstm128_bwd_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
                                                             float* __restrict__ G, int GS, const float* __restrict__ dout,
                                                             const float* __restrict__ Cs, int B, int T) {
+  pdl_sync();
   extern __shared__ __align__(16) float sml[];
   float4* Wsm = reinterpret_cast<float4*>(sml);          // [j = 16][tid 512] : W[32rp + 16 + j][4kg .. 4kg+3]
   float* das = sml + 16 * LG * 4;                        // da of the 4 sequences, padded (see didx)
@@ -247,6 +249,7 @@ __global__ void __launch_bounds__(512, 1) lstm128_bwd_kernel(const float* __rest
 __global__ void __launch_bounds__(128) lstm4_fwd_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
                                                        float* __restrict__ G, int GS, float* __restrict__ out, float* __restrict__ Cs,
                                                        float* __restrict__ Hp, int B, int T) {
+  pdl_sync();
   const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int j = threadIdx.x & 15;                       // gate row
   const bool live = gid < 2 * B;
@@ -291,6 +294,7 @@ __global__ void __launch_bounds__(128) lstm4_bwd_kernel(const float* __restrict_
                                                        float* __restrict__ G, int GS, const float* __restrict__ dout,
                                                        const float* __restrict__ Cs, const float* __restrict__ Hp,
                                                        float* __restrict__ dwhh_f, float* __restrict__ dwhh_r, int B, int T) {
+  pdl_sync();
   __shared__ float red[2][64];
   const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int j = threadIdx.x & 15;
