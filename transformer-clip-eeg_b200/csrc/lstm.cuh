@@ -175,17 +175,31 @@ __global__ void __launch_bounds__(512, 1) lstm128_bwd_kernel(const float* __rest
   float dc = 0.f;
   __syncthreads();
   const float4* d4 = reinterpret_cast<const float4*>(das);
+  // the saved state of step + 1 is fetched while step runs (seven loads per thread were issued and consumed in the same
+  // step: one exposed L2 / DRAM round trip per time step)
+  float n_g[4] = {0.f, 0.f, 0.f, 0.f}, n_ct = 0.f, n_cp = 0.f, n_dy = 0.f;
+  auto fetch = [&](int step_) {
+    if (live && step_ < T) {
+      const int t_ = dir ? step_ : T - 1 - step_;
+      const int tp_ = dir ? t_ + 1 : t_ - 1;
+      const long row_ = (long)b * T + t_;
+      const float* gp_ = G + row_ * GS + dir * LG + u;
+      n_g[0] = gp_[0]; n_g[1] = gp_[LH]; n_g[2] = gp_[2 * LH]; n_g[3] = gp_[3 * LH];
+      n_ct = Cs[row_ * 256 + dir * LH + u];
+      n_cp = (tp_ >= 0 && tp_ < T) ? Cs[((long)b * T + tp_) * 256 + dir * LH + u] : 0.f;
+      n_dy = dout[row_ * 256 + dir * LH + u];
+    }
+  };
+  fetch(0);
   for (int step = 0; step < T; ++step) {
     const int t = dir ? step : T - 1 - step;             // reverse of the forward order
-    const int tp = dir ? t + 1 : t - 1;                  // time index of the forward's previous step
     const long row = (long)b * T + t;
     float da[4] = {0.f, 0.f, 0.f, 0.f};
+    const float gi = n_g[0], gf = n_g[1], gg = n_g[2], go = n_g[3], ct = n_ct, cp = n_cp, dyv = n_dy;
+    fetch(step + 1);
     if (live) {
       float* gp = G + row * GS + dir * LG + u;
-      const float gi = gp[0], gf = gp[LH], gg = gp[2 * LH], go = gp[3 * LH];
-      const float ct = Cs[row * 256 + dir * LH + u];
-      const float cp = (tp >= 0 && tp < T) ? Cs[((long)b * T + tp) * 256 + dir * LH + u] : 0.f;
-      const float dh = dout[row * 256 + dir * LH + u] + dhs[s * LH + u];
+      const float dh = dyv + dhs[s * LH + u];
       const float tc = tanhf(ct);
       const float dct = dc + dh * go * (1.f - tc * tc);
       da[0] = dct * gg * gi * (1.f - gi);
@@ -246,6 +260,8 @@ __global__ void __launch_bounds__(512, 1) lstm128_bwd_kernel(const float* __rest
 // the next step's input projection is prefetched while the current one is computed.
 //   grid = ceil(2*B / 8) CTAs of 128 threads (8 groups); group id = dir * B + b.
 // ------------------------------------------------------------------------------------------------
+constexpr int LPF = 8;   // prefetch depth (time steps) of the H = 4 recurrences
+
 __global__ void __launch_bounds__(128) lstm4_fwd_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
                                                        float* __restrict__ G, int GS, float* __restrict__ out, float* __restrict__ Cs,
                                                        float* __restrict__ Hp, int B, int T) {
@@ -260,12 +276,27 @@ __global__ void __launch_bounds__(128) lstm4_fwd_kernel(const float* __restrict_
   const float w0 = __ldg(W), w1 = __ldg(W + 1), w2 = __ldg(W + 2), w3 = __ldg(W + 3);
   float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, c = 0.f;  // h replicated in every lane, c in the unit lanes (j < 4)
   const long rbase = (long)b * T;
-  float gnext = live ? G[(rbase + (dir ? T - 1 : 0)) * GS + dir * 16 + j] : 0.f;
-  for (int step = 0; step < T; ++step) {
+  // The input projections of the next LPF steps are prefetched while the current LPF steps run: with a one-step look-ahead
+  // every step waited ~0.5 us for its 64-byte gate row (the recurrence itself is ~200 dependent cycles per step).
+  float gbuf[LPF];
+#pragma unroll
+  for (int u = 0; u < LPF; ++u) gbuf[u] = (live && u < T) ? G[(rbase + (dir ? T - 1 - u : u)) * GS + dir * 16 + j] : 0.f;
+  for (int step0 = 0; step0 < T; step0 += LPF) {
+    float gcur[LPF];
+#pragma unroll
+    for (int u = 0; u < LPF; ++u) gcur[u] = gbuf[u];
+#pragma unroll
+    for (int u = 0; u < LPF; ++u) {
+      const int sn = step0 + LPF + u;
+      if (live && sn < T) gbuf[u] = G[(rbase + (dir ? T - 1 - sn : sn)) * GS + dir * 16 + j];
+    }
+#pragma unroll
+    for (int uu = 0; uu < LPF; ++uu) {
+    const int step = step0 + uu;
+    if (step >= T) break;
     const int t = dir ? T - 1 - step : step;
     const long row = rbase + t;
-    const float gx = gnext;
-    if (step + 1 < T && live) gnext = G[(rbase + (dir ? t - 1 : t + 1)) * GS + dir * 16 + j];
+    const float gx = gcur[uu];
     float a = gx;
     a = fmaf(w0, h0, a); a = fmaf(w1, h1, a); a = fmaf(w2, h2, a); a = fmaf(w3, h3, a);
     const float act = (j >> 2) == 2 ? tanhf(a) : sigmoidf_(a);
@@ -286,6 +317,7 @@ __global__ void __launch_bounds__(128) lstm4_fwd_kernel(const float* __restrict_
     }
     h0 = __shfl_sync(gmask, hn, lbase + 0); h1 = __shfl_sync(gmask, hn, lbase + 1);
     h2 = __shfl_sync(gmask, hn, lbase + 2); h3 = __shfl_sync(gmask, hn, lbase + 3);
+    }
   }
 }
 
@@ -310,18 +342,37 @@ __global__ void __launch_bounds__(128) lstm4_bwd_kernel(const float* __restrict_
   const long rbase = (long)b * T;
   if (threadIdx.x < 128) { red[0][threadIdx.x & 63] = 0.f; red[1][threadIdx.x & 63] = 0.f; }
   __syncthreads();
-  for (int step = 0; step < T; ++step) {
-    const int t = dir ? step : T - 1 - step;
-    const int tp = dir ? t + 1 : t - 1;
-    const long row = rbase + t;
-    float act = 0.f, ct = 0.f, cp = 0.f, dy = 0.f, hp = 0.f;
-    if (live) {
-      act = G[row * GS + dir * 16 + j];
-      ct = Cs[row * 8 + dir * 4 + u];
-      cp = (tp >= 0 && tp < T) ? Cs[(rbase + tp) * 8 + dir * 4 + u] : 0.f;
-      dy = dout[row * 8 + dir * 4 + u];
-      hp = Hp[row * 8 + dir * 4 + u];
+  // block prefetch of the saved state (see lstm4_fwd_kernel): the five loads of a step used to be issued and consumed in the
+  // same step -- one exposed L2 / DRAM round trip (~0.8 us) per time step
+  float b_act[LPF], b_ct[LPF], b_cp[LPF], b_dy[LPF], b_hp[LPF];
+  auto fetch = [&](int s_, float& act_, float& ct_, float& cp_, float& dy_, float& hp_) {
+    act_ = 0.f; ct_ = 0.f; cp_ = 0.f; dy_ = 0.f; hp_ = 0.f;
+    if (live && s_ < T) {
+      const int t_ = dir ? s_ : T - 1 - s_;
+      const int tp_ = dir ? t_ + 1 : t_ - 1;
+      const long row_ = rbase + t_;
+      act_ = G[row_ * GS + dir * 16 + j];
+      ct_ = Cs[row_ * 8 + dir * 4 + u];
+      cp_ = (tp_ >= 0 && tp_ < T) ? Cs[(rbase + tp_) * 8 + dir * 4 + u] : 0.f;
+      dy_ = dout[row_ * 8 + dir * 4 + u];
+      hp_ = Hp[row_ * 8 + dir * 4 + u];
     }
+  };
+#pragma unroll
+  for (int q = 0; q < LPF; ++q) fetch(q, b_act[q], b_ct[q], b_cp[q], b_dy[q], b_hp[q]);
+  for (int step0 = 0; step0 < T; step0 += LPF) {
+    float c_act[LPF], c_ct[LPF], c_cp[LPF], c_dy[LPF], c_hp[LPF];
+#pragma unroll
+    for (int q = 0; q < LPF; ++q) { c_act[q] = b_act[q]; c_ct[q] = b_ct[q]; c_cp[q] = b_cp[q]; c_dy[q] = b_dy[q]; c_hp[q] = b_hp[q]; }
+#pragma unroll
+    for (int q = 0; q < LPF; ++q) fetch(step0 + LPF + q, b_act[q], b_ct[q], b_cp[q], b_dy[q], b_hp[q]);
+#pragma unroll
+    for (int q = 0; q < LPF; ++q) {
+    const int step = step0 + q;
+    if (step >= T) break;
+    const int t = dir ? step : T - 1 - step;
+    const long row = rbase + t;
+    const float act = c_act[q], ct = c_ct[q], cp = c_cp[q], dy = c_dy[q], hp = c_hp[q];
     const float gi = __shfl_sync(gmask, act, lbase + u), gf = __shfl_sync(gmask, act, lbase + 4 + u);
     const float gg = __shfl_sync(gmask, act, lbase + 8 + u), go = __shfl_sync(gmask, act, lbase + 12 + u);
     const float dht = dy + dh;
@@ -346,6 +397,7 @@ __global__ void __launch_bounds__(128) lstm4_bwd_kernel(const float* __restrict_
       p2 += __shfl_xor_sync(gmask, p2, o); p3 += __shfl_xor_sync(gmask, p3, o);
     }
     dh = u == 0 ? p0 : u == 1 ? p1 : u == 2 ? p2 : p3;
+    }
   }
   // CTA-level reduction of dW_hh per direction (a CTA may straddle the two directions)
   if (live) {
