@@ -31,6 +31,10 @@ __device__ __forceinline__ uint32_t tf32(float x) {
   return r;
 }
 __device__ __forceinline__ float tf32f(float x) { return __uint_as_float(tf32(x)); }
+// cvt.rna.tf32.f32 for FINITE inputs in two integer instructions: ptxas lowers the PTX conversion to IADD + FSETP(+inf) + SEL + LOP3
+// (the compare / select only protect inf / NaN).  Probabilities and dS in the inner loops are finite; adding half an ulp of the 13
+// dropped bits to the sign-magnitude pattern and truncating is round-to-nearest, ties away from zero -- exactly .rna.
+__device__ __forceinline__ uint32_t tf32_fin(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 
 // D(16x8) = A(16x8, row) * B(8x8, col) + C
 __device__ __forceinline__ void mma_tf32(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1,
@@ -155,17 +159,19 @@ __global__ void __launch_bounds__(512, 2) attn_fwd_tc_kernel(const float* __rest
         keep0 = drop_bits8(drop, e0);
         keep1 = drop_bits8(drop, e0 + (uint64_t)8 * T);
       }
+      // the row maximum enters as the accumulator input of the score MMA: S - max costs no instruction
+      const float negmx[4] = {-mx[R][0], -mx[R][0], -mx[R][1], -mx[R][1]};
 #pragma unroll
       for (int X = 0; X < 4; ++X) {
         float s[4];
-        mma_tf32(s, qa[R][0], qa[R][1], qa[R][2], qa[R][3], __float_as_uint(kb[2 * X]), __float_as_uint(kb[2 * X + 1]), zero);
-        const float p0 = ex2(s[0] - mx[R][0]), p1 = ex2(s[1] - mx[R][0]), p2 = ex2(s[2] - mx[R][1]), p3 = ex2(s[3] - mx[R][1]);
+        mma_tf32(s, qa[R][0], qa[R][1], qa[R][2], qa[R][3], __float_as_uint(kb[2 * X]), __float_as_uint(kb[2 * X + 1]), negmx);
+        const float p0 = ex2(s[0]), p1 = ex2(s[1]), p2 = ex2(s[2]), p3 = ex2(s[3]);
         l[R][0] += p0 + p1; l[R][1] += p2 + p3;
         // this thread's keys of the block: 8tig + 2X (+1)
-        const uint32_t pa0 = (keep0 >> (2 * X)) & 1u ? tf32(p0) : 0u;
-        const uint32_t pa2 = (keep0 >> (2 * X + 1)) & 1u ? tf32(p1) : 0u;
-        const uint32_t pa1 = (keep1 >> (2 * X)) & 1u ? tf32(p2) : 0u;
-        const uint32_t pa3 = (keep1 >> (2 * X + 1)) & 1u ? tf32(p3) : 0u;
+        const uint32_t pa0 = (keep0 >> (2 * X)) & 1u ? tf32_fin(p0) : 0u;
+        const uint32_t pa2 = (keep0 >> (2 * X + 1)) & 1u ? tf32_fin(p1) : 0u;
+        const uint32_t pa1 = (keep1 >> (2 * X)) & 1u ? tf32_fin(p2) : 0u;
+        const uint32_t pa3 = (keep1 >> (2 * X + 1)) & 1u ? tf32_fin(p3) : 0u;
         mma_tf32(o[R], pa0, pa1, pa2, pa3, __float_as_uint(vb[2 * X]), __float_as_uint(vb[2 * X + 1]), o[R]);
       }
     }
@@ -279,21 +285,23 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_tc_kernel(const float* __rest
       keepa = drop_bits8(drop, ((uint64_t)bh * T + (uint64_t)(q0 + 2 * tig)) * (uint64_t)T + (uint64_t)(j0 + 8 * g));
       keepb = drop_bits8(drop, ((uint64_t)bh * T + (uint64_t)(q0 + 2 * tig + 1)) * (uint64_t)T + (uint64_t)(j0 + 8 * g));
     }
+    // -lse' of the two query columns enters as the accumulator input of the score MMA (S - lse' costs no instruction)
+    const float negL[4] = {-L.x, -L.y, -L.x, -L.y};
 #pragma unroll
     for (int Y = 0; Y < 4; ++Y) {
       float s[4], dp[4];
-      mma_tf32(s, ka[Y][0], ka[Y][1], ka[Y][2], ka[Y][3], qb0, qb1, zero);
+      mma_tf32(s, ka[Y][0], ka[Y][1], ka[Y][2], ka[Y][3], qb0, qb1, negL);
       mma_tf32(dp, va[Y][0], va[Y][1], va[Y][2], va[Y][3], ob0, ob1, zero);
       // fragment element e: row (key) 8g+2Y+(e>>1), column (query) 2tig+(e&1)
-      const float p0 = ex2(s[0] - L.x), p1 = ex2(s[1] - L.y), p2 = ex2(s[2] - L.x), p3 = ex2(s[3] - L.y);
+      const float p0 = ex2(s[0]), p1 = ex2(s[1]), p2 = ex2(s[2]), p3 = ex2(s[3]);
       const float k0m = (keepa >> (2 * Y)) & 1u ? dscale : 0.f, k1m = (keepb >> (2 * Y)) & 1u ? dscale : 0.f;
       const float k2m = (keepa >> (2 * Y + 1)) & 1u ? dscale : 0.f, k3m = (keepb >> (2 * Y + 1)) & 1u ? dscale : 0.f;
       const float pd0 = p0 * k0m, pd1 = p1 * k1m, pd2 = p2 * k2m, pd3 = p3 * k3m;
       const float ds0 = p0 * (dp[0] * k0m - Dq.x), ds1 = p1 * (dp[1] * k1m - Dq.y);
       const float ds2 = p2 * (dp[2] * k2m - Dq.x), ds3 = p3 * (dp[3] * k3m - Dq.y);
       // accumulator fragment -> A fragment (k-index tig <-> query 2tig, tig+4 <-> query 2tig+1)
-      mma_tf32(dv[Y], tf32(pd0), tf32(pd2), tf32(pd1), tf32(pd3), oc0, oc1, dv[Y]);
-      const uint32_t t0 = tf32(ds0), t1 = tf32(ds1), t2 = tf32(ds2), t3 = tf32(ds3);
+      mma_tf32(dv[Y], tf32_fin(pd0), tf32_fin(pd2), tf32_fin(pd1), tf32_fin(pd3), oc0, oc1, dv[Y]);
+      const uint32_t t0 = tf32_fin(ds0), t1 = tf32_fin(ds1), t2 = tf32_fin(ds2), t3 = tf32_fin(ds3);
       mma_tf32(dk[Y], t0, t2, t1, t3, qc0, qc1, dk[Y]);
       // stage dS^T[key][query] for the dQ product
       *reinterpret_cast<float2*>(stg + (8 * g + 2 * Y) * 8 + 2 * tig) = make_float2(__uint_as_float(t0), __uint_as_float(t1));
