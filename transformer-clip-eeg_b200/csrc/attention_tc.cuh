@@ -267,6 +267,8 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_tc_kernel(const float* __rest
   __syncthreads();
   const float zero[4] = {0.f, 0.f, 0.f, 0.f};
   const float dscale = drop.scale;
+  // (measured and rejected: starting every warp at a different query block so that the shared-memory compare-and-swap adds of
+  //  dQ do not collide -- 3.16 ms per step against 2.88 ms for the lock-step order)
   for (int q0 = 0; q0 < T; q0 += 8) {
     // B fragments: Q^T / dO^T (k = d, n = query)  and  Q / dO (k = query pair of this thread, n = d)
     const uint32_t qb0 = __float_as_uint(Qs[(q0 + g) * QS + tig]), qb1 = __float_as_uint(Qs[(q0 + g) * QS + tig + 4]);

@@ -87,7 +87,7 @@ __host__ __device__ inline uint32_t conv_smem_bytes(int T, int taps) {
 
 template <int NTERMS>
 __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
-  pdl_sync();
+  pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x, nb = blockIdx.y;
@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
   }
   if (warp == 2) tc::tmem_alloc(tmem_slot, ncols);
   uint32_t tmem = 0;
+  pdl_wait();   // global memory is read from here on
 
   for (int kb = 0; kb < nkb; ++kb) {
   // ---- stage the activation tile: fp32 (+skip) -> bf16 hi/lo, chunk-major, zero padded ----
@@ -528,7 +529,7 @@ __host__ __device__ inline uint32_t wgrad_smem_bytes(int T) {
 
 template <int NTERMS>
 __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a) {
-  pdl_sync();
+  pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntg = a.taps / WG_TAPS, nci = a.Cin / CH;
@@ -547,6 +548,7 @@ __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a)
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();   // global memory is read from here on
   const uint32_t idesc = tc::idesc_bf16(64, CH, 1, 1);   // both operands MN-major (K = time)
   uint32_t phase = 0;
   bool first = true;
