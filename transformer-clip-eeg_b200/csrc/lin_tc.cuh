@@ -162,13 +162,34 @@ __device__ __forceinline__ void convert_chunk(const ChunkRegs<ROWS, NPW>& R, lon
                                               float* colsum /* nullptr or 8 running sums */) {
   constexpr int ITERS = (ROWS / 8) * 2 / NPW;
   const int ch = (pw & 1) * 4 + (lane >> 3);
+  const int prog = PRO < 0 ? pro : PRO;
+  // 1-bit dropout: a warp's share of the chunk is ITERS x 8 rows x 32 columns = one 32-bit Philox word per row.  Lane l draws
+  // the words of rows (l >> 3, l & 7) of iterations 4j + (l >> 3) once, the iterations fetch theirs by shuffle: ITERS / 4
+  // Philox calls per thread and chunk instead of ITERS (the prologue was most of the producers' instruction count).
+  const bool fast = prog != PRO_NONE && drop.enabled && drop.onebit && (ncols_total & 31) == 0;
+  constexpr int NW = (ITERS + 3) / 4;
+  uint32_t wown[NW];
+  if (fast) {
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+      const int it_ = 4 * j + (lane >> 3);
+      const int rb_ = it_ * (NPW / 2) + (pw >> 1);
+      const uint64_t idx0 = (uint64_t)(row0 + rb_ * 8 + (lane & 7)) * (uint64_t)ncols_total + (uint64_t)(col0 + (pw & 1) * 32);
+      const uint4 w4 = drop_words(drop, idx0 >> 7);
+      wown[j] = word_of(w4, (uint32_t)(idx0 >> 5) & 3u);
+    }
+  }
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     const int rb = it * (NPW / 2) + (pw >> 1);
     const int rl = rb * 8 + (lane & 7);
     float v[8] = {R.x0[it].x, R.x0[it].y, R.x0[it].z, R.x0[it].w, R.x1[it].x, R.x1[it].y, R.x1[it].z, R.x1[it].w};
-    const int prog = PRO < 0 ? pro : PRO;
-    if (prog != PRO_NONE) {
+    if (fast) {
+      const uint32_t w = __shfl_sync(0xffffffffu, wown[it >> 2], ((it & 3) << 3) | (lane & 7));
+      const uint32_t bits = w >> ((lane >> 3) * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (prog == PRO_GELU_DROP ? gelu_f(v[e]) : v[e]) * ((bits >> e) & 1u ? drop.scale : 0.f);
+    } else if (prog != PRO_NONE) {
       const long r = row0 + rl;
       if (r < rows_total) {
         const uint64_t idx = (uint64_t)r * (uint64_t)ncols_total + (uint64_t)(col0 + ch * 8);
@@ -401,13 +422,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
         // the side stream of the epilogue (residual, or the saved multiplier) is fetched for all 8 row groups before any
         // of it is used: one exposed memory latency per 32-column block instead of one per row group
         const float* side_p = f_res ? a.residual : (f_mul ? a.mul_src : nullptr);
-        float4 side[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const long m = mrow0 + i * 4 + rq;
-          side[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (side_p && m < a.M) side[i] = *reinterpret_cast<const float4*>(side_p + m * a.ldc + n);
-        }
         // 1-bit dropout (p = 0.5, every dropout of the transformer block): one Philox call yields 128 decisions of ONE row, so
         // lane l draws the word of row mrow0 + l for this 32-column block once and the coalesced phase fetches it by shuffle --
         // one call per block and warp instead of one per float4 (32x redundant: the FFN1 epilogue was issue-bound on it)
@@ -418,8 +432,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
           const uint4 w4 = drop_words(a.drop, idx0 >> 7);
           wown = word_of(w4, (uint32_t)(idx0 >> 5) & 3u);
         }
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
+        // two halves of four row groups, each fully unrolled so that side[] stays in registers (one array of 8 indexed by a
+        // partially unrolled loop lived in local memory: 128-byte stack frames in every residual / multiplier variant)
+        for (int ih = 0; ih < 2; ++ih) {
+        float4 side[4];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const long m = mrow0 + (ih * 4 + i4) * 4 + rq;
+          side[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (side_p && m < a.M) side[i4] = *reinterpret_cast<const float4*>(side_p + m * a.ldc + n);
+        }
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int i = ih * 4 + i4;
           const int rl = i * 4 + rq;
           const long m = mrow0 + rl;
           const uint32_t wrow = __shfl_sync(0xffffffffu, wown, rl);
@@ -448,7 +473,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
             }
             if (f_act2) *reinterpret_cast<float4*>(a.aux + ci) = gd;
             if (f_mul) {
-              const float4 s4 = f_res ? ld_act(reinterpret_cast<const float4*>(a.mul_src + ci), a.policy) : side[i];
+              const float4 s4 = f_res ? ld_act(reinterpret_cast<const float4*>(a.mul_src + ci), a.policy) : side[i4];
               r.x *= s4.x; r.y *= s4.y; r.z *= s4.z; r.w *= s4.w;
             }
             if (f_ag) {
@@ -457,11 +482,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
             }
             if (f_res) {
               // (plain coherent loads above: the residual may alias C in the K-split accumulation passes)
-              const float4 s4 = side[i];
+              const float4 s4 = side[i4];
               r.x += s4.x; r.y += s4.y; r.z += s4.z; r.w += s4.w;
             }
             *reinterpret_cast<float4*>(a.C + ci) = r;
           }
+        }
         }
         __syncwarp();
         dbg_mark(dbg, 2, dn, 25);
