@@ -583,6 +583,7 @@ struct LinWgradArgs {
   float* partial;                         // [kin blocks][ctas][Nout*Kin + Nout]
   int want_db;
   int policy;                             // load policy of the streamed activations (0: L1 no-allocate, 1: __ldg)
+  unsigned long long* dbg;                // development timeline buffer (nullptr in production)
 };
 
 inline uint32_t wgrad_stage_bytes(int Nout, int Kin) { return (uint32_t)(Nout + Kin) * WT * 4; }
@@ -642,6 +643,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
       for (int e = 0; e < 8; ++e) cs[i][e] = 0.f;
     // (measured and rejected: issuing the loads of stage it+1 before / while stage it is converted -- whole-stage double
     //  buffering with 32-token stages 2.60 ms per step, chunk-level rolling reissue 2.75 ms, this loop 2.44 ms)
+    unsigned long long* dbgp = (blockIdx.x == 0 && blockIdx.y == 0 && warp == 3 && lane == 0) ? a.dbg : nullptr;
+    unsigned long long* dbgm = (blockIdx.x == 0 && blockIdx.y == 0 && warp == 0 && lane == 0) ? a.dbg : nullptr;
+    int dnp = 0, dnm = 0;
+    dbg_mark(dbgp, 0, dnp, 0);
     for (int it = 0; it < nst; ++it) {
       const int s = it & 1;
       uint8_t* sb = smem + s * STAGE;
@@ -657,7 +662,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
           x0[c] = ld_act(reinterpret_cast<const float4*>(src), a.policy); x1[c] = ld_act(reinterpret_cast<const float4*>(src) + 1, a.policy);
         }
       }
+      dbg_mark(dbgp, 0, dnp, 1);                       // loads issued
       tc::mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+      dbg_mark(dbgp, 0, dnp, 2);                       // slot free
 #pragma unroll
       for (int c = 0; c < WG_MAXC; ++c) {
         if (c < ntot) {
@@ -687,10 +694,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
       tc::fence_async_smem();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&full[s]);          // one arrival per warp (512 per-thread arrivals serialise on the barrier)
+      dbg_mark(dbgp, 0, dnp, 3);                       // converted + arrived
       if (warp == 0) {
         // ===== MMA (warp 0, after its own share of the stage): uniform descriptors, one elected lane issues =====
         tc::mbar_wait(&full[s], (it >> 1) & 1);
         tc::tc_fence_after();
+        dbg_mark(dbgm, 1, dnm, 12);                    // stage full
         const uint32_t sD = base + s * STAGE, sX = sD + 2 * PSD;
         const uint64_t b_hi = tc::smem_desc(sX, 128, W_CS), b_lo = tc::smem_desc(sX + PSX, 128, W_CS);
         if (tc::elect_one()) {
@@ -715,8 +724,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
           if (it == nst - 1) tc::tc_commit(accfull);
         }
         __syncwarp();
+        dbg_mark(dbgm, 1, dnm, 13);                    // MMAs issued
       }
     }
+    dbg_mark(dbgp, 0, dnp, 4);
     if (want_db) {
       // reduce over the 8 token lanes of a warp (lane & 7); the 8 row-block warps of a chunk half are summed below
 #pragma unroll
@@ -744,10 +755,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
   if (warp < 4) {
     // ===== epilogue: accumulators -> partial[cta][n][k] =====
     const int q = warp;
+    unsigned long long* dbge = (blockIdx.x == 0 && blockIdx.y == 0 && warp == 0 && lane == 0) ? a.dbg : nullptr;
+    int dne = 0;
+    dbg_mark(dbge, 2, dne, 20);
     if (nst > 0) {
       tc::mbar_wait(accfull, 0);
       tc::tc_fence_after();
     }
+    dbg_mark(dbge, 2, dne, 21);
     for (int mt = 0; mt < nmt; ++mt) {
       const int mrows = min(128, Nout - mt * 128);
       // M = 128: row = q*32 + lane ; M = 64: row = q*16 + lane (lanes 0-15 of each sub-partition)
@@ -782,6 +797,232 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem, ncols);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient, bulk-copy fed (dense operands: lddy == Nout, ldx == Kin -- every weight gradient of the transformer block).
+// The in-kernel timeline of the kernel above (tools/wgrad_timeline.py) showed 3.6 us per 64-token stage: 0.8 us to ISSUE the
+// stage's 160 warp-level 128-bit loads, ~1.5 us of exposed latency, ~1 us of conversion, and warp 0 -- producer and MMA issuer
+// at once -- held every stage back by another 0.9 us.  Here a stage (32 tokens) is TWO 1-D bulk async copies (the dy rows and
+// the x rows are contiguous; one copy per row was request-bound in the copy engine: 64 requests ~ 1 us), three stages in flight,
+// no registers and no LSU issue slots; sixteen producer warps convert landing -> bf16 hi/lo operand tiles; one warp issues
+// the copies, one the MMAs.
+//   landing: dense row-major fp32, read with consecutive lanes on consecutive 16-byte groups (conflict-free);
+//   operand tiles: chunk-major with the chunk stride padded to 32*16 + 16 bytes, which makes the transposing 8-byte stores of
+//   a half-warp (8 chunks x 2 halves) hit 32 different banks; the padding only changes the descriptors' stride field.
+//   thread -> (fixed 4-feature group, row slot): column sums for the bias gradient stay in registers.
+// ------------------------------------------------------------------------------------------------
+constexpr int WT2 = 32;                  // tokens per stage
+constexpr int W2_CS = WT2 * 16 + 16;     // padded chunk stride of the operand tiles (bytes)
+constexpr int W2_NL = 3;                 // landing stages
+constexpr int W2_NO = 2;                 // operand stages
+constexpr int W2_TMA_WARP = WG_NPROD, W2_MMA_WARP = WG_NPROD + 1;
+constexpr int W2_THREADS = (WG_NPROD + 2) * 32;
+
+inline uint32_t wgrad2_smem_bytes(int Nout, int Kin) {
+  return W2_NL * (uint32_t)(Nout + Kin) * WT2 * 4u + W2_NO * 2u * (uint32_t)((Nout + Kin) / 8) * W2_CS + 2048 * 4 + 256;
+}
+
+template <int NTERMS, int PDY, int PX, int WDB>
+__global__ void __launch_bounds__(W2_THREADS, 1) lin_wgrad_tma_kernel(const LinWgradArgs a) {
+  pdl_trigger();
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Nout = a.Nout, Kin = a.Kin;
+  const bool want_db = WDB < 0 ? a.want_db != 0 : WDB != 0;
+  const uint32_t LD_BYTES = (uint32_t)Nout * WT2 * 4u, LX_BYTES = (uint32_t)Kin * WT2 * 4u;   // landing blocks of a stage
+  const uint32_t LSTAGE = LD_BYTES + LX_BYTES;
+  const uint32_t PSD = (uint32_t)(Nout / 8) * W2_CS, PSX = (uint32_t)(Kin / 8) * W2_CS;       // plane strides
+  const uint32_t STAGE = 2 * PSD + 2 * PSX;
+  uint8_t* sL = smem;
+  uint8_t* sO = smem + W2_NL * LSTAGE;
+  float* sCol = reinterpret_cast<float*>(sO + W2_NO * STAGE);     // [row slots][Nout] column-sum staging (<= 2048 floats)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + 2048);
+  uint64_t* lfull = bars;                 // [W2_NL] copies landed (expect_tx)
+  uint64_t* lempty = bars + W2_NL;        // [W2_NL] producers done reading (16 warp arrivals)
+  uint64_t* ofull = bars + 2 * W2_NL;     // [W2_NO] operand tile written (16 warp arrivals)
+  uint64_t* oempty = ofull + W2_NO;       // [W2_NO] MMAs done (tcgen05.commit)
+  uint64_t* accfull = oempty + W2_NO;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
+
+  const int nmt = (Nout + 127) / 128;                 // M tiles (rows of dW)
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)(nmt * Kin)) ncols <<= 1;
+  if (tid == 0) {
+    for (int i = 0; i < W2_NL; ++i) { tc::mbar_init(&lfull[i], 1); tc::mbar_init(&lempty[i], WG_NPROD); }
+    for (int i = 0; i < W2_NO; ++i) { tc::mbar_init(&ofull[i], WG_NPROD); tc::mbar_init(&oempty[i], 1); }
+    tc::mbar_init(accfull, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == W2_MMA_WARP) tc::tmem_alloc(tmem_slot, ncols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();   // global memory is read from here on
+
+  // token range of this CTA, in units of WT2-token stages
+  const int nst_total = (a.M + WT2 - 1) / WT2;
+  const int per = (nst_total + gridDim.x - 1) / gridDim.x;
+  const int st_beg = blockIdx.x * per;
+  const int st_end = min(nst_total, st_beg + per);
+  const int nst = max(0, st_end - st_beg);
+  // producer geometry: a row of an operand is n4 = N / 4 float4 groups; rpp rows are converted per pass of the 512 threads
+  const int n4d = Nout >> 2, n4x = Kin >> 2;
+  const int rpp_d = min(WT2, (WG_NPROD * 32) / n4d), rpp_x = min(WT2, (WG_NPROD * 32) / n4x);
+
+  if (warp == W2_TMA_WARP) {
+    // ===== copy issuer: two bulk copies per stage =====
+    for (int it = 0; it < nst; ++it) {
+      const int ls = it % W2_NL;
+      tc::mbar_wait(&lempty[ls], ((it / W2_NL) & 1) ^ 1);
+      if (lane == 0) {
+        const long r0 = (long)(st_beg + it) * WT2;
+        const uint32_t rows = (uint32_t)min((long)WT2, (long)a.M - r0);
+        tc::mbar_expect_tx(&lfull[ls], rows * (uint32_t)(Nout + Kin) * 4u);
+        tc::bulk_g2s(sL + ls * LSTAGE, a.dy + r0 * Nout, rows * (uint32_t)Nout * 4u, &lfull[ls]);
+        tc::bulk_g2s(sL + ls * LSTAGE + LD_BYTES, a.x + r0 * Kin, rows * (uint32_t)Kin * 4u, &lfull[ls]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == W2_MMA_WARP) {
+    // ===== MMA issuer: uniform descriptors, one elected lane issues =====
+    const uint32_t base = tc::smem_u32(sO);
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % W2_NO;
+      tc::mbar_wait(&ofull[s], (it / W2_NO) & 1);
+      tc::tc_fence_after();
+      const uint32_t sD = base + s * STAGE, sX = sD + 2 * PSD;
+      const uint64_t b_hi = tc::smem_desc(sX, 128, W2_CS), b_lo = tc::smem_desc(sX + PSX, 128, W2_CS);
+      if (tc::elect_one()) {
+        for (int mt = 0; mt < nmt; ++mt) {
+          const int mrows = min(128, Nout - mt * 128);          // 128 or 64
+          const uint32_t idesc = tc::idesc_bf16(mrows, Kin, 1, 1);
+          const uint32_t d = tmem + (uint32_t)(mt * Kin);
+          // A = dy, B = x (both MN-major, K = tokens): hi*hi, hi*lo, lo*hi
+          const uint64_t a_hi = tc::smem_desc(sD + (uint32_t)(mt * 16) * W2_CS, 128, W2_CS);
+          const uint64_t a_lo = tc::smem_desc(sD + PSD + (uint32_t)(mt * 16) * W2_CS, 128, W2_CS);
+#pragma unroll
+          for (int ks = 0; ks < WT2 / 16; ++ks) {
+            const uint64_t dk = (uint64_t)(ks * 16);            // 16 token rows = 256 bytes = 16 address units
+            tc::mma_bf16(d, a_hi + dk, b_hi + dk, idesc, (it | ks) != 0);
+            if (NTERMS > 1) {
+              tc::mma_bf16(d, a_hi + dk, b_lo + dk, idesc, 1);
+              tc::mma_bf16(d, a_lo + dk, b_hi + dk, idesc, 1);
+            }
+          }
+        }
+        tc::tc_commit(&oempty[s]);
+        if (it == nst - 1) tc::tc_commit(accfull);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== producers =====
+    const int fd = tid % n4d, sd = tid / n4d;          // dy: float4 group of a row, row slot (active if sd < rpp_d)
+    const int fx = tid % n4x, sx = tid / n4x;          // x : likewise
+    const int pro_dy = PDY < 0 ? a.pro_dy : PDY, pro_x = PX < 0 ? a.pro_x : PX;
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};                // column sums of this thread's 4 dy features
+    auto put = [&](uint8_t* plane_hi, uint32_t PS, int f4, int row, const float4& q) {
+      __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+      tc::split_bf16(q.x, h0, l0); tc::split_bf16(q.y, h1, l1); tc::split_bf16(q.z, h2, l2); tc::split_bf16(q.w, h3, l3);
+      auto pk = [](__nv_bfloat16 u, __nv_bfloat16 v) { return (uint32_t)__bfloat16_as_ushort(u) | ((uint32_t)__bfloat16_as_ushort(v) << 16); };
+      uint8_t* d = plane_hi + (uint32_t)(f4 >> 1) * W2_CS + row * 16 + (f4 & 1) * 8;
+      *reinterpret_cast<uint2*>(d) = make_uint2(pk(h0, h1), pk(h2, h3));
+      if (NTERMS > 1) *reinterpret_cast<uint2*>(d + PS) = make_uint2(pk(l0, l1), pk(l2, l3));
+    };
+    for (int it = 0; it < nst; ++it) {
+      const int ls = it % W2_NL, s = it % W2_NO;
+      const long r0 = (long)(st_beg + it) * WT2;
+      const float4* Ld = reinterpret_cast<const float4*>(sL + ls * LSTAGE);
+      const float4* Lx = reinterpret_cast<const float4*>(sL + ls * LSTAGE + LD_BYTES);
+      uint8_t* sb = sO + s * STAGE;
+      tc::mbar_wait(&lfull[ls], (it / W2_NL) & 1);
+      tc::mbar_wait(&oempty[s], ((it / W2_NO) & 1) ^ 1);
+      if (sd < rpp_d) {
+        for (int row = sd; row < WT2; row += rpp_d) {
+          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r0 + row < a.M) {
+            q = Ld[row * n4d + fd];
+            if (pro_dy != PRO_NONE) {
+              const float4 m = drop_mult4(a.drop_dy, (uint64_t)(r0 + row) * (uint64_t)Nout + (uint64_t)(fd * 4));
+              if (pro_dy == PRO_GELU_DROP) { q.x = gelu_f(q.x); q.y = gelu_f(q.y); q.z = gelu_f(q.z); q.w = gelu_f(q.w); }
+              q.x *= m.x; q.y *= m.y; q.z *= m.z; q.w *= m.w;
+            }
+          }
+          if (want_db) { cs[0] += q.x; cs[1] += q.y; cs[2] += q.z; cs[3] += q.w; }
+          put(sb, PSD, fd, row, q);
+        }
+      }
+      if (sx < rpp_x) {
+        for (int row = sx; row < WT2; row += rpp_x) {
+          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r0 + row < a.M) {
+            q = Lx[row * n4x + fx];
+            if (pro_x != PRO_NONE) {
+              const float4 m = drop_mult4(a.drop_x, (uint64_t)(r0 + row) * (uint64_t)Kin + (uint64_t)(fx * 4));
+              if (pro_x == PRO_GELU_DROP) { q.x = gelu_f(q.x); q.y = gelu_f(q.y); q.z = gelu_f(q.z); q.w = gelu_f(q.w); }
+              q.x *= m.x; q.y *= m.y; q.z *= m.z; q.w *= m.w;
+            }
+          }
+          put(sb + 2 * PSD, PSX, fx, row, q);
+        }
+      }
+      tc::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) { tc::mbar_arrive(&ofull[s]); tc::mbar_arrive(&lempty[ls]); }
+    }
+    if (want_db && sd < rpp_d) {
+      float* o = sCol + sd * Nout + fd * 4;
+      o[0] = cs[0]; o[1] = cs[1]; o[2] = cs[2]; o[3] = cs[3];
+    }
+  }
+  __syncthreads();   // column sums staged; all roles done issuing
+  // blockIdx.y selects a Kin-wide column block of x (wide layers: one launch covers all blocks)
+  float* part = a.partial + ((long)blockIdx.y * gridDim.x + blockIdx.x) * ((long)Nout * Kin + Nout);
+  if (warp < 4) {
+    // ===== epilogue: accumulators -> partial[cta][n][k] =====
+    const int q = warp;
+    unsigned long long* dbge = (blockIdx.x == 0 && blockIdx.y == 0 && warp == 0 && lane == 0) ? a.dbg : nullptr;
+    int dne = 0;
+    if (nst > 0) {
+      tc::mbar_wait(accfull, 0);
+      tc::tc_fence_after();
+    }
+    for (int mt = 0; mt < nmt; ++mt) {
+      const int mrows = min(128, Nout - mt * 128);
+      // M = 128: row = q*32 + lane ; M = 64: row = q*16 + lane (lanes 0-15 of each sub-partition)
+      const int row = mrows == 128 ? q * 32 + lane : q * 16 + lane;
+      const bool valid = mrows == 128 || lane < 16;
+      for (int cb = 0; cb < Kin; cb += 32) {
+        float v[32];
+        if (nst > 0) tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * Kin + cb), v);
+        else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (valid) {
+          float* o = part + (long)(mt * 128 + row) * Kin + cb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+    }
+    if (want_db) {
+      float* pb = part + (long)Nout * Kin;
+      for (int n = tid; n < Nout; n += 128) {
+        float sum = 0.f;
+        if (nst > 0)
+#pragma unroll
+          for (int g = 0; g < rpp_d; ++g) sum += sCol[g * Nout + n];
+        pb[n] = sum;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == W2_MMA_WARP) tc::tmem_dealloc(tmem, ncols);
+}
+
 
 // dW (split over up to 3 destinations of rows_per_dst rows each) = sum over CTAs of the partials, fixed order.
 struct WgradReduceArgs {
@@ -854,6 +1095,24 @@ inline int lin_wgrad_launch_v(const LinWgradArgs& a, dim3 grid, uint32_t smem, c
   return EEGCLIP_OK;
 }
 
+// the bulk-copy kernel takes dense operands (a stage is one contiguous block); g_tune[9] = 1 forces the register-staged kernel
+inline bool lin_wgrad_tma_ok(const LinWgradArgs& a) {
+  return g_tune[9] == 0 && ((uintptr_t)a.dy & 15) == 0 && ((uintptr_t)a.x & 15) == 0 && a.lddy == a.Nout && a.ldx == a.Kin &&
+         wgrad2_smem_bytes(a.Nout, a.Kin) <= 227u * 1024u;
+}
+template <int NTERMS, int PDY, int PX, int WDB>
+inline int lin_wgrad_tma_launch_v(const LinWgradArgs& a, dim3 grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(lin_wgrad_tma_kernel<NTERMS, PDY, PX, WDB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return EEGCLIP_ERR_CUDA;
+    configured = true;
+  }
+  LAUNCH_PDL((lin_wgrad_tma_kernel<NTERMS, PDY, PX, WDB>), grid, W2_THREADS, wgrad2_smem_bytes(a.Nout, a.Kin), st, a);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
 template <int NTERMS>
 inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const db[3], int rows_per_dst, long ldw, cudaStream_t st,
                               const float* log_scale = nullptr, int kin_blocks = 1) {
@@ -862,11 +1121,18 @@ inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const d
   const int ctas = wgrad_token_ctas(nst, kin_blocks);
   a.want_db = (db[0] != nullptr) ? 1 : 0;
   a.policy = g_tune[1];
+  a.dbg = g_dbg_buf;
   {
     ProfScope prof(PROF_LIN_WGRAD, st);
     const dim3 grid(ctas, kin_blocks);
     const uint32_t smem = wgrad_lin_smem_bytes(a.Nout, a.Kin);
     int rc;
+    if (lin_wgrad_tma_ok(a)) {
+      if (a.pro_x == PRO_NONE && a.pro_dy == PRO_NONE && !a.want_db) rc = lin_wgrad_tma_launch_v<NTERMS, PRO_NONE, PRO_NONE, 0>(a, grid, st);
+      else if (a.pro_x == PRO_NONE && a.pro_dy == PRO_NONE && a.want_db) rc = lin_wgrad_tma_launch_v<NTERMS, PRO_NONE, PRO_NONE, 1>(a, grid, st);
+      else if (a.pro_x == PRO_NONE && a.pro_dy == PRO_DROP && a.want_db) rc = lin_wgrad_tma_launch_v<NTERMS, PRO_DROP, PRO_NONE, 1>(a, grid, st);
+      else rc = lin_wgrad_tma_launch_v<NTERMS, -1, -1, -1>(a, grid, st);
+    } else
     if (g_tune[3] == 0 && a.pro_x == PRO_NONE && a.pro_dy == PRO_NONE && !a.want_db) rc = lin_wgrad_launch_v<NTERMS, PRO_NONE, PRO_NONE, 0>(a, grid, smem, st);
     else if (g_tune[3] == 0 && a.pro_x == PRO_NONE && a.pro_dy == PRO_NONE && a.want_db) rc = lin_wgrad_launch_v<NTERMS, PRO_NONE, PRO_NONE, 1>(a, grid, smem, st);
     else if (g_tune[3] == 0 && a.pro_x == PRO_NONE && a.pro_dy == PRO_DROP && a.want_db) rc = lin_wgrad_launch_v<NTERMS, PRO_DROP, PRO_NONE, 1>(a, grid, smem, st);
