@@ -872,16 +872,21 @@ __global__ void __launch_bounds__(W2_THREADS, 1) lin_wgrad_tma_kernel(const LinW
 
   if (warp == W2_TMA_WARP) {
     // ===== copy issuer: two bulk copies per stage =====
+    const bool dense_dy = a.lddy == Nout, dense_x = a.ldx == Kin && gridDim.y == 1;
     for (int it = 0; it < nst; ++it) {
       const int ls = it % W2_NL;
       tc::mbar_wait(&lempty[ls], ((it / W2_NL) & 1) ^ 1);
-      if (lane == 0) {
-        const long r0 = (long)(st_beg + it) * WT2;
-        const uint32_t rows = (uint32_t)min((long)WT2, (long)a.M - r0);
-        tc::mbar_expect_tx(&lfull[ls], rows * (uint32_t)(Nout + Kin) * 4u);
-        tc::bulk_g2s(sL + ls * LSTAGE, a.dy + r0 * Nout, rows * (uint32_t)Nout * 4u, &lfull[ls]);
-        tc::bulk_g2s(sL + ls * LSTAGE + LD_BYTES, a.x + r0 * Kin, rows * (uint32_t)Kin * 4u, &lfull[ls]);
-      }
+      const long r0 = (long)(st_beg + it) * WT2;
+      const int rows = (int)min((long)WT2, (long)a.M - r0);
+      if (lane == 0) tc::mbar_expect_tx(&lfull[ls], (uint32_t)rows * (uint32_t)(Nout + Kin) * 4u);
+      __syncwarp();
+      // a dense operand (leading dimension == width) is one copy per stage, a strided one (column block of a wider tensor:
+      // speech features, LSTM gate buffers) one copy per row, issued by the lane that owns the row
+      uint8_t* ld = sL + ls * LSTAGE;
+      if (dense_dy) { if (lane == 0) tc::bulk_g2s(ld, a.dy + r0 * Nout, (uint32_t)rows * (uint32_t)Nout * 4u, &lfull[ls]); }
+      else if (lane < rows) tc::bulk_g2s(ld + (uint32_t)lane * Nout * 4u, a.dy + (r0 + lane) * a.lddy, (uint32_t)Nout * 4u, &lfull[ls]);
+      if (dense_x) { if (lane == 0) tc::bulk_g2s(ld + LD_BYTES, a.x + r0 * Kin, (uint32_t)rows * (uint32_t)Kin * 4u, &lfull[ls]); }
+      else if (lane < rows) tc::bulk_g2s(ld + LD_BYTES + (uint32_t)lane * Kin * 4u, a.x + (r0 + lane) * a.ldx + (long)blockIdx.y * Kin, (uint32_t)Kin * 4u, &lfull[ls]);
       __syncwarp();
     }
   } else if (warp == W2_MMA_WARP) {
@@ -1097,8 +1102,10 @@ inline int lin_wgrad_launch_v(const LinWgradArgs& a, dim3 grid, uint32_t smem, c
 
 // the bulk-copy kernel takes dense operands (a stage is one contiguous block); g_tune[9] = 1 forces the register-staged kernel
 inline bool lin_wgrad_tma_ok(const LinWgradArgs& a) {
-  return g_tune[9] == 0 && ((uintptr_t)a.dy & 15) == 0 && ((uintptr_t)a.x & 15) == 0 && a.lddy == a.Nout && a.ldx == a.Kin &&
-         wgrad2_smem_bytes(a.Nout, a.Kin) <= 227u * 1024u;
+  // at most one strided operand: per-row copies of BOTH would be 64 requests per stage (request-bound in the copy engine)
+  const bool dense_dy = a.lddy == a.Nout, dense_x = a.ldx == a.Kin;
+  return g_tune[9] == 0 && ((uintptr_t)a.dy & 15) == 0 && ((uintptr_t)a.x & 15) == 0 && (a.lddy & 3) == 0 && (a.ldx & 3) == 0 &&
+         (dense_dy || dense_x) && wgrad2_smem_bytes(a.Nout, a.Kin) <= 227u * 1024u;
 }
 template <int NTERMS, int PDY, int PX, int WDB>
 inline int lin_wgrad_tma_launch_v(const LinWgradArgs& a, dim3 grid, cudaStream_t st) {
