@@ -32,7 +32,7 @@ run(); torch.cuda.synchronize()
 _lib.call("eegclip_debug_buffer", None)
 d = dbg.cpu().view(3, 256)
 t0 = min(int(d[w_, 1]) for w_ in range(3) if int(d[w_, 255]) > 0)
-names = {0: "prod:start", 1: "prod:  loads issued", 2: "prod:  slot free + data", 3: "prod:  converted+arrived", 4: "prod:done",
+names = {0: "prod:start", 1: "prod:  data landed", 2: "prod:  operand slot free", 3: "prod:  converted+arrived", 4: "prod:done",
          12: "mma:stage full", 13: "mma:issued", 20: "epi:start", 21: "epi:acc full", 30: "tma:slot free, copies issued"}
 ev = []
 for w_ in range(3):

@@ -873,9 +873,12 @@ __global__ void __launch_bounds__(W2_THREADS, 1) lin_wgrad_tma_kernel(const LinW
   if (warp == W2_TMA_WARP) {
     // ===== copy issuer: two bulk copies per stage =====
     const bool dense_dy = a.lddy == Nout, dense_x = a.ldx == Kin && gridDim.y == 1;
+    unsigned long long* dbgt = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? a.dbg : nullptr;
+    int dnt = 0;
     for (int it = 0; it < nst; ++it) {
       const int ls = it % W2_NL;
       tc::mbar_wait(&lempty[ls], ((it / W2_NL) & 1) ^ 1);
+      dbg_mark(dbgt, 2, dnt, 30);
       const long r0 = (long)(st_beg + it) * WT2;
       const int rows = (int)min((long)WT2, (long)a.M - r0);
       if (lane == 0) tc::mbar_expect_tx(&lfull[ls], (uint32_t)rows * (uint32_t)(Nout + Kin) * 4u);
@@ -892,10 +895,13 @@ __global__ void __launch_bounds__(W2_THREADS, 1) lin_wgrad_tma_kernel(const LinW
   } else if (warp == W2_MMA_WARP) {
     // ===== MMA issuer: uniform descriptors, one elected lane issues =====
     const uint32_t base = tc::smem_u32(sO);
+    unsigned long long* dbgm = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? a.dbg : nullptr;
+    int dnm = 0;
     for (int it = 0; it < nst; ++it) {
       const int s = it % W2_NO;
       tc::mbar_wait(&ofull[s], (it / W2_NO) & 1);
       tc::tc_fence_after();
+      dbg_mark(dbgm, 1, dnm, 12);
       const uint32_t sD = base + s * STAGE, sX = sD + 2 * PSD;
       const uint64_t b_hi = tc::smem_desc(sX, 128, W2_CS), b_lo = tc::smem_desc(sX + PSX, 128, W2_CS);
       if (tc::elect_one()) {
@@ -920,20 +926,24 @@ __global__ void __launch_bounds__(W2_THREADS, 1) lin_wgrad_tma_kernel(const LinW
         if (it == nst - 1) tc::tc_commit(accfull);
       }
       __syncwarp();
+      dbg_mark(dbgm, 1, dnm, 13);
     }
   } else {
     // ===== producers =====
+    unsigned long long* dbgp = (blockIdx.x == 0 && blockIdx.y == 0 && warp == 3 && lane == 0) ? a.dbg : nullptr;
+    int dnp = 0;
+    dbg_mark(dbgp, 0, dnp, 0);
     const int fd = tid % n4d, sd = tid / n4d;          // dy: float4 group of a row, row slot (active if sd < rpp_d)
     const int fx = tid % n4x, sx = tid / n4x;          // x : likewise
     const int pro_dy = PDY < 0 ? a.pro_dy : PDY, pro_x = PX < 0 ? a.pro_x : PX;
     float cs[4] = {0.f, 0.f, 0.f, 0.f};                // column sums of this thread's 4 dy features
     auto put = [&](uint8_t* plane_hi, uint32_t PS, int f4, int row, const float4& q) {
-      __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-      tc::split_bf16(q.x, h0, l0); tc::split_bf16(q.y, h1, l1); tc::split_bf16(q.z, h2, l2); tc::split_bf16(q.w, h3, l3);
-      auto pk = [](__nv_bfloat16 u, __nv_bfloat16 v) { return (uint32_t)__bfloat16_as_ushort(u) | ((uint32_t)__bfloat16_as_ushort(v) << 16); };
+      uint2 h, l;
+      tc::split2(q.x, q.y, h.x, l.x);
+      tc::split2(q.z, q.w, h.y, l.y);
       uint8_t* d = plane_hi + (uint32_t)(f4 >> 1) * W2_CS + row * 16 + (f4 & 1) * 8;
-      *reinterpret_cast<uint2*>(d) = make_uint2(pk(h0, h1), pk(h2, h3));
-      if (NTERMS > 1) *reinterpret_cast<uint2*>(d + PS) = make_uint2(pk(l0, l1), pk(l2, l3));
+      *reinterpret_cast<uint2*>(d) = h;
+      if (NTERMS > 1) *reinterpret_cast<uint2*>(d + PS) = l;
     };
     for (int it = 0; it < nst; ++it) {
       const int ls = it % W2_NL, s = it % W2_NO;
@@ -942,7 +952,9 @@ __global__ void __launch_bounds__(W2_THREADS, 1) lin_wgrad_tma_kernel(const LinW
       const float4* Lx = reinterpret_cast<const float4*>(sL + ls * LSTAGE + LD_BYTES);
       uint8_t* sb = sO + s * STAGE;
       tc::mbar_wait(&lfull[ls], (it / W2_NL) & 1);
+      dbg_mark(dbgp, 0, dnp, 1);
       tc::mbar_wait(&oempty[s], ((it / W2_NO) & 1) ^ 1);
+      dbg_mark(dbgp, 0, dnp, 2);
       if (sd < rpp_d) {
         for (int row = sd; row < WT2; row += rpp_d) {
           float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -975,6 +987,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) lin_wgrad_tma_kernel(const LinW
       tc::fence_async_smem();
       __syncwarp();
       if (lane == 0) { tc::mbar_arrive(&ofull[s]); tc::mbar_arrive(&lempty[ls]); }
+      dbg_mark(dbgp, 0, dnp, 3);
     }
     if (want_db && sd < rpp_d) {
       float* o = sCol + sd * Nout + fd * 4;
