@@ -17,7 +17,7 @@ cap() {  # name regex skip count [extra]
 cap conv    'conv64_tc_kernel'      2 2 "--import-source on"
 cap wgrad   'wgrad64_tc_kernel'     1 1
 cap lin     'lin_tc_kernel'         10 8
-cap linwg   'lin_wgrad_tc_kernel'   4 4
+cap linwg   'lin_wgrad_t(c|ma)_kernel' 4 5
 cap attn    'attn_(fwd|bwd)_tc'     1 1
 cap attnb   'attn_bwd_tc'           1 1
 cap ew      'ln_ct|ln64|ct_reduce|add_kernel|adamw' 4 10
