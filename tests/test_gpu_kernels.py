@@ -92,7 +92,7 @@ def test_attention_tc_vs_fp32(cm, lib, T, B, train, p):
 # token GEMMs through the C ABI: every (N, K) family, ragged M, against fp64
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(1000, 64, 64), (4100, 192, 64), (777, 256, 64), (2048, 64, 256), (1300, 64, 1024), (520, 64, 192),
-                                   (640, 128, 128)])
+                                   (640, 128, 128), (5, 64, 64), (33, 192, 64), (31, 64, 256)])
 def test_linear_tc_vs_fp64(cm, M, N, K):
     torch.manual_seed(M + N + K)
     x = torch.randn(M, K, device=DEV, requires_grad=True)
