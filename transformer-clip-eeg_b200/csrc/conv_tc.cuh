@@ -654,6 +654,163 @@ __global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a)
   if (warp == 2) tc::tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient, double-buffered over time slices (the shipped variant).  The kernel above stages a whole sample (u and dy
+// tiles, 168 KB at T = 320), issues its MMAs, waits, stages the next one: ~3.5 us of staging exposed per 24 us of MMAs.  Here the
+// contraction over time is cut into S slices of TH = T / S rows (S = 2, 4 above T = 384): two slice buffers (86 KB each at
+// T = 320), seven producer warps stage slice i+1 while warp 0 issues the MMAs of slice i (mbarrier full / empty per buffer).
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int wgrad_db_slices(int T) { return T <= 384 ? 2 : 4; }
+__host__ __device__ inline uint32_t wgrad_db_smem_bytes(int T) {
+  const uint32_t TH = (uint32_t)T / wgrad_db_slices(T);
+  return 2u * (2u * 8u * (TH + WG_TAPS - 1) * 16u + 2u * 8u * TH * 16u) + 128;
+}
+
+template <int NTERMS>
+__global__ void __launch_bounds__(256, 1) wgrad64_db_kernel(const WgradTcArgs a) {
+  pdl_trigger();
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntg = a.taps / WG_TAPS, nci = a.Cin / CH;
+  const int tg = blockIdx.x % ntg, cib = (blockIdx.x / ntg) % nci, cob = blockIdx.x / (ntg * nci), grp = blockIdx.y;
+  const int T = a.T, TAPS = a.taps;
+  const int S = wgrad_db_slices(T), TH = T / S, TUH = TH + WG_TAPS - 1;
+  const int k0 = tg * WG_TAPS;
+  const uint32_t CSU = (uint32_t)TUH * 16u, PSU = 8u * CSU;
+  const uint32_t CSD = (uint32_t)TH * 16u, PSD = 8u * CSD;
+  const uint32_t BUF = 2u * PSU + 2u * PSD;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2u * BUF);
+  uint64_t* full = bars;        // [2] producers -> MMA (7 warp arrivals)
+  uint64_t* empty = bars + 2;   // [2] MMA -> producers (tcgen05.commit)
+  uint64_t* accfull = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&full[i], 7); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(accfull, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();   // global memory is read from here on
+  const int nsamp = grp < a.B ? (a.B - grp + a.groups - 1) / a.groups : 0;
+  const int nitems = nsamp * S;                      // item i = (sample grp + (i / S) * groups, time slice i % S)
+
+  if (warp == 0) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = tc::idesc_bf16(64, CH, 1, 1);   // both operands MN-major (K = time)
+    const int ksteps = TH >> 4;
+    for (int i = 0; i < nitems; ++i) {
+      const int s = i & 1;
+      tc::mbar_wait(&full[s], (i >> 1) & 1);
+      tc::tc_fence_after();
+      const uint32_t sU_u = tc::smem_u32(smem + s * BUF), sD_u = sU_u + 2u * PSU;
+      if (tc::elect_one()) {
+        for (int j = 0; j < WG_TAPS; ++j) {
+          const uint32_t d = tmem + (uint32_t)(j >> 1) * 64u + ((uint32_t)((j & 1) * 16) << 16);
+          // A = dy, B = u (both MN-major, K = time): hi*hi, hi*lo, lo*hi
+          const uint64_t a_hi = tc::smem_desc(sD_u, 128, CSD), a_lo = tc::smem_desc(sD_u + PSD, 128, CSD);
+          const uint64_t b_hi = tc::smem_desc(sU_u + (uint32_t)j * 16u, 128, CSU), b_lo = tc::smem_desc(sU_u + PSU + (uint32_t)j * 16u, 128, CSU);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t dk = (uint64_t)(ks * 16);                     // 16 time rows = 256 bytes = 16 address units
+            tc::mma_bf16(d, a_hi + dk, b_hi + dk, idesc, (uint32_t)((i | ks) != 0));
+            if (NTERMS > 1) {
+              tc::mma_bf16(d, a_hi + dk, b_lo + dk, idesc, 1);
+              tc::mma_bf16(d, a_lo + dk, b_hi + dk, idesc, 1);
+            }
+          }
+        }
+        tc::tc_commit(&empty[s]);
+        if (i == nitems - 1) tc::tc_commit(accfull);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== producers (warps 1-7): stage u rows [t0 + k0 - PL, + TUH) and dy rows [t0, t0 + TH) of the item's sample =====
+    const int ptid = tid - 32;
+    const int ldx = a.Cin, ldy = a.Cout;
+    constexpr int WG_U = 6, NPT = 224;
+    const int nu = TUH * 8, total = nu + TH * 8;     // work units [0, nu): u tile; [nu, total): dy tile
+    for (int i = 0; i < nitems; ++i) {
+      const int s = i & 1;
+      const int b = grp + (i / S) * a.groups, t0 = (i % S) * TH;
+      const float* xb = a.xin + (long)b * T * ldx + cib * CH;
+      const float* kb = a.skip ? a.skip + (long)b * T * ldx + cib * CH : nullptr;
+      const float* db = a.dypad + ((long)b * (T + TAPS - 1) + a.PLb + t0) * ldy + cob * CH;
+      uint8_t* sU = smem + s * BUF;
+      uint8_t* sD = sU + 2u * PSU;
+      tc::mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);
+      for (int base = 0; base < total; base += NPT * WG_U) {
+        float4 x[WG_U][2], y[WG_U][2];
+#pragma unroll
+        for (int u = 0; u < WG_U; ++u) {
+          const int idx = base + u * NPT + ptid;
+          x[u][0] = x[u][1] = y[u][0] = y[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < nu) {
+            const int r = idx >> 3, ch = idx & 7;
+            const int t = t0 + r + k0 - a.PL;
+            if (t >= 0 && t < T) {
+              const float4* p = reinterpret_cast<const float4*>(xb + (long)t * ldx + ch * 8);
+              x[u][0] = __ldg(p); x[u][1] = __ldg(p + 1);
+              if (kb) {
+                const float4* q = reinterpret_cast<const float4*>(kb + (long)t * ldx + ch * 8);
+                y[u][0] = __ldg(q); y[u][1] = __ldg(q + 1);
+              }
+            }
+          } else if (idx < total) {
+            const int i2 = idx - nu;
+            const float4* p = reinterpret_cast<const float4*>(db + (long)(i2 >> 3) * ldy + (i2 & 7) * 8);
+            x[u][0] = __ldg(p); x[u][1] = __ldg(p + 1);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < WG_U; ++u) {
+          const int idx = base + u * NPT + ptid;
+          if (idx < total) {
+            const float v[8] = {x[u][0].x + y[u][0].x, x[u][0].y + y[u][0].y, x[u][0].z + y[u][0].z, x[u][0].w + y[u][0].w,
+                                x[u][1].x + y[u][1].x, x[u][1].y + y[u][1].y, x[u][1].z + y[u][1].z, x[u][1].w + y[u][1].w};
+            uint4 hi, lo;
+            tc::split8(v, hi, lo);
+            const bool isu = idx < nu;
+            const int i2 = isu ? idx : idx - nu;
+            uint8_t* d = isu ? sU + (i2 & 7) * CSU + (i2 >> 3) * 16 : sD + (i2 & 7) * CSD + (i2 >> 3) * 16;
+            *reinterpret_cast<uint4*>(d) = hi;
+            if (NTERMS > 1) *reinterpret_cast<uint4*>(d + (isu ? PSU : PSD)) = lo;
+          }
+        }
+      }
+      tc::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&full[s]);
+    }
+  }
+  __syncthreads();
+  // ---- epilogue: 16 accumulators -> partial[grp][tap][co][ci] ----
+  if (warp >= 4 && nitems > 0) {
+    tc::mbar_wait(accfull, 0);
+    tc::tc_fence_after();
+    const int q = warp - 4;
+    const int co = q * 16 + (lane & 15);
+    for (int cb = 0; cb < 8; ++cb) {
+      const int tap = k0 + cb * 2 + (lane >> 4);
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + cb * 64;
+      float* o = a.partial + (((long)grp * TAPS + tap) * a.Cout + cob * CH + co) * a.Cin + cib * CH;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tc::tmem_ld32(taddr + half * 32, v);
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(o + half * 32 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem, 512);
+}
+
 // dW[co][ci][k] = sum_g partial[g][k][co][ci]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int groups, int TAPS, int Cin, int Cout) {
   pdl_sync();
@@ -760,6 +917,17 @@ inline int wgrad_tc_launch(const convtc::WgradTcArgs& a, cudaStream_t st) {
   }
   dim3 grid((a.taps / convtc::WG_TAPS) * (a.Cin / convtc::CH) * (a.Cout / convtc::CH), a.groups);
   ProfScope prof(PROF_WGRAD_TC, st);
+  if (g_tune[12] == 0) {   // shipped: double-buffered over time slices; g_tune[12] = 1 selects the single-buffer kernel (A/B timing)
+    static bool configured_db = false;
+    if (!configured_db) {
+      if (cudaFuncSetAttribute(convtc::wgrad64_db_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        return EEGCLIP_ERR_CUDA;
+      configured_db = true;
+    }
+    LAUNCH_PDL((convtc::wgrad64_db_kernel<NTERMS>), grid, 256, convtc::wgrad_db_smem_bytes(a.T), st, a);
+    LAUNCH_CHECK();
+    return EEGCLIP_OK;
+  }
   LAUNCH_PDL((convtc::wgrad64_tc_kernel<NTERMS>), grid, 256, convtc::wgrad_smem_bytes(a.T), st, a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
