@@ -124,7 +124,7 @@ int eegclip_bilstm_forward(const eegclip_bilstm_desc* dp, const float* const* pa
     }
     ProfScope prof(PROF_LSTM, st);
     LAUNCH_PDL((lstm::lstm128_fwd_kernel), dim3(ceil_div(d.B, lstm::LNB), 2), 512, lstm::L128_SMEM, st, params[1], params[5], G, L.GS, out,
-                                                                                             save + L.cs, save + L.hp, d.B, d.T);
+                                                                                             save + L.cs, save + L.hp, d.B, d.T, g_dbg_buf);
     LAUNCH_CHECK();
   } else {
     ProfScope prof(PROF_LSTM, st);

@@ -41,10 +41,16 @@ constexpr int L128_SMEM = (16 * LG * 4 + LHS + LNB * LG) * 4;         // W half 
 
 __global__ void __launch_bounds__(512, 1) lstm128_fwd_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
                                                             float* __restrict__ G, int GS, float* __restrict__ out,
-                                                            float* __restrict__ Cs, float* __restrict__ Hp, int B, int T) {
+                                                            float* __restrict__ Cs, float* __restrict__ Hp, int B, int T, unsigned long long* dbg) {
   pdl_sync();
   extern __shared__ __align__(16) float sml[];
   float4* Wsm = reinterpret_cast<float4*>(sml);          // [j = 16][tid 512] : rows 2,3 of the thread's tile
+  // development timeline: thread 0 of CTA (0,0) stamps the phases of the first steps (tools/lstm_timeline.py)
+  unsigned long long* dbgp = (dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ? dbg : nullptr;
+  int dbn = 0;
+  auto stamp = [&](int ev) {
+    if (dbgp && dbn < 120) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); dbgp[2 * dbn] = (unsigned long long)ev; dbgp[2 * dbn + 1] = t_; ++dbn; dbgp[255] = (unsigned long long)dbn; }
+  };
   float* hs = sml + 16 * LG * 4;                         // h of the 4 sequences, padded (see hidx)
   float* pre = hs + LHS;                                 // [seq 4][512]
   const int dir = blockIdx.y, b0 = blockIdx.x * LNB;
@@ -74,6 +80,7 @@ __global__ void __launch_bounds__(512, 1) lstm128_fwd_kernel(const float* __rest
   for (int step = 0; step < T; ++step) {
     const int t = dir ? T - 1 - step : step;
     const long row = (long)b * T + t;
+    stamp(0);
     float gx[4] = {0.f, 0.f, 0.f, 0.f};
     if (live) {
 #pragma unroll
@@ -118,8 +125,10 @@ __global__ void __launch_bounds__(512, 1) lstm128_fwd_kernel(const float* __rest
       }
       if (q == kq) mine = make_float4(v[0], v[1], v[2], v[3]);
     }
+    stamp(1);
     *reinterpret_cast<float4*>(pre + kq * LG + rg * 4) = mine;
     __syncthreads();
+    stamp(2);
     // ---- gates, state update (thread = (u, s)) ----
     const float hprev = hs[hidx(s, u)];
     const float ai = pre[s * LG + u] + gx[0], af = pre[s * LG + LH + u] + gx[1];
@@ -135,6 +144,7 @@ __global__ void __launch_bounds__(512, 1) lstm128_fwd_kernel(const float* __rest
       Cs[row * 256 + dir * LH + u] = c;
       Hp[row * 256 + dir * LH + u] = hprev;
     }
+    stamp(3);
     __syncthreads();
   }
 }
