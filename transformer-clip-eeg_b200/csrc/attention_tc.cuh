@@ -267,6 +267,8 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_tc_kernel(const float* __rest
   __syncthreads();
   const float zero[4] = {0.f, 0.f, 0.f, 0.f};
   const float dscale = drop.scale;
+  // Cost split of this loop (timing experiments at B = 256, depth 10): the whole dQ product below (8 half-filled MMAs, 16 LDS,
+  // staging stores, the compare-and-swap adds) is 0.77 ms of the 2.88 ms per step; the compare-and-swap adds alone 0.12 ms.
   // (measured and rejected: starting every warp at a different query block so that the shared-memory compare-and-swap adds of
   //  dQ do not collide -- 3.16 ms per step against 2.88 ms for the lock-step order)
   for (int q0 = 0; q0 < T; q0 += 8) {
