@@ -275,3 +275,17 @@ def test_pdl_off_matches_pdl_on(cm, lib):
     assert torch.equal(outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1:], outs[1][1:]):
         assert rel_err(a, b) < 1e-5
+
+
+def test_device_prefetcher_fp32_and_fp16_staging(lib):
+    """The input pipeline hands back exactly the host batches (fp32 staging) or their fp16 rounding (opt-in staging), in order."""
+    from transformer_clip_eeg_b200.train_clip_final import DevicePrefetcher
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randn(3, 64, 64, generator=g), [torch.randn(3, 64, 1024, generator=g)], torch.arange(3) + 10 * i, None) for i in range(5)]
+    for dt in (None, torch.float16):
+        got = [(e.clone(), s.clone(), i.clone()) for e, s, i in DevicePrefetcher(batches, torch.device(DEV), speech_stage_dtype=dt)]
+        assert len(got) == len(batches)
+        for (e, s, i), (he, hs, hi, _) in zip(got, batches):
+            assert torch.equal(e.cpu(), he) and torch.equal(i.cpu(), hi) and s.dtype == torch.float32
+            ref = hs[0] if dt is None else hs[0].half().float()
+            assert torch.equal(s.cpu(), ref)
