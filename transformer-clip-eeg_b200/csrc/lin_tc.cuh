@@ -156,10 +156,14 @@ __device__ __forceinline__ void load_chunk(ChunkRegs<ROWS, NPW>& R, const float*
 }
 
 // prologue + bf16 hi/lo split + shared-memory store of the loaded share
+// nxt_src != nullptr: as soon as iteration `it` of the chunk has been converted, the loads of iteration `it` of a LATER chunk (rows
+// nxt_row0.., columns nxt_col0..) are issued into the same registers -- a rolling prefetch that keeps two chunks of loads in
+// flight per thread without a third register set.
 template <int ROWS, int NTERMS, int NPW, int PRO /* -1: runtime `pro` */>
-__device__ __forceinline__ void convert_chunk(const ChunkRegs<ROWS, NPW>& R, long row0, long rows_total, int col0, int ncols_total,
+__device__ __forceinline__ void convert_chunk(ChunkRegs<ROWS, NPW>& R, long row0, long rows_total, int col0, int ncols_total,
                                               uint8_t* dst, uint32_t CS, uint32_t PS, int pw, int lane, int pro, const Drop& drop,
-                                              float* colsum /* nullptr or 8 running sums */) {
+                                              float* colsum /* nullptr or 8 running sums */, const float* __restrict__ nxt_src = nullptr,
+                                              long nxt_ld = 0, long nxt_row0 = 0, int nxt_col0 = 0, int policy = 0) {
   constexpr int ITERS = (ROWS / 8) * 2 / NPW;
   const int ch = (pw & 1) * 4 + (lane >> 3);
   const int prog = PRO < 0 ? pro : PRO;
@@ -208,6 +212,15 @@ __device__ __forceinline__ void convert_chunk(const ChunkRegs<ROWS, NPW>& R, lon
     uint8_t* d = dst + ch * CS + rl * 16;
     *reinterpret_cast<uint4*>(d) = hi;
     if (NTERMS > 1) *reinterpret_cast<uint4*>(d + PS) = lo;
+    if (nxt_src) {
+      const long r = nxt_row0 + rl;
+      if (r < rows_total) {
+        const float4* p = reinterpret_cast<const float4*>(nxt_src + r * nxt_ld + nxt_col0 + ch * 8);
+        R.x0[it] = ld_act(p, policy); R.x1[it] = ld_act(p + 1, policy);
+      } else {
+        R.x0[it] = make_float4(0.f, 0.f, 0.f, 0.f); R.x1[it] = R.x0[it];
+      }
+    }
   }
 }
 
@@ -296,8 +309,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
       // software-pipelined: chunk c+1's loads are issued before chunk c is converted (2 x 8 float4 per thread in flight)
       const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
       const int total = my_tiles * nchunk;
+      // two chunks of loads in flight per thread at all times: R[0], R[1] are loaded up front, and while chunk c is converted
+      // its registers are refilled, iteration by iteration, with chunk c + 2 (in-kernel timeline: with one-chunk look-ahead the
+      // chunks arrived in pairs with ~2 us of exposed latency between the pairs)
       ChunkRegs<BM, NPROD> R[2];
+      auto chunk_pos = [&](int c_, int& tile_, int& kc_) { tile_ = blockIdx.x + (c_ / nchunk) * gridDim.x; kc_ = c_ % nchunk; };
       if (total > 0) load_chunk<BM, NPROD>(R[0], a.A, a.lda, (long)blockIdx.x * BM, a.M, 0, pw, lane, a.policy);
+      if (total > 1) { int t1, k1; chunk_pos(1, t1, k1); load_chunk<BM, NPROD>(R[1], a.A, a.lda, (long)t1 * BM, a.M, k1 * KC, pw, lane, a.policy); }
       int tile = blockIdx.x, kc = 0;
       for (int c = 0; c < total; c += 2) {
 #pragma unroll
@@ -305,11 +323,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
           if (c + u < total) {
             int ntile = tile, nkc = kc + 1;
             if (nkc == nchunk) { nkc = 0; ntile += gridDim.x; }
-            if (c + u + 1 < total) load_chunk<BM, NPROD>(R[u ^ 1], a.A, a.lda, (long)ntile * BM, a.M, nkc * KC, pw, lane, a.policy);
+            int t2 = 0, k2 = 0;
+            const bool more = c + u + 2 < total;
+            if (more) chunk_pos(c + u + 2, t2, k2);
             tc::mbar_wait(&empty[s], ph ^ 1);
             dbg_mark(dbg, 0, dn, 1);
             convert_chunk<BM, NTERMS, NPROD, PRO>(R[u], (long)tile * BM, a.M, kc * KC, K, sA + s * A_STAGE, A_CS, A_PLANE, pw, lane, a.pro,
-                                                  a.pro_drop, nullptr);
+                                                  a.pro_drop, nullptr, more ? a.A : nullptr, a.lda, (long)t2 * BM, k2 * KC, a.policy);
             tc::fence_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&full[s]);
