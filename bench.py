@@ -109,7 +109,7 @@ def cpu_port_step_fn(batch):
         opt.zero_grad()
         l_tot.backward()
         opt.step()
-        return float(l_ce)
+        return float(l_ce.detach())
     return step
 
 
