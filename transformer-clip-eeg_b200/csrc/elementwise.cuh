@@ -57,6 +57,24 @@ inline int add_f32(const float* a, const float* b, float* out, long n, cudaStrea
   return EEGCLIP_OK;
 }
 
+// out = a + b + c, float4 (the two skip-gradient contributions of an interleaved layer in one pass)
+__global__ void add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, float* __restrict__ out,
+                            long n4) {
+  pdl_sync();
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<const float4*>(a)[i];
+  const float4 w = reinterpret_cast<const float4*>(b)[i], u = reinterpret_cast<const float4*>(c)[i];
+  v.x += w.x + u.x; v.y += w.y + u.y; v.z += w.z + u.z; v.w += w.w + u.w;
+  reinterpret_cast<float4*>(out)[i] = v;
+}
+inline int add3_f32(const float* a, const float* b, const float* c, float* out, long n, cudaStream_t st) {
+  long n4 = n / 4;
+  LAUNCH_PDL((add3_kernel), (unsigned)((n4 + 255) / 256), 256, 0, st, a, b, c, out, n4);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
 // out[i] = in[i] * dropmult(i)      (backward of a residual-branch dropout)
 __global__ void drop_mul_kernel(const float* __restrict__ in, float* __restrict__ out, long n4, Drop d) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

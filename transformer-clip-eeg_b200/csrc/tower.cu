@@ -564,11 +564,13 @@ int eegclip_tower_backward(const eegclip_tower_desc* dp, const float* const* par
       const bool last = (i == d.depth - 1);
       XfSave xs = xf_save(save, L, i);
       TRY(xf_block_bwd(d, i, xf_at<XfP>(params, d.n_conv, i), xf_at<XfG>(grads, d.n_conv, i), cb + L.c_out, xs, dz, dz2, w, st));
-      if (!last) TRY(add_f32(w.deeg, dz2, w.deeg, n * C, st));  // skip into the transformer input
       const float* xin = (i == 0) ? eegx : xf_save(save, L, i - 1).zout;
       TRY(conv_block_bwd(d.math, xin, eegx, conv_at<ConvP>(params, i), conv_at<ConvG>(grads, i), cb + L.c_y, cb + L.c_stats, dz2, dz,
                          w.upad, w.dypad, w.wtmp, w.tc, d.B, d.T, C, C, d.taps, 0, make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st));
-      TRY(add_f32(w.deeg, dz, w.deeg, n * C, st));              // skip into the conv input
+      // skip gradients into eeg_x: the transformer input (dz2, not on the last layer, clip_model.py:463-466) and the conv input (dz);
+      // dz2 is still intact here (conv_block_bwd only reads it), so both are added in one pass.  (fp32 sum order: deeg + (dz2 + dz))
+      if (!last) TRY(add3_f32(w.deeg, dz2, dz, w.deeg, n * C, st));
+      else TRY(add_f32(w.deeg, dz, w.deeg, n * C, st));
     }
     TRY(add_f32(w.deeg, dz, w.deeg, n * C, st));                // x_0 == eeg_x itself
   } else {
