@@ -42,16 +42,19 @@ def build(force=False, verbose=False):
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
         return LIB
-    objs = []
+    objs, procs = [], []
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    for src in SOURCES:
+    for src in SOURCES:                                   # the translation units compile concurrently
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
         cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
-        subprocess.run(cmd, check=True)
+        procs.append((cmd, subprocess.Popen(cmd)))
         objs.append(obj)
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
     cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-Xcompiler", "-fPIC"]
     subprocess.run(cmd, check=True)
     with open(stamp, "w") as f:
