@@ -811,18 +811,33 @@ __global__ void __launch_bounds__(256, 1) wgrad64_db_kernel(const WgradTcArgs a)
   if (warp == 2) tc::tmem_dealloc(tmem, 512);
 }
 
-// dW[co][ci][k] = sum_g partial[g][k][co][ci]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int groups, int TAPS, int Cin, int Cout) {
+// dW[co][ci][k] = sum_g partial[g][k][co][ci]   (fixed order: deterministic)
+// grid (TAPS / 16, Cin / 32, Cout), block 256: a 16-tap x 32-channel tile is summed over the groups with coalesced reads (ci
+// fastest) and transposed through shared memory so that the (co, ci, k) weight-gradient layout is written with k fastest.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int groups, int TAPS,
+                                                          int Cin, int Cout) {
   pdl_sync();
+  __shared__ float tile[16][33];
+  const int k0 = blockIdx.x * 16, ci0 = blockIdx.y * 32, co = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // ty: 0..7
   const long per = (long)TAPS * Cout * Cin;
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over (k * Cout + co) * Cin + ci
-  if (i >= per) return;
-  float s = 0.f;
-  for (int g = 0; g < groups; ++g) s += partial[(long)g * per + i];
-  const int ci = i % Cin;
-  const long r = i / Cin;
-  const int co = r % Cout, k = r / Cout;
-  dW[((long)co * Cin + ci) * TAPS + k] = s;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int k = k0 + ty + 8 * h;
+    const float* p = partial + ((long)k * Cout + co) * Cin + ci0 + tx;
+    float s = 0.f;
+#pragma unroll 4
+    for (int g = 0; g < groups; ++g) s += __ldg(p + (long)g * per);
+    tile[ty + 8 * h][tx] = s;
+  }
+  __syncthreads();
+  // 512 outputs of the tile: thread -> (ci = t >> 4, k = t & 15), two passes
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int t = threadIdx.x + 256 * h;
+    const int ci = t >> 4, kk = t & 15;
+    dW[((long)co * Cin + ci0 + ci) * TAPS + k0 + kk] = tile[kk][ci];
+  }
 }
 
 }  // namespace convtc
@@ -953,8 +968,7 @@ inline int conv_tc_backward(int math, const float* xin, const float* skip_in, co
   g.groups = conv_tc_wgrad_groups(B, taps, Cin, Cout);
   rc = math == EEGCLIP_MATH_BF16 ? wgrad_tc_launch<1>(g, st) : wgrad_tc_launch<3>(g, st);
   if (rc != EEGCLIP_OK) return rc;
-  const long n = (long)taps * Cin * Cout;
-  LAUNCH_PDL((convtc::wgrad_reduce_kernel), (unsigned)((n + 255) / 256), 256, 0, st, partial, dw, g.groups, taps, Cin, Cout);
+  LAUNCH_PDL((convtc::wgrad_reduce_kernel), dim3(taps / 16, Cin / 32, Cout), 256, 0, st, partial, dw, g.groups, taps, Cin, Cout);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
