@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EEGCLIP_ABI_VERSION 3
+#define EEGCLIP_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define EEGCLIP_API __attribute__((visibility("default")))
@@ -140,6 +140,29 @@ EEGCLIP_API int eegclip_xfblock_backward(const eegclip_xfblock_desc* d, const fl
                              size_t grad_bytes, const float* zin, const float* dzout, float* dzin, const void* save,
                              void* scratch, void* stream);
 
+/* Stand-alone pieces of the transformer block, for callers that use the reference's sub-modules directly
+ * (MultiHeadAttention.forward clip_model.py:30-45, ResidualAdd.forward :52-57, nn.LayerNorm(64) :84,89, nn.Dropout :86,91).
+ *   attention : qkv (B,T,192) = [q | k | v], head h owning columns 8h..8h+7 of each third -> out (B,T,64); softmax(QK^T/sqrt(64)),
+ *               dropout on the probabilities (Philox site ATTN of `layer`); lse (B,8,T) links forward and backward.
+ *   layernorm : per-token LayerNorm over C = 64 features, eps 1e-5; dgamma/dbeta are overwritten.
+ *   dropout   : out = in * keep/(1-p) with the Philox stream (layer, site); the same call is its own backward. */
+EEGCLIP_API int eegclip_attention_forward(const float* qkv, float* out, float* lse, int32_t B, int32_t T, float p_drop, int32_t train,
+                              int32_t layer, uint64_t seed, int32_t math, void* stream);
+EEGCLIP_API int eegclip_attention_backward(const float* qkv, const float* out, const float* dout, const float* lse, float* dqkv, int32_t B,
+                               int32_t T, float p_drop, int32_t train, int32_t layer, uint64_t seed, int32_t math, void* stream);
+EEGCLIP_API int eegclip_layernorm_forward(const float* x, const float* gamma, const float* beta, float* out, int64_t rows, int32_t C,
+                              void* stream);
+EEGCLIP_API int eegclip_layernorm_backward(const float* dout, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                               int64_t rows, int32_t C, void* stream);
+EEGCLIP_API int eegclip_dropout(const float* in, float* out, int64_t n, float p, int32_t train, int32_t layer, int32_t site, uint64_t seed,
+                    void* stream);
+/* nn.GELU() followed by nn.Dropout (FeedForwardBlock, clip_model.py:64-65) in one pass: out = dropout(GELU(pre)); backward
+ * dpre = dout * keep/(1-p) * GELU'(pre) (mask regenerated from the Philox stream (layer, site)). */
+EEGCLIP_API int eegclip_gelu_dropout_forward(const float* pre, float* out, int64_t n, float p, int32_t train, int32_t layer, int32_t site,
+                                 uint64_t seed, void* stream);
+EEGCLIP_API int eegclip_gelu_dropout_backward(const float* pre, const float* dout, float* dpre, int64_t n, float p, int32_t train,
+                                  int32_t layer, int32_t site, uint64_t seed, void* stream);
+
 /* BasicBlock (clip_model.py:234-249) / VLAAI conv+LN+LeakyReLU (vlaai.py:29-35,60-72) on a time-major tensor:
  *   y = act(LayerNorm_[C,T](dropout(conv1d_same(x (+ skip_in)))))      act: 0 GELU, 1 LeakyReLU(0.01)
  * x (B,T,Cin) -> out (B,T,Cout).  w (Cout,Cin,taps), gamma/beta (Cout,T).
@@ -216,13 +239,17 @@ EEGCLIP_API int eegclip_infonce_backward(const float* S_all, const float* E_all,
                              float* dS_loc, float* dE_loc, float* dtau_partial, int32_t math, int32_t one_sided,
                              void* scratch, void* stream);
 
-/* memoryBank.forward (clip_model.py:731-745): old = memory[idx]; memory[idx] = m*old + (1-m)*data. idx int64.
+/* memoryBank.forward (clip_model.py:731-745): old = memory[idx]; memory[idx] = m*old + (1-m)*data. idx int64, memory
+ * (bank_rows, D).  Every old row is gathered before any row is written (index_select, then index_copy_): duplicate ids in a
+ * batch all return the pre-batch row and the last occurrence's update is the one stored.  An id outside [0, bank_rows)
+ * (IndexError in the reference) writes nothing and returns a NaN row.
  * one_minus_momentum is passed separately because the reference rounds (1 - m) from a Python double. */
-EEGCLIP_API int eegclip_membank_update(float* memory, const int64_t* idx, const float* data, float* old_out, int32_t rows, int32_t D,
-                           float momentum, float one_minus_momentum, void* stream);
+EEGCLIP_API int eegclip_membank_update(float* memory, int64_t bank_rows, const int64_t* idx, const float* data, float* old_out,
+                           int32_t rows, int32_t D, float momentum, float one_minus_momentum, void* stream);
 
-/* AdamW over a table of tensors (train_clip_final.py:409-413,492; torch.optim.AdamW semantics, amsgrad off,
- * decoupled weight decay).  `table_dev` is a DEVICE-resident array of n_tensors entries (the caller builds it on the
+/* AdamW / Adam over a table of tensors (train_clip_final.py:403-413,492; torch.optim.AdamW semantics with decoupled
+ * weight decay, or torch.optim.Adam semantics -- decay added to the gradient -- when coupled_decay != 0; amsgrad when the
+ * entry carries a vmax buffer).  `table_dev` is a DEVICE-resident array of n_tensors entries (the caller builds it on the
  * host and uploads it once; it stays valid while the parameter/gradient/state pointers do).  One launch updates
  * every tensor: 16 B loads/stores, 7 x 4 B of traffic per element (HBM-bound). */
 typedef struct {
@@ -231,10 +258,11 @@ typedef struct {
   void* m;          /* exp_avg, fp32 */
   void* v;          /* exp_avg_sq, fp32 */
   int64_t numel;
+  void* vmax;       /* max_exp_avg_sq, fp32 (amsgrad), or NULL */
 } eegclip_adamw_entry;
 
 EEGCLIP_API int eegclip_adamw_step(const eegclip_adamw_entry* table_dev, int32_t n_tensors, int64_t max_numel, float lr, float beta1,
-                       float beta2, float eps, float weight_decay, int64_t step, void* stream);
+                       float beta2, float eps, float weight_decay, int32_t coupled_decay, int64_t step, void* stream);
 
 /* Match-mismatch scoring (train_clip_helper_functions.py:153-163,176-187).
  *   eegclip_mm_rowdots : scores[k][n] = <eeg[n], cand[n][k]>  (replaces the N x N matmul + diag) and argmax over k
@@ -245,6 +273,33 @@ EEGCLIP_API int eegclip_mm_rowdots(const float* eeg, const float* cand, float* s
 EEGCLIP_API int eegclip_mm_bank_workspace(int32_t N, int32_t M, int32_t D, size_t* scratch_bytes);
 EEGCLIP_API int eegclip_mm_bank_logits(const float* eeg, const float* bank, float* logits, int32_t N, int32_t M, int32_t D, int32_t math,
                            void* scratch, void* stream);
+
+/* Per-subject mean-variance normalisation of EEG windows (train_clip_helper_functions.py:133-136):
+ * x (rows = N*T, C) -> y = (x - mean_c) / std_c with the per-channel mean and population std over all rows
+ * (sums in fp64, fixed order).  scratch: eegclip_mvn_workspace bytes. */
+EEGCLIP_API int eegclip_mvn_workspace(int32_t C, size_t* scratch_bytes);
+EEGCLIP_API int eegclip_mvn_normalize(const float* x, float* y, int64_t rows, int32_t C, void* scratch, void* stream);
+
+/* Per-row top-k of a similarity matrix (train_clip_helper_functions.py:182-187: torch.topk(logits, min(100, M))):
+ * x (N, M) with row stride ld -> vals (N,k) descending, idx (N,k) = column + col_offset; ties go to the lower column.
+ * k <= 1024, k <= M.  Reads every row twice (radix/threshold select), writes nothing else. */
+EEGCLIP_API int eegclip_row_topk(const float* x, int64_t ld, int32_t N, int32_t M, int32_t k, int64_t col_offset, float* vals,
+                     int64_t* idx, void* stream);
+
+/* Downstream regression head (train_clip_helper_functions.py:1132-1140, 1107-1118; used by :620-640):
+ *   conv_small : out = LeakyReLU_0.01(Conv1d(Cin -> Cout, K, padding='same')(x)), channel-major x (B,Cin,T) -> out (B,Cout,T);
+ *                backward overwrites dw (Cout,Cin,K), db (Cout) (may be NULL) and, if dx != NULL, dx (B,Cin,T).
+ *   pearson    : PearsonLoss: r[b][c] = cosine(x - mean_t x, y - mean_t y) (eps 1e-6), loss[c] = -mean_b r[b][c];
+ *                backward gives dx (B,C,T) for an upstream gradient dloss (C) (device vector). */
+EEGCLIP_API int eegclip_conv_small_workspace(int32_t B, int32_t Cin, int32_t Cout, int32_t K, size_t* scratch_bytes);
+EEGCLIP_API int eegclip_conv_small_forward(const float* x, const float* w, const float* bias, float* out, int32_t B, int32_t Cin,
+                               int32_t Cout, int32_t T, int32_t K, void* stream);
+EEGCLIP_API int eegclip_conv_small_backward(const float* x, const float* w, const float* out, const float* dout, float* dx, float* dw,
+                                float* db, int32_t B, int32_t Cin, int32_t Cout, int32_t T, int32_t K, void* scratch, void* stream);
+EEGCLIP_API int eegclip_pearson_forward(const float* x, const float* y, float* r, float* loss, int32_t B, int32_t C, int32_t T,
+                            void* stream);
+EEGCLIP_API int eegclip_pearson_backward(const float* x, const float* y, const float* dloss, float* dx, int32_t B, int32_t C, int32_t T,
+                             void* stream);
 
 #ifdef __cplusplus
 }

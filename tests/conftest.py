@@ -15,5 +15,8 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     import json
-    with open(os.path.join(ROOT, "tests", "golden", "reference_golden.json")) as f:
-        return json.load(f)["cases"]
+    cases = {}
+    for name in ("reference_golden.json", "reference_golden_r2.json"):   # r2: oracle/make_golden_r2.py (BASELINE sizes, new rows)
+        with open(os.path.join(ROOT, "tests", "golden", name)) as f:
+            cases.update(json.load(f)["cases"])
+    return cases

@@ -8,11 +8,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libeegclip_b200.so")
-SOURCES = ["tower.cu", "head.cu", "lstm.cu"]
+SOURCES = ["tower.cu", "head.cu", "lstm.cu", "extras.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-    "--expt-relaxed-constexpr",
+    "--expt-relaxed-constexpr", "--extended-lambda",
 ]
 
 

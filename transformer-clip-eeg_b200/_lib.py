@@ -95,11 +95,26 @@ SIGNATURES = {
     "eegclip_infonce_lse": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "eegclip_infonce_loss": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "eegclip_infonce_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
-    "eegclip_membank_update": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _vp]),
-    "eegclip_adamw_step": (C.c_int, [_vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _vp]),
+    "eegclip_membank_update": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _vp]),
+    "eegclip_adamw_step": (C.c_int, [_vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _i64, _vp]),
     "eegclip_mm_rowdots": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "eegclip_mm_bank_workspace": (C.c_int, [_i32, _i32, _i32, _psz]),
     "eegclip_mm_bank_logits": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "eegclip_attention_forward": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _f32, _i32, _i32, C.c_uint64, _i32, _vp]),
+    "eegclip_attention_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _i32, C.c_uint64, _i32, _vp]),
+    "eegclip_layernorm_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "eegclip_layernorm_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "eegclip_dropout": (C.c_int, [_vp, _vp, _i64, _f32, _i32, _i32, _i32, C.c_uint64, _vp]),
+    "eegclip_gelu_dropout_forward": (C.c_int, [_vp, _vp, _i64, _f32, _i32, _i32, _i32, C.c_uint64, _vp]),
+    "eegclip_gelu_dropout_backward": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _i32, _i32, _i32, C.c_uint64, _vp]),
+    "eegclip_mvn_workspace": (C.c_int, [_i32, _psz]),
+    "eegclip_mvn_normalize": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "eegclip_row_topk": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i64, _vp, _vp, _vp]),
+    "eegclip_conv_small_workspace": (C.c_int, [_i32, _i32, _i32, _i32, _psz]),
+    "eegclip_conv_small_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "eegclip_conv_small_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "eegclip_pearson_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "eegclip_pearson_backward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
 }
 
 _ERR = {-1: "invalid argument", -2: "CUDA error", -3: "unsupported shape/configuration"}
@@ -120,7 +135,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.eegclip_abi_version() != 3:
+    if lib.eegclip_abi_version() != 4:
         raise EegclipError("libeegclip_b200.so ABI version mismatch")
     # development knobs from the environment: EEGCLIP_TUNE="7=1,6=1" -> eegclip_tune_set(7, 1), eegclip_tune_set(6, 1)
     for kv in filter(None, os.environ.get("EEGCLIP_TUNE", "").split(",")):
@@ -179,7 +194,8 @@ def new_seed():
 # Gradient sinks: the optimizer (optim.AdamW) owns one flat gradient arena and registers, per parameter, the arena view that
 # is its ``.grad``.  A backward of this package then writes the parameter gradients straight into those views and returns
 # None for them, so autograd launches no ``grad += new`` kernel per parameter (229 launches per step in the default model).
-# A view is handed out at most once per zero_grad() epoch; any second backward falls back to the ordinary accumulate path.
+# A view is handed out at most once per zero_grad() epoch; any second backward falls back to the ordinary accumulate path
+# (autograd then adds into the same view in place, which is the correct accumulation).
 # ---------------------------------------------------------------------------------------------------
 import weakref
 
@@ -192,7 +208,12 @@ def register_grad_sinks(params, views, arena):
 
 
 def claim_grad_sinks(ps):
-    """Arena views to write the gradients of ``ps`` into (in order), or None when any of them cannot be claimed."""
+    """Arena views to write the gradients of ``ps`` into (in order), or None when any of them cannot be claimed.
+
+    A view can be claimed once per zero_grad() epoch, and only while the parameter's ``.grad`` is None (set_to_none) or is
+    that very view; the claim sets ``.grad`` to the view, so after backward the parameter looks exactly as if autograd
+    had accumulated into it.  Parameters that are never claimed (nor reached by autograd) keep ``grad is None`` and the
+    optimizer skips them, as torch.optim does."""
     found = []
     for p_ in ps:
         e = _SINKS.get(p_.data_ptr())
@@ -200,10 +221,12 @@ def claim_grad_sinks(ps):
             return None
         ref, v, arena = e
         owner = ref()
-        if (owner is None or owner.data_ptr() != p_.data_ptr() or owner.grad is None or owner.grad.data_ptr() != v.data_ptr()
-                or v.shape != p_.shape or p_.data_ptr() in arena["written"]):
+        if owner is None or owner.data_ptr() != p_.data_ptr() or v.shape != p_.shape or p_.data_ptr() in arena["written"]:
             return None
-        found.append((v, arena))
-    for p_, (v, arena) in zip(ps, found):
+        if owner.grad is not None and owner.grad.data_ptr() != v.data_ptr():
+            return None                                  # a foreign gradient is already accumulated there
+        found.append((owner, v, arena))
+    for p_, (owner, v, arena) in zip(ps, found):
         arena["written"].add(p_.data_ptr())
-    return [v for v, _ in found]
+        owner.grad = v
+    return [v for _, v, _ in found]

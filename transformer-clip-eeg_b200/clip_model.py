@@ -8,12 +8,15 @@ Same class names, constructor / forward signatures, return arity and ``state_dic
     BasicBlock (:234-249), EEGConformer (:327-398), EEGConformerInterleaved (:400-474)
     SpeechSmallConv (:204-232), EEGConvLSTM (:251-325)
     CLIP (:657-693), memoryBank (:697-745), CLIPSimNoLatentProj (:868-944)
+    CLIPSim (:747-810), CLIPNoContrastiveLearning (:948-995), CLIPSimMultiplePositives[Adapted] (:1000-1168),
+    CLIPKLDNoLatentProj (:1174-1279), CLIPKLDWithLatentProj (:1325-1450) and their helpers (:1473-1500)
 
 The nested containers (nn.Sequential / nn.Linear / nn.LayerNorm / nn.Conv1d) only *hold* the
 parameters under the reference's key names; every forward below goes through the C ABI of
 libeegclip_b200.so (include/eegclip.h).  There is no eager/CPU fallback: CPU tensors raise.
 """
 import ctypes
+import math
 
 import torch
 import torch.nn as nn
@@ -25,7 +28,9 @@ from .parallel import infonce_loss, ce_rows_loss, l2_normalize
 __all__ = [
     "MultiHeadAttention", "ResidualAdd", "FeedForwardBlock", "TransformerEncoderBlock", "TransformerEncoder",
     "BasicBlock", "EEGConformer", "EEGConformerInterleaved", "SpeechSmallConv", "EEGConvLSTM", "CLIP", "memoryBank",
-    "CLIPSimNoLatentProj",
+    "CLIPSimNoLatentProj", "CLIPSim", "CLIPSimMultiplePositives", "CLIPSimMultiplePositivesAdapted", "CLIPKLDNoLatentProj",
+    "CLIPKLDWithLatentProj", "CLIPNoContrastiveLearning", "ProjectionHeadLinear", "multiple_postives_loss", "simloss",
+    "log_gauss", "kld", "LayerNorm", "Dropout",
 ]
 
 
@@ -235,12 +240,14 @@ class _BiLSTMFn(torch.autograd.Function):
 
 
 def _bilstm(mod, x):
-    """Run an nn.LSTM parameter container on the eegclip kernels when the shape is covered, else on the cuDNN library call."""
+    """Run an nn.LSTM parameter container on the eegclip recurrence kernels (no second backend: uncovered shapes raise)."""
     B, T, In = x.shape
     d = L.BiLstmDesc(B=B, T=T, In=In, H=mod.hidden_size, math=L.default_math())
-    if mod.bidirectional and mod.num_layers == 1 and mod.batch_first and L.load().eegclip_bilstm_supported(ctypes.byref(d)):
-        return _BiLSTMFn.apply(x, d, *[getattr(mod, n) for n in _LSTM_ORDER])
-    return mod(x)[0]
+    if not (mod.bidirectional and mod.num_layers == 1 and mod.batch_first and L.load().eegclip_bilstm_supported(ctypes.byref(d))):
+        raise L.EegclipError(f"bi-LSTM shape (input {In}, hidden {mod.hidden_size}, layers {mod.num_layers}, bidirectional "
+                             f"{mod.bidirectional}) is not covered by the eegclip recurrence kernels (H=128 with In 64/128, H=4 with In "
+                             "64..256; tensor-core math) and this path has no library fallback")
+    return _BiLSTMFn.apply(x, d, *[getattr(mod, n) for n in _LSTM_ORDER])
 
 
 def _require_cuda(x, who):
@@ -248,8 +255,125 @@ def _require_cuda(x, who):
         raise L.EegclipError(f"{who}: input is on {x.device}; this implementation runs on CUDA (sm_100a) only")
 
 
+def _check_ln_shape(norm, C, T, who):
+    """LayerNorm([C, time_dimension]) affines are read as a (C,T) array by the kernels: the window length must be the one the
+    module was built with (the reference raises a shape error from F.layer_norm in the same situation)."""
+    if tuple(norm.weight.shape) != (C, T):
+        raise RuntimeError(f"{who}: input has {C} channels x {T} time samples but the LayerNorm was built for "
+                           f"normalized_shape={list(norm.weight.shape)} (time_dimension mismatch)")
+
+
+SITE_CONV, SITE_ATTN, SITE_PROJ, SITE_FFN_HID, SITE_FFN_OUT = 0, 1, 2, 3, 4   # csrc/common.cuh
+
+
+class _AttentionFn(torch.autograd.Function):
+    """softmax(QK^T / sqrt(64)) (+ Philox dropout on the probabilities) . V on (B,T,192) = [q|k|v]."""
+
+    @staticmethod
+    def forward(ctx, qkv, p, train, layer, seed):
+        qkv = L.f32c(qkv)
+        B, T, _ = qkv.shape
+        out = torch.empty(B, T, 64, dtype=torch.float32, device=qkv.device)
+        lse = torch.empty(B, 8, T, dtype=torch.float32, device=qkv.device)
+        L.call("eegclip_attention_forward", L.ptr(qkv), L.ptr(out), L.ptr(lse), B, T, float(p), int(train), int(layer), int(seed),
+               L.default_math(), L.stream())
+        ctx.saved, ctx.meta = (qkv, out, lse), (B, T, float(p), int(train), int(layer), int(seed), L.default_math())
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved
+        B, T, p, train, layer, seed, math = ctx.meta
+        dqkv = torch.empty_like(qkv)
+        L.call("eegclip_attention_backward", L.ptr(qkv), L.ptr(out), L.ptr(L.f32c(dout)), L.ptr(lse), L.ptr(dqkv), B, T, p, train,
+               layer, seed, math, L.stream())
+        return dqkv, None, None, None, None
+
+
+class _LayerNorm64Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, g, b):
+        x, g, b = L.f32c(x), L.f32c(g), L.f32c(b)
+        out = torch.empty_like(x)
+        L.call("eegclip_layernorm_forward", L.ptr(x), L.ptr(g), L.ptr(b), L.ptr(out), x.numel() // 64, 64, L.stream())
+        ctx.saved = (x, g)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, g = ctx.saved
+        dx, dg, db = torch.empty_like(x), torch.empty_like(g), torch.empty_like(g)
+        L.call("eegclip_layernorm_backward", L.ptr(L.f32c(dout)), L.ptr(x), L.ptr(g), L.ptr(dx), L.ptr(dg), L.ptr(db), x.numel() // 64, 64,
+               L.stream())
+        return dx, dg, db
+
+
+class _DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, layer, site, seed):
+        x = L.f32c(x)
+        if x.numel() % 4:
+            raise L.EegclipError("dropout kernel: element count must be a multiple of 4")
+        out = torch.empty_like(x)
+        L.call("eegclip_dropout", L.ptr(x), L.ptr(out), x.numel(), float(p), 1, int(layer), int(site), int(seed), L.stream())
+        ctx.meta = (float(p), int(layer), int(site), int(seed))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        p, layer, site, seed = ctx.meta
+        dout = L.f32c(dout)
+        dx = torch.empty_like(dout)
+        L.call("eegclip_dropout", L.ptr(dout), L.ptr(dx), dout.numel(), p, 1, layer, site, seed, L.stream())
+        return dx, None, None, None, None
+
+
+class _GeluDropFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pre, p, train, layer, site, seed):
+        pre = L.f32c(pre)
+        out = torch.empty_like(pre)
+        L.call("eegclip_gelu_dropout_forward", L.ptr(pre), L.ptr(out), pre.numel(), float(p), int(train), int(layer), int(site),
+               int(seed), L.stream())
+        ctx.saved, ctx.meta = pre, (float(p), int(train), int(layer), int(site), int(seed))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        p, train, layer, site, seed = ctx.meta
+        dpre = torch.empty_like(ctx.saved)
+        L.call("eegclip_gelu_dropout_backward", L.ptr(ctx.saved), L.ptr(L.f32c(dout)), L.ptr(dpre), dpre.numel(), p, train, layer, site,
+               seed, L.stream())
+        return dpre, None, None, None, None, None
+
+
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm(64) of the transformer block (clip_model.py:84,89) on the eegclip per-token kernel when called directly."""
+
+    def forward(self, x):
+        _require_cuda(x, "LayerNorm")
+        if tuple(self.normalized_shape) != (64,) or x.shape[-1] != 64:
+            raise L.EegclipError("the eegclip LayerNorm kernel covers 64 features (the reference's only use)")
+        return _LayerNorm64Fn.apply(x, self.weight, self.bias)
+
+
+class Dropout(nn.Dropout):
+    """nn.Dropout with the counter-based Philox masks of the fused kernels (stream = (layer, site)) when called directly."""
+
+    def __init__(self, p=0.5, site=SITE_PROJ):
+        super().__init__(p)
+        self.site, self.layer = site, 0
+
+    def forward(self, x):
+        if not self.training or self.p == 0.0:
+            return x
+        _require_cuda(x, "Dropout")
+        return _DropoutFn.apply(x, self.p, self.layer, self.site, L.new_seed())
+
+
 # ---------------------------------------------------------------------------------------------------
-# Transformer blocks (parameter containers keep the reference key names)
+# Transformer blocks (parameter containers keep the reference key names).  TransformerEncoderBlock.forward is ONE fused
+# call; the sub-modules stay callable on their own (the reference's surface, SURVEY 8(b)) through the same kernels.
 # ---------------------------------------------------------------------------------------------------
 class MultiHeadAttention(nn.Module):
     """clip_model.py:19-45.  ``mask`` is dead in the reference (``energy.mask_fill`` does not exist, :37)."""
@@ -266,26 +390,43 @@ class MultiHeadAttention(nn.Module):
     def forward(self, x, mask=None):
         if mask is not None:  # same failure as the reference: Tensor has no attribute mask_fill
             raise AttributeError("'Tensor' object has no attribute 'mask_fill'")
-        raise L.EegclipError("MultiHeadAttention is fused into TransformerEncoderBlock on this path; call the block")
+        _require_cuda(x, "MultiHeadAttention")
+        if self.emb_size != 64 or self.num_heads != 8:
+            raise L.EegclipError("the attention kernels are specialised for emb_size=64, 8 heads (the reference's only use)")
+        q = _LinearFn.apply(x, self.queries.weight, self.queries.bias)
+        k = _LinearFn.apply(x, self.keys.weight, self.keys.bias)
+        v = _LinearFn.apply(x, self.values.weight, self.values.bias)
+        train = self.training and self.att_drop.p > 0
+        o = _AttentionFn.apply(torch.cat([q, k, v], dim=-1), self.att_drop.p, train, getattr(self, "layer", 0),
+                               L.new_seed() if train else 0)
+        return _LinearFn.apply(o, self.projection.weight, self.projection.bias)
 
 
 class ResidualAdd(nn.Module):
-    """clip_model.py:48-57 (container only; the residual add is fused into the block kernels)."""
+    """clip_model.py:48-57: x + fn(x) (inside TransformerEncoderBlock the add is fused into the GEMM epilogues)."""
 
     def __init__(self, fn):
         super().__init__()
         self.fn = fn
 
     def forward(self, x, **kwargs):
-        raise L.EegclipError("ResidualAdd is fused into TransformerEncoderBlock on this path; call the block")
+        _require_cuda(x, "ResidualAdd")
+        return self.fn(x, **kwargs) + x
 
 
 class FeedForwardBlock(nn.Sequential):
-    """clip_model.py:60-67."""
+    """clip_model.py:60-67: Linear -> GELU -> Dropout -> Linear."""
 
     def __init__(self, emb_size, expansion, drop_p):
         super().__init__(nn.Linear(emb_size, expansion * emb_size), nn.GELU(), nn.Dropout(drop_p),
                          nn.Linear(expansion * emb_size, emb_size))
+
+    def forward(self, x):
+        _require_cuda(x, "FeedForwardBlock")
+        pre = _LinearFn.apply(x, self[0].weight, self[0].bias)
+        train = self.training and self[2].p > 0
+        f = _GeluDropFn.apply(pre, self[2].p, train, getattr(self, "layer", 0), SITE_FFN_HID, L.new_seed() if train else 0)
+        return _LinearFn.apply(f, self[3].weight, self[3].bias)
 
 
 _XF_ORDER = ("0.fn.0.weight", "0.fn.0.bias", "0.fn.1.queries.weight", "0.fn.1.queries.bias", "0.fn.1.keys.weight",
@@ -299,10 +440,10 @@ class TransformerEncoderBlock(nn.Sequential):
 
     def __init__(self, emb_size, num_heads=8, drop_p=0.5, forward_expansion=4, forward_drop_p=0.5):
         super().__init__(
-            ResidualAdd(nn.Sequential(nn.LayerNorm(emb_size), MultiHeadAttention(emb_size, num_heads, drop_p), nn.Dropout(drop_p))),
-            ResidualAdd(nn.Sequential(nn.LayerNorm(emb_size),
+            ResidualAdd(nn.Sequential(LayerNorm(emb_size), MultiHeadAttention(emb_size, num_heads, drop_p), Dropout(drop_p, SITE_PROJ))),
+            ResidualAdd(nn.Sequential(LayerNorm(emb_size),
                                       FeedForwardBlock(emb_size, expansion=forward_expansion, drop_p=forward_drop_p),
-                                      nn.Dropout(drop_p))))
+                                      Dropout(drop_p, SITE_FFN_OUT))))
         if emb_size != 64 or num_heads != 8 or forward_expansion != 4:
             raise L.EegclipError("the B200 kernels are specialised for emb_size=64, 8 heads, expansion 4 (the reference's only use)")
         self.drop_p, self.forward_drop_p = drop_p, forward_drop_p
@@ -354,6 +495,7 @@ class BasicBlock(nn.Module):
         _require_cuda(x, "BasicBlock")
         B, T, cin = x.shape
         w = self.conv.weight
+        _check_ln_shape(self.normalization, w.shape[0], T, "BasicBlock")
         d = L.ConvBlockDesc(B=B, T=T, Cin=cin, Cout=w.shape[0], taps=w.shape[2], act=self._act, train=int(self.training),
                             math=L.default_math(), p_drop=self.dropout.p, layer=layer,
                             seed=L.new_seed() if self.training else 0)
@@ -394,6 +536,8 @@ class _TowerBase(nn.Module):
         if cin != 64:
             raise L.EegclipError("EEG towers take 64-channel windows (B,T,64)")
         taps = convs[0].conv.weight.shape[2] if convs else 1
+        for c in convs:
+            _check_ln_shape(c.normalization, 64, T, type(self).__name__)
         blk0 = xfs[0] if xfs else None
         d = L.TowerDesc(kind=self._kind, B=B, T=T, n_conv=len(convs), depth=len(xfs), taps=taps, latent=self.output_dim,
                         train=int(self.training), math=L.default_math(),
@@ -448,7 +592,7 @@ class EEGConformerInterleaved(_TowerBase):
 
 # ---------------------------------------------------------------------------------------------------
 # Speech towers (boundary: SURVEY §8(a14)).  The conv/LN blocks run on the kernels above; the two
-# bi-LSTMs of the default tower run on the recurrence kernels of csrc/lstm.cuh (other LSTM shapes: cuDNN library call).
+# bi-LSTMs of the default tower run on the recurrence kernels of csrc/lstm.cuh (other LSTM shapes raise: no library fallback).
 # ---------------------------------------------------------------------------------------------------
 class SpeechSmallConv(nn.Module):
     """clip_model.py:204-232: Conv1d(speech_dim->out, k, 'same') -> Dropout -> LayerNorm([out,T]) -> LeakyReLU."""
@@ -468,6 +612,7 @@ class SpeechSmallConv(nn.Module):
         _require_cuda(x, "SpeechSmallConv")
         B, T, cin = x.shape
         w = self.speech_spatial_mapping.weight
+        _check_ln_shape(self.layernorm, w.shape[0], T, "SpeechSmallConv")
         d = L.ConvBlockDesc(B=B, T=T, Cin=cin, Cout=w.shape[0], taps=w.shape[2], act=1, train=int(self.training),
                             math=L.default_math(), p_drop=self.dropout.p, layer=0, seed=L.new_seed() if self.training else 0)
         return _ConvBlockFn.apply(x, None, d, w, self.speech_spatial_mapping.bias, self.layernorm.weight, self.layernorm.bias)
@@ -534,9 +679,14 @@ class memoryBank(nn.Module):
         _require_cuda(data, "memoryBank")
         d = L.f32c(data)
         idx = idx.view(-1).to(torch.int64).contiguous()
+        if idx.device.type == "cpu":
+            if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= self.memory.shape[0]):
+                raise IndexError(f"memoryBank: index out of range for a bank of {self.memory.shape[0]} rows")   # as index_select (:738)
+            idx = idx.to(d.device)
         old = torch.empty_like(d)
-        L.call("eegclip_membank_update", L.ptr(self.memory), L.ptr(idx), L.ptr(d), L.ptr(old), d.shape[0], d.shape[1],
-               float(self.momentum), float(1 - self.momentum), L.stream())
+        # ids already on the device are range-checked by the kernel (no host sync): an out-of-range row writes nothing and reads NaN
+        L.call("eegclip_membank_update", L.ptr(self.memory), self.memory.shape[0], L.ptr(idx), L.ptr(d), L.ptr(old), d.shape[0],
+               d.shape[1], float(self.momentum), float(1 - self.momentum), L.stream())
         return old
 
 
@@ -585,3 +735,233 @@ class CLIPSimNoLatentProj(nn.Module):
             avg_loss = ce_rows_loss(avg, l2_normalize(E_raw), self.temperature_eeg)
         loss_total = self.lambda_clip * loss_ce + self.lambda_average * avg_loss
         return loss_ce.mean(), avg_loss.mean(), loss_total.mean()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Non-default loss wrappers (train_clip_final.py:379-396: --model_arch clip_sim / clip_mp / clip_kld / no_contrastive_learning).
+# All of them sit on the same kernels: towers, _LinearFn (latent projections and the S.E^T similarity GEMM with its two
+# gradient GEMMs), l2-normalisation, and -- where the logits are square -- the fused symmetric-InfoNCE head.  What is left in
+# torch is O(B x n.B) elementwise / log-sum-exp arithmetic on the similarity matrix and O(B x latent) regularisers.
+# ---------------------------------------------------------------------------------------------------
+def _flat(x):
+    return torch.flatten(x, start_dim=1)
+
+
+def _proj(lin, x):
+    return _LinearFn.apply(x, lin.weight, lin.bias)
+
+
+def _similarity(Sn, En, log_scale):
+    """(Sn . En^T) * exp(log_scale) with autograd to both operands (tcgen05 token-GEMM kernels)."""
+    return _LinearFn.apply(Sn, En, None) * torch.exp(log_scale)
+
+
+def _ce_columns(logits):
+    """F.cross_entropy(logits.T, targets) with targets = arange(rows) tiled over the columns (clip_model.py:1044-1049)."""
+    rows = logits.shape[0]
+    col = torch.arange(logits.shape[1], device=logits.device)
+    return (torch.logsumexp(logits, dim=0) - logits[col % rows, col]).mean()
+
+
+class CLIPSim(nn.Module):
+    """clip_model.py:747-810: latent projections (no bias) -> symmetric InfoNCE + MSE(normalize(bank average), EEG embedding)."""
+
+    def __init__(self, eegModel, speechModel, eegMemoryBank, temperature=1., latent_dim=16, window_length=192, lambda_clip=1,
+                 lambda_average=1):
+        super().__init__()
+        self.eegModel, self.speechModel, self.eegMemoryBank = eegModel, speechModel, eegMemoryBank
+        self.latent_dim, self.window_length = latent_dim, window_length
+        self.lambda_clip, self.lambda_average = lambda_clip, lambda_average
+        d_in = self.eegModel.get_output_dim(input_window_size=self.window_length)
+        self.latent_projection_eeg = nn.Linear(d_in, latent_dim, bias=False)
+        self.latent_projection_speech = nn.Linear(d_in, latent_dim, bias=False)
+        self.temperature = nn.Parameter(torch.tensor(temperature))
+        self.shard_group = None
+
+    def forward(self, eeg, speech, ids):
+        E = _proj(self.latent_projection_eeg, _flat(self.eegModel(eeg)))
+        S = _proj(self.latent_projection_speech, _flat(self.speechModel(speech)))
+        loss_ce, En = infonce_loss(E, S, self.temperature, group=self.shard_group, return_normalized=True)
+        avg = l2_normalize(self.eegMemoryBank(ids, En))
+        avg_loss = ((avg - l2_normalize(E)) ** 2).mean()          # the gradient reaches the EEG tower through the normalisation
+        loss_total = self.lambda_clip * loss_ce + self.lambda_average * avg_loss
+        return loss_ce.mean(), avg_loss.mean(), loss_total.mean()
+
+
+class CLIPNoContrastiveLearning(nn.Module):
+    """clip_model.py:948-995: binary cross-entropy on the diagonal (match) vs the first super-diagonal (mismatch)."""
+
+    def __init__(self, eegModel, speechModel, window_length=192):
+        super().__init__()
+        self.eegModel, self.speechModel, self.window_length = eegModel, speechModel, window_length
+
+    def forward(self, eeg, speech, ids):
+        ef, sf = self.eegModel(eeg), self.speechModel(speech)
+        if sf.shape[1] > sf.shape[2]:
+            sf = sf.transpose(1, 2)
+        if ef.shape[1] > ef.shape[2]:
+            ef = ef.transpose(1, 2)
+        En, Sn = l2_normalize(_flat(ef)), l2_normalize(_flat(sf))
+        logits = _LinearFn.apply(Sn, En, None)
+        match, mismatch = torch.diagonal(logits)[:-1], torch.diagonal(logits, offset=1)
+        loss = (F.softplus(-match).mean() + F.softplus(mismatch).mean()) / 2     # BCE-with-logits, targets 1 / 0
+        return loss.mean(), loss.mean(), loss.mean()
+
+
+def log_softmax_mp(x):
+    """clip_model.py:1484-1487 on x (B, n, B): log sum_n exp x[i,n,j] - log sum_{n,j} exp x[i,n,j]."""
+    return torch.logsumexp(x, dim=-2) - torch.logsumexp(x.flatten(-2), dim=-1, keepdim=True)
+
+
+def multiple_postives_loss(preds, targets, reduction='mean'):
+    """clip_model.py:1490-1494 (name as in the reference)."""
+    return F.nll_loss(log_softmax_mp(preds), targets, reduction=reduction)
+
+
+def simloss(x, target):
+    """clip_model.py:1478-1480."""
+    return F.nll_loss(x.sum(-2), target)
+
+
+class CLIPSimMultiplePositives(nn.Module):
+    """clip_model.py:1000-1078: the EEG batch holds n windows per speech segment; logits (B, n*B)."""
+
+    def __init__(self, eegModel, speechModel, temperature=1., window_length=192, lambda_clip=1, lambda_average=1):
+        super().__init__()
+        self.eegModel, self.speechModel, self.window_length = eegModel, speechModel, window_length
+        self.lambda_clip, self.lambda_average = lambda_clip, lambda_average
+        self.temperature = nn.Parameter(torch.tensor(temperature))
+        self.temperature_eeg = nn.Parameter(torch.tensor(temperature))
+
+    def _logits(self, eeg, speech):
+        En, Sn = l2_normalize(_flat(self.eegModel(eeg))), l2_normalize(_flat(self.speechModel(speech)))
+        return _similarity(Sn, En, self.temperature)
+
+    def forward(self, eeg, speech, ids):
+        logits = self._logits(eeg, speech)
+        B = logits.shape[0]
+        eeg_loss = _ce_columns(logits)
+        grouped = logits.reshape(B, -1, B)
+        targets = torch.arange(B, device=logits.device)
+        speech_loss = multiple_postives_loss(grouped, targets)
+        sim_loss = simloss(grouped, targets)
+        loss_ce = (speech_loss + eeg_loss) / 2.0
+        loss_total = self.lambda_clip * loss_ce + self.lambda_average * sim_loss
+        return loss_ce.mean(), sim_loss.mean(), loss_total.mean()
+
+
+class CLIPSimMultiplePositivesAdapted(CLIPSimMultiplePositives):
+    """clip_model.py:1081-1168: the n logits of a speech/EEG-group pair are summed before the row cross-entropy."""
+
+    def forward(self, eeg, speech, ids):
+        logits = self._logits(eeg, speech)
+        B = logits.shape[0]
+        eeg_loss = _ce_columns(logits)
+        summed = logits.reshape(B, -1, B).sum(dim=1)
+        speech_loss = (torch.logsumexp(summed, dim=1) - torch.diagonal(summed)).mean()
+        loss_ce = (speech_loss + eeg_loss) / 2.0
+        loss_total = self.lambda_clip * loss_ce
+        return loss_ce.mean(), loss_ce.mean(), loss_total.mean()
+
+
+def log_gauss(x, mu, logvar):
+    """clip_model.py:1499-1501: log N(x; mu, exp(logvar))."""
+    return -0.5 * (math.log(2 * math.pi) + logvar + (x - mu) ** 2 / torch.exp(logvar))
+
+
+def kld(p_mu, p_logvar, q_mu, q_logvar):
+    """clip_model.py:1503-1504: KL(N(p_mu, e^p_logvar) || N(q_mu, e^q_logvar)) per element."""
+    return -0.5 * (1 + p_logvar - q_logvar - ((p_mu - q_mu) ** 2 + torch.exp(p_logvar)) / torch.exp(q_logvar))
+
+
+def _kld_terms(mu2, z_mu, z_logvar):
+    """Variational lower bound shared by both KLD wrappers (clip_model.py:1231-1239, 1407-1415)."""
+    dev = z_mu.device
+    q_logvar = torch.tensor([math.log(0.5 ** 2)], dtype=torch.float32, device=dev)
+    zero = torch.zeros(1, dtype=torch.float32, device=dev)
+    log_pmu2 = log_gauss(mu2, zero, zero).mean(dim=1)
+    kld_z2 = kld(z_mu, z_logvar, mu2, q_logvar).mean(dim=1)
+    return log_pmu2, kld_z2, (-log_pmu2 + kld_z2).mean(dim=0)
+
+
+class _KLDBase(nn.Module):
+    def reparameterize(self, mu, logvar):
+        if self.training:
+            return torch.randn_like(logvar).mul(torch.exp(0.5 * logvar)).add_(mu)
+        return mu
+
+
+class CLIPKLDNoLatentProj(_KLDBase):
+    """clip_model.py:1174-1279: InfoNCE on the flattened tower outputs + KL of a per-segment latent (embedding table prior)."""
+
+    def __init__(self, eegModel, speechModel, latent_dimension, number_of_classes, latent_dimension2=64, temperature=1.,
+                 window_length=192, lambda_clip=1, lambda_lower_bound=1, lambda_discriminative=1):
+        super().__init__()
+        self.eegModel, self.speechModel, self.window_length = eegModel, speechModel, window_length
+        self.lambda_clip, self.lambda_lower_bound, self.lambda_discriminative = lambda_clip, lambda_lower_bound, lambda_discriminative
+        self.number_of_classes, self.latent_dimension, self.latent_dimension2 = number_of_classes, latent_dimension, latent_dimension2
+        self.temperature = nn.Parameter(torch.tensor(temperature))
+        self.temperature_eeg = nn.Parameter(torch.tensor(temperature))
+        self.mu_eeg_lookup = nn.Embedding(number_of_classes + 1, latent_dimension2)
+        self.eeg_mu_linear = nn.Linear(latent_dimension, latent_dimension2)
+        self.eeg_logvar_linear = nn.Linear(latent_dimension, latent_dimension2)
+        self.shard_group = None
+
+    def encode(self, eeg, speech, ids):
+        E, S = _flat(self.eegModel(eeg)), _flat(self.speechModel(speech))
+        mu2 = self.mu_eeg_lookup(ids)
+        z_mu, z_logvar = _proj(self.eeg_mu_linear, E), _proj(self.eeg_logvar_linear, E)
+        return mu2, z_mu, z_logvar, self.reparameterize(z_mu, z_logvar), S, E
+
+    def forward(self, eeg, speech, ids):
+        mu2, z_mu, z_logvar, _, S, E = self.encode(eeg, speech, ids)
+        log_pmu2, kld_z2, lower_bound = _kld_terms(mu2, z_mu, z_logvar)
+        loss_ce = infonce_loss(E, S, self.temperature, group=self.shard_group)
+        loss_total = self.lambda_clip * loss_ce + self.lambda_lower_bound * lower_bound
+        return loss_total.mean(), loss_ce.mean(), log_pmu2.mean(), kld_z2.mean()
+
+
+class ProjectionHeadLinear(nn.Module):
+    """clip_model.py:1303-1320: Linear -> LeakyReLU -> Linear."""
+
+    def __init__(self, embedding_dim, projection_dim=512):
+        super().__init__()
+        self.projection = nn.Linear(embedding_dim, projection_dim * 2)
+        self.relu = nn.LeakyReLU()
+        self.last_linear = nn.Linear(projection_dim * 2, projection_dim)
+
+    def forward(self, x):
+        _require_cuda(x, "ProjectionHeadLinear")
+        return _proj(self.last_linear, F.leaky_relu(_proj(self.projection, x), 0.01))
+
+
+class CLIPKLDWithLatentProj(_KLDBase):
+    """clip_model.py:1325-1450 with the default linear projection heads (the 'non-linear' head is outside the kernel set)."""
+
+    def __init__(self, eegModel, speechModel, latent_dimension, number_of_classes, temperature=1., window_length=192,
+                 lambda_clip=1, lambda_lower_bound=1, lambda_discriminative=1, projection_head='linear'):
+        super().__init__()
+        if projection_head != 'linear':
+            raise L.EegclipError("CLIPKLDWithLatentProj: only projection_head='linear' (the reference default) is on the B200 path")
+        self.eegModel, self.speechModel, self.window_length = eegModel, speechModel, window_length
+        self.lambda_clip, self.lambda_lower_bound, self.lambda_discriminative = lambda_clip, lambda_lower_bound, lambda_discriminative
+        self.number_of_classes, self.latent_dimension = number_of_classes, latent_dimension
+        self.temperature = nn.Parameter(torch.tensor(temperature))
+        self.temperature_eeg = nn.Parameter(torch.tensor(temperature))
+        self.mu_eeg_lookup = nn.Embedding(number_of_classes + 1, latent_dimension)
+        self.eeg_mu_linear = ProjectionHeadLinear(self.eegModel.get_output_dim(window_length), latent_dimension)
+        self.eeg_logvar_linear = ProjectionHeadLinear(self.eegModel.get_output_dim(window_length), latent_dimension)
+        self.speech_latent_projection = ProjectionHeadLinear(self.speechModel.get_output_dim(window_length), latent_dimension)
+        self.shard_group = None
+
+    def encode(self, eeg, speech, ids):
+        E, S = _flat(self.eegModel(eeg)), _flat(self.speechModel(speech))
+        z_logvar, z_mu, Sp = self.eeg_logvar_linear(E), self.eeg_mu_linear(E), self.speech_latent_projection(S)
+        return self.mu_eeg_lookup(ids), z_mu, z_logvar, self.reparameterize(z_mu, z_logvar), Sp, z_mu
+
+    def forward(self, eeg, speech, ids):
+        mu2, z_mu, z_logvar, _, Sp, Ep = self.encode(eeg, speech, ids)
+        log_pmu2, kld_z2, lower_bound = _kld_terms(mu2, z_mu, z_logvar)
+        loss_ce = infonce_loss(Ep, Sp, self.temperature, group=self.shard_group)   # normalises both sides, as :1383-1384
+        loss_total = self.lambda_clip * loss_ce + self.lambda_lower_bound * lower_bound
+        return loss_total.mean(), loss_ce.mean(), log_pmu2.mean(), kld_z2.mean()

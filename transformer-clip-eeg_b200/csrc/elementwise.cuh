@@ -107,6 +107,23 @@ inline int gelu_drop(const float* pre, float* out, long n, const Drop& d, cudaSt
   return EEGCLIP_OK;
 }
 
+// dpre = dout * dropmult * GELU'(pre)   (backward of gelu_drop)
+__global__ void gelu_drop_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ dout, float* __restrict__ dpre, long n4,
+                                     Drop d) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<const float4*>(pre)[i], g = reinterpret_cast<const float4*>(dout)[i];
+  float4 m = drop_mult4(d, (uint64_t)i * 4);
+  g.x *= gelu_grad_f(v.x) * m.x; g.y *= gelu_grad_f(v.y) * m.y; g.z *= gelu_grad_f(v.z) * m.z; g.w *= gelu_grad_f(v.w) * m.w;
+  reinterpret_cast<float4*>(dpre)[i] = g;
+}
+inline int gelu_drop_bwd(const float* pre, const float* dout, float* dpre, long n, const Drop& d, cudaStream_t st) {
+  long n4 = n / 4;
+  gelu_drop_bwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(pre, dout, dpre, n4, d);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over the whole (C,T) sample with (C,T)-shaped affine + activation (+ skip).
 // clip_model.py:239,247-248 (BasicBlock), vlaai.py:31,62.  One CTA per sample; the sample (T*C*4 B

@@ -123,54 +123,89 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ lr,
   if (threadIdx.x == 0) *loss = r.x / ((one_sided ? 1.f : 2.f) * (float)Bg);
 }
 
-__global__ void __launch_bounds__(256) membank_kernel(float* __restrict__ mem, const int64_t* __restrict__ idx,
-                                                     const float* __restrict__ data, float* __restrict__ old_out, int D,
-                                                     float momentum, float om) {
+// memoryBank.forward (clip_model.py:731-745) in two launches, so that every old row is read before any row is written (the
+// reference gathers with index_select before index_copy_): duplicate ids in one batch all see the pre-batch row, and the
+// LAST occurrence of an id is the one whose update lands (index_copy_ on CPU writes in order).  Ids outside [0, bank_rows)
+// -- an IndexError in the reference -- write nothing and return NaN rows, so the loss turns NaN instead of corrupting memory.
+__global__ void __launch_bounds__(256) membank_gather_kernel(const float* __restrict__ mem, const int64_t* __restrict__ idx,
+                                                            float* __restrict__ old_out, int D, long bank_rows) {
   pdl_sync();
   const long r = blockIdx.x;
-  float* m = mem + idx[r] * (long)D;
-  const float* d = data + r * D;
+  const long id = idx[r];
+  const bool ok = id >= 0 && id < bank_rows;
+  const float* m = mem + (ok ? id : 0) * (long)D;
   float* o = old_out + r * D;
+  const float nan = __int_as_float(0x7fc00000);
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(o + i) = ok ? *reinterpret_cast<const float4*>(m + i) : make_float4(nan, nan, nan, nan);
+}
+
+__global__ void __launch_bounds__(256) membank_scatter_kernel(float* __restrict__ mem, const int64_t* __restrict__ idx,
+                                                             const float* __restrict__ data, const float* __restrict__ old,
+                                                             int rows, int D, long bank_rows, float momentum, float om) {
+  pdl_sync();
+  __shared__ int later;
+  const int r = blockIdx.x;
+  const long id = idx[r];
+  if (id < 0 || id >= bank_rows) return;
+  if (threadIdx.x == 0) later = 0;
+  __syncthreads();
+  for (int j = r + 1 + threadIdx.x; j < rows; j += blockDim.x)
+    if (idx[j] == id) later = 1;                       // a later row of this batch carries the same id: it wins
+  __syncthreads();
+  if (later) return;
+  float* m = mem + id * (long)D;
+  const float* d = data + (long)r * D;
+  const float* o = old + (long)r * D;
   for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
-    float4 a = *reinterpret_cast<const float4*>(m + i), x = *reinterpret_cast<const float4*>(d + i);
-    *reinterpret_cast<float4*>(o + i) = a;
+    float4 a = *reinterpret_cast<const float4*>(o + i), x = *reinterpret_cast<const float4*>(d + i);
     // new = old*momentum + data*(1-momentum), same operation order as the reference (mul_ then add_)
     *reinterpret_cast<float4*>(m + i) = make_float4(a.x * momentum + x.x * om, a.y * momentum + x.y * om,
                                                     a.z * momentum + x.z * om, a.w * momentum + x.w * om);
   }
 }
 
-// AdamW, one launch for all tensors: blockIdx.y = tensor, grid-stride over its elements
+// AdamW / Adam, one launch for all tensors: blockIdx.y = tensor, grid-stride over its elements.  torch.optim semantics:
+// decoupled decay (AdamW) multiplies the parameter by (1 - lr*wd); coupled decay (Adam) adds wd*p to the gradient;
+// amsgrad (entry.vmax != NULL) keeps the running maximum of exp_avg_sq and divides by it.
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float* vmax, float lr, float b1, float b2, float eps,
+                                            float wd, int coupled, float step_size, float bc2_sqrt) {
+  if (coupled) g += wd * p; else p *= (1.f - lr * wd);
+  m = b1 * m + (1.f - b1) * g;
+  v = b2 * v + (1.f - b2) * g * g;
+  float vv = v;
+  if (vmax) { vv = fmaxf(*vmax, v); *vmax = vv; }
+  p -= step_size * m / (sqrtf(vv) / bc2_sqrt + eps);
+}
+
 __global__ void __launch_bounds__(256) adamw_kernel(const eegclip_adamw_entry* __restrict__ tab, float lr, float b1, float b2,
-                                                   float eps, float wd, float bc1, float bc2_sqrt) {
+                                                   float eps, float wd, int coupled, float bc1, float bc2_sqrt) {
   pdl_sync();
   const eegclip_adamw_entry e = tab[blockIdx.y];
   float* p = (float*)e.p; const float* g = (const float*)e.g; float* m = (float*)e.m; float* v = (float*)e.v;
+  float* vm = (float*)e.vmax;
   const long n = e.numel;
   const long stride = (long)gridDim.x * blockDim.x;
   const float step_size = lr / bc1;
-  const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)vm) & 15) == 0);
   const long n4 = vec ? (n >> 2) : 0;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<const float4*>(g)[i];
     float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    float4 X = vm ? reinterpret_cast<float4*>(vm)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float pp[4] = {P.x, P.y, P.z, P.w}, gg[4] = {G.x, G.y, G.z, G.w}, mm[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
+    float xx[4] = {X.x, X.y, X.z, X.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      pp[j] *= (1.f - lr * wd);
-      mm[j] = b1 * mm[j] + (1.f - b1) * gg[j];
-      vv[j] = b2 * vv[j] + (1.f - b2) * gg[j] * gg[j];
-      pp[j] -= step_size * mm[j] / (sqrtf(vv[j]) / bc2_sqrt + eps);
-    }
+    for (int j = 0; j < 4; ++j) adam_update(pp[j], gg[j], mm[j], vv[j], vm ? &xx[j] : nullptr, lr, b1, b2, eps, wd, coupled, step_size, bc2_sqrt);
     reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
     reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
     reinterpret_cast<float4*>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    if (vm) reinterpret_cast<float4*>(vm)[i] = make_float4(xx[0], xx[1], xx[2], xx[3]);
   }
   for (long i = n4 * 4 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float P = p[i] * (1.f - lr * wd), G = g[i];
-    float M = b1 * m[i] + (1.f - b1) * G, V = b2 * v[i] + (1.f - b2) * G * G;
-    p[i] = P - step_size * M / (sqrtf(V) / bc2_sqrt + eps);
-    m[i] = M; v[i] = V;
+    float P = p[i], M = m[i], V = v[i];
+    adam_update(P, g[i], M, V, vm ? vm + i : nullptr, lr, b1, b2, eps, wd, coupled, step_size, bc2_sqrt);
+    p[i] = P; m[i] = M; v[i] = V;
   }
 }
 
@@ -445,16 +480,20 @@ int eegclip_infonce_backward(const float* S_all, const float* E_all, const float
   return EEGCLIP_OK;
 }
 
-int eegclip_membank_update(float* memory, const int64_t* idx, const float* data, float* old_out, int32_t rows, int32_t D,
-                           float momentum, float one_minus_momentum, void* stream) {
-  if (!memory || !idx || !data || !old_out || rows <= 0 || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
-  LAUNCH_PDL((membank_kernel), rows, 256, 0, (cudaStream_t)stream, memory, idx, data, old_out, D, momentum, one_minus_momentum);
+int eegclip_membank_update(float* memory, int64_t bank_rows, const int64_t* idx, const float* data, float* old_out, int32_t rows,
+                           int32_t D, float momentum, float one_minus_momentum, void* stream) {
+  if (!memory || !idx || !data || !old_out || rows <= 0 || D <= 0 || (D & 3) || bank_rows <= 0) return EEGCLIP_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  LAUNCH_PDL((membank_gather_kernel), rows, 256, 0, st, (const float*)memory, idx, old_out, D, (long)bank_rows);
+  LAUNCH_CHECK();
+  LAUNCH_PDL((membank_scatter_kernel), rows, 256, 0, st, memory, idx, data, (const float*)old_out, rows, D, (long)bank_rows, momentum,
+             one_minus_momentum);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
 
 int eegclip_adamw_step(const eegclip_adamw_entry* table_dev, int32_t n_tensors, int64_t max_numel, float lr, float beta1,
-                       float beta2, float eps, float weight_decay, int64_t step, void* stream) {
+                       float beta2, float eps, float weight_decay, int32_t coupled_decay, int64_t step, void* stream) {
   if (!table_dev || n_tensors <= 0 || max_numel <= 0 || step <= 0) return EEGCLIP_ERR_ARG;
   double bc1 = 1.0 - pow((double)beta1, (double)step);
   double bc2 = 1.0 - pow((double)beta2, (double)step);
@@ -463,7 +502,8 @@ int eegclip_adamw_step(const eegclip_adamw_entry* table_dev, int32_t n_tensors, 
   if (gx < 1) gx = 1;
   if (gx > 128) gx = 128;
   dim3 grid(gx, n_tensors);
-  LAUNCH_PDL((adamw_kernel), grid, 256, 0, (cudaStream_t)stream, table_dev, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2));
+  LAUNCH_PDL((adamw_kernel), grid, 256, 0, (cudaStream_t)stream, table_dev, lr, beta1, beta2, eps, weight_decay, (int)coupled_decay,
+             (float)bc1, (float)sqrt(bc2));
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

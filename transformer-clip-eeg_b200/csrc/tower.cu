@@ -754,4 +754,58 @@ int eegclip_xfblock_backward(const eegclip_xfblock_desc* d, const float* const* 
   return xf_block_bwd(t, d->layer, xf_at<XfP>(params - 2, 0, 0), xf_at<XfG>(grads - 2, 0, 0), zin, xs, dzout, dzin, w, st);
 }
 
+// -------------------------------------------------------------------------------------------------
+// Stand-alone pieces of the transformer block (MultiHeadAttention.forward, ResidualAdd.forward; clip_model.py:30-57)
+// -------------------------------------------------------------------------------------------------
+int eegclip_attention_forward(const float* qkv, float* out, float* lse, int32_t B, int32_t T, float p_drop, int32_t train,
+                              int32_t layer, uint64_t seed, int32_t math, void* stream) {
+  if (!qkv || !out || !lse || B <= 0 || T <= 0 || (T & 3)) return EEGCLIP_ERR_ARG;
+  const Drop drop = make_drop(seed, layer, SITE_ATTN, p_drop, train);
+  if (math != EEGCLIP_MATH_FP32 && attention_tc_supported(T)) return attention_fwd_tc(qkv, out, lse, B, T, drop, (cudaStream_t)stream);
+  return attention_fwd(qkv, out, lse, B, T, drop, (cudaStream_t)stream);
+}
+
+int eegclip_attention_backward(const float* qkv, const float* out, const float* dout, const float* lse, float* dqkv, int32_t B,
+                               int32_t T, float p_drop, int32_t train, int32_t layer, uint64_t seed, int32_t math, void* stream) {
+  if (!qkv || !out || !dout || !lse || !dqkv || B <= 0 || T <= 0 || (T & 3)) return EEGCLIP_ERR_ARG;
+  const Drop drop = make_drop(seed, layer, SITE_ATTN, p_drop, train);
+  if (math != EEGCLIP_MATH_FP32 && attention_tc_supported(T)) return attention_bwd_tc(qkv, out, dout, lse, dqkv, B, T, drop, (cudaStream_t)stream);
+  return attention_bwd(qkv, out, dout, lse, dqkv, B, T, drop, (cudaStream_t)stream);
+}
+
+int eegclip_layernorm_forward(const float* x, const float* gamma, const float* beta, float* out, int64_t rows, int32_t C, void* stream) {
+  if (!x || !gamma || !beta || !out || rows <= 0) return EEGCLIP_ERR_ARG;
+  if (C != 64) return EEGCLIP_ERR_UNSUPPORTED;
+  return ln64_fwd(x, gamma, beta, out, rows, (cudaStream_t)stream);
+}
+
+int eegclip_layernorm_backward(const float* dout, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                               int64_t rows, int32_t C, void* stream) {
+  if (!dout || !x || !gamma || !dx || !dgamma || !dbeta || rows <= 0) return EEGCLIP_ERR_ARG;
+  if (C != 64) return EEGCLIP_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(dgamma, 0, 64 * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(dbeta, 0, 64 * sizeof(float), st));
+  return ln64_bwd(dout, x, gamma, nullptr, dx, dgamma, dbeta, rows, st);
+}
+
+int eegclip_dropout(const float* in, float* out, int64_t n, float p, int32_t train, int32_t layer, int32_t site, uint64_t seed,
+                    void* stream) {
+  if (!in || !out || n <= 0 || (n & 3) || site < 0 || site > 15) return EEGCLIP_ERR_ARG;
+  return drop_mul(in, out, n, make_drop(seed, layer, site, p, train), (cudaStream_t)stream);
+}
+
+// FeedForwardBlock's nn.GELU() -> nn.Dropout pair (clip_model.py:64-65) as one elementwise pass and its backward
+int eegclip_gelu_dropout_forward(const float* pre, float* out, int64_t n, float p, int32_t train, int32_t layer, int32_t site,
+                                 uint64_t seed, void* stream) {
+  if (!pre || !out || n <= 0 || (n & 3) || site < 0 || site > 15) return EEGCLIP_ERR_ARG;
+  return gelu_drop(pre, out, n, make_drop(seed, layer, site, p, train), (cudaStream_t)stream);
+}
+
+int eegclip_gelu_dropout_backward(const float* pre, const float* dout, float* dpre, int64_t n, float p, int32_t train, int32_t layer,
+                                  int32_t site, uint64_t seed, void* stream) {
+  if (!pre || !dout || !dpre || n <= 0 || (n & 3) || site < 0 || site > 15) return EEGCLIP_ERR_ARG;
+  return gelu_drop_bwd(pre, dout, dpre, n, make_drop(seed, layer, site, p, train), (cudaStream_t)stream);
+}
+
 }  // extern "C"

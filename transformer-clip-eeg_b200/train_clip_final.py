@@ -8,9 +8,10 @@ Call-compatible pieces:
   * ``main`` -- the training loop with StepLR per epoch (:419,503-504), validation and checkpointing (:506-540),
     optionally data-parallel under torchrun (sharded InfoNCE + SUM all-reduce; new functionality).
 
-Dataset plumbing (dataset_loader.py, file split, regression evaluations) is out of scope; ``--data_dir synthetic``
-feeds seeded synthetic batches of the reference's shapes, any other value expects the reference's own
-``dataset_loader`` / ``train_clip_helper_functions.get_train_val_test_files_final`` to be importable.
+Dataset plumbing (dataset_loader.py, the file split) is out of scope: ``main`` is wired for
+``--data_dir synthetic`` only (seeded synthetic batches of the reference's shapes) and raises for any other value.
+A caller with the reference's ``EEGDatasetSimdata`` at hand drives ``build_model`` / ``train_step`` / ``DevicePrefetcher``
+with its own loader -- they take the reference's batch tuples as they are.
 """
 import argparse
 import json
@@ -21,9 +22,9 @@ import torch
 import torch.distributed as dist
 
 from . import _lib as L
-from .clip_model import (CLIPSimNoLatentProj, EEGConformer, EEGConformerInterleaved, EEGConvLSTM, SpeechSmallConv,
-                         memoryBank)
-from .optim import AdamW
+from .clip_model import (CLIPKLDNoLatentProj, CLIPNoContrastiveLearning, CLIPSim, CLIPSimMultiplePositives, CLIPSimNoLatentProj,
+                         EEGConformer, EEGConformerInterleaved, EEGConvLSTM, SpeechSmallConv, memoryBank)
+from .optim import Adam, AdamW
 from .parallel import allreduce_gradients, broadcast_parameters
 from .vlaai import VLAAI
 
@@ -117,7 +118,7 @@ def speech_dimension_of(stimulus_features):
 
 
 def build_model(args, window_length, bank_size, device):
-    """Model construction of train_clip_final.py:338-399 (clip_sim_no_latent_proj branch)."""
+    """Model construction of train_clip_final.py:338-399."""
     global _latent_dim_global
     _latent_dim_global = args.latent_dim
     speech_dim, spatial_filters = speech_dimension_of(args.stimulus_features)
@@ -125,13 +126,35 @@ def build_model(args, window_length, bank_size, device):
                            args.latent_dim, args.attention_depth)
     speech = load_speech_encoder(args.speech_encoder, args.lstm_units, 'valid', spatial_filters, args.number_conv_layers,
                                  window_length, 3, speech_dim)
-    if args.model_arch != 'clip_sim_no_latent_proj':
-        raise NameError(f"model_arch '{args.model_arch}' is outside the B200 hot path (SURVEY §2.1 #7)")
-    bank = memoryBank(bank_size=bank_size, dim=speech.get_output_dim(window_length), momentum=args.momentum_membank,
-                      device=device) if bank_size else None
-    model = CLIPSimNoLatentProj(eeg, speech, bank, temperature=args.temperature, window_length=window_length,
-                                lambda_clip=args.lambda_clip_loss, lambda_average=args.lambda_sim_loss)
+    arch = args.model_arch
+    latent_dim = args.latent_dim
+    if arch in ('clip_sim_no_latent_proj', 'clip_kld'):
+        latent_dim = speech.get_output_dim(window_length)      # bank rows / KLD input are the flattened tower output (:367-368)
+    bank = memoryBank(bank_size=bank_size, dim=latent_dim, momentum=args.momentum_membank, device=device) if bank_size else None
+    common = dict(temperature=args.temperature, window_length=window_length, lambda_clip=args.lambda_clip_loss)
+    if arch == 'clip_sim_no_latent_proj':
+        model = CLIPSimNoLatentProj(eeg, speech, bank, lambda_average=args.lambda_sim_loss, **common)
+    elif arch == 'clip_sim':
+        model = CLIPSim(eeg, speech, bank, latent_dim=latent_dim, lambda_average=args.lambda_sim_loss, **common)
+    elif arch == 'clip_mp':
+        model = CLIPSimMultiplePositives(eeg, speech, lambda_average=args.lambda_sim_loss, **common)
+    elif arch == 'clip_kld':
+        model = CLIPKLDNoLatentProj(eeg, speech, latent_dimension=latent_dim, number_of_classes=bank_size,
+                                    lambda_lower_bound=args.lambda_sim_loss, lambda_discriminative=args.lambda_sim_loss, **common)
+    elif arch == 'no_contrastive_learning':
+        model = CLIPNoContrastiveLearning(eeg, speech, window_length=window_length)
+    else:
+        # same outcome as the reference for the names its factory never constructs: `model` is unbound (:379-399)
+        raise NameError(f"model_arch '{arch}' is not constructed by train_clip_final.py:379-396")
     return model.to(device)
+
+
+def build_optimizer(args, params):
+    """train_clip_final.py:403-413."""
+    kw = dict(betas=(args.beta1, args.beta2), amsgrad=args.use_amsgrad == 'yes', lr=args.learning_rate)
+    if args.optimizer == 'adam':
+        return Adam(params, **kw)
+    return AdamW(params, weight_decay=args.weight_decay, **kw)
 
 
 def train_step(model, optimizer, eeg, speech, ids, use_total=True, group=None):
@@ -140,7 +163,11 @@ def train_step(model, optimizer, eeg, speech, ids, use_total=True, group=None):
     Order is the reference's: forward, zero_grad, backward, step.  Under a data-parallel ``group`` gradients are
     SUM-all-reduced (one collective on the optimizer's flat arena) before the step.
     """
-    loss_ce, loss_avg, loss_total = model(eeg, speech, ids)
+    out = model(eeg, speech, ids)
+    if len(out) == 4:                                  # the KLD wrappers return (loss_total, loss_ce, log_pmu2, kld_z2) (:1277)
+        loss_total, loss_ce, loss_avg = out[0], out[1], out[3]
+    else:
+        loss_ce, loss_avg, loss_total = out
     optimizer.zero_grad()
     (loss_total if use_total else loss_ce).backward()
     if group is not None:
@@ -304,10 +331,7 @@ def main(argv=None):
     model = build_model(args, window_length, train_data.get_number_of_stimuli_segments(), device)
     model.shard_group = group
     broadcast_parameters(model, group)
-    if args.optimizer != 'adamw':
-        raise L.EegclipError("only --optimizer adamw is on the B200 path (reference default)")
-    opt = AdamW(model.parameters(), betas=(args.beta1, args.beta2), amsgrad=args.use_amsgrad == 'yes',
-                weight_decay=args.weight_decay, lr=args.learning_rate)
+    opt = build_optimizer(args, model.parameters())
     sched = torch.optim.lr_scheduler.StepLR(opt, step_size=args.step_size_scheduler, gamma=0.1) if args.lr_scheduler == 'step' else None
     results = os.path.join(args.results_folder, f"results_{args.model_arch}_eeg_{args.eeg_encoder}_speech_{args.speech_encoder}_date_"
                            f"{time.strftime('%m-%d-%H-%M-%S')}")

@@ -9,15 +9,22 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .clip_model import _ConvBlockFn, _LinearFn, _require_cuda
+from .clip_model import _ConvBlockFn, _LinearFn, _check_ln_shape, _require_cuda
+
+
+BRANCH_TAP = None   # tests: a list that receives, per conv block call, the LeakyReLU branch mask (out > 0) in (B,C,T) layout
 
 
 def _conv_ln_act(x, skip, conv, norm, training):
     B, T, cin = x.shape
     w = conv.weight
+    _check_ln_shape(norm, w.shape[0], T, "VLAAI conv block")
     d = L.ConvBlockDesc(B=B, T=T, Cin=cin, Cout=w.shape[0], taps=w.shape[2], act=1, train=0, math=L.default_math(),
                         p_drop=0.0, layer=0, seed=0)
-    return _ConvBlockFn.apply(x, skip, d, w, conv.bias, norm.weight, norm.bias)
+    out = _ConvBlockFn.apply(x, skip, d, w, conv.bias, norm.weight, norm.bias)
+    if BRANCH_TAP is not None:
+        BRANCH_TAP.append((out.detach() > 0).transpose(1, 2).cpu())
+    return out
 
 
 class Extractor(nn.Module):
