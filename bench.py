@@ -24,9 +24,16 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = "EEG-speech CLIP train samples/sec"
+CONV_MATH_NOTE = "bf16x3 executes 3 MMAs per algorithmic MAC: ceiling of frac is 1/3"
 UNIT = "samples/s"
 T_WIN, F_SPEECH, DEPTH = 320, 1024, 10
 CONV_FLOP_PER_SAMPLE = 2 * T_WIN * 64 * 64 * 64          # one Conv1d(64,64,k=64) pass over one window (fwd == dgrad == wgrad)
+CONV32_FLOP_PER_SAMPLE = 2 * T_WIN * 64 * 64 * 32        # the speech tower's BasicBlock(k=32) conv (clip_model.py:285-291)
+# class-0 launches per step: fwd + dgrad of the 10 EEG BasicBlocks (k=64) and of the speech tower's one BasicBlock (k=32)
+CONV_CLASS0_FLOP_PER_SAMPLE_STEP = 2 * DEPTH * CONV_FLOP_PER_SAMPLE + 2 * CONV32_FLOP_PER_SAMPLE
+# whole-step algorithmic work per sample: EEG tower fwd+bwd 6769.5 MFLOP + convLSTM speech tower 771 MFLOP
+STEP_MFLOP_PER_SAMPLE = 6769.5 + 771.0
+VLAAI_FWDBWD_FLOP = 98758e6                               # per sample
 
 
 def parse():
@@ -36,7 +43,8 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     p.add_argument("--batch", type=int, default=256, help="windows per GPU")
-    p.add_argument("--cpu_batch", type=int, default=8, help="windows per CPU-baseline step (bounded sample)")
+    p.add_argument("--cpu_batch", type=int, default=64, help="windows per CPU-baseline step (BASELINE config 1: batch 64)")
+    p.add_argument("--no_extras", action="store_true", help="skip the head / scoring / VLAAI / config-3 side measurements")
     p.add_argument("--math", type=str, default=None, choices=["fp32", "bf16x3", "bf16"])
     p.add_argument("--no_cpu_baseline", action="store_true")
     return p.parse_args()
@@ -86,7 +94,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU baseline: the reference algorithm restated in oracle/ (the reference itself is Python and is not on the GPU box)
 # ---------------------------------------------------------------------------------------------------
-def cpu_port_step_fn(batch):
+def cpu_port_step_fn(batch, train=True):
     from oracle import eegclip_oracle as O, synth
     torch.set_num_threads(os.cpu_count() or 1)
     sd = {}
@@ -98,7 +106,7 @@ def cpu_port_step_fn(batch):
     params = list(sd.values()) + [tau, tau_e]
     opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.999), weight_decay=0.01)
     mem = torch.rand(10001, T_WIN * 8)
-    drop = O.Drop(train=True, seed=0, native=True)   # torch's own dropout: the reference's actual cost (72 % bernoulli_)
+    drop = O.Drop(train=train, seed=0, native=True)  # torch's own dropout: the reference's actual cost (72 % bernoulli_)
     eeg, sp = synth.randn(3, batch, T_WIN, 64), synth.randn(4, batch, T_WIN, F_SPEECH)
     ids = torch.arange(1, batch + 1)
 
@@ -113,8 +121,8 @@ def cpu_port_step_fn(batch):
     return step
 
 
-def time_cpu_port(batch, steps, warmup):
-    step = cpu_port_step_fn(batch)
+def time_cpu_port(batch, steps, warmup, train=True):
+    step = cpu_port_step_fn(batch, train)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -130,7 +138,8 @@ def run_reference(args):
         return
     val, ms = time_cpu_port(args.cpu_batch, args.steps, max(args.warmup, 1))
     cores = os.cpu_count() or 1
-    sample = f"{args.cpu_batch} windows per step (bounded sample of the batch-256 workload), train mode, fwd+bwd+AdamW"
+    sample = (f"{args.cpu_batch} windows per step (BASELINE config 1's batch; a bounded sample of the batch-{args.batch} workload: the "
+              "per-window cost of the CPU path does not depend on the batch), train mode, fwd+bwd+AdamW")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -148,6 +157,81 @@ def run_reference(args):
 def workload_name(batch):
     return (f"full CLIP train step (fwd+bwd+AdamW, train mode): EEGConformerInterleaved depth {DEPTH} + convLSTM speech tower + "
             f"CLIPSimNoLatentProj, 64-ch 64 Hz 5 s windows (T={T_WIN}), wav2vec2-shaped speech ({F_SPEECH}), batch {batch} per GPU")
+
+
+# ---------------------------------------------------------------------------------------------------
+# side measurements carried in the same JSON line (BASELINE metric's "fused-loss % of roofline", configs 3-5)
+# ---------------------------------------------------------------------------------------------------
+def _timed_ms(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def measure_head(dev, pk, B=4096, D=2560):
+    """Fused contrastive head at BASELINE config 3's size on ONE GPU: l2-normalise + S.E^T.e^tau + row/column CE + backward
+    (all gradients incl. normalisation), CUDA events over 5 passes; algorithmic work 6.B^2.D (fwd 2, bwd 4)."""
+    from transformer_clip_eeg_b200.parallel import infonce_loss
+    g = torch.Generator().manual_seed(1)
+    E = torch.randn(B, D, generator=g).to(dev).requires_grad_(True)
+    S = torch.randn(B, D, generator=g).to(dev).requires_grad_(True)
+    tau = torch.tensor(0.075, device=dev, requires_grad=True)
+
+    def fb():
+        E.grad = S.grad = tau.grad = None
+        infonce_loss(E, S, tau).backward()
+    ms = _timed_ms(fb)
+    tf = 6.0 * B * B * D / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "symmetric InfoNCE head fwd+bwd (eegclip_l2norm_* + eegclip_infonce_lse/_loss/_backward), one GPU",
+            "B": B, "D": D, "ms": ms, "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"],
+            "algorithmic_flop": 6.0 * B * B * D}
+
+
+def measure_scoring(dev, pk, N=4096, D=2560):
+    """BASELINE config 4 on one GPU: candidate row-dots (HBM-bound) and bank similarity + top-100 (tensor-bound GEMM)."""
+    from transformer_clip_eeg_b200 import train_clip_helper_functions as H
+    g = torch.Generator().manual_seed(2)
+    E = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=1).to(dev)
+    out = {"N": N, "D": D, "rowdots": {}, "bank": {}}
+    for K in (2, 5, 100):
+        C = torch.randn(N, K, D, device=dev)
+        ms = _timed_ms(lambda: H.mm_scores(E, C), reps=3, warm=1)
+        gbs = N * K * D * 4 / (ms * 1e-3) / 1e9
+        out["rowdots"][f"K={K}"] = {"ms": ms, "GB/s": gbs, "frac_hbm": gbs / pk["hbm_gbs"]}
+        del C
+    for M in (1000, 10000, 100000):
+        Bk = torch.randn(M, D, device=dev)
+        ms = _timed_ms(lambda: H.bank_logits(E, Bk), reps=3, warm=1)
+        ms_k = _timed_ms(lambda: H.bank_topk(E, Bk, 100), reps=3, warm=1)
+        out["bank"][f"M={M}"] = {"logits_ms": ms, "TFLOP/s": 2.0 * N * M * D / (ms * 1e-3) / 1e12, "with_top100_ms": ms_k,
+                                 "top100_over_gemm": ms_k / ms}
+        del Bk
+    return out
+
+
+def measure_vlaai(dev, pk):
+    """BASELINE config 5: VLAAI forward+backward on synthetic EEG, one GPU."""
+    from transformer_clip_eeg_b200 import vlaai
+    torch.manual_seed(0)
+    model = vlaai.VLAAI().to(dev).train()
+    out = {}
+    for B in (64, 256):
+        x = torch.randn(B, 320, 64, device=dev)
+
+        def fb():
+            model.zero_grad(set_to_none=True)
+            model(x).sum().backward()
+        ms = _timed_ms(fb, reps=3, warm=2)
+        tf = B * VLAAI_FWDBWD_FLOP / (ms * 1e-3) / 1e12
+        out[f"B={B}"] = {"ms_fwd_bwd": ms, "samples/s": B / (ms * 1e-3), "TFLOP/s": tf, "frac_tensor": tf / pk["bf16_sustained"]}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -262,16 +346,40 @@ def run_b200(args):
     run_e2e(args.steps)
     ms_e2e = timed(run_e2e, args.steps, whole=True)
 
+    pk = peaks()
+    extras = None
+    if not args.no_extras:
+        extras = {}
+        if world > 1 and B != 512:
+            # BASELINE config 3 proper: 512 windows per rank (global 4096 at 8 GPUs), timed beside the 256-per-rank weak-scaling number
+            B3 = 512
+            g3 = torch.Generator().manual_seed(100 + rank)
+            batch3 = (torch.randn(B3, T_WIN, 64, generator=g3).to(dev), torch.randn(B3, T_WIN, F_SPEECH, generator=g3).to(dev),
+                      (torch.randperm(10000, generator=g3)[:B3] + 1).to(dev))
+            fn3 = lambda i: tcf.train_step(model, opt, *batch3, group=group)
+            for i in range(3):
+                fn3(i)
+            ms3 = timed(fn3, max(3, args.steps // 2))
+            extras["config3_512_per_rank"] = {"global_batch": world * B3, "ms_per_step": ms3, "value": world * B3 / (ms3 * 1e-3), "unit": UNIT}
+            del batch3
+        if world == 1:
+            torch.cuda.empty_cache()
+            extras["roofline_head"] = measure_head(dev, pk)
+            extras["scoring"] = measure_scoring(dev, pk)
+            extras["vlaai"] = measure_vlaai(dev, pk)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    pk = peaks()
     names = ["conv_fwd_dgrad_tc", "conv_wgrad_tc", "attn_fwd", "attn_bwd", "ln_ct", "gemm_f32", "lin_tc", "lin_wgrad_tc", "lstm_recurrence"]
     kern = {n: {"ms_per_step": prof_ms[i] / args.steps, "launches_per_step": prof_n[i] / args.steps} for i, n in enumerate(names)}
     conv_launches = max(1, conv_launches_timed)
     conv_ms = conv_ms_total / conv_launches
-    achieved = B * CONV_FLOP_PER_SAMPLE / (conv_ms * 1e-3) / 1e12 if conv_launches_timed else 0.0
+    # class 0 = 20 Conv1d(k=64) fwd/dgrad launches + 2 launches of the speech tower's k=32 conv per step: credit each its own FLOPs
+    conv_flop_timed = args.steps * B * CONV_CLASS0_FLOP_PER_SAMPLE_STEP
+    achieved = conv_flop_timed / (conv_ms_total * 1e-3) / 1e12 if conv_launches_timed else 0.0
+    step_flop = B * STEP_MFLOP_PER_SAMPLE * 1e6 + 6.0 * B * (world * B) * (T_WIN * 8)
+    step_tf = step_flop / (ms_step * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
     if os.path.exists(tpath):
@@ -294,19 +402,30 @@ def run_b200(args):
         "roofline": {"bound": "tensor", "kernel": "conv64_tc_kernel (Conv1d k=64 forward + data-gradient launches)",
                      "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                      "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                     "algorithmic_flop_per_launch": B * CONV_FLOP_PER_SAMPLE, "avg_launch_ms": conv_ms,
-                     "launches_timed": int(conv_launches_timed), "note": "bf16x3 executes 3 MMAs per algorithmic MAC: ceiling of frac is 1/3",
+                     "algorithmic_flop_per_launch": conv_flop_timed / conv_launches, "avg_launch_ms": conv_ms,
+                     "launches_timed": int(conv_launches_timed),
+                     "note": "per step 20 launches of the k=64 conv (B x 167.77 MFLOP each) + 2 of the speech tower's k=32 conv (B x 83.89 MFLOP "
+                             "each), each credited its own FLOPs; " + CONV_MATH_NOTE,
                      "traffic": traffic},
+        "roofline_whole_step": {"bound": "tensor", "achieved": step_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                                "frac": step_tf / pk["bf16_sustained"], "algorithmic_flop_per_step": step_flop,
+                                "note": "per sample 6769.5 MFLOP (EEG tower fwd+bwd) + 771 MFLOP (convLSTM speech tower) + head 6.b.B.D, "
+                                        "divided by ms_per_step; the step is a chain of HBM-bound token kernels around the tensor-bound conv"},
         "kernels": kern,
         "kernels_note": f"per-class CUDA-event times from a second pass of the same {args.steps} steps with events around every launch "
                         f"({ms_step_profiled:.2f} ms/step: the events serialise the launches); the timed region records events around the "
                         "roofline kernel's launches only",
     }
+    if extras is not None:
+        line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
         val, ms = time_cpu_port(args.cpu_batch, 2, 1)
+        val_e, ms_e = time_cpu_port(args.cpu_batch, 1, 1, train=False)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                "sample": f"{args.cpu_batch} windows per step, 2 timed steps after 1 warm-up ({ms:.0f} ms/step), same "
-                                          "model/step as the GPU arm, torch CPU ops on all host threads"}
+                                "sample": f"{args.cpu_batch} windows per step (BASELINE config 1's batch), 2 timed steps after 1 warm-up "
+                                          f"({ms:.0f} ms/step), train mode (torch's own dropout), same model/step as the GPU arm, torch CPU "
+                                          "ops on all host threads",
+                                "value_eval_mode": val_e, "ms_per_step_eval_mode": ms_e}
     _OUT.write(json.dumps(line) + "\n")
     _OUT.flush()
     if world > 1:
