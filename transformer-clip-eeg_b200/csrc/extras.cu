@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(TK_THREADS) row_topk_kernel(const float* __res
   __shared__ uint32_t tsum[TK_THREADS];
   __shared__ uint32_t ckey[TK_CAP];
   __shared__ int cidx[TK_CAP];
-  __shared__ uint32_t s_bin, s_above, s_ncand, s_neq;
+  __shared__ uint32_t s_bin, s_above, s_ncand;
   const float* row = x + (long)blockIdx.x * ld;
   const int tid = threadIdx.x;
   const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
@@ -183,17 +183,37 @@ __global__ void __launch_bounds__(TK_THREADS) row_topk_kernel(const float* __res
       if (total_ge <= (uint32_t)TK_CAP) break;
       if (level == 2) exact = true;      // prefix is a full key and too many elements equal it: take only `need` of them
     }
-    if (tid == 0) { s_ncand = 0; s_neq = 0; }
+    if (tid == 0) s_ncand = 0;
     __syncthreads();
     scan_row(row, M, vec, [&](uint32_t key, int i) {
       const uint32_t top = pbits == 32 ? key : (key >> (32 - pbits));
-      bool take = top > prefix;
-      if (top == prefix) take = exact ? (atomicAdd(&s_neq, 1u) < need) : true;
-      if (take) {
+      if (top > prefix || (!exact && top == prefix)) {
         const uint32_t pos = atomicAdd(&s_ncand, 1u);
         if (pos < (uint32_t)TK_CAP) { ckey[pos] = key; cidx[pos] = i; }
       }
     });
+    __syncthreads();
+    if (exact) {
+      // massive tie at the k-th value: take the `need` LOWEST columns that equal it (ordered pass over the row, block-wide ranks)
+      uint32_t taken = 0;
+      const int lane = tid & 31, wid = tid >> 5;
+      for (int base = 0; base < M && taken < need; base += TK_THREADS) {
+        const int i = base + tid;
+        const bool eq = i < M && f2key(row[i]) == prefix;
+        const uint32_t bal = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) tsum[wid] = __popc(bal);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int w = 0; w < TK_THREADS / 32; ++w) { if (w < wid) before += tsum[w]; total += tsum[w]; }
+        const uint32_t rank = taken + before + __popc(bal & ((1u << lane) - 1u));
+        if (eq && rank < need) {
+          const uint32_t pos = atomicAdd(&s_ncand, 1u);
+          if (pos < (uint32_t)TK_CAP) { ckey[pos] = prefix; cidx[pos] = i; }
+        }
+        taken += total;
+        __syncthreads();
+      }
+    }
     __syncthreads();
   }
   const int n = (int)min(s_ncand, (uint32_t)TK_CAP);

@@ -84,11 +84,12 @@ class AdamW(torch.optim.Optimizer):
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)                # fills self.state[p] with loaded copies
+        loaded = {p: dict(st) for p, st in self.state.items()}   # (arena creation below republishes self.state)
         for gi, g in enumerate(self.param_groups):
             a = self._group_arena(gi, g)
             names = ["exp_avg", "exp_avg_sq"] + (["max_exp_avg_sq"] if g["amsgrad"] else [])
             for i, p in enumerate(a["ps"]):
-                st = self.state.get(p)
+                st = loaded.get(p)
                 if not st:
                     continue
                 for k, name in enumerate(names):
