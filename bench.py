@@ -240,7 +240,7 @@ def run_b200(args):
     import transformer_clip_eeg_b200 as pkg
     from transformer_clip_eeg_b200 import _lib, train_clip_final as tcf
     from transformer_clip_eeg_b200.optim import AdamW
-    from transformer_clip_eeg_b200.parallel import broadcast_parameters
+    from transformer_clip_eeg_b200.parallel import bind_to_gpu_numa_node, broadcast_parameters
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -255,6 +255,7 @@ def run_b200(args):
         group = dist.group.WORLD
     if args.math:
         _lib.set_default_math(args.math)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None   # before the pinned staging buffers are allocated
     lib = _lib.load()
     B = args.batch
     torch.manual_seed(0)
@@ -391,6 +392,7 @@ def run_b200(args):
         "dtype": math_name, "data": "synthetic",
         "config": {"workload": workload_name(B), "global_batch": world * B,
                    "parallelism": f"dp{world}: per-rank towers, NCCL all-gather of embeddings, sharded InfoNCE, SUM all-reduce of grads",
+                   "numa": f"rank 0 bound to NUMA node {numa_node} of its GPU (every rank binds to its own GPU's node)" if numa_node is not None else "no NUMA binding",
                    "l2": f"per-step inputs ({h2d_bytes / 1e6:.0f} MB) and activations (>2 GB) exceed the 126 MB L2; {NBUF} batches rotate",
                    "speech_tower": "1x1 conv, BasicBlock(k=32) and both bi-LSTMs (input GEMMs + recurrence kernels) on eegclip kernels"},
         "clocks": clocks,

@@ -297,7 +297,7 @@ int eegclip_l2norm_backward(const float* xn, const float* inv_norm, const float*
 }
 
 struct HeadScratch {
-  size_t part1, part2, g1, g2, packS, packE, wgp, total;
+  size_t part1, part2, g1, g2, packS, packE, packST, packET, total;
 };
 static HeadScratch head_scratch(int b, int Bg, int D) {
   HeadScratch h;
@@ -305,14 +305,15 @@ static HeadScratch head_scratch(int b, int Bg, int D) {
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
   const size_t part = (size_t)b * ceil_div(Bg, GBN) * sizeof(float2);
   h.part1 = take(part); h.part2 = take(part);
-  h.g1 = take((size_t)b * Bg * sizeof(float));
-  h.g2 = take((size_t)b * Bg * sizeof(float));
   const bool tcok = headtc::head_tc_supported(b, Bg, D);
+  // G blocks: fp32 (b, Bg) on the CUDA-core path; packed bf16 hi/lo operand blocks [b/128][Bg/64] (same bytes, rounded up) on tcgen05
+  const size_t gbytes = tcok ? headtc::epack_bytes(b, (int)align_up((size_t)Bg, headtc::KC)) : (size_t)b * Bg * sizeof(float);
+  h.g1 = take(gbytes);
+  h.g2 = take(gbytes);
   h.packS = take(tcok ? headtc::epack_bytes(Bg, D) : 0);
   h.packE = take(tcok ? headtc::epack_bytes(Bg, D) : 0);
-  // weight-gradient-style partials of a backward contraction: [D/kin blocks][token CTAs][256 x kin (+256)]
-  const int kin = 64;
-  h.wgp = take(tcok ? lintc::lin_wgrad_partial_bytes(256, kin, D / kin) : 0);
+  h.packST = take(tcok ? headtc::epack_t_bytes(Bg, D) : 0);     // S_all^T / E_all^T operand blocks of the backward contractions
+  h.packET = take(tcok ? headtc::epack_t_bytes(Bg, D) : 0);
   h.total = o;
   return h;
 }
@@ -404,39 +405,37 @@ int eegclip_infonce_backward(const float* S_all, const float* E_all, const float
     uint8_t* pE = (uint8_t*)(sc + hs.packE);
     TRY(headtc::epack(S_all, pS, Bg, D, st));
     TRY(headtc::epack(E_all, pE, Bg, D, st));
-    // GrT[j][i] = G(i = local speech row, j = any EEG column)        -> dS_loc = exp(tau) GrT^T . E_all
+    // Gr(i = local speech row, j = any EEG column), packed as the A operand (rows i, contraction j)  -> dS_loc = exp(tau) Gr . E_all
+    const int nkc_g = ceil_div(Bg, headtc::KC);
+    uint8_t* pGr = (uint8_t*)Gr;
+    uint8_t* pGc = (uint8_t*)Gc;
     headtc::LogitsArgs a{};
     a.Ap = pS; a.Bp = pE; a.a_blk0 = row0 / headtc::RB; a.M = b; a.N = Bg; a.D = D; a.tau = tau;
     a.m_off = row0; a.n_off = 0; a.lse_m = lse_row_all; a.lse_n = lse_col_all; a.up = dloss; a.inv_2b = 0.5f / (float)Bg;
-    a.one_sided = one_sided; a.GT = Gr; a.ldg = b; a.dtau = dtau_partial;
-    TRY(headtc::logits_launch<2>(math, a, st));
-    // Gc[i][j] = G(i = any speech row, j = local EEG column): the (E_loc x S_all) product stored transposed.
+    a.one_sided = one_sided; a.Gp = pGr; a.nkc_g = nkc_g; a.dtau = dtau_partial;
+    const bool need_ds = dS_loc && !one_sided;
+    TRY(headtc::logits_launch<2>(math, a, st));   // (one-sided: only d tau comes out of this block, its G is not consumed)
+    // Gc^T(j = local EEG column, i = any speech row): the (E_loc x S_all) product, packed with rows j and contraction i
+    //   -> dE_loc = exp(tau) Gc^T . S_all.
     // One-sided (memory-bank term, clip_model.py:934-937): G(i,j) = (softmax_j L(i,.) - delta) / B, the statistics belong to
     // the rows i of X = S_all, which are the n side of this product (one_sided = 2); only E has a gradient.
     headtc::LogitsArgs c = a;
-    c.Ap = pE; c.Bp = pS; c.GT = Gc; c.dtau = nullptr;
+    c.Ap = pE; c.Bp = pS; c.Gp = pGc; c.dtau = nullptr;
     c.lse_m = one_sided ? nullptr : lse_col_all;
     c.lse_n = lse_row_all;
     c.one_sided = one_sided ? 2 : 0;
-    float* const none3[3] = {nullptr, nullptr, nullptr};
-    auto contract = [&](const float* GT, const float* X, float* out) -> int {
-      // out[i][d] = exp(tau) * sum_j GT[j][i] * X[j][d]   (contraction over the global batch index j; D in 64-wide blocks
-      // handled by one launch, the local rows i in blocks of <= 256)
-      const int kin = 64;
-      for (int i0 = 0; i0 < b; i0 += 256) {
-        const int nb = min(256, b - i0);
-        lintc::LinWgradArgs w{};
-        w.dy = GT + i0; w.lddy = b; w.Nout = nb; w.x = X; w.ldx = D; w.Kin = kin; w.M = Bg;
-        w.drop_dy = make_drop(0, 0, 0, 0.f, 0); w.drop_x = w.drop_dy; w.partial = (float*)(sc + hs.wgp);
-        float* dW[3] = {out + (long)i0 * D, nullptr, nullptr};
-        int rc = lintc::lin_wgrad_launch(math, w, dW, none3, nb, st, D, tau, D / kin);
-        if (rc != EEGCLIP_OK) return rc;
-      }
-      return EEGCLIP_OK;
-    };
     TRY(headtc::logits_launch<2>(math, c, st));
-    if (dS_loc && !one_sided) TRY(contract(Gr, E_all, dS_loc));
-    TRY(contract(Gc, S_all, dE_loc));
+    // the two contractions over the global batch index: out (b x D) = exp(tau) * Gpacked (b x Bg) . X_all (Bg x D), i.e. the
+    // similarity kernel again with A = packed G and B = packed X^T (rows = features), dot products stored row-major
+    auto contract = [&](const uint8_t* Gpk, const float* X, uint8_t* pXT, float* out) -> int {
+      int rc = headtc::epack_t(X, pXT, Bg, D, st);
+      if (rc != EEGCLIP_OK) return rc;
+      headtc::LogitsArgs g{};
+      g.Ap = Gpk; g.Bp = pXT; g.a_blk0 = 0; g.M = b; g.N = D; g.D = nkc_g * headtc::KC; g.tau = tau; g.out = out; g.ldo = D;
+      return headtc::logits_launch<3>(math, g, st);
+    };
+    if (need_ds) TRY(contract(pGr, E_all, (uint8_t*)(sc + hs.packET), dS_loc));
+    TRY(contract(pGc, S_all, (uint8_t*)(sc + hs.packST), dE_loc));
     return EEGCLIP_OK;
   }
   // G rows block, scaled by dloss * exp(tau) on the fly?  exp(tau) is a device scalar -> applied in the second GEMM.

@@ -7,11 +7,12 @@
 //   logits_tc_kernel    CTA (m block of 128 rows) x (n tile of 256 columns): TMA producer thread + MMA thread (K loop over
 //                       D in 64-column chunks, 2-stage ring) + 4 epilogue warps (one thread per row):
 //       MODE 1  per-row (max, sum exp) partial of the tile + the diagonal logit        (forward: row / column LSE)
-//       MODE 2  G = (exp(L - lse_m) + exp(L - lse_n) - 2 delta) / (2B) * upstream, stored TRANSPOSED (n-major, coalesced)
-//               + sum G.L for d tau                                                     (backward: cross-entropy gradient)
-//       MODE 3  raw similarities stored row-major (match-mismatch bank scoring, train_clip_helper_functions.py:182)
-//   The two products of the backward, dS = exp(tau) G.E and dE = exp(tau) G^T.S, are contractions over the batch index
-//   and run on lin_wgrad_tc_kernel (lin_tc.cuh) with G^T / G as the token-major operand.
+//       MODE 2  G = (exp(L - lse_m) + exp(L - lse_n) - 2 delta) / (2B) * upstream, written straight into the packed bf16 hi/lo
+//               A-operand layout of the next GEMM (rows m, contraction index n) + sum G.L for d tau   (backward: CE gradient)
+//       MODE 3  dot products (x exp(tau) when tau is given) stored row-major: match-mismatch bank scoring
+//               (train_clip_helper_functions.py:182) and the two products of the backward
+//   The products of the backward, dS = exp(tau) G.E and dE = exp(tau) G^T.S, are contractions over the batch index: the same
+//   kernel in MODE 3 with A = packed G (K = batch) and B = the TRANSPOSED embeddings packed by epack_t_kernel (rows = features).
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -57,6 +58,35 @@ __global__ void __launch_bounds__(256) epack_kernel(const float* __restrict__ X,
   }
 }
 
+// Transposed pack: X (R x D fp32) -> operand blocks of X^T (D rows x R contraction columns), same block layout as epack_kernel.
+// grid (ceil(R/64) chunks, ceil(D/128) row blocks); the 64 x 128 fp32 tile goes through shared memory (coalesced reads along D,
+// conflict-free column reads).
+__global__ void __launch_bounds__(256) epack_t_kernel(const float* __restrict__ X, uint8_t* __restrict__ P, int R, int D) {
+  pdl_sync();
+  __shared__ float tile[KC][RB + 1];
+  const int kc = blockIdx.x, rb = blockIdx.y, nkc = gridDim.x;
+  const int r0 = kc * KC, d0 = rb * RB;
+  for (int i = threadIdx.x; i < KC * (RB / 4); i += 256) {
+    const int r = i / (RB / 4), d4 = (i % (RB / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 + r < R && d0 + d4 < D) v = __ldg(reinterpret_cast<const float4*>(X + (long)(r0 + r) * D + d0 + d4));   // D % 4 == 0
+    tile[r][d4] = v.x; tile[r][d4 + 1] = v.y; tile[r][d4 + 2] = v.z; tile[r][d4 + 3] = v.w;
+  }
+  __syncthreads();
+  uint8_t* blk = P + ((size_t)rb * nkc + kc) * BLK;
+  for (int u = threadIdx.x; u < 8 * RB; u += 256) {
+    const int c8 = u / RB, row = u % RB;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = tile[c8 * 8 + e][row];
+    uint4 hi, lo;
+    tc::split8(v, hi, lo);
+    uint8_t* d = blk + (c8 * RB + row) * 16;
+    *reinterpret_cast<uint4*>(d) = hi;
+    *reinterpret_cast<uint4*>(d + PLANE) = lo;
+  }
+}
+
 struct LogitsArgs {
   const uint8_t* Ap;      // packed row operand (m), block index = (m0/128 + blockIdx.y) * nkc + kc
   const uint8_t* Bp;      // packed column operand (n)
@@ -73,11 +103,11 @@ struct LogitsArgs {
   const float* up;        // device scalar: upstream gradient of the loss
   float inv_2b;
   int one_sided;          // 1: G = (exp(L - lse_m) - delta) / B ; 2: G = (exp(L - lse_n) - delta) / B ; 0: symmetric
-  float* GT;              // [N][ldg]: GT[n][m] = G(m, n)
-  int ldg;
+  uint8_t* Gp;            // packed G: operand blocks [m / 128][n / 64], the A operand of the backward contractions over n
+  int nkc_g;              // 64-column chunks per row block of Gp (= ceil(N / 64))
   float* dtau;            // += sum G * L (nullptr: skip)
   // MODE 3
-  float* out;             // [M][ldo] raw dot products (no temperature)
+  float* out;             // [M][ldo] dot products (x exp(tau) when tau != nullptr)
   long ldo;
 };
 
@@ -197,11 +227,12 @@ __global__ void __launch_bounds__(192, 1) logits_tc_kernel(const LogitsArgs a) {
           float* o = a.out + (long)m * a.ldo + n0 + cb;
           if (cb + 32 <= ncols && (a.ldo & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j] * scale, v[j + 1] * scale, v[j + 2] * scale, v[j + 3] * scale);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (cb + j < ncols) o[j] = v[j];
+              if (cb + j < ncols) o[j] = v[j] * scale;
           }
         }
       }
@@ -212,22 +243,32 @@ __global__ void __launch_bounds__(192, 1) logits_tc_kernel(const LogitsArgs a) {
       const float kk = (a.one_sided ? 2.f * a.inv_2b : a.inv_2b) * up;
       const float dsub = a.one_sided ? 1.f : 2.f;
       float tsum = 0.f;
-      for (int cb = 0; cb < ncols; cb += 32) {
+      // whole 64-column contraction chunks are written (zeros beyond the last valid column: the consumer reads full chunks)
+      const int ccols = min(NT, ((ncols + KC - 1) / KC) * KC);
+      uint8_t* grow = a.Gp + (size_t)blockIdx.y * a.nkc_g * BLK + (size_t)(q * 32 + lane) * 16;
+      for (int cb = 0; cb < ccols; cb += 32) {
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = n0 + cb + j;
+          float g = 0.f;
           if (cb + j < ncols) {
             const float Lg = v[j] * scale;
-            float g = use_m ? __expf(Lg - lm) : 0.f;
+            g = use_m ? __expf(Lg - lm) : 0.f;
             if (use_n) g += __expf(Lg - __ldg(a.lse_n + n + a.n_off));
             g = (g - (gm == n + a.n_off ? dsub : 0.f)) * kk;
-            if (mv) {
-              a.GT[(long)n * a.ldg + m] = g;
-              tsum += g * Lg;
-            }
+            if (mv) tsum += g * Lg;
           }
+          v[j] = mv ? g : 0.f;
+        }
+        uint8_t* gblk = grow + (size_t)((n0 + cb) / KC) * BLK + (size_t)(((n0 + cb) % KC) / 8) * (RB * 16);
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          uint4 hi, lo;
+          tc::split8(v + 8 * j8, hi, lo);
+          *reinterpret_cast<uint4*>(gblk + j8 * (RB * 16)) = hi;
+          *reinterpret_cast<uint4*>(gblk + j8 * (RB * 16) + PLANE) = lo;
         }
       }
       if (a.dtau) {
@@ -251,6 +292,14 @@ inline int epack(const float* X, uint8_t* P, int R, int D, cudaStream_t st) {
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
+
+inline int epack_t(const float* X, uint8_t* P, int R, int D, cudaStream_t st) {
+  dim3 grid((R + KC - 1) / KC, (D + RB - 1) / RB);
+  LAUNCH_PDL((epack_t_kernel), grid, 256, 0, st, X, P, R, D);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+inline size_t epack_t_bytes(int R, int D) { return (size_t)((D + RB - 1) / RB) * ((R + KC - 1) / KC) * BLK; }
 
 template <int MODE, int NTERMS>
 inline int logits_launch_t(const LogitsArgs& a, cudaStream_t st) {

@@ -74,8 +74,28 @@ class AdamW(torch.optim.Optimizer):
                 st["max_exp_avg_sq"] = a["views"][3][i]
             self.state[p] = st
 
+    def _fold_foreign_grads(self, a):
+        """Gradients that autograd produced outside the arena (e.g. the log-scales, whose gradient is returned by an autograd
+        Function instead of being sunk) are copied into their arena views; returns the per-parameter "has a gradient" flags."""
+        active = []
+        for p, v in zip(a["ps"], a["views"][0]):
+            if p.grad is None:                             # torch skips parameters without a gradient
+                active.append(False)
+                continue
+            if p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
+            active.append(True)
+        return tuple(active)
+
     def flat_grads(self):
-        return [self._group_arena(gi, g)["flat_g"] for gi, g in enumerate(self.param_groups)]
+        """The flat gradient arenas (one per group) with EVERY existing gradient inside: what the data-parallel all-reduce sums."""
+        out = []
+        for gi, g in enumerate(self.param_groups):
+            a = self._group_arena(gi, g)
+            self._fold_foreign_grads(a)
+            out.append(a["flat_g"])
+        return out
 
     def state_dict(self):
         for gi, g in enumerate(self.param_groups):
@@ -127,16 +147,7 @@ class AdamW(torch.optim.Optimizer):
         loss = closure() if closure is not None else None
         for gi, g in enumerate(self.param_groups):
             a = self._group_arena(gi, g)
-            active = []
-            for p, v in zip(a["ps"], a["views"][0]):
-                if p.grad is None:                         # torch skips parameters without a gradient
-                    active.append(False)
-                    continue
-                if p.grad.data_ptr() != v.data_ptr():      # produced outside the arena (autograd replaced .grad): fold it back in
-                    v.copy_(p.grad)
-                    p.grad = v
-                active.append(True)
-            table = self._table(a, tuple(active), g["amsgrad"])
+            table = self._table(a, self._fold_foreign_grads(a), g["amsgrad"])
             a["step"] += 1
             if table is None:
                 continue

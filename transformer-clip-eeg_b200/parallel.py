@@ -212,3 +212,38 @@ def allreduce_gradients(params, group=None, flat=None):
     for g in grads:
         g.copy_(buf[o:o + g.numel()].view_as(g))
         o += g.numel()
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (and therefore the first-touch placement of the pinned staging buffers it allocates next) to the CPUs
+    of the NUMA node the GPU hangs off.  With one process per GPU and 357 MB of fp32 speech features per rank and step, eight
+    ranks that all stage from one socket's memory are bound by that socket's memory / UPI bandwidth, not by PCIe (round-1 SCALE:
+    end-to-end efficiency 0.91 at 4 and 8 GPUs against 0.98 device-side).  Returns the node id, or None when the topology
+    cannot be read (the call is then a no-op)."""
+    import os
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(torch.cuda.get_device_properties(device_index), "pci_bus_id") else None
+        if bdf is None:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:                 # nvml prints a 32-bit domain, sysfs a 16-bit one
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None

@@ -25,7 +25,7 @@ from . import _lib as L
 from .clip_model import (CLIPKLDNoLatentProj, CLIPNoContrastiveLearning, CLIPSim, CLIPSimMultiplePositives, CLIPSimNoLatentProj,
                          EEGConformer, EEGConformerInterleaved, EEGConvLSTM, SpeechSmallConv, memoryBank)
 from .optim import Adam, AdamW
-from .parallel import allreduce_gradients, broadcast_parameters
+from .parallel import allreduce_gradients, bind_to_gpu_numa_node, broadcast_parameters
 from .vlaai import VLAAI
 
 # flag table: (name, type, default, choices) -- train_clip_final.py:163-216
@@ -320,6 +320,7 @@ def main(argv=None):
     device = torch.device("cuda", local_rank)
     group = None
     if world > 1:
+        bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=device)
         group = dist.group.WORLD
     window_length = args.window_length
