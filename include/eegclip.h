@@ -98,10 +98,13 @@ EEGCLIP_API const char* eegclip_build_info(void);
 EEGCLIP_API long long eegclip_launch_count(void);
 /* Development knobs for kernel tuning sweeps and A/B timing; 0 everywhere = shipped configuration.  Keys:
  *   0 token-GEMM ring depth (2..3)          1 activation load policy (1 = __ldg)      3 force the generic token-GEMM instantiation
- *   4 producer / epilogue warp split rule   6 conv forward: 1 = TS-form kernel        7 1 = no programmatic dependent launch
- *   8 bit mask of kernel classes that record profiling events (0 = all)               9 1 = register-staged token weight gradient
- *  10 ln64 backward rows per CTA           11 column-sum rows per CTA                12 1 = single-buffer conv weight gradient
- * (the Python layer reads EEGCLIP_TUNE="key=value,..." from the environment at load time). */
+ *   4 producer / epilogue warp split rule   7 1 = no programmatic dependent launch    8 bit mask of kernel classes that record
+ *   profiling events (0 = all)              9 1 = register-staged token weight gradient
+ *  10 ln64 backward rows per CTA           11 column-sum rows per CTA
+ * (the Python layer reads EEGCLIP_TUNE="key=value,..." from the environment at load time).
+ * THREADING: the knobs, the launch counter and the profiling state are PROCESS-GLOBAL development state, written without
+ * synchronisation -- set them before compute starts, from one thread.  All compute entry points are reentrant per
+ * (device, stream): they keep no state of their own besides one-time cudaFuncSetAttribute calls and read the knobs only. */
 EEGCLIP_API int eegclip_tune_set(int32_t key, int32_t value);
 /* Development: device buffer (>= 3*256 uint64) that CTA 0 of the token-GEMM kernel fills with a (event, globaltimer) timeline
  * of its producer / MMA / epilogue roles; NULL (default) disables it. */

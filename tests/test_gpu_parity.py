@@ -317,30 +317,6 @@ def test_conv_tensor_core_channel_blocks_vs_fp32(cm, pkg, Cin, Cout, taps, T, B)
         assert rel_err(a, b) < 2e-4, (name, rel_err(a, b))
 
 
-def test_conv_ts_form_kernel_vs_fp32(cm, pkg):
-    """The TS-form conv kernel (weights as the TMEM A operand; selectable experiment, conv_tc.cuh) == exact-fp32 path."""
-    from transformer_clip_eeg_b200 import _lib
-    T, B = 320, 3
-    blk = cm.BasicBlock(64, 64, kernel_size=64, time_dimension=T).to(DEV).eval()
-    x = torch.randn(B, T, 64, device=DEV)
-    w = torch.randn(B, T, 64, device=DEV)
-    res = {}
-    for m, ts in (("fp32", 0), ("bf16x3", 1)):
-        _lib.set_default_math(m)
-        _lib.call("eegclip_tune_set", 6, ts)
-        try:
-            xx = x.clone().requires_grad_(True)
-            blk.zero_grad()
-            y = blk.forward_time_major(xx, None)
-            (y * w).sum().backward()
-            res[m] = (y.detach(), xx.grad.detach(), blk.conv.weight.grad.detach().clone())
-        finally:
-            _lib.set_default_math("bf16x3")
-            _lib.call("eegclip_tune_set", 6, 0)
-    for a, b, name in zip(res["bf16x3"], res["fp32"], ("y", "dx", "dw")):
-        assert rel_err(a, b) < 2e-4, (name, rel_err(a, b))
-
-
 def test_full_size_properties(cm):
     """BASELINE config 2 sizes (B=256, T=320, depth 10): properties that need no CPU oracle run."""
     torch.manual_seed(0)

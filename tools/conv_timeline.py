@@ -16,7 +16,7 @@ modes = [int(m) for m in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
 ss_list = [int(m) for m in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0]   # 1 = TS-form kernel (g_tune[6])
 for ss, mode in [(q, m) for q in ss_list for m in modes]:     # mode: unused (the exp_mode experiments are recorded in conv_tc.cuh)
     _lib.call("eegclip_tune_set", 5, mode)
-    _lib.call("eegclip_tune_set", 6, ss)
+    pass  # (the TS-form conv experiment was removed in round 2; DESIGN.md keeps its measurement)
     dbg = torch.zeros(768, dtype=torch.int64, device=dev)
     blk.forward_time_major(x, skip)
     _lib.call("eegclip_debug_buffer", dbg.data_ptr())
@@ -28,4 +28,4 @@ for ss, mode in [(q, m) for q in ss_list for m in modes]:     # mode: unused (th
     t = [int(d[i]) - int(d[0]) for i in range(4)]
     print(f"{'TS' if ss else 'SS'} exp_mode {mode}: conv block fwd (pack + conv + LN) {e0.elapsed_time(e1) * 1e3:.1f} us; CTA0: staged {t[1] / 1e3:.2f} us, mma done {t[2] / 1e3:.2f} us, end {t[3] / 1e3:.2f} us")
 _lib.call("eegclip_tune_set", 5, 0)
-_lib.call("eegclip_tune_set", 6, 0)
+pass

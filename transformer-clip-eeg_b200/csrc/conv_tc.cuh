@@ -279,239 +279,6 @@ __global__ void __launch_bounds__(256, 1) conv64_tc_kernel(const ConvTcArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// "TS" forward / data gradient: operand roles swapped so that the WEIGHTS are the A operand and live in TMEM.
-//
-// Experiment (kept selectable, see conv_ts_selected): does a larger N per instruction / an A operand that is not fetched
-// from shared memory raise the pipe rate?  It does not -- see the measurement next to conv_ts_selected.
-// Here  D[(term, co)][t] = sum_k  Wstack[(term, co)][k] * X[t + tap][k] :
-//   A = Wstack = [W_hi ; W_lo] (M = 128 rows, K = 64 input channels per tap), written into a 4-slot TMEM ring (32 columns
-//       per tap: lane = row, column j = channels 2j, 2j+1) by four loader warps with tcgen05.st straight from the packed
-//       global copy -- no shared-memory weight ring at all;
-//   B = the resident activation tile, N = up to 256 TIME rows per instruction, the tap shift is still a +16 B descriptor
-//       offset; planes X_hi and X_lo are two instructions on the same accumulator, which makes this a 4-term product
-//       (hi.hi + lo.hi + hi.lo + lo.lo) at the price of 2 instructions per K-step: 128 cycles per 256 rows each.
-// Accumulators: lanes 0-63 = sum over W_hi rows, lanes 64-127 = sum over W_lo rows, T columns.  Epilogue: the two lane
-// halves are added through shared memory (the activation tile is dead by then), which also transposes to time-major so
-// that bias / Philox dropout / stores are the same 128-bit code as before.
-// ------------------------------------------------------------------------------------------------
-constexpr int TS_WCOL = 384;         // first TMEM column of the weight ring (accumulators use [0, T), T <= 384)
-constexpr int TS_SLOTS = 4;
-
-// Wstack packing: per (n block, k block, tap) 128 rows x 64 contraction channels bf16 (128 B per row): rows 0-63 hi, 64-127 lo
-__global__ void pack_conv_weights_ts_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int mode, int TAPS, int Cin, int Cout) {
-  pdl_sync();
-  const int nN = (mode == 0 ? Cout : Cin) / CH, nK = (mode == 0 ? Cin : Cout) / CH;
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over blocks * taps * 64 n * 8 chunks
-  if (i >= (long)nN * nK * TAPS * CH * 8) return;
-  const int ch = i & 7, n = (i >> 3) & 63;
-  const long rest = i >> 9;
-  const int tap = rest % TAPS;
-  const int blk = rest / TAPS, kb = blk % nK, nb = blk / nK;
-  float v[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int kk = kb * CH + ch * 8 + e, nn = nb * CH + n;
-    v[e] = mode == 0 ? W[((long)nn * Cin + kk) * TAPS + tap] : W[((long)kk * Cin + nn) * TAPS + (TAPS - 1 - tap)];
-  }
-  uint4 hi, lo;
-  tc::split8(v, hi, lo);
-  uint8_t* base = out + ((long)blk * TAPS + tap) * W_TAP_BYTES + n * 128 + ch * 16;
-  *reinterpret_cast<uint4*>(base) = hi;
-  *reinterpret_cast<uint4*>(base + CH * 128) = lo;
-}
-
-__host__ __device__ inline uint32_t conv_ts_smem_bytes(int T, int taps) {
-  uint32_t TP = T + taps - 1;
-  return 2u * 8u * TP * 16u + 128;
-}
-
-template <int NTERMS>
-__global__ void __launch_bounds__(256, 1) conv64_ts_kernel(const ConvTcArgs a) {
-  pdl_sync();
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x, nb = blockIdx.y;
-  const int nkb = a.src_ld / CH;
-  const int T = a.T, TAPS = a.taps, TP = T + TAPS - 1;
-  const uint32_t CS = (uint32_t)TP * 16u;   // chunk stride (bytes)
-  const uint32_t PS = 8u * CS;              // plane stride
-  uint8_t* sA = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2u * PS);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + TS_SLOTS;
-  uint64_t* accfull = bars + 2 * TS_SLOTS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TS_SLOTS + 1);
-
-  auto stamp = [&](int slot) {
-    if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 128) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      a.dbg[slot] = t;
-    }
-  };
-  stamp(0);
-  if (tid == 0) {
-    for (int i = 0; i < TS_SLOTS; ++i) { tc::mbar_init(&full[i], 4); tc::mbar_init(&empty[i], 1); }
-    tc::mbar_init(accfull, 1);
-    tc::mbar_fence_init();
-  }
-  if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
-  uint32_t tmem = 0;
-
-  for (int kb = 0; kb < nkb; ++kb) {
-    // ---- stage the activation tile: fp32 (+skip) -> bf16 hi/lo, chunk-major, zero padded (loads issued STAGE_U deep) ----
-    {
-      const int ld = a.src_ld;
-      const float* sb = a.src + (long)b * a.src_rows * ld + kb * CH;
-      const float* kp = a.skip ? a.skip + (long)b * a.src_rows * ld + kb * CH : nullptr;
-      constexpr int STAGE_U = 6;
-      const int total = TP * 8;
-      for (int base = 0; base < total; base += 256 * STAGE_U) {
-        float4 x[STAGE_U][2], y[STAGE_U][2];
-#pragma unroll
-        for (int u = 0; u < STAGE_U; ++u) {
-          const int idx = base + u * 256 + tid;
-          const int r = idx >> 3, ch = idx & 7;
-          const int t = r - a.row_off;
-          x[u][0] = x[u][1] = y[u][0] = y[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (idx < total && t >= 0 && t < a.src_rows) {
-            const float4* p = reinterpret_cast<const float4*>(sb + (long)t * ld + ch * 8);
-            x[u][0] = __ldg(p); x[u][1] = __ldg(p + 1);
-            if (kp) {
-              const float4* q = reinterpret_cast<const float4*>(kp + (long)t * ld + ch * 8);
-              y[u][0] = __ldg(q); y[u][1] = __ldg(q + 1);
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < STAGE_U; ++u) {
-          const int idx = base + u * 256 + tid;
-          if (idx < total) {
-            const int r = idx >> 3, ch = idx & 7;
-            const float v[8] = {x[u][0].x + y[u][0].x, x[u][0].y + y[u][0].y, x[u][0].z + y[u][0].z, x[u][0].w + y[u][0].w,
-                                x[u][1].x + y[u][1].x, x[u][1].y + y[u][1].y, x[u][1].z + y[u][1].z, x[u][1].w + y[u][1].w};
-            uint4 hi, lo;
-            tc::split8(v, hi, lo);
-            uint8_t* d = sA + ch * CS + r * 16;
-            *reinterpret_cast<uint4*>(d) = hi;
-            if (NTERMS > 1) *reinterpret_cast<uint4*>(d + PS) = lo;
-          }
-        }
-      }
-    }
-    tc::fence_async_smem();
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    tmem = *tmem_slot;
-    if (kb == 0) stamp(1);
-    const uint8_t* wblk = a.wpacked + ((long)nb * nkb + kb) * TAPS * W_TAP_BYTES;
-    const int g0 = kb * TAPS;               // global tap counter of this block's first tap (ring slot / phase bookkeeping)
-
-    if (warp >= 4) {
-      // ===== weight loaders: this thread owns Wstack row 32*(warp-4)+lane; 128 B per tap: global -> registers -> TMEM ring =====
-      const int row = (warp - 4) * 32 + lane;
-      const uint4* src = reinterpret_cast<const uint4*>(wblk + row * 128);
-      uint4 cur[8], nxt[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) cur[j] = __ldg(src + j);
-      for (int tap = 0; tap < TAPS; ++tap) {
-        if (tap + 1 < TAPS) {
-          const uint4* sn = src + (long)(tap + 1) * (W_TAP_BYTES / 16);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) nxt[j] = __ldg(sn + j);
-        }
-        const int s = (g0 + tap) % TS_SLOTS;
-        const uint32_t ph = ((g0 + tap) / TS_SLOTS) & 1;
-        tc::mbar_wait(&empty[s], ph ^ 1);
-        tc::tc_fence_after();
-        tc::tmem_st32(tmem + ((uint32_t)((warp - 4) * 32) << 16) + TS_WCOL + s * 32, reinterpret_cast<const uint32_t*>(cur));
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&full[s]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-      }
-    } else if (warp == 1) {
-      // ===== MMA issuer (whole warp converged, one elected lane issues) =====
-      const uint32_t sA_u = tc::smem_u32(sA);
-      const int nt = (T + 255) >> 8;
-      const int nlast = T - (nt - 1) * 256;                      // 64 .. 256, multiple of 64
-      const uint32_t id256 = tc::idesc_bf16(128, 256, 0, 0), idlast = tc::idesc_bf16(128, nlast, 0, 0);
-      for (int tap = 0; tap < TAPS; ++tap) {
-        const int s = (g0 + tap) % TS_SLOTS;
-        const uint32_t ph = ((g0 + tap) / TS_SLOTS) & 1;
-        const uint32_t acc = (uint32_t)((kb | tap) != 0);
-        tc::mbar_wait(&full[s], ph);
-        tc::tc_fence_after();
-        const uint32_t wa = tmem + TS_WCOL + s * 32;
-        if (tc::elect_one()) {
-          for (int tile = 0; tile < nt; ++tile) {
-            const uint32_t idn = tile == nt - 1 ? idlast : id256;
-            const uint32_t d = tmem + tile * 256;
-            const uint64_t b_hi = tc::smem_desc(sA_u + (uint32_t)(tile * 256 + tap) * 16u, CS, 128);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t db = (uint64_t)((2 * ks * CS) >> 4);   // start-address field is in 16-byte units
-              tc::mma_bf16_ts(d, wa + ks * 8, b_hi + db, idn, acc | (uint32_t)(ks != 0));
-              if (NTERMS > 1) tc::mma_bf16_ts(d, wa + ks * 8, b_hi + db + (uint64_t)(PS >> 4), idn, 1);
-            }
-          }
-          tc::tc_commit(&empty[s]);
-        }
-        __syncwarp();
-      }
-      if (tc::elect_one()) tc::tc_commit(accfull);
-      __syncwarp();
-    }
-    __syncwarp();
-    // every MMA that reads this input block's tile / the weight ring has completed
-    tc::mbar_wait(accfull, (uint32_t)(kb & 1));
-    tc::tc_fence_after();
-  }  // kb
-  stamp(2);
-  // ===== epilogue: add the W_hi and W_lo lane halves through shared memory, transposed to S[t][co] =====
-  float* S = reinterpret_cast<float*>(sA);
-  {
-    const int q = warp & 3, hsel = warp >> 2;          // TMEM lane quarter; column half of this warp
-    const int c_begin = hsel * (T >> 1), c_end = c_begin + (T >> 1);   // T/2 is a multiple of 32
-    const int co = (q & 1) * 32 + lane;
-    if (q >= 2) {
-      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-        float v[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) S[(c0 + j) * CH + co] = v[j];
-      }
-    }
-    __syncthreads();
-    if (q < 2) {
-      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-        float v[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) S[(c0 + j) * CH + co] += v[j];
-      }
-    }
-    __syncthreads();
-    const int c4 = tid & 15;
-    const float4 bb = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + nb * CH) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = tid >> 4; t < T; t += 16) {
-      float4 r = *reinterpret_cast<const float4*>(S + t * CH + c4 * 4);
-      r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
-      const uint64_t didx = ((uint64_t)b * T + t) * a.out_ld + nb * CH + c4 * 4;
-      const float4 m = drop_mult4(a.drop, didx);
-      r.x *= m.x; r.y *= m.y; r.z *= m.z; r.w *= m.w;
-      *reinterpret_cast<float4*>(a.out + ((long)b * T + t) * a.out_ld + nb * CH + c4 * 4) = r;
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  stamp(3);
-  if (warp == 2) tc::tmem_dealloc(tmem, 512);
-}
-
-// ------------------------------------------------------------------------------------------------
 // Weight gradient
 // ------------------------------------------------------------------------------------------------
 struct WgradTcArgs {
@@ -523,140 +290,11 @@ struct WgradTcArgs {
   int Cin, Cout;        // multiples of 64; grid.x = (taps / 16) * (Cout / 64) * (Cin / 64)
 };
 
-__host__ __device__ inline uint32_t wgrad_smem_bytes(int T) {
-  return 2u * 8u * (uint32_t)(T + WG_TAPS - 1) * 16u + 2u * 8u * (uint32_t)T * 16u + 128;
-}
-
-template <int NTERMS>
-__global__ void __launch_bounds__(256, 1) wgrad64_tc_kernel(const WgradTcArgs a) {
-  pdl_trigger();
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ntg = a.taps / WG_TAPS, nci = a.Cin / CH;
-  const int tg = blockIdx.x % ntg, cib = (blockIdx.x / ntg) % nci, cob = blockIdx.x / (ntg * nci), grp = blockIdx.y;
-  const int T = a.T, TAPS = a.taps, TU = T + WG_TAPS - 1;
-  const int k0 = tg * WG_TAPS;
-  const uint32_t CSU = (uint32_t)TU * 16u, PSU = 8u * CSU;
-  const uint32_t CSD = (uint32_t)T * 16u, PSD = 8u * CSD;
-  uint8_t* sU = smem;
-  uint8_t* sD = smem + 2u * PSU;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sD + 2u * PSD);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-  if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); }
-  if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  pdl_wait();   // global memory is read from here on
-  const uint32_t idesc = tc::idesc_bf16(64, CH, 1, 1);   // both operands MN-major (K = time)
-  uint32_t phase = 0;
-  bool first = true;
-  for (int b = grp; b < a.B; b += a.groups) {
-    // ---- stage u rows [k0 - PL, k0 - PL + TU) of the padded input and the T rows of dy (loads issued WG_U deep) ----
-    const int ldx = a.Cin, ldy = a.Cout;
-    const float* xb = a.xin + (long)b * T * ldx + cib * CH;
-    const float* kb = a.skip ? a.skip + (long)b * T * ldx + cib * CH : nullptr;
-    const float* db = a.dypad + ((long)b * (T + TAPS - 1) + a.PLb) * ldy + cob * CH;
-    constexpr int WG_U = 6;
-    const int nu = TU * 8, total = nu + T * 8;       // items [0, nu): u tile; [nu, total): dy tile
-    for (int base = 0; base < total; base += 256 * WG_U) {
-      float4 x[WG_U][2], y[WG_U][2];
-#pragma unroll
-      for (int u = 0; u < WG_U; ++u) {
-        const int idx = base + u * 256 + tid;
-        x[u][0] = x[u][1] = y[u][0] = y[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < nu) {
-          const int r = idx >> 3, ch = idx & 7;
-          const int t = r + k0 - a.PL;
-          if (t >= 0 && t < T) {
-            const float4* p = reinterpret_cast<const float4*>(xb + (long)t * ldx + ch * 8);
-            x[u][0] = __ldg(p); x[u][1] = __ldg(p + 1);
-            if (kb) {
-              const float4* q = reinterpret_cast<const float4*>(kb + (long)t * ldx + ch * 8);
-              y[u][0] = __ldg(q); y[u][1] = __ldg(q + 1);
-            }
-          }
-        } else if (idx < total) {
-          const int i2 = idx - nu;
-          const float4* p = reinterpret_cast<const float4*>(db + (long)(i2 >> 3) * ldy + (i2 & 7) * 8);
-          x[u][0] = __ldg(p); x[u][1] = __ldg(p + 1);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < WG_U; ++u) {
-        const int idx = base + u * 256 + tid;
-        if (idx < total) {
-          const float v[8] = {x[u][0].x + y[u][0].x, x[u][0].y + y[u][0].y, x[u][0].z + y[u][0].z, x[u][0].w + y[u][0].w,
-                              x[u][1].x + y[u][1].x, x[u][1].y + y[u][1].y, x[u][1].z + y[u][1].z, x[u][1].w + y[u][1].w};
-          uint4 hi, lo;
-          tc::split8(v, hi, lo);
-          const bool isu = idx < nu;
-          const int i2 = isu ? idx : idx - nu;
-          uint8_t* d = isu ? sU + (i2 & 7) * CSU + (i2 >> 3) * 16 : sD + (i2 & 7) * CSD + (i2 >> 3) * 16;
-          *reinterpret_cast<uint4*>(d) = hi;
-          if (NTERMS > 1) *reinterpret_cast<uint4*>(d + (isu ? PSU : PSD)) = lo;
-        }
-      }
-    }
-    tc::fence_async_smem();
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    if (warp == 0) {
-      const uint32_t sU_u = tc::smem_u32(sU), sD_u = tc::smem_u32(sD);
-      const int ksteps = T >> 4;
-      const uint32_t acc0 = first ? 0u : 1u;
-      if (tc::elect_one()) {
-        for (int j = 0; j < WG_TAPS; ++j) {
-          const uint32_t d = tmem + (uint32_t)(j >> 1) * 64u + ((uint32_t)((j & 1) * 16) << 16);
-          // A = dy, B = u (both MN-major, K = time): hi*hi, hi*lo, lo*hi
-          const uint64_t a_hi = tc::smem_desc(sD_u, 128, CSD), a_lo = tc::smem_desc(sD_u + PSD, 128, CSD);
-          const uint64_t b_hi = tc::smem_desc(sU_u + (uint32_t)j * 16u, 128, CSU), b_lo = tc::smem_desc(sU_u + PSU + (uint32_t)j * 16u, 128, CSU);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t dk = (uint64_t)(ks * 16);                     // 16 time rows = 256 bytes = 16 address units
-            tc::mma_bf16(d, a_hi + dk, b_hi + dk, idesc, acc0 | (uint32_t)(ks != 0));
-            if (NTERMS > 1) {
-              tc::mma_bf16(d, a_hi + dk, b_lo + dk, idesc, 1);
-              tc::mma_bf16(d, a_lo + dk, b_hi + dk, idesc, 1);
-            }
-          }
-        }
-        tc::tc_commit(bar);
-      }
-      __syncwarp();
-    }
-    tc::mbar_wait(bar, phase);   // all MMAs that read this sample's tiles are done
-    tc::tc_fence_after();
-    phase ^= 1;
-    first = false;
-    __syncthreads();
-  }
-  // ---- epilogue: 16 accumulators -> partial[grp][tap][co][ci] ----
-  if (warp >= 4 && !first) {
-    const int q = warp - 4;
-    const int co = q * 16 + (lane & 15);
-    for (int cb = 0; cb < 8; ++cb) {
-      const int tap = k0 + cb * 2 + (lane >> 4);
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + cb * 64;
-      float* o = a.partial + (((long)grp * TAPS + tap) * a.Cout + cob * CH + co) * a.Cin + cib * CH;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float v[32];
-        tc::tmem_ld32(taddr + half * 32, v);
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(o + half * 32 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-      }
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tmem, 512);
-}
 
 // ------------------------------------------------------------------------------------------------
-// Weight gradient, double-buffered over time slices (the shipped variant).  The kernel above stages a whole sample (u and dy
-// tiles, 168 KB at T = 320), issues its MMAs, waits, stages the next one: ~3.5 us of staging exposed per 24 us of MMAs.  Here the
+// Weight gradient, double-buffered over time slices.  (Round 1's first version staged a whole sample -- u and dy tiles, 168 KB at
+// T = 320 -- issued its MMAs, waited, staged the next one: ~3.5 us of staging exposed per 24 us of MMAs, 2.07 ms per step against
+// 1.64 ms for this kernel; that code is gone, the measurement is in DESIGN.md.)  Here the
 // contraction over time is cut into S slices of TH = T / S rows (S = 2, 4 above T = 384): two slice buffers (86 KB each at
 // T = 320), seven producer warps stage slice i+1 while warp 0 issues the MMAs of slice i (mbarrier full / empty per buffer).
 // ------------------------------------------------------------------------------------------------
@@ -867,30 +505,8 @@ inline size_t conv_tc_scratch_bytes(int B, int T, int taps, int Cin, int Cout) {
          (size_t)conv_tc_wgrad_groups(B, taps, Cin, Cout) * taps * Cin * Cout * sizeof(float) + 256;
 }
 
-// The TS kernel (T <= 384: accumulator columns + the 128-column weight ring) is selected with g_tune[6] = 1.  It is parity-
-// tested but NOT the shipped path: measured per window 63.4 us of MMA time against 60.9 us for the SS kernel -- both forms run
-// at ~21 + 0.63 N cycles per instruction (M = 128, K = 16), i.e. the pipe's real column rate, and the 4-term TS product
-// issues 640 accumulator columns per (tap, K-step) against 576 for the 3-term SS product.
-inline bool conv_ts_selected(int T) { return T <= convtc::TS_WCOL && g_tune[6] == 1; }
-
-template <int NTERMS>
-inline int conv_ts_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
-  static bool configured = false;
-  uint32_t smem = convtc::conv_ts_smem_bytes(a.T, a.taps);
-  if (!configured) {
-    if (cudaFuncSetAttribute(convtc::conv64_ts_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return EEGCLIP_ERR_CUDA;
-    configured = true;
-  }
-  ProfScope prof(PROF_CONV_TC, st);
-  LAUNCH_PDL((convtc::conv64_ts_kernel<NTERMS>), dim3(B, a.out_ld / convtc::CH), 256, smem, st, a);
-  LAUNCH_CHECK();
-  return EEGCLIP_OK;
-}
-
 template <int NTERMS>
 inline int conv_tc_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
-  if (conv_ts_selected(a.T)) return conv_ts_launch<NTERMS>(a, B, st);
   static bool configured = false;
   uint32_t smem = convtc::conv_smem_bytes(a.T, a.taps);
   if (!configured) {
@@ -906,8 +522,8 @@ inline int conv_tc_launch(const convtc::ConvTcArgs& a, int B, cudaStream_t st) {
 
 inline int conv_tc_pack(const float* w, uint8_t* wp, int mode, int taps, int Cin, int Cout, int T, cudaStream_t st) {
   const long n = (long)(Cin / 64) * (Cout / 64) * taps * 8 * 64;
-  if (conv_ts_selected(T)) LAUNCH_PDL((convtc::pack_conv_weights_ts_kernel), (unsigned)((n + 255) / 256), 256, 0, st, w, wp, mode, taps, Cin, Cout);
-  else LAUNCH_PDL((convtc::pack_conv_weights_kernel), (unsigned)((n + 255) / 256), 256, 0, st, w, wp, mode, taps, Cin, Cout);
+  (void)T;
+  LAUNCH_PDL((convtc::pack_conv_weights_kernel), (unsigned)((n + 255) / 256), 256, 0, st, w, wp, mode, taps, Cin, Cout);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -926,24 +542,13 @@ template <int NTERMS>
 inline int wgrad_tc_launch(const convtc::WgradTcArgs& a, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(convtc::wgrad64_tc_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(convtc::wgrad64_db_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
   dim3 grid((a.taps / convtc::WG_TAPS) * (a.Cin / convtc::CH) * (a.Cout / convtc::CH), a.groups);
   ProfScope prof(PROF_WGRAD_TC, st);
-  if (g_tune[12] == 0) {   // shipped: double-buffered over time slices; g_tune[12] = 1 selects the single-buffer kernel (A/B timing)
-    static bool configured_db = false;
-    if (!configured_db) {
-      if (cudaFuncSetAttribute(convtc::wgrad64_db_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-        return EEGCLIP_ERR_CUDA;
-      configured_db = true;
-    }
-    LAUNCH_PDL((convtc::wgrad64_db_kernel<NTERMS>), grid, 256, convtc::wgrad_db_smem_bytes(a.T), st, a);
-    LAUNCH_CHECK();
-    return EEGCLIP_OK;
-  }
-  LAUNCH_PDL((convtc::wgrad64_tc_kernel<NTERMS>), grid, 256, convtc::wgrad_smem_bytes(a.T), st, a);
+  LAUNCH_PDL((convtc::wgrad64_db_kernel<NTERMS>), grid, 256, convtc::wgrad_db_smem_bytes(a.T), st, a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
