@@ -1069,16 +1069,15 @@ struct WgradReduceArgs {
   const float* log_scale;         // optional device scalar: results are multiplied by exp(*log_scale)
   float* dW[4]; float* db[4];     // destination d covers rows [d*rows_per_dst, (d+1)*rows_per_dst); null = discard (padding rows)
 };
-static __global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const WgradReduceArgs a) {
-  pdl_sync();
+__device__ __forceinline__ void wgrad_reduce_body(const WgradReduceArgs& a, int bx, int by) {
   // 32 consecutive outputs x 8 partial groups per CTA; 8 independent loads in flight per thread (latency-bound otherwise)
   __shared__ float sh[8][33];
   const int total = a.Nout * a.Kin + a.Nout;
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + lane;
+  const int i = bx * 32 + lane;
   float s = 0.f;
   if (i < total) {
-    const float* p = a.partial + (long)blockIdx.y * a.ctas * total + i;
+    const float* p = a.partial + (long)by * a.ctas * total + i;
     int c = g;
     for (; c + 56 < a.ctas; c += 64) {
       float v[8];
@@ -1097,13 +1096,41 @@ static __global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const Wgra
     if (i < a.Nout * a.Kin) {
       const int n = i / a.Kin, k = i - n * a.Kin;
       const int d = n / a.rows_per_dst;
-      if (d < 4 && a.dW[d]) a.dW[d][(long)(n - d * a.rows_per_dst) * a.ldw + (long)blockIdx.y * a.Kin + k] = s;
+      if (d < 4 && a.dW[d]) a.dW[d][(long)(n - d * a.rows_per_dst) * a.ldw + (long)by * a.Kin + k] = s;
     } else {
       const int n = i - a.Nout * a.Kin;
       const int d = n / a.rows_per_dst;
-      if (d < 4 && a.db[d] && blockIdx.y == 0) a.db[d][n - d * a.rows_per_dst] = s;
+      if (d < 4 && a.db[d] && by == 0) a.db[d][n - d * a.rows_per_dst] = s;
     }
   }
+}
+static __global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const WgradReduceArgs a) {
+  pdl_sync();
+  wgrad_reduce_body(a, blockIdx.x, blockIdx.y);
+}
+// Several reductions in one launch (blockIdx.z = job): the four weight gradients of a transformer block write their partials to
+// separate regions and are folded together at the end of the block's backward (one launch instead of four ~10 us ones).
+constexpr int MAX_REDUCE_JOBS = 4;
+struct WgradReduceBatch { WgradReduceArgs j[MAX_REDUCE_JOBS]; int kin_blocks[MAX_REDUCE_JOBS]; int n; };
+static __global__ void __launch_bounds__(256) lin_wgrad_reduce_batch_kernel(const WgradReduceBatch b) {
+  pdl_sync();
+  const WgradReduceArgs& a = b.j[blockIdx.z];
+  const int total = a.Nout * a.Kin + a.Nout;
+  if ((int)blockIdx.y >= b.kin_blocks[blockIdx.z] || (int)blockIdx.x * 32 >= total) return;
+  wgrad_reduce_body(a, blockIdx.x, blockIdx.y);
+}
+inline int lin_wgrad_reduce_flush(WgradReduceBatch& b, cudaStream_t st) {
+  if (b.n <= 0) return EEGCLIP_OK;
+  int gx = 1, gy = 1;
+  for (int i = 0; i < b.n; ++i) {
+    const int total = b.j[i].Nout * b.j[i].Kin + b.j[i].Nout;
+    gx = max(gx, (total + 31) / 32);
+    gy = max(gy, b.kin_blocks[i]);
+  }
+  LAUNCH_PDL((lin_wgrad_reduce_batch_kernel), dim3(gx, gy, b.n), 256, 0, st, b);
+  LAUNCH_CHECK();
+  b.n = 0;
+  return EEGCLIP_OK;
 }
 
 inline bool lin_wgrad_tc_supported(long M, int Nout, int Kin) {
@@ -1155,7 +1182,7 @@ inline int lin_wgrad_tma_launch_v(const LinWgradArgs& a, dim3 grid, cudaStream_t
 
 template <int NTERMS>
 inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const db[3], int rows_per_dst, long ldw, cudaStream_t st,
-                              const float* log_scale = nullptr, int kin_blocks = 1) {
+                              const float* log_scale = nullptr, int kin_blocks = 1, WgradReduceBatch* defer = nullptr) {
   if (!lin_wgrad_tc_supported(a.M, a.Nout, a.Kin)) return EEGCLIP_ERR_UNSUPPORTED;
   const int nst = (a.M + WT - 1) / WT;
   const int ctas = wgrad_token_ctas(nst, kin_blocks);
@@ -1183,15 +1210,19 @@ inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const d
   r.partial = a.partial; r.ctas = ctas; r.Nout = a.Nout; r.Kin = a.Kin; r.rows_per_dst = rows_per_dst; r.ldw = ldw > 0 ? ldw : a.Kin; r.log_scale = log_scale;
   for (int i = 0; i < 3; ++i) { r.dW[i] = dW[i]; r.db[i] = db[i]; }
   r.dW[3] = nullptr; r.db[3] = nullptr;
+  if (defer && defer->n < MAX_REDUCE_JOBS) {          // the caller folds this reduction into a later batched launch
+    defer->j[defer->n] = r; defer->kin_blocks[defer->n] = kin_blocks; ++defer->n;
+    return EEGCLIP_OK;
+  }
   const int total = a.Nout * a.Kin + a.Nout;
   LAUNCH_PDL((lin_wgrad_reduce_kernel), dim3((total + 31) / 32, kin_blocks), 256, 0, st, r);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
 inline int lin_wgrad_launch(int math, const LinWgradArgs& a, float* const dW[3], float* const db[3], int rows_per_dst, cudaStream_t st,
-                            long ldw = 0, const float* log_scale = nullptr, int kin_blocks = 1) {
-  return math == EEGCLIP_MATH_BF16 ? lin_wgrad_launch_t<1>(a, dW, db, rows_per_dst, ldw, st, log_scale, kin_blocks)
-                                   : lin_wgrad_launch_t<3>(a, dW, db, rows_per_dst, ldw, st, log_scale, kin_blocks);
+                            long ldw = 0, const float* log_scale = nullptr, int kin_blocks = 1, WgradReduceBatch* defer = nullptr) {
+  return math == EEGCLIP_MATH_BF16 ? lin_wgrad_launch_t<1>(a, dW, db, rows_per_dst, ldw, st, log_scale, kin_blocks, defer)
+                                   : lin_wgrad_launch_t<3>(a, dW, db, rows_per_dst, ldw, st, log_scale, kin_blocks, defer);
 }
 
 // ------------------------------------------------------------------------------------------------

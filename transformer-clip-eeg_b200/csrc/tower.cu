@@ -42,10 +42,11 @@ struct SaveLayout {
   size_t conv_stride, xf_stride, conv0, xf0, total;
   // within a conv block: y (n*C), out (n*C), stats (2B rounded to 4)
   size_t c_y, c_out, c_stats;
-  // within a transformer block: qkv (n*192), o (n*C), lse (B*8*T), z1 (n*C), fpre (n*FF), gp (n*FF), zout (n*C)
+  // within a transformer block: qkv (n*192), o (n*C), lse (B*8*T), z1 (n*C), fpre (n*FF), gp (n*FF), zout (n*C),
+  //   h1 = LN1(zin), h2 = LN2(z1) (n*C each; tcgen05 path: kept so that the backward's weight gradients need no LayerNorm recompute)
   //   fp32 path   : fpre = FFN pre-activation (GELU and mask recomputed in the backward), gp unused
   //   tcgen05 path: fpre slot holds f = dropout(GELU(pre)), gp = mask * GELU'(pre): the backward multiplies, no erf / Philox
-  size_t x_qkv, x_o, x_lse, x_z1, x_fpre, x_gp, x_zout, x_wp;
+  size_t x_qkv, x_o, x_lse, x_z1, x_fpre, x_gp, x_zout, x_h1, x_h2, x_wp;
   size_t map_wp;               // packed eeg_spatial_mapping weights (forward + data-gradient forms)
 };
 
@@ -73,7 +74,8 @@ SaveLayout save_layout(const eegclip_tower_desc& d) {
   L.conv_stride = 2 * n * C + align_up((size_t)2 * d.B, 4);
   L.x_qkv = 0; L.x_o = n * AQKV; L.x_lse = L.x_o + n * C; L.x_z1 = L.x_lse + align_up((size_t)d.B * AH * d.T, 4);
   L.x_fpre = L.x_z1 + n * C; L.x_gp = L.x_fpre + n * FF; L.x_zout = L.x_gp + n * FF;
-  L.x_wp = L.x_zout + n * C;
+  L.x_h1 = L.x_zout + n * C; L.x_h2 = L.x_h1 + n * C;
+  L.x_wp = L.x_h2 + n * C;
   L.xf_stride = L.x_wp + XfPacked::BYTES / sizeof(float);
   L.map_wp = o; o += MAP_WP_BYTES / sizeof(float);
   L.conv0 = o; o += L.conv_stride * d.n_conv;
@@ -83,7 +85,8 @@ SaveLayout save_layout(const eegclip_tower_desc& d) {
 }
 
 struct Scratch {
-  float *upad, *dypad, *h, *f, *dfpre, *dqkv, *d_o, *dg, *dza, *dzb, *dzc, *deeg, *wtmp, *wgp;
+  float *upad, *dypad, *h, *f, *dfpre, *dqkv, *d_o, *dg, *dza, *dzb, *dzc, *deeg, *wtmp, *wgp;   // wgp: 4 partial regions
+  size_t wgp_stride;
   void* tc;
   size_t total;
 };
@@ -106,7 +109,8 @@ Scratch scratch_layout(const eegclip_tower_desc& d, float* base) {
   s.dzc = take(n * C);
   s.deeg = take(n * C);
   s.wtmp = take((size_t)C * C * d.taps);
-  s.wgp = take(lintc::lin_wgrad_partial_bytes(256, 64) / sizeof(float));
+  s.wgp_stride = align_up(lintc::lin_wgrad_partial_bytes(256, 64) / sizeof(float), 64);
+  s.wgp = take(4 * s.wgp_stride);    // one region per weight gradient of a transformer block (their reductions are batched)
   s.tc = take(align_up(ln_ct_scratch_floats(d.T, C), 64) + conv_tc_scratch_bytes(d.B, d.T, d.taps, C, C) / sizeof(float) + 64);
   s.total = o;
   return s;
@@ -251,7 +255,7 @@ int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP
   return EEGCLIP_OK;
 }
 
-struct XfSave { float *qkv, *o, *lse, *z1, *fpre, *gp, *zout; uint8_t* wp; };
+struct XfSave { float *qkv, *o, *lse, *z1, *fpre, *gp, *zout, *h1, *h2; uint8_t* wp; };
 bool xf_tc_ok(const eegclip_tower_desc& d);
 int xf_block_fwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const float* zin, const XfSave& s, Scratch& w, cudaStream_t st);
 int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const XfG& g, const float* zin, const XfSave& s,
@@ -365,9 +369,9 @@ int xf_block_fwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
   using namespace lintc;
   const long n = (long)d.B * d.T;
   TRY(xf_pack(p, s.wp, st));
-  TRY(ln64_fwd(zin, p.ln1g, p.ln1b, w.h, n, st));
+  TRY(ln64_fwd(zin, p.ln1g, p.ln1b, s.h1, n, st));
   {
-    LinTcArgs a = lin_args(w.h, C, s.wp + XfPacked::QKV_F, s.qkv, AQKV, n, AQKV, C);
+    LinTcArgs a = lin_args(s.h1, C, s.wp + XfPacked::QKV_F, s.qkv, AQKV, n, AQKV, C);
     a.bias = (const float*)(s.wp + XfPacked::BQKV);
     TRY(lin_tc_launch(d.math, a, st));
   }
@@ -378,10 +382,10 @@ int xf_block_fwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
     a.bias = p.bo; a.drop = make_drop(d.seed, layer, SITE_PROJ, d.p_proj, d.train); a.drop_on = a.drop.enabled; a.residual = zin;
     TRY(lin_tc_launch(d.math, a, st));
   }
-  TRY(ln64_fwd(s.z1, p.ln2g, p.ln2b, w.h, n, st));
+  TRY(ln64_fwd(s.z1, p.ln2g, p.ln2b, s.h2, n, st));
   {
     // f = mask * GELU(pre) -> saved (W2 operand now, dW2 operand later); gp = mask * GELU'(pre) -> saved for the data gradient
-    LinTcArgs a = lin_args(w.h, C, s.wp + XfPacked::W1_F, s.fpre, FF, n, FF, C);
+    LinTcArgs a = lin_args(s.h2, C, s.wp + XfPacked::W1_F, s.fpre, FF, n, FF, C);
     a.bias = p.b1; a.act = 2; a.aux = s.gp;
     a.drop = make_drop(d.seed, layer, SITE_FFN_HID, d.p_ffn_hid, d.train); a.drop_on = a.drop.enabled;
     TRY(lin_tc_launch(d.math, a, st));
@@ -401,6 +405,7 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
   const Drop d_out = make_drop(d.seed, layer, SITE_FFN_OUT, d.p_ffn_out, d.train);
   const Drop d_hid = make_drop(d.seed, layer, SITE_FFN_HID, d.p_ffn_hid, d.train);
   const Drop d_proj = make_drop(d.seed, layer, SITE_PROJ, d.p_proj, d.train);
+  WgradReduceBatch red; red.n = 0;          // the four partial reductions of this block run as ONE launch at the end
   // ---- FFN branch: dg = dzout * mask_out (never materialised: prologue of both consumers) ----
   {
     LinWgradArgs a{};
@@ -409,7 +414,7 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
     a.pro_x = PRO_NONE; a.drop_x = d_hid;                            // x = f = dropout(GELU(pre)), saved by the forward
     a.partial = w.wgp;
     float* dW[3] = {g.w2, nullptr, nullptr}; float* db[3] = {g.b2, nullptr, nullptr};
-    TRY(lin_wgrad_launch(d.math, a, dW, db, C, st));
+    TRY(lin_wgrad_launch(d.math, a, dW, db, C, st, 0, nullptr, 1, &red));
   }
   {
     LinTcArgs a = lin_args(dzout, C, s.wp + XfPacked::W2_D, w.dfpre, FF, n, FF, C);
@@ -417,13 +422,12 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
     a.mul_src = s.gp;                                                // * mask * GELU'(pre), saved by the forward
     TRY(lin_tc_launch(d.math, a, st));
   }
-  TRY(ln64_fwd(s.z1, p.ln2g, p.ln2b, w.h, n, st));
   {
     LinWgradArgs a{};
-    a.dy = w.dfpre; a.lddy = FF; a.Nout = FF; a.x = w.h; a.ldx = C; a.Kin = C; a.M = (int)n;
-    a.drop_dy = d_out; a.drop_x = d_out; a.partial = w.wgp;
+    a.dy = w.dfpre; a.lddy = FF; a.Nout = FF; a.x = s.h2; a.ldx = C; a.Kin = C; a.M = (int)n;
+    a.drop_dy = d_out; a.drop_x = d_out; a.partial = w.wgp + w.wgp_stride;
     float* dW[3] = {g.w1, nullptr, nullptr}; float* db[3] = {g.b1, nullptr, nullptr};
-    TRY(lin_wgrad_launch(d.math, a, dW, db, FF, st));
+    TRY(lin_wgrad_launch(d.math, a, dW, db, FF, st, 0, nullptr, 1, &red));
   }
   {
     LinTcArgs a = lin_args(w.dfpre, FF, s.wp + XfPacked::W1_D, w.d_o, C, n, C, FF);     // d_o reused as dh2
@@ -434,9 +438,9 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
   {
     LinWgradArgs a{};
     a.dy = w.dzc; a.lddy = C; a.Nout = C; a.x = s.o; a.ldx = C; a.Kin = C; a.M = (int)n;
-    a.pro_dy = d_proj.enabled ? PRO_DROP : PRO_NONE; a.drop_dy = d_proj; a.drop_x = d_proj; a.partial = w.wgp;
+    a.pro_dy = d_proj.enabled ? PRO_DROP : PRO_NONE; a.drop_dy = d_proj; a.drop_x = d_proj; a.partial = w.wgp + 2 * w.wgp_stride;
     float* dW[3] = {g.wo, nullptr, nullptr}; float* db[3] = {g.bo, nullptr, nullptr};
-    TRY(lin_wgrad_launch(d.math, a, dW, db, C, st));
+    TRY(lin_wgrad_launch(d.math, a, dW, db, C, st, 0, nullptr, 1, &red));
   }
   {
     LinTcArgs a = lin_args(w.dzc, C, s.wp + XfPacked::WO_D, w.d_o, C, n, C, C);         // grad wrt attention output
@@ -445,13 +449,12 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
   }
   if (attention_tc_supported(d.T)) TRY(attention_bwd_tc(s.qkv, s.o, w.d_o, s.lse, w.dqkv, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
   else TRY(attention_bwd(s.qkv, s.o, w.d_o, s.lse, w.dqkv, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
-  TRY(ln64_fwd(zin, p.ln1g, p.ln1b, w.h, n, st));
   {
     LinWgradArgs a{};
-    a.dy = w.dqkv; a.lddy = AQKV; a.Nout = AQKV; a.x = w.h; a.ldx = C; a.Kin = C; a.M = (int)n;
-    a.drop_dy = d_out; a.drop_x = d_out; a.partial = w.wgp;
+    a.dy = w.dqkv; a.lddy = AQKV; a.Nout = AQKV; a.x = s.h1; a.ldx = C; a.Kin = C; a.M = (int)n;
+    a.drop_dy = d_out; a.drop_x = d_out; a.partial = w.wgp + 3 * w.wgp_stride;
     float* dW[3] = {g.wq, g.wk, g.wv}; float* db[3] = {g.bq, g.bk, g.bv};
-    TRY(lin_wgrad_launch(d.math, a, dW, db, C, st));
+    TRY(lin_wgrad_launch(d.math, a, dW, db, C, st, 0, nullptr, 1, &red));
   }
   {
     LinTcArgs a = lin_args(w.dqkv, AQKV, s.wp + XfPacked::QKV_D, w.d_o, C, n, C, AQKV);  // dh1 = dq.Wq + dk.Wk + dv.Wv
@@ -459,12 +462,14 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
   }
 
   TRY(ln64_bwd(w.d_o, zin, p.ln1g, w.dzc, dzin, g.ln1g, g.ln1b, n, st));
+  TRY(lin_wgrad_reduce_flush(red, st));
   return EEGCLIP_OK;
 }
 
 XfSave xf_save(float* save, const SaveLayout& L, int j) {
   float* b = save + L.xf0 + L.xf_stride * j;
-  return XfSave{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, b + L.x_gp, b + L.x_zout, (uint8_t*)(b + L.x_wp)};
+  return XfSave{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, b + L.x_gp, b + L.x_zout, b + L.x_h1, b + L.x_h2,
+                (uint8_t*)(b + L.x_wp)};
 }
 
 }  // namespace
@@ -734,7 +739,7 @@ int eegclip_xfblock_forward(const eegclip_xfblock_desc* d, const float* const* p
   eegclip_tower_desc t = xf_as_tower(d);
   SaveLayout L = save_layout(t);
   float* b = (float*)save;
-  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, b + L.x_gp, zout, (uint8_t*)(b + L.x_wp)};
+  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, b + L.x_gp, zout, b + L.x_h1, b + L.x_h2, (uint8_t*)(b + L.x_wp)};
   Scratch w = scratch_layout(t, (float*)scratch);
   const float* const* tp = params - 2;  // xf_at() skips the two mapping entries
   return xf_block_fwd(t, d->layer, xf_at<XfP>(tp, 0, 0), zin, xs, w, (cudaStream_t)stream);
@@ -748,7 +753,7 @@ int eegclip_xfblock_backward(const eegclip_xfblock_desc* d, const float* const* 
   eegclip_tower_desc t = xf_as_tower(d);
   SaveLayout L = save_layout(t);
   float* b = (float*)save;
-  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, b + L.x_gp, nullptr, (uint8_t*)(b + L.x_wp)};
+  XfSave xs{b + L.x_qkv, b + L.x_o, b + L.x_lse, b + L.x_z1, b + L.x_fpre, b + L.x_gp, nullptr, b + L.x_h1, b + L.x_h2, (uint8_t*)(b + L.x_wp)};
   Scratch w = scratch_layout(t, (float*)scratch);
   if (grad_base && grad_bytes) CUDA_TRY(cudaMemsetAsync(grad_base, 0, grad_bytes, st));
   return xf_block_bwd(t, d->layer, xf_at<XfP>(params - 2, 0, 0), xf_at<XfG>(grads - 2, 0, 0), zin, xs, dzout, dzin, w, st);
