@@ -64,7 +64,7 @@ def test_bilstm_uncovered_shape_raises(cm, lib):
 # ---------------------------------------------------------------------------------------------------------------
 # tensor-core attention vs the exact-fp32 attention kernels of the same library (identical Philox masks)
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("T,B,train,p", [(64, 3, False, 0.5), (192, 2, True, 0.5), (320, 2, True, 0.5), (128, 2, True, 0.3)])
+@pytest.mark.parametrize("T,B,train,p", [(64, 3, False, 0.5), (192, 2, True, 0.5), (320, 2, True, 0.5), (128, 2, True, 0.3), (448, 1, True, 0.5), (512, 1, True, 0.5)])
 def test_attention_tc_vs_fp32(cm, lib, T, B, train, p):
     torch.manual_seed(T + B)
     blk = cm.TransformerEncoderBlock(64, drop_p=p, forward_drop_p=p).to(DEV)
@@ -258,8 +258,8 @@ def test_loss_reader_returns_every_step_in_order(lib):
 
 def test_pdl_off_matches_pdl_on(cm, lib):
     """Programmatic dependent launch only overlaps launch latency: the forward is bit-identical with the attribute off
-    (g_tune[7]); gradients agree to fp32 rounding (the attention backward sums dQ over warps with shared-memory float atomics,
-    so it is not bitwise reproducible run to run with or without PDL)."""
+    (g_tune[7]); gradients agree to fp32 rounding (the attention backward sums dQ over warps with shared-memory float atomics
+    and the LayerNorm affine / bias column sums use global ones, so gradients are not bitwise reproducible run to run)."""
     torch.manual_seed(11)
     model = cm.EEGConformerInterleaved(output_dim=8, time_dimension=192, depth=2).to(DEV).eval()
     x = torch.randn(4, 192, 64, device=DEV)

@@ -197,7 +197,9 @@ __global__ void __launch_bounds__(512, 2) attn_fwd_tc_kernel(const float* __rest
 // Backward.  grid = B*H, block = (T/64) warps; warp w owns keys [64w, 64w+64) and loops over all query tiles of 8.
 //   S^T = K'.Q^T, dP^T = V.dO^T  (rows = keys)   ->   dV += Pd^T.dO, dK += dS^T.Q  (accumulators in registers)
 //   dQ^T = K'^T.dS^T needs dS^T as a B fragment: staged through a per-warp 64 x 8 shared tile, accumulated over the
-//   warps of the CTA in shared memory (red.shared), written once at the end.
+//   warps of the CTA in shared memory (red.shared), written once at the end.  (Measured alternative, round 2: a private
+//   [T][8] dQ slab per warp summed in warp order is bitwise reproducible but needs 105 KB instead of 66 KB of shared memory at
+//   T = 320 -- occupancy 3 -> 2 CTAs per SM -- and ran 2.86 -> 3.49 ms per step; the float atomics stay.)
 // smem: Qs, dOs [T][QS] (TF32), Ls (lse * log2e), Ds (dO.O) [T], dQs [T][8], per-warp staging [64][8], keep bits [T][T/32].
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2) attn_bwd_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ out,
@@ -367,7 +369,7 @@ inline int attention_bwd_tc(const float* qkv, const float* out, const float* dou
   const size_t smem = ((size_t)T * (2 * attntc::QS + 2 + 8) + (size_t)warps * 512) * sizeof(float) + (size_t)T * T / 8;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attntc::attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(attntc::attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024) != cudaSuccess)   // T = 512: 118.8 KB
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
