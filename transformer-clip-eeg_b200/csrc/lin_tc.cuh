@@ -48,7 +48,13 @@ enum : int { PRO_NONE = 0, PRO_DROP = 1, PRO_GELU_DROP = 2 };
 // Compile-time feature masks of the token-GEMM epilogue.  The kernels are instantiated per (prologue, epilogue mask) actually
 // used by the encoder, so each variant carries only its own code: the all-features kernel was > 64 KB of SASS, twice the
 // instruction cache, and every role ran ~4x slower than its instruction count predicts.  Mask -1 = generic (runtime flags).
-enum : int { EF_BIAS = 1, EF_ACT1 = 2, EF_ACT2 = 4, EF_DROP = 8, EF_ACTGRAD = 16, EF_MULSRC = 32, EF_RES = 64 };
+enum : int { EF_BIAS = 1, EF_ACT1 = 2, EF_ACT2 = 4, EF_DROP = 8, EF_ACTGRAD = 16, EF_MULSRC = 32, EF_RES = 64, EF_LNBWD = 128 };
+// EF_LNBWD (N = 64, four epilogue warps): the GEMM result is dh, the gradient w.r.t. a per-token LayerNorm(64) output; the epilogue
+// runs the LayerNorm backward in place of the plain store:  C = residual + LNbwd(dh ; x = lnb_x, gamma = lnb_gamma)  and leaves the
+// CTA's column sums of dh * xhat and dh in lnb_partial (folded by lin_wgrad_reduce).  Replaces a data-gradient launch that wrote dh
+// plus an ln64_bwd launch that read it back with x and the residual (clip_model.py:84,89 backward).
+constexpr int LNB_R = 2;                // rows whose loads are in flight together in that epilogue
+constexpr int LNB_LD = 68;               // floats per staged row of the LayerNorm-backward epilogue (64 + pad, 16 B aligned)
 
 // streaming 128-bit load.  The CTAs here keep > 160 KB of shared memory, which leaves only a few KB of L1: plain
 // (allocating) loads then throttle on free L1 lines long before HBM saturates, so activations bypass L1 allocation.
@@ -249,6 +255,9 @@ struct LinTcArgs {
   int drop_on; Drop drop;         // v *= dropmult(m*N + n)
   const float* act_grad_src;      // v *= GELU'(src[m][n])
   const float* residual;          // v += residual[m][n]
+  const float* lnb_x;             // EF_LNBWD: LayerNorm input rows (M, 64)
+  const float* lnb_gamma;         // EF_LNBWD: LayerNorm weight (64)
+  float* lnb_partial;             // EF_LNBWD: [gridDim.x][130]: sum dh*xhat (64), sum dh (64), 2 pad
   int nstage;                     // ring depth (2..NSTAGE)
   int policy;                     // load policy of the streamed activations (0: L1 no-allocate, 1: __ldg)
   unsigned long long* dbg;        // development timeline buffer (nullptr in production)
@@ -270,7 +279,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
   uint8_t* sA = smem + 2 * WP;
   const int nstage = a.nstage;
   float* sE = reinterpret_cast<float*>(sA + nstage * A_STAGE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + NEPI * EPI_WARP_FLOATS);
+  constexpr bool LNB = EF >= 0 && (EF & EF_LNBWD) != 0;
+  constexpr int EPI_SLOTS = LNB ? 8 : NEPI;       // the LayerNorm-backward epilogue stages 32 x 64 per warp: two slots each
+  static_assert(!LNB || NEPI == 4, "EF_LNBWD runs with four epilogue warps");
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + EPI_SLOTS * EPI_WARP_FLOATS);
   uint64_t* full = bars;                  // [NSTAGE] producers -> MMA   (NPROD*32 arrivals)
   uint64_t* empty = bars + NSTAGE;        // [NSTAGE] MMA -> producers   (tcgen05.commit)
   uint64_t* accfull = bars + 2 * NSTAGE;  // [2] MMA -> epilogue
@@ -406,6 +418,105 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
     }
   } else {
     // ===== epilogue: warp w reads TMEM lane quarter w%4, columns [ (w/4)*N/2, (w/4+1)*N/2 ) =====
+    if constexpr (LNB) {
+      // ---- LayerNorm(64) backward epilogue: warp q owns the 32 rows of TMEM lane quarter q, all 64 columns ----
+      const int q = warp & 3;
+      float* stg = sE + warp * 2 * EPI_WARP_FLOATS;                 // [32][LNB_LD]
+      const int c8 = (lane & 7) * 8, rq = lane >> 3;                // coalesced phase: 8 lanes per row, 4 rows per step
+      float g8[8], ag[8], ab[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { g8[j] = __ldg(a.lnb_gamma + c8 + j); ag[j] = 0.f; ab[j] = 0.f; }
+      uint32_t t = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+        const uint32_t buf = t & 1;
+        tc::mbar_wait(&accfull[buf], (t >> 1) & 1);
+        tc::tc_fence_after();
+        const long mrow0 = (long)tile * BM + q * 32;
+#pragma unroll
+        for (int cb = 0; cb < 64; cb += 32) {
+          float v[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)N + cb, v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stg + lane * LNB_LD + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&accempty[buf]);                            // the accumulator is free as soon as it sits in shared memory
+        __syncwarp();
+        // LNB_R rows in flight per thread: their loads are issued together (one exposed memory latency per pair)
+#pragma unroll 1
+        for (int i0 = 0; i0 < 8; i0 += LNB_R) {
+          float xv[LNB_R][8], rv[LNB_R][8], dh[LNB_R][8];
+          bool ok[LNB_R];
+#pragma unroll
+          for (int u = 0; u < LNB_R; ++u) {
+            const int rl = (i0 + u) * 4 + rq;
+            const long m = mrow0 + rl;
+            ok[u] = m < a.M;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 x0 = ok[u] ? ld_act(reinterpret_cast<const float4*>(a.lnb_x + m * 64 + c8), a.policy) : z4;
+            const float4 x1 = ok[u] ? ld_act(reinterpret_cast<const float4*>(a.lnb_x + m * 64 + c8 + 4), a.policy) : z4;
+            const float4 r0 = (ok[u] && a.residual) ? ld_act(reinterpret_cast<const float4*>(a.residual + m * a.ldc + c8), a.policy) : z4;
+            const float4 r1 = (ok[u] && a.residual) ? ld_act(reinterpret_cast<const float4*>(a.residual + m * a.ldc + c8 + 4), a.policy) : z4;
+            const float4 d0 = *reinterpret_cast<const float4*>(stg + rl * LNB_LD + c8);
+            const float4 d1 = *reinterpret_cast<const float4*>(stg + rl * LNB_LD + c8 + 4);
+            xv[u][0] = x0.x; xv[u][1] = x0.y; xv[u][2] = x0.z; xv[u][3] = x0.w; xv[u][4] = x1.x; xv[u][5] = x1.y; xv[u][6] = x1.z; xv[u][7] = x1.w;
+            rv[u][0] = r0.x; rv[u][1] = r0.y; rv[u][2] = r0.z; rv[u][3] = r0.w; rv[u][4] = r1.x; rv[u][5] = r1.y; rv[u][6] = r1.z; rv[u][7] = r1.w;
+            dh[u][0] = d0.x; dh[u][1] = d0.y; dh[u][2] = d0.z; dh[u][3] = d0.w; dh[u][4] = d1.x; dh[u][5] = d1.y; dh[u][6] = d1.z; dh[u][7] = d1.w;
+          }
+#pragma unroll
+          for (int u = 0; u < LNB_R; ++u) {
+            // row statistics over the 8 lanes that share the row (same arithmetic as ln64_fwd / ln64_bwd)
+            float sx = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sx += xv[u][j];
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o, 8);
+            const float mean = sx * (1.f / 64.f);
+            float qv = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { xv[u][j] -= mean; qv = fmaf(xv[u][j], xv[u][j], qv); }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, o, 8);
+            const float rstd = rsqrtf(qv * (1.f / 64.f) + 1e-5f);
+            float s1 = 0.f, s2 = 0.f, e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              xv[u][j] *= rstd;                                     // xhat
+              e[j] = dh[u][j] * g8[j];
+              s1 += e[j];
+              s2 = fmaf(e[j], xv[u][j], s2);
+              ag[j] = fmaf(dh[u][j], xv[u][j], ag[j]);              // rows beyond M staged zeros: they add nothing
+              ab[j] += dh[u][j];
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+              s1 += __shfl_xor_sync(0xffffffffu, s1, o, 8);
+              s2 += __shfl_xor_sync(0xffffffffu, s2, o, 8);
+            }
+            const float m1 = s1 * (1.f / 64.f), m2 = s2 * (1.f / 64.f);
+            if (ok[u]) {
+              float o8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o8[j] = rv[u][j] + rstd * (e[j] - m1 - xv[u][j] * m2);
+              float* op = a.C + (mrow0 + (i0 + u) * 4 + rq) * a.ldc + c8;
+              *reinterpret_cast<float4*>(op) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+              *reinterpret_cast<float4*>(op + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      // column sums of this warp: fold the four row groups (lanes with equal lane & 7), park them for the CTA-wide fold below
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ag[j] += __shfl_xor_sync(0xffffffffu, ag[j], 8); ag[j] += __shfl_xor_sync(0xffffffffu, ag[j], 16);
+        ab[j] += __shfl_xor_sync(0xffffffffu, ab[j], 8); ab[j] += __shfl_xor_sync(0xffffffffu, ab[j], 16);
+      }
+      if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { stg[c8 + j] = ag[j]; stg[64 + c8 + j] = ab[j]; }
+      }
+    } else {
     const int q = warp & 3, chalf = warp >> 2;
     float* stg = sE + warp * EPI_WARP_FLOATS;
     const int cq = (lane & 7) * 4, rq = lane >> 3;      // coalesced phase: 4 columns x (4 rows per iteration)
@@ -516,10 +627,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
       tc::mbar_arrive(&accempty[buf]);
       dbg_mark(dbg, 2, dn, 22);
     }
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) tc::tmem_dealloc(tmem, ncols);
+  if constexpr (LNB) {
+    // CTA-wide fold of the four epilogue warps' column sums (fixed order) -> this CTA's partial
+    if (tid < 128) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) sum += sE[w * 2 * EPI_WARP_FLOATS + tid];
+      a.lnb_partial[(long)blockIdx.x * 130 + tid] = sum;
+    } else if (tid < 130) {
+      a.lnb_partial[(long)blockIdx.x * 130 + tid] = 0.f;
+    }
+  }
 }
 
 inline bool lin_tc_supported(long M, int N, int K) {
@@ -535,7 +658,8 @@ inline int lin_tc_launch_w(const LinTcArgs& a, int grid, cudaStream_t st) {
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
-  LAUNCH_PDL((lin_tc_kernel<NTERMS, PRO, EF, NEPI>), grid, NTHREADS, lin_smem_bytes(a.N, a.K, a.nstage, NEPI), st, a);
+  constexpr int slots = (EF >= 0 && (EF & EF_LNBWD)) ? 8 : NEPI;
+  LAUNCH_PDL((lin_tc_kernel<NTERMS, PRO, EF, NEPI>), grid, NTHREADS, lin_smem_bytes(a.N, a.K, a.nstage, slots), st, a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -550,10 +674,15 @@ inline int lin_tc_launch_v(const LinTcArgs& a, int grid, uint32_t, cudaStream_t 
   return lin_tc_launch_w<NTERMS, PRO, EF, 8>(a, grid, st);
 }
 
+// CTAs of a token-GEMM launch over M rows (persistent: one per SM at most) -- also the number of EF_LNBWD partials
+inline int lin_tc_grid(long M) {
+  const long ntiles = (M + BM - 1) / BM;
+  return (int)(ntiles < 148 ? ntiles : 148);
+}
+
 template <int NTERMS>
 inline int lin_tc_launch_t(LinTcArgs a, cudaStream_t st) {
-  const int ntiles = (a.M + BM - 1) / BM;
-  const int grid = ntiles < 148 ? ntiles : 148;
+  const int grid = lin_tc_grid(a.M);
   a.nstage = g_tune[0] >= 2 && g_tune[0] <= NSTAGE ? g_tune[0] : 2;
   while (a.nstage > 2 && lin_smem_bytes(a.N, a.K, a.nstage) > 227u * 1024u) --a.nstage;
   a.policy = g_tune[1];
@@ -562,6 +691,12 @@ inline int lin_tc_launch_t(LinTcArgs a, cudaStream_t st) {
   const int mask = (a.bias ? EF_BIAS : 0) | (a.act == 1 ? EF_ACT1 : 0) | (a.act == 2 ? EF_ACT2 : 0) | (a.drop_on ? EF_DROP : 0) |
                    (a.act_grad_src ? EF_ACTGRAD : 0) | (a.mul_src ? EF_MULSRC : 0) | (a.residual ? EF_RES : 0);
   ProfScope prof(PROF_LIN_TC, st);
+  if (a.lnb_x) {          // data gradient + LayerNorm backward in one launch (plain prologue, N = 64)
+    if (a.N != 64 || a.pro != PRO_NONE || !a.lnb_gamma || !a.lnb_partial || a.bias || a.act || a.drop_on || a.act_grad_src || a.mul_src ||
+        lin_smem_bytes(a.N, a.K, a.nstage, 8) > 227u * 1024u)
+      return EEGCLIP_ERR_UNSUPPORTED;
+    return lin_tc_launch_w<NTERMS, PRO_NONE, EF_LNBWD, 4>(a, grid, st);
+  }
   if (g_tune[3] == 0) {   // g_tune[3] != 0 forces the generic kernel (development)
     // the variants the encoder launches: QKV / plain, out-proj + FFN2, FFN1, and the four data gradients
     if (a.pro == PRO_NONE) {
@@ -1110,7 +1245,7 @@ static __global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const Wgra
 }
 // Several reductions in one launch (blockIdx.z = job): the four weight gradients of a transformer block write their partials to
 // separate regions and are folded together at the end of the block's backward (one launch instead of four ~10 us ones).
-constexpr int MAX_REDUCE_JOBS = 4;
+constexpr int MAX_REDUCE_JOBS = 6;
 struct WgradReduceBatch { WgradReduceArgs j[MAX_REDUCE_JOBS]; int kin_blocks[MAX_REDUCE_JOBS]; int n; };
 static __global__ void __launch_bounds__(256) lin_wgrad_reduce_batch_kernel(const WgradReduceBatch b) {
   pdl_sync();

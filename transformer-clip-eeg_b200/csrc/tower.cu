@@ -87,6 +87,7 @@ SaveLayout save_layout(const eegclip_tower_desc& d) {
 struct Scratch {
   float *upad, *dypad, *h, *f, *dfpre, *dqkv, *d_o, *dg, *dza, *dzb, *dzc, *deeg, *wtmp, *wgp;   // wgp: 4 partial regions
   size_t wgp_stride;
+  float* lnp;                       // 2 x [148][130]: per-CTA column sums of the fused LayerNorm-backward epilogues
   void* tc;
   size_t total;
 };
@@ -111,6 +112,7 @@ Scratch scratch_layout(const eegclip_tower_desc& d, float* base) {
   s.wtmp = take((size_t)C * C * d.taps);
   s.wgp_stride = align_up(lintc::lin_wgrad_partial_bytes(256, 64) / sizeof(float), 64);
   s.wgp = take(4 * s.wgp_stride);    // one region per weight gradient of a transformer block (their reductions are batched)
+  s.lnp = take(2 * 148 * 130);
   s.tc = take(align_up(ln_ct_scratch_floats(d.T, C), 64) + conv_tc_scratch_bytes(d.B, d.T, d.taps, C, C) / sizeof(float) + 64);
   s.total = o;
   return s;
@@ -429,11 +431,21 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
     float* dW[3] = {g.w1, nullptr, nullptr}; float* db[3] = {g.b1, nullptr, nullptr};
     TRY(lin_wgrad_launch(d.math, a, dW, db, FF, st, 0, nullptr, 1, &red));
   }
+  // dh2 = dfpre . W1 and the LayerNorm-2 backward in ONE launch: dzc = dz1 = dzout + LNbwd(dh2 ; z1); the affine gradients come out
+  // as per-CTA column sums and join the batched reduction at the end of the block
+  auto ln_reduce_job = [&](float* partial, float* dgamma, float* dbeta) {
+    WgradReduceArgs r{};
+    r.partial = partial; r.ctas = lin_tc_grid(n); r.Nout = 2; r.Kin = 64; r.rows_per_dst = 1; r.ldw = 64; r.log_scale = nullptr;
+    r.dW[0] = dgamma; r.dW[1] = dbeta; r.dW[2] = nullptr; r.dW[3] = nullptr;
+    for (int i = 0; i < 4; ++i) r.db[i] = nullptr;
+    red.j[red.n] = r; red.kin_blocks[red.n] = 1; ++red.n;
+  };
   {
-    LinTcArgs a = lin_args(w.dfpre, FF, s.wp + XfPacked::W1_D, w.d_o, C, n, C, FF);     // d_o reused as dh2
+    LinTcArgs a = lin_args(w.dfpre, FF, s.wp + XfPacked::W1_D, w.dzc, C, n, C, FF);
+    a.lnb_x = s.z1; a.lnb_gamma = p.ln2g; a.lnb_partial = w.lnp; a.residual = dzout;
     TRY(lin_tc_launch(d.math, a, st));
+    ln_reduce_job(w.lnp, g.ln2g, g.ln2b);
   }
-  TRY(ln64_bwd(w.d_o, s.z1, p.ln2g, dzout, w.dzc, g.ln2g, g.ln2b, n, st));              // dzc = dz1
   // ---- attention branch: dp = dz1 * mask_proj (prologue) ----
   {
     LinWgradArgs a{};
@@ -457,11 +469,12 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
     TRY(lin_wgrad_launch(d.math, a, dW, db, C, st, 0, nullptr, 1, &red));
   }
   {
-    LinTcArgs a = lin_args(w.dqkv, AQKV, s.wp + XfPacked::QKV_D, w.d_o, C, n, C, AQKV);  // dh1 = dq.Wq + dk.Wk + dv.Wv
+    // dh1 = dq.Wq + dk.Wk + dv.Wv and the LayerNorm-1 backward: dzin = dz1 + LNbwd(dh1 ; zin)
+    LinTcArgs a = lin_args(w.dqkv, AQKV, s.wp + XfPacked::QKV_D, dzin, C, n, C, AQKV);
+    a.lnb_x = zin; a.lnb_gamma = p.ln1g; a.lnb_partial = w.lnp + 148 * 130; a.residual = w.dzc;
     TRY(lin_tc_launch(d.math, a, st));
+    ln_reduce_job(w.lnp + 148 * 130, g.ln1g, g.ln1b);
   }
-
-  TRY(ln64_bwd(w.d_o, zin, p.ln1g, w.dzc, dzin, g.ln1g, g.ln1b, n, st));
   TRY(lin_wgrad_reduce_flush(red, st));
   return EEGCLIP_OK;
 }
