@@ -343,7 +343,7 @@ int eegclip_infonce_lse(const float* S_all, const float* E_all, const float* tau
     uint8_t* pE = (uint8_t*)(sc + hs.packE);
     TRY(headtc::epack(S_all, pS, Bg, D, st));
     TRY(headtc::epack(E_all, pE, Bg, D, st));
-    const int nt = ceil_div(Bg, headtc::NT);
+    const int nt = 2 * ceil_div(Bg, headtc::NT);           // one (max, sum exp) partial per tile and 128-column half
     headtc::LogitsArgs a{};
     a.Ap = pS; a.Bp = pE; a.a_blk0 = row0 / headtc::RB; a.M = b; a.N = Bg; a.D = D; a.tau = tau;
     a.m_off = row0; a.n_off = 0; a.part = part; a.diag = diag;

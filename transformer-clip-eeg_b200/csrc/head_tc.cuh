@@ -5,7 +5,8 @@
 //                       (128-row block, 64-column chunk):  [plane][c8][row][8]   (tc_common.cuh chunk-major layout)
 //                       so that a GEMM stage is ONE contiguous bulk async copy (TMA engine) per operand block.
 //   logits_tc_kernel    CTA (m block of 128 rows) x (n tile of 256 columns): TMA producer thread + MMA thread (K loop over
-//                       D in 64-column chunks, 2-stage ring) + 4 epilogue warps (one thread per row):
+//                       D in 64-column chunks, 2-stage ring) + 8 epilogue warps (one thread per row and 128-column half;
+//                       with 4 the exp / pack work of MODE 2 was 32 us of latency-bound epilogue per 49 us of MMAs):
 //       MODE 1  per-row (max, sum exp) partial of the tile + the diagonal logit        (forward: row / column LSE)
 //       MODE 2  G = (exp(L - lse_m) + exp(L - lse_n) - 2 delta) / (2B) * upstream, written straight into the packed bf16 hi/lo
 //               A-operand layout of the next GEMM (rows m, contraction index n) + sum G.L for d tau   (backward: CE gradient)
@@ -112,7 +113,7 @@ struct LogitsArgs {
 };
 
 template <int MODE, int NTERMS>
-__global__ void __launch_bounds__(192, 1) logits_tc_kernel(const LogitsArgs a) {
+__global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
   pdl_sync();
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -182,19 +183,20 @@ __global__ void __launch_bounds__(192, 1) logits_tc_kernel(const LogitsArgs a) {
       __syncwarp();
     }
   } else {
-    // ===== epilogue: thread = logit row m =====
-    const int q = warp;
+    // ===== epilogue: thread = logit row m; warps 0-3 take columns [0,128) of the tile, warps 6-9 columns [128,256) =====
+    const int q = warp & 3, chalf = warp >= 6 ? 1 : 0;      // TMEM lane quarter of a warp is warp % 4
     const int m = m0 + q * 32 + lane;
     const bool mv = m < a.M;
     tc::mbar_wait(accfull, 0);
     tc::tc_fence_after();
     const float scale = a.tau ? __expf(*a.tau) : 1.f;
     const int ncols = min(NT, a.N - n0);
+    const int c_lo = chalf * (NT / 2), c_hi = min(ncols, c_lo + NT / 2);   // this warp's columns (empty when c_lo >= ncols)
     const int gm = m + a.m_off;
     if (MODE == 1) {
       const float sc2 = scale * LOG2E;                     // work in base 2
       float mx = -INFINITY, sum = 0.f;
-      for (int cb = 0; cb < ncols; cb += 32) {
+      for (int cb = c_lo; cb < c_hi; cb += 32) {
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb, v);
         float cm = -INFINITY;
@@ -218,9 +220,10 @@ __global__ void __launch_bounds__(192, 1) logits_tc_kernel(const LogitsArgs a) {
         }
       }
       // natural-log convention of the partials: (max, sum exp(L - max))
-      if (mv) a.part[(long)m * gridDim.x + blockIdx.x] = make_float2(mx * (1.0f / LOG2E), sum);
+      // one partial per (tile, column half); an empty half leaves (-inf, 0), which the combine ignores
+      if (mv) a.part[(long)m * (2 * gridDim.x) + 2 * blockIdx.x + chalf] = make_float2(mx * (1.0f / LOG2E), sum);
     } else if (MODE == 3) {
-      for (int cb = 0; cb < ncols; cb += 32) {
+      for (int cb = c_lo; cb < c_hi; cb += 32) {
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb, v);
         if (mv) {
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(192, 1) logits_tc_kernel(const LogitsArgs a) {
       // whole 64-column contraction chunks are written (zeros beyond the last valid column: the consumer reads full chunks)
       const int ccols = min(NT, ((ncols + KC - 1) / KC) * KC);
       uint8_t* grow = a.Gp + (size_t)blockIdx.y * a.nkc_g * BLK + (size_t)(q * 32 + lane) * 16;
-      for (int cb = 0; cb < ccols; cb += 32) {
+      for (int cb = c_lo; cb < min(ccols, c_lo + NT / 2); cb += 32) {
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb, v);
 #pragma unroll
@@ -312,7 +315,7 @@ inline int logits_launch_t(const LogitsArgs& a, cudaStream_t st) {
   }
   dim3 grid((a.N + NT - 1) / NT, (a.M + RB - 1) / RB);
   ProfScope prof(PROF_GEMM_F32, st);
-  LAUNCH_PDL((logits_tc_kernel<MODE, NTERMS>), grid, 192, smem, st, a);
+  LAUNCH_PDL((logits_tc_kernel<MODE, NTERMS>), grid, 320, smem, st, a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
