@@ -112,25 +112,28 @@ struct LogitsArgs {
   long ldo;
 };
 
+// Persistent: CTA c works on tiles c, c + gridDim.x, ... (n tile fastest, so neighbouring CTAs share the A row block in L2); the
+// accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i overlaps the K loop of tile i + 1.
 template <int MODE, int NTERMS>
 __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
   pdl_sync();
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE);
-  uint64_t* full = bars;              // [NSTAGE]
-  uint64_t* empty = bars + NSTAGE;    // [NSTAGE]
-  uint64_t* accfull = bars + 2 * NSTAGE;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
+  uint64_t* full = bars;                  // [NSTAGE]  TMA -> MMA
+  uint64_t* empty = bars + NSTAGE;        // [NSTAGE]  MMA -> TMA   (tcgen05.commit)
+  uint64_t* accfull = bars + 2 * NSTAGE;  // [2]       MMA -> epilogue
+  uint64_t* accempty = accfull + 2;       // [2]       epilogue -> MMA (8 warps x 32 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
   const int nkc = a.D / KC;
-  const int n0 = blockIdx.x * NT, m0 = blockIdx.y * RB;
-  const int nb_blocks = (a.N - n0 > RB) ? 2 : 1;            // valid column blocks of this tile
+  const int ntn = (a.N + NT - 1) / NT, ntm = (a.M + RB - 1) / RB;
+  const int ntiles = ntn * ntm;
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    tc::mbar_init(accfull, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&accfull[i], 1); tc::mbar_init(&accempty[i], 8 * 32); }
     tc::mbar_fence_init();
   }
-  if (warp == 5) tc::tmem_alloc(tmem_slot, 256);
+  if (warp == 5) tc::tmem_alloc(tmem_slot, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -139,57 +142,76 @@ __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
   if (warp == 4) {
     // ===== TMA producer: one bulk copy per operand block =====
     if (lane == 0) {
-      const uint32_t bytes = (uint32_t)(1 + nb_blocks) * (NTERMS > 1 ? BLK : PLANE);
-      const uint8_t* ab = a.Ap + (size_t)(a.a_blk0 + blockIdx.y) * nkc * BLK;
-      const uint8_t* bb0 = a.Bp + (size_t)(blockIdx.x * 2) * nkc * BLK;
-      for (int kc = 0; kc < nkc; ++kc) {
-        const int s = kc % NSTAGE;
-        tc::mbar_wait(&empty[s], ((kc / NSTAGE) & 1) ^ 1);
-        tc::mbar_expect_tx(&full[s], bytes);
-        uint8_t* st = smem + s * STAGE;
+      uint32_t c = 0;                      // chunk counter across tiles: ring slot and phase
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tn = tile % ntn, tm = tile / ntn;
+        const int nb_blocks = (a.N - tn * NT > RB) ? 2 : 1;            // valid column blocks of this tile
         const uint32_t one = NTERMS > 1 ? BLK : PLANE;
-        tc::bulk_g2s(st, ab + (size_t)kc * BLK, one, &full[s]);
-        for (int j = 0; j < nb_blocks; ++j) tc::bulk_g2s(st + (1 + j) * BLK, bb0 + ((size_t)j * nkc + kc) * BLK, one, &full[s]);
+        const uint32_t bytes = (uint32_t)(1 + nb_blocks) * one;
+        const uint8_t* ab = a.Ap + (size_t)(a.a_blk0 + tm) * nkc * BLK;
+        const uint8_t* bb0 = a.Bp + (size_t)(tn * 2) * nkc * BLK;
+        for (int kc = 0; kc < nkc; ++kc, ++c) {
+          const int s = c % NSTAGE;
+          tc::mbar_wait(&empty[s], ((c / NSTAGE) & 1) ^ 1);
+          tc::mbar_expect_tx(&full[s], bytes);
+          uint8_t* st = smem + s * STAGE;
+          tc::bulk_g2s(st, ab + (size_t)kc * BLK, one, &full[s]);
+          for (int j = 0; j < nb_blocks; ++j) tc::bulk_g2s(st + (1 + j) * BLK, bb0 + ((size_t)j * nkc + kc) * BLK, one, &full[s]);
+        }
       }
     }
   } else if (warp == 5) {
     // ===== MMA issue (whole warp runs the loop, one elected lane issues) =====
     const uint32_t base = tc::smem_u32(smem);
     const uint32_t idesc = tc::idesc_bf16(128, 128, 0, 0);
-    for (int kc = 0; kc < nkc; ++kc) {
-      const int s = kc % NSTAGE;
-      tc::mbar_wait(&full[s], (kc / NSTAGE) & 1);
+    uint32_t c = 0, t = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+      const int tn = tile % ntn;
+      const int nb_blocks = (a.N - tn * NT > RB) ? 2 : 1;
+      const uint32_t buf = t & 1;
+      tc::mbar_wait(&accempty[buf], ((t >> 1) & 1) ^ 1);
       tc::tc_fence_after();
-      const uint32_t st = base + s * STAGE;
-      const uint64_t a_hi = tc::smem_desc(st, RB * 16, 128), a_lo = tc::smem_desc(st + PLANE, RB * 16, 128);
-      if (tc::elect_one()) {
-        for (int j = 0; j < nb_blocks; ++j) {
-          const uint32_t bs = st + (1 + j) * BLK;
-          const uint64_t b_hi = tc::smem_desc(bs, RB * 16, 128), b_lo = tc::smem_desc(bs + PLANE, RB * 16, 128);
-          const uint32_t d = tmem + j * 128;
+      for (int kc = 0; kc < nkc; ++kc, ++c) {
+        const int s = c % NSTAGE;
+        tc::mbar_wait(&full[s], (c / NSTAGE) & 1);
+        tc::tc_fence_after();
+        const uint32_t st = base + s * STAGE;
+        const uint64_t a_hi = tc::smem_desc(st, RB * 16, 128), a_lo = tc::smem_desc(st + PLANE, RB * 16, 128);
+        if (tc::elect_one()) {
+          for (int j = 0; j < nb_blocks; ++j) {
+            const uint32_t bs = st + (1 + j) * BLK;
+            const uint64_t b_hi = tc::smem_desc(bs, RB * 16, 128), b_lo = tc::smem_desc(bs + PLANE, RB * 16, 128);
+            const uint32_t d = tmem + buf * 256 + j * 128;
 #pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks) {
-            const uint64_t dk = (uint64_t)((2 * ks * RB * 16) >> 4);
-            tc::mma_bf16(d, a_hi + dk, b_hi + dk, idesc, (kc | ks) != 0);
-            if (NTERMS > 1) {
-              tc::mma_bf16(d, a_hi + dk, b_lo + dk, idesc, 1);
-              tc::mma_bf16(d, a_lo + dk, b_hi + dk, idesc, 1);
+            for (int ks = 0; ks < KC / 16; ++ks) {
+              const uint64_t dk = (uint64_t)((2 * ks * RB * 16) >> 4);
+              tc::mma_bf16(d, a_hi + dk, b_hi + dk, idesc, (kc | ks) != 0);
+              if (NTERMS > 1) {
+                tc::mma_bf16(d, a_hi + dk, b_lo + dk, idesc, 1);
+                tc::mma_bf16(d, a_lo + dk, b_hi + dk, idesc, 1);
+              }
             }
           }
+          tc::tc_commit(&empty[s]);
+          if (kc == nkc - 1) tc::tc_commit(&accfull[buf]);
         }
-        tc::tc_commit(&empty[s]);
-        if (kc == nkc - 1) tc::tc_commit(accfull);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ===== epilogue: thread = logit row m; warps 0-3 take columns [0,128) of the tile, warps 6-9 columns [128,256) =====
     const int q = warp & 3, chalf = warp >= 6 ? 1 : 0;      // TMEM lane quarter of a warp is warp % 4
+    const float scale = a.tau ? __expf(*a.tau) : 1.f;
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+    const int tn = tile % ntn, tm = tile / ntn;
+    const int n0 = tn * NT, m0 = tm * RB;
+    const uint32_t buf = t & 1;
+    const uint32_t tacc = tmem + buf * 256 + ((uint32_t)(q * 32) << 16);
     const int m = m0 + q * 32 + lane;
     const bool mv = m < a.M;
-    tc::mbar_wait(accfull, 0);
+    tc::mbar_wait(&accfull[buf], (t >> 1) & 1);
     tc::tc_fence_after();
-    const float scale = a.tau ? __expf(*a.tau) : 1.f;
     const int ncols = min(NT, a.N - n0);
     const int c_lo = chalf * (NT / 2), c_hi = min(ncols, c_lo + NT / 2);   // this warp's columns (empty when c_lo >= ncols)
     const int gm = m + a.m_off;
@@ -198,7 +220,7 @@ __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
       float mx = -INFINITY, sum = 0.f;
       for (int cb = c_lo; cb < c_hi; cb += 32) {
         float v[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb, v);
+        tc::tmem_ld32(tacc + cb, v);
         float cm = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -221,11 +243,11 @@ __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
       }
       // natural-log convention of the partials: (max, sum exp(L - max))
       // one partial per (tile, column half); an empty half leaves (-inf, 0), which the combine ignores
-      if (mv) a.part[(long)m * (2 * gridDim.x) + 2 * blockIdx.x + chalf] = make_float2(mx * (1.0f / LOG2E), sum);
+      if (mv) a.part[(long)m * (2 * ntn) + 2 * tn + chalf] = make_float2(mx * (1.0f / LOG2E), sum);
     } else if (MODE == 3) {
       for (int cb = c_lo; cb < c_hi; cb += 32) {
         float v[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb, v);
+        tc::tmem_ld32(tacc + cb, v);
         if (mv) {
           float* o = a.out + (long)m * a.ldo + n0 + cb;
           if (cb + 32 <= ncols && (a.ldo & 3) == 0) {
@@ -248,10 +270,10 @@ __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
       float tsum = 0.f;
       // whole 64-column contraction chunks are written (zeros beyond the last valid column: the consumer reads full chunks)
       const int ccols = min(NT, ((ncols + KC - 1) / KC) * KC);
-      uint8_t* grow = a.Gp + (size_t)blockIdx.y * a.nkc_g * BLK + (size_t)(q * 32 + lane) * 16;
+      uint8_t* grow = a.Gp + (size_t)tm * a.nkc_g * BLK + (size_t)(q * 32 + lane) * 16;
       for (int cb = c_lo; cb < min(ccols, c_lo + NT / 2); cb += 32) {
         float v[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb, v);
+        tc::tmem_ld32(tacc + cb, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = n0 + cb + j;
@@ -279,10 +301,13 @@ __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
         if (lane == 0) atomicAdd(a.dtau, tsum);
       }
     }
+    tc::tc_fence_before();
+    tc::mbar_arrive(&accempty[buf]);        // every epilogue thread: this buffer's columns have been read
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 5) tc::tmem_dealloc(tmem, 256);
+  if (warp == 5) tc::tmem_dealloc(tmem, 512);
 }
 
 inline bool head_tc_supported(int b, int Bg, int D) {
@@ -313,7 +338,8 @@ inline int logits_launch_t(const LogitsArgs& a, cudaStream_t st) {
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
-  dim3 grid((a.N + NT - 1) / NT, (a.M + RB - 1) / RB);
+  const int ntiles = ((a.N + NT - 1) / NT) * ((a.M + RB - 1) / RB);
+  const int grid = ntiles < 148 ? ntiles : 148;           // persistent: one CTA per SM at most
   ProfScope prof(PROF_GEMM_F32, st);
   LAUNCH_PDL((logits_tc_kernel<MODE, NTERMS>), grid, 320, smem, st, a);
   LAUNCH_CHECK();
