@@ -339,6 +339,8 @@ for (k, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
     assert rel_err(p.grad, q.grad, floor=1e-3 * gn) < 2e-4, (k, rel_err(p.grad, q.grad, floor=1e-3 * gn))
     num += float((p.grad - q.grad).norm()) ** 2
 assert num ** 0.5 / gn < 2e-4
+# the memory bank: identical on every rank and equal to the single-rank bank at the global batch
+assert rel_err(model.eegMemoryBank.memory, ref.eegMemoryBank.memory) < 1e-6
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")

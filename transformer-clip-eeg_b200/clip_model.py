@@ -23,7 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib as L
-from .parallel import infonce_loss, ce_rows_loss, l2_normalize
+from .parallel import _all_gather_rows, _world, infonce_loss, ce_rows_loss, l2_normalize
 
 __all__ = [
     "MultiHeadAttention", "ResidualAdd", "FeedForwardBlock", "TransformerEncoderBlock", "TransformerEncoder",
@@ -724,8 +724,19 @@ class CLIPSimNoLatentProj(nn.Module):
         if ef.shape[1] > ef.shape[2]:
             ef = ef.transpose(1, 2)
         E_raw, S_raw = torch.flatten(ef, start_dim=1), torch.flatten(sf, start_dim=1)
-        loss_ce, En = infonce_loss(E_raw, S_raw, self.temperature, group=self.shard_group, return_normalized=True)
-        avg = self.eegMemoryBank(ids, En.detach())
+        loss_ce, En, E_all = infonce_loss(E_raw, S_raw, self.temperature, group=self.shard_group, return_normalized="all")
+        world, rank = _world(self.shard_group)
+        if world > 1:
+            # data-parallel: every rank applies the SAME bank update (ids of all ranks, gathered embeddings), so the banks stay
+            # identical across ranks and equal to a single process at the global batch; this rank keeps its rows of the old values
+            if self.lambda_average != 0:
+                raise L.EegclipError("CLIPSimNoLatentProj: the memory-bank loss term (lambda_average != 0) is not sharded; train it "
+                                     "on one rank or with lambda_sim_loss = 0 (the reference default)")
+            ids_all = _all_gather_rows(ids.view(-1).to(torch.int64).contiguous(), self.shard_group, world)
+            b = En.shape[0]
+            avg = self.eegMemoryBank(ids_all, E_all.detach())[rank * b:(rank + 1) * b]
+        else:
+            avg = self.eegMemoryBank(ids, En.detach())
         if self.lambda_average == 0:
             with torch.no_grad():
                 avg_val = ce_rows_loss(avg, En.detach(), self.temperature_eeg.detach())

@@ -108,11 +108,12 @@ class _InfoNCEFn(torch.autograd.Function):
         loss = ops.loss(vec_all, False)
         ctx.saved = (En, invE, Sn, invS, E_all, S_all, tau_c, vec_all)
         ctx.meta = (b, rank * b, ops, tau.shape)
-        ctx.mark_non_differentiable(En)
-        return loss, En
+        E_all_out = E_all if world > 1 else En.detach()     # (a distinct tensor object: one output per object)
+        ctx.mark_non_differentiable(En, E_all_out)
+        return loss, En, E_all_out
 
     @staticmethod
-    def backward(ctx, dloss, _dEn):
+    def backward(ctx, dloss, _dEn, _dEall):
         En, invE, Sn, invS, E_all, S_all, tau_c, vec_all = ctx.saved
         b, row0, ops, tau_shape = ctx.meta
         dl = dloss.detach().to(En.dtype).reshape(1).contiguous()
@@ -169,12 +170,15 @@ def infonce_loss(E_raw, S_raw, tau, group=None, return_normalized=False, ops=Non
     """Symmetric InfoNCE of clip_model.py:675-693 on raw (un-normalised) flattened embeddings (b,D).
 
     With ``group`` set and torch.distributed initialised the batch is the concatenation over ranks.
-    Returns the loss (0-dim) and, if asked, this rank's normalised EEG embeddings (detached).
+    Returns the loss (0-dim) and, if asked, this rank's normalised EEG embeddings (detached); ``return_normalized="all"`` adds the
+    gathered normalised EEG embeddings of all ranks (what a sharded memory-bank update needs).
     """
     ops = ops or _CUDA_OPS
     if ops is _CUDA_OPS and not E_raw.is_cuda:
         raise L.EegclipError("infonce_loss: embeddings must be CUDA tensors (no CPU fallback on this path)")
-    loss, En = _InfoNCEFn.apply(E_raw, S_raw, tau, group, ops)
+    loss, En, E_all = _InfoNCEFn.apply(E_raw, S_raw, tau, group, ops)
+    if return_normalized == "all":     # (loss, this rank's normalised EEG rows, the gathered normalised EEG rows of every rank)
+        return loss, En, E_all
     return (loss, En) if return_normalized else loss
 
 

@@ -216,6 +216,7 @@ class DevicePrefetcher:
         self._dev = [None, None]
         self._wide = [None, None]
         self._free = [None, None]      # main-stream event after which device buffer `slot` may be overwritten
+        self._copied = [None, None]    # copy-stream event after which pinned staging buffer `slot` may be rewritten by the host
 
     def _stage(self, slot, data):
         eeg, speech, ids = data[0], data[1][0] if isinstance(data[1], (list, tuple)) else data[1], data[2]
@@ -227,6 +228,9 @@ class DevicePrefetcher:
             pin = self._pinned[slot]
             if pin is None or any(p.shape != t.shape for p, t in zip(pin, src)):
                 pin = self._pinned[slot] = tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in src)
+            if self._copied[slot] is not None:
+                self._copied[slot].synchronize()       # the previous H2D copy OUT of this pinned buffer has finished (host-side wait:
+                                                       # stream events order the device, not the host's next write into the buffer)
             for p_, t in zip(pin, src):
                 p_.copy_(t)
         dev = self._dev[slot]
@@ -244,6 +248,7 @@ class DevicePrefetcher:
                 out = (dev[0], self._wide[slot], dev[2])
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        self._copied[slot] = ev
         return out, ev
 
     def __iter__(self):
