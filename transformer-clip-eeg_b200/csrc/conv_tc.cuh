@@ -484,8 +484,13 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 // Interface used by tower.cu
 // ------------------------------------------------------------------------------------------------
 inline bool conv_tc_supported(int Cin, int Cout, int taps, int T) {
-  return Cin >= 64 && Cout >= 64 && (Cin % 64) == 0 && (Cout % 64) == 0 && Cin <= 512 && Cout <= 512 && taps >= 16 &&
+  return Cin >= 64 && Cout >= 64 && (Cin % 64) == 0 && (Cout % 64) == 0 && Cin <= 1024 && Cout <= 512 && taps >= 16 &&
          taps <= convtc::MAX_TAPS && (taps % 16) == 0 && T >= 64 && (T % 64) == 0 && T <= 512;
+}
+// narrow outputs (SpeechSmallConv: 1024 -> 8 channels, clip_model.py:204-232) run on the same kernels with the output channels
+// zero-padded to one 64-channel block (tower.cu::conv_block_fwd / _bwd)
+inline bool conv_tc_padded_ok(int Cin, int Cout, int taps, int T) {
+  return Cout < 64 && (Cout % 4) == 0 && conv_tc_supported(Cin, 64, taps, T);
 }
 
 // weight-gradient sample groups: (tap groups x channel blocks) x groups CTAs ~ one wave of 148 SMs

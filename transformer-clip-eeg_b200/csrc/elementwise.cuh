@@ -41,6 +41,42 @@ inline int pad_add(const float* x1, const float* x2, float* out, int B, int T, i
   return EEGCLIP_OK;
 }
 
+// narrow-output convs on the 64-channel tensor-core kernels: channel padding of the output gradient and compaction (+ dropout,
+// indexed in the compact (rows, Cs) layout like every other path) of the padded conv output
+__global__ void pad_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, long rows, int Cs, int Cd) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // one float4 of dst
+  const int d4 = Cd >> 2;
+  if (i >= rows * d4) return;
+  const long r = i / d4;
+  const int c = (int)(i - r * d4) * 4;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < Cs) v = *reinterpret_cast<const float4*>(src + r * Cs + c);
+  reinterpret_cast<float4*>(dst)[i] = v;
+}
+inline int pad_channels(const float* src, float* dst, long rows, int Cs, int Cd, cudaStream_t st) {
+  const long n4 = rows * (Cd >> 2);
+  pad_channels_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(src, dst, rows, Cs, Cd);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+__global__ void compact_channels_drop_kernel(const float* __restrict__ src, float* __restrict__ dst, long rows, int Cs, int Cd, Drop d) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // one float4 of dst
+  const int d4 = Cd >> 2;
+  if (i >= rows * d4) return;
+  const long r = i / d4;
+  const int c = (int)(i - r * d4) * 4;
+  float4 v = *reinterpret_cast<const float4*>(src + r * Cs + c);
+  const float4 m = drop_mult4(d, (uint64_t)i * 4);
+  v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+  reinterpret_cast<float4*>(dst)[i] = v;
+}
+inline int compact_channels_drop(const float* src, float* dst, long rows, int Cs, int Cd, const Drop& d, cudaStream_t st) {
+  const long n4 = rows * (Cd >> 2);
+  compact_channels_drop_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(src, dst, rows, Cs, Cd, d);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
 // out = a + b (b optional), float4
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long n4) {
   pdl_sync();

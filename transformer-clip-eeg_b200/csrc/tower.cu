@@ -217,14 +217,40 @@ int conv_wgrad_f32(const float* dypad, int PLb, const float* upad, float* tmp, i
 // -------------------------------------------------------------------------------------------------
 // BasicBlock forward on time-major data.  xin (+ skip_in) -> conv -> dropout -> LN([C,T]) -> act (+ skip_out)
 // -------------------------------------------------------------------------------------------------
+// scratch of the padded narrow-output path (floats): padded weights | padded bias | padded conv output / output gradient |
+// padded weight gradient, then the tensor-core conv scratch for Cout = 64
+struct PadScr { float *w, *b, *y, *dw; void* tcs; };
+size_t pad_scr_floats(int B, int T, int Cin, int taps) {
+  const size_t TP = T + taps - 1;
+  return 2 * align_up((size_t)64 * Cin * taps, 64) + 64 + align_up((size_t)B * TP * 64, 64) +
+         conv_tc_scratch_bytes(B, T, taps, Cin, 64) / sizeof(float) + 64;
+}
+PadScr pad_scr(float* base, int B, int T, int Cin, int taps) {
+  const size_t TP = T + taps - 1;
+  PadScr s;
+  s.w = base; s.b = s.w + align_up((size_t)64 * Cin * taps, 64); s.y = s.b + 64; s.dw = s.y + align_up((size_t)B * TP * 64, 64);
+  s.tcs = s.dw + align_up((size_t)64 * Cin * taps, 64);
+  return s;
+}
+
 int conv_block_fwd(int math, const float* xin, const float* skip_in, const ConvP& p, const float* skip_out, float* y, float* stats,
                    float* out, float* upad, void* tcs, int B, int T, int Cin, int Cout, int taps, int act, const Drop& drop,
-                   cudaStream_t st) {
+                   cudaStream_t st, float* padscr = nullptr) {
   const int PL = (taps - 1) / 2;
   float* lnscr = (float*)tcs;                      // scratch layout: [LN transposed affine + partials][conv tensor-core scratch]
   tcs = lnscr + align_up(ln_ct_scratch_floats(T, Cout), 64);
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
     TRY(conv_tc_forward(math, xin, skip_in, p.w, p.b, y, B, T, Cin, Cout, taps, PL, drop, tcs, st));
+  } else if (math != EEGCLIP_MATH_FP32 && padscr && conv_tc_padded_ok(Cin, Cout, taps, T)) {
+    // narrow output (SpeechSmallConv): weights / bias zero-padded to 64 output channels, conv on the tensor-core kernel without
+    // dropout, then compaction to Cout channels with the dropout mask indexed in the compact layout
+    PadScr ps = pad_scr(padscr, B, T, Cin, taps);
+    const size_t wrow = (size_t)Cin * taps;
+    CUDA_TRY(cudaMemsetAsync(ps.w, 0, (64 * wrow + 64 + 64) * sizeof(float), st));      // (w, and b right behind it)
+    CUDA_TRY(cudaMemcpyAsync(ps.w, p.w, (size_t)Cout * wrow * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (p.b) CUDA_TRY(cudaMemcpyAsync(ps.b, p.b, (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TRY(conv_tc_forward(math, xin, skip_in, ps.w, ps.b, ps.y, B, T, Cin, 64, taps, PL, make_drop(0, 0, 0, 0.f, 0), ps.tcs, st));
+    TRY(compact_channels_drop(ps.y, y, (long)B * T, 64, Cout, drop, st));
   } else {
     TRY(pad_add(xin, skip_in, upad, B, T, Cin, PL, taps, st));
     TRY(conv_fwd_f32(upad, p.w, p.b, y, B, T, Cin, Cout, taps, drop, st));
@@ -237,7 +263,7 @@ int conv_block_fwd(int math, const float* xin, const float* skip_in, const ConvP
 // Produces du (gradient w.r.t. xin + skip_in) and fills the four parameter gradients (pre-zeroed).
 int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP& p, const ConvG& gr, const float* y,
                    const float* stats, const float* dout, float* du, float* upad, float* dypad, float* wtmp, void* tcs, int B, int T,
-                   int Cin, int Cout, int taps, int act, const Drop& drop, cudaStream_t st) {
+                   int Cin, int Cout, int taps, int act, const Drop& drop, cudaStream_t st, float* padscr = nullptr) {
   const int PL = (taps - 1) / 2, PLb = taps - 1 - PL, TP = T + taps - 1;
   float* lnscr = (float*)tcs;
   tcs = lnscr + align_up(ln_ct_scratch_floats(T, Cout), 64);
@@ -247,6 +273,14 @@ int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP
   TRY(colsum(dypad, gr.b, (long)B * TP, Cout, Cout, st));
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
     TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, Cin, Cout, taps, PLb, du, gr.w, B, T, tcs, st));
+  } else if (math != EEGCLIP_MATH_FP32 && padscr && conv_tc_padded_ok(Cin, Cout, taps, T)) {
+    PadScr ps = pad_scr(padscr, B, T, Cin, taps);
+    const size_t wrow = (size_t)Cin * taps;
+    CUDA_TRY(cudaMemsetAsync(ps.w, 0, 64 * wrow * sizeof(float), st));
+    CUDA_TRY(cudaMemcpyAsync(ps.w, p.w, (size_t)Cout * wrow * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TRY(pad_channels(dypad, ps.y, (long)B * TP, Cout, 64, st));                  // output gradient, channels zero-padded to 64
+    TRY(conv_tc_backward(math, xin, skip_in, ps.w, ps.y, Cin, 64, taps, PLb, du, ps.dw, B, T, ps.tcs, st));
+    CUDA_TRY(cudaMemcpyAsync(gr.w, ps.dw, (size_t)Cout * wrow * sizeof(float), cudaMemcpyDeviceToDevice, st));
   } else {
     TRY(pad_add(xin, skip_in, upad, B, T, Cin, PL, taps, st));
     CUDA_TRY(cudaMemsetAsync(wtmp, 0, (size_t)Cout * Cin * taps * sizeof(float), st));
@@ -633,8 +667,19 @@ int eegclip_convblock_workspace(const eegclip_convblock_desc* d, size_t* save_by
   if (scratch_bytes)
     *scratch_bytes = (align_up((size_t)d->B * TP * d->Cin, 64) + align_up((size_t)d->B * TP * d->Cout, 64) +
                       align_up((size_t)d->Cout * d->Cin * d->taps, 64)) * sizeof(float) + conv_tc_scratch_bytes(d->B, d->T, d->taps, d->Cin, d->Cout) +
-                      align_up(ln_ct_scratch_floats(d->T, d->Cout), 64) * sizeof(float) + 256;
+                      align_up(ln_ct_scratch_floats(d->T, d->Cout), 64) * sizeof(float) + 256 +
+                      (conv_tc_padded_ok(d->Cin, d->Cout, d->taps, d->T) ? pad_scr_floats(d->B, d->T, d->Cin, d->taps) * sizeof(float) + 256 : 0);
   return EEGCLIP_OK;
+}
+// start of the padded-path scratch inside a convblock scratch buffer (nullptr when the shape does not use it)
+static float* convblock_padscr(const eegclip_convblock_desc* d, void* scratch) {
+  if (!conv_tc_padded_ok(d->Cin, d->Cout, d->taps, d->T)) return nullptr;
+  const size_t TP = d->T + d->taps - 1;
+  const size_t front = (align_up((size_t)d->B * TP * d->Cin, 64) + align_up((size_t)d->B * TP * d->Cout, 64) +
+                        align_up((size_t)d->Cout * d->Cin * d->taps, 64)) * sizeof(float) +
+                       conv_tc_scratch_bytes(d->B, d->T, d->taps, d->Cin, d->Cout) +
+                       align_up(ln_ct_scratch_floats(d->T, d->Cout), 64) * sizeof(float) + 256;
+  return (float*)((char*)scratch + align_up(front, 256));
 }
 
 int eegclip_convblock_forward(const eegclip_convblock_desc* d, const float* x, const float* skip_in, const float* w,
@@ -651,7 +696,7 @@ int eegclip_convblock_forward(const eegclip_convblock_desc* d, const float* x, c
               align_up((size_t)d->Cout * d->Cin * d->taps, 64);
   ConvP p{w, bias, gamma, beta};
   return conv_block_fwd(d->math, x, skip_in, p, nullptr, y, stats, out, upad, tcs, d->B, d->T, d->Cin, d->Cout, d->taps, d->act,
-                        make_drop(d->seed, d->layer, SITE_CONV, d->p_drop, d->train), (cudaStream_t)stream);
+                        make_drop(d->seed, d->layer, SITE_CONV, d->p_drop, d->train), (cudaStream_t)stream, convblock_padscr(d, scratch));
 }
 
 int eegclip_convblock_backward(const eegclip_convblock_desc* d, const float* x, const float* skip_in, const float* w,
@@ -673,7 +718,7 @@ int eegclip_convblock_backward(const eegclip_convblock_desc* d, const float* x, 
   ConvP p{w, nullptr, gamma, beta};
   ConvG g{dw, dbias, dgamma, dbeta};
   return conv_block_bwd(d->math, x, skip_in, p, g, y, stats, dout, dx, upad, dypad, wtmp, tcs, d->B, d->T, d->Cin, d->Cout, d->taps, d->act,
-                        make_drop(d->seed, d->layer, SITE_CONV, d->p_drop, d->train), st);
+                        make_drop(d->seed, d->layer, SITE_CONV, d->p_drop, d->train), st, convblock_padscr(d, scratch));
 }
 
 int eegclip_linear_workspace(int64_t M, int32_t N, int32_t K, size_t* scratch_bytes) {
