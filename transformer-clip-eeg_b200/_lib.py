@@ -230,3 +230,12 @@ def claim_grad_sinks(ps):
         arena["written"].add(p_.data_ptr())
         owner.grad = v
     return [v for _, v, _ in found]
+
+
+# listeners told that a backward of this package has just written a set of gradient sinks (data-parallel bucketed all-reduce)
+_SINK_LISTENERS = []
+
+
+def fire_sinks_written(views):
+    for fn in list(_SINK_LISTENERS):
+        fn(views)

@@ -84,6 +84,7 @@ class _TowerFn(torch.autograd.Function):
                flat.numel() * 4 if flat is not None else 0, L.ptr(x), L.ptr(dout), L.ptr(dx), L.ptr(ctx.save), L.ptr(scratch), L.stream())
         ctx.save = None
         if sinks is not None:
+            L.fire_sinks_written(sinks)     # data-parallel: this tower's slice of the gradient arena can be all-reduced from here on
             return (dx, None, *([None] * len(ps)))
         return (dx, None, *views)
 
@@ -718,7 +719,10 @@ class CLIPSimNoLatentProj(nn.Module):
         self.shard_group = None
 
     def forward(self, eeg, speech, ids):
-        ef, sf = self.eegModel(eeg), self.speechModel(speech)
+        # the speech tower runs first so that autograd runs the (three times longer) EEG tower backward first: under data
+        # parallelism its 14.5 MB of gradients are all-reduced while the speech tower's backward is still running
+        sf = self.speechModel(speech)
+        ef = self.eegModel(eeg)
         if sf.shape[1] > sf.shape[2]:
             sf = sf.transpose(1, 2)
         if ef.shape[1] > ef.shape[2]:

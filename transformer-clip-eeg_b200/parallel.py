@@ -198,6 +198,58 @@ def broadcast_parameters(module, group=None, src=0):
         dist.broadcast(t.data, src=src, group=group)
 
 
+class BucketedGradReducer:
+    """SUM-all-reduce of the optimizer's flat gradient arena in two buckets: the slice a tower backward has just finished writing is
+    reduced asynchronously (NCCL stream) while the rest of the backward runs, the remainder after the backward.  Falls back to one
+    collective over the whole arena whenever the written views do not form one exact contiguous slice."""
+
+    def __init__(self, optimizer, group):
+        self.opt, self.group = optimizer, group
+        self.pending = []          # (flat index, lo, hi, work)
+
+    def __enter__(self):
+        L._SINK_LISTENERS.append(self._on_sinks)
+        return self
+
+    def __exit__(self, *exc):
+        L._SINK_LISTENERS.remove(self._on_sinks)
+        return False
+
+    def _on_sinks(self, views):
+        if not views or self.pending:
+            return
+        for fi, a in self.opt._arena.items():
+            flat = a["flat_g"]
+            base, esz = flat.data_ptr(), flat.element_size()
+            los = [(v.data_ptr() - base) // esz for v in views]
+            if min(los) < 0 or max(los) >= flat.numel():
+                continue
+            lo = min(los)
+            hi = max(o + (v.numel() + 3) // 4 * 4 for o, v in zip(los, views))
+            if hi > flat.numel() or sum((v.numel() + 3) // 4 * 4 for v in views) != hi - lo:
+                return                                     # not one exact slice: leave it to the final collective
+            work = dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self.pending.append((fi, lo, hi, work))
+            return
+
+    def finish(self):
+        """After backward: reduce what has not been reduced yet, then make the compute stream wait for the early bucket."""
+        flats = self.opt.flat_grads()                      # (folds autograd-produced gradients into the arena first)
+        done = {fi: (lo, hi) for fi, lo, hi, _ in self.pending}
+        for fi, flat in enumerate(flats):
+            if fi in done:
+                lo, hi = done[fi]
+                if lo > 0:
+                    dist.all_reduce(flat[:lo], op=dist.ReduceOp.SUM, group=self.group)
+                if hi < flat.numel():
+                    dist.all_reduce(flat[hi:], op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        for _, _, _, work in self.pending:
+            work.wait()
+        self.pending = []
+
+
 def allreduce_gradients(params, group=None, flat=None):
     """SUM-all-reduce the gradients (one collective when ``flat`` -- the optimizer's flat gradient arena -- is given)."""
     if not (dist.is_available() and dist.is_initialized()):

@@ -25,7 +25,7 @@ from . import _lib as L
 from .clip_model import (CLIPKLDNoLatentProj, CLIPNoContrastiveLearning, CLIPSim, CLIPSimMultiplePositives, CLIPSimNoLatentProj,
                          EEGConformer, EEGConformerInterleaved, EEGConvLSTM, SpeechSmallConv, memoryBank)
 from .optim import Adam, AdamW
-from .parallel import allreduce_gradients, bind_to_gpu_numa_node, broadcast_parameters
+from .parallel import BucketedGradReducer, allreduce_gradients, bind_to_gpu_numa_node, broadcast_parameters
 from .vlaai import VLAAI
 
 # flag table: (name, type, default, choices) -- train_clip_final.py:163-216
@@ -169,11 +169,15 @@ def train_step(model, optimizer, eeg, speech, ids, use_total=True, group=None):
     else:
         loss_ce, loss_avg, loss_total = out
     optimizer.zero_grad()
-    (loss_total if use_total else loss_ce).backward()
-    if group is not None:
-        flats = optimizer.flat_grads() if hasattr(optimizer, "flat_grads") else [None]
-        for f in flats:
-            allreduce_gradients(model.parameters(), group, flat=f)
+    if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1 and hasattr(optimizer, "flat_grads"):
+        # bucketed: the EEG tower's gradients go out while the speech tower's backward runs, the rest after the backward
+        with BucketedGradReducer(optimizer, group) as reducer:
+            (loss_total if use_total else loss_ce).backward()
+            reducer.finish()
+    else:
+        (loss_total if use_total else loss_ce).backward()
+        if group is not None:
+            allreduce_gradients(model.parameters(), group)
     optimizer.step()
     return loss_ce, loss_avg, loss_total
 
