@@ -736,7 +736,7 @@ class CLIPSimNoLatentProj(nn.Module):
             if self.lambda_average != 0:
                 raise L.EegclipError("CLIPSimNoLatentProj: the memory-bank loss term (lambda_average != 0) is not sharded; train it "
                                      "on one rank or with lambda_sim_loss = 0 (the reference default)")
-            ids_all = _all_gather_rows(ids.view(-1).to(torch.int64).contiguous(), self.shard_group, world)
+            ids_all = _all_gather_rows(ids.view(-1).to(device=En.device, dtype=torch.int64).contiguous(), self.shard_group, world)
             b = En.shape[0]
             avg = self.eegMemoryBank(ids_all, E_all.detach())[rank * b:(rank + 1) * b]
         else:
@@ -760,6 +760,13 @@ class CLIPSimNoLatentProj(nn.Module):
 # ---------------------------------------------------------------------------------------------------
 def _flat(x):
     return torch.flatten(x, start_dim=1)
+
+
+def _single_rank_only(module):
+    """The non-default wrappers carry batch-mean regularisers and per-rank state that the SUM all-reduce of the sharded scheme would
+    mis-scale: data parallelism is implemented for CLIP and CLIPSimNoLatentProj (the CLI default) only."""
+    if _world(getattr(module, "shard_group", None))[0] > 1:
+        raise L.EegclipError(f"{type(module).__name__}: sharded (data-parallel) training is implemented for CLIP / CLIPSimNoLatentProj only")
 
 
 def _proj(lin, x):
@@ -794,6 +801,7 @@ class CLIPSim(nn.Module):
         self.shard_group = None
 
     def forward(self, eeg, speech, ids):
+        _single_rank_only(self)
         E = _proj(self.latent_projection_eeg, _flat(self.eegModel(eeg)))
         S = _proj(self.latent_projection_speech, _flat(self.speechModel(speech)))
         loss_ce, En = infonce_loss(E, S, self.temperature, group=self.shard_group, return_normalized=True)
@@ -929,6 +937,7 @@ class CLIPKLDNoLatentProj(_KLDBase):
         return mu2, z_mu, z_logvar, self.reparameterize(z_mu, z_logvar), S, E
 
     def forward(self, eeg, speech, ids):
+        _single_rank_only(self)
         mu2, z_mu, z_logvar, _, S, E = self.encode(eeg, speech, ids)
         log_pmu2, kld_z2, lower_bound = _kld_terms(mu2, z_mu, z_logvar)
         loss_ce = infonce_loss(E, S, self.temperature, group=self.shard_group)
@@ -975,6 +984,7 @@ class CLIPKLDWithLatentProj(_KLDBase):
         return self.mu_eeg_lookup(ids), z_mu, z_logvar, self.reparameterize(z_mu, z_logvar), Sp, z_mu
 
     def forward(self, eeg, speech, ids):
+        _single_rank_only(self)
         mu2, z_mu, z_logvar, _, Sp, Ep = self.encode(eeg, speech, ids)
         log_pmu2, kld_z2, lower_bound = _kld_terms(mu2, z_mu, z_logvar)
         loss_ce = infonce_loss(Ep, Sp, self.temperature, group=self.shard_group)   # normalises both sides, as :1383-1384
