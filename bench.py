@@ -372,7 +372,8 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    names = ["conv_fwd_dgrad_tc", "conv_wgrad_tc", "attn_fwd", "attn_bwd", "ln_ct", "gemm_f32", "lin_tc", "lin_wgrad_tc", "lstm_recurrence"]
+    # class 5 holds the head's tcgen05 similarity launches (and the exact-fp32 GEMMs, of which the bf16x3 step launches none)
+    names = ["conv_fwd_dgrad_tc", "conv_wgrad_tc", "attn_fwd", "attn_bwd", "ln_ct", "head_similarity_tc", "lin_tc", "lin_wgrad_tc", "lstm_recurrence"]
     kern = {n: {"ms_per_step": prof_ms[i] / args.steps, "launches_per_step": prof_n[i] / args.steps} for i, n in enumerate(names)}
     conv_launches = max(1, conv_launches_timed)
     conv_ms = conv_ms_total / conv_launches

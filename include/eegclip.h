@@ -92,7 +92,7 @@ EEGCLIP_API const char* eegclip_build_info(void);
 
 /* Measurement hooks (bench.py): number of kernels this library has launched so far, and optional CUDA-event timing of
  * the dominant kernel classes on the stream they are launched on.  Classes: 0 conv fwd/dgrad (tcgen05), 1 conv wgrad
- * (tcgen05), 2 attention fwd, 3 attention bwd, 4 LayerNorm([C,T]) fwd+bwd, 5 fp32 GEMMs + head logits, 6 token GEMMs
+ * (tcgen05), 2 attention fwd, 3 attention bwd, 4 LayerNorm([C,T]) fwd+bwd, 5 head similarity kernel (tcgen05) + exact-fp32 GEMMs, 6 token GEMMs
  * (tcgen05), 7 token weight-gradient GEMMs (tcgen05), 8 LSTM recurrences.  eegclip_profile_end synchronises the device and
  * returns summed milliseconds and launch counts per class (arrays of >= 12 entries). */
 EEGCLIP_API long long eegclip_launch_count(void);
