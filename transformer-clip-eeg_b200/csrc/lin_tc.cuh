@@ -75,6 +75,24 @@ __device__ __forceinline__ void dbg_mark(unsigned long long* dbg, int who, int& 
   }
 }
 __device__ __forceinline__ float4 ld_act(const float4* p, int policy) { return policy == 1 ? __ldg(p) : ld_stream(p); }
+// 32 contiguous bytes per lane.  As TWO 128-bit loads every warp instruction touches 32-byte sectors it uses only half of, and with
+// L1::no_allocate the second instruction fetches the same sectors from L2 again: the producers' lane mapping (8 rows x four 32-byte
+// pieces per warp instruction) streamed at 2.46 TB/s that way and at 5.43 TB/s with ONE 256-bit load per lane
+// (tools/micro/load_probe.cu, one persistent CTA per SM) -- the reason every register-staged token kernel sat at 45-60 % of the
+// copy bandwidth in round 1.  `p` must be 32-byte aligned for the 256-bit form (checked per launch: LinTcArgs::vec8).
+__device__ __forceinline__ void ld_act8(const float* p, int policy, bool vec8, float4& a, float4& b) {
+  if (vec8) {
+    if (policy == 1)
+      asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+    else
+      asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+  } else {
+    a = ld_act(reinterpret_cast<const float4*>(p), policy);
+    b = ld_act(reinterpret_cast<const float4*>(p) + 1, policy);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Weight packing.  Packed operand B (Ntot x Ktot, "n" = output feature, "k" = contraction index):
@@ -144,7 +162,7 @@ struct ChunkRegs { float4 x0[(ROWS / 8) * 2 / NPW], x1[(ROWS / 8) * 2 / NPW]; };
 // issue the global loads of this thread's share of a ROWS x 64 chunk
 template <int ROWS, int NPW>
 __device__ __forceinline__ void load_chunk(ChunkRegs<ROWS, NPW>& R, const float* __restrict__ src, long ld, long row0, long rows_total,
-                                           int col0, int pw, int lane, int policy) {
+                                           int col0, int pw, int lane, int policy, bool vec8 = false) {
   constexpr int ITERS = (ROWS / 8) * 2 / NPW;
   static_assert(((ROWS / 8) * 2) % NPW == 0, "producer warps must divide the chunk");
   const int ch = (pw & 1) * 4 + (lane >> 3);
@@ -153,8 +171,7 @@ __device__ __forceinline__ void load_chunk(ChunkRegs<ROWS, NPW>& R, const float*
     const int rb = it * (NPW / 2) + (pw >> 1);
     const long r = row0 + rb * 8 + (lane & 7);
     if (r < rows_total) {
-      const float4* p = reinterpret_cast<const float4*>(src + r * ld + col0 + ch * 8);
-      R.x0[it] = ld_act(p, policy); R.x1[it] = ld_act(p + 1, policy);
+      ld_act8(src + r * ld + col0 + ch * 8, policy, vec8, R.x0[it], R.x1[it]);
     } else {
       R.x0[it] = make_float4(0.f, 0.f, 0.f, 0.f); R.x1[it] = R.x0[it];
     }
@@ -169,7 +186,7 @@ template <int ROWS, int NTERMS, int NPW, int PRO /* -1: runtime `pro` */>
 __device__ __forceinline__ void convert_chunk(ChunkRegs<ROWS, NPW>& R, long row0, long rows_total, int col0, int ncols_total,
                                               uint8_t* dst, uint32_t CS, uint32_t PS, int pw, int lane, int pro, const Drop& drop,
                                               float* colsum /* nullptr or 8 running sums */, const float* __restrict__ nxt_src = nullptr,
-                                              long nxt_ld = 0, long nxt_row0 = 0, int nxt_col0 = 0, int policy = 0) {
+                                              long nxt_ld = 0, long nxt_row0 = 0, int nxt_col0 = 0, int policy = 0, bool vec8 = false) {
   constexpr int ITERS = (ROWS / 8) * 2 / NPW;
   const int ch = (pw & 1) * 4 + (lane >> 3);
   const int prog = PRO < 0 ? pro : PRO;
@@ -221,8 +238,7 @@ __device__ __forceinline__ void convert_chunk(ChunkRegs<ROWS, NPW>& R, long row0
     if (nxt_src) {
       const long r = nxt_row0 + rl;
       if (r < rows_total) {
-        const float4* p = reinterpret_cast<const float4*>(nxt_src + r * nxt_ld + nxt_col0 + ch * 8);
-        R.x0[it] = ld_act(p, policy); R.x1[it] = ld_act(p + 1, policy);
+        ld_act8(nxt_src + r * nxt_ld + nxt_col0 + ch * 8, policy, vec8, R.x0[it], R.x1[it]);
       } else {
         R.x0[it] = make_float4(0.f, 0.f, 0.f, 0.f); R.x1[it] = R.x0[it];
       }
@@ -233,9 +249,9 @@ __device__ __forceinline__ void convert_chunk(ChunkRegs<ROWS, NPW>& R, long row0
 template <int ROWS, int NTERMS, int NPW /* producer warps */, int PRO /* -1: runtime `pro` */>
 __device__ __forceinline__ void stage_chunk(const float* __restrict__ src, long ld, long row0, long rows_total, int col0, int ncols_total,
                                             uint8_t* dst, uint32_t CS, uint32_t PS, int pw, int lane, int pro, const Drop& drop,
-                                            float* colsum /* nullptr or 8 running sums */, int policy) {
+                                            float* colsum /* nullptr or 8 running sums */, int policy, bool vec8 = false) {
   ChunkRegs<ROWS, NPW> R;
-  load_chunk<ROWS, NPW>(R, src, ld, row0, rows_total, col0, pw, lane, policy);
+  load_chunk<ROWS, NPW>(R, src, ld, row0, rows_total, col0, pw, lane, policy, vec8);
   convert_chunk<ROWS, NTERMS, NPW, PRO>(R, row0, rows_total, col0, ncols_total, dst, CS, PS, pw, lane, pro, drop, colsum);
 }
 
@@ -260,6 +276,7 @@ struct LinTcArgs {
   float* lnb_partial;             // EF_LNBWD: [gridDim.x][130]: sum dh*xhat (64), sum dh (64), 2 pad
   int nstage;                     // ring depth (2..NSTAGE)
   int policy;                     // load policy of the streamed activations (0: L1 no-allocate, 1: __ldg)
+  int vec8;                       // A (and the LayerNorm-backward side streams) are 32-byte aligned: 256-bit loads
   unsigned long long* dbg;        // development timeline buffer (nullptr in production)
 };
 
@@ -326,8 +343,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
       // chunks arrived in pairs with ~2 us of exposed latency between the pairs)
       ChunkRegs<BM, NPROD> R[2];
       auto chunk_pos = [&](int c_, int& tile_, int& kc_) { tile_ = blockIdx.x + (c_ / nchunk) * gridDim.x; kc_ = c_ % nchunk; };
-      if (total > 0) load_chunk<BM, NPROD>(R[0], a.A, a.lda, (long)blockIdx.x * BM, a.M, 0, pw, lane, a.policy);
-      if (total > 1) { int t1, k1; chunk_pos(1, t1, k1); load_chunk<BM, NPROD>(R[1], a.A, a.lda, (long)t1 * BM, a.M, k1 * KC, pw, lane, a.policy); }
+      const bool v8 = a.vec8 != 0;
+      if (total > 0) load_chunk<BM, NPROD>(R[0], a.A, a.lda, (long)blockIdx.x * BM, a.M, 0, pw, lane, a.policy, v8);
+      if (total > 1) { int t1, k1; chunk_pos(1, t1, k1); load_chunk<BM, NPROD>(R[1], a.A, a.lda, (long)t1 * BM, a.M, k1 * KC, pw, lane, a.policy, v8); }
       int tile = blockIdx.x, kc = 0;
       for (int c = 0; c < total; c += 2) {
 #pragma unroll
@@ -341,7 +359,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
             tc::mbar_wait(&empty[s], ph ^ 1);
             dbg_mark(dbg, 0, dn, 1);
             convert_chunk<BM, NTERMS, NPROD, PRO>(R[u], (long)tile * BM, a.M, kc * KC, K, sA + s * A_STAGE, A_CS, A_PLANE, pw, lane, a.pro,
-                                                  a.pro_drop, nullptr, more ? a.A : nullptr, a.lda, (long)t2 * BM, k2 * KC, a.policy);
+                                                  a.pro_drop, nullptr, more ? a.A : nullptr, a.lda, (long)t2 * BM, k2 * KC, a.policy, v8);
             tc::fence_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&full[s]);
@@ -357,7 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
           tc::mbar_wait(&empty[s], ph ^ 1);
           dbg_mark(dbg, 0, dn, 1);
           stage_chunk<BM, NTERMS, NPROD, PRO>(a.A, a.lda, (long)tile * BM, a.M, kc * KC, K, sA + s * A_STAGE, A_CS, A_PLANE, pw, lane, a.pro,
-                                              a.pro_drop, nullptr, a.policy);
+                                              a.pro_drop, nullptr, a.policy, a.vec8 != 0);
           tc::fence_async_smem();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&full[s]);
@@ -453,10 +471,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
             const long m = mrow0 + rl;
             ok[u] = m < a.M;
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 x0 = ok[u] ? ld_act(reinterpret_cast<const float4*>(a.lnb_x + m * 64 + c8), a.policy) : z4;
-            const float4 x1 = ok[u] ? ld_act(reinterpret_cast<const float4*>(a.lnb_x + m * 64 + c8 + 4), a.policy) : z4;
-            const float4 r0 = (ok[u] && a.residual) ? ld_act(reinterpret_cast<const float4*>(a.residual + m * a.ldc + c8), a.policy) : z4;
-            const float4 r1 = (ok[u] && a.residual) ? ld_act(reinterpret_cast<const float4*>(a.residual + m * a.ldc + c8 + 4), a.policy) : z4;
+            float4 x0 = z4, x1 = z4, r0 = z4, r1 = z4;
+            if (ok[u]) {
+              ld_act8(a.lnb_x + m * 64 + c8, a.policy, a.vec8 != 0, x0, x1);
+              if (a.residual) ld_act8(a.residual + m * a.ldc + c8, a.policy, a.vec8 != 0, r0, r1);
+            }
             const float4 d0 = *reinterpret_cast<const float4*>(stg + rl * LNB_LD + c8);
             const float4 d1 = *reinterpret_cast<const float4*>(stg + rl * LNB_LD + c8 + 4);
             xv[u][0] = x0.x; xv[u][1] = x0.y; xv[u][2] = x0.z; xv[u][3] = x0.w; xv[u][4] = x1.x; xv[u][5] = x1.y; xv[u][6] = x1.z; xv[u][7] = x1.w;
@@ -687,6 +706,9 @@ inline int lin_tc_launch_t(LinTcArgs a, cudaStream_t st) {
   while (a.nstage > 2 && lin_smem_bytes(a.N, a.K, a.nstage) > 227u * 1024u) --a.nstage;
   a.policy = g_tune[1];
   a.dbg = g_dbg_buf;
+  // 256-bit loads need 32-byte aligned rows (g_tune[13] = 1 forces the 2 x 128-bit form for A/B timing)
+  a.vec8 = (g_tune[13] == 0 && ((uintptr_t)a.A & 31) == 0 && (a.lda & 7) == 0 &&
+            (!a.lnb_x || ((((uintptr_t)a.lnb_x | (uintptr_t)a.residual) & 31) == 0 && (a.ldc & 7) == 0))) ? 1 : 0;
   const uint32_t smem = 0;
   const int mask = (a.bias ? EF_BIAS : 0) | (a.act == 1 ? EF_ACT1 : 0) | (a.act == 2 ? EF_ACT2 : 0) | (a.drop_on ? EF_DROP : 0) |
                    (a.act_grad_src ? EF_ACTGRAD : 0) | (a.mul_src ? EF_MULSRC : 0) | (a.residual ? EF_RES : 0);
@@ -802,6 +824,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) lin_wgrad_tc_kernel(const LinWg
     unsigned long long* dbgm = (blockIdx.x == 0 && blockIdx.y == 0 && warp == 0 && lane == 0) ? a.dbg : nullptr;
     int dnp = 0, dnm = 0;
     dbg_mark(dbgp, 0, dnp, 0);
+    // one 256-bit load per lane when both operands have 32-byte aligned rows (see ld_act8)
+    const bool v8w = ((((uintptr_t)a.dy | (uintptr_t)a.x) & 31) == 0) && ((a.lddy | a.ldx) & 7) == 0;
     for (int it = 0; it < nst; ++it) {
       const int s = it & 1;
       uint8_t* sb = smem + s * STAGE;
