@@ -213,6 +213,17 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2* sh /* >= 
   return sh[32];
 }
 
+// 256-bit global accesses (sm_100): a thread that owns 32 contiguous bytes moves them with one instruction, so a warp instruction
+// covers whole 32-byte sectors (two 128-bit accesses per thread touch every sector twice, half of it each time)
+__device__ __forceinline__ void ld256(const float* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void st256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+               "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -410,11 +410,9 @@ __global__ void __launch_bounds__(256) ln_ct_bwd_apply_kernel(const float* __res
   for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; }
   for (int b = blockIdx.y; b < B; b += gridDim.y) {
     const float mean = stats[2 * b], rstd = stats[2 * b + 1], m1 = m12[2 * b], m2 = m12[2 * b + 1];
-    const float4* yp = reinterpret_cast<const float4*>(y + b * n + i);
-    const float4* dp = reinterpret_cast<const float4*>(dout + b * n + i);
-    const float4 v0 = yp[0], v1 = yp[1], d0 = dp[0], d1 = dp[1];
-    const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float vv[8], dd[8];
+    ld256(y + b * n + i, vv);            // (i is a multiple of 8 floats and the tensors are 32-byte aligned: checked by the launcher)
+    ld256(dout + b * n + i, dd);
     float mm[8], o[8];
     drop_mult8(drop, (uint64_t)b * n + i, mm);
 #pragma unroll
@@ -424,21 +422,17 @@ __global__ void __launch_bounds__(256) ln_ct_bwd_apply_kernel(const float* __res
       ag[j] += dl * xh; ab[j] += dl;
       o[j] = rstd * (dl * g[j] - m1 - xh * m2) * mm[j];
     }
-    float4* op = reinterpret_cast<float4*>(dypad + ((long)b * TP + PL) * C + i);
-    op[0] = make_float4(o[0], o[1], o[2], o[3]);
-    op[1] = make_float4(o[4], o[5], o[6], o[7]);
+    st256(dypad + ((long)b * TP + PL) * C + i, o);
   }
-  float4* pg = reinterpret_cast<float4*>(part + (long)(2 * blockIdx.y) * n + i);
-  float4* pb = reinterpret_cast<float4*>(part + (long)(2 * blockIdx.y + 1) * n + i);
-  pg[0] = make_float4(ag[0], ag[1], ag[2], ag[3]); pg[1] = make_float4(ag[4], ag[5], ag[6], ag[7]);
-  pb[0] = make_float4(ab[0], ab[1], ab[2], ab[3]); pb[1] = make_float4(ab[4], ab[5], ab[6], ab[7]);
+  st256(part + (long)(2 * blockIdx.y) * n + i, ag);
+  st256(part + (long)(2 * blockIdx.y + 1) * n + i, ab);
 }
 
 // m12: 2*B floats of scratch; lnscr: ln_ct_scratch_floats(T, C) floats
 inline int ln_ct_act_bwd(const float* dout, const float* y, const float* stats, const float* gamma, const float* beta,
                          float* dypad, float* dgamma, float* dbeta, float* m12, float* lnscr, int B, int T, int C, int PL, int taps,
                          int act, const Drop& drop, cudaStream_t st) {
-  if (C & 7) return EEGCLIP_ERR_UNSUPPORTED;
+  if ((C & 7) || ((((uintptr_t)dout | (uintptr_t)y | (uintptr_t)dypad | (uintptr_t)lnscr) & 31) != 0)) return EEGCLIP_ERR_UNSUPPORTED;   // 256-bit accesses
   ProfScope prof(PROF_LNCT, st);
   float* gT = lnscr;
   float* bT = lnscr + (size_t)T * C;

@@ -71,8 +71,8 @@ SaveLayout save_layout(const eegclip_tower_desc& d) {
   size_t o = 0;
   L.eegx = o; o += n * C;
   L.c_y = 0; L.c_out = n * C; L.c_stats = 2 * n * C;
-  L.conv_stride = 2 * n * C + align_up((size_t)2 * d.B, 4);
-  L.x_qkv = 0; L.x_o = n * AQKV; L.x_lse = L.x_o + n * C; L.x_z1 = L.x_lse + align_up((size_t)d.B * AH * d.T, 4);
+  L.conv_stride = 2 * n * C + align_up((size_t)2 * d.B, 8);      // (every saved tensor starts 32-byte aligned: 256-bit accesses)
+  L.x_qkv = 0; L.x_o = n * AQKV; L.x_lse = L.x_o + n * C; L.x_z1 = L.x_lse + align_up((size_t)d.B * AH * d.T, 8);
   L.x_fpre = L.x_z1 + n * C; L.x_gp = L.x_fpre + n * FF; L.x_zout = L.x_gp + n * FF;
   L.x_h1 = L.x_zout + n * C; L.x_h2 = L.x_h1 + n * C;
   L.x_wp = L.x_h2 + n * C;
