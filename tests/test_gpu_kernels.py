@@ -31,7 +31,7 @@ def cm(lib):
 # ---------------------------------------------------------------------------------------------------------------
 # bidirectional LSTM (clip_model.py:267-268,322-323) vs the oracle's restated recurrence, incl. ragged batches
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("In,H,B,T", [(64, 128, 5, 24), (64, 128, 8, 64), (256, 4, 7, 40), (256, 4, 32, 64)])
+@pytest.mark.parametrize("In,H,B,T", [(64, 128, 5, 24), (64, 128, 8, 64), (64, 128, 20, 320), (256, 4, 7, 40), (256, 4, 32, 64)])
 def test_bilstm_vs_oracle(cm, In, H, B, T):
     torch.manual_seed(In + H + B)
     mod = torch.nn.LSTM(In, H, batch_first=True, bidirectional=True)

@@ -265,6 +265,375 @@ __global__ void __launch_bounds__(512, 1) lstm128_bwd_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// H = 128 on the warp-level tensor cores (mma.sync.m16n8k16, split-bf16: W_hi.h_hi + W_hi.h_lo + W_lo.h_hi, fp32 accumulate).
+// The recurrent product of a time step is pre^T (512 gate rows x 8 sequences) = W_hh (512 x 128) . h^T (128 x 8): the gate
+// rows are the M side (W_hh fragments stay ON CHIP for the whole sequence: the hi halves in registers, 128 per thread, the lo
+// halves in 128 KB of shared memory in fragment order), the 8 sequences of a CTA are the N = 8 side, so no MMA row is padding.
+// A per-step latency chain bounds a 320-step recurrence, not throughput: 8 sequences per CTA put the 2 x 256 sequences of
+// the benchmarked batch on 64 SMs at ~1/3 of the FFMA2 kernel's time per step (2.8 us for 4 sequences, issue-bound on 256
+// packed FMAs + 48 LDS per thread).  tcgen05 is not used on purpose: its smallest shapes (M = 128 x N = 16) cost ~31 cycles per
+// instruction x 96 instructions per step on one issuing thread, plus a TMEM round trip per step.
+//   block 256 = 8 warps.  Forward: warp w owns hidden units [16w, 16w+16) = 4 m-tiles (sub-block sb, gate pair): tile rows
+//   0-7 = gate i (g) of units 16w+8sb+r, rows 8-15 = gate f (o) of the same units, so a thread's accumulators hold i, f, g, o
+//   of ITS (unit, sequence) pairs and the cell update is thread-local (4 pairs per thread: unit 16w+8sb+(lane>>2), sequence
+//   2(lane&3)+e).  h_t goes back to shared memory as bf16 hi / lo planes in B-fragment order (double buffered: one barrier
+//   per step).  The contraction index is permuted (k-step s, fragment column 2t+e [+8] <-> unit 32t+4s+e [+2]) so that a
+//   thread's B fragments of all 8 k-steps are 64 contiguous bytes.
+//   Backward: warp w owns the m-tile of hidden units [16w, 16w+16) over all 512 gate rows (32 k-steps), so dh_{t-1} of a
+//   thread's 4 (unit, sequence) pairs never leaves its registers; da goes to shared memory the same way (k-step s, column
+//   2t+e [+8] <-> gate t, unit 4s+e [+2]).
+// ------------------------------------------------------------------------------------------------
+constexpr int LMS = 8;                                                // sequences per CTA (the MMA's N)
+constexpr int LM_WLO = 8 * 32 * 32 * 16;                              // W_lo fragments: [warp 8][32 (tile, k-step)][lane 32] uint4
+
+__device__ __forceinline__ void mma_bf16(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// split a pair of fp32 values into packed bf16 (hi, lo): element 0 in the low half
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float fa = __uint_as_float(hi << 16), fb = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - fb), "f"(a - fa));
+}
+__device__ __forceinline__ float ex2a(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcpa(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// four / five instructions each; absolute error ~1e-7 (ex2.approx 2^-22 relative, rcp.approx 1 ulp)
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcpa(1.f + ex2a(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(-2.f, rcpa(1.f + ex2a(2.8853900817779268f * x)), 1.f); }
+constexpr int LGS = 8 * LH;                                          // row stride of the gate buffer at H = 128
+// Global traffic goes through shared-memory stages so that every global access is a full 512-byte row piece per warp: an
+// accumulator fragment owns (8 units) x (2 sequences) per register, i.e. 32-byte pieces of 4 different rows per store
+// instruction -- 28 such stores per thread and step held the recurrence at 2.15 us per step (1.8 us without them).
+//   forward : x-projections of step s+1 arrive by cp.async while step s runs; gates / h / c of step s are staged and written
+//             out by (warp = sequence, lane = 4 units) at the start of step s+1 (h_{t-1} for Hp is that thread's previous h).
+//   backward: saved gates by cp.async, da staged and written out under the MMA phase of the same step.
+constexpr int LOS = 7 * LH + 4;                                       // forward out-stage row [i f g o h c h_prev][128]; +4: bank shift per sequence
+constexpr int LXS = 4 * LH + 4;                                       // gate-row stage [4][128]
+constexpr int LM_HB = 2 * 2 * 128 * 16;                               // h planes: [buffer][hi, lo][128 uint4]
+constexpr int LM_DB = 2 * 2 * 512 * 16;                               // da planes
+constexpr int L128M_SMEM = LM_WLO + LM_HB + 2 * LMS * LOS * 4 + 2 * LMS * LXS * 4;
+constexpr int L128MB_SMEM = LM_WLO + LM_DB + 2 * 2 * LMS * LXS * 4;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// shared -> global through the TMA engine (1-D bulk copy): the stores of a step do not occupy LSU slots of the 8 warps (a warp
+// sustains ~2.4 B/clk of st.global: the 28 KB of a step took 0.55 us as float4 stores)
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"((uint32_t)__cvta_generic_to_shared(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(256, 1) lstm128_fwd_mma_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
+                                                                float* __restrict__ G, float* __restrict__ out,
+                                                                float* __restrict__ Cs, float* __restrict__ Hp, int B, int T, unsigned long long* dbg) {
+  pdl_sync();
+  extern __shared__ __align__(16) uint8_t smm[];
+  // development timeline: thread 0 of CTA (0,0) stamps the phases of the first steps (tools/time_lstm.py timeline)
+  unsigned long long* dbgp = (dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ? dbg : nullptr;
+  int dbn = 0;
+  auto stamp = [&](int ev) {
+    if (dbgp && dbn < 120) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); dbgp[2 * dbn] = (unsigned long long)ev; dbgp[2 * dbn + 1] = t_; ++dbn; dbgp[255] = (unsigned long long)dbn; }
+  };
+  uint4* Wlo = reinterpret_cast<uint4*>(smm);
+  uint4* hbuf = reinterpret_cast<uint4*>(smm + LM_WLO);
+  float* ostage = reinterpret_cast<float*>(smm + LM_WLO + LM_HB);      // [2][8][LOS]
+  float* xstage = ostage + 2 * LMS * LOS;                             // [2][8][LXS]
+  const int dir = blockIdx.y, b0 = blockIdx.x * LMS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+  const float* W = dir ? w_hh_r : w_hh_f;
+  // ---- copy role: warp = sequence, lane = 4 consecutive units.  Sequences past the batch read sequence b0's rows (valid
+  //      memory, results unused) and store nothing. ----
+  const bool clive = b0 + warp < B;
+  const int t0 = dir ? T - 1 : 0;
+  const long dstep = dir ? -1 : 1;
+  const long crow = (long)(clive ? b0 + warp : b0) * T + t0;          // row of step 0; step s is row crow + s * dstep
+  auto fetch_x = [&](int step_) {
+    const float* src = G + (crow + step_ * dstep) * LGS + dir * LG + 4 * lane;
+    float* dst = xstage + ((step_ & 1) * LMS + warp) * LXS + 4 * lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cp_async16(dst + k * LH, src + k * LH);
+  };
+  fetch_x(0);
+  // ---- A fragments: tile tl = 2 sb + pair; a0/a2 = row (gate 2 pair, unit), a1/a3 = row (gate 2 pair + 1, unit) ----
+  uint32_t whi[4][8][4];
+#pragma unroll
+  for (int tl = 0; tl < 4; ++tl) {
+    const int unit = 16 * warp + 8 * (tl >> 1) + g;
+    const float* r0p = W + (long)((2 * (tl & 1)) * LH + unit) * LH + 32 * tig;
+    const float* r1p = r0p + (long)LH * LH;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(r0p) + ks), r1 = __ldg(reinterpret_cast<const float4*>(r1p) + ks);
+      uint4 lo;
+      split_pair(r0.x, r0.y, whi[tl][ks][0], lo.x);
+      split_pair(r1.x, r1.y, whi[tl][ks][1], lo.y);
+      split_pair(r0.z, r0.w, whi[tl][ks][2], lo.z);
+      split_pair(r1.z, r1.w, whi[tl][ks][3], lo.w);
+      Wlo[((warp * 4 + tl) * 8 + ks) * 32 + lane] = lo;
+    }
+  }
+  for (int i = tid; i < 2 * 2 * 128; i += 256) hbuf[i] = make_uint4(0u, 0u, 0u, 0u);
+  // compute role: (unit u = 16w + 8sb + g, sequence n = 2tig + e).  h of (u, n) lives at bf16 index
+  // (((u % 32) / 8 * 8 + n) * 4 + u / 32) * 8 + u % 8 of a plane: chunk 2(w&1) + sb, reader lane-quarter w >> 1, element g
+  const int hoff = ((2 * (warp & 1) * 8 + 2 * tig) * 4 + (warp >> 1)) * 8 + g;      // + sb * 256 + e * 32 (bf16 elements)
+  const int xo = 2 * tig * LXS + 16 * warp + g;                                    // + e * LXS + gate * LH + 8 sb
+  const int oo = 2 * tig * LOS + 16 * warp + g;                                    // + e * LOS + array * LH + 8 sb
+  float c[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float hprev[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  // lane 0 of warp w writes sequence w's staged rows of a step: gates (2 KB contiguous), h, c, h_{t-1}
+  auto copy_out = [&](int step_) {
+    if (lane == 0 && clive) {
+      const float* src = ostage + ((step_ & 1) * LMS + warp) * LOS;
+      const long row = crow + step_ * dstep;
+      bulk_s2g(G + row * LGS + dir * LG, src, 4 * LH * 4);
+      const long o = row * 256 + dir * LH;
+      bulk_s2g(out + o, src + 4 * LH, LH * 4);
+      bulk_s2g(Cs + o, src + 5 * LH, LH * 4);
+      bulk_s2g(Hp + o, src + 6 * LH, LH * 4);
+      bulk_commit();
+    }
+  };
+  cp_async_wait_all();
+  __syncthreads();
+  for (int step = 0; step < T; ++step) {
+    stamp(0);
+    if (step + 1 < T) fetch_x(step + 1);
+    stamp(5);
+    const uint4* hh = hbuf + (step & 1) * 256;
+    const uint4* hl = hh + 128;
+    float acc[4][2][4];                                   // [tile][hi.hi (+ x-projection), hi.lo + lo.hi]
+    {
+      // accumulator j of tile tl = (gate 2 (tl & 1) + (j >> 1), sequence 2 tig + (j & 1))
+      const float* xs = xstage + (step & 1) * LMS * LXS + xo;
+#pragma unroll
+      for (int tl = 0; tl < 4; ++tl)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[tl][0][j] = xs[(j & 1) * LXS + (2 * (tl & 1) + (j >> 1)) * LH + 8 * (tl >> 1)];
+          acc[tl][1][j] = 0.f;
+        }
+    }
+    if (dbgp) { if (acc[0][0][0] + acc[3][0][3] == 123.456f) dbgp[254] = 1; stamp(6); }
+    if (step > 0) copy_out(step - 1);
+    stamp(1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 vh = hh[(i * 8 + g) * 4 + tig], vl = hl[(i * 8 + g) * 4 + tig];
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int ks = 2 * i + kk;
+        const uint32_t bh0 = kk ? vh.z : vh.x, bh1 = kk ? vh.w : vh.y, bl0 = kk ? vl.z : vl.x, bl1 = kk ? vl.w : vl.y;
+#pragma unroll
+        for (int tl = 0; tl < 4; ++tl) {
+          const uint4 al = Wlo[((warp * 4 + tl) * 8 + ks) * 32 + lane];
+          const uint32_t alo[4] = {al.x, al.y, al.z, al.w};
+          mma_bf16(acc[tl][0], whi[tl][ks], bh0, bh1);
+          mma_bf16(acc[tl][1], whi[tl][ks], bl0, bl1);
+          mma_bf16(acc[tl][1], alo, bh0, bh1);
+        }
+      }
+    }
+    // ---- gates and state of this thread's 4 (unit, sequence) pairs ----
+    if (dbgp) { if (acc[0][0][0] + acc[3][1][3] == 123.456f) dbgp[254] = 1; stamp(2); }
+    uint16_t* nh = reinterpret_cast<uint16_t*>(hbuf + ((step + 1) & 1) * 256) + hoff;
+    float* os = ostage + (step & 1) * LMS * LOS + oo;
+#pragma unroll
+    for (int sb = 0; sb < 2; ++sb) {
+      float hn[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float gi = sigmoid_fast(acc[2 * sb][0][e] + acc[2 * sb][1][e]);
+        const float gf = sigmoid_fast(acc[2 * sb][0][2 + e] + acc[2 * sb][1][2 + e]);
+        const float gg = tanh_fast(acc[2 * sb + 1][0][e] + acc[2 * sb + 1][1][e]);
+        const float go = sigmoid_fast(acc[2 * sb + 1][0][2 + e] + acc[2 * sb + 1][1][2 + e]);
+        const float cn = fmaf(gf, c[sb][e], gi * gg);
+        c[sb][e] = cn;
+        hn[e] = go * tanh_fast(cn);
+        float* op = os + e * LOS + 8 * sb;
+        op[0] = gi; op[LH] = gf; op[2 * LH] = gg; op[3 * LH] = go; op[4 * LH] = hn[e]; op[5 * LH] = cn; op[6 * LH] = hprev[sb][e];
+        hprev[sb][e] = hn[e];
+      }
+      uint32_t hi, lo;
+      split_pair(hn[0], hn[1], hi, lo);
+      nh[sb * 256] = (uint16_t)(hi & 0xffffu);
+      nh[sb * 256 + 32] = (uint16_t)(hi >> 16);
+      nh[128 * 8 + sb * 256] = (uint16_t)(lo & 0xffffu);
+      nh[128 * 8 + sb * 256 + 32] = (uint16_t)(lo >> 16);
+    }
+    stamp(3);
+    fence_async_smem();                                   // staged rows -> visible to the bulk copies issued after the barrier
+    cp_async_wait_all();
+    if (lane == 0) bulk_wait_read();                      // the previous step's stage may be rewritten after the barrier
+    stamp(4);
+    __syncthreads();
+  }
+  copy_out(T - 1);
+  if (lane == 0) bulk_wait_all();
+}
+
+__global__ void __launch_bounds__(256, 1) lstm128_bwd_mma_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
+                                                                float* __restrict__ G, const float* __restrict__ dout,
+                                                                const float* __restrict__ Cs, int B, int T) {
+  pdl_sync();
+  extern __shared__ __align__(16) uint8_t smm[];
+  uint4* Wlo = reinterpret_cast<uint4*>(smm);
+  uint4* dbuf = reinterpret_cast<uint4*>(smm + LM_WLO);
+  float* gstage = reinterpret_cast<float*>(smm + LM_WLO + LM_DB);      // saved gates in:  [2][8][LXS]
+  float* dstage = gstage + 2 * LMS * LXS;                             // da out:          [2][8][LXS]
+  const int dir = blockIdx.y, b0 = blockIdx.x * LMS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+  const float* W = dir ? w_hh_r : w_hh_f;
+  // ---- copy role (warp = sequence, lane = 4 units) ----
+  const bool clive = b0 + warp < B;
+  const int t0 = dir ? 0 : T - 1;                                                   // reverse of the forward order
+  const long dstep = dir ? 1 : -1;
+  const long crow = (long)(clive ? b0 + warp : b0) * T + t0;
+  auto fetch_g = [&](int step_) {
+    const float* src = G + (crow + step_ * dstep) * LGS + dir * LG + 4 * lane;
+    float* dst = gstage + ((step_ & 1) * LMS + warp) * LXS + 4 * lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cp_async16(dst + k * LH, src + k * LH);
+  };
+  fetch_g(0);
+  // ---- A fragments of W^T: rows = units 16w+g (a0, a2) and 16w+8+g (a1, a3); k-step s column 2tig+e [+8] <-> gate row 128 tig + 4s + e [+2]
+  uint32_t whi[32][4];
+  {
+    const float* wc = W + (long)(128 * tig) * LH + 16 * warp + g;
+#pragma unroll
+    for (int ks = 0; ks < 32; ++ks) {
+      const float* p = wc + (long)(4 * ks) * LH;
+      uint4 lo;
+      split_pair(__ldg(p), __ldg(p + LH), whi[ks][0], lo.x);
+      split_pair(__ldg(p + 8), __ldg(p + LH + 8), whi[ks][1], lo.y);
+      split_pair(__ldg(p + 2 * LH), __ldg(p + 3 * LH), whi[ks][2], lo.z);
+      split_pair(__ldg(p + 2 * LH + 8), __ldg(p + 3 * LH + 8), whi[ks][3], lo.w);
+      Wlo[(warp * 32 + ks) * 32 + lane] = lo;
+    }
+  }
+  // compute role: pairs (unit 16w + 8ub + g, sequence 2tig + e).  da of (gate gt, unit u, sequence n) lives at bf16 index
+  // ((u / 8 * 8 + n) * 4 + gt) * 8 + u % 8 of a plane
+  const int doff = ((2 * warp * 8 + 2 * tig) * 4) * 8 + g;                           // + ub * 256 + e * 32 + gt * 8 (bf16 elements)
+  const int xo = 2 * tig * LXS + 16 * warp + g;                                     // + e * LXS + gate * LH + 8 ub
+  const bool live0 = b0 + 2 * tig < B, live1 = b0 + 2 * tig + 1 < B;
+  const int col = dir * LH + 16 * warp + g;
+  long so[2] = {((long)(live0 ? b0 + 2 * tig : b0) * T + t0) * 256 + col, ((long)(live1 ? b0 + 2 * tig + 1 : b0) * T + t0) * 256 + col};
+  float dh[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, dc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float n_cp[2][2], n_dy[2][2], ct[2][2];
+  // dy and c_{t-1} of the step whose state row is o; `has_prev`: a forward-earlier step exists
+  auto fetch_s = [&](const long* o, bool has_prev) {
+#pragma unroll
+    for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        n_dy[ub][e] = dout[o[e] + 8 * ub];
+        n_cp[ub][e] = has_prev ? Cs[o[e] + dstep * 256 + 8 * ub] : 0.f;
+      }
+  };
+#pragma unroll
+  for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) ct[ub][e] = Cs[so[e] + 8 * ub];
+  fetch_s(so, T > 1);
+  cp_async_wait_all();
+  __syncthreads();
+  for (int step = 0; step < T; ++step) {
+    float dyv[2][2], cpv[2][2];
+#pragma unroll
+    for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) { dyv[ub][e] = n_dy[ub][e]; cpv[ub][e] = n_cp[ub][e]; }
+    if (step + 1 < T) {                                    // uniform
+      fetch_g(step + 1);
+      so[0] += dstep * 256; so[1] += dstep * 256;
+      fetch_s(so, step + 2 < T);
+    }
+    // ---- gate phase: da of this thread's 4 pairs ----
+    uint16_t* dw = reinterpret_cast<uint16_t*>(dbuf + (step & 1) * 1024) + doff;
+    const float* gs = gstage + (step & 1) * LMS * LXS + xo;
+    float* ds = dstage + (step & 1) * LMS * LXS + xo;
+    float da[2][2][4];
+#pragma unroll
+    for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float* gp = gs + e * LXS + 8 * ub;
+        const float gi = gp[0], gf = gp[LH], gg = gp[2 * LH], go = gp[3 * LH], cp = cpv[ub][e];
+        const float dht = dyv[ub][e] + dh[ub][e];
+        const float tc = tanh_fast(ct[ub][e]);
+        const float dct = fmaf(dht * go, fmaf(-tc, tc, 1.f), dc[ub][e]);
+        da[ub][e][0] = dct * gg * gi * (1.f - gi);
+        da[ub][e][1] = dct * cp * gf * (1.f - gf);
+        da[ub][e][2] = dct * gi * fmaf(-gg, gg, 1.f);
+        da[ub][e][3] = dht * tc * go * (1.f - go);
+        dc[ub][e] = dct * gf;
+        ct[ub][e] = cp;                                    // c_{t-1} is the next step's c_t
+        float* dp = ds + e * LXS + 8 * ub;
+        dp[0] = da[ub][e][0]; dp[LH] = da[ub][e][1]; dp[2 * LH] = da[ub][e][2]; dp[3 * LH] = da[ub][e][3];
+      }
+#pragma unroll
+    for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+      for (int gt = 0; gt < 4; ++gt) {
+        uint32_t hi, lo;
+        split_pair(da[ub][0][gt], da[ub][1][gt], hi, lo);
+        dw[ub * 256 + gt * 8] = (uint16_t)(hi & 0xffffu);
+        dw[ub * 256 + gt * 8 + 32] = (uint16_t)(hi >> 16);
+        dw[512 * 8 + ub * 256 + gt * 8] = (uint16_t)(lo & 0xffffu);
+        dw[512 * 8 + ub * 256 + gt * 8 + 32] = (uint16_t)(lo >> 16);
+      }
+    fence_async_smem();
+    cp_async_wait_all();
+    if (lane == 0) bulk_wait_read();                       // step - 1's da stage is rewritten in step + 1, after this barrier
+    __syncthreads();
+    // ---- da of this step out to G: one 2 KB bulk copy per sequence (lane 0 of warp = sequence), under the MMA phase ----
+    if (lane == 0 && clive) {
+      bulk_s2g(G + (crow + step * dstep) * LGS + dir * LG, dstage + ((step & 1) * LMS + warp) * LXS, 4 * LH * 4);
+      bulk_commit();
+    }
+    // ---- dh_{t-1}^T (this warp's 16 units x 8 sequences) = W^T . da^T over the 512 gate rows ----
+    const uint4* dah = dbuf + (step & 1) * 1024;
+    const uint4* dal = dah + 512;
+    float acc[4][4];                                       // hi.hi and (hi.lo + lo.hi), each over even / odd k-steps
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[q][j] = 0.f;
+#pragma unroll
+    for (int cch = 0; cch < 16; ++cch) {
+      const uint4 vh = dah[(cch * 8 + g) * 4 + tig], vl = dal[(cch * 8 + g) * 4 + tig];
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int ks = 2 * cch + kk;
+        const uint32_t bh0 = kk ? vh.z : vh.x, bh1 = kk ? vh.w : vh.y, bl0 = kk ? vl.z : vl.x, bl1 = kk ? vl.w : vl.y;
+        const uint4 al = Wlo[(warp * 32 + ks) * 32 + lane];
+        const uint32_t alo[4] = {al.x, al.y, al.z, al.w};
+        mma_bf16(acc[kk], whi[ks], bh0, bh1);
+        mma_bf16(acc[2 + kk], whi[ks], bl0, bl1);
+        mma_bf16(acc[2 + kk], alo, bh0, bh1);
+      }
+    }
+    // accumulator j: unit 16w + 8 (j >> 1) + g, sequence 2 tig + (j & 1)
+#pragma unroll
+    for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 2 * ub + e;
+        dh[ub][e] = (acc[0][j] + acc[1][j]) + (acc[2][j] + acc[3][j]);
+      }
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------------
 // H = 4 (speech_lstm2): 16 gate rows = one half-warp per (sequence, direction); lane j of the group owns gate row j
 // (gate j >> 2, unit j & 3), so the gate row of a time step is one coalesced 64-byte access.  State exchange by shuffles;
 // the next step's input projection is prefetched while the current one is computed.
