@@ -115,27 +115,10 @@ int eegclip_bilstm_forward(const eegclip_bilstm_desc* dp, const float* const* pa
     TRY(lintc::lin_tc_launch(d.math, a, st));
   }
   // ---- recurrence ----
-  if (d.H == 128 && g_tune[14] == 0) {
-    static bool configured = false;
-    if (!configured) {
-      if (cudaFuncSetAttribute(lstm::lstm128_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::L128M_SMEM) != cudaSuccess)
-        return EEGCLIP_ERR_CUDA;
-      configured = true;
-    }
+  if (d.H == 128) {
     ProfScope prof(PROF_LSTM, st);
-    LAUNCH_PDL((lstm::lstm128_fwd_mma_kernel), dim3(ceil_div(d.B, lstm::LMS), 2), 256, lstm::L128M_SMEM, st, params[1], params[5], G, out,
-                                                                                                 save + L.cs, save + L.hp, d.B, d.T, g_dbg_buf);
-    LAUNCH_CHECK();
-  } else if (d.H == 128) {                                  // g_tune[14] = 1: the fp32 FFMA2 recurrence (A/B timing)
-    static bool configured = false;
-    if (!configured) {
-      if (cudaFuncSetAttribute(lstm::lstm128_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::L128_SMEM) != cudaSuccess)
-        return EEGCLIP_ERR_CUDA;
-      configured = true;
-    }
-    ProfScope prof(PROF_LSTM, st);
-    LAUNCH_PDL((lstm::lstm128_fwd_kernel), dim3(ceil_div(d.B, lstm::LNB), 2), 512, lstm::L128_SMEM, st, params[1], params[5], G, L.GS, out,
-                                                                                             save + L.cs, save + L.hp, d.B, d.T, g_dbg_buf);
+    LAUNCH_PDL((lstm::lstm128_fwd_c2_kernel), dim3(2 * ceil_div(d.B, lstm::LMS), 2), 256, 0, st, params[1], params[5], G, out, save + L.cs, save + L.hp,
+                                                                                d.B, d.T, g_dbg_buf);
     LAUNCH_CHECK();
   } else {
     ProfScope prof(PROF_LSTM, st);
@@ -164,27 +147,9 @@ int eegclip_bilstm_backward(const eegclip_bilstm_desc* dp, const float* const* p
   float* partial = (float*)(sc + L.wgp);
   const Drop nodrop = make_drop(0, 0, 0, 0.f, 0);
   // ---- recurrence: gates -> da (in place) ----
-  if (H == 128 && g_tune[14] == 0) {
-    static bool configured = false;
-    if (!configured) {
-      if (cudaFuncSetAttribute(lstm::lstm128_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::L128MB_SMEM) != cudaSuccess)
-        return EEGCLIP_ERR_CUDA;
-      configured = true;
-    }
+  if (H == 128) {
     ProfScope prof(PROF_LSTM, st);
-    LAUNCH_PDL((lstm::lstm128_bwd_mma_kernel), dim3(ceil_div(d.B, lstm::LMS), 2), 256, lstm::L128MB_SMEM, st, params[1], params[5], G, dout,
-                                                                                                  Cs, d.B, d.T);
-    LAUNCH_CHECK();
-  } else if (H == 128) {
-    static bool configured = false;
-    if (!configured) {
-      if (cudaFuncSetAttribute(lstm::lstm128_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::L128B_SMEM) != cudaSuccess)
-        return EEGCLIP_ERR_CUDA;
-      configured = true;
-    }
-    ProfScope prof(PROF_LSTM, st);
-    LAUNCH_PDL((lstm::lstm128_bwd_kernel), dim3(ceil_div(d.B, lstm::LNB), 2), 512, lstm::L128B_SMEM, st, params[1], params[5], G, L.GS, dout, Cs, d.B,
-                                                                                              d.T);
+    LAUNCH_PDL((lstm::lstm128_bwd_c2_kernel), dim3(2 * ceil_div(d.B, lstm::LMS), 2), 256, 0, st, params[1], params[5], G, dout, Cs, d.B, d.T);
     LAUNCH_CHECK();
   } else {
     CUDA_TRY(cudaMemsetAsync(grads[1], 0, (size_t)G4 * H * sizeof(float), st));
