@@ -21,7 +21,15 @@ __global__ void probe(float* out, long long* clk, int iters) {
         asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                      : "+f"(acc[c][0]), "+f"(acc[c][1]), "+f"(acc[c][2]), "+f"(acc[c][3])
                      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-      else
+      else if (KIND == 2)
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                     : "+f"(acc[c][0]), "+f"(acc[c][1]), "+f"(acc[c][2]), "+f"(acc[c][3])
+                     : "r"(a0), "r"(a1), "r"(b0));
+      else if (KIND == 3) {
+        uint32_t t;
+        asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(t) : "r"(__float_as_uint(acc[c][0])));
+        acc[c][0] = __uint_as_float(t);
+      } else
         asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                      : "+f"(acc[c][0]), "+f"(acc[c][1]), "+f"(acc[c][2]), "+f"(acc[c][3])
                      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -44,6 +52,7 @@ void run(int warps, float* out, long long* clk) {
   cudaMemcpy(&c, clk, 8, cudaMemcpyDeviceToHost);
   const double per = (double)c / iters;
   const double flop = (KIND == 0 ? 4096.0 : 2048.0) * CH * warps;   // per SM per iteration
+  if (KIND >= 2) { printf("%s chains/warp %2d warps/SM %2d: %.1f clk per instruction per warp\n", KIND == 2 ? "f16 m16n8k8" : "movmatrix  ", CH, warps, per / CH); return; }
   printf("%s chains/warp %2d warps/SM %2d: %.1f clk per round of %d MMAs per warp -> %.1f clk per MMA per warp, %.0f dense FLOP/clk/SM\n",
          KIND == 0 ? "bf16 m16n8k16" : "tf32 m16n8k8 ", CH, warps, per, CH, per / CH, flop / per);
 }
@@ -54,5 +63,7 @@ int main() {
   run<1, 0>(1, out, clk); run<2, 0>(1, out, clk); run<4, 0>(1, out, clk); run<8, 0>(1, out, clk); run<12, 0>(1, out, clk);
   run<1, 0>(4, out, clk); run<4, 0>(4, out, clk); run<8, 0>(4, out, clk); run<12, 0>(8, out, clk); run<8, 0>(16, out, clk); run<8, 0>(32, out, clk);
   run<1, 1>(1, out, clk); run<8, 1>(1, out, clk); run<8, 1>(8, out, clk); run<8, 1>(16, out, clk); run<8, 1>(32, out, clk);
+  run<1, 2>(1, out, clk); run<8, 2>(1, out, clk); run<8, 2>(8, out, clk); run<8, 2>(16, out, clk);
+  run<1, 3>(1, out, clk); run<8, 3>(1, out, clk); run<8, 3>(8, out, clk); run<8, 3>(16, out, clk);
   return 0;
 }

@@ -1,11 +1,15 @@
 // Tensor-core short-sequence attention (clip_model.py:30-45): 8 heads x head_dim 8, T <= 512, softmax(QK^T / sqrt(64)),
 // dropout on the probabilities, no mask.  The (B,8,T,T) energy / probability tensors never exist.
 //
-// head_dim = 8 is exactly the K extent of mma.sync.m16n8k8 (TF32 operands, fp32 accumulate): one MMA produces a 16 x 8
-// score tile, and its accumulator fragment can be re-used in place as the A fragment of the next MMA (P.V, P^T.dO,
-// dS^T.Q) if the 8 contracted indices are taken in the order the fragment already has them -- so probabilities never
-// move between threads.  tcgen05 is not used here on purpose: the contraction dimension is 8, the work per
-// score is dominated by exp2 + Philox, not by the MMA, and the warp-level MMA keeps everything in registers.
+// Warp-level mma.sync on fp16 operands with fp32 accumulation.  head_dim = 8 is the K extent of m16n8k8: one MMA produces a
+// 16 x 8 score tile, and its accumulator fragment is re-used in place as the A fragment of the next MMA (P.V, P^T.dO, dS^T.Q:
+// one cvt.rn.f16x2 per pair of scores) if the contracted indices are taken in the order the fragment already has them -- so
+// probabilities never move between threads.  tcgen05 is not used here on purpose: the contraction dimension is 8,
+// the work per score is exp2 + dropout + conversion (measured: the forward sits at 57 % of the MUFU pipe, 54 % of the ALU pipe,
+// 68 % of the issue slots and only 35 % of the legacy tensor pipe), and the warp-level MMA keeps everything in registers.
+// History (B = 256, T = 320, per layer): TF32 m16n8k8 with dS staged through shared memory for dQ: forward 118 us, backward
+// 288 us; fp16 with m16n8k16 over queries / keys and movmatrix for dQ (this file): 96 / 174 us.  Every mma.sync shape costs the
+// same 8 clk per SM sub-partition (tools/micro/hmma_probe.cu), so k = 16 forms do twice the work per tensor-pipe slot.
 //
 // Dropout grouping: one Philox call yields 8 decisions for 8 consecutive key indices of one query row (common.cuh), so
 // the key <-> fragment-column assignment is permuted such that every thread owns 8 consecutive keys of its rows:
@@ -13,8 +17,10 @@
 //   backward (rows = keys)   : a warp owns 64 keys = 4 m-tiles Y; tile Y row g <-> key 8g+2Y, row g+8 <-> key 8g+2Y+1
 // The B/A fragments of K and V are laid out in shared memory / registers in exactly that order.
 //
-// Numerics: Q,K,V,P,dO,dS are rounded to TF32 (cvt.rna) before the MMAs, accumulation and softmax statistics are fp32.
+// Numerics: Q, K, V, P, dO, dS are rounded to fp16 (11-bit significand, the precision of the TF32 form this replaced; dO is
+// brought into fp16's range by a power-of-two scale per (batch, head)), accumulation and softmax statistics are fp32.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "attention.cuh"
 
@@ -23,26 +29,6 @@ namespace attntc {
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
-constexpr int QS = 12;   // padded row stride (floats) of the Q / dO shared-memory copies: conflict-free for both B-fragment patterns
-
-__device__ __forceinline__ uint32_t tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float tf32f(float x) { return __uint_as_float(tf32(x)); }
-// cvt.rna.tf32.f32 for FINITE inputs in two integer instructions: ptxas lowers the PTX conversion to IADD + FSETP(+inf) + SEL + LOP3
-// (the compare / select only protect inf / NaN).  Probabilities and dS in the inner loops are finite; adding half an ulp of the 13
-// dropped bits to the sign-magnitude pattern and truncating is round-to-nearest, ties away from zero -- exactly .rna.
-__device__ __forceinline__ uint32_t tf32_fin(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
-
-// D(16x8) = A(16x8, row) * B(8x8, col) + C
-__device__ __forceinline__ void mma_tf32(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1,
-                                         const float* c) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
-               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
-               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
-}
 
 __device__ __forceinline__ float ex2(float x) {
   float r;
@@ -63,69 +49,120 @@ __device__ __forceinline__ void build_keep_bits(uint32_t* smask, const Drop& dro
 }
 
 // ------------------------------------------------------------------------------------------------
-// Forward.  grid = B*H, block = (T/32) warps; warp w owns query rows [32w, 32w+32) as two 16-row tiles (two independent
-// MMA / exp2 chains per warp).  smem: Kf / Vf fragment tables, float4 [T/32 blocks][2 halves][32 lanes] each, + keep bits.
+// Backward on fp16 operands (same 11-bit significand as TF32; fp32 accumulation and softmax arithmetic unchanged).
+// Every mma.sync costs the same 8 clk per SM sub-partition whatever its shape (tools/micro/hmma_probe.cu), so the products
+// whose contraction runs over queries or keys use m16n8k16 (two query blocks per instruction), and 16-bit fragments make three
+// things cheap that TF32 did not: accumulator -> A fragment is ONE cvt.rn.f16x2 per pair (TF32: add + and per element), the
+// B fragments are single 32-bit shared loads, and dS^T reaches the dQ product through movmatrix (register 8x8 transpose)
+// instead of a shared-memory staging tile (16 LDS + 8 STS + 8 half-filled MMAs per 8 queries before).
+//   per 16 queries and 16-key tile: S^T - lse: 2 x m16n8k16 (lse in the spare contraction slots), dP^T: 2 x m16n8k8;
+//   dV += Pd^T.dO, dK += dS^T.Q: 2 x m16n8k16;  dQ += dS.K': 1 x m16n8k16 (16 queries x 16 keys, no padding) + 4 movmatrix.
+// Range: everything downstream of dO is linear in dO, so dO is scaled by a power of two per (batch, head) to [8, 16) max
+// magnitude before it is rounded to fp16 and the three gradients are scaled back (gradients of 1e-6 would be fp16 subnormals).
+// smem: Qh, dOh [T][8] and their transposes QT, dOT [8][T+8] (fp16), LB [T][4] (-lse' terms), Ds [T], dQs [T][8] (fp32), keep bits.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 2) attn_fwd_tc_kernel(const float* __restrict__ qkv, float* __restrict__ out,
-                                                            float* __restrict__ lse, int T, Drop drop) {
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void mma_h8(float* d, uint32_t a0, uint32_t a1, uint32_t b0, const float* c) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%8,%9,%10};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a0), "r"(a1), "r"(b0), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+}
+__device__ __forceinline__ void mma_h16(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// x as three fp16 terms (hi, mid | lo, 0): the row maximum / log-sum-exp rides in contraction slots 8..10 of a k = 16 score MMA
+// against ones (every mma.sync costs the same 8 clk whatever its k), so S - max is produced by the MMA with a ZERO accumulator
+// input -- as the accumulator input it cost four register moves per MMA (the C operand is a register quad)
+__device__ __forceinline__ void split3_h(float x, uint32_t& w0, uint32_t& w1) {
+  const __half h1 = __float2half_rn(x);
+  const float r1 = x - __half2float(h1);
+  const __half h2 = __float2half_rn(r1);
+  const __half h3 = __float2half_rn(r1 - __half2float(h2));
+  w0 = (uint32_t)__half_as_ushort(h1) | ((uint32_t)__half_as_ushort(h2) << 16);
+  w1 = (uint32_t)__half_as_ushort(h3);
+}
+__device__ __forceinline__ void mma_h16z(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+__device__ __forceinline__ uint32_t movm_t(uint32_t x) {
+  uint32_t r;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+
+// Forward on fp16 operands: S = Q.K^T as m16n8k8 (the contraction is the head dimension, 8), P.V as m16n8k16 -- the score
+// accumulators of two 8-key tiles become one A fragment with four cvt.rn.f16x2 (the flash-attention register reuse), so the P.V
+// product takes half the instructions of the TF32 form and its operand tables half the shared memory.  Two passes (row
+// maximum first): fp16 probabilities need the true maximum -- an upper bound (|q| max|k|) would push them below 2^-14.
+//   grid = B*H, block = (T/32) warps; warp w owns query rows [32w, 32w+32) as two 16-row tiles.
+//   smem: Kf, Vf: uint4 [T/32 blocks][32 lanes] (K: tile X column g <-> key 8(g>>1)+2X+(g&1), dims 2tig, 2tig+1; V: keys
+//   8tig..8tig+7 of the block for dim g), + keep bits.
+__global__ void __launch_bounds__(512, 2) attn_fwd_h_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                           float* __restrict__ lse, int T, Drop drop) {
   pdl_sync();
-  extern __shared__ float4 smf[];
-  float4* Kf = smf;
-  float4* Vf = smf + (T / 32) * 64;
-  uint32_t* smask = reinterpret_cast<uint32_t*>(Vf + (T / 32) * 64);
+  extern __shared__ uint4 smq[];
+  uint4* Kf = smq;
+  uint4* Vf = smq + T;
+  uint32_t* smask = reinterpret_cast<uint32_t*>(Vf + T);
   const int bh = blockIdx.x, b = bh / AH, h = bh % AH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
   const float* base = qkv + (long)b * T * AQKV;
   const int nblk = T >> 5;
-  // ---- build the fragment tables: one (block, lane) entry of K or V per iteration (2T entries) ----
   for (int e = tid; e < 2 * T; e += blockDim.x) {
     const int isv = e >= T;
     const int r = isv ? e - T : e;
     const int blk = r >> 5, l = r & 31, eg = l >> 2, et = l & 3;
-    float v[8];
+    uint4 v;
     if (!isv) {
-      // S tile X, column eg  <->  key 8*(eg>>1) + 2X + (eg&1);  b0 = K[key][et], b1 = K[key][et+4]
+      uint32_t w[4];
 #pragma unroll
       for (int X = 0; X < 4; ++X) {
-        const float* kr = base + (long)(blk * 32 + 8 * (eg >> 1) + 2 * X + (eg & 1)) * AQKV + 64 + h * AD;
-        v[2 * X] = tf32f(__ldg(kr + et));
-        v[2 * X + 1] = tf32f(__ldg(kr + et + 4));
+        const float2 kk = __ldg(reinterpret_cast<const float2*>(base + (long)(blk * 32 + 8 * (eg >> 1) + 2 * X + (eg & 1)) * AQKV + 64 + h * AD + 2 * et));
+        w[X] = pack_h2(kk.x, kk.y);
       }
+      v = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
-      // P.V k-index et <-> key 8et+2X, et+4 <-> key 8et+2X+1 ; b = V[key][d = eg]  => 8 consecutive keys
+      float f[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = tf32f(__ldg(base + (long)(blk * 32 + 8 * et + j) * AQKV + 128 + h * AD + eg));
+      for (int j = 0; j < 8; ++j) f[j] = __ldg(base + (long)(blk * 32 + 8 * et + j) * AQKV + 128 + h * AD + eg);
+      v = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
     }
-    float4* dst = (isv ? Vf : Kf) + blk * 64 + l;
-    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-    dst[32] = make_float4(v[4], v[5], v[6], v[7]);
+    (isv ? Vf : Kf)[blk * 32 + l] = v;
   }
   const bool bitmask = drop.enabled && drop.onebit;
   if (bitmask) build_keep_bits(smask, drop, bh, T);
   // ---- Q fragments of this warp (two row tiles), scaled by log2(e)/sqrt(64) ----
   const int i0 = warp * 32;
   const float qs = LOG2E * 0.125f;
-  uint32_t qa[2][4];
+  uint32_t qa[2][2];
 #pragma unroll
   for (int R = 0; R < 2; ++R) {
-    const float* q0p = base + (long)(i0 + 16 * R + g) * AQKV + h * AD;
-    const float* q1p = q0p + 8 * AQKV;
-    qa[R][0] = tf32(__ldg(q0p + tig) * qs); qa[R][1] = tf32(__ldg(q1p + tig) * qs);
-    qa[R][2] = tf32(__ldg(q0p + tig + 4) * qs); qa[R][3] = tf32(__ldg(q1p + tig + 4) * qs);
+    const float* q0p = base + (long)(i0 + 16 * R + g) * AQKV + h * AD + 2 * tig;
+    const float2 a = __ldg(reinterpret_cast<const float2*>(q0p)), c = __ldg(reinterpret_cast<const float2*>(q0p + 8 * AQKV));
+    qa[R][0] = pack_h2(a.x * qs, a.y * qs);
+    qa[R][1] = pack_h2(c.x * qs, c.y * qs);
   }
   __syncthreads();
   const float zero[4] = {0.f, 0.f, 0.f, 0.f};
   // ---- pass 1: row maxima ----
   float mx[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
   for (int blk = 0; blk < nblk; ++blk) {
-    const float4 k0 = Kf[blk * 64 + lane], k1 = Kf[blk * 64 + 32 + lane];
-    const float kb[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    const uint4 k4 = Kf[blk * 32 + lane];
+    const uint32_t kb[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
     for (int X = 0; X < 4; ++X)
 #pragma unroll
       for (int R = 0; R < 2; ++R) {
         float s[4];
-        mma_tf32(s, qa[R][0], qa[R][1], qa[R][2], qa[R][3], __float_as_uint(kb[2 * X]), __float_as_uint(kb[2 * X + 1]), zero);
+        mma_h8(s, qa[R][0], qa[R][1], kb[X], zero);
         mx[R][0] = fmaxf(mx[R][0], fmaxf(s[0], s[1]));
         mx[R][1] = fmaxf(mx[R][1], fmaxf(s[2], s[3]));
       }
@@ -140,13 +177,14 @@ __global__ void __launch_bounds__(512, 2) attn_fwd_tc_kernel(const float* __rest
       mx[R][hh] = m;
     }
   // ---- pass 2: probabilities, dropout, P.V ----
+  // (measured and dropped here: the maximum in the spare contraction slots of a k = 16 score MMA, as the backward does with the
+  //  log-sum-exp, plus packed f32x2 adds for the row sums: 99 against 96 us per launch -- this kernel is bound by the MUFU
+  //  and ALU pipes at 55-57 % each, not by the register moves in front of the MMA)
   float l[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   for (int blk = 0; blk < nblk; ++blk) {
-    const float4 k0 = Kf[blk * 64 + lane], k1 = Kf[blk * 64 + 32 + lane];
-    const float4 v0 = Vf[blk * 64 + lane], v1 = Vf[blk * 64 + 32 + lane];
-    const float kb[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-    const float vb[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const uint4 k4 = Kf[blk * 32 + lane], v4 = Vf[blk * 32 + lane];
+    const uint32_t kb[4] = {k4.x, k4.y, k4.z, k4.w}, vb[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
     for (int R = 0; R < 2; ++R) {
       const int r0 = i0 + 16 * R + g;
@@ -159,20 +197,23 @@ __global__ void __launch_bounds__(512, 2) attn_fwd_tc_kernel(const float* __rest
         keep0 = drop_bits8(drop, e0);
         keep1 = drop_bits8(drop, e0 + (uint64_t)8 * T);
       }
-      // the row maximum enters as the accumulator input of the score MMA: S - max costs no instruction
+      // the row maximum enters as the accumulator input of the score MMA: S - max costs no arithmetic instruction
       const float negmx[4] = {-mx[R][0], -mx[R][0], -mx[R][1], -mx[R][1]};
 #pragma unroll
-      for (int X = 0; X < 4; ++X) {
-        float s[4];
-        mma_tf32(s, qa[R][0], qa[R][1], qa[R][2], qa[R][3], __float_as_uint(kb[2 * X]), __float_as_uint(kb[2 * X + 1]), negmx);
-        const float p0 = ex2(s[0]), p1 = ex2(s[1]), p2 = ex2(s[2]), p3 = ex2(s[3]);
-        l[R][0] += p0 + p1; l[R][1] += p2 + p3;
-        // this thread's keys of the block: 8tig + 2X (+1)
-        const uint32_t pa0 = (keep0 >> (2 * X)) & 1u ? tf32_fin(p0) : 0u;
-        const uint32_t pa2 = (keep0 >> (2 * X + 1)) & 1u ? tf32_fin(p1) : 0u;
-        const uint32_t pa1 = (keep1 >> (2 * X)) & 1u ? tf32_fin(p2) : 0u;
-        const uint32_t pa3 = (keep1 >> (2 * X + 1)) & 1u ? tf32_fin(p3) : 0u;
-        mma_tf32(o[R], pa0, pa1, pa2, pa3, __float_as_uint(vb[2 * X]), __float_as_uint(vb[2 * X + 1]), o[R]);
+      for (int XP = 0; XP < 2; ++XP) {
+        uint32_t pa[4];
+#pragma unroll
+        for (int xx = 0; xx < 2; ++xx) {
+          const int X = 2 * XP + xx;
+          float s[4];
+          mma_h8(s, qa[R][0], qa[R][1], kb[X], negmx);
+          const float p0 = ex2(s[0]), p1 = ex2(s[1]), p2 = ex2(s[2]), p3 = ex2(s[3]);
+          l[R][0] += p0 + p1; l[R][1] += p2 + p3;
+          // this thread's keys of the block: 8tig + 2X (+1)
+          pa[2 * xx] = pack_h2((keep0 >> (2 * X)) & 1u ? p0 : 0.f, (keep0 >> (2 * X + 1)) & 1u ? p1 : 0.f);
+          pa[2 * xx + 1] = pack_h2((keep1 >> (2 * X)) & 1u ? p2 : 0.f, (keep1 >> (2 * X + 1)) & 1u ? p3 : 0.f);
+        }
+        mma_h16(o[R], pa[0], pa[1], pa[2], pa[3], vb[2 * XP], vb[2 * XP + 1]);
       }
     }
   }
@@ -193,73 +234,93 @@ __global__ void __launch_bounds__(512, 2) attn_fwd_tc_kernel(const float* __rest
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Backward.  grid = B*H, block = (T/64) warps; warp w owns keys [64w, 64w+64) and loops over all query tiles of 8.
-//   S^T = K'.Q^T, dP^T = V.dO^T  (rows = keys)   ->   dV += Pd^T.dO, dK += dS^T.Q  (accumulators in registers)
-//   dQ^T = K'^T.dS^T needs dS^T as a B fragment: staged through a per-warp 64 x 8 shared tile, accumulated over the
-//   warps of the CTA in shared memory (red.shared), written once at the end.  (Measured alternative, round 2: a private
-//   [T][8] dQ slab per warp summed in warp order is bitwise reproducible but needs 105 KB instead of 66 KB of shared memory at
-//   T = 320 -- occupancy 3 -> 2 CTAs per SM -- and ran 2.86 -> 3.49 ms per step; the float atomics stay.)
-// smem: Qs, dOs [T][QS] (TF32), Ls (lse * log2e), Ds (dO.O) [T], dQs [T][8], per-warp staging [64][8], keep bits [T][T/32].
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) attn_bwd_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ out,
-                                                            const float* __restrict__ dout, const float* __restrict__ lse,
-                                                            float* __restrict__ dqkv, int T, Drop drop) {
+__global__ void __maxnreg__(112) attn_bwd_h_kernel(const float* __restrict__ qkv, const float* __restrict__ out,
+                                                           const float* __restrict__ dout, const float* __restrict__ lse,
+                                                           float* __restrict__ dqkv, int T, Drop drop) {
   pdl_sync();
-  extern __shared__ float smb[];
-  float* Qs = smb;
-  float* dOs = Qs + T * QS;
-  float* Ls = dOs + T * QS;
-  float* Ds = Ls + T;
+  extern __shared__ __align__(16) uint8_t smh[];
+  const int TP = T + 8;
+  __half* Qh = reinterpret_cast<__half*>(smh);
+  __half* dOh = Qh + T * 8;
+  __half* QT = dOh + T * 8;
+  __half* dOT = QT + 8 * TP;
+  uint32_t* LB = reinterpret_cast<uint32_t*>(dOT + 8 * TP);   // [T][4]: -lse' as three fp16 terms (words 0, 1), zeros (2, 3)
+  float* Ds = reinterpret_cast<float*>(LB + 4 * T);
   float* dQs = Ds + T;
-  float* stg_all = dQs + T * 8;
-  uint32_t* smask = reinterpret_cast<uint32_t*>(stg_all + (blockDim.x >> 5) * 512);
+  float* red = dQs + T * 8;
+  uint32_t* smask = reinterpret_cast<uint32_t*>(red + 8);
   const bool bitmask = drop.enabled && drop.onebit;
   const int nblk = T >> 5;
   const int bh = blockIdx.x, b = bh / AH, h = bh % AH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+  const int nthr = blockDim.x;                            // T / 2: every thread stages rows tid and tid + T/2
   const float* base = qkv + (long)b * T * AQKV;
-  float* stg = stg_all + warp * 512;
-  // ---- stage Q, dO (TF32), lse', D, zero dQ ----
-  for (int i = tid; i < T; i += blockDim.x) {
-    float q[8], dO[8], o[8];
+  // ---- stage Q (fp16, both layouts), lse', zero dQ; keep dO in registers until its scale is known ----
+  float dOr[2][8], dsum[2];
+  float amax = 0.f;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = tid + r * nthr;
+    float q[8], o[8];
     load8(base + (long)i * AQKV + h * AD, q);
-    load8(dout + ((long)b * T + i) * AE + h * AD, dO);
+    load8(dout + ((long)b * T + i) * AE + h * AD, dOr[r]);
     load8(out + ((long)b * T + i) * AE + h * AD, o);
-    float dsum = 0.f;
+    float ds_ = 0.f;
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
-      dsum = fmaf(dO[d], o[d], dsum);
-      Qs[i * QS + d] = tf32f(q[d]);
-      dOs[i * QS + d] = tf32f(dO[d]);
+      ds_ = fmaf(dOr[r][d], o[d], ds_);
+      amax = fmaxf(amax, fabsf(dOr[r][d]));
+      const __half qh = __float2half_rn(q[d]);
+      Qh[i * 8 + d] = qh;
+      QT[d * TP + i] = qh;
       dQs[i * 8 + d] = 0.f;
     }
-    Ds[i] = dsum;
-    Ls[i] = lse[(long)bh * T + i] * LOG2E;
+    dsum[r] = ds_;
+    uint32_t w0, w1;
+    split3_h(-lse[(long)bh * T + i] * LOG2E, w0, w1);
+    *reinterpret_cast<uint4*>(LB + 4 * i) = make_uint4(w0, w1, 0u, 0u);
   }
+#pragma unroll
+  for (int o_ = 16; o_ > 0; o_ >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o_));
+  if (lane == 0) red[warp] = amax;
   if (bitmask) build_keep_bits(smask, drop, bh, T);
-  // ---- A fragments of this warp's 64 keys ----
+  __syncthreads();
+  amax = red[0];
+  for (int w_ = 1; w_ < (nthr >> 5); ++w_) amax = fmaxf(amax, red[w_]);
+  // power-of-two scale that brings max |dO| into [8, 16)
+  float scale = 1.f, inv = 1.f;
+  if (amax > 1e-30f) {
+    const int e_ = (int)((__float_as_uint(amax) >> 23) & 0xffu) - 127;
+    scale = __uint_as_float((uint32_t)(127 + 3 - e_) << 23);
+    inv = __uint_as_float((uint32_t)(127 - 3 + e_) << 23);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = tid + r * nthr;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      const __half v = __float2half_rn(dOr[r][d] * scale);
+      dOh[i * 8 + d] = v;
+      dOT[d * TP + i] = v;
+    }
+    Ds[i] = dsum[r] * scale;
+  }
+  // ---- A fragments of this warp's 64 keys.  Tile Y: row g <-> key 8g+2Y, row g+8 <-> key 8g+2Y+1 ----
   const int j0 = warp * 64;
   const float ks = LOG2E * 0.125f;
-  uint32_t ka[4][4], va[4][4], kt[8][2];
+  uint32_t ka[4][2], va[4][2], kt[4][2];
 #pragma unroll
   for (int Y = 0; Y < 4; ++Y) {
-    // tile Y: row g <-> key 8g+2Y, row g+8 <-> key 8g+2Y+1
-    const float* k0 = base + (long)(j0 + 8 * g + 2 * Y) * AQKV + 64 + h * AD;
+    const float* k0 = base + (long)(j0 + 8 * g + 2 * Y) * AQKV + 64 + h * AD + 2 * tig;
     const float* k1 = k0 + AQKV;
-    ka[Y][0] = tf32(__ldg(k0 + tig) * ks); ka[Y][1] = tf32(__ldg(k1 + tig) * ks);
-    ka[Y][2] = tf32(__ldg(k0 + tig + 4) * ks); ka[Y][3] = tf32(__ldg(k1 + tig + 4) * ks);
-    const float* v0 = k0 + 64;
-    const float* v1 = k1 + 64;
-    va[Y][0] = tf32(__ldg(v0 + tig)); va[Y][1] = tf32(__ldg(v1 + tig));
-    va[Y][2] = tf32(__ldg(v0 + tig + 4)); va[Y][3] = tf32(__ldg(v1 + tig + 4));
-  }
-  // dQ^T = K'^T . dS^T : A rows = d (g; rows 8..15 are zero), k-step s covers keys 8s..8s+7: a0 = K'[8s+tig][g], a2 = K'[8s+tig+4][g]
-#pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    const float* kr = base + (long)(j0 + 8 * s + tig) * AQKV + 64 + h * AD + g;
-    kt[s][0] = tf32(__ldg(kr) * ks);
-    kt[s][1] = tf32(__ldg(kr + 4 * AQKV) * ks);
+    const float2 a = __ldg(reinterpret_cast<const float2*>(k0)), c = __ldg(reinterpret_cast<const float2*>(k1));
+    ka[Y][0] = pack_h2(a.x * ks, a.y * ks); ka[Y][1] = pack_h2(c.x * ks, c.y * ks);
+    const float2 va_ = __ldg(reinterpret_cast<const float2*>(k0 + 64)), vc_ = __ldg(reinterpret_cast<const float2*>(k1 + 64));
+    va[Y][0] = pack_h2(va_.x, va_.y); va[Y][1] = pack_h2(vc_.x, vc_.y);
+    // dQ = dS . K' : B fragment (n = d = g), contraction index = tile row: 2tig, 2tig+1 <-> keys 16tig+2Y, 16tig+8+2Y; +8 <-> the same + 1
+    const float* kr = base + (long)(j0 + 16 * tig + 2 * Y) * AQKV + 64 + h * AD + g;
+    kt[Y][0] = pack_h2(__ldg(kr) * ks, __ldg(kr + 8 * AQKV) * ks);
+    kt[Y][1] = pack_h2(__ldg(kr + AQKV) * ks, __ldg(kr + 9 * AQKV) * ks);
   }
   float dk[4][4], dv[4][4];
 #pragma unroll
@@ -269,78 +330,79 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_tc_kernel(const float* __rest
   __syncthreads();
   const float zero[4] = {0.f, 0.f, 0.f, 0.f};
   const float dscale = drop.scale;
-  // Cost split of this loop (timing experiments at B = 256, depth 10): the whole dQ product below (8 half-filled MMAs, 16 LDS,
-  // staging stores, the compare-and-swap adds) is 0.77 ms of the 2.88 ms per step; the compare-and-swap adds alone 0.12 ms.
-  // (measured and rejected: starting every warp at a different query block so that the shared-memory compare-and-swap adds of
-  //  dQ do not collide -- 3.16 ms per step against 2.88 ms for the lock-step order)
-  for (int q0 = 0; q0 < T; q0 += 8) {
-    // B fragments: Q^T / dO^T (k = d, n = query)  and  Q / dO (k = query pair of this thread, n = d)
-    const uint32_t qb0 = __float_as_uint(Qs[(q0 + g) * QS + tig]), qb1 = __float_as_uint(Qs[(q0 + g) * QS + tig + 4]);
-    const uint32_t ob0 = __float_as_uint(dOs[(q0 + g) * QS + tig]), ob1 = __float_as_uint(dOs[(q0 + g) * QS + tig + 4]);
-    const uint32_t qc0 = __float_as_uint(Qs[(q0 + 2 * tig) * QS + g]), qc1 = __float_as_uint(Qs[(q0 + 2 * tig + 1) * QS + g]);
-    const uint32_t oc0 = __float_as_uint(dOs[(q0 + 2 * tig) * QS + g]), oc1 = __float_as_uint(dOs[(q0 + 2 * tig + 1) * QS + g]);
-    const float2 L = *reinterpret_cast<const float2*>(Ls + q0 + 2 * tig);
-    const float2 Dq = *reinterpret_cast<const float2*>(Ds + q0 + 2 * tig);
-    // dropout decisions of this thread's 8 keys (8g .. 8g+7 of the warp's 64) for its two queries
-    uint32_t keepa, keepb;
-    if (bitmask) {
-      const int wcol = (j0 >> 5) + (g >> 2), sh = 8 * (g & 3);
-      keepa = (smask[(q0 + 2 * tig) * nblk + wcol] >> sh) & 0xffu;
-      keepb = (smask[(q0 + 2 * tig + 1) * nblk + wcol] >> sh) & 0xffu;
-    } else {
-      keepa = drop_bits8(drop, ((uint64_t)bh * T + (uint64_t)(q0 + 2 * tig)) * (uint64_t)T + (uint64_t)(j0 + 8 * g));
-      keepb = drop_bits8(drop, ((uint64_t)bh * T + (uint64_t)(q0 + 2 * tig + 1)) * (uint64_t)T + (uint64_t)(j0 + 8 * g));
-    }
-    // -lse' of the two query columns enters as the accumulator input of the score MMA (S - lse' costs no instruction)
-    const float negL[4] = {-L.x, -L.y, -L.x, -L.y};
+  const uint32_t kone = tig == 0 ? 0x3c003c00u : tig == 1 ? 0x00003c00u : 0u;   // ones in contraction slots 8, 9, 10 (see split3_h)
+  const uint32_t* Qw = reinterpret_cast<const uint32_t*>(Qh);
+  const uint32_t* Ow = reinterpret_cast<const uint32_t*>(dOh);
+  for (int q0 = 0; q0 < T; q0 += 16) {
+    // B fragments of the two query blocks X = 0, 1 (queries q0 + 8X + ...)
+    uint32_t qb[2], ob[2], qt[2], ot[2], lb[2];
+    float2 Dq[2];
+    uint32_t keep[2][2];                                   // [block][query 2tig + e]: decisions of keys j0 + 8g .. +7
 #pragma unroll
-    for (int Y = 0; Y < 4; ++Y) {
-      float s[4], dp[4];
-      mma_tf32(s, ka[Y][0], ka[Y][1], ka[Y][2], ka[Y][3], qb0, qb1, negL);
-      mma_tf32(dp, va[Y][0], va[Y][1], va[Y][2], va[Y][3], ob0, ob1, zero);
-      // fragment element e: row (key) 8g+2Y+(e>>1), column (query) 2tig+(e&1)
-      const float p0 = ex2(s[0]), p1 = ex2(s[1]), p2 = ex2(s[2]), p3 = ex2(s[3]);
-      const float k0m = (keepa >> (2 * Y)) & 1u ? dscale : 0.f, k1m = (keepb >> (2 * Y)) & 1u ? dscale : 0.f;
-      const float k2m = (keepa >> (2 * Y + 1)) & 1u ? dscale : 0.f, k3m = (keepb >> (2 * Y + 1)) & 1u ? dscale : 0.f;
-      const float pd0 = p0 * k0m, pd1 = p1 * k1m, pd2 = p2 * k2m, pd3 = p3 * k3m;
-      const float ds0 = p0 * (dp[0] * k0m - Dq.x), ds1 = p1 * (dp[1] * k1m - Dq.y);
-      const float ds2 = p2 * (dp[2] * k2m - Dq.x), ds3 = p3 * (dp[3] * k3m - Dq.y);
-      // accumulator fragment -> A fragment (k-index tig <-> query 2tig, tig+4 <-> query 2tig+1)
-      mma_tf32(dv[Y], tf32_fin(pd0), tf32_fin(pd2), tf32_fin(pd1), tf32_fin(pd3), oc0, oc1, dv[Y]);
-      const uint32_t t0 = tf32_fin(ds0), t1 = tf32_fin(ds1), t2 = tf32_fin(ds2), t3 = tf32_fin(ds3);
-      mma_tf32(dk[Y], t0, t2, t1, t3, qc0, qc1, dk[Y]);
-      // stage dS^T[key][query] for the dQ product
-      *reinterpret_cast<float2*>(stg + (8 * g + 2 * Y) * 8 + 2 * tig) = make_float2(__uint_as_float(t0), __uint_as_float(t1));
-      *reinterpret_cast<float2*>(stg + (8 * g + 2 * Y + 1) * 8 + 2 * tig) = make_float2(__uint_as_float(t2), __uint_as_float(t3));
+    for (int X = 0; X < 2; ++X) {
+      const int qq = q0 + 8 * X;
+      qb[X] = Qw[(qq + g) * 4 + tig];                      // (k = d 2tig, 2tig+1 ; n = query g)
+      ob[X] = Ow[(qq + g) * 4 + tig];
+      qt[X] = *reinterpret_cast<const uint32_t*>(QT + g * TP + qq + 2 * tig);    // (k = queries 2tig, 2tig+1 ; n = d g)
+      ot[X] = *reinterpret_cast<const uint32_t*>(dOT + g * TP + qq + 2 * tig);
+      lb[X] = LB[(qq + g) * 4 + tig];                      // (k = 8 + 2tig, 9 + 2tig ; n = query g): -lse' terms against the ones of `kone`
+      Dq[X] = *reinterpret_cast<const float2*>(Ds + qq + 2 * tig);
+      if (bitmask) {
+        const int wcol = (j0 >> 5) + (g >> 2), sh = 8 * (g & 3);
+        keep[X][0] = (smask[(qq + 2 * tig) * nblk + wcol] >> sh) & 0xffu;
+        keep[X][1] = (smask[(qq + 2 * tig + 1) * nblk + wcol] >> sh) & 0xffu;
+      } else {
+        keep[X][0] = drop_bits8(drop, ((uint64_t)bh * T + (uint64_t)(qq + 2 * tig)) * (uint64_t)T + (uint64_t)(j0 + 8 * g));
+        keep[X][1] = drop_bits8(drop, ((uint64_t)bh * T + (uint64_t)(qq + 2 * tig + 1)) * (uint64_t)T + (uint64_t)(j0 + 8 * g));
+      }
     }
-    __syncwarp();
     float dq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int s8 = 0; s8 < 8; ++s8) {
-      const uint32_t b0 = __float_as_uint(stg[(8 * s8 + tig) * 8 + g]), b1 = __float_as_uint(stg[(8 * s8 + tig + 4) * 8 + g]);
-      mma_tf32(dq, kt[s8][0], 0u, kt[s8][1], 0u, b0, b1, dq);
+    for (int Y = 0; Y < 4; ++Y) {
+      uint32_t pa[2][2], sa[2][2];                         // Pd and dS as A fragments: [block][rows g / g+8]
+#pragma unroll
+      for (int X = 0; X < 2; ++X) {
+        float s[4], dp[4];
+        mma_h16z(s, ka[Y][0], ka[Y][1], kone, kone, qb[X], lb[X]);
+        mma_h8(dp, va[Y][0], va[Y][1], ob[X], zero);
+        // element e: row (key) 8g+2Y+(e>>1), column (query) 2tig+(e&1)
+        const float p0 = ex2(s[0]), p1 = ex2(s[1]), p2 = ex2(s[2]), p3 = ex2(s[3]);
+        const float m0 = (keep[X][0] >> (2 * Y)) & 1u ? dscale : 0.f, m1 = (keep[X][1] >> (2 * Y)) & 1u ? dscale : 0.f;
+        const float m2 = (keep[X][0] >> (2 * Y + 1)) & 1u ? dscale : 0.f, m3 = (keep[X][1] >> (2 * Y + 1)) & 1u ? dscale : 0.f;
+        pa[X][0] = pack_h2(p0 * m0, p1 * m1);
+        pa[X][1] = pack_h2(p2 * m2, p3 * m3);
+        sa[X][0] = pack_h2(p0 * fmaf(dp[0], m0, -Dq[X].x), p1 * fmaf(dp[1], m1, -Dq[X].y));
+        sa[X][1] = pack_h2(p2 * fmaf(dp[2], m2, -Dq[X].x), p3 * fmaf(dp[3], m3, -Dq[X].y));
+      }
+      mma_h16(dv[Y], pa[0][0], pa[0][1], pa[1][0], pa[1][1], ot[0], ot[1]);
+      mma_h16(dk[Y], sa[0][0], sa[0][1], sa[1][0], sa[1][1], qt[0], qt[1]);
+      // dQ (16 queries x 8 dims) += dS (queries x this tile's 16 keys) . K': the transposed dS fragments of both blocks fill all 16 rows
+      mma_h16(dq, movm_t(sa[0][0]), movm_t(sa[1][0]), movm_t(sa[0][1]), movm_t(sa[1][1]), kt[Y][0], kt[Y][1]);
     }
-    __syncwarp();
-    // dq[0], dq[1] = dQ'[query 2tig, 2tig+1][d = g] (rows 8..15 of the tile are padding)
-    atomicAdd(dQs + (q0 + 2 * tig) * 8 + g, dq[0]);
-    atomicAdd(dQs + (q0 + 2 * tig + 1) * 8 + g, dq[1]);
+    // dq[0], dq[1] = dQ'[query q0 + g][d = 2tig, 2tig+1];  dq[2], dq[3]: query q0 + 8 + g
+    atomicAdd(dQs + (q0 + g) * 8 + 2 * tig, dq[0]);
+    atomicAdd(dQs + (q0 + g) * 8 + 2 * tig + 1, dq[1]);
+    atomicAdd(dQs + (q0 + 8 + g) * 8 + 2 * tig, dq[2]);
+    atomicAdd(dQs + (q0 + 8 + g) * 8 + 2 * tig + 1, dq[3]);
   }
   // ---- dK, dV of this warp's keys ----
+  const float sk = 0.125f * inv;
 #pragma unroll
   for (int Y = 0; Y < 4; ++Y) {
     float* r0 = dqkv + ((long)b * T + j0 + 8 * g + 2 * Y) * AQKV + h * AD + 2 * tig;
     float* r1 = r0 + AQKV;
-    *reinterpret_cast<float2*>(r0 + 64) = make_float2(dk[Y][0] * 0.125f, dk[Y][1] * 0.125f);
-    *reinterpret_cast<float2*>(r1 + 64) = make_float2(dk[Y][2] * 0.125f, dk[Y][3] * 0.125f);
-    *reinterpret_cast<float2*>(r0 + 128) = make_float2(dv[Y][0], dv[Y][1]);
-    *reinterpret_cast<float2*>(r1 + 128) = make_float2(dv[Y][2], dv[Y][3]);
+    *reinterpret_cast<float2*>(r0 + 64) = make_float2(dk[Y][0] * sk, dk[Y][1] * sk);
+    *reinterpret_cast<float2*>(r1 + 64) = make_float2(dk[Y][2] * sk, dk[Y][3] * sk);
+    *reinterpret_cast<float2*>(r0 + 128) = make_float2(dv[Y][0] * inv, dv[Y][1] * inv);
+    *reinterpret_cast<float2*>(r1 + 128) = make_float2(dv[Y][2] * inv, dv[Y][3] * inv);
   }
   __syncthreads();
   // dQ = ln2 * sum over warps (K' carries log2e/8)
+  const float sq = LN2 * inv;
   for (int i = tid; i < T * 2; i += blockDim.x) {
     const int t = i >> 1, half = i & 1;
     float4 v = *reinterpret_cast<const float4*>(dQs + t * 8 + half * 4);
-    v.x *= LN2; v.y *= LN2; v.z *= LN2; v.w *= LN2;
+    v.x *= sq; v.y *= sq; v.z *= sq; v.w *= sq;
     *reinterpret_cast<float4*>(dqkv + ((long)b * T + t) * AQKV + h * AD + half * 4) = v;
   }
 }
@@ -350,15 +412,14 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_tc_kernel(const float* __rest
 inline bool attention_tc_supported(int T) { return T >= 64 && (T % 64) == 0 && T <= 512; }
 
 inline int attention_fwd_tc(const float* qkv, float* out, float* lse, int B, int T, const Drop& drop, cudaStream_t st) {
-  const size_t smem = (size_t)(T / 32) * 64 * 2 * sizeof(float4) + (size_t)T * T / 8;
+  const size_t smem = (size_t)T * 2 * sizeof(uint4) + (size_t)T * T / 8;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attntc::attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
-      return EEGCLIP_ERR_CUDA;
+    if (cudaFuncSetAttribute(attntc::attn_fwd_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess) return EEGCLIP_ERR_CUDA;   // T = 512: 48 KB
     configured = true;
   }
   ProfScope prof(PROF_ATTN_FWD, st);
-  LAUNCH_PDL((attntc::attn_fwd_tc_kernel), B * AH, (T / 32) * 32, smem, st, qkv, out, lse, T, drop);
+  LAUNCH_PDL((attntc::attn_fwd_h_kernel), B * AH, (T / 32) * 32, smem, st, qkv, out, lse, T, drop);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -366,15 +427,15 @@ inline int attention_fwd_tc(const float* qkv, float* out, float* lse, int B, int
 inline int attention_bwd_tc(const float* qkv, const float* out, const float* dout, const float* lse, float* dqkv, int B, int T,
                             const Drop& drop, cudaStream_t st) {
   const int warps = T / 64;
-  const size_t smem = ((size_t)T * (2 * attntc::QS + 2 + 8) + (size_t)warps * 512) * sizeof(float) + (size_t)T * T / 8;
+  const size_t smem = (size_t)(16 * T + 16 * (T + 8)) * 2 + (size_t)(13 * T + 8) * sizeof(float) + (size_t)T * T / 8;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attntc::attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024) != cudaSuccess)   // T = 512: 118.8 KB
+    if (cudaFuncSetAttribute(attntc::attn_bwd_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)   // T = 512: 92.4 KB
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
   ProfScope prof(PROF_ATTN_BWD, st);
-  LAUNCH_PDL((attntc::attn_bwd_tc_kernel), B * AH, warps * 32, smem, st, qkv, out, dout, lse, dqkv, T, drop);
+  LAUNCH_PDL((attntc::attn_bwd_h_kernel), B * AH, warps * 32, smem, st, qkv, out, dout, lse, dqkv, T, drop);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
