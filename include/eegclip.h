@@ -100,7 +100,8 @@ EEGCLIP_API long long eegclip_launch_count(void);
  *   0 token-GEMM ring depth (2..3)          1 activation load policy (1 = __ldg)      3 force the generic token-GEMM instantiation
  *   4 producer / epilogue warp split rule   7 1 = no programmatic dependent launch    8 bit mask of kernel classes that record
  *   profiling events (0 = all)              9 1 = register-staged token weight gradient
- *  10 ln64 backward rows per CTA           11 column-sum rows per CTA               13 1 = token-GEMM producers load 2 x 128 bit
+ *  10 ln64 backward rows per CTA           11 column-sum rows per CTA               12 1 = strided weight-gradient operands by
+ *      per-row bulk copies instead of 2-D tensor maps (A/B timing)             13 1 = token-GEMM producers load 2 x 128 bit
  *      instead of 1 x 256 bit per lane (A/B timing)
  * (the Python layer reads EEGCLIP_TUNE="key=value,..." from the environment at load time).
  * THREADING: the knobs, the launch counter and the profiling state are PROCESS-GLOBAL development state, written without

@@ -24,6 +24,7 @@
 //
 // Arithmetic: NTERMS = 3 -> split-bf16 (hi*hi + hi*lo + lo*hi, fp32 accumulate); NTERMS = 1 -> plain bf16.
 #pragma once
+#include <string.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -1002,7 +1003,8 @@ inline uint32_t wgrad2_smem_bytes(int Nout, int Kin) {
 }
 
 template <int NTERMS, int PDY, int PX, int WDB>
-__global__ void __launch_bounds__(W2_THREADS, 1) lin_wgrad_tma_kernel(const LinWgradArgs a) {
+__global__ void __launch_bounds__(W2_THREADS, 1) lin_wgrad_tma_kernel(const LinWgradArgs a, const __grid_constant__ CUtensorMap tm_dy,
+                                                                      const __grid_constant__ CUtensorMap tm_x, const int use_tm) {
   pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1060,14 +1062,19 @@ __global__ void __launch_bounds__(W2_THREADS, 1) lin_wgrad_tma_kernel(const LinW
       dbg_mark(dbgt, 2, dnt, 30);
       const long r0 = (long)(st_beg + it) * WT2;
       const int rows = (int)min((long)WT2, (long)a.M - r0);
-      if (lane == 0) tc::mbar_expect_tx(&lfull[ls], (uint32_t)rows * (uint32_t)(Nout + Kin) * 4u);
+      // a dense operand (leading dimension == width) is one 1-D bulk copy per stage; a strided one (column block of a wider
+      // tensor: speech features, LSTM gate / state buffers) is ONE tensor-map copy of the 32-row box (rows past M arrive as
+      // zeros and count for the transaction bytes).  (Without a tensor map: one copy per row, 32 requests per stage -- the copy
+      // engine is request-bound there, and with both operands strided the register-staged kernel had to take over.)
+      const bool tm_d = (use_tm & 1) != 0, tm_xx = (use_tm & 2) != 0;
+      if (lane == 0) tc::mbar_expect_tx(&lfull[ls], (uint32_t)(tm_d ? WT2 : rows) * (uint32_t)Nout * 4u + (uint32_t)(tm_xx ? WT2 : rows) * (uint32_t)Kin * 4u);
       __syncwarp();
-      // a dense operand (leading dimension == width) is one copy per stage, a strided one (column block of a wider tensor:
-      // speech features, LSTM gate buffers) one copy per row, issued by the lane that owns the row
       uint8_t* ld = sL + ls * LSTAGE;
-      if (dense_dy) { if (lane == 0) tc::bulk_g2s(ld, a.dy + r0 * Nout, (uint32_t)rows * (uint32_t)Nout * 4u, &lfull[ls]); }
+      if (tm_d) { if (lane == 0) tc::tma_load_2d(ld, &tm_dy, 0, (int)r0, &lfull[ls]); }
+      else if (dense_dy) { if (lane == 0) tc::bulk_g2s(ld, a.dy + r0 * Nout, (uint32_t)rows * (uint32_t)Nout * 4u, &lfull[ls]); }
       else if (lane < rows) tc::bulk_g2s(ld + (uint32_t)lane * Nout * 4u, a.dy + (r0 + lane) * a.lddy, (uint32_t)Nout * 4u, &lfull[ls]);
-      if (dense_x) { if (lane == 0) tc::bulk_g2s(ld + LD_BYTES, a.x + r0 * Kin, (uint32_t)rows * (uint32_t)Kin * 4u, &lfull[ls]); }
+      if (tm_xx) { if (lane == 0) tc::tma_load_2d(ld + LD_BYTES, &tm_x, (int)blockIdx.y * Kin, (int)r0, &lfull[ls]); }
+      else if (dense_x) { if (lane == 0) tc::bulk_g2s(ld + LD_BYTES, a.x + r0 * Kin, (uint32_t)rows * (uint32_t)Kin * 4u, &lfull[ls]); }
       else if (lane < rows) tc::bulk_g2s(ld + LD_BYTES + (uint32_t)lane * Kin * 4u, a.x + (r0 + lane) * a.ldx + (long)blockIdx.y * Kin, (uint32_t)Kin * 4u, &lfull[ls]);
       __syncwarp();
     }
@@ -1319,22 +1326,21 @@ inline int lin_wgrad_launch_v(const LinWgradArgs& a, dim3 grid, uint32_t smem, c
   return EEGCLIP_OK;
 }
 
-// the bulk-copy kernel takes dense operands (a stage is one contiguous block); g_tune[9] = 1 forces the register-staged kernel
+// the bulk-copy kernel: dense operands arrive as one 1-D bulk copy per stage, strided ones through a 2-D tensor map;
+// g_tune[9] = 1 forces the register-staged kernel, g_tune[12] = 1 the per-row copies (A/B timing)
 inline bool lin_wgrad_tma_ok(const LinWgradArgs& a) {
-  // at most one strided operand: per-row copies of BOTH would be 64 requests per stage (request-bound in the copy engine)
-  const bool dense_dy = a.lddy == a.Nout, dense_x = a.ldx == a.Kin;
   return g_tune[9] == 0 && ((uintptr_t)a.dy & 15) == 0 && ((uintptr_t)a.x & 15) == 0 && (a.lddy & 3) == 0 && (a.ldx & 3) == 0 &&
-         (dense_dy || dense_x) && wgrad2_smem_bytes(a.Nout, a.Kin) <= 227u * 1024u;
+         wgrad2_smem_bytes(a.Nout, a.Kin) <= 227u * 1024u;
 }
 template <int NTERMS, int PDY, int PX, int WDB>
-inline int lin_wgrad_tma_launch_v(const LinWgradArgs& a, dim3 grid, cudaStream_t st) {
+inline int lin_wgrad_tma_launch_v(const LinWgradArgs& a, dim3 grid, cudaStream_t st, const CUtensorMap& tm_dy, const CUtensorMap& tm_x, int use_tm) {
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(lin_wgrad_tma_kernel<NTERMS, PDY, PX, WDB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
-  LAUNCH_PDL((lin_wgrad_tma_kernel<NTERMS, PDY, PX, WDB>), grid, W2_THREADS, wgrad2_smem_bytes(a.Nout, a.Kin), st, a);
+  LAUNCH_PDL((lin_wgrad_tma_kernel<NTERMS, PDY, PX, WDB>), grid, W2_THREADS, wgrad2_smem_bytes(a.Nout, a.Kin), st, a, tm_dy, tm_x, use_tm);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
@@ -1353,11 +1359,25 @@ inline int lin_wgrad_launch_t(LinWgradArgs a, float* const dW[3], float* const d
     const dim3 grid(ctas, kin_blocks);
     const uint32_t smem = wgrad_lin_smem_bytes(a.Nout, a.Kin);
     int rc;
-    if (lin_wgrad_tma_ok(a)) {
-      if (a.pro_x == PRO_NONE && a.pro_dy == PRO_NONE && !a.want_db) rc = lin_wgrad_tma_launch_v<NTERMS, PRO_NONE, PRO_NONE, 0>(a, grid, st);
-      else if (a.pro_x == PRO_NONE && a.pro_dy == PRO_NONE && a.want_db) rc = lin_wgrad_tma_launch_v<NTERMS, PRO_NONE, PRO_NONE, 1>(a, grid, st);
-      else if (a.pro_x == PRO_NONE && a.pro_dy == PRO_DROP && a.want_db) rc = lin_wgrad_tma_launch_v<NTERMS, PRO_DROP, PRO_NONE, 1>(a, grid, st);
-      else rc = lin_wgrad_tma_launch_v<NTERMS, -1, -1, -1>(a, grid, st);
+    // strided operands: one tensor map each (host-side encode, no device work); both strided without maps -> register-staged kernel
+    alignas(64) CUtensorMap tm_dy, tm_x;
+    memset(&tm_dy, 0, sizeof(tm_dy)); memset(&tm_x, 0, sizeof(tm_x));
+    int use_tm = 0;
+    bool tma = lin_wgrad_tma_ok(a);
+    if (tma) {
+      const bool dense_dy = a.lddy == a.Nout, dense_x = a.ldx == a.Kin && kin_blocks == 1;
+      if (g_tune[12] == 0) {
+        if (!dense_dy && tc::make_tmap_2d_f32(&tm_dy, a.dy, (uint64_t)a.Nout, (uint64_t)a.M, (uint64_t)a.lddy, (uint32_t)a.Nout, WT2) == 0) use_tm |= 1;
+        if (!dense_x && tc::make_tmap_2d_f32(&tm_x, a.x, (uint64_t)a.Kin * kin_blocks, (uint64_t)a.M, (uint64_t)a.ldx, (uint32_t)a.Kin, WT2) == 0) use_tm |= 2;
+      }
+      const bool row_dy = !dense_dy && !(use_tm & 1), row_x = !dense_x && !(use_tm & 2);
+      if (row_dy && row_x) tma = false;                    // per-row copies of BOTH operands: 64 requests per stage
+    }
+    if (tma) {
+      if (a.pro_x == PRO_NONE && a.pro_dy == PRO_NONE && !a.want_db) rc = lin_wgrad_tma_launch_v<NTERMS, PRO_NONE, PRO_NONE, 0>(a, grid, st, tm_dy, tm_x, use_tm);
+      else if (a.pro_x == PRO_NONE && a.pro_dy == PRO_NONE && a.want_db) rc = lin_wgrad_tma_launch_v<NTERMS, PRO_NONE, PRO_NONE, 1>(a, grid, st, tm_dy, tm_x, use_tm);
+      else if (a.pro_x == PRO_NONE && a.pro_dy == PRO_DROP && a.want_db) rc = lin_wgrad_tma_launch_v<NTERMS, PRO_DROP, PRO_NONE, 1>(a, grid, st, tm_dy, tm_x, use_tm);
+      else rc = lin_wgrad_tma_launch_v<NTERMS, -1, -1, -1>(a, grid, st, tm_dy, tm_x, use_tm);
     } else
     if (g_tune[3] == 0 && a.pro_x == PRO_NONE && a.pro_dy == PRO_NONE && !a.want_db) rc = lin_wgrad_launch_v<NTERMS, PRO_NONE, PRO_NONE, 0>(a, grid, smem, st);
     else if (g_tune[3] == 0 && a.pro_x == PRO_NONE && a.pro_dy == PRO_NONE && a.want_db) rc = lin_wgrad_launch_v<NTERMS, PRO_NONE, PRO_NONE, 1>(a, grid, smem, st);

@@ -10,6 +10,7 @@
 // and a row shift of the whole operand is a +16 B shift of the descriptor start address -- which is what makes
 // the 64 taps of Conv1d('same') 64 descriptors over one resident activation tile.
 #pragma once
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched from the driver at run time, nothing links libcuda)
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -60,6 +61,34 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- tensor-map TMA (cp.async.bulk.tensor): a strided 2-D fp32 tile in ONE copy ---------------------------------
+// View of `cols` x `rows` elements at `base` with a row pitch of `ld` elements; box = box_cols x box_rows, no swizzle (the box
+// lands row-major and dense), out-of-range rows are zero-filled and still count for the transaction bytes.
+inline int make_tmap_2d_f32(CUtensorMap* tm, const float* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return -1;
+    fn = reinterpret_cast<EncodeFn>(p);
+  }
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstr[1] = {ld * 4};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? 0
+             : -1;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tm, int col0, int row0, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst_smem)),
+               "l"(tm), "r"(col0), "r"(row0), "r"(smem_u32(bar))
                : "memory");
 }
 
