@@ -64,9 +64,11 @@ constexpr int LGS = 8 * LH;                                          // row stri
 //             step and CTA); one cluster barrier per step (planes double buffered).
 //   backward: split over K: CTA r contracts over ITS 256 gate rows (its units' da, produced locally -- no da exchange) for
 //             all 128 units and sends the half of the partial dh_{t-1} that the peer owns (2 KB per step, DSMEM).
-// Global accesses are per-thread 32-byte pieces (8 loads + 14 stores per thread and step forward, 12 + 8 backward), issued
-// BETWEEN the cluster barrier's arrive and wait: the arrive's release waits for every earlier write of the thread, and with
-// the global stores in front of it every step paid their ~0.8 us round trip.
+// The hand-over is st.async + mbarrier (the DSMEM store itself signals the destination CTA's barrier with its byte count), one
+// CTA-local __syncthreads and one mbarrier wait per step.  With st.shared::cluster + barrier.cluster the arrive's release
+// waited for EVERY memory operation of the thread in flight, the step's global loads / stores included: 0.85 us of a 1.85 us
+// step, 0.45 us of 1.4 us with the stores moved behind the arrive.  Global accesses are per-thread 32-byte pieces (8 loads +
+// 14 stores per thread and step forward, 12 + 8 backward).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t map_peer(const void* p, uint32_t rank) {
@@ -76,6 +78,14 @@ __device__ __forceinline__ uint32_t map_peer(const void* p, uint32_t rank) {
 }
 __device__ __forceinline__ void st_cluster_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory"); }
 __device__ __forceinline__ void st_cluster_f32x2(uint32_t addr, float a, float b) { asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory"); }
+// DSMEM store that signals the DESTINATION CTA's mbarrier with its byte count (st.async): the hand-over needs no release
+// fence on the sending thread, so the thread's global loads / stores in flight do not hold the step
+__device__ __forceinline__ void st_async_b32(uint32_t addr, uint32_t v, uint32_t mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(v), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_f32x2(uint32_t addr, float a, float b, uint32_t mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(addr), "f"(a), "f"(b), "r"(mbar) : "memory");
+}
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
@@ -91,7 +101,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     if (dbgp && dbn < 120) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); dbgp[2 * dbn] = (unsigned long long)ev; dbgp[2 * dbn + 1] = t_; ++dbn; dbgp[255] = (unsigned long long)dbn; }
   };
   __shared__ __align__(16) uint4 hbuf[2 * 2 * 128];        // h planes: [buffer][hi, lo][128 uint4], all 128 units
+  __shared__ __align__(8) uint64_t hbar[2];                // per buffer: the peer's 2 KB of h have landed
   const uint32_t rank = cluster_rank();
+  if (threadIdx.x == 0) { tc::mbar_init(&hbar[0], 1); tc::mbar_init(&hbar[1], 1); tc::mbar_fence_init(); }
   const int dir = blockIdx.y, b0 = (blockIdx.x >> 1) * LMS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
   const float* W = dir ? w_hh_r : w_hh_f;
@@ -112,9 +124,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     }
   }
   for (int i = tid; i < 2 * 2 * 128; i += 256) hbuf[i] = make_uint4(0u, 0u, 0u, 0u);
-  // h of (unit u, sequence n) lives at bf16 index (((u % 32) / 8 * 8 + n) * 4 + u / 32) * 8 + u % 8 of a plane
-  const int hoff = (((warp & 3) * 8 + 2 * tig) * 4 + 2 * (int)rank + (warp >> 2)) * 8 + g;      // + e * 32 (bf16 elements)
-  const uint32_t hpeer = map_peer(hbuf, rank ^ 1u) + 2u * (uint32_t)hoff;
+  // h of (unit u, sequence n) lives at bf16 index (((u % 32) / 8 * 8 + n) * 4 + u / 32) * 8 + u % 8 of a plane.  Lane pairs
+  // (g even / odd = adjacent units) swap one sequence each, so a thread writes ONE 32-bit word (units u & ~1, u | 1) per plane
+  // of sequence 2tig + (g & 1) -- st.async moves 32-bit words
+  const int hword = ((((warp & 3) * 8 + 2 * tig + (g & 1)) * 4 + 2 * (int)rank + (warp >> 2)) * 8 + (g & 6)) >> 1;   // 32-bit word index in a plane
+  const uint32_t hpeer = map_peer(hbuf, rank ^ 1u) + 4u * (uint32_t)hword;
+  const uint32_t bpeer = map_peer(hbar, rank ^ 1u);
   const bool live0 = b0 + 2 * tig < B, live1 = b0 + 2 * tig + 1 < B;
   const int t0 = dir ? T - 1 : 0;
   const long dstep = dir ? -1 : 1;
@@ -124,17 +139,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
   long so1 = ((long)(live1 ? b0 + 2 * tig + 1 : b0) * T + t0) * 256 + dir * LH + unit;
   float c[2] = {0.f, 0.f}, hprev[2] = {0.f, 0.f};
   // x-projection (+ biases) in accumulator order: [tile p][j] = (gate 2p + (j >> 1), sequence 2 tig + (j & 1))
-  float ngx[2][4];
-  auto fetch = [&](const float* p0, const float* p1) {
+  // Loaded TWO steps ahead into two register sets (even / odd steps): a step is ~1.3 us, a 32-byte global load under this
+  // access pattern takes about as long, and with a one-step look-ahead every step waited for its x-projection.
+  float gxa[2][4], gxb[2][4];
+  auto fetch = [&](float (&dst)[2][4], const float* p0, const float* p1) {
 #pragma unroll
     for (int p = 0; p < 2; ++p)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ngx[p][j] = ((j & 1) ? p1 : p0)[(2 * p + (j >> 1)) * LH];
+      for (int j = 0; j < 4; ++j) dst[p][j] = ((j & 1) ? p1 : p0)[(2 * p + (j >> 1)) * LH];
   };
-  fetch(gq0, gq1);
+  fetch(gxa, gq0, gq1);
+  {
+    const long nd = T > 1 ? dstep * LGS : 0;
+    fetch(gxb, gq0 + nd, gq1 + nd);
+  }
   cluster_sync_all();                                      // both CTAs' planes are zeroed before anyone writes remotely
-  for (int step = 0; step < T; ++step) {
+  auto do_step = [&](const int step, float (&ngx)[2][4]) {
     stamp(0);
+    if (tid == 0) tc::mbar_expect_tx(&hbar[(step + 1) & 1], 2048);   // this step's h of the peer: 256 threads x 2 words
     const uint4* hh = hbuf + (step & 1) * 256;
     const uint4* hl = hh + 128;
     float acc[2][2][4];                                    // [tile][hi.hi (+ x-projection), hi.lo + lo.hi]
@@ -143,8 +165,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 #pragma unroll
       for (int j = 0; j < 4; ++j) { acc[p][0][j] = ngx[p][j]; acc[p][1][j] = 0.f; }
     {
-      const long nd = step + 1 < T ? dstep * LGS : 0;      // the last step re-reads its own row (unused)
-      fetch(gq0 + nd, gq1 + nd);
+      const long nd = step + 2 < T ? 2 * dstep * LGS : 0;  // past the end: re-read a valid row (unused)
+      fetch(ngx, gq0 + nd, gq1 + nd);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -176,18 +198,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     {
       uint32_t hi, lo;
       split_pair(hn[0], hn[1], hi, lo);
-      // (measured: forwarding the 16 completed uint4 of the warp as 16-byte DSMEM stores from 16 lanes instead of four 2-byte
-      //  stores per thread made the step SLOWER: 646 against 438 us for the 320 steps)
-      const int nb = ((step + 1) & 1) * 256 * 16;           // byte offset of the next step's buffer
-      uint16_t* nh = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(hbuf) + nb) + hoff;
-      nh[0] = (uint16_t)(hi & 0xffffu); nh[32] = (uint16_t)(hi >> 16);
-      nh[128 * 8] = (uint16_t)(lo & 0xffffu); nh[128 * 8 + 32] = (uint16_t)(lo >> 16);
-      const uint32_t pa = hpeer + (uint32_t)nb;
-      st_cluster_u16(pa, hi & 0xffffu); st_cluster_u16(pa + 64, hi >> 16);
-      st_cluster_u16(pa + 2048, lo & 0xffffu); st_cluster_u16(pa + 2048 + 64, lo >> 16);
+      const uint32_t phi = __shfl_xor_sync(0xffffffffu, hi, 4), plo = __shfl_xor_sync(0xffffffffu, lo, 4);
+      // even g: sequence 2tig of units (u, u+1) = (own low half, partner's low half); odd g: sequence 2tig+1 of (u-1, u)
+      const uint32_t whi = (g & 1) ? __byte_perm(phi, hi, 0x7632) : __byte_perm(hi, phi, 0x5410);
+      const uint32_t wlo = (g & 1) ? __byte_perm(plo, lo, 0x7632) : __byte_perm(lo, plo, 0x5410);
+      const int nbuf = (step + 1) & 1;
+      uint32_t* nh = reinterpret_cast<uint32_t*>(hbuf + nbuf * 256) + hword;
+      nh[0] = whi;
+      nh[128 * 4] = wlo;
+      const uint32_t pa = hpeer + (uint32_t)(nbuf * 256 * 16), pb = bpeer + 8u * (uint32_t)nbuf;
+      st_async_b32(pa, whi, pb);
+      st_async_b32(pa + 2048, wlo, pb);
     }
     stamp(3);
-    cluster_arrive();
+    // (history: with st.shared::cluster + barrier.cluster the arrive's release waited for every global load / store of the
+    //  thread in flight: 0.45 us of a 1.4 us step even with the stores moved behind the arrive)
     if (live0) {
       gq0[0] = gi[0]; gq0[LH] = gf[0]; gq0[2 * LH] = gg[0]; gq0[3 * LH] = go[0];
       out[so0] = hn[0]; Cs[so0] = cn[0]; Hp[so0] = hprev[0];
@@ -199,8 +224,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     hprev[0] = hn[0]; hprev[1] = hn[1];
     gq0 += dstep * LGS; gq1 += dstep * LGS; so0 += dstep * 256; so1 += dstep * 256;
     stamp(4);
-    cluster_wait();
+    __syncthreads();                                       // this CTA's half of h_t is in its planes
+    tc::mbar_wait(&hbar[(step + 1) & 1], (step >> 1) & 1);   // ... and the peer's half (each barrier completes every other step)
+  };
+  for (int step = 0; step < T; step += 2) {
+    do_step(step, gxa);
+    if (step + 1 < T) do_step(step + 1, gxb);
   }
+  cluster_sync_all();                                      // neither CTA leaves while the other may still address it
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
@@ -209,7 +240,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
   pdl_sync();
   __shared__ __align__(16) uint4 dbuf[2 * 256];            // da planes of this CTA's 256 gate rows: [hi, lo][256 uint4]
   __shared__ __align__(16) float dhx[2 * 2 * 64 * 8];      // partial dh_{t-1} of this CTA's units: [buffer][own, peer's][unit 64][sequence 8]
+  __shared__ __align__(8) uint64_t dbar[2];                // per buffer: the peer's 2 KB of partial sums have landed
   const uint32_t rank = cluster_rank();
+  if (threadIdx.x == 0) { tc::mbar_init(&dbar[0], 1); tc::mbar_init(&dbar[1], 1); tc::mbar_fence_init(); }
   const int dir = blockIdx.y, b0 = (blockIdx.x >> 1) * LMS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
   const float* W = dir ? w_hh_r : w_hh_f;
@@ -236,6 +269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
   const bool mine = (uint32_t)(warp >> 2) == rank;
   const int poff = (mine ? 0 : 64 * 8) + (16 * (warp & 3) + g) * 8 + 2 * tig;          // + 64 for the second row; [own, peer's] halves
   const uint32_t ppeer = map_peer(dhx, rank ^ 1u) + 4u * (uint32_t)poff;
+  const uint32_t bpeer = map_peer(dbar, rank ^ 1u);
   const bool live0 = b0 + 2 * tig < B, live1 = b0 + 2 * tig + 1 < B;
   const int t0 = dir ? 0 : T - 1;                                                   // reverse of the forward order
   const long dstep = dir ? 1 : -1;
@@ -243,20 +277,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
                   G + ((long)(live1 ? b0 + 2 * tig + 1 : b0) * T + t0) * LGS + dir * LG + unit};
   long so[2] = {((long)(live0 ? b0 + 2 * tig : b0) * T + t0) * 256 + dir * LH + unit,
                 ((long)(live1 ? b0 + 2 * tig + 1 : b0) * T + t0) * 256 + dir * LH + unit};
-  float dc[2] = {0.f, 0.f}, ct[2], n_g[2][4], n_cp[2], n_dy[2];
-  auto fetch = [&](float* const* gp, const long* o, bool has_prev) {
+  // saved state of a step: [e][gate 0..3, dy, c_{t-1}], loaded two steps ahead into two register sets (see the forward kernel);
+  // `ahead` = steps past the cursors, `has_prev`: a forward-earlier step exists for that step
+  float dc[2] = {0.f, 0.f}, ct[2], sva[2][6], svb[2][6];
+  auto fetch = [&](float (&dst)[2][6], long ahead, bool has_prev) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
 #pragma unroll
-      for (int gt = 0; gt < 4; ++gt) n_g[e][gt] = gp[e][gt * LH];
-      n_dy[e] = dout[o[e]];
-      n_cp[e] = has_prev ? Cs[o[e] + dstep * 256] : 0.f;
+      for (int gt = 0; gt < 4; ++gt) dst[e][gt] = gq[e][ahead * dstep * LGS + gt * LH];
+      dst[e][4] = dout[so[e] + ahead * dstep * 256];
+      dst[e][5] = has_prev ? Cs[so[e] + (ahead + 1) * dstep * 256] : 0.f;
     }
   };
   ct[0] = Cs[so[0]]; ct[1] = Cs[so[1]];
-  fetch(gq, so, T > 1);
+  fetch(sva, 0, T > 1);
+  fetch(svb, T > 1 ? 1 : 0, T > 2);
   cluster_sync_all();
-  for (int step = 0; step < T; ++step) {
+  auto do_step = [&](const int step, float (&sv)[2][6]) {
+    if (tid == 0) tc::mbar_expect_tx(&dbar[(step + 1) & 1], 2048);   // the peer's four non-owner warps x 32 lanes x 2 x 8 bytes
     // ---- gate phase: da of this thread's 2 pairs ----
     const float* dx = dhx + (step & 1) * 2 * 64 * 8 + lu * 8 + 2 * tig;
     const float2 d_own = *reinterpret_cast<const float2*>(dx), d_peer = *reinterpret_cast<const float2*>(dx + 64 * 8);
@@ -264,8 +302,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     float da[2][4];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const float gi = n_g[e][0], gf = n_g[e][1], gg = n_g[e][2], go = n_g[e][3], cp = n_cp[e];
-      const float dht = n_dy[e] + dhv[e];
+      const float gi = sv[e][0], gf = sv[e][1], gg = sv[e][2], go = sv[e][3], cp = sv[e][5];
+      const float dht = sv[e][4] + dhv[e];
       const float tc = tanh_fast(ct[e]);
       const float dct = fmaf(dht * go, fmaf(-tc, tc, 1.f), dc[e]);
       da[e][0] = dct * gg * gi * (1.f - gi);
@@ -275,12 +313,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
       dc[e] = dct * gf;
       ct[e] = cp;                                          // c_{t-1} is the next step's c_t
     }
-    float* const gw0 = gq[0];                              // this step's rows: da is stored after the cluster arrive (below)
-    float* const gw1 = gq[1];
-    if (step + 1 < T) {                                    // uniform
-      gq[0] += dstep * LGS; gq[1] += dstep * LGS; so[0] += dstep * 256; so[1] += dstep * 256;
-      fetch(gq, so, step + 2 < T);
-    }
+    if (live0) { gq[0][0] = da[0][0]; gq[0][LH] = da[0][1]; gq[0][2 * LH] = da[0][2]; gq[0][3 * LH] = da[0][3]; }
+    if (live1) { gq[1][0] = da[1][0]; gq[1][LH] = da[1][1]; gq[1][2 * LH] = da[1][2]; gq[1][3 * LH] = da[1][3]; }
+    fetch(sv, step + 2 < T ? 2 : 0, step + 3 < T);         // past the end: re-read a valid row (unused)
+    gq[0] += dstep * LGS; gq[1] += dstep * LGS; so[0] += dstep * 256; so[1] += dstep * 256;
     {
       uint16_t* dw = reinterpret_cast<uint16_t*>(dbuf) + doff;
 #pragma unroll
@@ -319,16 +355,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         *reinterpret_cast<float2*>(dhx + nb + poff) = make_float2(p0, p1);
         *reinterpret_cast<float2*>(dhx + nb + poff + 64) = make_float2(p2, p3);
       } else {
-        st_cluster_f32x2(ppeer + 4u * (uint32_t)nb, p0, p1);
-        st_cluster_f32x2(ppeer + 4u * (uint32_t)(nb + 64), p2, p3);
+        const uint32_t pb = bpeer + 8u * (uint32_t)((step + 1) & 1);
+        st_async_f32x2(ppeer + 4u * (uint32_t)nb, p0, p1, pb);
+        st_async_f32x2(ppeer + 4u * (uint32_t)(nb + 64), p2, p3, pb);
       }
     }
-    // global stores between arrive and wait (see the forward kernel)
-    cluster_arrive();
-    if (live0) { gw0[0] = da[0][0]; gw0[LH] = da[0][1]; gw0[2 * LH] = da[0][2]; gw0[3 * LH] = da[0][3]; }
-    if (live1) { gw1[0] = da[1][0]; gw1[LH] = da[1][1]; gw1[2 * LH] = da[1][2]; gw1[3 * LH] = da[1][3]; }
-    cluster_wait();
+    __syncthreads();                                       // own partial sums written; the da planes may be rewritten
+    tc::mbar_wait(&dbar[(step + 1) & 1], (step >> 1) & 1);   // the peer's partial sums have landed
+  };
+  for (int step = 0; step < T; step += 2) {
+    do_step(step, sva);
+    if (step + 1 < T) do_step(step + 1, svb);
   }
+  cluster_sync_all();                                      // neither CTA leaves while the other may still address it
 }
 
 // ------------------------------------------------------------------------------------------------
