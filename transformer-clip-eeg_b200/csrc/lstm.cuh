@@ -13,8 +13,6 @@
 namespace eegclip {
 namespace lstm {
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
-
 constexpr int LH = 128, LG = 512;
 
 // ------------------------------------------------------------------------------------------------
@@ -415,13 +413,13 @@ __global__ void __launch_bounds__(128) lstm4_fwd_kernel(const float* __restrict_
     const float gx = gcur[uu];
     float a = gx;
     a = fmaf(w0, h0, a); a = fmaf(w1, h1, a); a = fmaf(w2, h2, a); a = fmaf(w3, h3, a);
-    const float act = (j >> 2) == 2 ? tanhf(a) : sigmoidf_(a);
+    const float act = (j >> 2) == 2 ? tanh_fast(a) : sigmoid_fast(a);
     // unit lane u (= j & 3) gathers i, f, g, o of its unit
     const int u = j & 3;
     const float gi = __shfl_sync(gmask, act, lbase + u), gf = __shfl_sync(gmask, act, lbase + 4 + u);
     const float gg = __shfl_sync(gmask, act, lbase + 8 + u), go = __shfl_sync(gmask, act, lbase + 12 + u);
     c = gf * c + gi * gg;                               // identical in the 4 lanes sharing a unit; lanes j < 4 are authoritative
-    const float hn = go * tanhf(c);
+    const float hn = go * tanh_fast(c);
     if (live) {
       G[row * GS + dir * 16 + j] = act;
       if (j < 4) {
@@ -492,7 +490,7 @@ __global__ void __launch_bounds__(128) lstm4_bwd_kernel(const float* __restrict_
     const float gi = __shfl_sync(gmask, act, lbase + u), gf = __shfl_sync(gmask, act, lbase + 4 + u);
     const float gg = __shfl_sync(gmask, act, lbase + 8 + u), go = __shfl_sync(gmask, act, lbase + 12 + u);
     const float dht = dy + dh;
-    const float tc = tanhf(ct);
+    const float tc = tanh_fast(ct);
     const float dct = dc + dht * go * (1.f - tc * tc);
     // pre-activation gradient of THIS lane's gate row
     float da;
