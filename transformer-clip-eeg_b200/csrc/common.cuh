@@ -1,6 +1,7 @@
 // Shared device/host helpers for the EEG-CLIP B200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a profiler injects itself
 #include <stdint.h>
 #include <math.h>
 
@@ -34,6 +35,15 @@ struct ProfScope {
   int cls; cudaStream_t st;
   ProfScope(int c, cudaStream_t s) : cls(c), st(s) { prof_begin(c, s); }
   ~ProfScope() { prof_end(cls, st); }
+};
+
+// NVTX range around a host-side enqueue section (C-ABI entry points, per layer inside the towers): names the launch groups in
+// Nsight Systems / ncu --nvtx timelines.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 // Programmatic dependent launch.  A step is ~510 dependent kernel launches on one stream and the back-to-back launch gap

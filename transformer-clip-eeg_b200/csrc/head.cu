@@ -332,6 +332,7 @@ int eegclip_infonce_lse(const float* S_all, const float* E_all, const float* tau
                         float* lse_row, float* lse_col, float* diag, int32_t math, int32_t one_sided, void* scratch, void* stream) {
   if (!S_all || !E_all || !tau || !lse_row || (!lse_col && !one_sided) || !diag || !scratch) return EEGCLIP_ERR_ARG;
   if (b <= 0 || row0 < 0 || row0 + b > Bg || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
+  NvtxRange nvtx_("eegclip_infonce_lse");
   cudaStream_t st = (cudaStream_t)stream;
   const HeadScratch hs = head_scratch(b, Bg, D);
   char* sc = (char*)scratch;
@@ -394,6 +395,7 @@ int eegclip_infonce_backward(const float* S_all, const float* E_all, const float
   if (!S_all || !E_all || !tau || !lse_row_all || !dE_loc || !dtau_partial || !scratch || !dloss) return EEGCLIP_ERR_ARG;
   if (!one_sided && (!lse_col_all || !dS_loc)) return EEGCLIP_ERR_ARG;
   if (b <= 0 || row0 < 0 || row0 + b > Bg || D <= 0 || (D & 3)) return EEGCLIP_ERR_ARG;
+  NvtxRange nvtx_("eegclip_infonce_backward");
   cudaStream_t st = (cudaStream_t)stream;
   const HeadScratch hs = head_scratch(b, Bg, D);
   char* sc = (char*)scratch;

@@ -83,6 +83,7 @@ int eegclip_bilstm_forward(const eegclip_bilstm_desc* dp, const float* const* pa
                            void* scratch_v, void* stream) {
   if (!lstm_ok(dp)) return EEGCLIP_ERR_UNSUPPORTED;
   if (!params || !x || !out || !save_v || !scratch_v) return EEGCLIP_ERR_ARG;
+  NvtxRange nvtx_("eegclip_bilstm_forward");
   const eegclip_bilstm_desc& d = *dp;
   cudaStream_t st = (cudaStream_t)stream;
   const LstmLayout L = lstm_layout(d);
@@ -134,6 +135,7 @@ int eegclip_bilstm_backward(const eegclip_bilstm_desc* dp, const float* const* p
                             const float* dout, float* dx, void* save_v, void* scratch_v, void* stream) {
   if (!lstm_ok(dp)) return EEGCLIP_ERR_UNSUPPORTED;
   if (!params || !grads || !x || !dout || !save_v || !scratch_v) return EEGCLIP_ERR_ARG;
+  NvtxRange nvtx_("eegclip_bilstm_backward");
   const eegclip_bilstm_desc& d = *dp;
   cudaStream_t st = (cudaStream_t)stream;
   const LstmLayout L = lstm_layout(d);

@@ -533,6 +533,7 @@ int eegclip_tower_workspace(const eegclip_tower_desc* d, size_t* save_bytes, siz
 int eegclip_tower_forward(const eegclip_tower_desc* dp, const float* const* params, const float* x, float* out, void* save_v,
                           void* scratch_v, void* stream) {
   if (!desc_ok(dp) || !params || !x || !out || !scratch_v || !save_v) return EEGCLIP_ERR_ARG;
+  NvtxRange nvtx_("eegclip_tower_forward");
   const eegclip_tower_desc& d = *dp;
   cudaStream_t st = (cudaStream_t)stream;
   SaveLayout L = save_layout(d);
@@ -547,6 +548,7 @@ int eegclip_tower_forward(const eegclip_tower_desc* dp, const float* const* para
   const float* xin = eegx;
   if (d.kind == EEGCLIP_TOWER_INTERLEAVED) {
     for (int i = 0; i < d.depth; ++i) {
+      NvtxRange nvtx_layer("tower layer forward (conv block + transformer block)");
       ConvP cp = conv_at<ConvP>(params, i);
       float* cb = save + L.conv0 + L.conv_stride * i;
       const bool last = (i == d.depth - 1);
@@ -582,6 +584,7 @@ int eegclip_tower_backward(const eegclip_tower_desc* dp, const float* const* par
                            size_t grad_bytes, const float* x, const float* dout, float* dx, const void* save_v, void* scratch_v,
                            void* stream) {
   if (!desc_ok(dp) || !params || !grads || !x || !dout || !save_v || !scratch_v) return EEGCLIP_ERR_ARG;
+  NvtxRange nvtx_("eegclip_tower_backward");
   const eegclip_tower_desc& d = *dp;
   cudaStream_t st = (cudaStream_t)stream;
   SaveLayout L = save_layout(d);
