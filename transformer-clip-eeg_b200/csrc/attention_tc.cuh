@@ -59,7 +59,7 @@ __device__ __forceinline__ void build_keep_bits(uint32_t* smask, const Drop& dro
 //   dV += Pd^T.dO, dK += dS^T.Q: 2 x m16n8k16;  dQ += dS.K': 1 x m16n8k16 (16 queries x 16 keys, no padding) + 4 movmatrix.
 // Range: everything downstream of dO is linear in dO, so dO is scaled by a power of two per (batch, head) to [8, 16) max
 // magnitude before it is rounded to fp16 and the three gradients are scaled back (gradients of 1e-6 would be fp16 subnormals).
-// smem: Qh, dOh [T][8] and their transposes QT, dOT [8][T+8] (fp16), LB [T][4] (-lse' terms), Ds [T], dQs [T][8] (fp32), keep bits.
+// smem: Qh, dOh [T][8] and their transposes QT, dOT [8][T+8] (fp16), LB [T][4] (-lse' terms), Ds [T], per-warp dQ slots, keep bits.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   uint32_t r;
@@ -246,8 +246,8 @@ __global__ void __maxnreg__(112) attn_bwd_h_kernel(const float* __restrict__ qkv
   __half* dOT = QT + 8 * TP;
   uint32_t* LB = reinterpret_cast<uint32_t*>(dOT + 8 * TP);   // [T][4]: -lse' as three fp16 terms (words 0, 1), zeros (2, 3)
   float* Ds = reinterpret_cast<float*>(LB + 4 * T);
-  float* dQs = Ds + T;
-  float* red = dQs + T * 8;
+  float* dqp = Ds + T;                                     // [2][warps][16 x 8]: per-warp dQ partials of a 16-query block
+  float* red = dqp + 2 * (T >> 6) * 128;
   uint32_t* smask = reinterpret_cast<uint32_t*>(red + 8);
   const bool bitmask = drop.enabled && drop.onebit;
   const int nblk = T >> 5;
@@ -273,7 +273,6 @@ __global__ void __maxnreg__(112) attn_bwd_h_kernel(const float* __restrict__ qkv
       const __half qh = __float2half_rn(q[d]);
       Qh[i * 8 + d] = qh;
       QT[d * TP + i] = qh;
-      dQs[i * 8 + d] = 0.f;
     }
     dsum[r] = ds_;
     uint32_t w0, w1;
@@ -330,6 +329,8 @@ __global__ void __maxnreg__(112) attn_bwd_h_kernel(const float* __restrict__ qkv
   __syncthreads();
   const float zero[4] = {0.f, 0.f, 0.f, 0.f};
   const float dscale = drop.scale;
+  const float sq = LN2 * inv;
+  const int nwarp = nthr >> 5;
   const uint32_t kone = tig == 0 ? 0x3c003c00u : tig == 1 ? 0x00003c00u : 0u;   // ones in contraction slots 8, 9, 10 (see split3_h)
   const uint32_t* Qw = reinterpret_cast<const uint32_t*>(Qh);
   const uint32_t* Ow = reinterpret_cast<const uint32_t*>(dOh);
@@ -379,11 +380,22 @@ __global__ void __maxnreg__(112) attn_bwd_h_kernel(const float* __restrict__ qkv
       // dQ (16 queries x 8 dims) += dS (queries x this tile's 16 keys) . K': the transposed dS fragments of both blocks fill all 16 rows
       mma_h16(dq, movm_t(sa[0][0]), movm_t(sa[1][0]), movm_t(sa[0][1]), movm_t(sa[1][1]), kt[Y][0], kt[Y][1]);
     }
-    // dq[0], dq[1] = dQ'[query q0 + g][d = 2tig, 2tig+1];  dq[2], dq[3]: query q0 + 8 + g
-    atomicAdd(dQs + (q0 + g) * 8 + 2 * tig, dq[0]);
-    atomicAdd(dQs + (q0 + g) * 8 + 2 * tig + 1, dq[1]);
-    atomicAdd(dQs + (q0 + 8 + g) * 8 + 2 * tig, dq[2]);
-    atomicAdd(dQs + (q0 + 8 + g) * 8 + 2 * tig + 1, dq[3]);
+    // dq[0], dq[1] = dQ'[query q0 + g][d = 2tig, 2tig+1];  dq[2], dq[3]: query q0 + 8 + g.  The block's dQ is complete once
+    // every warp (= every key range) has contributed: the partials go to per-warp slots and 128 threads sum them IN WARP ORDER
+    // and write the rows out -- no atomics, bitwise reproducible (the shared-memory float atomics this replaces were
+    // compare-and-swap loops).  Slots are double buffered: one barrier per 16 queries.
+    {
+      float* slot = dqp + (((q0 >> 4) & 1) * nwarp + warp) * 128;
+      *reinterpret_cast<float2*>(slot + g * 8 + 2 * tig) = make_float2(dq[0], dq[1]);
+      *reinterpret_cast<float2*>(slot + (8 + g) * 8 + 2 * tig) = make_float2(dq[2], dq[3]);
+      __syncthreads();
+      if (tid < 128) {
+        const float* sl = dqp + ((q0 >> 4) & 1) * nwarp * 128 + tid;
+        float acc = sl[0];
+        for (int w_ = 1; w_ < nwarp; ++w_) acc += sl[w_ * 128];
+        dqkv[((long)b * T + q0 + (tid >> 3)) * AQKV + h * AD + (tid & 7)] = acc * sq;   // dQ = ln2 * sum (K' carries log2e / 8)
+      }
+    }
   }
   // ---- dK, dV of this warp's keys ----
   const float sk = 0.125f * inv;
@@ -395,15 +407,6 @@ __global__ void __maxnreg__(112) attn_bwd_h_kernel(const float* __restrict__ qkv
     *reinterpret_cast<float2*>(r1 + 64) = make_float2(dk[Y][2] * sk, dk[Y][3] * sk);
     *reinterpret_cast<float2*>(r0 + 128) = make_float2(dv[Y][0] * inv, dv[Y][1] * inv);
     *reinterpret_cast<float2*>(r1 + 128) = make_float2(dv[Y][2] * inv, dv[Y][3] * inv);
-  }
-  __syncthreads();
-  // dQ = ln2 * sum over warps (K' carries log2e/8)
-  const float sq = LN2 * inv;
-  for (int i = tid; i < T * 2; i += blockDim.x) {
-    const int t = i >> 1, half = i & 1;
-    float4 v = *reinterpret_cast<const float4*>(dQs + t * 8 + half * 4);
-    v.x *= sq; v.y *= sq; v.z *= sq; v.w *= sq;
-    *reinterpret_cast<float4*>(dqkv + ((long)b * T + t) * AQKV + h * AD + half * 4) = v;
   }
 }
 
@@ -427,7 +430,7 @@ inline int attention_fwd_tc(const float* qkv, float* out, float* lse, int B, int
 inline int attention_bwd_tc(const float* qkv, const float* out, const float* dout, const float* lse, float* dqkv, int B, int T,
                             const Drop& drop, cudaStream_t st) {
   const int warps = T / 64;
-  const size_t smem = (size_t)(16 * T + 16 * (T + 8)) * 2 + (size_t)(13 * T + 8) * sizeof(float) + (size_t)T * T / 8;
+  const size_t smem = (size_t)(16 * T + 16 * (T + 8)) * 2 + (size_t)(5 * T + 2 * (T / 64) * 128 + 8) * sizeof(float) + (size_t)T * T / 8;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(attntc::attn_bwd_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)   // T = 512: 92.4 KB
