@@ -339,10 +339,15 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     conv_ms_total, conv_launches_timed = prof_ms[0], prof_n[0]
     # per-class breakdown: a second pass of the same K steps with events around every launch (not part of `value`)
+    # (single stream: with the speech tower on its side stream the per-launch events of the two towers would overlap)
     _lib.call("eegclip_tune_set", 8, 0)
+    two_streams = os.environ.get("EEGCLIP_TWO_STREAMS", "1")
+    os.environ["EEGCLIP_TWO_STREAMS"] = "0"
+    step_resident(0)
     _lib.call("eegclip_profile_begin")
     ms_step_profiled = timed(step_resident, args.steps)
     _lib.call("eegclip_profile_end", ctypes.cast(prof_ms, ctypes.c_void_p), ctypes.cast(prof_n, ctypes.c_void_p), 12)
+    os.environ["EEGCLIP_TWO_STREAMS"] = two_streams
     run_e2e(max(args.warmup, 3) + 3)                 # warm-up: also lets the copy stream's allocator pool reach steady state
     run_e2e(args.steps)
     ms_e2e = timed(run_e2e, args.steps, whole=True)
@@ -395,7 +400,9 @@ def run_b200(args):
                    "parallelism": f"dp{world}: per-rank towers, NCCL all-gather of embeddings, sharded InfoNCE, SUM all-reduce of grads",
                    "numa": f"rank 0 bound to NUMA node {numa_node} of its GPU (every rank binds to its own GPU's node)" if numa_node is not None else "no NUMA binding",
                    "l2": f"per-step inputs ({h2d_bytes / 1e6:.0f} MB) and activations (>2 GB) exceed the 126 MB L2; {NBUF} batches rotate",
-                   "speech_tower": "1x1 conv, BasicBlock(k=32) and both bi-LSTMs (input GEMMs + recurrence kernels) on eegclip kernels"},
+                   "speech_tower": "1x1 conv, BasicBlock(k=32) and both bi-LSTMs (input GEMMs + recurrence kernels) on eegclip kernels",
+                   "streams": ("speech tower on a side stream next to the EEG tower, forward and backward (clip_model.run_towers)"
+                               if two_streams != "0" else "both towers on one stream (EEGCLIP_TWO_STREAMS=0)")},
         "clocks": clocks,
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4,
@@ -407,8 +414,13 @@ def run_b200(args):
                      "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                      "algorithmic_flop_per_launch": conv_flop_timed / conv_launches, "avg_launch_ms": conv_ms,
                      "launches_timed": int(conv_launches_timed),
+                     "frac_single_stream": (args.steps * B * CONV_CLASS0_FLOP_PER_SAMPLE_STEP / (prof_ms[0] * 1e-3) / 1e12 / pk["bf16_sustained"])
+                                           if prof_ms[0] > 0 else None,
                      "note": "per step 20 launches of the k=64 conv (B x 167.77 MFLOP each) + 2 of the speech tower's k=32 conv (B x 83.89 MFLOP "
-                             "each), each credited its own FLOPs; " + CONV_MATH_NOTE,
+                             "each), each credited its own FLOPs; " + CONV_MATH_NOTE +
+                             "; in the timed region the speech tower runs on a side stream, so a conv launch shares the SMs with the other "
+                             "tower's kernels for part of its duration (frac_single_stream: the same launches in the single-stream "
+                             "per-class pass)",
                      "traffic": traffic},
         "roofline_whole_step": {"bound": "tensor", "achieved": step_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                                 "frac": step_tf / pk["bf16_sustained"], "algorithmic_flop_per_step": step_flop,
@@ -416,8 +428,8 @@ def run_b200(args):
                                         "divided by ms_per_step; the step is a chain of HBM-bound token kernels around the tensor-bound conv"},
         "kernels": kern,
         "kernels_note": f"per-class CUDA-event times from a second pass of the same {args.steps} steps with events around every launch "
-                        f"({ms_step_profiled:.2f} ms/step: the events serialise the launches); the timed region records events around the "
-                        "roofline kernel's launches only",
+                        f"and both towers on one stream ({ms_step_profiled:.2f} ms/step: the events serialise the launches); the timed "
+                        "region records events around the roofline kernel's launches only",
     }
     if extras is not None:
         line.update(extras)

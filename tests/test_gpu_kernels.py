@@ -272,6 +272,44 @@ def test_loss_reader_returns_every_step_in_order(lib):
     assert got == vals
 
 
+def test_two_stream_towers_match_single_stream(cm, lib, monkeypatch):
+    """The speech tower on a side stream (clip_model.run_towers, the default) runs the same kernels in the same per-tower order as
+    the single-stream step.  Three train steps (train mode, same seeds): the first loss is bitwise equal, the first step's whole
+    gradient arena agrees to 1e-6 (the float-atomic bias sums are the only run-to-run noise), later losses / gradients / parameters
+    agree to what AdamW's g / (|g| + eps) normalisation makes of that noise -- so no cross-stream edge is missing (forward join,
+    end-of-backward join before optimizer.step, next step's side stream waiting for the parameter update)."""
+    from transformer_clip_eeg_b200.optim import AdamW
+    from transformer_clip_eeg_b200 import train_clip_final as tcf
+    T, B, lr = 128, 16, 1e-3
+    args = tcf.build_parser().parse_args(["--attention_depth", "2"])
+    res = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("EEGCLIP_TWO_STREAMS", mode)
+        assert cm.two_streams_enabled() == (mode == "1")
+        torch.manual_seed(5)
+        model = tcf.build_model(args, T, 100, torch.device(DEV)).train()
+        opt = AdamW(model.parameters(), lr=lr, weight_decay=0.01)
+        g = torch.Generator().manual_seed(9)
+        losses, grads = [], []
+        for step in range(3):
+            eeg, sp = torch.randn(B, T, 64, generator=g).to(DEV), torch.randn(B, T, 1024, generator=g).to(DEV)
+            ids = torch.arange(1, B + 1, device=DEV)
+            loss_ce, _, _ = tcf.train_step(model, opt, eeg, sp, ids)
+            losses.append(loss_ce.detach().clone())
+            grads.append(opt.flat_grads()[0].detach().clone())
+        torch.cuda.synchronize()
+        res.append((torch.stack(losses).cpu(), grads, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    (l0, g0, p0), (l1, g1, p1) = res
+    assert torch.equal(l0[0], l1[0])                                     # first forward: bitwise
+    assert float(g0[0].norm()) > 0 and rel_err(g0[0], g1[0]) < 1e-6      # first backward, both towers' gradients
+    assert rel_err(l0, l1) < 1e-5
+    for a, b in zip(g0[1:], g1[1:]):
+        assert rel_err(a, b) < 1e-4
+    bad = {k: float((v.float() - p1[k].float()).abs().max()) for k, v in p0.items()
+           if float((v.float() - p1[k].float()).abs().max()) > 0.1 * lr}      # a missed update would be >= lr per step
+    assert not bad, bad
+
+
 def test_pdl_off_matches_pdl_on(cm, lib):
     """Programmatic dependent launch only overlaps launch latency: the forward is bit-identical with the attribute off
     (g_tune[7]); gradients agree to fp32 rounding (the bias column sums use global float atomics, so parameter gradients are not

@@ -651,6 +651,66 @@ class EEGConvLSTM(nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------------
+# Two-stream towers.  The two encoders of a CLIP wrapper are independent until the head, and the speech tower is a chain of
+# latency-bound launches (two bi-LSTM recurrences on 128 SMs, skinny projections) while the EEG tower's 1.73-wave convolutions
+# leave 40 SMs idle in their second round: the speech tower therefore runs on a side stream next to the EEG tower, in the
+# forward AND -- autograd runs a node's backward on the stream of its forward -- in the backward.  Ordering: the side stream
+# waits for the caller's stream before it starts (inputs, parameter updates of the previous step), the caller's stream waits
+# for the side stream before the head, and once more when the backward pass has been enqueued (a final engine callback), so
+# optimizer.step(), gradient all-reduces and reads of .grad on the caller's stream see every gradient.
+# EEGCLIP_TWO_STREAMS=0 runs both towers on the caller's stream (identical results: the kernels and their order per tower are the same).
+# ---------------------------------------------------------------------------------------------------
+import os as _os
+
+_SIDE_STREAMS = {}
+
+
+def two_streams_enabled():
+    return _os.environ.get("EEGCLIP_TWO_STREAMS", "1") != "0"
+
+
+def _side_stream(device):
+    s = _SIDE_STREAMS.get(device.index)
+    if s is None:
+        s = _SIDE_STREAMS[device.index] = torch.cuda.Stream(device=device)
+    return s
+
+
+class _RejoinFn(torch.autograd.Function):
+    """Identity on the side-stream tower's output, applied on the caller's stream after it has waited for the side stream; its
+    backward queues the end-of-backward wait of the caller's stream on the side stream."""
+
+    @staticmethod
+    def forward(ctx, x, main, side):
+        ctx.main, ctx.side = main, side
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        main, side = ctx.main, ctx.side
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: main.wait_stream(side))
+        return g, None, None
+
+
+def run_towers(eegModel, speechModel, eeg, speech):
+    """(eegModel(eeg), speechModel(speech)) with the speech tower on a side stream (see above)."""
+    if not (two_streams_enabled() and eeg.is_cuda and speech.is_cuda and eeg.device == speech.device):
+        sf = speechModel(speech)
+        return eegModel(eeg), sf
+    main, side = torch.cuda.current_stream(eeg.device), _side_stream(eeg.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        sf = speechModel(speech)
+    speech.record_stream(side)
+    ef = eegModel(eeg)
+    main.wait_stream(side)
+    sf.record_stream(main)
+    if sf.requires_grad:
+        sf = _RejoinFn.apply(sf, main, side)
+    return ef, sf
+
+
+# ---------------------------------------------------------------------------------------------------
 # Loss wrappers
 # ---------------------------------------------------------------------------------------------------
 class CLIP(nn.Module):
@@ -663,8 +723,8 @@ class CLIP(nn.Module):
         self.shard_group = None  # set to a torch.distributed group for sharded InfoNCE
 
     def forward(self, eeg, speech):
-        E = torch.flatten(self.eegModel(eeg), start_dim=1)
-        S = torch.flatten(self.speechModel(speech), start_dim=1)
+        ef, sf = run_towers(self.eegModel, self.speechModel, eeg, speech)
+        E, S = torch.flatten(ef, start_dim=1), torch.flatten(sf, start_dim=1)
         return infonce_loss(E, S, self.temperature, group=self.shard_group)
 
 
@@ -721,8 +781,7 @@ class CLIPSimNoLatentProj(nn.Module):
     def forward(self, eeg, speech, ids):
         # the speech tower runs first so that autograd runs the (three times longer) EEG tower backward first: under data
         # parallelism its 14.5 MB of gradients are all-reduced while the speech tower's backward is still running
-        sf = self.speechModel(speech)
-        ef = self.eegModel(eeg)
+        ef, sf = run_towers(self.eegModel, self.speechModel, eeg, speech)
         if sf.shape[1] > sf.shape[2]:
             sf = sf.transpose(1, 2)
         if ef.shape[1] > ef.shape[2]:
