@@ -66,24 +66,35 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        # started before the warm-up steps (nvidia-smi takes ~0.2 s to come up); only the samples that arrived between
+        # mark_begin() and mark_end() -- the timed region -- count (a sample is printed up to one period after it was taken)
+        lo, hi = (self.t0 or 0.0), (self.t1 or time.time()) + 0.02
+        self.rows = [r for t, r in self.rows if lo <= t <= hi]
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = max([int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()] or [0])
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -257,6 +268,9 @@ def run_b200(args):
         _lib.set_default_math(args.math)
     numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None   # before the pinned staging buffers are allocated
     lib = _lib.load()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                              # (nvidia-smi is up long before the timed region; only that region's samples count)
     B = args.batch
     torch.manual_seed(0)
     cli = tcf.build_parser().parse_args([])          # reference defaults: depth 10, convLSTM, latent 8, tau 0.075 ...
@@ -323,15 +337,14 @@ def run_b200(args):
 
     for i in range(max(args.warmup, 3)):
         step_resident(i)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     l0 = lib.eegclip_launch_count()
     # timed region: CUDA events around the roofline kernel's launches only (class 0); events around every launch would sit
     # between all kernels and switch off programmatic dependent launch for the whole step
     _lib.call("eegclip_tune_set", 8, 1)
     _lib.call("eegclip_profile_begin")
+    sampler.mark_begin()
     ms_step = timed(step_resident, args.steps)
+    sampler.mark_end()
     prof_ms = (ctypes.c_double * 12)()
     prof_n = (ctypes.c_longlong * 12)()
     _lib.call("eegclip_profile_end", ctypes.cast(prof_ms, ctypes.c_void_p), ctypes.cast(prof_n, ctypes.c_void_p), 12)

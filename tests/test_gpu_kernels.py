@@ -305,8 +305,9 @@ def test_two_stream_towers_match_single_stream(cm, lib, monkeypatch):
     assert rel_err(l0, l1) < 1e-5
     for a, b in zip(g0[1:], g1[1:]):
         assert rel_err(a, b) < 1e-4
+    # (keys.bias has a mathematically zero gradient, SURVEY H3: AdamW normalises its rounding noise to +-lr per step)
     bad = {k: float((v.float() - p1[k].float()).abs().max()) for k, v in p0.items()
-           if float((v.float() - p1[k].float()).abs().max()) > 0.1 * lr}      # a missed update would be >= lr per step
+           if not k.endswith("keys.bias") and float((v.float() - p1[k].float()).abs().max()) > 0.1 * lr}   # a missed update: >= lr
     assert not bad, bad
 
 
