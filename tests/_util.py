@@ -41,3 +41,16 @@ def rel_err(a, b, floor=0.0):
 
 def global_grad_norm(dig_map):
     return sum(v["norm"] ** 2 for v in dig_map.values()) ** 0.5
+
+
+def poison_cuda_cache(mbytes=512):
+    """Fill the caching allocator's free blocks with NaN, so that an output element a kernel fails to write cannot come out
+    right by accident (torch.empty reusing the block that an earlier, correct run of the same shape has just freed)."""
+    if not torch.cuda.is_available():
+        return
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    big = torch.full((mbytes * 262144,), float("nan"), device="cuda")                      # large pool
+    small = [torch.full((131072,), float("nan"), device="cuda") for _ in range(64)]        # small pool (< 1 MB requests)
+    torch.cuda.synchronize()
+    del big, small

@@ -20,3 +20,12 @@ def golden():
         with open(os.path.join(ROOT, "tests", "golden", name)) as f:
             cases.update(json.load(f)["cases"])
     return cases
+
+
+@pytest.fixture(autouse=True)
+def _poisoned_cuda_cache(request):
+    """GPU tests start with NaN in every cached free block (see _util.poison_cuda_cache)."""
+    if request.node.get_closest_marker("gpu") is not None:
+        from _util import poison_cuda_cache
+        poison_cuda_cache()
+    yield

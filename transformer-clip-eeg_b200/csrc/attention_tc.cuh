@@ -389,11 +389,11 @@ __global__ void __maxnreg__(112) attn_bwd_h_kernel(const float* __restrict__ qkv
       *reinterpret_cast<float2*>(slot + g * 8 + 2 * tig) = make_float2(dq[0], dq[1]);
       *reinterpret_cast<float2*>(slot + (8 + g) * 8 + 2 * tig) = make_float2(dq[2], dq[3]);
       __syncthreads();
-      if (tid < 128) {
-        const float* sl = dqp + ((q0 >> 4) & 1) * nwarp * 128 + tid;
+      for (int e = tid; e < 128; e += nthr) {              // (T = 128, 192 run 2, 3 warps: fewer threads than the 128 elements)
+        const float* sl = dqp + ((q0 >> 4) & 1) * nwarp * 128 + e;
         float acc = sl[0];
         for (int w_ = 1; w_ < nwarp; ++w_) acc += sl[w_ * 128];
-        dqkv[((long)b * T + q0 + (tid >> 3)) * AQKV + h * AD + (tid & 7)] = acc * sq;   // dQ = ln2 * sum (K' carries log2e / 8)
+        dqkv[((long)b * T + q0 + (e >> 3)) * AQKV + h * AD + (e & 7)] = acc * sq;   // dQ = ln2 * sum (K' carries log2e / 8)
       }
     }
   }
