@@ -600,6 +600,55 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
     atomicAdd(out + threadIdx.x, acc);
   }
 }
+// Deterministic form: per-CTA partials into `scratch` (colsum_det_ctas(M) x N floats), folded in CTA order by one CTA.
+__global__ void __launch_bounds__(256) colsum_part_kernel(const float* __restrict__ X, float* __restrict__ part, long M, int N,
+                                                         int ld, int rows_per_cta) {
+  pdl_sync();
+  __shared__ float sh[256 * 4];
+  const int lanes = N >> 2;               // threads across float4 columns
+  const int rgroups = 256 / lanes;        // row groups per CTA
+  const int cl = threadIdx.x % lanes, rg = threadIdx.x / lanes;
+  long r0 = (long)blockIdx.x * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rg < rgroups)
+    for (long r = r0 + rg; r < r1; r += rgroups) {
+      float4 v = reinterpret_cast<const float4*>(X + r * ld)[cl];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  reinterpret_cast<float4*>(sh)[threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.x < N) {
+    int c4 = threadIdx.x >> 2, j = threadIdx.x & 3;
+    float acc = 0.f;
+    for (int g = 0; g < rgroups; ++g) acc += sh[(g * lanes + c4) * 4 + j];
+    part[(long)blockIdx.x * N + threadIdx.x] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_fold_kernel(const float* __restrict__ part, float* __restrict__ out, int ctas, int N) {
+  pdl_sync();
+  if (threadIdx.x < N) {
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // four fixed interleaved chains (latency), combined in fixed order
+    int c = 0;
+    for (; c + 4 <= ctas; c += 4) {
+      acc0 += part[(long)(c + 0) * N + threadIdx.x]; acc1 += part[(long)(c + 1) * N + threadIdx.x];
+      acc2 += part[(long)(c + 2) * N + threadIdx.x]; acc3 += part[(long)(c + 3) * N + threadIdx.x];
+    }
+    for (; c < ctas; ++c) acc0 += part[(long)c * N + threadIdx.x];
+    out[threadIdx.x] += (acc0 + acc1) + (acc2 + acc3);
+  }
+}
+constexpr int COLSUM_DET_ROWS = 512;
+inline int colsum_det_ctas(long M) { return (int)((M + COLSUM_DET_ROWS - 1) / COLSUM_DET_ROWS); }
+inline int colsum_det(const float* X, float* out, long M, int N, int ld, float* scratch, cudaStream_t st) {
+  if (N > 256 || (N & 3) || (256 % (N >> 2)) || (ld & 3)) return EEGCLIP_ERR_UNSUPPORTED;
+  const int ctas = colsum_det_ctas(M);
+  LAUNCH_PDL((colsum_part_kernel), (unsigned)ctas, 256, 0, st, X, scratch, M, N, ld, COLSUM_DET_ROWS);
+  LAUNCH_CHECK();
+  LAUNCH_PDL((colsum_fold_kernel), 1, 256, 0, st, (const float*)scratch, out, ctas, N);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
 inline int colsum(const float* X, float* out, long M, int N, int ld, cudaStream_t st) {
   if (N > 256 || (N & 3) || (256 % (N >> 2)) || (ld & 3)) return EEGCLIP_ERR_UNSUPPORTED;
   int rows_per_cta = g_tune[11] > 0 ? g_tune[11] : 512;

@@ -415,14 +415,18 @@ int eegclip_infonce_backward(const float* S_all, const float* E_all, const float
     a.Ap = pS; a.Bp = pE; a.a_blk0 = row0 / headtc::RB; a.M = b; a.N = Bg; a.D = D; a.tau = tau;
     a.m_off = row0; a.n_off = 0; a.lse_m = lse_row_all; a.lse_n = lse_col_all; a.up = dloss; a.inv_2b = 0.5f / (float)Bg;
     a.one_sided = one_sided; a.Gp = pGr; a.nkc_g = nkc_g; a.dtau = dtau_partial;
+    // d tau without float atomics: per-(CTA, epilogue warp) sums land in the (not yet written) second G buffer and are folded in
+    // fixed order before the next launch overwrites it
+    a.dtau_slots = (size_t)headtc::logits_grid(a) * 8 * sizeof(float) <= hs.g2 - hs.g1 ? (float*)pGc : nullptr;
     const bool need_ds = dS_loc && !one_sided;
     TRY(headtc::logits_launch<2>(math, a, st));   // (one-sided: only d tau comes out of this block, its G is not consumed)
+    if (a.dtau_slots) TRY(headtc::dtau_fold(a.dtau_slots, headtc::logits_grid(a), dtau_partial, st));
     // Gc^T(j = local EEG column, i = any speech row): the (E_loc x S_all) product, packed with rows j and contraction i
     //   -> dE_loc = exp(tau) Gc^T . S_all.
     // One-sided (memory-bank term, clip_model.py:934-937): G(i,j) = (softmax_j L(i,.) - delta) / B, the statistics belong to
     // the rows i of X = S_all, which are the n side of this product (one_sided = 2); only E has a gradient.
     headtc::LogitsArgs c = a;
-    c.Ap = pE; c.Bp = pS; c.Gp = pGc; c.dtau = nullptr;
+    c.Ap = pE; c.Bp = pS; c.Gp = pGc; c.dtau = nullptr; c.dtau_slots = nullptr;
     c.lse_m = one_sided ? nullptr : lse_col_all;
     c.lse_n = lse_row_all;
     c.one_sided = one_sided ? 2 : 0;

@@ -106,7 +106,8 @@ struct LogitsArgs {
   int one_sided;          // 1: G = (exp(L - lse_m) - delta) / B ; 2: G = (exp(L - lse_n) - delta) / B ; 0: symmetric
   uint8_t* Gp;            // packed G: operand blocks [m / 128][n / 64], the A operand of the backward contractions over n
   int nkc_g;              // 64-column chunks per row block of Gp (= ceil(N / 64))
-  float* dtau;            // += sum G * L (nullptr: skip)
+  float* dtau;            // += sum G * L (nullptr: skip) -- float atomics unless dtau_slots is given
+  float* dtau_slots;      // [gridDim.x][8]: per-(CTA, epilogue warp) sums of G * L, folded in fixed order by dtau_fold (dtau then unused)
   // MODE 3
   float* out;             // [M][ldo] dot products (x exp(tau) when tau != nullptr)
   long ldo;
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
     // ===== epilogue: thread = logit row m; warps 0-3 take columns [0,128) of the tile, warps 6-9 columns [128,256) =====
     const int q = warp & 3, chalf = warp >= 6 ? 1 : 0;      // TMEM lane quarter of a warp is warp % 4
     const float scale = a.tau ? __expf(*a.tau) : 1.f;
+    float tsum_cta = 0.f;                                   // MODE 2 with dtau_slots: this thread's sum of G * L over all its tiles
     uint32_t t = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
     const int tn = tile % ntn, tm = tile / ntn;
@@ -296,13 +298,19 @@ __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
           *reinterpret_cast<uint4*>(gblk + j8 * (RB * 16) + PLANE) = lo;
         }
       }
-      if (a.dtau) {
+      if (a.dtau_slots) {
+        tsum_cta += tsum;
+      } else if (a.dtau) {
         tsum = warp_sum(tsum);
         if (lane == 0) atomicAdd(a.dtau, tsum);
       }
     }
     tc::tc_fence_before();
     tc::mbar_arrive(&accempty[buf]);        // every epilogue thread: this buffer's columns have been read
+    }
+    if (MODE == 2 && a.dtau_slots) {
+      tsum_cta = warp_sum(tsum_cta);
+      if (lane == 0) a.dtau_slots[blockIdx.x * 8 + q + 4 * chalf] = tsum_cta;
     }
   }
   tc::tc_fence_before();
@@ -329,6 +337,24 @@ inline int epack_t(const float* X, uint8_t* P, int R, int D, cudaStream_t st) {
 }
 inline size_t epack_t_bytes(int R, int D) { return (size_t)((D + RB - 1) / RB) * ((R + KC - 1) / KC) * BLK; }
 
+// d tau = sum of the per-(CTA, warp) slots of a MODE-2 launch, in slot order (one warp; bitwise reproducible)
+__global__ void __launch_bounds__(32) dtau_fold_kernel(const float* __restrict__ slots, int n, float* __restrict__ dtau) {
+  pdl_sync();
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) acc += slots[i];
+  acc = warp_sum(acc);
+  if (threadIdx.x == 0) *dtau = acc;
+}
+inline int logits_grid(const LogitsArgs& a) {
+  const int ntiles = ((a.N + NT - 1) / NT) * ((a.M + RB - 1) / RB);
+  return ntiles < 148 ? ntiles : 148;                     // persistent: one CTA per SM at most
+}
+inline int dtau_fold(const float* slots, int grid, float* dtau, cudaStream_t st) {
+  LAUNCH_PDL((dtau_fold_kernel), 1, 32, 0, st, slots, grid * 8, dtau);
+  LAUNCH_CHECK();
+  return EEGCLIP_OK;
+}
+
 template <int MODE, int NTERMS>
 inline int logits_launch_t(const LogitsArgs& a, cudaStream_t st) {
   static bool configured = false;
@@ -338,8 +364,7 @@ inline int logits_launch_t(const LogitsArgs& a, cudaStream_t st) {
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
-  const int ntiles = ((a.N + NT - 1) / NT) * ((a.M + RB - 1) / RB);
-  const int grid = ntiles < 148 ? ntiles : 148;           // persistent: one CTA per SM at most
+  const int grid = logits_grid(a);
   ProfScope prof(PROF_GEMM_F32, st);
   LAUNCH_PDL((logits_tc_kernel<MODE, NTERMS>), grid, 320, smem, st, a);
   LAUNCH_CHECK();

@@ -154,12 +154,22 @@ int eegclip_bilstm_backward(const eegclip_bilstm_desc* dp, const float* const* p
     LAUNCH_PDL((lstm::lstm128_bwd_c2_kernel), dim3(2 * ceil_div(d.B, lstm::LMS), 2), 256, 0, st, params[1], params[5], G, dout, Cs, d.B, d.T);
     LAUNCH_CHECK();
   } else {
-    CUDA_TRY(cudaMemsetAsync(grads[1], 0, (size_t)G4 * H * sizeof(float), st));
-    CUDA_TRY(cudaMemsetAsync(grads[5], 0, (size_t)G4 * H * sizeof(float), st));
+    // dW_hh: per-CTA partials in the (still unused) weight-gradient partial buffer, folded in CTA order; float atomics only if
+    // that buffer were too small
+    const int ctas = ceil_div(2 * d.B * 16, 128);
+    const size_t p1 = lintc::lin_wgrad_partial_bytes(64, d.In < 256 ? d.In : 256, 1), p2 = lintc::lin_wgrad_partial_bytes(256, 64, 2);
+    float* dwpart = (size_t)ctas * 128 * sizeof(float) <= (p1 > p2 ? p1 : p2) ? partial : nullptr;
+    if (!dwpart) {
+      CUDA_TRY(cudaMemsetAsync(grads[1], 0, (size_t)G4 * H * sizeof(float), st));
+      CUDA_TRY(cudaMemsetAsync(grads[5], 0, (size_t)G4 * H * sizeof(float), st));
+    }
     ProfScope prof(PROF_LSTM, st);
-    LAUNCH_PDL((lstm::lstm4_bwd_kernel), ceil_div(2 * d.B * 16, 128), 128, 0, st, params[1], params[5], G, L.GS, dout, Cs, Hp, grads[1], grads[5],
-                                                                        d.B, d.T);
+    LAUNCH_PDL((lstm::lstm4_bwd_kernel), ctas, 128, 0, st, params[1], params[5], G, L.GS, dout, Cs, Hp, grads[1], grads[5], d.B, d.T, dwpart);
     LAUNCH_CHECK();
+    if (dwpart) {
+      LAUNCH_PDL((lstm::lstm4_dw_fold_kernel), 1, 128, 0, st, (const float*)dwpart, ctas, grads[1], grads[5]);
+      LAUNCH_CHECK();
+    }
   }
   // ---- dW_ih = da^T . x, db = sum da ; dW_hh = da^T . h_prev ----
   if (H == 128) {

@@ -439,9 +439,11 @@ __global__ void __launch_bounds__(128) lstm4_fwd_kernel(const float* __restrict_
 __global__ void __launch_bounds__(128) lstm4_bwd_kernel(const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
                                                        float* __restrict__ G, int GS, const float* __restrict__ dout,
                                                        const float* __restrict__ Cs, const float* __restrict__ Hp,
-                                                       float* __restrict__ dwhh_f, float* __restrict__ dwhh_r, int B, int T) {
+                                                       float* __restrict__ dwhh_f, float* __restrict__ dwhh_r, int B, int T,
+                                                       float* __restrict__ part /* [gridDim.x][2][64] or nullptr (atomics) */) {
   pdl_sync();
   __shared__ float red[2][64];
+  __shared__ __align__(16) float slot[8][64];
   const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int j = threadIdx.x & 15;
   const bool live = gid < 2 * B;
@@ -514,6 +516,19 @@ __global__ void __launch_bounds__(128) lstm4_bwd_kernel(const float* __restrict_
     }
   }
   // CTA-level reduction of dW_hh per direction (a CTA may straddle the two directions)
+  if (part) {
+    // fixed order: the 8 sequences of the CTA in sequence order, the CTAs in CTA order (lstm4_dw_fold_kernel)
+    *reinterpret_cast<float4*>(&slot[threadIdx.x >> 4][j * 4]) = live ? make_float4(dw0, dw1, dw2, dw3) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const int e = threadIdx.x & 63, dsel = threadIdx.x >> 6;
+    float acc = 0.f;
+    for (int sgrp = 0; sgrp < 8; ++sgrp) {
+      const int gid_ = blockIdx.x * 8 + sgrp;
+      if (gid_ < 2 * B && gid_ / B == dsel) acc += slot[sgrp][e];
+    }
+    part[(long)blockIdx.x * 128 + threadIdx.x] = acc;
+    return;
+  }
   if (live) {
     float* r = red[dir];
     atomicAdd(r + j * 4 + 0, dw0); atomicAdd(r + j * 4 + 1, dw1); atomicAdd(r + j * 4 + 2, dw2); atomicAdd(r + j * 4 + 3, dw3);
@@ -523,6 +538,21 @@ __global__ void __launch_bounds__(128) lstm4_bwd_kernel(const float* __restrict_
     if (red[0][threadIdx.x] != 0.f) atomicAdd(dwhh_f + threadIdx.x, red[0][threadIdx.x]);
     if (red[1][threadIdx.x] != 0.f) atomicAdd(dwhh_r + threadIdx.x, red[1][threadIdx.x]);
   }
+}
+
+// dW_hh (both directions, 64 floats each) = sum of the per-CTA partials in CTA order
+__global__ void __launch_bounds__(128) lstm4_dw_fold_kernel(const float* __restrict__ part, int ctas, float* __restrict__ dwhh_f,
+                                                            float* __restrict__ dwhh_r) {
+  pdl_sync();
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int c = 0;
+  for (; c + 4 <= ctas; c += 4) {
+    a0 += part[(long)(c + 0) * 128 + threadIdx.x]; a1 += part[(long)(c + 1) * 128 + threadIdx.x];
+    a2 += part[(long)(c + 2) * 128 + threadIdx.x]; a3 += part[(long)(c + 3) * 128 + threadIdx.x];
+  }
+  for (; c < ctas; ++c) a0 += part[(long)c * 128 + threadIdx.x];
+  const float v = (a0 + a1) + (a2 + a3);
+  if (threadIdx.x < 64) dwhh_f[threadIdx.x] = v; else dwhh_r[threadIdx.x - 64] = v;
 }
 
 }  // namespace lstm
