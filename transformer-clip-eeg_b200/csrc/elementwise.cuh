@@ -172,7 +172,9 @@ inline int gelu_drop_bwd(const float* pre, const float* dout, float* dpre, long 
 // affine is channel-major; reading it in place costs 32 sectors per warp load (measured: the LN kernels ran at 1.2-1.9 TB/s).
 // One 164 KB transpose per block and direction makes every parameter access a coalesced float4.
 constexpr int LNCT_GROUPS = 32;      // sample groups of the backward apply pass (affine-gradient partials per group)
-inline size_t ln_ct_scratch_floats(int T, int C) { return (size_t)(2 + 2 * LNCT_GROUPS) * T * C; }
+// (gT, bT, 2 x LNCT_GROUPS affine-gradient partials) + the conv-bias partials of the fused column sum: [groups][CTAs along T*C][C]
+inline size_t ln_ct_bias_part_floats(int T, int C) { return (size_t)(((long)T * C / 8 + 255) / 256) * LNCT_GROUPS * C; }
+inline size_t ln_ct_scratch_floats(int T, int C) { return (size_t)(2 + 2 * LNCT_GROUPS) * T * C + ln_ct_bias_part_floats(T, C); }
 
 __global__ void __launch_bounds__(256) ct_transpose2_kernel(const float* __restrict__ g, const float* __restrict__ b,
                                                            float* __restrict__ gT, float* __restrict__ bT, int C, int T) {
@@ -390,16 +392,34 @@ __global__ void __launch_bounds__(512) ln_ct_bwd_stats_kernel(const float* __res
 }
 
 // grid (T*C/8/256, groups), block 256; thread = (t, c8) position, samples b = group, group + groups, ...
+// BIAS: the conv bias gradient (column sums of dy over samples and time) rides along: every thread sums its dy over its samples, the
+// CTA folds its 2048 / C time rows through shared memory in row order and writes one C-vector per CTA to bpart[group][cta][C]
+// (folded in fixed order by colsum_fold_kernel); needs 2048 % C == 0.
+template <bool BIAS>
 __global__ void __launch_bounds__(256) ln_ct_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y,
                                                              const float* __restrict__ stats, const float* __restrict__ m12,
                                                              const float* __restrict__ gT, const float* __restrict__ bT,
                                                              float* __restrict__ dypad, float* __restrict__ part, int B, int T, int C,
-                                                             int PL, int TP, int act, Drop drop) {
+                                                             int PL, int TP, int act, Drop drop, float* __restrict__ bpart) {
   pdl_sync();
+  __shared__ __align__(16) float sbias[BIAS ? 256 * 8 : 8];
   const long n = (long)T * C;
   const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (i >= n) return;
-  float g[8], be[8], ag[8], ab[8];
+  if (i >= n) {
+    if (BIAS) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sbias[threadIdx.x * 8 + j] = 0.f;
+      __syncthreads();
+      if (threadIdx.x < C) {
+        const int rows = 2048 / C, c8n = C >> 3;
+        float acc = 0.f;
+        for (int r = 0; r < rows; ++r) acc += sbias[(r * c8n + (threadIdx.x >> 3)) * 8 + (threadIdx.x & 7)];
+        bpart[((long)blockIdx.y * gridDim.x + blockIdx.x) * C + threadIdx.x] = acc;
+      }
+    }
+    return;
+  }
+  float g[8], be[8], ag[8], ab[8], ob[8];
   {
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gT + i)), g1 = __ldg(reinterpret_cast<const float4*>(gT + i) + 1);
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bT + i)), b1 = __ldg(reinterpret_cast<const float4*>(bT + i) + 1);
@@ -407,7 +427,7 @@ __global__ void __launch_bounds__(256) ln_ct_bwd_apply_kernel(const float* __res
     be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; }
+  for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; ob[j] = 0.f; }
   for (int b = blockIdx.y; b < B; b += gridDim.y) {
     const float mean = stats[2 * b], rstd = stats[2 * b + 1], m1 = m12[2 * b], m2 = m12[2 * b + 1];
     float vv[8], dd[8];
@@ -421,17 +441,30 @@ __global__ void __launch_bounds__(256) ln_ct_bwd_apply_kernel(const float* __res
       const float dl = dd[j] * act_grad_f(xh * g[j] + be[j], act);
       ag[j] += dl * xh; ab[j] += dl;
       o[j] = rstd * (dl * g[j] - m1 - xh * m2) * mm[j];
+      if (BIAS) ob[j] += o[j];
     }
     st256(dypad + ((long)b * TP + PL) * C + i, o);
   }
   st256(part + (long)(2 * blockIdx.y) * n + i, ag);
   st256(part + (long)(2 * blockIdx.y + 1) * n + i, ab);
+  if (BIAS) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sbias[threadIdx.x * 8 + j] = ob[j];
+    __syncthreads();
+    if (threadIdx.x < C) {       // thread tid of the CTA sits at time row tid / (C/8), channel chunk tid % (C/8)
+      const int rows = 2048 / C, c8n = C >> 3;
+      float acc = 0.f;
+      for (int r = 0; r < rows; ++r) acc += sbias[(r * c8n + (threadIdx.x >> 3)) * 8 + (threadIdx.x & 7)];
+      bpart[((long)blockIdx.y * gridDim.x + blockIdx.x) * C + threadIdx.x] = acc;
+    }
+  }
 }
+__global__ void __launch_bounds__(256) colsum_fold_kernel(const float* __restrict__ part, float* __restrict__ out, int ctas, int N);
 
 // m12: 2*B floats of scratch; lnscr: ln_ct_scratch_floats(T, C) floats
 inline int ln_ct_act_bwd(const float* dout, const float* y, const float* stats, const float* gamma, const float* beta,
                          float* dypad, float* dgamma, float* dbeta, float* m12, float* lnscr, int B, int T, int C, int PL, int taps,
-                         int act, const Drop& drop, cudaStream_t st) {
+                         int act, const Drop& drop, cudaStream_t st, float* dbias = nullptr, bool* dbias_done = nullptr) {
   if ((C & 7) || ((((uintptr_t)dout | (uintptr_t)y | (uintptr_t)dypad | (uintptr_t)lnscr) & 31) != 0)) return EEGCLIP_ERR_UNSUPPORTED;   // 256-bit accesses
   ProfScope prof(PROF_LNCT, st);
   float* gT = lnscr;
@@ -443,11 +476,22 @@ inline int ln_ct_act_bwd(const float* dout, const float* y, const float* stats, 
   const long n8 = (long)T * C / 8;
   const int groups = B < LNCT_GROUPS ? B : LNCT_GROUPS;
   dim3 grid((unsigned)((n8 + 255) / 256), groups);
-  LAUNCH_PDL((ln_ct_bwd_apply_kernel), grid, 256, 0, st, dout, y, stats, m12, gT, bT, dypad, part, B, T, C, PL, T + taps - 1, act, drop);
+  // dbias (+= column sums of dy over samples and time) from the same pass when a CTA's 2048 floats are whole time rows
+  const bool fuse_bias = dbias != nullptr && C <= 256 && (2048 % C) == 0;
+  float* bpart = lnscr + (size_t)(2 + 2 * LNCT_GROUPS) * T * C;
+  if (fuse_bias)
+    LAUNCH_PDL((ln_ct_bwd_apply_kernel<true>), grid, 256, 0, st, dout, y, stats, m12, gT, bT, dypad, part, B, T, C, PL, T + taps - 1, act, drop, bpart);
+  else
+    LAUNCH_PDL((ln_ct_bwd_apply_kernel<false>), grid, 256, 0, st, dout, y, stats, m12, gT, bT, dypad, part, B, T, C, PL, T + taps - 1, act, drop, bpart);
   LAUNCH_CHECK();
   dim3 g2((T + 7) / 8, (C + 31) / 32);
   LAUNCH_PDL((ct_reduce_transpose_kernel), g2, 256, 0, st, part, dgamma, dbeta, groups, C, T);
   LAUNCH_CHECK();
+  if (fuse_bias) {
+    LAUNCH_PDL((colsum_fold_kernel), 1, 256, 0, st, (const float*)bpart, dbias, (int)grid.x * groups, C);
+    LAUNCH_CHECK();
+  }
+  if (dbias_done) *dbias_done = fuse_bias;
   return EEGCLIP_OK;
 }
 

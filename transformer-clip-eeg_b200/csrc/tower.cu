@@ -268,10 +268,12 @@ int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP
   float* lnscr = (float*)tcs;
   tcs = lnscr + align_up(ln_ct_scratch_floats(T, Cout), 64);
   CUDA_TRY(cudaMemsetAsync(dypad, 0, (size_t)B * TP * Cout * sizeof(float), st));
+  bool bias_done = false;   // the conv bias gradient (column sums of dy) comes out of the LayerNorm backward's apply pass when it can
   TRY(ln_ct_act_bwd(dout, y, stats, p.g, p.be, dypad, gr.g, gr.be, wtmp /* 2B floats of per-sample means */, lnscr, B, T, Cout, PLb, taps, act,
-                    drop, st));
-  // bias gradient: column sums of dypad in fixed order (the LayerNorm scratch is free again: stream order)
-  if ((size_t)colsum_det_ctas((long)B * TP) * Cout <= ln_ct_scratch_floats(T, Cout)) TRY(colsum_det(dypad, gr.b, (long)B * TP, Cout, Cout, lnscr, st));
+                    drop, st, gr.b, &bias_done));
+  // otherwise: column sums of dypad in fixed order (the LayerNorm scratch is free again: stream order)
+  if (bias_done) {
+  } else if ((size_t)colsum_det_ctas((long)B * TP) * Cout <= ln_ct_scratch_floats(T, Cout)) TRY(colsum_det(dypad, gr.b, (long)B * TP, Cout, Cout, lnscr, st));
   else TRY(colsum(dypad, gr.b, (long)B * TP, Cout, Cout, st));
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
     TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, Cin, Cout, taps, PLb, du, gr.w, B, T, tcs, st));
