@@ -303,7 +303,7 @@ static HeadScratch head_scratch(int b, int Bg, int D) {
   HeadScratch h;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
-  const size_t part = (size_t)b * ceil_div(Bg, GBN) * sizeof(float2);
+  const size_t part = (size_t)b * 2 * ceil_div(Bg, GBN) * sizeof(float2);   // fp32 path: one per 64 columns; tcgen05 64-wide tiles: two
   h.part1 = take(part); h.part2 = take(part);
   const bool tcok = headtc::head_tc_supported(b, Bg, D);
   // G blocks: fp32 (b, Bg) on the CUDA-core path; packed bf16 hi/lo operand blocks [b/128][Bg/64] (same bytes, rounded up) on tcgen05
@@ -344,7 +344,7 @@ int eegclip_infonce_lse(const float* S_all, const float* E_all, const float* tau
     uint8_t* pE = (uint8_t*)(sc + hs.packE);
     TRY(headtc::epack(S_all, pS, Bg, D, st));
     TRY(headtc::epack(E_all, pE, Bg, D, st));
-    const int nt = 2 * ceil_div(Bg, headtc::NT);           // one (max, sum exp) partial per tile and 128-column half
+    const int nt = 2 * ceil_div(Bg, headtc::logits_ntc(1, b, Bg));   // one (max, sum exp) partial per tile and column half
     headtc::LogitsArgs a{};
     a.Ap = pS; a.Bp = pE; a.a_blk0 = row0 / headtc::RB; a.M = b; a.N = Bg; a.D = D; a.tau = tau;
     a.m_off = row0; a.n_off = 0; a.part = part; a.diag = diag;
@@ -417,10 +417,11 @@ int eegclip_infonce_backward(const float* S_all, const float* E_all, const float
     a.one_sided = one_sided; a.Gp = pGr; a.nkc_g = nkc_g; a.dtau = dtau_partial;
     // d tau without float atomics: per-(CTA, epilogue warp) sums land in the (not yet written) second G buffer and are folded in
     // fixed order before the next launch overwrites it
-    a.dtau_slots = (size_t)headtc::logits_grid(a) * 8 * sizeof(float) <= hs.g2 - hs.g1 ? (float*)pGc : nullptr;
+    const int grid2 = headtc::logits_grid(a, headtc::logits_ntc(2, a.M, a.N));
+    a.dtau_slots = (size_t)grid2 * 8 * sizeof(float) <= hs.g2 - hs.g1 ? (float*)pGc : nullptr;
     const bool need_ds = dS_loc && !one_sided;
     TRY(headtc::logits_launch<2>(math, a, st));   // (one-sided: only d tau comes out of this block, its G is not consumed)
-    if (a.dtau_slots) TRY(headtc::dtau_fold(a.dtau_slots, headtc::logits_grid(a), dtau_partial, st));
+    if (a.dtau_slots) TRY(headtc::dtau_fold(a.dtau_slots, grid2, dtau_partial, st));
     // Gc^T(j = local EEG column, i = any speech row): the (E_loc x S_all) product, packed with rows j and contraction i
     //   -> dE_loc = exp(tau) Gc^T . S_all.
     // One-sided (memory-bank term, clip_model.py:934-937): G(i,j) = (softmax_j L(i,.) - delta) / B, the statistics belong to

@@ -30,6 +30,27 @@ constexpr int NSTAGE = 2;
 constexpr int STAGE = 3 * BLK;                 // A block + 2 B blocks = 96 KB
 constexpr float LOG2E = 1.4426950408889634f;
 
+// Tile width.  NTC = 256: two whole 128-row operand blocks of the column operand per stage (large batches).  NTC = 64: small
+// batches -- at B = 256 the 256-wide form is 2 CTAs on 148 SMs running 480 N=128 MMAs per 64-feature chunk each (the in-step head
+// was 5 launches of ~50 us on two SMs); 64-column tiles are 4 x as many CTAs with a quarter of the MMA work and a 48 KB stage
+// (four stages in flight).  The 64-row sub-block of an operand block is eight 1 KB pieces per plane (one per 8-feature chunk).
+template <int NTC>
+struct Tile {
+  static constexpr bool SUB = NTC < RB;                                  // column operand is a sub-block of one operand block
+  static constexpr int NBLK = SUB ? 1 : NTC / RB;
+  static constexpr uint32_t BPLANE = SUB ? 8u * NTC * 16u : (uint32_t)PLANE;
+  static constexpr uint32_t BBYTES = SUB ? 2u * BPLANE : (uint32_t)(NBLK * BLK);
+  static constexpr uint32_t STAGE_B = (uint32_t)BLK + BBYTES;
+  static constexpr int NSTG = SUB ? 4 : 2;
+  static constexpr int HALF = NTC / 2 < 32 ? 32 : NTC / 2;               // columns per epilogue warp set
+};
+// tiles of the 256-wide form below which the 64-wide form is launched (its CTA count is 4 x that)
+constexpr int SMALL_TILES = 37;
+inline int logits_ntc(int mode, int M, int N) {
+  const int t256 = ((N + NT - 1) / NT) * ((M + RB - 1) / RB);
+  return (mode != 3 && t256 <= SMALL_TILES) ? 64 : NT;
+}
+
 inline size_t epack_bytes(int R, int D) { return (size_t)((R + RB - 1) / RB) * (D / KC) * BLK; }
 
 // grid: (D/64 chunks, row blocks); block 256: lane -> (row = lane & 7, c8 = lane >> 3 (+4 per half)) as in lin_tc stage_chunk
@@ -115,9 +136,13 @@ struct LogitsArgs {
 
 // Persistent: CTA c works on tiles c, c + gridDim.x, ... (n tile fastest, so neighbouring CTAs share the A row block in L2); the
 // accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i overlaps the K loop of tile i + 1.
-template <int MODE, int NTERMS>
+template <int MODE, int NTERMS, int NTC>
 __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
   pdl_sync();
+  using TL = Tile<NTC>;
+  constexpr int NT = NTC;                       // (shadows the namespace constant: tile width of this instantiation)
+  constexpr int NSTAGE = TL::NSTG;
+  constexpr uint32_t STAGE = TL::STAGE_B;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE);
@@ -146,10 +171,29 @@ __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
       uint32_t c = 0;                      // chunk counter across tiles: ring slot and phase
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int tn = tile % ntn, tm = tile / ntn;
-        const int nb_blocks = (a.N - tn * NT > RB) ? 2 : 1;            // valid column blocks of this tile
         const uint32_t one = NTERMS > 1 ? BLK : PLANE;
-        const uint32_t bytes = (uint32_t)(1 + nb_blocks) * one;
         const uint8_t* ab = a.Ap + (size_t)(a.a_blk0 + tm) * nkc * BLK;
+        if (TL::SUB) {
+          // rows [r0, r0 + NT) of operand block tn * NT / 128: per plane eight contiguous NT x 16 byte pieces (one per chunk)
+          const uint8_t* bb0 = a.Bp + (size_t)((tn * NT) / RB) * nkc * BLK + (size_t)((tn * NT) % RB) * 16;
+          constexpr uint32_t piece = (uint32_t)NT * 16u;
+          const uint32_t bytes = one + (NTERMS > 1 ? 16u : 8u) * piece;
+          for (int kc = 0; kc < nkc; ++kc, ++c) {
+            const int s = c % NSTAGE;
+            tc::mbar_wait(&empty[s], ((c / NSTAGE) & 1) ^ 1);
+            tc::mbar_expect_tx(&full[s], bytes);
+            uint8_t* st = smem + s * STAGE;
+            tc::bulk_g2s(st, ab + (size_t)kc * BLK, one, &full[s]);
+            const uint8_t* src = bb0 + (size_t)kc * BLK;
+#pragma unroll
+            for (int pl = 0; pl < (NTERMS > 1 ? 2 : 1); ++pl)
+#pragma unroll
+              for (int c8 = 0; c8 < 8; ++c8)
+                tc::bulk_g2s(st + BLK + pl * TL::BPLANE + c8 * piece, src + pl * PLANE + c8 * (RB * 16), piece, &full[s]);
+          }
+        } else {
+        const int nb_blocks = (a.N - tn * NT > RB) ? 2 : 1;            // valid column blocks of this tile
+        const uint32_t bytes = (uint32_t)(1 + nb_blocks) * one;
         const uint8_t* bb0 = a.Bp + (size_t)(tn * 2) * nkc * BLK;
         for (int kc = 0; kc < nkc; ++kc, ++c) {
           const int s = c % NSTAGE;
@@ -159,16 +203,18 @@ __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
           tc::bulk_g2s(st, ab + (size_t)kc * BLK, one, &full[s]);
           for (int j = 0; j < nb_blocks; ++j) tc::bulk_g2s(st + (1 + j) * BLK, bb0 + ((size_t)j * nkc + kc) * BLK, one, &full[s]);
         }
+        }
       }
     }
   } else if (warp == 5) {
     // ===== MMA issue (whole warp runs the loop, one elected lane issues) =====
     const uint32_t base = tc::smem_u32(smem);
-    const uint32_t idesc = tc::idesc_bf16(128, 128, 0, 0);
+    constexpr int NCOL = TL::SUB ? NT : RB;                  // columns per MMA (one operand block, or the sub-block)
+    const uint32_t idesc = tc::idesc_bf16(128, NCOL, 0, 0);
     uint32_t c = 0, t = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
       const int tn = tile % ntn;
-      const int nb_blocks = (a.N - tn * NT > RB) ? 2 : 1;
+      const int nb_blocks = TL::SUB ? 1 : ((a.N - tn * NT > RB) ? 2 : 1);
       const uint32_t buf = t & 1;
       tc::mbar_wait(&accempty[buf], ((t >> 1) & 1) ^ 1);
       tc::tc_fence_after();
@@ -181,15 +227,16 @@ __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
         if (tc::elect_one()) {
           for (int j = 0; j < nb_blocks; ++j) {
             const uint32_t bs = st + (1 + j) * BLK;
-            const uint64_t b_hi = tc::smem_desc(bs, RB * 16, 128), b_lo = tc::smem_desc(bs + PLANE, RB * 16, 128);
-            const uint32_t d = tmem + buf * 256 + j * 128;
+            const uint64_t b_hi = tc::smem_desc(bs, NCOL * 16, 128), b_lo = tc::smem_desc(bs + TL::BPLANE, NCOL * 16, 128);
+            const uint32_t d = tmem + buf * NT + j * 128;
 #pragma unroll
             for (int ks = 0; ks < KC / 16; ++ks) {
-              const uint64_t dk = (uint64_t)((2 * ks * RB * 16) >> 4);
-              tc::mma_bf16(d, a_hi + dk, b_hi + dk, idesc, (kc | ks) != 0);
+              const uint64_t dk = (uint64_t)((2 * ks * RB * 16) >> 4);         // A: 16 features = two chunks of RB rows
+              const uint64_t dkb = (uint64_t)((2 * ks * NCOL * 16) >> 4);      // B: two chunks of NCOL rows
+              tc::mma_bf16(d, a_hi + dk, b_hi + dkb, idesc, (kc | ks) != 0);
               if (NTERMS > 1) {
-                tc::mma_bf16(d, a_hi + dk, b_lo + dk, idesc, 1);
-                tc::mma_bf16(d, a_lo + dk, b_hi + dk, idesc, 1);
+                tc::mma_bf16(d, a_hi + dk, b_lo + dkb, idesc, 1);
+                tc::mma_bf16(d, a_lo + dk, b_hi + dkb, idesc, 1);
               }
             }
           }
@@ -209,13 +256,13 @@ __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
     const int tn = tile % ntn, tm = tile / ntn;
     const int n0 = tn * NT, m0 = tm * RB;
     const uint32_t buf = t & 1;
-    const uint32_t tacc = tmem + buf * 256 + ((uint32_t)(q * 32) << 16);
+    const uint32_t tacc = tmem + buf * NT + ((uint32_t)(q * 32) << 16);
     const int m = m0 + q * 32 + lane;
     const bool mv = m < a.M;
     tc::mbar_wait(&accfull[buf], (t >> 1) & 1);
     tc::tc_fence_after();
     const int ncols = min(NT, a.N - n0);
-    const int c_lo = chalf * (NT / 2), c_hi = min(ncols, c_lo + NT / 2);   // this warp's columns (empty when c_lo >= ncols)
+    const int c_lo = chalf * TL::HALF, c_hi = min(ncols, c_lo + TL::HALF);   // this warp's columns (empty when c_lo >= ncols)
     const int gm = m + a.m_off;
     if (MODE == 1) {
       const float sc2 = scale * LOG2E;                     // work in base 2
@@ -273,7 +320,7 @@ __global__ void __launch_bounds__(320, 1) logits_tc_kernel(const LogitsArgs a) {
       // whole 64-column contraction chunks are written (zeros beyond the last valid column: the consumer reads full chunks)
       const int ccols = min(NT, ((ncols + KC - 1) / KC) * KC);
       uint8_t* grow = a.Gp + (size_t)tm * a.nkc_g * BLK + (size_t)(q * 32 + lane) * 16;
-      for (int cb = c_lo; cb < min(ccols, c_lo + NT / 2); cb += 32) {
+      for (int cb = c_lo; cb < min(ccols, c_lo + TL::HALF); cb += 32) {
         float v[32];
         tc::tmem_ld32(tacc + cb, v);
 #pragma unroll
@@ -345,8 +392,8 @@ __global__ void __launch_bounds__(32) dtau_fold_kernel(const float* __restrict__
   acc = warp_sum(acc);
   if (threadIdx.x == 0) *dtau = acc;
 }
-inline int logits_grid(const LogitsArgs& a) {
-  const int ntiles = ((a.N + NT - 1) / NT) * ((a.M + RB - 1) / RB);
+inline int logits_grid(const LogitsArgs& a, int ntc = NT) {
+  const int ntiles = ((a.N + ntc - 1) / ntc) * ((a.M + RB - 1) / RB);
   return ntiles < 148 ? ntiles : 148;                     // persistent: one CTA per SM at most
 }
 inline int dtau_fold(const float* slots, int grid, float* dtau, cudaStream_t st) {
@@ -355,24 +402,27 @@ inline int dtau_fold(const float* slots, int grid, float* dtau, cudaStream_t st)
   return EEGCLIP_OK;
 }
 
-template <int MODE, int NTERMS>
+template <int MODE, int NTERMS, int NTC>
 inline int logits_launch_t(const LogitsArgs& a, cudaStream_t st) {
   static bool configured = false;
-  const uint32_t smem = NSTAGE * STAGE + 256;
+  const uint32_t smem = Tile<NTC>::NSTG * Tile<NTC>::STAGE_B + 256;
   if (!configured) {
-    if (cudaFuncSetAttribute(logits_tc_kernel<MODE, NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(logits_tc_kernel<MODE, NTERMS, NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
-  const int grid = logits_grid(a);
+  const int grid = logits_grid(a, NTC);
   ProfScope prof(PROF_GEMM_F32, st);
-  LAUNCH_PDL((logits_tc_kernel<MODE, NTERMS>), grid, 320, smem, st, a);
+  LAUNCH_PDL((logits_tc_kernel<MODE, NTERMS, NTC>), grid, 320, smem, st, a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }
+// the tile width is logits_ntc(MODE, a.M, a.N): callers size the MODE-1 partials (2 per tile) and the d tau slots with it
 template <int MODE>
 inline int logits_launch(int math, const LogitsArgs& a, cudaStream_t st) {
-  return math == EEGCLIP_MATH_BF16 ? logits_launch_t<MODE, 1>(a, st) : logits_launch_t<MODE, 3>(a, st);
+  if (MODE != 3 && logits_ntc(MODE, a.M, a.N) == 64)
+    return math == EEGCLIP_MATH_BF16 ? logits_launch_t<MODE == 3 ? 1 : MODE, 1, 64>(a, st) : logits_launch_t<MODE == 3 ? 1 : MODE, 3, 64>(a, st);
+  return math == EEGCLIP_MATH_BF16 ? logits_launch_t<MODE, 1, NT>(a, st) : logits_launch_t<MODE, 3, NT>(a, st);
 }
 
 }  // namespace headtc
