@@ -17,13 +17,17 @@ def fb():
     E.grad = S.grad = tau.grad = None
     infonce_loss(E, S, tau).backward()
 
-for _ in range(2):
-    fb()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(reps):
-    fb()
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / reps
-print(f"head fwd+bwd B={B} D={D}: {ms:.3f} ms -> {6.0 * B * B * D / ms / 1e9:.1f} TFLOP/s algorithmic")
+from transformer_clip_eeg_b200 import _lib
+for wide in (0, 1):   # eegclip_tune_set(14, 1): always 256-column tiles (the 64-column small-batch form off)
+    _lib.call("eegclip_tune_set", 14, wide)
+    for _ in range(2):
+        fb()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fb()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"head fwd+bwd B={B} D={D} {'256-wide tiles only' if wide else 'default tiles'}: {ms:.3f} ms -> {6.0 * B * B * D / ms / 1e9:.1f} TFLOP/s algorithmic")
+_lib.call("eegclip_tune_set", 14, 0)

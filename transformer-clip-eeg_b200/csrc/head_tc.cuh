@@ -48,7 +48,7 @@ struct Tile {
 constexpr int SMALL_TILES = 37;
 inline int logits_ntc(int mode, int M, int N) {
   const int t256 = ((N + NT - 1) / NT) * ((M + RB - 1) / RB);
-  return (mode != 3 && t256 <= SMALL_TILES) ? 64 : NT;
+  return (mode != 3 && t256 <= SMALL_TILES && g_tune[14] == 0) ? 64 : NT;   // (g_tune[14] = 1: always 256-wide, A/B timing)
 }
 
 inline size_t epack_bytes(int R, int D) { return (size_t)((R + RB - 1) / RB) * (D / KC) * BLK; }
