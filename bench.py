@@ -308,16 +308,32 @@ def run_b200(args):
                 e, s_, ids_ = host[i % NBUF]
                 yield e, [s_], ids_, None
 
-    def run_e2e(steps):
+    def run_e2e(steps, timed_from=None):
         # public API end to end: DevicePrefetcher (pinned H2D on a copy stream, double-buffered) -> train_step -> loss.item()
+        # timed_from = W: ONE continuous run of W + K steps; the K timed steps start once the pipeline is in steady state (the first
+        # batch of a run has nothing to hide its H2D copy under: at K = 10 that fill alone was 0.6 ms per timed step).  Every timed
+        # step still has its own H2D copy (of the next batch, on the copy stream) and its own loss read inside the region.
         reader = tcf.LossReader(dev)
         got = []
-        for eeg, sp, ids in tcf.DevicePrefetcher(_HostBatches(steps), dev):
+        e0 = e1 = None
+        for k, (eeg, sp, ids) in enumerate(tcf.DevicePrefetcher(_HostBatches(steps), dev)):
+            if timed_from is not None and k == timed_from:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
             loss_ce, _, _ = tcf.train_step(model, opt, eeg, sp, ids, group=group)
             got += reader.push(loss_ce)              # device -> host read of every step's loss (pinned, read one step later)
+        if e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
         got += reader.drain()
         assert len(got) == steps and all(v == v for v in got), got
-        return got[-1]
+        if e0 is None:
+            return got[-1]
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / (steps - timed_from)
 
     def timed(fn, steps, whole=False):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -362,8 +378,8 @@ def run_b200(args):
     _lib.call("eegclip_profile_end", ctypes.cast(prof_ms, ctypes.c_void_p), ctypes.cast(prof_n, ctypes.c_void_p), 12)
     os.environ["EEGCLIP_TWO_STREAMS"] = two_streams
     run_e2e(max(args.warmup, 3) + 3)                 # warm-up: also lets the copy stream's allocator pool reach steady state
-    run_e2e(args.steps)
-    ms_e2e = timed(run_e2e, args.steps, whole=True)
+    sync_all()
+    ms_e2e = run_e2e(max(args.warmup, 3) + args.steps, timed_from=max(args.warmup, 3))
 
     pk = peaks()
     extras = None
@@ -414,13 +430,16 @@ def run_b200(args):
                    "numa": f"rank 0 bound to NUMA node {numa_node} of its GPU (every rank binds to its own GPU's node)" if numa_node is not None else "no NUMA binding",
                    "l2": f"per-step inputs ({h2d_bytes / 1e6:.0f} MB) and activations (>2 GB) exceed the 126 MB L2; {NBUF} batches rotate",
                    "speech_tower": "1x1 conv, BasicBlock(k=32) and both bi-LSTMs (input GEMMs + recurrence kernels) on eegclip kernels",
+                   "instrumentation": "the timed region of `value` records CUDA events around the roofline kernel's 22 launches per step "
+                                      "(programmatic dependent launch overlap ends at an event: ~0.2 ms per step); the e2e region carries none",
                    "streams": ("speech tower on a side stream next to the EEG tower, forward and backward (clip_model.run_towers)"
                                if two_streams != "0" else "both towers on one stream (EEGCLIP_TWO_STREAMS=0)")},
         "clocks": clocks,
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4,
                 "pipeline": "DevicePrefetcher: pinned double-buffered H2D on a copy stream overlapping the previous step; every step's loss is "
-                            "copied to pinned host memory and read on the host one step later (LossReader), all inside the timed region"},
+                            "copied to pinned host memory and read on the host one step later (LossReader), all inside the timed region; "
+                            "the K timed steps are the last K of one continuous run of W + K steps (pipeline in steady state)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "conv64_tc_kernel (Conv1d k=64 forward + data-gradient launches)",
                      "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
