@@ -19,6 +19,9 @@ dev = torch.device("cuda")
 model = t.build_model(t.build_parser().parse_args([]), T, 10000, dev).train()
 opt = AdamW(model.parameters(), lr=1e-3, weight_decay=0.01)
 batches = [(torch.randn(B, T, 64, device=dev), torch.randn(B, T, 1024, device=dev), torch.arange(1, B + 1, device=dev)) for _ in range(2)]
+for kv in filter(None, os.environ.get("FIX", "").split(",")):     # FIX="15=1,7=0": knobs held fixed during the A/B
+    k_, v_ = kv.split("=")
+    _lib.call("eegclip_tune_set", int(k_), int(v_))
 for rnd in range(3):
     for v in (va, vb):
         _lib.call("eegclip_tune_set", knob, v)

@@ -27,6 +27,7 @@ namespace eegclip {
 // ---- launch accounting + optional per-kernel-class device timing (bench.py roofline; see eegclip_profile_*) ----
 extern long long g_launch_count;
 extern int g_tune[16];
+extern thread_local int g_pdl_break;   // set by pdl_break(): the next LAUNCH_PDL of this thread omits the programmatic-launch attribute
 extern unsigned long long* g_dbg_buf;   // development timeline buffer (eegclip_debug_buffer), nullptr in production   // development knobs (eegclip_tune_set): 0 lin ring depth, 1 streaming-load policy
 enum : int { PROF_CONV_TC = 0, PROF_WGRAD_TC = 1, PROF_ATTN_FWD = 2, PROF_ATTN_BWD = 3, PROF_LNCT = 4, PROF_GEMM_F32 = 5, PROF_LIN_TC = 6, PROF_LIN_WGRAD = 7, PROF_LSTM = 8, PROF_NCLASS = 12 };
 void prof_begin(int cls, cudaStream_t st);
@@ -66,9 +67,13 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_tune[7] ? 0 : 1;
+  cfg.numAttrs = (g_tune[7] || g_pdl_break) ? 0 : 1;
+  g_pdl_break = 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// pdl_break(): the NEXT launch of this thread goes out without the attribute, i.e. in plain stream order -- it is not scheduled
+// before its predecessor has drained (see STREAM_BREAK in tower.cu for where that is faster and by how much)
+inline void pdl_break() { g_pdl_break = 1; }
 #define LAUNCH_PDL(kernel, grid, block, smem, st, ...) (void)::eegclip::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
 
 // dropout site ids; stream = layer * 16 + site  (oracle/philox_ref.py::stream_id)

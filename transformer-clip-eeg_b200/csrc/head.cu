@@ -15,6 +15,7 @@ using namespace eegclip;
 namespace eegclip {
 long long g_launch_count = 0;
 int g_tune[16] = {0};
+thread_local int g_pdl_break = 0;
 unsigned long long* g_dbg_buf = nullptr;
 constexpr int PROF_MAX = 8192;
 static bool g_prof_on = false;

@@ -233,12 +233,22 @@ PadScr pad_scr(float* base, int B, int T, int Cin, int taps) {
   return s;
 }
 
+// Stream breaks.  A 4-byte memset between two launches ends the programmatic-dependent-launch chain at that point: the next kernel
+// is not scheduled before the previous one has drained.  Measured (tools/time_step_ab.py 15 ..., one box, B = 256): at the start of a
+// conv block's backward this is WORTH 0.28 ms per step (15.64 -> 15.33 ms single-stream) -- found when hoisting the per-layer
+// dypad memset out of the loop made the step slower.  g_tune[15]: 0 = the shipped set, k > 0 = the bit mask k - 1 (A/B timing).
+constexpr int DEFAULT_BREAKS = 1 | 4 | 8;   // conv block backward start, before the attention backward, conv block forward start
+inline int stream_breaks() { return g_tune[15] ? g_tune[15] - 1 : DEFAULT_BREAKS; }
+// g_tune[6] = 1: the break is a 4-byte memset (how it was found); default: the next launch simply omits the PDL attribute
+#define STREAM_BREAK(bit, ptr) do { if (stream_breaks() & (bit)) { if (g_tune[6]) CUDA_TRY(cudaMemsetAsync((void*)(ptr), 0, 4, st)); else pdl_break(); } } while (0)
+
 int conv_block_fwd(int math, const float* xin, const float* skip_in, const ConvP& p, const float* skip_out, float* y, float* stats,
                    float* out, float* upad, void* tcs, int B, int T, int Cin, int Cout, int taps, int act, const Drop& drop,
                    cudaStream_t st, float* padscr = nullptr) {
   const int PL = (taps - 1) / 2;
   float* lnscr = (float*)tcs;                      // scratch layout: [LN transposed affine + partials][conv tensor-core scratch]
   tcs = lnscr + align_up(ln_ct_scratch_floats(T, Cout), 64);
+  STREAM_BREAK(8, lnscr);
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
     TRY(conv_tc_forward(math, xin, skip_in, p.w, p.b, y, B, T, Cin, Cout, taps, PL, drop, tcs, st));
   } else if (math != EEGCLIP_MATH_FP32 && padscr && conv_tc_padded_ok(Cin, Cout, taps, T)) {
@@ -263,11 +273,15 @@ int conv_block_fwd(int math, const float* xin, const float* skip_in, const ConvP
 // Produces du (gradient w.r.t. xin + skip_in) and fills the four parameter gradients (pre-zeroed).
 int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP& p, const ConvG& gr, const float* y,
                    const float* stats, const float* dout, float* du, float* upad, float* dypad, float* wtmp, void* tcs, int B, int T,
-                   int Cin, int Cout, int taps, int act, const Drop& drop, cudaStream_t st, float* padscr = nullptr) {
+                   int Cin, int Cout, int taps, int act, const Drop& drop, cudaStream_t st, float* padscr = nullptr,
+                   bool zero_dypad = true) {
   const int PL = (taps - 1) / 2, PLb = taps - 1 - PL, TP = T + taps - 1;
   float* lnscr = (float*)tcs;
   tcs = lnscr + align_up(ln_ct_scratch_floats(T, Cout), 64);
-  CUDA_TRY(cudaMemsetAsync(dypad, 0, (size_t)B * TP * Cout * sizeof(float), st));
+  // only the pad rows need the zeros (the LayerNorm backward writes every valid row); a tower whose conv blocks all share one
+  // geometry zeroes the buffer for its first block only (zero_dypad = false afterwards: nothing ever writes the pad rows)
+  if (zero_dypad) CUDA_TRY(cudaMemsetAsync(dypad, 0, (size_t)B * TP * Cout * sizeof(float), st));
+  else STREAM_BREAK(1, wtmp);
   bool bias_done = false;   // the conv bias gradient (column sums of dy) comes out of the LayerNorm backward's apply pass when it can
   TRY(ln_ct_act_bwd(dout, y, stats, p.g, p.be, dypad, gr.g, gr.be, wtmp /* 2B floats of per-sample means */, lnscr, B, T, Cout, PLb, taps, act,
                     drop, st, gr.b, &bias_done));
@@ -276,7 +290,7 @@ int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP
   } else if ((size_t)colsum_det_ctas((long)B * TP) * Cout <= ln_ct_scratch_floats(T, Cout)) TRY(colsum_det(dypad, gr.b, (long)B * TP, Cout, Cout, lnscr, st));
   else TRY(colsum(dypad, gr.b, (long)B * TP, Cout, Cout, st));
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
-    TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, Cin, Cout, taps, PLb, du, gr.w, B, T, tcs, st));
+    TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, Cin, Cout, taps, PLb, du, gr.w, B, T, tcs, st, stream_breaks()));
   } else if (math != EEGCLIP_MATH_FP32 && padscr && conv_tc_padded_ok(Cin, Cout, taps, T)) {
     PadScr ps = pad_scr(padscr, B, T, Cin, taps);
     const size_t wrow = (size_t)Cin * taps;
@@ -408,6 +422,7 @@ int xf_block_fwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
                     cudaStream_t st) {
   using namespace lintc;
   const long n = (long)d.B * d.T;
+  STREAM_BREAK(16, s.h1);
   TRY(xf_pack(p, s.wp, st));
   TRY(ln64_fwd(zin, p.ln1g, p.ln1b, s.h1, n, st));
   {
@@ -415,8 +430,10 @@ int xf_block_fwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
     a.bias = (const float*)(s.wp + XfPacked::BQKV);
     TRY(lin_tc_launch(d.math, a, st));
   }
+  STREAM_BREAK(32, s.o);
   if (attention_tc_supported(d.T)) TRY(attention_fwd_tc(s.qkv, s.o, s.lse, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
   else TRY(attention_fwd(s.qkv, s.o, s.lse, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
+  STREAM_BREAK(256, s.z1);
   {
     LinTcArgs a = lin_args(s.o, C, s.wp + XfPacked::WO_F, s.z1, C, n, C, C);
     a.bias = p.bo; a.drop = make_drop(d.seed, layer, SITE_PROJ, d.p_proj, d.train); a.drop_on = a.drop.enabled; a.residual = zin;
@@ -446,6 +463,7 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
   const Drop d_hid = make_drop(d.seed, layer, SITE_FFN_HID, d.p_ffn_hid, d.train);
   const Drop d_proj = make_drop(d.seed, layer, SITE_PROJ, d.p_proj, d.train);
   WgradReduceBatch red; red.n = 0;          // the four partial reductions of this block run as ONE launch at the end
+  STREAM_BREAK(2, w.wgp);
   // ---- FFN branch: dg = dzout * mask_out (never materialised: prologue of both consumers) ----
   {
     LinWgradArgs a{};
@@ -497,8 +515,10 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
     a.pro = d_proj.enabled ? PRO_DROP : PRO_NONE; a.pro_drop = d_proj;
     TRY(lin_tc_launch(d.math, a, st));
   }
+  STREAM_BREAK(4, w.dqkv);
   if (attention_tc_supported(d.T)) TRY(attention_bwd_tc(s.qkv, s.o, w.d_o, s.lse, w.dqkv, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
   else TRY(attention_bwd(s.qkv, s.o, w.d_o, s.lse, w.dqkv, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
+  STREAM_BREAK(512, w.wgp + 3 * w.wgp_stride);
   {
     LinWgradArgs a{};
     a.dy = w.dqkv; a.lddy = AQKV; a.Nout = AQKV; a.x = s.h1; a.ldx = C; a.Kin = C; a.M = (int)n;
@@ -625,7 +645,8 @@ int eegclip_tower_backward(const eegclip_tower_desc* dp, const float* const* par
       TRY(xf_block_bwd(d, i, xf_at<XfP>(params, d.n_conv, i), xf_at<XfG>(grads, d.n_conv, i), cb + L.c_out, xs, dz, dz2, w, st));
       const float* xin = (i == 0) ? eegx : xf_save(save, L, i - 1).zout;
       TRY(conv_block_bwd(d.math, xin, eegx, conv_at<ConvP>(params, i), conv_at<ConvG>(grads, i), cb + L.c_y, cb + L.c_stats, dz2, dz,
-                         w.upad, w.dypad, w.wtmp, w.tc, d.B, d.T, C, C, d.taps, 0, make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st));
+                         w.upad, w.dypad, w.wtmp, w.tc, d.B, d.T, C, C, d.taps, 0, make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st,
+                         nullptr, last));
       // skip gradients into eeg_x: the transformer input (dz2, not on the last layer, clip_model.py:463-466) and the conv input (dz);
       // dz2 is still intact here (conv_block_bwd only reads it), so both are added in one pass.  (fp32 sum order: deeg + (dz2 + dz))
       if (!last) TRY(add3_f32(w.deeg, dz2, dz, w.deeg, n * C, st));
@@ -646,7 +667,7 @@ int eegclip_tower_backward(const eegclip_tower_desc* dp, const float* const* par
       const float* xin = (i == 0) ? eegx : save + L.conv0 + L.conv_stride * (i - 1) + L.c_out;
       TRY(conv_block_bwd(d.math, xin, last ? nullptr : eegx, conv_at<ConvP>(params, i), conv_at<ConvG>(grads, i), cb + L.c_y,
                          cb + L.c_stats, dz, dz2, w.upad, w.dypad, w.wtmp, w.tc, d.B, d.T, C, C, d.taps, 0,
-                         make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st));
+                         make_drop(d.seed, i, SITE_CONV, d.p_conv, d.train), st, nullptr, last));
       if (!last) TRY(add_f32(w.deeg, dz2, w.deeg, n * C, st));
       float* t = dz; dz = dz2; dz2 = t;
     }
