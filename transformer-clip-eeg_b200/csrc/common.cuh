@@ -69,6 +69,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.attrs = attr;
   cfg.numAttrs = (g_tune[7] || g_pdl_break) ? 0 : 1;
   g_pdl_break = 0;
+
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 // pdl_break(): the NEXT launch of this thread goes out without the attribute, i.e. in plain stream order -- it is not scheduled

@@ -560,7 +560,7 @@ inline int wgrad_tc_launch(const convtc::WgradTcArgs& a, cudaStream_t st) {
 
 // du = dgrad(dypad, w) ; dw = wgrad(dypad, xin + skip_in)
 inline int conv_tc_backward(int math, const float* xin, const float* skip_in, const float* w, const float* dypad, int Cin, int Cout,
-                            int taps, int PLb, float* du, float* dw, int B, int T, void* scratch, cudaStream_t st, int conv_breaks = 0) {
+                            int taps, int PLb, float* du, float* dw, int B, int T, void* scratch, cudaStream_t st) {
   uint8_t* wp = (uint8_t*)scratch;
   const size_t blocks = (size_t)(Cin / 64) * (Cout / 64);
   float* partial = (float*)(wp + align_up(blocks * taps * convtc::W_TAP_BYTES, 256));
@@ -570,10 +570,8 @@ inline int conv_tc_backward(int math, const float* xin, const float* skip_in, co
   a.src = dypad; a.skip = nullptr; a.wpacked = wp; a.bias = nullptr; a.out = du; a.src_ld = Cout; a.out_ld = Cin;
   a.T = T; a.src_rows = TP; a.row_off = 0; a.taps = taps; a.dbg = g_dbg_buf;
   a.drop = make_drop(0, 0, 0, 0.f, 0);
-  if (conv_breaks & 64) cudaMemsetAsync(du, 0, 4, st);
   int rc = math == EEGCLIP_MATH_BF16 ? conv_tc_launch<1>(a, B, st) : conv_tc_launch<3>(a, B, st);
   if (rc != EEGCLIP_OK) return rc;
-  if (conv_breaks & 128) cudaMemsetAsync(partial, 0, 4, st);
   convtc::WgradTcArgs g;
   g.xin = xin; g.skip = skip_in; g.dypad = dypad; g.partial = partial; g.B = B; g.T = T; g.PL = taps - 1 - PLb; g.PLb = PLb; g.taps = taps;
   g.Cin = Cin; g.Cout = Cout;

@@ -413,6 +413,7 @@ inline int logits_launch_t(const LogitsArgs& a, cudaStream_t st) {
   }
   const int grid = logits_grid(a, NTC);
   ProfScope prof(PROF_GEMM_F32, st);
+  if (g_tune[5] == 0) pdl_break();   // plain stream order into the similarity kernels (measured -0.04 ms per step; see STREAM_BREAK, tower.cu)
   LAUNCH_PDL((logits_tc_kernel<MODE, NTERMS, NTC>), grid, 320, smem, st, a);
   LAUNCH_CHECK();
   return EEGCLIP_OK;

@@ -233,14 +233,21 @@ PadScr pad_scr(float* base, int B, int T, int Cin, int taps) {
   return s;
 }
 
-// Stream breaks.  A 4-byte memset between two launches ends the programmatic-dependent-launch chain at that point: the next kernel
-// is not scheduled before the previous one has drained.  Measured (tools/time_step_ab.py 15 ..., one box, B = 256): at the start of a
-// conv block's backward this is WORTH 0.28 ms per step (15.64 -> 15.33 ms single-stream) -- found when hoisting the per-layer
-// dypad memset out of the loop made the step slower.  g_tune[15]: 0 = the shipped set, k > 0 = the bit mask k - 1 (A/B timing).
-constexpr int DEFAULT_BREAKS = 1 | 4 | 8;   // conv block backward start, before the attention backward, conv block forward start
+// Stream breaks.  pdl_break() makes the next launch go out in plain stream order (no programmatic dependent launch on that edge):
+// the kernel is not scheduled before its predecessor has drained.  On three edges per layer that is FASTER than the overlapped
+// launch -- found when hoisting the per-layer dypad memset out of the loop made the step slower (the memset had been acting as such a
+// break), then mapped edge by edge (tools/time_step_ab.py 15 <mask + 1> ..., one box, B = 256, T = 320, two streams):
+//   bit 1  start of a conv block's backward (ct_transpose2 / LayerNorm statistics after the transformer block's reductions)  -0.28 ms
+//   bit 4  before the attention backward (after the out-projection data gradient)                                            -0.30 ms
+//   bit 8  start of a conv block's forward (weight pack / conv after the FFN2 GEMM)                                          -0.10 ms
+// together 15.02 -> 14.41 ms per step.  Every other launch edge of the transformer / conv blocks (18 positions: block starts, before
+// and after the attention kernels, before each token GEMM / weight gradient / reduction, before the conv data / weight gradient, before
+// the LayerNorm forward, before the skip sums) measured neutral or slower (+0.02 ... +0.07 ms), as did dropping the attribute on every
+// large <-> small shared-memory transition; programmatic launch off everywhere (g_tune[7]) is 0.2 ms slower on one stream.
+// g_tune[15]: 0 = the shipped set, k > 0 = the bit mask k - 1.  g_tune[6] = 1: the break is a 4-byte memset instead (same timing).
+constexpr int DEFAULT_BREAKS = 1 | 4 | 8;
 inline int stream_breaks() { return g_tune[15] ? g_tune[15] - 1 : DEFAULT_BREAKS; }
-// g_tune[6] = 1: the break is a 4-byte memset (how it was found); default: the next launch simply omits the PDL attribute
-#define STREAM_BREAK(bit, ptr) do { if (stream_breaks() & (bit)) { if (g_tune[6]) CUDA_TRY(cudaMemsetAsync((void*)(ptr), 0, 4, st)); else pdl_break(); } } while (0)
+#define STREAM_BREAK(bit, ptr) do { if (stream_breaks() & (bit)) { if (g_tune[6] && (void*)(ptr) != nullptr) CUDA_TRY(cudaMemsetAsync((void*)(ptr), 0, 4, st)); else pdl_break(); } } while (0)
 
 int conv_block_fwd(int math, const float* xin, const float* skip_in, const ConvP& p, const float* skip_out, float* y, float* stats,
                    float* out, float* upad, void* tcs, int B, int T, int Cin, int Cout, int taps, int act, const Drop& drop,
@@ -290,7 +297,7 @@ int conv_block_bwd(int math, const float* xin, const float* skip_in, const ConvP
   } else if ((size_t)colsum_det_ctas((long)B * TP) * Cout <= ln_ct_scratch_floats(T, Cout)) TRY(colsum_det(dypad, gr.b, (long)B * TP, Cout, Cout, lnscr, st));
   else TRY(colsum(dypad, gr.b, (long)B * TP, Cout, Cout, st));
   if (math != EEGCLIP_MATH_FP32 && conv_tc_supported(Cin, Cout, taps, T)) {
-    TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, Cin, Cout, taps, PLb, du, gr.w, B, T, tcs, st, stream_breaks()));
+    TRY(conv_tc_backward(math, xin, skip_in, p.w, dypad, Cin, Cout, taps, PLb, du, gr.w, B, T, tcs, st));
   } else if (math != EEGCLIP_MATH_FP32 && padscr && conv_tc_padded_ok(Cin, Cout, taps, T)) {
     PadScr ps = pad_scr(padscr, B, T, Cin, taps);
     const size_t wrow = (size_t)Cin * taps;
@@ -422,7 +429,6 @@ int xf_block_fwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
                     cudaStream_t st) {
   using namespace lintc;
   const long n = (long)d.B * d.T;
-  STREAM_BREAK(16, s.h1);
   TRY(xf_pack(p, s.wp, st));
   TRY(ln64_fwd(zin, p.ln1g, p.ln1b, s.h1, n, st));
   {
@@ -430,10 +436,8 @@ int xf_block_fwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
     a.bias = (const float*)(s.wp + XfPacked::BQKV);
     TRY(lin_tc_launch(d.math, a, st));
   }
-  STREAM_BREAK(32, s.o);
   if (attention_tc_supported(d.T)) TRY(attention_fwd_tc(s.qkv, s.o, s.lse, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
   else TRY(attention_fwd(s.qkv, s.o, s.lse, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
-  STREAM_BREAK(256, s.z1);
   {
     LinTcArgs a = lin_args(s.o, C, s.wp + XfPacked::WO_F, s.z1, C, n, C, C);
     a.bias = p.bo; a.drop = make_drop(d.seed, layer, SITE_PROJ, d.p_proj, d.train); a.drop_on = a.drop.enabled; a.residual = zin;
@@ -463,7 +467,6 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
   const Drop d_hid = make_drop(d.seed, layer, SITE_FFN_HID, d.p_ffn_hid, d.train);
   const Drop d_proj = make_drop(d.seed, layer, SITE_PROJ, d.p_proj, d.train);
   WgradReduceBatch red; red.n = 0;          // the four partial reductions of this block run as ONE launch at the end
-  STREAM_BREAK(2, w.wgp);
   // ---- FFN branch: dg = dzout * mask_out (never materialised: prologue of both consumers) ----
   {
     LinWgradArgs a{};
@@ -518,7 +521,6 @@ int xf_block_bwd_tc(const eegclip_tower_desc& d, int layer, const XfP& p, const 
   STREAM_BREAK(4, w.dqkv);
   if (attention_tc_supported(d.T)) TRY(attention_bwd_tc(s.qkv, s.o, w.d_o, s.lse, w.dqkv, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
   else TRY(attention_bwd(s.qkv, s.o, w.d_o, s.lse, w.dqkv, d.B, d.T, make_drop(d.seed, layer, SITE_ATTN, d.p_attn, d.train), st));
-  STREAM_BREAK(512, w.wgp + 3 * w.wgp_stride);
   {
     LinWgradArgs a{};
     a.dy = w.dqkv; a.lddy = AQKV; a.Nout = AQKV; a.x = s.h1; a.ldx = C; a.Kin = C; a.M = (int)n;
