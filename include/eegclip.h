@@ -103,6 +103,7 @@ EEGCLIP_API long long eegclip_launch_count(void);
  *  10 ln64 backward rows per CTA           11 column-sum rows per CTA               12 1 = strided weight-gradient operands by
  *      per-row bulk copies instead of 2-D tensor maps (A/B timing)             13 1 = token-GEMM producers load 2 x 128 bit
  *      instead of 1 x 256 bit per lane (A/B timing)
+ *   2 bit 0 / 1: lin_tc_kernel / lin_wgrad_tma_kernel issue griddepcontrol.launch_dependents after their last MMA (A/B timing)
  *   5 1 = programmatic launch also into the head's similarity kernels      6 1 = stream breaks as 4-byte memsets (as first found)
  *  14 1 = similarity kernel always with 256-column tiles (the 64-column small-batch form off)
  *  15 k > 0 = bit mask k - 1 of the launch edges that go out in plain stream order instead of programmatic dependent launch

@@ -278,6 +278,7 @@ struct LinTcArgs {
   int nstage;                     // ring depth (2..NSTAGE)
   int policy;                     // load policy of the streamed activations (0: L1 no-allocate, 1: __ldg)
   int vec8;                       // A (and the LayerNorm-backward side streams) are 32-byte aligned: 256-bit loads
+  int late_trigger;               // g_tune[2]: griddepcontrol.launch_dependents after the last MMA instead of first thing (A/B timing)
   unsigned long long* dbg;        // development timeline buffer (nullptr in production)
 };
 
@@ -287,7 +288,7 @@ inline uint32_t lin_smem_bytes(int N, int K, int nstage = NSTAGE, int nepi = 8) 
 
 template <int NTERMS, int PRO, int EF, int NEPI>
 __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) {
-  pdl_trigger();
+  if (!a.late_trigger) pdl_trigger();
   constexpr int NPROD = NWARPS - 1 - NEPI;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -435,6 +436,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lin_tc_kernel(const LinTcArgs a) 
       if (tc::elect_one()) tc::tc_commit(&accfull[buf]);
       __syncwarp();
     }
+    if (a.late_trigger) pdl_trigger();    // experiment: dependents may launch once every CTA has issued its last MMA
   } else {
     // ===== epilogue: warp w reads TMEM lane quarter w%4, columns [ (w/4)*N/2, (w/4+1)*N/2 ) =====
     if constexpr (LNB) {
@@ -708,6 +710,7 @@ inline int lin_tc_launch_t(LinTcArgs a, cudaStream_t st) {
   a.policy = g_tune[1];
   a.dbg = g_dbg_buf;
   // 256-bit loads need 32-byte aligned rows (g_tune[13] = 1 forces the 2 x 128-bit form for A/B timing)
+  a.late_trigger = g_tune[2] & 1;
   a.vec8 = (g_tune[13] == 0 && ((uintptr_t)a.A & 31) == 0 && (a.lda & 7) == 0 &&
             (!a.lnb_x || ((((uintptr_t)a.lnb_x | (uintptr_t)a.residual) & 31) == 0 && (a.ldc & 7) == 0))) ? 1 : 0;
   const uint32_t smem = 0;
@@ -760,6 +763,7 @@ struct LinWgradArgs {
   int pro_x; Drop drop_x;                 // prologue on x  (element index m*Kin + k)
   float* partial;                         // [kin blocks][ctas][Nout*Kin + Nout]
   int want_db;
+  int late_trigger;                       // (g_tune[2] & 2) griddepcontrol.launch_dependents after the last MMA (A/B timing)
   int policy;                             // load policy of the streamed activations (0: L1 no-allocate, 1: __ldg)
   unsigned long long* dbg;                // development timeline buffer (nullptr in production)
 };
@@ -1005,7 +1009,7 @@ inline uint32_t wgrad2_smem_bytes(int Nout, int Kin) {
 template <int NTERMS, int PDY, int PX, int WDB>
 __global__ void __launch_bounds__(W2_THREADS, 1) lin_wgrad_tma_kernel(const LinWgradArgs a, const __grid_constant__ CUtensorMap tm_dy,
                                                                       const __grid_constant__ CUtensorMap tm_x, const int use_tm) {
-  pdl_trigger();
+  if (!a.late_trigger) pdl_trigger();
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Nout = a.Nout, Kin = a.Kin;
@@ -1114,6 +1118,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) lin_wgrad_tma_kernel(const LinW
       __syncwarp();
       dbg_mark(dbgm, 1, dnm, 13);
     }
+    if (a.late_trigger) pdl_trigger();    // experiment (g_tune[2] & 2): dependents may launch once every CTA has issued its last MMA
   } else {
     // ===== producers =====
     unsigned long long* dbgp = (blockIdx.x == 0 && blockIdx.y == 0 && warp == 3 && lane == 0) ? a.dbg : nullptr;
@@ -1340,7 +1345,9 @@ inline int lin_wgrad_tma_launch_v(const LinWgradArgs& a, dim3 grid, cudaStream_t
       return EEGCLIP_ERR_CUDA;
     configured = true;
   }
-  LAUNCH_PDL((lin_wgrad_tma_kernel<NTERMS, PDY, PX, WDB>), grid, W2_THREADS, wgrad2_smem_bytes(a.Nout, a.Kin), st, a, tm_dy, tm_x, use_tm);
+  LinWgradArgs al = a;
+  al.late_trigger = (g_tune[2] >> 1) & 1;
+  LAUNCH_PDL((lin_wgrad_tma_kernel<NTERMS, PDY, PX, WDB>), grid, W2_THREADS, wgrad2_smem_bytes(a.Nout, a.Kin), st, al, tm_dy, tm_x, use_tm);
   LAUNCH_CHECK();
   return EEGCLIP_OK;
 }

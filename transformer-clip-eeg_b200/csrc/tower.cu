@@ -244,6 +244,9 @@ PadScr pad_scr(float* base, int B, int T, int Cin, int taps) {
 // and after the attention kernels, before each token GEMM / weight gradient / reduction, before the conv data / weight gradient, before
 // the LayerNorm forward, before the skip sums) measured neutral or slower (+0.02 ... +0.07 ms), as did dropping the attribute on every
 // large <-> small shared-memory transition; programmatic launch off everywhere (g_tune[7]) is 0.2 ms slower on one stream.
+// A hint at the mechanism: with NO breaks, issuing griddepcontrol.launch_dependents in lin_tc_kernel after its last MMA instead of
+// first thing (g_tune[2] = 1) recovers 0.53 of those 0.6 ms -- the loss comes with the EARLY launch of a token GEMM's dependents; with
+// the breaks in place the early trigger is the faster one again (14.22 vs 14.30 ms), so it stays.
 // g_tune[15]: 0 = the shipped set, k > 0 = the bit mask k - 1.  g_tune[6] = 1: the break is a 4-byte memset instead (same timing).
 constexpr int DEFAULT_BREAKS = 1 | 4 | 8;
 inline int stream_breaks() { return g_tune[15] ? g_tune[15] - 1 : DEFAULT_BREAKS; }
