@@ -692,17 +692,26 @@ class _RejoinFn(torch.autograd.Function):
         return g, None, None
 
 
-def run_towers(eegModel, speechModel, eeg, speech):
-    """(eegModel(eeg), speechModel(speech)) with the speech tower on a side stream (see above)."""
+def run_towers(eegModel, speechModel, eeg, speech, speech_first=True):
+    """(eegModel(eeg), speechModel(speech)) with the speech tower on a side stream (see above).  ``speech_first`` is the order in
+    which the two towers are called on the host -- the order of their dropout-seed draws and, reversed, of their backward nodes: the
+    CLI default wrapper calls the speech tower first (data-parallel bucket overlap), the other wrappers the EEG tower, as the
+    reference does."""
     if not (two_streams_enabled() and eeg.is_cuda and speech.is_cuda and eeg.device == speech.device):
-        sf = speechModel(speech)
-        return eegModel(eeg), sf
+        if speech_first:
+            sf = speechModel(speech)
+            return eegModel(eeg), sf
+        ef = eegModel(eeg)
+        return ef, speechModel(speech)
     main, side = torch.cuda.current_stream(eeg.device), _side_stream(eeg.device)
-    side.wait_stream(main)
+    side.wait_stream(main)                      # (before the EEG tower is enqueued: the side stream must not wait for it)
+    if not speech_first:
+        ef = eegModel(eeg)
     with torch.cuda.stream(side):
         sf = speechModel(speech)
     speech.record_stream(side)
-    ef = eegModel(eeg)
+    if speech_first:
+        ef = eegModel(eeg)
     main.wait_stream(side)
     sf.record_stream(main)
     if sf.requires_grad:
@@ -861,8 +870,9 @@ class CLIPSim(nn.Module):
 
     def forward(self, eeg, speech, ids):
         _single_rank_only(self)
-        E = _proj(self.latent_projection_eeg, _flat(self.eegModel(eeg)))
-        S = _proj(self.latent_projection_speech, _flat(self.speechModel(speech)))
+        ef, sf = run_towers(self.eegModel, self.speechModel, eeg, speech, speech_first=False)
+        E = _proj(self.latent_projection_eeg, _flat(ef))
+        S = _proj(self.latent_projection_speech, _flat(sf))
         loss_ce, En = infonce_loss(E, S, self.temperature, group=self.shard_group, return_normalized=True)
         avg = l2_normalize(self.eegMemoryBank(ids, En))
         avg_loss = ((avg - l2_normalize(E)) ** 2).mean()          # the gradient reaches the EEG tower through the normalisation
@@ -878,7 +888,7 @@ class CLIPNoContrastiveLearning(nn.Module):
         self.eegModel, self.speechModel, self.window_length = eegModel, speechModel, window_length
 
     def forward(self, eeg, speech, ids):
-        ef, sf = self.eegModel(eeg), self.speechModel(speech)
+        ef, sf = run_towers(self.eegModel, self.speechModel, eeg, speech, speech_first=False)
         if sf.shape[1] > sf.shape[2]:
             sf = sf.transpose(1, 2)
         if ef.shape[1] > ef.shape[2]:
@@ -916,7 +926,8 @@ class CLIPSimMultiplePositives(nn.Module):
         self.temperature_eeg = nn.Parameter(torch.tensor(temperature))
 
     def _logits(self, eeg, speech):
-        En, Sn = l2_normalize(_flat(self.eegModel(eeg))), l2_normalize(_flat(self.speechModel(speech)))
+        ef, sf = run_towers(self.eegModel, self.speechModel, eeg, speech, speech_first=False)
+        En, Sn = l2_normalize(_flat(ef)), l2_normalize(_flat(sf))
         return _similarity(Sn, En, self.temperature)
 
     def forward(self, eeg, speech, ids):
@@ -990,7 +1001,8 @@ class CLIPKLDNoLatentProj(_KLDBase):
         self.shard_group = None
 
     def encode(self, eeg, speech, ids):
-        E, S = _flat(self.eegModel(eeg)), _flat(self.speechModel(speech))
+        ef, sf = run_towers(self.eegModel, self.speechModel, eeg, speech, speech_first=False)
+        E, S = _flat(ef), _flat(sf)
         mu2 = self.mu_eeg_lookup(ids)
         z_mu, z_logvar = _proj(self.eeg_mu_linear, E), _proj(self.eeg_logvar_linear, E)
         return mu2, z_mu, z_logvar, self.reparameterize(z_mu, z_logvar), S, E
@@ -1038,7 +1050,8 @@ class CLIPKLDWithLatentProj(_KLDBase):
         self.shard_group = None
 
     def encode(self, eeg, speech, ids):
-        E, S = _flat(self.eegModel(eeg)), _flat(self.speechModel(speech))
+        ef, sf = run_towers(self.eegModel, self.speechModel, eeg, speech, speech_first=False)
+        E, S = _flat(ef), _flat(sf)
         z_logvar, z_mu, Sp = self.eeg_logvar_linear(E), self.eeg_mu_linear(E), self.speech_latent_projection(S)
         return self.mu_eeg_lookup(ids), z_mu, z_logvar, self.reparameterize(z_mu, z_logvar), Sp, z_mu
 
